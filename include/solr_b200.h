@@ -1,0 +1,89 @@
+/* solr_b200.h — C ABI of the B200-native engine for Sol-R's ray-propagation hot path.
+ *
+ * The ten seam functions below are what the reference's engine host class binds
+ * (/root/reference/solr/engines/cuda/CudaRayTracer.h:25-67, called from CudaKernel.cpp:116-145,174-302,
+ * 304-313): same argument order, same by-value structs (include/solr_b200_types.h has the wire format),
+ * same call protocol (init -> (h2d* -> render -> d2h)* -> finalize).  Names carry a b200_ prefix so the
+ * library can sit in one process next to the reference's own engine.  All functions return void like the
+ * reference's; failures are logged to stderr and latched — query with b200_last_error().  Unlike the
+ * reference (CudaRayTracer.cu:1530) finalize does NOT cudaDeviceReset(): the process may share the device
+ * with NCCL / PyTorch.
+ *
+ * One process drives one GPU (occupancyParameters.x must be 1; .y is ignored — persistent CTAs replace the
+ * reference's stream split).  Multi-GPU = one process per GPU, the frame split by b200_set_partition().
+ */
+#ifndef SOLR_B200_H
+#define SOLR_B200_H
+
+#include "solr_b200_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- the seam (1:1 with CudaRayTracer.h) ------------------------------------------------------------ */
+
+/* CudaRayTracer.h:25 / CudaRayTracer.cu:1408-1491.  Creates the stream and scene-independent state. */
+void b200_initialize_scene(b200_int2 occupancyParameters, b200_SceneInfo sceneInfo, int nbPrimitives, int nbLamps,
+                           int nbMaterials);
+/* CudaRayTracer.h:33 / .cu:1499-1532.  Frees every device buffer; no device reset. */
+void b200_finalize_scene(b200_int2 occupancyParameters);
+/* CudaRayTracer.h:40 / .cu:1360-1400.  (Re)allocates the per-pixel buffers for the frame-size limits
+ * (b200_set_limits; default = the reference's 1920x1080) and zeroes them. */
+void b200_reshape_scene(b200_int2 occupancyParameters, b200_SceneInfo sceneInfo);
+/* CudaRayTracer.h:42 / .cu:1540-1555.  Takes the flattened AoS arrays produced by compactBoxes and
+ * re-lays them out for the device (DESIGN.md "Data layout"). */
+void b200_h2d_scene(b200_int2 occupancyParameters, const b200_BoundingBox* boundingBoxes, int nbActiveBoxes,
+                    const b200_Primitive* primitives, int nbPrimitives, const int* lamps, int nbLamps);
+/* CudaRayTracer.h:45 / .cu:1557-1565 */
+void b200_h2d_materials(b200_int2 occupancyParameters, const b200_Material* materials, int nbActiveMaterials);
+/* CudaRayTracer.h:47 / .cu:1567-1576.  Copies exactly maxWidth*maxHeight floats (the limits). */
+void b200_h2d_randoms(b200_int2 occupancyParameters, const float* randoms);
+/* CudaRayTracer.h:49 / .cu:1578-1613 */
+void b200_h2d_textures(b200_int2 occupancyParameters, int activeTextures, const b200_TextureInfo* textureInfos);
+/* CudaRayTracer.h:51 / .cu:1615-1625 */
+void b200_h2d_lightInformation(b200_int2 occupancyParameters, const b200_LightInformation* lightInformation,
+                               int lightInformationSize);
+/* CudaRayTracer.h:54 / .cu:1647-1672.  Synchronises the render stream, then copies RGB8 (W*H*3) and ids
+ * (W*H int4) to the caller's host buffers. Returns when the copies are complete. */
+void b200_d2h_bitmap(b200_int2 occupancyParameters, b200_SceneInfo sceneInfo, b200_BitmapBuffer* bitmap,
+                     b200_PrimitiveXYIdBuffer* primitivesXYIds);
+/* CudaRayTracer.h:57 (cudaRender) / .cu:1680-1908.  objects = {boxes, primitives, lamps, lightInformation}.
+ * blockSize is accepted for signature parity and ignored (persistent CTAs). Asynchronous on the stream. */
+void b200_render(b200_int2 occupancyParameters, b200_int4 blockSize, b200_SceneInfo sceneInfo, b200_int4 objects,
+                 b200_PostProcessingInfo postProcessingInfo, b200_float3 origin, b200_float3 direction,
+                 b200_float4 angles);
+
+/* ---- extensions (not in the reference seam) ------------------------------------------------------------ */
+
+/* 0 = ok; otherwise the first latched error (cudaError_t value or negative engine code); msg may be NULL. */
+int b200_last_error(char* msg, int msgCapacity);
+void b200_clear_error(void);
+/* CUDA device ordinal for this process (default: current device). Call before initialize_scene. */
+void b200_set_device(int device);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*), e.g. PyTorch's current stream; NULL = own stream. */
+void b200_set_stream(void* cudaStream);
+/* Frame-size limits (the reference hard-codes 1920x1080, Consts.h:39-41; 4K configs need more). Also the
+ * length of the random table and the modulus of its index wraps. Call before reshape_scene. */
+void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
+/* Multi-GPU frame split: this process renders tiles t with t % worldSize == rank (interleaved 8x4-pixel
+ * tiles). Non-owned pixels of the device bitmap/ids stay zero so frames merge by summation. */
+void b200_set_partition(int rank, int worldSize);
+/* Device pointers of the per-pixel buffers for in-place collectives (NCCL) — valid until reshape/finalize. */
+void b200_device_buffers(void** bitmap, void** primitivesXYIds, void** postProcessingBuffer);
+/* Work done by b200_render calls since the last reset: rays = box-list walks (closest-hit + shadow),
+ * pixels = pixels actually traced.  Synchronises the stream. */
+void b200_get_counters(unsigned long long* rays, unsigned long long* pixels, int reset);
+/* Device time of the last b200_render's kernels in ms (CUDA events on the render stream); synchronises. */
+float b200_last_render_ms(void);
+/* Number of kernels this library launched since initialize_scene. */
+unsigned long long b200_kernel_launches(void);
+/* Compacted scene statistics of the last h2d_scene: boxes kept after single-child chain collapse etc. */
+void b200_scene_stats(int* nbBoxesIn, int* nbBoxesDevice, int* nbPrimitives, int* reserved);
+/* Block until everything queued on the render stream is done. */
+void b200_synchronize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOLR_B200_H */

@@ -1,0 +1,688 @@
+// engine.cu — the C ABI of include/solr_b200.h: device-buffer ownership, scene re-layout at upload, the
+// persistent render kernel and the readback.  One process drives one GPU.
+//
+// Replaces, behind the same seam, /root/reference/solr/engines/cuda/CudaRayTracer.cu:1360-1908
+// (reshape/initialize/finalize_scene, h2d_*, d2h_bitmap, cudaRender) and the kernels it launches
+// (k_standardRenderer :437-563, k_anaglyphRenderer :840-926, k_default :1057-1073).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/solr_b200.h"
+#include "shade.cuh"
+
+#define TILE_W 8
+#define TILE_H 4
+#define CTA_THREADS 128
+#define MIN_CTAS_PER_SM 4
+
+// GeometryShaders.cuh:132-165 (makeColor) fused with k_default's averaging (CudaRayTracer.cu:1068-1072)
+SB_DEV void packPixel(float4 color, unsigned char* bitmap, const int index)
+{
+    if (cSI.pathTracingIteration > B200_NB_MAX_ITERATIONS)
+        color /= (float)(cSI.pathTracingIteration - B200_NB_MAX_ITERATIONS + 1);
+    color.x = (color.x > 1.f) ? 1.f : color.x; color.y = (color.y > 1.f) ? 1.f : color.y; color.z = (color.z > 1.f) ? 1.f : color.z;
+    color.x = (color.x < 0.f) ? 0.f : color.x; color.y = (color.y < 0.f) ? 0.f : color.y; color.z = (color.z < 0.f) ? 0.f : color.z;
+    if (cSI.frameBufferType == B200_FT_BGR)
+    {
+        const int y = index / cSI.size.y, x = index % cSI.size.x;
+        const int i = ((y + 1) * cSI.size.y - x - 1) * B200_COLOR_DEPTH;
+        bitmap[i] = (unsigned char)(color.z * 255.f);
+        bitmap[i + 1] = (unsigned char)(color.y * 255.f);
+        bitmap[i + 2] = (unsigned char)(color.x * 255.f);
+    }
+    else
+    {
+        const int i = index * B200_COLOR_DEPTH;
+        bitmap[i] = (unsigned char)(color.x * 255.f);
+        bitmap[i + 1] = (unsigned char)(color.y * 255.f);
+        bitmap[i + 2] = (unsigned char)(color.z * 255.f);
+    }
+}
+
+// One pixel: CudaRayTracer.cu:437-563 (standard / orthographic / antialiased cameras) and :840-926
+// (anaglyph), followed by k_default for that pixel.  The cameras differ only in how many ray trees a
+// pixel owns and how they are combined, so they share one loop around a single launchRayTracing site:
+//   standard/orthographic: 1 sample; antialiased: 4 offset samples + 1; anaglyph: left eye, right eye.
+SB_DEV void renderPixel(const Rotation& rot, const int x, const int y, Counters& cnt, unsigned int& pixelsTraced)
+{
+    const int W = cSI.size.x, H = cSI.size.y;
+    const int index = y * W + x;
+    const int iter = cSI.pathTracingIteration;
+    int4 id = cP.ids[index];
+    // pixels whose ray tree ended before this deepening pass need no work (:454-458)
+    if (iter > id.y && id.w == 0 && iter > 0 && iter <= B200_NB_MAX_ITERATIONS) return;
+    pixelsTraced++;
+    const int camera = cSI.cameraType;
+    const float3 rotationCenter = (camera == B200_CT_VR) ? cP.eye : f3(0.f, 0.f, 0.f);
+    float dof = 0.f;
+    float4 stored = *reinterpret_cast<float4*>(&cP.post[index].colorInfo);
+    const float ratio = (float)W / (float)H;
+    const float stepx = ratio * cP.angles.w / (float)W, stepy = cP.angles.w / (float)H;
+    const bool anaglyph = camera == B200_CT_ANAGLYPH, antialiased = camera == B200_CT_ANTIALIASED;
+
+    float3 o = cP.eye, t = cP.target;
+    if (!anaglyph)
+    {
+        // NATURAL_DEPTHOFFIELD (Consts.h:54; CudaRayTracer.cu:470-479), precedence as written there
+        if (cP.pp.type != B200_PPE_DEPTH_OF_FIELD && iter >= B200_NB_MAX_ITERATIONS)
+        {
+            const float a = (cP.pp.param1 / 20000.f);
+            const int rindex = index + cSI.timestamp % (cS.randomTableSize - 2);
+            const bool in = rindex + 1 < cS.randomTableSize + 4;
+            o.x += (in ? rnd(rindex) : 0.f) * stored.w * a;
+            o.y += (in ? rnd(rindex + 1) : 0.f) * stored.w * a;
+        }
+        if (camera == B200_CT_ORTHOGRAPHIC)
+        {
+            t.x = o.z * 0.001f * (x - (W / 2));
+            t.y = -o.z * 0.001f * (y - (H / 2));
+            o.x = t.x;
+            o.y = t.y;
+        }
+        else
+        {
+            t.x = t.x - stepx * (x - (W / 2));
+            t.y = t.y + stepy * (y - (H / 2));
+        }
+        vectorRotation(o, rotationCenter, rot);
+        vectorRotation(t, rotationCenter, rot);
+        if (!antialiased && iter >= B200_NB_MAX_ITERATIONS)
+        {
+            // rotated-grid jitter of the accumulation passes (:515-522), applied after the rotation
+            const int k = iter % 4;
+            t.x += (k == 0) ? 3.f : (k == 1) ? 5.f : (k == 2) ? -3.f : -5.f;
+            t.y += (k == 0) ? 5.f : (k == 1) ? -3.f : (k == 2) ? -5.f : 3.f;
+        }
+    }
+
+    const int nSamples = anaglyph ? 2 : (antialiased ? 5 : 1);
+    float4 color = f4(0.f, 0.f, 0.f, 0.f);
+    float4 left = f4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int s = 0; s < nSamples; ++s)
+    {
+        if (anaglyph)
+        {
+            // eyes at origin.x -/+ eyeSeparation, both origin and target rotated (:866-901)
+            o = f3(s == 0 ? cP.eye.x - cSI.eyeSeparation : cP.eye.x + cSI.eyeSeparation, cP.eye.y, cP.eye.z);
+            t.x = cP.target.x - stepx * (float)(x - (W / 2));
+            t.y = cP.target.y + stepy * (float)(y - (H / 2));
+            t.z = cP.target.z;
+            vectorRotation(o, rotationCenter, rot);
+            vectorRotation(t, rotationCenter, rot);
+        }
+        else if (antialiased && s < 4)
+        {
+            // the reference offsets the ORIGIN cumulatively (:504-514); the 5th tree uses the sum (= 0,0)
+            o.x += (s == 0) ? 3.f : (s == 1) ? 5.f : (s == 2) ? -3.f : -5.f;
+            o.y += (s == 0) ? 5.f : (s == 1) ? -3.f : (s == 2) ? -5.f : 3.f;
+        }
+        const float4 c = launchRayTracing(index, o, t, dof, id, cnt);
+        if (anaglyph && s == 0) left = c;
+        else color += c;
+    }
+
+    float4 sinfo = *reinterpret_cast<float4*>(&cP.post[index].sceneInfo);
+    if (iter == 0) stored.w = dof;
+    if (anaglyph)
+    {
+        // left eye -> luma in red, right eye -> green/blue (:903-925); sceneInfo is not written
+        const float r1 = left.x * 0.299f + left.y * 0.587f + left.z * 0.114f;
+        const float g2 = color.y, b2 = color.z;
+        if (iter <= B200_NB_MAX_ITERATIONS) { stored.x = r1 + 0.f; stored.y = 0.f + g2; stored.z = 0.f + b2; }
+        else { stored.x += r1 + 0.f; stored.y += 0.f + g2; stored.z += 0.f + b2; }
+    }
+    else
+    {
+        if (cSI.advancedIllumination == B200_AI_RANDOM)
+        {
+            const int rindex = (index + cSI.timestamp) % cS.randomTableSize;
+            color += f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w) * rnd(rindex) * 5.f;
+        }
+        if (antialiased) color /= 5.f;
+        if (iter <= B200_NB_MAX_ITERATIONS)
+        {
+            stored.x = color.x; stored.y = color.y; stored.z = color.z;
+            sinfo.x = color.x; sinfo.y = color.y; sinfo.z = color.z;
+        }
+        else
+        {
+            // accumulation passes (:550-562)
+            sinfo.x = (id.z > 0) ? fmaxf(sinfo.x, color.x) : color.x;
+            sinfo.y = (id.z > 0) ? fmaxf(sinfo.y, color.y) : color.y;
+            sinfo.z = (id.z > 0) ? fmaxf(sinfo.z, color.z) : color.z;
+            stored.x += sinfo.x; stored.y += sinfo.y; stored.z += sinfo.z;
+        }
+        *reinterpret_cast<float4*>(&cP.post[index].sceneInfo) = sinfo;
+    }
+    *reinterpret_cast<float4*>(&cP.post[index].colorInfo) = stored;
+    cP.ids[index] = id;
+    packPixel(stored, cP.bitmap, index);
+}
+
+// Persistent CTAs: every warp pulls 8x4-pixel tiles from one atomic queue until the frame is drained, so
+// a warp stuck on deep bounce chains does not hold back the rest of its CTA or its SM.
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_render()
+{
+    const int lane = threadIdx.x & 31;
+    Counters cnt;
+    cnt.rays = 0;
+    unsigned int pixelsTraced = 0;
+    // VectorUtils.cuh:108-114 evaluates these six per pixel and per rotated vector (fast-math sinf/cosf);
+    // same intrinsics, once per thread.
+    Rotation rot;
+    rot.cx = cosf(cP.angles.x); rot.cy = cosf(cP.angles.y); rot.cz = cosf(cP.angles.z);
+    rot.sx = sinf(cP.angles.x); rot.sy = sinf(cP.angles.y); rot.sz = sinf(cP.angles.z);
+    while (true)
+    {
+        unsigned int k = 0;
+        if (lane == 0) k = atomicAdd(cP.tileCounter, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= (unsigned int)cP.nbLocalTiles) break;
+        const int tile = k * cP.worldSize + cP.rank; // interleaved tile ownership across GPUs
+        const int tx = tile % cP.tilesX, ty = tile / cP.tilesX;
+        const int x = tx * TILE_W + (lane & (TILE_W - 1));
+        const int y = ty * TILE_H + (lane / TILE_W);
+        if (x < cSI.size.x && y < cSI.size.y) renderPixel(rot, x, y, cnt, pixelsTraced);
+        __syncwarp();
+    }
+    // one atomic per warp for the work counters
+    unsigned int rays = cnt.rays, px = pixelsTraced;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        rays += __shfl_xor_sync(0xffffffffu, rays, o);
+        px += __shfl_xor_sync(0xffffffffu, px, o);
+    }
+    if (lane == 0)
+    {
+        atomicAdd(cP.workCounters, (unsigned long long)rays);
+        atomicAdd(cP.workCounters + 1, (unsigned long long)px);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host state
+// ----------------------------------------------------------------------------------------------------
+namespace
+{
+struct Engine
+{
+    bool initialised = false;
+    int device = -1;
+    cudaStream_t ownStream = nullptr;
+    cudaStream_t stream = nullptr; // the stream in use (own or caller's)
+    int maxW = B200_REF_MAX_BITMAP_WIDTH, maxH = B200_REF_MAX_BITMAP_HEIGHT;
+    int rank = 0, world = 1;
+    int numSMs = 0, ctasPerSM = 0;
+    // scene
+    float4* dBoxes = nullptr; int nbBoxes = 0; int nbBoxesIn = 0;
+    float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
+    b200_BoundingBox* dRawBoxes = nullptr;
+    b200_Material* dMats = nullptr; int nbMats = 0;
+    b200_LightInformation* dLights = nullptr; int nbLights = 0;
+    unsigned char* dTex = nullptr; size_t texBytes = 0;
+    float* dRandoms = nullptr;
+    size_t capBoxes = 0, capPrims = 0, capMats = 0;
+    // host copies needed to (re)build the packed per-primitive word when either side changes
+    std::vector<b200_Primitive> hPrims;
+    std::vector<b200_Material> hMats;
+    // frame
+    b200_PostProcessingBuffer* dPost = nullptr; int4* dIds = nullptr; unsigned char* dBitmap = nullptr;
+    unsigned int* dTileCounter = nullptr; unsigned long long* dWork = nullptr;
+    size_t pixelsCap = 0;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    bool timed = false;
+    unsigned long long launches = 0;
+    // pinned registration cache for caller-owned readback buffers
+    void* regBitmap = nullptr; size_t regBitmapBytes = 0;
+    void* regIds = nullptr; size_t regIdsBytes = 0;
+    int err = 0;
+    char errMsg[256] = {0};
+};
+Engine G;
+
+void latch(int code, const char* what, const char* detail)
+{
+    fprintf(stderr, "[solr_b200] ERROR %s: %s (%d)\n", what, detail ? detail : "", code);
+    if (G.err == 0)
+    {
+        G.err = code;
+        snprintf(G.errMsg, sizeof(G.errMsg), "%s: %s", what, detail ? detail : "");
+    }
+}
+#define CK(call)                                                                       \
+    do                                                                                 \
+    {                                                                                  \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) latch((int)e_, #call, cudaGetErrorString(e_));          \
+    } while (0)
+
+template <typename T>
+void freeDev(T*& p)
+{
+    if (p) { CK(cudaFree(p)); p = nullptr; }
+}
+
+bool ensureDevice()
+{
+    if (G.device < 0)
+    {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) { latch(-1, "ensureDevice", "no CUDA device: this engine has no CPU fallback"); return false; }
+        G.device = d;
+    }
+    cudaError_t e = cudaSetDevice(G.device);
+    if (e != cudaSuccess) { latch((int)e, "cudaSetDevice", cudaGetErrorString(e)); return false; }
+    return true;
+}
+
+float intBits(int v)
+{
+    float f;
+    memcpy(&f, &v, sizeof(f));
+    return f;
+}
+
+int packMeta(const b200_Primitive& p, const std::vector<b200_Material>& mats)
+{
+    int fast = 0, procedural = 0, transparent = 0;
+    if (p.materialId >= 0 && (size_t)p.materialId < mats.size())
+    {
+        const b200_Material& m = mats[p.materialId];
+        fast = (m.attributes.x == 0) ? 0 : (m.attributes.x == 1 ? 1 : 2);
+        procedural = m.attributes.y != 0;
+        transparent = m.transparency != 0.f;
+    }
+    return (p.type & 0xF) | (fast << 4) | (procedural << 6) | (transparent << 7) | (p.materialId << 8);
+}
+
+void uploadMeta()
+{
+    if (G.hPrims.empty() || !G.dMeta) return;
+    std::vector<int> meta(G.hPrims.size());
+    for (size_t i = 0; i < G.hPrims.size(); ++i) meta[i] = packMeta(G.hPrims[i], G.hMats);
+    CK(cudaMemcpyAsync(G.dMeta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+    CK(cudaStreamSynchronize(G.stream)); // meta is a stack-lifetime staging vector
+}
+
+void unregisterHost()
+{
+    if (G.regBitmap) { cudaHostUnregister(G.regBitmap); G.regBitmap = nullptr; }
+    if (G.regIds) { cudaHostUnregister(G.regIds); G.regIds = nullptr; }
+    cudaGetLastError();
+}
+} // namespace
+
+// ----------------------------------------------------------------------------------------------------
+// the seam
+// ----------------------------------------------------------------------------------------------------
+extern "C" {
+
+void b200_set_device(int device) { G.device = device; }
+void b200_set_stream(void* s) { G.stream = s ? (cudaStream_t)s : G.ownStream; }
+void b200_set_limits(int w, int h) { if (w > 0 && h > 0) { G.maxW = w; G.maxH = h; } }
+void b200_set_partition(int rank, int world)
+{
+    if (world < 1 || rank < 0 || rank >= world) { latch(-2, "b200_set_partition", "rank/world out of range"); return; }
+    G.rank = rank; G.world = world;
+}
+int b200_last_error(char* msg, int cap)
+{
+    if (msg && cap > 0) { strncpy(msg, G.errMsg, cap - 1); msg[cap - 1] = 0; }
+    return G.err;
+}
+void b200_clear_error(void) { G.err = 0; G.errMsg[0] = 0; }
+
+void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
+{
+    if (occ.x != 1) latch(-3, "b200_initialize_scene", "one process drives one GPU: occupancyParameters.x must be 1 (use b200_set_partition)");
+    if (!ensureDevice()) return;
+    if (G.initialised) return;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, G.device));
+    G.numSMs = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&G.ownStream, cudaStreamNonBlocking));
+    if (!G.stream) G.stream = G.ownStream;
+    CK(cudaEventCreate(&G.evStart));
+    CK(cudaEventCreate(&G.evStop));
+    CK(cudaMalloc(&G.dTileCounter, sizeof(unsigned int)));
+    CK(cudaMalloc(&G.dWork, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(G.dWork, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&G.dLights, B200_NB_MAX_LIGHTINFORMATIONS * sizeof(b200_LightInformation)));
+    CK(cudaMemset(G.dLights, 0, B200_NB_MAX_LIGHTINFORMATIONS * sizeof(b200_LightInformation)));
+    int perSM = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render, CTA_THREADS, 0));
+    G.ctasPerSM = perSM > 0 ? perSM : 1;
+    G.initialised = true;
+    G.launches = 0;
+}
+
+void b200_finalize_scene(b200_int2)
+{
+    if (!G.initialised) return;
+    if (!ensureDevice()) return;
+    cudaDeviceSynchronize();
+    unregisterHost();
+    freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
+    freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
+    freeDev(G.dTileCounter); freeDev(G.dWork);
+    if (G.evStart) { cudaEventDestroy(G.evStart); G.evStart = nullptr; }
+    if (G.evStop) { cudaEventDestroy(G.evStop); G.evStop = nullptr; }
+    if (G.stream == G.ownStream) G.stream = nullptr;
+    if (G.ownStream) { cudaStreamDestroy(G.ownStream); G.ownStream = nullptr; }
+    G.capBoxes = G.capPrims = G.capMats = 0; G.pixelsCap = 0; G.texBytes = 0;
+    G.nbBoxes = G.nbPrims = G.nbMats = G.nbLights = 0;
+    G.hPrims.clear(); G.hMats.clear();
+    G.initialised = false; G.timed = false;
+    // no cudaDeviceReset(): the process may share the device with NCCL / PyTorch
+}
+
+void b200_reshape_scene(b200_int2, b200_SceneInfo)
+{
+    if (!ensureDevice()) return;
+    const size_t px = (size_t)G.maxW * (size_t)G.maxH;
+    freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
+    unregisterHost();
+    CK(cudaMalloc(&G.dRandoms, (px + 4) * sizeof(float)));
+    CK(cudaMemset(G.dRandoms, 0, (px + 4) * sizeof(float)));
+    CK(cudaMalloc(&G.dPost, px * sizeof(b200_PostProcessingBuffer)));
+    CK(cudaMemset(G.dPost, 0, px * sizeof(b200_PostProcessingBuffer)));
+    CK(cudaMalloc(&G.dIds, px * sizeof(int4)));
+    CK(cudaMemset(G.dIds, 0, px * sizeof(int4)));
+    CK(cudaMalloc(&G.dBitmap, px * B200_COLOR_DEPTH));
+    CK(cudaMemset(G.dBitmap, 0, px * B200_COLOR_DEPTH));
+    G.pixelsCap = px;
+}
+
+// Scene re-layout.  Input: the flattened AoS arrays of GPUKernel::compactBoxes (GPUKernel.cpp:1085-1281):
+// boxes in depth-first order with "slots to skip on a miss" counts.  Output (DESIGN.md "Data layout"):
+//   boxes   float4[2n']  (min, w0) (max, w1)    leaf: w0 = first primitive, w1 = count
+//                                               inner: w0 = skip, w1 = 0
+//   geo     float4[4m]   (p0,size.x) (p1,size.y) (p2,size.z) (n1,0)
+//   meta    int[m]       type | fast-transparency | procedural | transparent | materialId
+// with every inner box that has exactly one child dropped (its child's slab interval is contained in its
+// own, so the pair of tests equals the child's test alone), and skip counts recomputed.
+void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const b200_Primitive* prims, int nbPrims, const int*, int)
+{
+    if (!G.initialised) { latch(-4, "b200_h2d_scene", "initialize_scene not called"); return; }
+    if (!ensureDevice()) return;
+    if (nbBoxes < 0 || nbPrims < 0) { latch(-5, "b200_h2d_scene", "negative count"); return; }
+    G.nbBoxesIn = nbBoxes;
+
+    // 1. survivors of the chain collapse
+    std::vector<unsigned char> keep(nbBoxes, 1);
+    for (int i = 0; i < nbBoxes; ++i)
+    {
+        const b200_BoundingBox& b = boxes[i];
+        const int skip = b.indexForNextBox.x;
+        if (b.nbPrimitives != 0 || skip <= 1 || i + 1 >= nbBoxes || i + skip > nbBoxes) continue;
+        const b200_BoundingBox& c = boxes[i + 1];
+        if (c.indexForNextBox.x != skip - 1) continue; // more than one child
+        const bool contained = b.parameters[0].x <= c.parameters[0].x && b.parameters[0].y <= c.parameters[0].y &&
+                               b.parameters[0].z <= c.parameters[0].z && b.parameters[1].x >= c.parameters[1].x &&
+                               b.parameters[1].y >= c.parameters[1].y && b.parameters[1].z >= c.parameters[1].z;
+        if (contained) keep[i] = 0;
+    }
+    // 2. new positions; a leaf whose reference skip is not 1 (lights box with children, GPUKernel.cpp:1248-1251)
+    //    is emitted as an inner box with identical bounds followed by the leaf.
+    std::vector<int> pos(nbBoxes + 1, 0);
+    for (int i = 0; i < nbBoxes; ++i)
+    {
+        int n = keep[i] ? 1 : 0;
+        if (keep[i] && boxes[i].nbPrimitives > 0 && boxes[i].indexForNextBox.x != 1) n = 2;
+        pos[i + 1] = pos[i] + n;
+    }
+    const int nOut = pos[nbBoxes];
+    std::vector<float4> packed(2 * (size_t)nOut);
+    for (int i = 0; i < nbBoxes; ++i)
+    {
+        if (!keep[i]) continue;
+        const b200_BoundingBox& b = boxes[i];
+        int end = i + b.indexForNextBox.x;
+        if (end > nbBoxes) end = nbBoxes;
+        if (end <= i) end = i + 1; // a zero/negative skip would never terminate in the reference; advance instead
+        int o = pos[i];
+        const float4 lo = make_float4(b.parameters[0].x, b.parameters[0].y, b.parameters[0].z, 0.f);
+        const float4 hi = make_float4(b.parameters[1].x, b.parameters[1].y, b.parameters[1].z, 0.f);
+        auto put = [&](int at, int w0, int w1) {
+            packed[2 * (size_t)at] = lo; packed[2 * (size_t)at + 1] = hi;
+            packed[2 * (size_t)at].w = intBits(w0); packed[2 * (size_t)at + 1].w = intBits(w1);
+        };
+        if (b.nbPrimitives > 0)
+        {
+            if (b.indexForNextBox.x != 1) { put(o, pos[end] - o, 0); ++o; }
+            put(o, b.startIndex, b.nbPrimitives);
+        }
+        else
+            put(o, pos[end] - o, 0);
+    }
+
+    // 3. primitives
+    std::vector<float4> geo(4 * (size_t)nbPrims);
+    for (int i = 0; i < nbPrims; ++i)
+    {
+        const b200_Primitive& p = prims[i];
+        geo[4 * (size_t)i + 0] = make_float4(p.p0.x, p.p0.y, p.p0.z, p.size.x);
+        geo[4 * (size_t)i + 1] = make_float4(p.p1.x, p.p1.y, p.p1.z, p.size.y);
+        geo[4 * (size_t)i + 2] = make_float4(p.p2.x, p.p2.y, p.p2.z, p.size.z);
+        geo[4 * (size_t)i + 3] = make_float4(p.n1.x, p.n1.y, p.n1.z, 0.f);
+    }
+    G.hPrims.assign(prims, prims + nbPrims);
+
+    // 4. device buffers (grow-only) and upload
+    if ((size_t)nOut > G.capBoxes || (size_t)nbBoxes > G.capBoxes)
+    {
+        freeDev(G.dBoxes); freeDev(G.dRawBoxes);
+        G.capBoxes = (size_t)(nbBoxes > nOut ? nbBoxes : nOut) + 1024;
+        CK(cudaMalloc(&G.dBoxes, 2 * G.capBoxes * sizeof(float4)));
+        CK(cudaMalloc(&G.dRawBoxes, G.capBoxes * sizeof(b200_BoundingBox)));
+    }
+    if ((size_t)nbPrims > G.capPrims)
+    {
+        freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims);
+        G.capPrims = (size_t)nbPrims + 1024;
+        CK(cudaMalloc(&G.dGeo, 4 * G.capPrims * sizeof(float4)));
+        CK(cudaMalloc(&G.dMeta, G.capPrims * sizeof(int)));
+        CK(cudaMalloc(&G.dPrims, G.capPrims * sizeof(b200_Primitive)));
+    }
+    if (nOut) CK(cudaMemcpyAsync(G.dBoxes, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+    if (nbBoxes) CK(cudaMemcpyAsync(G.dRawBoxes, boxes, (size_t)nbBoxes * sizeof(b200_BoundingBox), cudaMemcpyHostToDevice, G.stream));
+    if (nbPrims)
+    {
+        CK(cudaMemcpyAsync(G.dGeo, geo.data(), geo.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+        CK(cudaMemcpyAsync(G.dPrims, prims, (size_t)nbPrims * sizeof(b200_Primitive), cudaMemcpyHostToDevice, G.stream));
+    }
+    CK(cudaStreamSynchronize(G.stream)); // staging vectors die at scope exit
+    G.nbBoxes = nOut; G.nbPrims = nbPrims;
+    uploadMeta();
+}
+
+void b200_h2d_materials(b200_int2, const b200_Material* materials, int n)
+{
+    if (!G.initialised) { latch(-4, "b200_h2d_materials", "initialize_scene not called"); return; }
+    if (!ensureDevice() || n <= 0) return;
+    if ((size_t)n > G.capMats)
+    {
+        freeDev(G.dMats);
+        G.capMats = (size_t)n + 64;
+        CK(cudaMalloc(&G.dMats, G.capMats * sizeof(b200_Material)));
+    }
+    CK(cudaMemcpyAsync(G.dMats, materials, (size_t)n * sizeof(b200_Material), cudaMemcpyHostToDevice, G.stream));
+    CK(cudaStreamSynchronize(G.stream));
+    G.hMats.assign(materials, materials + n);
+    G.nbMats = n;
+    uploadMeta(); // the packed word caches three material bits
+}
+
+void b200_h2d_randoms(b200_int2, const float* randoms)
+{
+    if (!G.dRandoms) { latch(-4, "b200_h2d_randoms", "reshape_scene not called"); return; }
+    if (!ensureDevice()) return;
+    CK(cudaMemcpyAsync(G.dRandoms, randoms, (size_t)G.maxW * G.maxH * sizeof(float), cudaMemcpyHostToDevice, G.stream));
+    CK(cudaStreamSynchronize(G.stream));
+}
+
+void b200_h2d_textures(b200_int2, int nbTextures, const b200_TextureInfo* infos)
+{
+    if (!G.initialised) { latch(-4, "b200_h2d_textures", "initialize_scene not called"); return; }
+    if (!ensureDevice()) return;
+    size_t total = 0;
+    for (int i = 0; i < nbTextures; ++i)
+        if (infos[i].buffer)
+        {
+            const size_t end = (size_t)infos[i].offset + (size_t)infos[i].size.x * infos[i].size.y * infos[i].size.z;
+            if (end > total) total = end;
+        }
+    freeDev(G.dTex);
+    G.texBytes = total;
+    if (!total) return;
+    CK(cudaMalloc(&G.dTex, total + 16));
+    CK(cudaMemset(G.dTex, 0, total + 16));
+    for (int i = 0; i < nbTextures; ++i)
+        if (infos[i].buffer)
+            CK(cudaMemcpyAsync(G.dTex + infos[i].offset, infos[i].buffer, (size_t)infos[i].size.x * infos[i].size.y * infos[i].size.z,
+                               cudaMemcpyHostToDevice, G.stream));
+    CK(cudaStreamSynchronize(G.stream));
+}
+
+void b200_h2d_lightInformation(b200_int2, const b200_LightInformation* li, int n)
+{
+    if (!G.initialised) { latch(-4, "b200_h2d_lightInformation", "initialize_scene not called"); return; }
+    if (!ensureDevice()) return;
+    if (n > B200_NB_MAX_LIGHTINFORMATIONS) n = B200_NB_MAX_LIGHTINFORMATIONS;
+    if (n > 0)
+    {
+        CK(cudaMemcpyAsync(G.dLights, li, (size_t)n * sizeof(b200_LightInformation), cudaMemcpyHostToDevice, G.stream));
+        CK(cudaStreamSynchronize(G.stream));
+    }
+    G.nbLights = n;
+}
+
+void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b200_PostProcessingInfo pp, b200_float3 origin,
+                 b200_float3 direction, b200_float4 angles)
+{
+    if (!G.initialised || !G.dPost) { latch(-4, "b200_render", "initialize_scene/reshape_scene not called"); return; }
+    if (!ensureDevice()) return;
+    if (si.size.x <= 0 || si.size.y <= 0 || (size_t)si.size.x * si.size.y > G.pixelsCap)
+    {
+        latch(-6, "b200_render", "frame larger than the limits (b200_set_limits before reshape_scene)");
+        return;
+    }
+    if (si.cameraType == B200_CT_VR || si.cameraType == B200_CT_PANORAMIC || si.cameraType == B200_CT_VOLUME)
+    {
+        latch(-7, "b200_render", "camera type outside this engine's path (VR/panoramic/volume): see DESIGN.md scope");
+        return;
+    }
+    if (pp.type != B200_PPE_NONE) { latch(-8, "b200_render", "post-processing effects are outside this engine's path: see DESIGN.md scope"); return; }
+    if (objects.y > G.nbPrims || objects.w > B200_NB_MAX_LIGHTINFORMATIONS) { latch(-9, "b200_render", "object counts exceed uploaded scene"); return; }
+    if (!G.dMats && G.nbPrims > 0) { latch(-10, "b200_render", "materials not uploaded"); return; }
+
+    RenderParams P;
+    memset(&P, 0, sizeof(P));
+    P.scene.boxes = G.dBoxes; P.scene.nbBoxes = G.nbBoxes;
+    P.scene.geo = G.dGeo; P.scene.meta = G.dMeta; P.scene.prims = G.dPrims; P.scene.nbPrimitives = objects.y;
+    P.scene.mats = G.dMats; P.scene.lights = G.dLights; P.scene.lightInfoSize = objects.w; P.scene.nbLamps = objects.z;
+    P.scene.tex = G.dTex; P.scene.randoms = G.dRandoms; P.scene.randomTableSize = G.maxW * G.maxH;
+    P.scene.rawBoxes = G.dRawBoxes; P.scene.nbRawBoxes = objects.x < G.nbBoxesIn ? objects.x : G.nbBoxesIn;
+    P.si = si; P.pp = pp;
+    P.eye = make_float3(origin.x, origin.y, origin.z);
+    P.target = make_float3(direction.x, direction.y, direction.z);
+    P.angles = make_float4(angles.x, angles.y, angles.z, angles.w);
+    P.post = G.dPost; P.ids = G.dIds; P.bitmap = G.dBitmap;
+    P.tileCounter = G.dTileCounter; P.workCounters = G.dWork;
+    P.tilesX = (si.size.x + TILE_W - 1) / TILE_W;
+    P.tilesY = (si.size.y + TILE_H - 1) / TILE_H;
+    const int nbTiles = P.tilesX * P.tilesY;
+    P.rank = G.rank; P.worldSize = G.world;
+    P.nbLocalTiles = (nbTiles - G.rank + G.world - 1) / G.world;
+
+    CK(cudaEventRecord(G.evStart, G.stream));
+    CK(cudaMemsetAsync(G.dTileCounter, 0, sizeof(unsigned int), G.stream));
+    const int warpsPerCta = CTA_THREADS / 32;
+    int grid = G.numSMs * G.ctasPerSM;
+    const int needed = (P.nbLocalTiles + warpsPerCta - 1) / warpsPerCta;
+    if (grid > needed) grid = needed > 0 ? needed : 1;
+    CK(cudaMemcpyToSymbolAsync(cP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, G.stream));
+    k_render<<<grid, CTA_THREADS, 0, G.stream>>>();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) latch((int)e, "k_render launch", cudaGetErrorString(e));
+    G.launches++;
+    CK(cudaEventRecord(G.evStop, G.stream));
+    G.timed = true;
+}
+
+void b200_d2h_bitmap(b200_int2, b200_SceneInfo si, b200_BitmapBuffer* bitmap, b200_PrimitiveXYIdBuffer* ids)
+{
+    if (!G.dBitmap) { latch(-4, "b200_d2h_bitmap", "reshape_scene not called"); return; }
+    if (!ensureDevice()) return;
+    const size_t px = (size_t)si.size.x * si.size.y;
+    if (px > G.pixelsCap) { latch(-6, "b200_d2h_bitmap", "frame larger than the limits"); return; }
+    // The caller's buffers are pageable (GPUKernel.cpp:344-360); pin them in place once so every later
+    // frame is a straight DMA instead of a staged copy.
+    if (bitmap && (G.regBitmap != bitmap || G.regBitmapBytes < px * 3))
+    {
+        if (G.regBitmap) { cudaHostUnregister(G.regBitmap); G.regBitmap = nullptr; }
+        if (cudaHostRegister(bitmap, px * 3, cudaHostRegisterDefault) == cudaSuccess) { G.regBitmap = bitmap; G.regBitmapBytes = px * 3; }
+        else cudaGetLastError();
+    }
+    if (ids && (G.regIds != ids || G.regIdsBytes < px * 16))
+    {
+        if (G.regIds) { cudaHostUnregister(G.regIds); G.regIds = nullptr; }
+        if (cudaHostRegister(ids, px * 16, cudaHostRegisterDefault) == cudaSuccess) { G.regIds = ids; G.regIdsBytes = px * 16; }
+        else cudaGetLastError();
+    }
+    if (bitmap) CK(cudaMemcpyAsync(bitmap, G.dBitmap, px * 3, cudaMemcpyDeviceToHost, G.stream));
+    if (ids) CK(cudaMemcpyAsync(ids, G.dIds, px * 16, cudaMemcpyDeviceToHost, G.stream));
+    CK(cudaStreamSynchronize(G.stream));
+}
+
+void b200_device_buffers(void** bitmap, void** ids, void** post)
+{
+    if (bitmap) *bitmap = G.dBitmap;
+    if (ids) *ids = G.dIds;
+    if (post) *post = G.dPost;
+}
+
+void b200_get_counters(unsigned long long* rays, unsigned long long* pixels, int reset)
+{
+    unsigned long long h[2] = {0, 0};
+    if (G.dWork && ensureDevice())
+    {
+        CK(cudaStreamSynchronize(G.stream));
+        CK(cudaMemcpy(h, G.dWork, sizeof(h), cudaMemcpyDeviceToHost));
+        if (reset) CK(cudaMemset(G.dWork, 0, sizeof(h)));
+    }
+    if (rays) *rays = h[0];
+    if (pixels) *pixels = h[1];
+}
+
+float b200_last_render_ms(void)
+{
+    if (!G.timed || !ensureDevice()) return -1.f;
+    float ms = -1.f;
+    CK(cudaEventSynchronize(G.evStop));
+    CK(cudaEventElapsedTime(&ms, G.evStart, G.evStop));
+    return ms;
+}
+
+unsigned long long b200_kernel_launches(void) { return G.launches; }
+
+void b200_scene_stats(int* in, int* dev, int* prims, int* reserved)
+{
+    if (in) *in = G.nbBoxesIn;
+    if (dev) *dev = G.nbBoxes;
+    if (prims) *prims = G.nbPrims;
+    if (reserved) *reserved = G.numSMs * G.ctasPerSM;
+}
+
+void b200_synchronize(void)
+{
+    if (G.stream && ensureDevice()) CK(cudaStreamSynchronize(G.stream));
+}
+}

@@ -1,0 +1,656 @@
+// shade.cuh — shading, texture lookup and the bounce loop of the ray-propagation path.
+// Semantics: reference CUDA engine (paths relative to /root/reference/solr/engines/cuda/).
+#pragma once
+#include "trace.cuh"
+
+#define SB_PI 3.14159265358979323846f
+
+// ---------------------------------------------------------------- texture maps (TextureMapping.cuh:30-116)
+SB_DEV void texMaps(const b200_Material& m, const int index, float3& normal, float4& specular, float4& attributes,
+                    float4& adv)
+{
+    const unsigned char* t = cS.tex;
+    // bump map (:45-57) only computes a local `value`; nothing observable.
+    if (m.textureIds.y != B200_TEXTURE_NONE) // normal map :30-40
+    {
+        const int i = m.textureOffset.y + index;
+        normal.x -= 3.f * (t[i] / 256.f - 0.5f);
+        normal.y -= 3.f * (t[i + 1] / 256.f - 0.5f);
+        normal.z = 0.f;
+    }
+    if (m.textureIds.w != B200_TEXTURE_NONE) // specular map :62-73
+    {
+        const int i = m.textureOffset.w + index;
+        specular.x = t[i] / 256.f;
+        specular.y = 1000.f * t[i + 1] / 256.f;
+        specular.z = t[i + 2] / 256.f;
+    }
+    if (m.advancedTextureIds.x != B200_TEXTURE_NONE) // reflection map :78-87
+    {
+        const int i = m.advancedTextureOffset.x + index;
+        attributes.x *= (t[i] + t[i + 1] + t[i + 2]) / 768.f;
+    }
+    if (m.advancedTextureIds.y != B200_TEXTURE_NONE) // transparency map :92-102
+    {
+        const int i = m.advancedTextureOffset.y + index;
+        attributes.y *= (t[i] + t[i + 1] + t[i + 2]) / 768.f;
+    }
+    if (m.advancedTextureIds.z != B200_TEXTURE_NONE) // ambient occlusion map :107-116
+    {
+        const int i = m.advancedTextureOffset.z + index;
+        adv.x = (t[i] + t[i + 1] + t[i + 2]) / 768.f;
+    }
+}
+
+SB_DEV void fetchTexel(const b200_Material& m, const int u, const int v, float4& result, float3& normal,
+                       float4& specular, float4& attributes, float4& adv)
+{
+    const int A = (v * m.textureMapping.x + u) * m.textureMapping.w;
+    const int B = m.textureMapping.x * m.textureMapping.y * m.textureMapping.w;
+    const int index = A % B;
+    const int i = m.textureOffset.x + index;
+    result.x = cS.tex[i] / 256.f; result.y = cS.tex[i + 1] / 256.f; result.z = cS.tex[i + 2] / 256.f;
+    texMaps(m, index, normal, specular, attributes, adv);
+}
+
+// TextureMapping.cuh:118-160
+__device__ __noinline__ void juliaSet(const b200_Material& m, const float x, const float y, float4& color)
+{
+    const float W = (float)m.textureMapping.x, H = (float)m.textureMapping.y;
+    const float cRe = -0.7f + 0.4f * sinf(cSI.timestamp / 1500.f);
+    const float cIm = 0.27015f + 0.4f * cosf(cSI.timestamp / 2000.f);
+    float newRe = 1.5f * (x - W / 2.f) / (0.5f * W);
+    float newIm = (y - H / 2.f) / (0.5f * H);
+    int n;
+    const float maxIterations = 40.f + cSI.pathTracingIteration;
+    for (n = 0; n < maxIterations; n++)
+    {
+        const float oldRe = newRe, oldIm = newIm;
+        newRe = oldRe * oldRe - oldIm * oldIm + cRe;
+        newIm = 2.f * oldRe * oldIm + cIm;
+        if ((newRe * newRe + newIm * newIm) > 4.f) break;
+    }
+    color.x = 1.f - color.x * (n / maxIterations);
+    color.y = 1.f - color.y * (n / maxIterations);
+    color.z = 1.f - color.z * (n / maxIterations);
+    color.w = 1.f - (n / maxIterations);
+}
+
+// TextureMapping.cuh:162-198 (Im_factor is a double there)
+__device__ __noinline__ void mandelbrotSet(const b200_Material& m, const float x, const float y, float4& color)
+{
+    const float W = (float)m.textureMapping.x, H = (float)m.textureMapping.y;
+    const float MinRe = -2.f, MaxRe = 1.f, MinIm = -1.2f;
+    const float MaxIm = MinIm + (MaxRe - MinRe) * H / W;
+    const float Re_factor = (MaxRe - MinRe) / (W - 1.f);
+    const double Im_factor = (MaxIm - MinIm) / (H - 1.f);
+    const float maxIterations = B200_NB_MAX_ITERATIONS + cSI.pathTracingIteration;
+    const float c_im = MaxIm - y * Im_factor;
+    const float c_re = MinRe + x * Re_factor;
+    float Z_re = c_re, Z_im = c_im;
+    bool isInside = true;
+    unsigned n;
+    for (n = 0; isInside && n < maxIterations; ++n)
+    {
+        const float Z_re2 = Z_re * Z_re, Z_im2 = Z_im * Z_im;
+        if (Z_re2 + Z_im2 > 4.f) isInside = false;
+        Z_im = 2.f * Z_re * Z_im + c_im;
+        Z_re = Z_re2 - Z_im2 + c_re;
+    }
+    color.x = 1.f - color.x * (n / maxIterations);
+    color.y = 1.f - color.y * (n / maxIterations);
+    color.z = 1.f - color.z * (n / maxIterations);
+    color.w = 1.f - (n / maxIterations);
+}
+
+// TextureMapping.cuh:205-286
+__device__ __noinline__ float4 triangleUVMapping(const b200_Primitive& p, const float3 areas,
+                                                 float3& normal, float4& specular, float4& attributes, float4& adv)
+{
+    const b200_Material& m = cS.mats[p.materialId];
+    float4 result = f4(m.color.x, m.color.y, m.color.z, m.color.w);
+    const float sum = areas.x + areas.y + areas.z;
+    const float Tx = (p.vt0.x * areas.x + p.vt1.x * areas.y + p.vt2.x * areas.z) / sum;
+    const float Ty = (p.vt0.y * areas.x + p.vt1.y * areas.y + p.vt2.y * areas.z) / sum;
+    float mox = 0.f, moy = 0.f;
+    if (m.attributes.y == 1)
+    {
+        mox = m.mappingOffset.x * cSI.timestamp;
+        moy = m.mappingOffset.y * cSI.timestamp;
+    }
+    int u = Tx * m.textureMapping.x + mox;
+    int v = Ty * m.textureMapping.y + moy;
+    u = u % m.textureMapping.x;
+    v = v % m.textureMapping.y;
+    if (u >= 0 && u < m.textureMapping.x && v >= 0 && v < m.textureMapping.y)
+    {
+        switch (m.textureIds.x)
+        {
+        case B200_TEXTURE_MANDELBROT: mandelbrotSet(m, u, v, result); break;
+        case B200_TEXTURE_JULIA: juliaSet(m, u, v, result); break;
+        default: fetchTexel(m, u, v, result, normal, specular, attributes, adv);
+        }
+    }
+    return result;
+}
+
+// TextureMapping.cuh:294-349
+__device__ __noinline__ float4 sphereUVMapping(const b200_Primitive& p, const float3 I, float3& normal, float4& specular,
+                                               float4& attributes, float4& adv)
+{
+    const b200_Material& m = cS.mats[p.materialId];
+    float4 result = f4(m.color.x, m.color.y, m.color.z, m.color.w);
+    const float3 d = normalize(I - f3(p.p0.x, p.p0.y, p.p0.z));
+    const float U = ((atan2f(d.x, d.z) / SB_PI) + 1.f) * .5f;
+    const float V = (asinf(d.y) / SB_PI) + .5f;
+    int u = m.textureMapping.x * (U * p.vt1.x);
+    int v = m.textureMapping.y * (V * p.vt1.y);
+    if (m.textureMapping.x != 0) u = u % m.textureMapping.x;
+    if (m.textureMapping.y != 0) v = v % m.textureMapping.y;
+    if (u >= 0 && u < m.textureMapping.x && v >= 0 && v < m.textureMapping.y)
+        fetchTexel(m, u, v, result, normal, specular, attributes, adv);
+    return result;
+}
+
+// TextureMapping.cuh:357-447 (non-Kinect branch)
+__device__ __noinline__ float4 cubeMapping(const b200_Primitive& p, float3 I, float3& normal,
+                                           float4& specular, float4& attributes, float4& adv)
+{
+    const b200_Material& m = cS.mats[p.materialId];
+    float4 result = f4(m.color.x, m.color.y, m.color.z, m.color.w);
+    int u = ((p.type == B200_PT_CHECKBOARD) || (p.type == B200_PT_XZPLANE) || (p.type == B200_PT_XYPLANE))
+                ? (I.x - p.p0.x + p.size.x) : (I.z - p.p0.z + p.size.z);
+    int v = ((p.type == B200_PT_CHECKBOARD) || (p.type == B200_PT_XZPLANE)) ? (I.z + p.p0.z + p.size.z) : (I.y - p.p0.y + p.size.y);
+    if (m.textureMapping.x != 0) u = u % m.textureMapping.x;
+    if (m.textureMapping.y != 0) v = v % m.textureMapping.y;
+    if (u >= 0 && u < m.textureMapping.x && v >= 0 && v < m.textureMapping.x)
+    {
+        switch (m.textureIds.x)
+        {
+        case B200_TEXTURE_MANDELBROT: mandelbrotSet(m, u, v, result); break;
+        case B200_TEXTURE_JULIA: juliaSet(m, u, v, result); break;
+        default: fetchTexel(m, u, v, result, normal, specular, attributes, adv);
+        }
+    }
+    return result;
+}
+
+// GeometryIntersections.cuh:87-151
+__device__ __noinline__ float4 skyboxMapping(const float3 origin, const float3 target)
+{
+    const b200_Material& m = cS.mats[cSI.skyboxMaterialId];
+    float4 result = f4(m.color.x, m.color.y, m.color.z, m.color.w);
+    const float3 dir = normalize(target - origin);
+    const float a = 2.f * dot(dir, dir);
+    const float b = 2.f * dot(origin, dir);
+    const float c = dot(origin, origin) - (cSI.skyboxRadius * cSI.skyboxRadius);
+    const float d = b * b - 2.f * a * c;
+    if (d <= 0.f || a == 0.f) return result;
+    const float r = sqrtf(d);
+    const float t1 = (-b - r) / a;
+    const float t2 = (-b + r) / a;
+    if (t1 <= cSI.geometryEpsilon && t2 <= cSI.geometryEpsilon) return result;
+    float t = 0.f;
+    if (t1 <= cSI.geometryEpsilon) t = t2;
+    else if (t2 <= cSI.geometryEpsilon) t = t1;
+    else t = (t1 < t2) ? t1 : t2;
+    if (t < cSI.geometryEpsilon) return result;
+    const float3 I = normalize(origin + t * dir);
+    const float U = ((atan2f(I.x, I.z) / SB_PI) + 1.f) * .5f;
+    const float V = (asinf(I.y) / SB_PI) + .5f;
+    int u = int(m.textureMapping.x * U);
+    int v = int(m.textureMapping.y * V);
+    if (m.textureMapping.x != 0) u %= m.textureMapping.x;
+    if (m.textureMapping.y != 0) v %= m.textureMapping.y;
+    if (u >= 0 && u < m.textureMapping.x && v >= 0 && v < m.textureMapping.y)
+    {
+        const int A = (v * m.textureMapping.x + u) * m.textureMapping.w;
+        const int B = m.textureMapping.x * m.textureMapping.y * m.textureMapping.w;
+        const int i = m.textureOffset.x + A % B;
+        result.x = cS.tex[i] / 256.f; result.y = cS.tex[i + 1] / 256.f; result.z = cS.tex[i + 2] / 256.f;
+    }
+    return result;
+}
+
+// GeometryShaders.cuh:36-124
+SB_DEV float4 intersectionShader(const b200_Primitive& p, const b200_Material& m, const float3 I,
+                                 const float3 areas, float3& normal, float4& specular, float4& attributes, float4& adv)
+{
+    float4 col = f4(m.color.x, m.color.y, m.color.z, 0.f);
+    const bool textured = m.textureIds.x != B200_TEXTURE_NONE;
+    if (cSI.extendedGeometry)
+    {
+        switch (p.type)
+        {
+        case B200_PT_CONE: case B200_PT_CYLINDER: case B200_PT_ENVIRONMENT: case B200_PT_SPHERE: case B200_PT_ELLIPSOID:
+            if (textured) col = sphereUVMapping(p, I, normal, specular, attributes, adv);
+            break;
+        case B200_PT_CHECKBOARD:
+            if (textured)
+                col = cubeMapping(p, I, normal, specular, attributes, adv);
+            else
+            {
+                const int x = cSI.viewDistance + ((I.x - p.p0.x) / p.size.x);
+                const int z = cSI.viewDistance + ((I.z - p.p0.z) / p.size.x);
+                if (x % 2 == 0)
+                {
+                    if (z % 2 == 0) { col.x = 1.f - col.x; col.y = 1.f - col.y; col.z = 1.f - col.z; }
+                }
+                else
+                {
+                    if (z % 2 != 0) { col.x = 1.f - col.x; col.y = 1.f - col.y; col.z = 1.f - col.z; }
+                }
+            }
+            break;
+        case B200_PT_XYPLANE: case B200_PT_YZPLANE: case B200_PT_XZPLANE: case B200_PT_CAMERA:
+            if (textured) col = cubeMapping(p, I, normal, specular, attributes, adv);
+            break;
+        case B200_PT_TRIANGLE:
+            if (textured) col = triangleUVMapping(p, areas, normal, specular, attributes, adv);
+            break;
+        }
+    }
+    else if (textured)
+        col = triangleUVMapping(p, areas, normal, specular, attributes, adv);
+    return col;
+}
+
+SB_DEV float rnd(const int i) { return __ldg(cS.randoms + i); }
+
+// GeometryIntersections.cuh:916-1080
+SB_DEV float4 primitiveShader(const int index, const float3 origin, float3& normal,
+                              const int objectId, const float3 I, const float3 areas, float4& closestColor, const int iteration,
+                              float& shadowIntensity, float4& totalBlinn, float4& attributes, Counters& cnt)
+{
+    const b200_Primitive& primitive = cS.prims[objectId];
+    const b200_Material& material = cS.mats[primitive.materialId];
+    const int primIndex = primitive.index;
+    const float4 mInner = *reinterpret_cast<const float4*>(&material.innerIllumination);
+    float4 lampsColor = f4(0.f, 0.f, 0.f, 0.f);
+    shadowIntensity = 0.f;
+    float3 bumpNormal = f3(0.f, 0.f, 0.f);
+    float4 adv = f4(0.f, 0.f, 0.f, 0.f);
+    float4 specular = f4(material.specular.x, material.specular.y, material.specular.z, 0.f);
+    const float4 intersectionColor = intersectionShader(primitive, material, I, areas, bumpNormal, specular, attributes, adv);
+    normal += bumpNormal;
+    normal = normalize(normal);
+    if (material.attributes.z == 1) return intersectionColor;
+    if (cSI.graphicsLevel > B200_GL_NO_SHADING)
+    {
+        closestColor *= mInner.x;
+        for (int cpt = 0; cpt < cS.lightInfoSize; ++cpt)
+        {
+            const int cptLamp = (cSI.pathTracingIteration >= B200_NB_MAX_ITERATIONS) ? (cSI.pathTracingIteration % cS.lightInfoSize) : 0;
+            const b200_LightInformation& li = cS.lights[cptLamp];
+            const float4 liColor = *reinterpret_cast<const float4*>(&li.color);
+            if (li.primitiveId != primIndex)
+            {
+                float3 center = f3(li.location.x, li.location.y, li.location.z);
+                const int t = (index + cSI.timestamp) % (cS.randomTableSize - 3);
+                const b200_Material& m = cS.mats[li.materialId];
+                const float4 lInner = *reinterpret_cast<const float4*>(&m.innerIllumination);
+                if (cSI.pathTracingIteration >= B200_NB_MAX_ITERATIONS)
+                {
+                    const float a = lInner.y * 10.f * cSI.pathTracingIteration / cSI.maxPathTracingIterations;
+                    center.x += rnd(t) * a; center.y += rnd(t + 1) * a; center.z += rnd(t + 2) * a;
+                }
+                float3 lightRay = center - I;
+                const float lightRayLength = length(lightRay);
+                if (lightRayLength < lInner.z)
+                {
+                    float4 shadowColor = f4(0.f, 0.f, 0.f, 0.f);
+                    lightRay = normalize(lightRay);
+                    float lambert = mInner.x + dot(normal, lightRay);
+                    if (lambert > 0.f && cSI.graphicsLevel > 3 && iteration < 4 && mInner.x == 0.f)
+                    {
+                        cnt.rays++;
+                        const float4 sh = shadowWalk(center, I, li.primitiveId, iteration, objectId);
+                        shadowColor.x = sh.x; shadowColor.y = sh.y; shadowColor.z = sh.z;
+                        shadowIntensity = sh.w;
+                    }
+                    float photonEnergy = sqrtf(lightRayLength / lInner.z);
+                    photonEnergy = (photonEnergy > 1.f) ? 1.f : photonEnergy;
+                    photonEnergy = (photonEnergy < 0.f) ? 0.f : photonEnergy;
+                    lambert *= (lambert < 0.f) ? -material.transparency : 1.f;
+                    if (li.materialId != B200_MATERIAL_NONE)
+                        lambert *= lInner.x;
+                    else
+                        lambert *= liColor.w;
+                    if (mInner.w != 0.f) lambert *= (1.f + rnd(t) * mInner.w * 100.f);
+                    lambert *= (1.f - shadowIntensity);
+                    lambert += cSI.backgroundColor.w;
+                    lambert *= (1.f - photonEnergy);
+                    lampsColor += lambert * liColor - shadowColor;
+                    if (cSI.graphicsLevel > 1 && shadowIntensity < cSI.shadowIntensity)
+                    {
+                        const float3 viewRay = normalize(I - origin);
+                        float3 blinnDir = lightRay - viewRay;
+                        const float temp = sqrtf(dot(blinnDir, blinnDir));
+                        if (temp != 0.f)
+                        {
+                            blinnDir = (1.f / temp) * blinnDir;
+                            float blinnTerm = dot(blinnDir, normal);
+                            blinnTerm = (blinnTerm < 0.f) ? 0.f : blinnTerm;
+                            blinnTerm = specular.x * powf(blinnTerm, specular.y);
+                            blinnTerm *= (1.f - photonEnergy);
+                            totalBlinn += liColor * liColor.w * blinnTerm;
+                            totalBlinn.w = specular.z;
+                        }
+                    }
+                }
+            }
+            closestColor += intersectionColor * lampsColor;
+            if (material.advancedTextureIds.z != B200_TEXTURE_NONE) closestColor *= adv.x;
+            saturate4(closestColor);
+            saturate4(totalBlinn);
+        }
+    }
+    else
+        closestColor = intersectionColor;
+    return closestColor;
+}
+
+SB_DEV void vectorReflection(float3& r, const float3 i, const float3 n) { r = i - 2.f * dot(i, n) * n; } // VectorUtils.cuh:61-64
+SB_DEV void vectorRefraction(float3& refracted, const float3 incident, const float n1, const float3 normal, const float n2) // :73-87
+{
+    refracted = incident;
+    if (n2 != 0.f)
+    {
+        const float eta = n1 / n2;
+        const float c1 = -dot(incident, normal);
+        const float cs2 = 1.f - eta * eta * (1.f - c1 * c1);
+        if (cs2 >= 0.f) refracted = eta * incident + (eta * c1 - sqrtf(cs2)) * normal;
+    }
+}
+
+// VectorUtils.cuh:104-142, with the six sin/cos hoisted to the host (they depend on the camera only).
+struct Rotation { float cx, cy, cz, sx, sy, sz; };
+SB_DEV void vectorRotation(float3& v, const float3 c, const Rotation& R)
+{
+    float3 vec = f3(v.x - c.x, v.y - c.y, v.z - c.z);
+    float3 res = vec;
+    res.y = vec.y * R.cx - vec.z * R.sx;
+    res.z = vec.y * R.sx + vec.z * R.cx;
+    vec = res;
+    res.z = vec.z * R.cy - vec.x * R.sy;
+    res.x = vec.z * R.sy + vec.x * R.cy;
+    vec = res;
+    res.x = vec.x * R.cz - vec.y * R.sz;
+    res.y = vec.x * R.sz + vec.y * R.cz;
+    v.x = res.x + c.x; v.y = res.y + c.y; v.z = res.z + c.z;
+}
+
+// CudaRayTracer.cu:69-408 — the bounce loop.  colors[]/colorContributions[] of the reference (11-entry
+// local arrays folded back to front at :382-385) stay local arrays here; only `iteration` entries are live.
+SB_DEV float4 launchRayTracing(const int index, const float3 rayO, const float3 rayT,
+                                   float& depthOfField, int4& id, Counters& cnt)
+{
+    float4 intersectionColor = f4(0.f, 0.f, 0.f, 0.f);
+    float3 normal = f3(0.f, 0.f, 0.f);
+    bool carryon = true;
+    float3 curO = rayO, curT = rayT;
+    float initialRefraction = 1.f;
+    int iteration = 0;
+    id.x = -1; id.z = 0; id.w = 0;
+    int currentMaterialId = -2;
+    float colorContributions[B200_NB_MAX_ITERATIONS + 1];
+    float4 colors[B200_NB_MAX_ITERATIONS + 1];
+#pragma unroll
+    for (int i = 0; i <= B200_NB_MAX_ITERATIONS; ++i) { colorContributions[i] = 0.f; colors[i] = f4(0.f, 0.f, 0.f, 0.f); }
+    float4 recursiveBlinn = f4(0.f, 0.f, 0.f, 0.f);
+    float shadowIntensity = 0.f;
+    float3 reflectedTarget = f3(0.f, 0.f, 0.f);
+    float4 closestColor = f4(0.f, 0.f, 0.f, 0.f), colorBox = f4(0.f, 0.f, 0.f, 0.f);
+    float3 latestIntersection = rayO;
+    float rayLength = 0.f;
+    depthOfField = cSI.viewDistance;
+    int reflectedRays = -1;
+    float3 reflO = f3(0.f, 0.f, 0.f), reflT = f3(0.f, 0.f, 0.f);
+    float reflectedRatio = 0.f;
+    float3 giO = f3(0.f, 0.f, 0.f), giT = f3(0.f, 0.f, 0.f);
+    float pathTracingRatio = 0.f;
+    float4 pathTracingColor = f4(0.f, 0.f, 0.f, 0.f);
+    bool useGlobalIllumination = false;
+    float4 rBlinn = f4(0.f, 0.f, 0.f, 0.f);
+    int currentMaxIteration = (cSI.graphicsLevel < B200_GL_REFLECTIONS) ? 1 : cSI.nbRayIterations + cSI.pathTracingIteration;
+    currentMaxIteration = (currentMaxIteration > B200_NB_MAX_ITERATIONS) ? B200_NB_MAX_ITERATIONS : currentMaxIteration;
+    Hit hit;
+    hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
+    float3 rayNd = f3(0.f, 0.f, 0.f); // normalize(target - origin) of the walk that produced `hit`
+
+    while (iteration < currentMaxIteration && rayLength < cSI.viewDistance && carryon)
+    {
+        float3 areas = f3(0.f, 0.f, 0.f);
+        if (cSI.renderBoxes != 0)
+        {
+            cnt.rays++;
+            boxDebugWalk(curO, curT, iteration, colorBox);
+            carryon = false;
+        }
+        else
+        {
+            cnt.rays++;
+            hit = closestHit(curO, curT, iteration, currentMaterialId);
+            rayNd = normalize(curT - curO);
+            carryon = hit.prim >= 0;
+        }
+        if (carryon)
+        {
+            const int meta = __ldg(cS.meta + hit.prim);
+            hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
+            const int matId = PM_MATERIAL(meta);
+            const b200_Material& mat = cS.mats[matId];
+            currentMaterialId = matId;
+            const float4 rrto = *reinterpret_cast<const float4*>(&mat.reflection); // reflection, refraction, transparency, opacity
+            float4 attributes = f4(rrto.x, rrto.z, rrto.y, rrto.w);
+            const float matInnerX = mat.innerIllumination.x;
+            const float3 closestIntersection = hit.p;
+            if (iteration == 0)
+            {
+                colors[0] = f4(0.f, 0.f, 0.f, 0.f);
+                colorContributions[0] = 1.f;
+                latestIntersection = closestIntersection;
+                depthOfField = length(closestIntersection - rayO);
+                if (matInnerX == 0.f && (cSI.advancedIllumination == B200_AI_BASIC || cSI.advancedIllumination == B200_AI_FULL))
+                {
+                    const int t = (index + cSI.pathTracingIteration * 100 + cSI.timestamp) % (cS.randomTableSize - 3);
+                    giO = closestIntersection + normal * cSI.rayEpsilon;
+                    giT.x = normal.x + 100.f * rnd(t);
+                    giT.y = normal.y + 100.f * rnd(t + 1);
+                    giT.z = normal.z + 100.f * rnd(t + 2);
+                    const float cos_theta = dot(normalize(giT), normal);
+                    if (cos_theta < 0.f) giT = -giT;
+                    giT += closestIntersection;
+                    pathTracingRatio = (1.f - attributes.y) * fabsf(cos_theta);
+                    useGlobalIllumination = true;
+                }
+                id.x = __ldg(&cS.prims[hit.prim].index);
+            }
+            rBlinn.w = attributes.y;
+            colors[iteration] = primitiveShader(index, curO, normal, hit.prim, closestIntersection, areas, closestColor, iteration,
+                                                shadowIntensity, rBlinn, attributes, cnt);
+            id.z += matInnerX * 256;
+            const float segmentLength = length(closestIntersection - latestIntersection);
+            latestIntersection = closestIntersection;
+            const float transparency = attributes.y;
+            float a = 0.f;
+            if (attributes.y != 0.f)
+            {
+                float refraction = attributes.z;
+                if (initialRefraction == refraction)
+                {
+                    refraction = 1.f;
+                    const float len = segmentLength * (attributes.w * (1.f - transparency));
+                    rayLength += len;
+                    rayLength = (rayLength > cSI.viewDistance) ? cSI.viewDistance : rayLength;
+                    a = (rayLength / cSI.viewDistance);
+                    colors[iteration].x -= a; colors[iteration].y -= a; colors[iteration].z -= a;
+                }
+                const float3 O_E = normalize(closestIntersection - curO);
+                vectorRefraction(reflectedTarget, O_E, refraction, normal, initialRefraction);
+                colorContributions[iteration] = transparency - a;
+                initialRefraction = refraction;
+                if (reflectedRays == -1 && attributes.x != 0.f)
+                {
+                    float3 rd;
+                    vectorReflection(rd, O_E, normal);
+                    reflO = closestIntersection + rd * cSI.rayEpsilon;
+                    reflT = closestIntersection + rd;
+                    reflectedRatio = attributes.x;
+                    reflectedRays = iteration;
+                }
+            }
+            else if (attributes.x != 0.f)
+            {
+                const float3 O_E = normalize(closestIntersection - curO);
+                vectorReflection(reflectedTarget, O_E, normal);
+                colorContributions[iteration] = attributes.x;
+            }
+            else
+            {
+                carryon = false;
+                colorContributions[iteration] = 1.f;
+            }
+            rBlinn /= (float)(iteration + 1);
+            recursiveBlinn.x = (rBlinn.x > recursiveBlinn.x) ? rBlinn.x : recursiveBlinn.x;
+            recursiveBlinn.y = (rBlinn.y > recursiveBlinn.y) ? rBlinn.y : recursiveBlinn.y;
+            recursiveBlinn.z = (rBlinn.z > recursiveBlinn.z) ? rBlinn.z : recursiveBlinn.z;
+            curO = closestIntersection + reflectedTarget * cSI.rayEpsilon;
+            curT = closestIntersection + reflectedTarget;
+            if (cSI.pathTracingIteration != 0 && mat.color.w != 0.f)
+            {
+                float ratio = mat.color.w;
+                ratio *= (attributes.y == 0.f) ? 1000.f : 1.f;
+                const int rindex = (index + cSI.timestamp) % (cS.randomTableSize - 3);
+                curT.x += rnd(rindex) * ratio;
+                curT.y += rnd(rindex + 1) * ratio;
+                curT.z += rnd(rindex + 2) * ratio;
+            }
+        }
+        else
+        {
+            if (cSI.skyboxMaterialId != B200_MATERIAL_NONE)
+            {
+                colors[iteration] = skyboxMapping(curO, curT);
+                const float rad = colors[iteration].x + colors[iteration].y + colors[iteration].z;
+                id.z += (rad > 2.5f) ? rad * 256.f : 0.f;
+            }
+            else if (cSI.gradientBackground)
+            {
+                const float3 up = f3(0.f, 1.f, 0.f);
+                const float3 dir = normalize(curT - curO);
+                float angle = 0.5f - dot(up, dir);
+                angle = (angle > 1.f) ? 1.f : angle;
+                colors[iteration] = (1.f - angle) * f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w);
+            }
+            else
+                colors[iteration] = f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w);
+            colorContributions[iteration] = 1.f;
+        }
+        iteration++;
+    }
+
+    // extra reflected ray of the first transparent + reflective hit (:296-315)
+    if (cSI.graphicsLevel >= B200_GL_REFLECTIONS && reflectedRays != -1 && cSI.renderBoxes == 0)
+    {
+        cnt.rays++;
+        hit = closestHit(reflO, reflT, reflectedRays, currentMaterialId);
+        rayNd = normalize(reflT - reflO);
+        if (hit.prim >= 0)
+        {
+            float3 areas;
+            const int meta = __ldg(cS.meta + hit.prim);
+            hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
+            float4 attributes = f4(cS.mats[PM_MATERIAL(meta)].reflection, 0.f, 0.f, 0.f);
+            const float4 color = primitiveShader(index, reflO, normal, hit.prim, hit.p, areas, closestColor, reflectedRays,
+                                                 shadowIntensity, rBlinn, attributes, cnt);
+            colors[reflectedRays] += color * reflectedRatio;
+            id.w = shadowIntensity * 255;
+        }
+    }
+    else if (cSI.graphicsLevel >= B200_GL_REFLECTIONS && reflectedRays != -1)
+    {
+        cnt.rays++;
+        boxDebugWalk(reflO, reflT, reflectedRays, colorBox);
+    }
+
+    bool test = true;
+    if ((cSI.advancedIllumination == B200_AI_BASIC || cSI.advancedIllumination == B200_AI_FULL) &&
+        cSI.pathTracingIteration >= B200_NB_MAX_ITERATIONS)
+    {
+        // global-illumination ray (:317-378)
+        if (useGlobalIllumination && cSI.advancedIllumination == B200_AI_FULL)
+        {
+            bool giHit = false;
+            if (cSI.renderBoxes != 0) { cnt.rays++; boxDebugWalk(giO, giT, 30, colorBox); }
+            else
+            {
+                cnt.rays++;
+                hit = closestHit(giO, giT, 30, B200_MATERIAL_NONE);
+                rayNd = normalize(giT - giO);
+                giHit = hit.prim >= 0;
+            }
+            if (giHit)
+            {
+                float3 areas;
+                const int meta = __ldg(cS.meta + hit.prim);
+                hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
+                const b200_Material& material = cS.mats[PM_MATERIAL(meta)];
+                const float4 mc = f4(material.color.x, material.color.y, material.color.z, material.color.w);
+                if (cS.prims[hit.prim].materialId != B200_MATERIAL_NONE)
+                {
+                    if (material.innerIllumination.x == 0.f)
+                    {
+                        colors[0] = mc * material.innerIllumination.x * pathTracingRatio;
+                        test = false;
+                    }
+                    else
+                        colors[0] = mc * pathTracingRatio;
+                }
+                if (test)
+                {
+                    pathTracingRatio *= 0.1f; // STANDARD_LUNINANCE_STRENGTH (Consts.h:52)
+                    float4 attributes = f4(0.f, 0.f, 0.f, 0.f);
+                    if (material.innerIllumination.x == 0.f)
+                        colors[0] -= cSI.shadowIntensity;
+                    else
+                        pathTracingColor = primitiveShader(index, giO, normal, hit.prim, hit.p, areas, closestColor, iteration,
+                                                           shadowIntensity, rBlinn, attributes, cnt);
+                }
+            }
+            else if (cSI.skyboxMaterialId != B200_MATERIAL_NONE)
+            {
+                pathTracingColor = skyboxMapping(giO, giT);
+                pathTracingRatio *= 0.2f; // SKYBOX_LUNINANCE_STRENGTH (Consts.h:53)
+            }
+        }
+        else if (cSI.skyboxMaterialId != B200_MATERIAL_NONE)
+        {
+            pathTracingColor = skyboxMapping(giO, giT);
+            pathTracingRatio *= 0.2f;
+        }
+        if (test) colors[0] += pathTracingColor * pathTracingRatio;
+    }
+
+    if (test)
+    {
+        for (int i = iteration - 2; i >= 0; --i)
+            colors[i] = colors[i] * (1.f - colorContributions[i]) + colors[i + 1] * colorContributions[i];
+        intersectionColor = colors[0];
+        intersectionColor += recursiveBlinn;
+    }
+    else
+        intersectionColor = colors[0];
+
+    const float D1 = cSI.viewDistance * 0.95f;
+    if (cSI.atmosphericEffect == B200_AE_FOG && depthOfField > D1)
+    {
+        const float D2 = cSI.viewDistance * 0.05f;
+        const float a = depthOfField - D1;
+        const float b = 1.f - (a / D2);
+        intersectionColor = intersectionColor * b + f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w) * (1.f - b);
+    }
+    id.y = iteration;
+    intersectionColor -= colorBox;
+    return intersectionColor;
+}

@@ -1,0 +1,600 @@
+// trace.cuh — device code of the ray-propagation path: box-list walk, primitive tests, shadow walk,
+// shading and the bounce loop.  Semantics follow the reference CUDA engine (cited per function, paths
+// relative to /root/reference/solr/engines/cuda/); structure does not:
+//   * the walk runs over the compact device layout (engine.cu "scene re-layout"): 32 B per box
+//     (two float4: min+w0, max+w1), 64 B of hot geometry per primitive (four float4: (p0,size.x)
+//     (p1,size.y) (p2,size.z) (n1,0); a sphere test reads only the first) + one packed int of
+//     type/material flags, so the inner loops never touch the 128 B Primitive / 176 B Material records;
+//   * single-child box chains are collapsed at upload (exact: a child's slab interval is contained in its
+//     parent's, so "parent hit and child hit" == "child hit");
+//   * hit attributes (normal, triangle areas) are pure functions of (primitive, hit point, ray) and are
+//     computed once for the closest hit instead of for every candidate (the reference recomputes them in
+//     every primitive test, GeometryIntersections.cuh:261-282,342-344,629-654);
+//   * the walk is a while-while loop (find next leaf / test its primitives) so lanes of a warp re-converge
+//     between the two phases.
+#pragma once
+#include "vec.cuh"
+#include "../../include/solr_b200_types.h"
+
+// packed per-primitive word: type | fast-transparency class | flags | material id
+#define PM_TYPE(m) ((m) & 0xF)
+#define PM_FAST(m) (((m) >> 4) & 3)      // Material.attributes.x: 0, 1, 2 = any other value
+#define PM_PROCEDURAL(m) (((m) >> 6) & 1) // Material.attributes.y != 0
+#define PM_TRANSPARENT(m) (((m) >> 7) & 1) // Material.transparency != 0
+#define PM_MATERIAL(m) ((m) >> 8)
+
+struct SceneDev
+{
+    const float4* __restrict__ boxes; // [2*nbBoxes] (min.xyz, w0) (max.xyz, w1); leaf: w0=start,w1=count; inner: w0=skip,w1=0
+    int nbBoxes;
+    const float4* __restrict__ geo;   // [4*nbPrimitives] hot geometry, per type (engine.cu packPrimitive)
+    const int* __restrict__ meta;     // [nbPrimitives]
+    const b200_Primitive* __restrict__ prims; // cold: full records, read once per shaded hit
+    int nbPrimitives;
+    const b200_Material* __restrict__ mats;
+    const b200_LightInformation* __restrict__ lights;
+    int lightInfoSize;
+    int nbLamps;
+    const unsigned char* __restrict__ tex;
+    const float* __restrict__ randoms; // randomTableSize + 4 floats (tail zero)
+    int randomTableSize;               // the reference's MAX_BITMAP_SIZE
+    const b200_BoundingBox* __restrict__ rawBoxes; // uncollapsed list, only walked when renderBoxes != 0
+    int nbRawBoxes;
+};
+
+struct RenderParams
+{
+    SceneDev scene;
+    b200_SceneInfo si;
+    b200_PostProcessingInfo pp;
+    float3 eye, target;
+    float4 angles;
+    b200_PostProcessingBuffer* post;
+    int4* ids;
+    unsigned char* bitmap;
+    unsigned int* tileCounter;        // atomic tile queue head
+    unsigned long long* workCounters; // [0] rays, [1] pixels
+    int tilesX, tilesY, nbLocalTiles;
+    int rank, worldSize;
+};
+
+// One frame's parameters live in constant memory (uploaded on the render stream before the launch):
+// every device function reads scene pointers / SceneInfo fields as uniform constant-bank operands, and
+// the two out-of-line walks below need no pointer arguments.
+__constant__ RenderParams cP;
+#define cS (cP.scene)
+#define cSI (cP.si)
+
+struct Ray // direction form used inside a walk (GeometryIntersections.cuh:676-679, :36-44)
+{
+    float3 o, d, nd, inv; // origin, target-origin (not normalised), normalize(d), inverse direction
+};
+
+struct Hit
+{
+    int prim;   // index into the compacted primitive arrays
+    float3 p;   // intersection point
+    int flags;  // bit0: sphere hit from inside ("back"), bit1: plane normal flipped
+};
+
+struct Counters { unsigned int rays; };
+
+SB_DEV void makeRay(Ray& r, float3 origin, float3 dir)
+{
+    r.o = origin; r.d = dir;
+    r.nd = normalize(dir);
+    // GeometryIntersections.cuh:38-40: 1.f (not inf) for zero components
+    r.inv.x = dir.x != 0.f ? 1.f / dir.x : 1.f;
+    r.inv.y = dir.y != 0.f ? 1.f / dir.y : 1.f;
+    r.inv.z = dir.z != 0.f ? 1.f / dir.z : 1.f;
+}
+
+// GeometryIntersections.cuh:52-79.  Same twelve subtract/multiply results and the same comparisons as the
+// reference's sign-indexed corners with early returns, evaluated without branches: a divergent branch
+// inside the walk loop would leave the lanes of a warp un-reconverged for the rest of the walk.
+// (t0 = 0 at every call site, :690,:818.)
+SB_DEV bool slab(const float4 lo, const float4 hi, const Ray& r, const float t1)
+{
+    const bool sx = r.inv.x < 0.f, sy = r.inv.y < 0.f, sz = r.inv.z < 0.f;
+    const float txmin = ((sx ? hi.x : lo.x) - r.o.x) * r.inv.x;
+    const float txmax = ((sx ? lo.x : hi.x) - r.o.x) * r.inv.x;
+    const float tymin = ((sy ? hi.y : lo.y) - r.o.y) * r.inv.y;
+    const float tymax = ((sy ? lo.y : hi.y) - r.o.y) * r.inv.y;
+    const float tzmin = ((sz ? hi.z : lo.z) - r.o.z) * r.inv.z;
+    const float tzmax = ((sz ? lo.z : hi.z) - r.o.z) * r.inv.z;
+    const bool missXY = (txmin > tymax) | (tymin > txmax);
+    const float tmin = (tymin > txmin) ? tymin : txmin;
+    const float tmax = (tymax < txmax) ? tymax : txmax;
+    const bool missZ = (tmin > tzmax) | (tzmin > tmax);
+    const float tmin2 = (tzmin > tmin) ? tzmin : tmin;
+    const float tmax2 = (tzmax < tmax) ? tzmax : tmax;
+    return !missXY & !missZ & (tmin2 < t1) & (tmax2 > 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Primitive tests: "does the ray hit, and where".  Normals are deferred to hitNormal().
+// ---------------------------------------------------------------------------------------------------
+
+// GeometryIntersections.cuh:220-257 (sphere), solve part.  g0 = (centre, radius)
+SB_DEV bool sphereTest(const float4 g0, const Ray& r, const float eps, float3& I, int& flags)
+{
+    const float3 O_C = r.o - xyz(g0);
+    const float3 dir = r.nd;
+    const float a = 2.f * dot(dir, dir);
+    const float b = 2.f * dot(O_C, dir);
+    const float c = dot(O_C, O_C) - (g0.w * g0.w);
+    const float d = b * b - 2.f * a * c;
+    if (d <= 0.f || a == 0.f) return false;
+    const float rt = sqrtf(d);
+    const float t1 = (-b - rt) / a;
+    const float t2 = (-b + rt) / a;
+    if (t1 <= eps && t2 <= eps) return false;
+    float t = 0.f;
+    int back = 0;
+    if (t1 <= eps) { t = t2; back = 1; }
+    else if (t2 <= eps) t = t1;
+    else t = (t1 < t2) ? t1 : t2;
+    if (t < eps) return false;
+    I = r.o + t * dir;
+    flags = back;
+    return true;
+}
+
+// GeometryIntersections.cuh:159-203 (ellipsoid).  size = (g0.w, g1.w, g2.w)
+SB_DEV bool ellipsoidTest(const float4 g0, const float3 g1, const Ray& r, const float eps, float3& I)
+{
+    const float3 O_C = r.o - xyz(g0);
+    const float3 dir = r.nd;
+    const float a = ((dir.x * dir.x) / (g1.x * g1.x)) + ((dir.y * dir.y) / (g1.y * g1.y)) + ((dir.z * dir.z) / (g1.z * g1.z));
+    const float b = ((2.f * O_C.x * dir.x) / (g1.x * g1.x)) + ((2.f * O_C.y * dir.y) / (g1.y * g1.y)) + ((2.f * O_C.z * dir.z) / (g1.z * g1.z));
+    const float c = ((O_C.x * O_C.x) / (g1.x * g1.x)) + ((O_C.y * O_C.y) / (g1.y * g1.y)) + ((O_C.z * O_C.z) / (g1.z * g1.z)) - 1.f;
+    float d = ((b * b) - (4.f * a * c));
+    if (d < 0.f || a == 0.f || b == 0.f || c == 0.f) return false;
+    d = sqrtf(d);
+    const float t1 = (-b + d) / (2.f * a);
+    const float t2 = (-b - d) / (2.f * a);
+    if (t1 <= eps && t2 <= eps) return false;
+    float t = 0.f;
+    if (t1 <= eps) t = t2;
+    else if (t2 <= eps) t = t1;
+    else t = (t1 < t2) ? t1 : t2;
+    if (t < eps) return false;
+    I = r.o + t * dir;
+    return true;
+}
+
+// GeometryIntersections.cuh:293-340 (cylinder) == :358-405 (cone).
+// g0 = (p0, size.x) g1 = (p1, size.y) g3 = (n1 axis, -)
+SB_DEV bool cylinderTest(const float4 g0, const float4 g1, const float4 g3, const Ray& r, const float eps, float3& I)
+{
+    const float3 p0 = xyz(g0), p1 = xyz(g1), n1 = xyz(g3);
+    const float3 O_C = r.o - p0;
+    const float3 dir = r.d;
+    float3 n = cross(dir, n1);
+    const float ln = length(n);
+    if ((ln < eps) && (ln > -eps)) return false;
+    n = normalize(n);
+    const float d = fabsf(dot(O_C, n));
+    if (d > g1.w) return false;
+    float3 O = cross(O_C, n1);
+    const float t = -dot(O, n) / ln;
+    if (t < 0.f) return false;
+    O = normalize(cross(n, n1));
+    const float s = fabsf(sqrtf(g0.w * g0.w - d * d) / dot(dir, O));
+    const float t1 = t - s;
+    const float t2 = t + s;
+    I = r.o + t1 * dir;
+    float3 HB1 = I - p0, HB2 = I - p1;
+    float scale1 = dot(HB1, n1), scale2 = dot(HB2, n1);
+    if (scale1 < eps || scale2 > eps)
+    {
+        I = r.o + t2 * dir;
+        HB1 = I - p0; HB2 = I - p1;
+        scale1 = dot(HB1, n1); scale2 = dot(HB2, n1);
+        if (scale1 < eps || scale2 > eps) return false;
+    }
+    return true;
+}
+
+// GeometryIntersections.cuh:575-626 (triangle), up to the hit point.  The `a + b > 1` branch of the
+// reference builds E21 = p1 - p1 = 0 (:604) so det_ = 0 and it always rejects (:607-608).
+SB_DEV bool triangleTest(const float4 g0, const float4 g1, const float4 g2, const Ray& r, const float eps, float3& I)
+{
+    const float3 p0 = xyz(g0), p1 = xyz(g1), p2 = xyz(g2);
+    const float3 E01 = p1 - p0;
+    const float3 E03 = p2 - p0;
+    const float3 P = cross(r.d, E03);
+    const float det = dot(E01, P);
+    if (fabsf(det) < eps) return false;
+    const float3 T = r.o - p0;
+    const float a = dot(T, P) / det;
+    if (a < 0.f || a > 1.f) return false;
+    const float3 Q = cross(T, E01);
+    const float b = dot(r.d, Q) / det;
+    if (b < 0.f || b > 1.f) return false;
+    if ((a + b) > 1.f)
+    {
+        // det_ = dot(p0 - p1, cross(dir, 0)) = 0 unless a component is non-finite; |0| < eps rejects.
+        if (0.f < eps) return false;
+    }
+    const float t = dot(E03, Q) / det;
+    if (t < 0) return false;
+    I = r.o + t * r.d;
+    return true;
+}
+
+SB_DEV bool wireFrameMapping(float x, float y, int width) // TextureMapping.cuh:449-456
+{
+    const int X = fabsf(x), Y = fabsf(y);
+    return (X % 100 <= width) || (Y % 100 <= width);
+}
+
+// forward: texture mapping used by textured planes inside the intersection test
+__device__ __noinline__ float4 cubeMapping(const b200_Primitive& p, float3 I,
+                                           float3& normal, float4& specular, float4& attributes, float4& adv);
+
+// GeometryIntersections.cuh:424-567.  Rare primitive class (the reference's default transparentColor = 0
+// makes every plane miss, :561-564); reads the cold records.  Kept out of line so it costs the walk no
+// registers.
+__device__ __noinline__ bool planeTest(const int primIdx, const Ray& r, float3& I,
+                                       int& flags, float& shadowIntensity)
+{
+    const b200_Primitive& p = cS.prims[primIdx];
+    const b200_Material& mat = cS.mats[p.materialId];
+    bool collision = false;
+    const float reverted = 1.f; // every call site passes reverse = false (:739-740,:861-862)
+    float3 normal = f3(p.n0.x, p.n0.y, p.n0.z);
+    int flipped = 0;
+    const float3 ro = r.o, rd = r.d;
+    switch (p.type)
+    {
+    case B200_PT_MAGICCARPET:
+    case B200_PT_CHECKBOARD:
+    {
+        I.y = p.p0.y;
+        const float y = ro.y - p.p0.y;
+        if (reverted * rd.y < 0.f && reverted * ro.y > reverted * p.p0.y)
+        {
+            I.x = ro.x + y * rd.x / -rd.y;
+            I.z = ro.z + y * rd.z / -rd.y;
+            collision = fabsf(I.x - p.p0.x) < p.size.x && fabsf(I.z - p.p0.z) < p.size.z;
+        }
+        break;
+    }
+    case B200_PT_XZPLANE:
+    {
+        const float y = ro.y - p.p0.y;
+        if (reverted * rd.y < 0.f && reverted * ro.y > reverted * p.p0.y)
+        {
+            I.x = ro.x + y * rd.x / -rd.y; I.y = p.p0.y; I.z = ro.z + y * rd.z / -rd.y;
+            collision = fabsf(I.x - p.p0.x) < p.size.x && fabsf(I.z - p.p0.z) < p.size.z;
+            if (mat.attributes.z == 2) collision &= wireFrameMapping(I.x, I.z, mat.attributes.w);
+        }
+        if (!collision && reverted * rd.y > 0.f && reverted * ro.y < reverted * p.p0.y)
+        {
+            flipped ^= 1;
+            I.x = ro.x + y * rd.x / -rd.y; I.y = p.p0.y; I.z = ro.z + y * rd.z / -rd.y;
+            collision = fabsf(I.x - p.p0.x) < p.size.x && fabsf(I.z - p.p0.z) < p.size.z;
+            if (mat.attributes.z == 2) collision &= wireFrameMapping(I.x, I.z, mat.attributes.w);
+        }
+        break;
+    }
+    case B200_PT_YZPLANE:
+    {
+        const float x = ro.x - p.p0.x;
+        if (reverted * rd.x < 0.f && reverted * ro.x > reverted * p.p0.x)
+        {
+            I.x = p.p0.x; I.y = ro.y + x * rd.y / -rd.x; I.z = ro.z + x * rd.z / -rd.x;
+            collision = fabsf(I.y - p.p0.y) < p.size.y && fabsf(I.z - p.p0.z) < p.size.z;
+            if (mat.innerIllumination.x != 0.f)
+                collision &= int(fabsf(I.z)) % 4000 < 2000 && int(fabsf(I.y)) % 4000 < 2000;
+            if (mat.attributes.z == 2) collision &= wireFrameMapping(I.y, I.z, mat.attributes.w);
+        }
+        if (!collision && reverted * rd.x > 0.f && reverted * ro.x < reverted * p.p0.x)
+        {
+            flipped ^= 1;
+            I.x = p.p0.x; I.y = ro.y + x * rd.y / -rd.x; I.z = ro.z + x * rd.z / -rd.x;
+            collision = fabsf(I.y - p.p0.y) < p.size.y && fabsf(I.z - p.p0.z) < p.size.z;
+            if (mat.innerIllumination.x != 0.f)
+                collision &= int(fabsf(I.z)) % 4000 < 2000 && int(fabsf(I.y)) % 4000 < 2000;
+            if (mat.attributes.z == 2) collision &= wireFrameMapping(I.y, I.z, mat.attributes.w);
+        }
+        break;
+    }
+    case B200_PT_XYPLANE:
+    case B200_PT_CAMERA:
+    {
+        const float z = ro.z - p.p0.z;
+        if (reverted * rd.z < 0.f && reverted * ro.z > reverted * p.p0.z)
+        {
+            I.z = p.p0.z; I.x = ro.x + z * rd.x / -rd.z; I.y = ro.y + z * rd.y / -rd.z;
+            collision = fabsf(I.x - p.p0.x) < p.size.x && fabsf(I.y - p.p0.y) < p.size.y;
+            if (mat.attributes.z == 2) collision &= wireFrameMapping(I.x, I.y, mat.attributes.w);
+        }
+        if (!collision && reverted * rd.z > 0.f && reverted * ro.z < reverted * p.p0.z)
+        {
+            flipped ^= 1;
+            I.z = p.p0.z; I.x = ro.x + z * rd.x / -rd.z; I.y = ro.y + z * rd.y / -rd.z;
+            collision = fabsf(I.x - p.p0.x) < p.size.x && fabsf(I.y - p.p0.y) < p.size.y;
+            if (mat.attributes.z == 2) collision &= wireFrameMapping(I.x, I.y, mat.attributes.w);
+        }
+        break;
+    }
+    }
+    if (collision)
+    {
+        shadowIntensity = 1.f;
+        float4 color = f4(mat.color.x, mat.color.y, mat.color.z, mat.color.w);
+        if (p.type == B200_PT_CAMERA || mat.textureIds.x != B200_TEXTURE_NONE)
+        {
+            if (flipped) normal = -normal;
+            float4 specular = f4(0.f, 0.f, 0.f, 0.f), attributes = f4(0.f, 0.f, 0.f, 0.f), adv = f4(0.f, 0.f, 0.f, 0.f);
+            color = cubeMapping(p, I, normal, specular, attributes, adv);
+            shadowIntensity = color.w;
+        }
+        if ((color.x + color.y + color.z) / 3.f >= cSI.transparentColor) collision = false;
+    }
+    flags = flipped << 1;
+    return collision;
+}
+
+// One primitive of a leaf: dispatch on type (GeometryIntersections.cuh:712-747).  Returns hit + point.
+SB_DEV bool primitiveTest(const int idx, const int meta, const Ray& r, float3& I,
+                          int& flags, float& planeShadow)
+{
+    const float eps = cSI.geometryEpsilon;
+    const float4* g = cS.geo + 4 * (size_t)idx;
+    flags = 0;
+    if (!cSI.extendedGeometry)
+        return triangleTest(__ldg(g), __ldg(g + 1), __ldg(g + 2), r, eps, I);
+    switch (PM_TYPE(meta))
+    {
+    case B200_PT_ENVIRONMENT:
+    case B200_PT_SPHERE: return sphereTest(__ldg(g), r, eps, I, flags);
+    case B200_PT_CYLINDER:
+    case B200_PT_CONE: return cylinderTest(__ldg(g), __ldg(g + 1), __ldg(g + 3), r, eps, I);
+    case B200_PT_ELLIPSOID:
+    {
+        const float4 g0 = __ldg(g);
+        return ellipsoidTest(g0, f3(g0.w, __ldg(g + 1).w, __ldg(g + 2).w), r, eps, I);
+    }
+    case B200_PT_TRIANGLE: return triangleTest(__ldg(g), __ldg(g + 1), __ldg(g + 2), r, eps, I);
+    default: return planeTest(idx, r, I, flags, planeShadow);
+    }
+}
+
+// Normal (and triangle areas) of an accepted hit — the tail of each reference test:
+// sphere :261-277, ellipsoid :205-210, cylinder/cone :342-344, plane :431,:464, triangle :629-654.
+SB_DEV void hitNormal(const int idx, const int meta, const float3 I, const int flags, const float3 rayNd, float3& normal,
+                      float3& areas)
+{
+    const float4* g = cS.geo + 4 * (size_t)idx;
+    areas = f3(0.f, 0.f, 0.f);
+    const int type = cSI.extendedGeometry ? PM_TYPE(meta) : B200_PT_TRIANGLE;
+    switch (type)
+    {
+    case B200_PT_ENVIRONMENT:
+    case B200_PT_SPHERE:
+    {
+        const float4 g0 = __ldg(g);
+        if (!PM_PROCEDURAL(meta))
+            normal = I - xyz(g0);
+        else
+        {
+            const float sy = __ldg(g + 1).w, sz = __ldg(g + 2).w; // size.y, size.z
+            float3 nc;
+            nc.x = g0.x + 0.008f * g0.w * cosf(cSI.timestamp + I.x);
+            nc.y = g0.y + 0.008f * sy * sinf(cSI.timestamp + I.y);
+            nc.z = g0.z + 0.008f * sz * sinf(cosf(cSI.timestamp + I.z));
+            normal = I - nc;
+        }
+        normal = normalize(normal);
+        if (flags & 1) normal *= -1.f;
+        break;
+    }
+    case B200_PT_ELLIPSOID:
+    {
+        const float4 g0 = __ldg(g);
+        const float3 g1 = f3(g0.w, __ldg(g + 1).w, __ldg(g + 2).w);
+        normal = I - xyz(g0);
+        normal.x = 2.f * normal.x / (g1.x * g1.x);
+        normal.y = 2.f * normal.y / (g1.y * g1.y);
+        normal.z = 2.f * normal.z / (g1.z * g1.z);
+        normal = normalize(normal);
+        break;
+    }
+    case B200_PT_CYLINDER:
+    case B200_PT_CONE:
+    {
+        const float3 n1 = xyz(__ldg(g + 3));
+        const float3 V = I - xyz(__ldg(g + 2));
+        normal = V - n1 * (dot(V, n1) / dot(n1, n1)); // project(), VectorUtils.cuh:92-95
+        normal = normalize(normal);
+        break;
+    }
+    case B200_PT_TRIANGLE:
+    {
+        const float3 p0 = xyz(__ldg(g)), p1 = xyz(__ldg(g + 1)), p2 = xyz(__ldg(g + 2));
+        const b200_Primitive& p = cS.prims[idx];
+        const float3 v0 = p0 - I, v1 = p1 - I, v2 = p2 - I;
+        areas.x = 0.5f * length(cross(v1, v2));
+        areas.y = 0.5f * length(cross(v0, v2));
+        areas.z = 0.5f * length(cross(v0, v1));
+        normal = normalize((f3(p.n0.x, p.n0.y, p.n0.z) * areas.x + f3(p.n1.x, p.n1.y, p.n1.z) * areas.y +
+                            f3(p.n2.x, p.n2.y, p.n2.z) * areas.z) / (areas.x + areas.y + areas.z));
+        const float rr = dot(rayNd, normal);
+        if (rr > 0.f) normal *= -1.f;
+        break;
+    }
+    default:
+    {
+        const b200_Primitive& p = cS.prims[idx];
+        normal = f3(p.n0.x, p.n0.y, p.n0.z);
+        if (flags & 2) normal = -normal;
+    }
+    }
+}
+
+// One walk step over the compacted box list shared by both walks: advance `box` to just past the next
+// leaf this ray enters; returns that leaf's primitive range (count = 0: list exhausted).  The body has no
+// divergent branch other than the loop exit, so a warp stays converged while its lanes step through
+// different boxes.
+SB_DEV int nextLeaf(const float4* __restrict__ boxes, const int nbBoxes, int& box, const Ray& r, const float minDistance, int& start)
+{
+    int count = 0;
+    while (box < nbBoxes)
+    {
+        const float4 lo = __ldg(boxes + 2 * box);
+        const float4 hi = __ldg(boxes + 2 * box + 1);
+        const int w0 = __float_as_int(lo.w), w1 = __float_as_int(hi.w);
+        const bool h = slab(lo, hi, r, minDistance);
+        // hit: step into the subtree / leaf (box + 1); miss: jump over it (leaf: 1, inner: w0)
+        box += (h | (w1 > 0)) ? 1 : w0;
+        if (h & (w1 > 0)) { start = w0; count = w1; break; }
+    }
+    return count;
+}
+
+// GeometryIntersections.cuh:667-772 — closest hit over the compacted box list.  Out of line and by value:
+// one copy of the walk serves the bounce loop, the extra reflected ray and the GI ray, with its own
+// register allocation.  hit.prim = -1: no hit.
+__device__ __noinline__ Hit closestHit(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)
+{
+    Hit hit;
+    hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
+    float minDistance = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
+    Ray r;
+    makeRay(r, origin, target - origin);
+    const float eps = cSI.geometryEpsilon;
+    const float4* __restrict__ boxes = cS.boxes;
+    const int* __restrict__ metas = cS.meta;
+    const int nbBoxes = cS.nbBoxes;
+    int box = 0;
+    while (true)
+    {
+        int start = 0;
+        const int count = nextLeaf(boxes, nbBoxes, box, r, minDistance, start);
+        if (count == 0) break;
+        // the leaf's primitives, in array order (first in order wins ties: strict < at :751)
+        for (int k = 0; k < count; ++k)
+        {
+            const int idx = start + k;
+            const int meta = __ldg(metas + idx);
+            const int fast = PM_FAST(meta);
+            if (fast == 0 || (fast == 1 && currentMaterialId != PM_MATERIAL(meta)))
+            {
+                float3 I;
+                int flags;
+                float planeShadow;
+                if (primitiveTest(idx, meta, r, I, flags, planeShadow))
+                {
+                    const float distance = length(I - r.o);
+                    if (distance > eps && distance < minDistance)
+                    {
+                        minDistance = distance;
+                        hit.prim = idx; hit.p = I; hit.flags = flags;
+                    }
+                }
+            }
+        }
+    }
+    return hit;
+}
+
+// renderBoxes != 0 (debug view, GeometryIntersections.cuh:693-696): every box the ray enters adds its
+// material colour / 200; primitives are never tested, so the ray always "misses".  Walks the raw list.
+__device__ __noinline__ void boxDebugWalk(const float3 origin, const float3 target,
+                                          const int iteration, float4& colorBox)
+{
+    const float minDistance = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
+    Ray r;
+    makeRay(r, origin, target - origin);
+    int box = 0;
+    while (box < cS.nbRawBoxes)
+    {
+        const b200_BoundingBox& b = cS.rawBoxes[box];
+        const float4 lo = f4(b.parameters[0].x, b.parameters[0].y, b.parameters[0].z, 0.f);
+        const float4 hi = f4(b.parameters[1].x, b.parameters[1].y, b.parameters[1].z, 0.f);
+        if (slab(lo, hi, r, minDistance))
+        {
+            const b200_float4 c = cS.mats[b.startIndex % B200_NB_MAX_MATERIALS].color;
+            colorBox += f4(c.x, c.y, c.z, c.w) / 200.f;
+            ++box;
+        }
+        else
+            box += b.indexForNextBox.x;
+    }
+}
+
+// GeometryIntersections.cuh:798-908 — shadow walk: accumulates blocker opacity until it saturates.
+// Returns (tint.xyz, shadow intensity).
+__device__ __noinline__ float4 shadowWalk(const float3 lampCenter, const float3 origin, const int lightId, const int iteration, const int objectId)
+{
+    float result = 0.f;
+    float3 color = f3(0.f, 0.f, 0.f);
+    Ray r;
+    const float3 dirv = lampCenter - origin;
+    makeRay(r, origin + normalize(dirv) * cSI.rayEpsilon, dirv);
+    const float minDistance = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
+    const float eps = cSI.geometryEpsilon;
+    const float shadowLimit = cSI.shadowIntensity;
+    const float lenOL = length(r.d);
+    const float4* __restrict__ boxes = cS.boxes;
+    const int* __restrict__ metas = cS.meta;
+    const int nbBoxes = cS.nbBoxes;
+    const bool extended = cSI.extendedGeometry != 0;
+    int box = 0;
+    while (result < shadowLimit)
+    {
+        int start = 0;
+        const int count = nextLeaf(boxes, nbBoxes, box, r, minDistance, start);
+        if (count == 0) break;
+        for (int k = 0; k < count && result < shadowLimit; ++k)
+        {
+            const int idx = start + k;
+            const int meta = __ldg(metas + idx);
+            if (PM_FAST(meta) != 0) continue;
+            const int origIndex = __ldg(&cS.prims[idx].index);
+            // objectId is a compacted index compared with an original id — as the reference does (:829)
+            if (origIndex == lightId || origIndex == objectId) continue;
+            const int type = extended ? PM_TYPE(meta) : B200_PT_TRIANGLE;
+            // :857-859 ptCamera never shadows; :860-863 ptEnvironment falls to planeIntersection, whose switch has no such case
+            if (type == B200_PT_CAMERA || type == B200_PT_ENVIRONMENT) continue;
+            float3 I;
+            int flags = 0;
+            float shadowIntensity = 1.f;
+            bool hit = primitiveTest(idx, meta, r, I, flags, shadowIntensity);
+            if (hit && type == B200_PT_TRIANGLE && cSI.doubleSidedTriangles)
+                hit = false; // dangling else (:643-647): with processingShadows both arms return false
+            if (hit)
+            {
+                const float l = length(I - r.o);
+                if (l > eps && l < lenOL)
+                {
+                    float3 normal = f3(0.f, 0.f, 0.f), areas;
+                    const bool transparent = PM_TRANSPARENT(meta);
+                    if (transparent) hitNormal(idx, meta, I, flags, r.nd, normal, areas);
+                    if (type == B200_PT_SPHERE)
+                        shadowIntensity = transparent ? (1.f - fabsf(dot(r.nd, normal))) : 1.f; // :280-281
+                    else if (type < B200_PT_CHECKBOARD || type == B200_PT_ELLIPSOID || type == B200_PT_CONE)
+                        shadowIntensity = 1.f;
+                    float ratio = shadowIntensity * shadowLimit;
+                    if (transparent)
+                    {
+                        const b200_Material& m = cS.mats[PM_MATERIAL(meta)];
+                        const float3 O_L = normalize(r.d);
+                        const float a = fabsf(dot(O_L, normal));
+                        const float rr = (m.transparency == 0.f) ? 1.f : (1.f - m.transparency);
+                        ratio *= rr * a;
+                        color.x += ratio * (0.3f - 0.3f * m.color.x);
+                        color.y += ratio * (0.3f - 0.3f * m.color.y);
+                        color.z += ratio * (0.3f - 0.3f * m.color.z);
+                    }
+                    result += ratio;
+                }
+            }
+        }
+    }
+    result = fmaxf(0.f, fminf(result, shadowLimit));
+    return f4(color.x, color.y, color.z, result);
+}

@@ -1,0 +1,40 @@
+// vec.cuh — float3/float4 arithmetic for the engine's device code.
+// Component-wise, left-to-right, so expression shapes (and therefore nvcc's FMA contraction and the
+// --use_fast_math lowering of / sqrtf rsqrtf) match what the reference engine computes with its vector
+// helpers (/root/reference/solr/engines/cuda/helper_math.h:1248-1318: dot, length, normalize = v*rsqrtf(dot)).
+#pragma once
+#include <cuda_runtime.h>
+
+#define SB_DEV __device__ __forceinline__
+
+SB_DEV float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+SB_DEV float4 f4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
+SB_DEV float3 xyz(const float4& a) { return make_float3(a.x, a.y, a.z); }
+SB_DEV float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+SB_DEV float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+SB_DEV float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+SB_DEV float3 operator*(float3 a, float b) { return f3(a.x * b, a.y * b, a.z * b); }
+SB_DEV float3 operator*(float b, float3 a) { return f3(b * a.x, b * a.y, b * a.z); }
+SB_DEV float3 operator/(float3 a, float b) { return f3(a.x / b, a.y / b, a.z / b); }
+SB_DEV void operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
+SB_DEV void operator*=(float3& a, float b) { a.x *= b; a.y *= b; a.z *= b; }
+SB_DEV float4 operator+(float4 a, float4 b) { return f4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+SB_DEV float4 operator-(float4 a, float4 b) { return f4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+SB_DEV float4 operator*(float4 a, float4 b) { return f4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+SB_DEV float4 operator*(float4 a, float b) { return f4(a.x * b, a.y * b, a.z * b, a.w * b); }
+SB_DEV float4 operator*(float b, float4 a) { return f4(b * a.x, b * a.y, b * a.z, b * a.w); }
+SB_DEV float4 operator/(float4 a, float b) { return f4(a.x / b, a.y / b, a.z / b, a.w / b); }
+SB_DEV void operator+=(float4& a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+SB_DEV void operator-=(float4& a, float4 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; a.w -= b.w; }
+SB_DEV void operator-=(float4& a, float b) { a.x -= b; a.y -= b; a.z -= b; a.w -= b; }
+SB_DEV void operator*=(float4& a, float b) { a.x *= b; a.y *= b; a.z *= b; a.w *= b; }
+SB_DEV void operator/=(float4& a, float b) { a.x /= b; a.y /= b; a.z /= b; a.w /= b; }
+SB_DEV float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+SB_DEV float length(float3 v) { return sqrtf(dot(v, v)); }
+SB_DEV float3 normalize(float3 v) { float invLen = rsqrtf(dot(v, v)); return v * invLen; }
+SB_DEV float3 cross(float3 b, float3 c) { return f3(b.y * c.z - b.z * c.y, b.z * c.x - b.x * c.z, b.x * c.y - b.y * c.x); }
+SB_DEV void saturate4(float4& v)
+{
+    v.x = (v.x < 0.f) ? 0.f : v.x; v.y = (v.y < 0.f) ? 0.f : v.y; v.z = (v.z < 0.f) ? 0.f : v.z; v.w = (v.w < 0.f) ? 0.f : v.w;
+    v.x = (v.x > 1.f) ? 1.f : v.x; v.y = (v.y > 1.f) ? 1.f : v.y; v.z = (v.z > 1.f) ? 1.f : v.z; v.w = (v.w > 1.f) ? 1.f : v.w;
+}

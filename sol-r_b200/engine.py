@@ -1,0 +1,173 @@
+"""ctypes binding of the engine's C ABI (include/solr_b200.h) — the calls the reference's engine host
+class makes across its seam (/root/reference/solr/engines/cuda/CudaKernel.cpp:116-145 initializeDevice,
+:174-302 render_begin, :304-313 render_end).  There is no CPU fallback: a missing library or a missing
+GPU raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import wire
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libsolr_b200.so")
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError("CUDA engine library missing: %s (run __graft_entry__.build(); there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    I2, I4, F3, F4 = wire.Int2, wire.Int4, wire.Float3, wire.Float4
+    SI, PPI = wire.SceneInfo, wire.PostProcessingInfo
+    lib.b200_initialize_scene.argtypes = [I2, SI, C.c_int, C.c_int, C.c_int]
+    lib.b200_finalize_scene.argtypes = [I2]
+    lib.b200_reshape_scene.argtypes = [I2, SI]
+    lib.b200_h2d_scene.argtypes = [I2, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.b200_h2d_materials.argtypes = [I2, C.c_void_p, C.c_int]
+    lib.b200_h2d_randoms.argtypes = [I2, C.c_void_p]
+    lib.b200_h2d_textures.argtypes = [I2, C.c_int, C.c_void_p]
+    lib.b200_h2d_lightInformation.argtypes = [I2, C.c_void_p, C.c_int]
+    lib.b200_d2h_bitmap.argtypes = [I2, SI, C.c_void_p, C.c_void_p]
+    lib.b200_render.argtypes = [I2, I4, SI, I4, PPI, F3, F3, F4]
+    lib.b200_last_error.argtypes = [C.c_char_p, C.c_int]
+    lib.b200_last_error.restype = C.c_int
+    lib.b200_set_device.argtypes = [C.c_int]
+    lib.b200_set_stream.argtypes = [C.c_void_p]
+    lib.b200_set_limits.argtypes = [C.c_int, C.c_int]
+    lib.b200_set_partition.argtypes = [C.c_int, C.c_int]
+    lib.b200_device_buffers.argtypes = [C.POINTER(C.c_void_p)] * 3
+    lib.b200_get_counters.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
+    lib.b200_last_render_ms.restype = C.c_float
+    lib.b200_kernel_launches.restype = C.c_ulonglong
+    lib.b200_scene_stats.argtypes = [C.POINTER(C.c_int)] * 4
+    for f in ("b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
+              "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
+              "b200_set_device", "b200_set_stream", "b200_set_limits", "b200_set_partition", "b200_device_buffers",
+              "b200_get_counters", "b200_scene_stats", "b200_synchronize", "b200_clear_error"):
+        getattr(lib, f).restype = None
+    _lib = lib
+    return lib
+
+
+# every symbol include/solr_b200.h declares (checked by tests/test_abi.py without a GPU)
+ABI_SYMBOLS = [
+    "b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
+    "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
+    "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_stream", "b200_set_limits", "b200_set_partition",
+    "b200_device_buffers", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
+    "b200_synchronize",
+]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Engine:
+    """One GPU's engine, driven exactly as CudaKernel drives the reference's (initBuffers -> h2d_* ->
+    cudaRender -> d2h_bitmap).  `arrays` is the dict of flattened wire-format arrays (uint8 views)."""
+
+    OCC = wire.Int2(1, 1)
+
+    def __init__(self, scene_info, device=None, limits=None, rank=0, world=1, stream=None):
+        self.lib = load()
+        if device is not None:
+            self.lib.b200_set_device(device)
+        if limits is not None:
+            self.lib.b200_set_limits(limits[0], limits[1])
+        self.limits = limits or (1920, 1080)
+        self.lib.b200_clear_error()
+        self.lib.b200_set_partition(rank, world)
+        self.lib.b200_initialize_scene(self.OCC, scene_info, 0, 0, 0)
+        if stream is not None:
+            self.lib.b200_set_stream(C.c_void_p(stream))
+        self.lib.b200_reshape_scene(self.OCC, scene_info)
+        self.check()
+        self.objects = wire.Int4(0, 0, 0, 0)
+        self._keep = {}
+
+    def check(self):
+        buf = C.create_string_buffer(256)
+        code = self.lib.b200_last_error(buf, 256)
+        if code != 0:
+            raise EngineError("solr_b200 engine error %d: %s" % (code, buf.value.decode()))
+
+    def upload(self, arrays, randoms=None, textures=None):
+        a = arrays
+        self._keep = {k: np.ascontiguousarray(v) for k, v in a.items() if isinstance(v, np.ndarray)}
+        k = self._keep
+        self.lib.b200_h2d_scene(self.OCC, _ptr(k["boxes"]), a["nbBoxes"], _ptr(k["primitives"]), a["nbPrimitives"],
+                                _ptr(k.get("lamps")) if a.get("nbLamps", 0) else None, a.get("nbLamps", 0))
+        self.lib.b200_h2d_lightInformation(self.OCC, _ptr(k["lightInformation"]) if a["lightInformationSize"] else None,
+                                           a["lightInformationSize"])
+        self.lib.b200_h2d_materials(self.OCC, _ptr(k["materials"]), a["nbMaterials"])
+        if randoms is not None:
+            r = np.ascontiguousarray(randoms, np.float32)
+            assert r.shape[0] >= self.limits[0] * self.limits[1]
+            self.lib.b200_h2d_randoms(self.OCC, _ptr(r))
+        if textures is not None:
+            infos, n = textures
+            self.lib.b200_h2d_textures(self.OCC, n, C.cast(infos, C.c_void_p))
+        self.objects = wire.Int4(a["nbBoxes"], a["nbPrimitives"], a.get("nbLamps", 0), a["lightInformationSize"])
+        self.check()
+
+    def render(self, scene_info, eye, target, angles, post_info=None):
+        """cudaRender: asynchronous on the engine's stream."""
+        pp = post_info or wire.PostProcessingInfo()
+        self.lib.b200_render(self.OCC, wire.Int4(8, 4, 1, 0), scene_info, self.objects, pp,
+                             wire.Float3(*[float(v) for v in eye]), wire.Float3(*[float(v) for v in target]),
+                             wire.Float4(*[float(v) for v in angles]))
+
+    def readback(self, scene_info, bitmap=None, ids=None):
+        """d2h_bitmap into caller-owned host buffers (allocated here if not given)."""
+        W, H = scene_info.size.x, scene_info.size.y
+        if bitmap is None:
+            bitmap = np.zeros((H, W, 3), np.uint8)
+        if ids is None:
+            ids = np.zeros((H, W, 4), np.int32)
+        self.lib.b200_d2h_bitmap(self.OCC, scene_info, _ptr(bitmap), _ptr(ids))
+        self.check()
+        return bitmap, ids
+
+    def read_post_buffer(self, scene_info):
+        """Test hook: the float accumulation buffer, through torch-free cudaMemcpy in the library's runtime."""
+        raise NotImplementedError
+
+    def counters(self, reset=False):
+        r, p = C.c_ulonglong(), C.c_ulonglong()
+        self.lib.b200_get_counters(C.byref(r), C.byref(p), 1 if reset else 0)
+        return int(r.value), int(p.value)
+
+    def last_render_ms(self):
+        return float(self.lib.b200_last_render_ms())
+
+    def kernel_launches(self):
+        return int(self.lib.b200_kernel_launches())
+
+    def scene_stats(self):
+        v = [C.c_int() for _ in range(4)]
+        self.lib.b200_scene_stats(*[C.byref(x) for x in v])
+        return {"boxes_in": v[0].value, "boxes_device": v[1].value, "primitives": v[2].value, "resident_ctas": v[3].value}
+
+    def device_buffers(self):
+        b, i, p = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.lib.b200_device_buffers(C.byref(b), C.byref(i), C.byref(p))
+        return b.value, i.value, p.value
+
+    def set_stream(self, stream):
+        self.lib.b200_set_stream(C.c_void_p(stream) if stream else None)
+
+    def synchronize(self):
+        self.lib.b200_synchronize()
+
+    def close(self):
+        self.lib.b200_finalize_scene(self.OCC)
