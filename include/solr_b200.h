@@ -71,6 +71,9 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
 void b200_set_partition(int rank, int worldSize);
 /* Device pointers of the per-pixel buffers for in-place collectives (NCCL) — valid until reshape/finalize. */
 void b200_device_buffers(void** bitmap, void** primitivesXYIds, void** postProcessingBuffer);
+/* Copies the float accumulation buffer (W*H PostProcessingBuffer) to the host — the state k_default packs
+ * into RGB8; the reference keeps it device-only (CudaRayTracer.cu:38).  Used by parity tests. */
+void b200_d2h_post(b200_SceneInfo sceneInfo, b200_PostProcessingBuffer* postProcessingBuffer);
 /* Work done by b200_render calls since the last reset: rays = box-list walks (closest-hit + shadow),
  * pixels = pixels actually traced.  Synchronises the stream. */
 void b200_get_counters(unsigned long long* rays, unsigned long long* pixels, int reset);

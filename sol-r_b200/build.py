@@ -48,7 +48,9 @@ def build_host(force=False):
     if not os.path.exists(src[0]):
         return None
     if force or _stale(HOST_LIB, src):
-        subprocess.check_call([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB, src[0], "-ldl"])
+        build_engine()
+        subprocess.check_call([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-sign-compare", "-o", HOST_LIB, src[0],
+                               "-L" + CSRC, "-lsolr_b200", "-Wl,-rpath,$ORIGIN"])
     return HOST_LIB
 
 

@@ -642,6 +642,15 @@ void b200_d2h_bitmap(b200_int2, b200_SceneInfo si, b200_BitmapBuffer* bitmap, b2
     CK(cudaStreamSynchronize(G.stream));
 }
 
+void b200_d2h_post(b200_SceneInfo si, b200_PostProcessingBuffer* post)
+{
+    if (!G.dPost || !ensureDevice()) { latch(-4, "b200_d2h_post", "reshape_scene not called"); return; }
+    const size_t px = (size_t)si.size.x * si.size.y;
+    if (px > G.pixelsCap) { latch(-6, "b200_d2h_post", "frame larger than the limits"); return; }
+    CK(cudaStreamSynchronize(G.stream));
+    CK(cudaMemcpy(post, G.dPost, px * sizeof(b200_PostProcessingBuffer), cudaMemcpyDeviceToHost));
+}
+
 void b200_device_buffers(void** bitmap, void** ids, void** post)
 {
     if (bitmap) *bitmap = G.dBitmap;

@@ -1,0 +1,763 @@
+// scene_host.cpp — see scene_host.h.  Literal restatement of the reference's host-side scene container,
+// grid-hierarchy builder and frame protocol (paths relative to /root/reference/solr/engines/).
+#include "scene_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <random>
+
+namespace solr_b200
+{
+namespace
+{
+const unsigned int AABB_MAGIC_NUMBER = 6400; // GPUKernel.cpp:69
+const size_t REF_NB_MAX_BOXES = 2500000;     // Consts.h:32
+const size_t REF_NB_MAX_PRIMITIVES = 2500000; // Consts.h:33
+const int NB_MAX_LAMPS = 512;                // Consts.h:34
+
+b200_float3 v3(float x, float y, float z) { b200_float3 r = {x, y, z}; return r; }
+b200_float3 min2(b200_float3 a, b200_float3 b) { return v3(std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z)); }
+b200_float3 max2(b200_float3 a, b200_float3 b) { return v3(std::max(a.x, b.x), std::max(a.y, b.y), std::max(a.z, b.z)); }
+b200_float3 min3(b200_float3 a, b200_float3 b, b200_float3 c)
+{
+    return v3(std::min(std::min(a.x, b.x), c.x), std::min(std::min(a.y, b.y), c.y), std::min(std::min(a.z, b.z), c.z));
+}
+b200_float3 max3(b200_float3 a, b200_float3 b, b200_float3 c)
+{
+    return v3(std::max(std::max(a.x, b.x), c.x), std::max(std::max(a.y, b.y), c.y), std::max(std::max(a.z, b.z), c.z));
+}
+void normalizeVector(b200_float3& v) // GPUKernel.cpp:142-151
+{
+    float l = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+    if (l != 0.f) { v.x /= l; v.y /= l; v.z /= l; }
+}
+b200_float3 crossProduct(const b200_float3& b, const b200_float3& c) // GPUKernel.cpp:153-160
+{
+    return v3(b.y * c.z - b.z * c.y, b.z * c.x - b.x * c.z, b.x * c.y - b.y * c.x);
+}
+} // namespace
+
+SceneHost::SceneHost(const b200_SceneInfo& sceneInfo)
+    : m_sceneInfo(sceneInfo), m_treeDepth(2), m_nbActiveTextures(0), m_nbActiveBoxes(0), m_nbActivePrimitives(0),
+      m_nbActiveLamps(0), m_nbActiveMaterials(-1), m_lightInformationSize(0), m_maxBoxes(REF_NB_MAX_BOXES),
+      m_maxPrimitives(REF_NB_MAX_PRIMITIVES), m_primitivesTransfered(false), m_materialsTransfered(false),
+      m_texturesTransfered(false), m_randomsTransfered(false), m_refresh(true), m_deviceInitialised(false),
+      m_maxWidth(B200_REF_MAX_BITMAP_WIDTH), m_maxHeight(B200_REF_MAX_BITMAP_HEIGHT), m_rank(0), m_world(1), m_device(-1)
+{
+    memset(&m_postProcessingInfo, 0, sizeof(m_postProcessingInfo));
+    m_viewPos = v3(0.f, 0.f, 0.f);
+    m_viewDir = v3(0.f, 0.f, 0.f);
+    m_angles.x = m_angles.y = m_angles.z = m_angles.w = 0.f;
+    // The reference never initialises m_minPos/m_maxPos before the first scene (only cleanup() does,
+    // GPUKernel.cpp:394-399); its ~1.6 MB kernel object comes from fresh zero pages, so they start at 0.
+    m_minPos = v3(0.f, 0.f, 0.f);
+    m_maxPos = v3(0.f, 0.f, 0.f);
+    b200_Material zero;
+    memset(&zero, 0, sizeof(zero));
+    m_hMaterials.assign(B200_NB_MAX_MATERIALS + 1, zero); // GPUKernel.cpp:307-308
+    m_textures.resize(B200_NB_MAX_TEXTURES);
+    for (auto& t : m_textures) { t.offset = 0; t.size.x = t.size.y = t.size.z = 0; }
+}
+
+SceneHost::~SceneHost()
+{
+    if (m_deviceInitialised)
+    {
+        b200_int2 occ = {1, 1};
+        b200_finalize_scene(occ);
+    }
+}
+
+void SceneHost::setCamera(const b200_float3& eye, const b200_float3& dir, const b200_float4& angles) // GPUKernel.cpp:481-493
+{
+    m_viewPos = eye; m_viewDir = dir; m_angles = angles;
+    m_refresh = true;
+}
+
+int SceneHost::addPrimitive(int type) // GPUKernel.cpp:495-516
+{
+    HostPrimitive p;
+    memset(&p, 0, sizeof(p));
+    p.type = type;
+    const int index = static_cast<int>(m_primitives.size());
+    m_primitives[index] = p;
+    return index;
+}
+
+// GPUKernel.cpp:540-684
+void SceneHost::setPrimitive(int index, float x0, float y0, float z0, float x1, float y1, float z1, float x2, float y2, float z2,
+                             float w, float h, float d, int materialId)
+{
+    const float scale = 1.f;
+    m_primitivesTransfered = false;
+    if (!(index >= 0 && (size_t)index <= m_primitives.size()))
+    {
+        fprintf(stderr, "[solr_b200] SceneHost::setPrimitive: out of bounds (%d)\n", index);
+        return;
+    }
+    HostPrimitive& p = m_primitives[index];
+    p.p0 = v3(x0 * scale, y0 * scale, z0 * scale);
+    p.p1 = v3(x1 * scale, y1 * scale, z1 * scale);
+    p.p2 = v3(x2 * scale, y2 * scale, z2 * scale);
+    p.size = v3(w * scale, h * scale, d * scale);
+    p.n0 = p.n1 = p.n2 = v3(0.f, 0.f, 0.f);
+    p.vt0.x = p.vt0.y = p.vt1.x = p.vt1.y = p.vt2.x = p.vt2.y = 0.f;
+    p.materialId = materialId;
+    switch (p.type)
+    {
+    case B200_PT_SPHERE: p.size = v3(w * scale, w * scale, w * scale); break;
+    case B200_PT_ELLIPSOID: p.size = v3(w * scale, h * scale, d * scale); break;
+    case B200_PT_CYLINDER:
+    case B200_PT_CONE:
+    {
+        b200_float3 axis = v3(x1 * scale - x0 * scale, y1 * scale - y0 * scale, z1 * scale - z0 * scale);
+        float len = sqrt(axis.x * axis.x + axis.y * axis.y + axis.z * axis.z);
+        if (len != 0.f) { axis.x /= len; axis.y /= len; axis.z /= len; }
+        p.n1 = axis;
+        p.p2 = v3((x0 * scale + x1 * scale) / 2.f, (y0 * scale + y1 * scale) / 2.f, (z0 * scale + z1 * scale) / 2.f);
+        p.size = v3(w * scale, w * scale, w * scale);
+        break;
+    }
+    case B200_PT_XYPLANE: p.n0 = v3(0.f, 0.f, 1.f); p.n1 = p.n0; p.n2 = p.n0; break;
+    case B200_PT_YZPLANE: p.n0 = v3(1.f, 0.f, 0.f); p.n1 = p.n0; p.n2 = p.n0; break;
+    case B200_PT_XZPLANE:
+    case B200_PT_CHECKBOARD: p.n0 = v3(0.f, 1.f, 0.f); p.n1 = p.n0; p.n2 = p.n0; break;
+    case B200_PT_TRIANGLE:
+    {
+        b200_float3 v0 = v3(p.p1.x - p.p0.x, p.p1.y - p.p0.y, p.p1.z - p.p0.z);
+        normalizeVector(v0);
+        b200_float3 v1 = v3(p.p2.x - p.p0.x, p.p2.y - p.p0.y, p.p2.z - p.p0.z);
+        normalizeVector(v1);
+        p.n0 = crossProduct(v0, v1);
+        normalizeVector(p.n0);
+        p.n1 = p.n0; p.n2 = p.n0;
+        break;
+    }
+    }
+    // scene bounds grow with p0 only (GPUKernel.cpp:670-678)
+    m_minPos = v3(std::min(x0 * scale, m_minPos.x), std::min(y0 * scale, m_minPos.y), std::min(z0 * scale, m_minPos.z));
+    m_maxPos = v3(std::max(x0 * scale, m_maxPos.x), std::max(y0 * scale, m_maxPos.y), std::max(z0 * scale, m_maxPos.z));
+}
+
+void SceneHost::setPrimitiveNormals(unsigned index, b200_float3 n0, b200_float3 n1, b200_float3 n2) // GPUKernel.cpp:714-727
+{
+    if (index < m_primitives.size())
+    {
+        HostPrimitive& p = m_primitives[index];
+        normalizeVector(n0); p.n0 = n0;
+        normalizeVector(n1); p.n1 = n1;
+        normalizeVector(n2); p.n2 = n2;
+        m_primitivesTransfered = false;
+    }
+}
+
+void SceneHost::setPrimitiveTextureCoordinates(unsigned index, b200_float2 vt0, b200_float2 vt1, b200_float2 vt2) // :703-712
+{
+    if (index < m_primitives.size())
+    {
+        HostPrimitive& p = m_primitives[index];
+        p.vt0 = vt0; p.vt1 = vt1; p.vt2 = vt2;
+        m_primitivesTransfered = false;
+    }
+}
+
+int SceneHost::addMaterial() { return ++m_nbActiveMaterials; } // GPUKernel.cpp:1761-1767
+
+void SceneHost::setMaterial(unsigned index, const b200_Material& material) // GPUKernel.cpp:1769-1776
+{
+    if (index < (unsigned)B200_NB_MAX_MATERIALS) { m_hMaterials[index] = material; m_materialsTransfered = false; }
+}
+
+// GPUKernel.cpp:1778-1909
+void SceneHost::setMaterial(unsigned index, float r, float g, float b, float noise, float reflection, float refraction,
+                            bool procedural, bool wireframe, int wireframeWidth, float transparency, float opacity,
+                            int diffuseTextureId, int normalTextureId, int bumpTextureId, int specularTextureId,
+                            int reflectionTextureId, int transparentTextureId, int ambientOcclusionTextureId, float specValue,
+                            float specPower, float specCoef, float innerIllumination, float illuminationDiffusion,
+                            float illuminationPropagation, bool fastTransparency)
+{
+    if (index >= (unsigned)B200_NB_MAX_MATERIALS)
+    {
+        fprintf(stderr, "[solr_b200] SceneHost::setMaterial: out of bounds (%u)\n", index);
+        return;
+    }
+    b200_Material& m = m_hMaterials[index];
+    m.color.x = r; m.color.y = g; m.color.z = b; m.color.w = 0.f;
+    m.specular.x = specValue; m.specular.y = specPower; m.specular.z = 0.f; m.specular.w = specCoef;
+    m.innerIllumination.x = innerIllumination; m.innerIllumination.y = illuminationDiffusion;
+    m.innerIllumination.z = illuminationPropagation; m.innerIllumination.w = noise;
+    m.reflection = reflection; m.refraction = refraction; m.transparency = transparency; m.opacity = opacity;
+    m.attributes.x = fastTransparency ? 1 : 0;
+    m.attributes.y = procedural ? 1 : 0;
+    m.attributes.z = wireframe ? ((wireframeWidth == 0) ? 1 : 2) : 0;
+    m.attributes.w = wireframeWidth;
+    m.textureMapping.x = 1; m.textureMapping.y = 1; m.textureMapping.z = B200_TEXTURE_NONE; m.textureMapping.w = 0;
+    m.textureIds.x = diffuseTextureId; m.textureIds.y = normalTextureId; m.textureIds.z = bumpTextureId; m.textureIds.w = specularTextureId;
+    m.advancedTextureIds.x = reflectionTextureId; m.advancedTextureIds.y = transparentTextureId;
+    m.advancedTextureIds.z = ambientOcclusionTextureId; m.advancedTextureIds.w = B200_TEXTURE_NONE;
+    m.advancedTextureOffset.x = m.advancedTextureOffset.y = m.advancedTextureOffset.z = m.advancedTextureOffset.w = 0;
+    m.mappingOffset.x = 1.f; m.mappingOffset.y = 1.f;
+    auto off = [&](int id) { return (id == B200_TEXTURE_NONE) ? 0 : m_textures[id].offset; };
+    if (diffuseTextureId >= 0 && diffuseTextureId < m_nbActiveTextures)
+    {
+        m.textureMapping.x = m_textures[diffuseTextureId].size.x;
+        m.textureMapping.y = m_textures[diffuseTextureId].size.y;
+        m.textureMapping.w = m_textures[diffuseTextureId].size.z;
+        m.textureMapping.z = B200_TEXTURE_NONE;
+        m.textureOffset.x = m_textures[diffuseTextureId].offset;
+        m.textureOffset.y = off(normalTextureId);
+        m.textureOffset.z = off(bumpTextureId);
+        m.textureOffset.w = off(specularTextureId);
+        m.advancedTextureOffset.x = off(reflectionTextureId);
+        m.advancedTextureOffset.y = off(transparentTextureId);
+        m.advancedTextureOffset.z = off(ambientOcclusionTextureId);
+    }
+    else
+    {
+        // "computed textures" branch — also taken by every untextured material (:1886-1900)
+        m.textureMapping.x = 40000; m.textureMapping.y = 40000; m.textureMapping.z = B200_TEXTURE_NONE; m.textureMapping.w = 3;
+        m.textureIds.x = diffuseTextureId; m.textureIds.y = B200_TEXTURE_NONE; m.textureIds.z = B200_TEXTURE_NONE; m.textureIds.w = B200_TEXTURE_NONE;
+        m.textureOffset.x = m.textureOffset.y = m.textureOffset.z = m.textureOffset.w = 0;
+    }
+    m_materialsTransfered = false;
+}
+
+// GPUKernel.cpp:2017-2033 + processTextureOffsets :2691-2705
+void SceneHost::setTexture(int index, const unsigned char* texels, int width, int height, int depth)
+{
+    if (index < 0 || index >= B200_NB_MAX_TEXTURES) return;
+    if (index >= m_nbActiveTextures) ++m_nbActiveTextures;
+    Texture& t = m_textures[index];
+    t.texels.assign(texels, texels + (size_t)width * height * depth);
+    t.size.x = width; t.size.y = height; t.size.z = depth;
+    realignTexturesAndMaterials();
+    m_texturesTransfered = false;
+}
+
+// GPUKernel.cpp:2238-2340.  The reference also runs this over untextured materials, where it indexes
+// m_hTextures[-1] (:2284-2289, out of bounds); those materials never read the fields it writes, so only
+// textured and fractal materials are touched here.
+void SceneHost::realignTexturesAndMaterials()
+{
+    int totalSize = 0;
+    for (auto& t : m_textures)
+    {
+        if (!t.texels.empty()) { t.offset = totalSize; totalSize += t.size.x * t.size.y * t.size.z; }
+        else t.offset = 0;
+    }
+    auto off = [&](int id) { return (id == B200_TEXTURE_NONE || id < 0) ? 0 : m_textures[id].offset; };
+    for (int i = 0; i < m_nbActiveMaterials; ++i)
+    {
+        b200_Material& m = m_hMaterials[i];
+        const int diffuse = m.textureIds.x;
+        if (diffuse == B200_TEXTURE_MANDELBROT || diffuse == B200_TEXTURE_JULIA)
+        {
+            m.textureMapping.x = 40000; m.textureMapping.y = 40000; m.textureMapping.z = B200_TEXTURE_NONE; m.textureMapping.w = 3;
+            m.textureIds.y = m.textureIds.z = m.textureIds.w = B200_TEXTURE_NONE;
+            m.textureOffset.x = m.textureOffset.y = m.textureOffset.z = m.textureOffset.w = 0;
+            m.advancedTextureIds.x = m.advancedTextureIds.y = m.advancedTextureIds.z = m.advancedTextureIds.w = B200_TEXTURE_NONE;
+            m.advancedTextureOffset.x = m.advancedTextureOffset.y = m.advancedTextureOffset.z = m.advancedTextureOffset.w = 0;
+        }
+        else if (diffuse >= 0 && diffuse < m_nbActiveTextures)
+        {
+            m.textureMapping.x = m_textures[diffuse].size.x;
+            m.textureMapping.y = m_textures[diffuse].size.y;
+            m.textureMapping.z = B200_TEXTURE_NONE;
+            m.textureMapping.w = m_textures[diffuse].size.z;
+            m.textureOffset.x = m_textures[diffuse].offset;
+            m.textureOffset.y = off(m.textureIds.y);
+            m.textureOffset.z = off(m.textureIds.z);
+            m.textureOffset.w = off(m.textureIds.w);
+            m.advancedTextureOffset.x = off(m.advancedTextureIds.x);
+            m.advancedTextureOffset.y = off(m.advancedTextureIds.y);
+            m.mappingOffset.x = 1.f; m.mappingOffset.y = 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// grid hierarchy (GPUKernel.cpp:741-1083)
+// ---------------------------------------------------------------------------------------------------
+bool SceneHost::updateBoundingBox(HostBox& box) // :741-839
+{
+    bool result = false;
+    b200_float3 corner0, corner1;
+    box.parameters[0] = v3(1000000, 1000000, 1000000);
+    box.parameters[1] = v3(-1000000, -1000000, -1000000);
+    for (const auto& p : box.primitives)
+    {
+        HostPrimitive& primitive = m_primitives[p];
+        result = (m_hMaterials[primitive.materialId].innerIllumination.x != 0.f);
+        switch (primitive.type)
+        {
+        case B200_PT_TRIANGLE: corner0 = min3(primitive.p0, primitive.p1, primitive.p2); corner1 = max3(primitive.p0, primitive.p1, primitive.p2); break;
+        case B200_PT_CYLINDER: corner0 = min2(primitive.p0, primitive.p1); corner1 = max2(primitive.p0, primitive.p1); break;
+        default: corner0 = primitive.p0; corner1 = primitive.p0; break;
+        }
+        b200_float3 p0, p1;
+        p0.x = (corner0.x <= corner1.x) ? corner0.x : corner1.x;
+        p0.y = (corner0.y <= corner1.y) ? corner0.y : corner1.y;
+        p0.z = (corner0.z <= corner1.z) ? corner0.z : corner1.z;
+        p1.x = (corner0.x > corner1.x) ? corner0.x : corner1.x;
+        p1.y = (corner0.y > corner1.y) ? corner0.y : corner1.y;
+        p1.z = (corner0.z > corner1.z) ? corner0.z : corner1.z;
+        switch (primitive.type)
+        {
+        case B200_PT_CYLINDER:
+        case B200_PT_SPHERE:
+        case B200_PT_CONE:
+            p0.x -= primitive.size.x; p0.y -= primitive.size.x; p0.z -= primitive.size.x;
+            p1.x += primitive.size.x; p1.y += primitive.size.x; p1.z += primitive.size.x;
+            break;
+        default:
+            p0.x -= primitive.size.x; p0.y -= primitive.size.y; p0.z -= primitive.size.z;
+            p1.x += primitive.size.x; p1.y += primitive.size.y; p1.z += primitive.size.z;
+            break;
+        }
+        if (p0.x < box.parameters[0].x) box.parameters[0].x = p0.x;
+        if (p0.y < box.parameters[0].y) box.parameters[0].y = p0.y;
+        if (p0.z < box.parameters[0].z) box.parameters[0].z = p0.z;
+        if (p1.x > box.parameters[1].x) box.parameters[1].x = p1.x;
+        if (p1.y > box.parameters[1].y) box.parameters[1].y = p1.y;
+        if (p1.z > box.parameters[1].z) box.parameters[1].z = p1.z;
+    }
+    box.center.x = (box.parameters[0].x + box.parameters[1].x) / 2.f;
+    box.center.y = (box.parameters[0].y + box.parameters[1].y) / 2.f;
+    box.center.z = (box.parameters[0].z + box.parameters[1].z) / 2.f;
+    return result;
+}
+
+void SceneHost::updateOutterBoundingBox(HostBox& outterBox, int depth) // :841-892
+{
+    const float vd = m_sceneInfo.viewDistance;
+    outterBox.parameters[0] = v3(vd, vd, vd);
+    outterBox.parameters[1] = v3(-vd, -vd, -vd);
+    for (const auto& p : outterBox.primitives)
+    {
+        HostBox& box = m_boundingBoxes[depth][p]; // operator[]: a missing key is created empty, as in the reference
+        if (outterBox.parameters[0].x > box.parameters[0].x) outterBox.parameters[0].x = box.parameters[0].x;
+        if (outterBox.parameters[0].y > box.parameters[0].y) outterBox.parameters[0].y = box.parameters[0].y;
+        if (outterBox.parameters[0].z > box.parameters[0].z) outterBox.parameters[0].z = box.parameters[0].z;
+        if (outterBox.parameters[1].x < box.parameters[1].x) outterBox.parameters[1].x = box.parameters[1].x;
+        if (outterBox.parameters[1].y < box.parameters[1].y) outterBox.parameters[1].y = box.parameters[1].y;
+        if (outterBox.parameters[1].z < box.parameters[1].z) outterBox.parameters[1].z = box.parameters[1].z;
+    }
+    outterBox.center.x = (outterBox.parameters[0].x + outterBox.parameters[1].x) / 2.f;
+    outterBox.center.y = (outterBox.parameters[0].y + outterBox.parameters[1].y) / 2.f;
+    outterBox.center.z = (outterBox.parameters[0].z + outterBox.parameters[1].z) / 2.f;
+}
+
+void SceneHost::resetBoxes(bool resetPrimitives) // :894-901
+{
+    if (resetPrimitives)
+        for (size_t i = 0; i < m_boundingBoxes[0].size(); ++i) resetBox(m_boundingBoxes[0][(unsigned)i], resetPrimitives);
+    else
+        m_boundingBoxes[0].clear();
+}
+
+void SceneHost::resetBox(HostBox& box, bool resetPrimitives) // :903-917
+{
+    if (resetPrimitives) { box.primitives.clear(); box.indexForNextBox = 1; }
+    const float vd = m_sceneInfo.viewDistance;
+    box.parameters[0] = v3(vd, vd, vd);
+    box.parameters[1] = v3(-vd, -vd, -vd);
+}
+
+void SceneHost::processBoxes(const int boxSize) // :919-992 (simulate == false)
+{
+    b200_float3 boxSteps;
+    boxSteps.x = (m_maxPos.x - m_minPos.x) / boxSize;
+    boxSteps.y = (m_maxPos.y - m_minPos.y) / boxSize;
+    boxSteps.z = (m_maxPos.z - m_minPos.z) / boxSize;
+    boxSteps.x = (boxSteps.x == 0.f) ? 1 : boxSteps.x;
+    boxSteps.y = (boxSteps.y == 0.f) ? 1 : boxSteps.y;
+    boxSteps.z = (boxSteps.z == 0.f) ? 1 : boxSteps.z;
+    const float vd = m_sceneInfo.viewDistance;
+    unsigned int p = 0;
+    for (const auto& prim : m_primitives)
+    {
+        const HostPrimitive& primitive = prim.second;
+        const b200_float3& center = primitive.p0;
+        // unsigned arithmetic: the key wraps modulo 2^32 for X >= 105 (:938-941)
+        unsigned int X = static_cast<int>((center.x - m_minPos.x) / boxSteps.x);
+        unsigned int Y = static_cast<int>((center.y - m_minPos.y) / boxSteps.y);
+        unsigned int Z = static_cast<int>((center.z - m_minPos.z) / boxSteps.z);
+        unsigned int B = 1 + 1000 * (X * boxSize * boxSize + Y * boxSize + Z);
+        if (m_boundingBoxes[0].find(B) == m_boundingBoxes[0].end())
+        {
+            HostBox box;
+            box.parameters[0] = v3(vd, vd, vd);
+            box.parameters[1] = v3(-vd, -vd, -vd);
+            box.center = v3(0.f, 0.f, 0.f);
+            box.indexForNextBox = 1;
+            m_boundingBoxes[0].insert(std::make_pair(B, box));
+        }
+        if (m_hMaterials[primitive.materialId].innerIllumination.x != 0.f)
+            m_boundingBoxes[m_treeDepth][0].primitives.push_back(p); // lights: first box of the top level
+        else
+            m_boundingBoxes[0][B].primitives.push_back(p);
+        ++p;
+    }
+    for (auto& box : m_boundingBoxes[0]) updateBoundingBox(box.second);
+}
+
+void SceneHost::processOutterBoxes(const int boxSize, const int depth) // :994-1039
+{
+    b200_float3 boxSteps;
+    boxSteps.x = (m_maxPos.x - m_minPos.x) / boxSize;
+    boxSteps.y = (m_maxPos.y - m_minPos.y) / boxSize;
+    boxSteps.z = (m_maxPos.z - m_minPos.z) / boxSize;
+    boxSteps.x = (boxSteps.x == 0.f) ? 1 : boxSteps.x;
+    boxSteps.y = (boxSteps.y == 0.f) ? 1 : boxSteps.y;
+    boxSteps.z = (boxSteps.z == 0.f) ? 1 : boxSteps.z;
+    const float vd = m_sceneInfo.viewDistance;
+    for (const auto& box : m_boundingBoxes[depth - 1])
+    {
+        const b200_float3& center = box.second.center;
+        int X = static_cast<int>((center.x - m_minPos.x) / boxSteps.x);
+        int Y = static_cast<int>((center.y - m_minPos.y) / boxSteps.y);
+        int Z = static_cast<int>((center.z - m_minPos.z) / boxSteps.z);
+        // int arithmetic in the reference (:1012-1014); it overflows for large grids, so wrap explicitly
+        const uint32_t bs = (uint32_t)boxSize;
+        uint32_t Bu = (uint32_t)X * bs * bs + (uint32_t)Y * bs + (uint32_t)Z;
+        Bu += 1; // key 0 holds the lights
+        HostBox& ob = m_boundingBoxes[depth][Bu];
+        ob.parameters[0] = v3(vd, vd, vd);
+        ob.parameters[1] = v3(-vd, -vd, -vd);
+        ob.primitives.push_back(box.first);
+    }
+    for (auto& box : m_boundingBoxes[depth]) updateOutterBoundingBox(box.second, depth - 1);
+}
+
+int SceneHost::compactBoxes(bool reconstructBoxes) // :1041-1083
+{
+    m_primitivesTransfered = false;
+    if (reconstructBoxes)
+    {
+        resetBox(m_boundingBoxes[m_treeDepth][0], true);
+        const int gridGranularity = 2, gridDivider = 4;
+        m_treeDepth = 0;
+        int nbBoxes = static_cast<int>(m_primitives.size());
+        while (nbBoxes > gridGranularity) { ++m_treeDepth; nbBoxes /= gridDivider; }
+        processBoxes(AABB_MAGIC_NUMBER);
+        m_treeDepth = 0;
+        nbBoxes = static_cast<int>(m_primitives.size());
+        do
+        {
+            ++m_treeDepth;
+            processOutterBoxes(nbBoxes, m_treeDepth);
+            nbBoxes /= gridDivider;
+        } while (nbBoxes > gridGranularity);
+    }
+    streamDataToGPU();
+    return m_nbActiveBoxes;
+}
+
+void SceneHost::emitPrimitive(long id) // :1116-1135, :1199-1212
+{
+    HostPrimitive& primitive = m_primitives[(unsigned)id];
+    b200_Primitive out;
+    memset(&out, 0, sizeof(out));
+    out.index = (int)id;
+    out.type = primitive.type;
+    out.p0 = primitive.p0; out.p1 = primitive.p1; out.p2 = primitive.p2;
+    out.n0 = primitive.n0; out.n1 = primitive.n1; out.n2 = primitive.n2;
+    out.size = primitive.size;
+    out.materialId = primitive.materialId;
+    out.vt0 = primitive.vt0; out.vt1 = primitive.vt1; out.vt2 = primitive.vt2;
+    m_hPrimitives.push_back(out);
+    ++m_nbActivePrimitives;
+}
+
+void SceneHost::recursiveDataStreamToGPU(const int depth, std::vector<long>& elements) // :1085-1149
+{
+    for (const auto& element : elements)
+    {
+        HostBox& box = m_boundingBoxes[depth][(unsigned)element];
+        if (box.primitives.size() != 0 && (size_t)m_nbActiveBoxes < m_maxBoxes)
+        {
+            const int boxIndex = m_nbActiveBoxes;
+            b200_BoundingBox out;
+            memset(&out, 0, sizeof(out));
+            out.parameters[0] = box.parameters[0];
+            out.parameters[1] = box.parameters[1];
+            out.nbPrimitives = (depth == 0) ? static_cast<int>(box.primitives.size()) : 0;
+            out.startIndex = (depth == 0) ? m_nbActivePrimitives : depth;
+            m_hBoundingBoxes.push_back(out);
+            ++m_nbActiveBoxes;
+            if (depth == 0)
+            {
+                for (long id : box.primitives)
+                    if ((size_t)id < m_maxPrimitives && (size_t)m_nbActivePrimitives < m_maxPrimitives) emitPrimitive(id);
+            }
+            else
+                recursiveDataStreamToGPU(depth - 1, box.primitives);
+            m_hBoundingBoxes[boxIndex].indexForNextBox.x = (depth == 0) ? 1 : m_nbActiveBoxes - boxIndex;
+        }
+    }
+}
+
+void SceneHost::streamDataToGPU() // :1151-1281
+{
+    m_primitivesTransfered = false;
+    m_nbActiveBoxes = 0; m_nbActivePrimitives = 0; m_nbActiveLamps = 0;
+    m_hBoundingBoxes.clear(); m_hPrimitives.clear(); m_hLamps.clear();
+    const float vd = m_sceneInfo.viewDistance;
+    const int maxDepth = (int)m_treeDepth;
+    bool first = true;
+    for (auto& entry : m_boundingBoxes[maxDepth])
+    {
+        HostBox& box = entry.second;
+        const int boxIndex = m_nbActiveBoxes;
+        b200_BoundingBox out;
+        memset(&out, 0, sizeof(out));
+        out.parameters[0] = box.parameters[0];
+        out.parameters[1] = box.parameters[1];
+        out.nbPrimitives = 0;
+        out.startIndex = maxDepth;
+        if (first)
+        {
+            // box 0 of the top level holds the lights, with bounds +-viewDistance (:1177-1190)
+            m_lightInformationSize = 0;
+            m_lightInformation.clear();
+            out.parameters[0] = v3(-vd, -vd, -vd);
+            out.parameters[1] = v3(vd, vd, vd);
+            out.nbPrimitives = static_cast<int>(box.primitives.size());
+            out.startIndex = 0;
+            m_hBoundingBoxes.push_back(out);
+            for (long id : box.primitives)
+            {
+                emitPrimitive(id);
+                const HostPrimitive& primitive = m_primitives[(unsigned)id];
+                const b200_Material& material = m_hMaterials[primitive.materialId];
+                b200_LightInformation li;
+                memset(&li, 0, sizeof(li));
+                li.primitiveId = (int)id;
+                li.materialId = primitive.materialId;
+                li.location = primitive.p0;
+                li.color.x = material.color.x; li.color.y = material.color.y; li.color.z = material.color.z;
+                li.color.w = material.innerIllumination.x;
+                if (m_lightInformationSize < B200_NB_MAX_LIGHTINFORMATIONS) m_lightInformation.push_back(li);
+                if (m_nbActiveLamps < NB_MAX_LAMPS) m_hLamps.push_back((int)id);
+                ++m_nbActiveLamps;
+                ++m_lightInformationSize;
+            }
+        }
+        else
+            m_hBoundingBoxes.push_back(out);
+        first = false;
+        ++m_nbActiveBoxes;
+        if (maxDepth > 0) recursiveDataStreamToGPU(maxDepth - 1, box.primitives);
+        m_hBoundingBoxes[boxIndex].indexForNextBox.x = m_nbActiveBoxes - boxIndex;
+    }
+    if ((size_t)m_nbActivePrimitives != m_primitives.size())
+        fprintf(stderr, "[solr_b200] compactBoxes: lost primitives on the way... %d != %zu\n", m_nbActivePrimitives, m_primitives.size());
+}
+
+void SceneHost::sceneBounds(float* o) const
+{
+    o[0] = m_minPos.x; o[1] = m_minPos.y; o[2] = m_minPos.z; o[3] = m_maxPos.x; o[4] = m_maxPos.y; o[5] = m_maxPos.z;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// frame protocol (cuda/CudaKernel.cpp:116-145, 174-313)
+// ---------------------------------------------------------------------------------------------------
+void SceneHost::setLimits(int w, int h) { m_maxWidth = w; m_maxHeight = h; }
+void SceneHost::setPartition(int rank, int world) { m_rank = rank; m_world = world; }
+void SceneHost::setDevice(int device) { m_device = device; }
+
+void SceneHost::setRandoms(const float* randoms, size_t n, int timestamp)
+{
+    m_hRandoms.assign((size_t)m_maxWidth * m_maxHeight, 0.f);
+    memcpy(m_hRandoms.data(), randoms, std::min(n, m_hRandoms.size()) * sizeof(float));
+    m_sceneInfo.timestamp = timestamp;
+    m_randomsTransfered = false;
+}
+
+void SceneHost::initBuffers() // CudaKernel.cpp:116-145 + GPUKernel.cpp:299-360
+{
+    const size_t px = (size_t)m_maxWidth * m_maxHeight;
+    m_bitmap.assign(px * B200_COLOR_DEPTH, 0);
+    b200_PrimitiveXYIdBuffer zero = {0, 0, 0, 0};
+    m_primitivesXYIds.assign(px, zero);
+    if (m_hRandoms.size() != px)
+    {
+        // GPUKernel::render_begin fills the table with 0.000005f * (rand() % 2000 - 1000), rand() seeded from
+        // time(0) (GPUKernel.cpp:2719-2727).  Same distribution, fixed seed: frames are reproducible.
+        std::mt19937 gen(20261017u);
+        m_hRandoms.resize(px);
+        for (size_t i = 0; i < px; ++i) m_hRandoms[i] = 0.000005f * ((int)(gen() % 2000u) - 1000);
+    }
+    b200_int2 occ = {1, 1};
+    if (m_device >= 0) b200_set_device(m_device);
+    b200_set_limits(m_maxWidth, m_maxHeight);
+    b200_set_partition(m_rank, m_world);
+    b200_initialize_scene(occ, m_sceneInfo, (int)m_maxPrimitives, NB_MAX_LAMPS, B200_NB_MAX_MATERIALS);
+    b200_reshape_scene(occ, m_sceneInfo);
+    m_deviceInitialised = true;
+    m_primitivesTransfered = m_materialsTransfered = m_texturesTransfered = m_randomsTransfered = false;
+}
+
+void SceneHost::render_begin(const float) // CudaKernel.cpp:174-302
+{
+    if (!m_deviceInitialised) initBuffers();
+    b200_int2 occ = {1, 1};
+    if (m_refresh)
+    {
+        const int nbBoxes = m_nbActiveBoxes, nbPrimitives = m_nbActivePrimitives, nbLamps = m_nbActiveLamps;
+        const int nbMaterials = m_nbActiveMaterials + 1;
+        if (!m_primitivesTransfered)
+        {
+            b200_h2d_scene(occ, m_hBoundingBoxes.data(), nbBoxes, m_hPrimitives.data(), nbPrimitives, m_hLamps.data(), nbLamps);
+            b200_h2d_lightInformation(occ, m_lightInformation.data(), (int)m_lightInformation.size());
+            m_primitivesTransfered = true;
+        }
+        if (!m_randomsTransfered)
+        {
+            b200_h2d_randoms(occ, m_hRandoms.data());
+            m_randomsTransfered = true;
+        }
+        if (!m_materialsTransfered)
+        {
+            realignTexturesAndMaterials();
+            b200_h2d_materials(occ, m_hMaterials.data(), nbMaterials);
+            m_materialsTransfered = true;
+        }
+        if (!m_texturesTransfered)
+        {
+            std::vector<b200_TextureInfo> infos(m_textures.size());
+            for (size_t i = 0; i < m_textures.size(); ++i)
+            {
+                memset(&infos[i], 0, sizeof(b200_TextureInfo));
+                infos[i].buffer = m_textures[i].texels.empty() ? nullptr : m_textures[i].texels.data();
+                infos[i].offset = m_textures[i].offset;
+                infos[i].size = m_textures[i].size;
+            }
+            b200_h2d_textures(occ, (int)infos.size(), infos.data());
+            m_texturesTransfered = true;
+        }
+        b200_int4 objects = {nbBoxes, nbPrimitives, nbLamps, m_lightInformationSize};
+        b200_SceneInfo sceneInfo = m_sceneInfo;
+        if (m_sceneInfo.draftMode && m_sceneInfo.pathTracingIteration == 0) sceneInfo.graphicsLevel = B200_GL_NO_SHADING;
+        if (m_sceneInfo.draftMode && m_sceneInfo.pathTracingIteration == m_sceneInfo.maxPathTracingIterations)
+            sceneInfo.cameraType = B200_CT_ANTIALIASED;
+        b200_int4 blockSize = {8, 4, 1, 0};
+        b200_render(occ, blockSize, sceneInfo, objects, m_postProcessingInfo, m_viewPos, m_viewDir, m_angles);
+    }
+    m_refresh = (m_sceneInfo.pathTracingIteration < m_sceneInfo.maxPathTracingIterations);
+}
+
+void SceneHost::render_end() // CudaKernel.cpp:304-313 (the GL blit that follows there is the viewer's business)
+{
+    b200_int2 occ = {1, 1};
+    b200_d2h_bitmap(occ, m_sceneInfo, m_bitmap.data(), m_primitivesXYIds.data());
+}
+
+unsigned int SceneHost::getPrimitiveAt(int x, int y) // GPUKernel.cpp:729-739
+{
+    unsigned int returnValue = (unsigned int)-1;
+    const unsigned int index = y * m_sceneInfo.size.x + x;
+    if (index < static_cast<unsigned int>(m_sceneInfo.size.x * m_sceneInfo.size.y)) returnValue = m_primitivesXYIds[index].x;
+    return returnValue;
+}
+} // namespace solr_b200
+
+// ---------------------------------------------------------------------------------------------------
+// flat C API (ctypes)
+// ---------------------------------------------------------------------------------------------------
+using solr_b200::SceneHost;
+
+struct b200h_Scene
+{
+    const void* boxes; int nbBoxes;
+    const void* primitives; int nbPrimitives;
+    const void* materials; int nbMaterials;
+    const void* lightInformation; int lightInformationSize;
+    const int* lamps; int nbLamps;
+    float bounds[6];
+    int treeDepth;
+};
+
+extern "C" {
+void* b200h_create(const b200_SceneInfo* si) { return new SceneHost(*si); }
+void b200h_destroy(void* h) { delete static_cast<SceneHost*>(h); }
+void b200h_set_scene_info(void* h, const b200_SceneInfo* si) { static_cast<SceneHost*>(h)->setSceneInfo(*si); }
+void b200h_set_post_processing_info(void* h, const b200_PostProcessingInfo* pp) { static_cast<SceneHost*>(h)->setPostProcessingInfo(*pp); }
+void b200h_set_camera(void* h, const float* eye, const float* dir, const float* angles)
+{
+    b200_float3 e = {eye[0], eye[1], eye[2]}, d = {dir[0], dir[1], dir[2]};
+    b200_float4 a;
+    a.x = angles[0]; a.y = angles[1]; a.z = angles[2]; a.w = angles[3];
+    static_cast<SceneHost*>(h)->setCamera(e, d, a);
+}
+int b200h_add_primitive(void* h, int type) { return static_cast<SceneHost*>(h)->addPrimitive(type); }
+void b200h_set_primitive(void* h, int index, const float* v, int materialId)
+{
+    static_cast<SceneHost*>(h)->setPrimitive(index, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], materialId);
+}
+void b200h_add_primitives(void* h, int n, const int* types, const float* v, const int* materialIds)
+{
+    SceneHost* s = static_cast<SceneHost*>(h);
+    for (int p = 0; p < n; ++p)
+    {
+        const int id = s->addPrimitive(types[p]);
+        const float* V = v + 12 * p;
+        s->setPrimitive(id, V[0], V[1], V[2], V[3], V[4], V[5], V[6], V[7], V[8], V[9], V[10], V[11], materialIds[p]);
+    }
+}
+void b200h_set_normals_bulk(void* h, int first, int n, const float* normals)
+{
+    SceneHost* s = static_cast<SceneHost*>(h);
+    for (int p = 0; p < n; ++p)
+    {
+        const float* N = normals + 9 * p;
+        b200_float3 n0 = {N[0], N[1], N[2]}, n1 = {N[3], N[4], N[5]}, n2 = {N[6], N[7], N[8]};
+        s->setPrimitiveNormals(first + p, n0, n1, n2);
+    }
+}
+void b200h_set_texcoords(void* h, int index, const float* t)
+{
+    b200_float2 a = {t[0], t[1]}, b = {t[2], t[3]}, c = {t[4], t[5]};
+    static_cast<SceneHost*>(h)->setPrimitiveTextureCoordinates(index, a, b, c);
+}
+int b200h_add_material(void* h) { return static_cast<SceneHost*>(h)->addMaterial(); }
+void b200h_add_materials(void* h, int n, const float* f, const int* i)
+{
+    SceneHost* s = static_cast<SceneHost*>(h);
+    for (int m = 0; m < n; ++m)
+    {
+        const int id = s->addMaterial();
+        const float* F = f + 14 * m;
+        const int* I = i + 11 * m;
+        s->setMaterial(id, F[0], F[1], F[2], F[3], F[4], F[5], I[0] != 0, I[1] != 0, I[2], F[6], F[7], I[3], I[4], I[5], I[6],
+                       I[7], I[8], I[9], F[8], F[9], F[10], F[11], F[12], F[13], I[10] != 0);
+    }
+}
+void b200h_set_material_raw(void* h, int index, const b200_Material* m) { static_cast<SceneHost*>(h)->setMaterial(index, *m); }
+void b200h_set_texture(void* h, int index, const unsigned char* texels, int w, int hh, int d) { static_cast<SceneHost*>(h)->setTexture(index, texels, w, hh, d); }
+int b200h_compact_boxes(void* h, int reconstruct) { return static_cast<SceneHost*>(h)->compactBoxes(reconstruct != 0); }
+void b200h_get_scene(void* h, b200h_Scene* out)
+{
+    SceneHost* s = static_cast<SceneHost*>(h);
+    out->boxes = s->boxes(); out->nbBoxes = s->nbActiveBoxes();
+    out->primitives = s->primitives(); out->nbPrimitives = s->nbActivePrimitives();
+    out->materials = s->materials(); out->nbMaterials = s->nbMaterials();
+    out->lightInformation = s->lightInformation(); out->lightInformationSize = s->lightInformationSize();
+    out->lamps = s->lamps(); out->nbLamps = s->nbActiveLamps();
+    s->sceneBounds(out->bounds);
+    out->treeDepth = s->treeDepth();
+}
+void b200h_set_randoms(void* h, const float* r, long n, int timestamp) { static_cast<SceneHost*>(h)->setRandoms(r, (size_t)n, timestamp); }
+void b200h_set_limits(void* h, int w, int hh) { static_cast<SceneHost*>(h)->setLimits(w, hh); }
+void b200h_set_partition(void* h, int rank, int world) { static_cast<SceneHost*>(h)->setPartition(rank, world); }
+void b200h_set_device(void* h, int device) { static_cast<SceneHost*>(h)->setDevice(device); }
+void b200h_init_buffers(void* h) { static_cast<SceneHost*>(h)->initBuffers(); }
+void b200h_render_begin(void* h, float timer) { static_cast<SceneHost*>(h)->render_begin(timer); }
+void b200h_render_end(void* h) { static_cast<SceneHost*>(h)->render_end(); }
+unsigned char* b200h_get_bitmap(void* h) { return static_cast<SceneHost*>(h)->getBitmap(); }
+void* b200h_get_primitive_ids(void* h) { return static_cast<SceneHost*>(h)->getPrimitiveIds(); }
+unsigned int b200h_get_primitive_at(void* h, int x, int y) { return static_cast<SceneHost*>(h)->getPrimitiveAt(x, y); }
+}

@@ -46,6 +46,8 @@ def load():
     lib.b200_set_partition.argtypes = [C.c_int, C.c_int]
     lib.b200_device_buffers.argtypes = [C.POINTER(C.c_void_p)] * 3
     lib.b200_get_counters.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
+    lib.b200_d2h_post.argtypes = [SI, C.c_void_p]
+    lib.b200_d2h_post.restype = None
     lib.b200_last_render_ms.restype = C.c_float
     lib.b200_kernel_launches.restype = C.c_ulonglong
     lib.b200_scene_stats.argtypes = [C.POINTER(C.c_int)] * 4
@@ -63,7 +65,7 @@ ABI_SYMBOLS = [
     "b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
     "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
     "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_stream", "b200_set_limits", "b200_set_partition",
-    "b200_device_buffers", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
+    "b200_device_buffers", "b200_d2h_post", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
     "b200_synchronize",
 ]
 
@@ -139,8 +141,11 @@ class Engine:
         return bitmap, ids
 
     def read_post_buffer(self, scene_info):
-        """Test hook: the float accumulation buffer, through torch-free cudaMemcpy in the library's runtime."""
-        raise NotImplementedError
+        """The float accumulation buffer (colorInfo, sceneInfo per pixel)."""
+        post = np.zeros((scene_info.size.y, scene_info.size.x, 8), np.float32)
+        self.lib.b200_d2h_post(scene_info, _ptr(post))
+        self.check()
+        return post
 
     def counters(self, reset=False):
         r, p = C.c_ulonglong(), C.c_ulonglong()
