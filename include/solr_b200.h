@@ -83,6 +83,10 @@ float b200_last_render_ms(void);
 unsigned long long b200_kernel_launches(void);
 /* Compacted scene statistics of the last h2d_scene: boxes kept after single-child chain collapse etc. */
 void b200_scene_stats(int* nbBoxesIn, int* nbBoxesDevice, int* nbPrimitives, int* reserved);
+/* Host-only (no CUDA call): the box re-layout h2d_scene applies — single-child chains collapsed, skip counts
+ * recomputed, 8 floats per box: (min.xyz, w0) (max.xyz, w1), w as int bits.  Returns the number of boxes kept;
+ * writes them if capacityBoxes suffices.  Lets tests check the collapse without a GPU. */
+int b200_debug_relayout_boxes(const b200_BoundingBox* boxes, int nbBoxes, float* outPacked, int capacityBoxes);
 /* Block until everything queued on the render stream is done. */
 void b200_synchronize(void);
 

@@ -13,11 +13,14 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(_MSC_VER)
+#define SOLR_B200_ALIGN16 __declspec(align(16))
+#else
+#define SOLR_B200_ALIGN16 __attribute__((aligned(16)))
+#endif
 #if defined(__cplusplus)
-#define SOLR_B200_ALIGN16 alignas(16)
 #define SOLR_B200_STATIC_ASSERT(c, m) static_assert(c, m)
 #else
-#define SOLR_B200_ALIGN16 _Alignas(16)
 #define SOLR_B200_STATIC_ASSERT(c, m) _Static_assert(c, m)
 #endif
 

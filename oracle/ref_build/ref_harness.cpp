@@ -160,6 +160,20 @@ void refh_set_normals_bulk(void* h, int first, int n, const float* normals)
     }
 }
 
+void refh_set_texture(void* h, int index, const unsigned char* texels, int width, int height, int depth)
+{
+    TextureInfo ti;
+    memset(&ti, 0, sizeof(ti));
+    ti.buffer = const_cast<unsigned char*>(texels);
+    ti.size.x = width; ti.size.y = height; ti.size.z = depth;
+    static_cast<HarnessKernel*>(h)->setTexture(index, ti);
+}
+
+void refh_set_material_raw(void* h, int index, const Material* m)
+{
+    static_cast<HarnessKernel*>(h)->setMaterial(index, *m);
+}
+
 int refh_compact_boxes(void* h)
 {
     return static_cast<HarnessKernel*>(h)->compactBoxes(true);

@@ -68,7 +68,7 @@ struct Ctx
     const b200_PostProcessingInfo& pp;
     const b200_BoundingBox* boxes; int nbBoxes;
     const b200_Primitive* prims; int nbPrims;
-    const b200_Material* mats;
+    const b200_Material* mats; int nbMats;
     const b200_LightInformation* lights; int lightInfoSize; int nbLamps;
     const unsigned char* tex;
     const float* randoms; int randomTableSize; // "MAX_BITMAP_SIZE" of the build being restated
@@ -650,7 +650,12 @@ bool intersectionWithPrimitives(const Ctx& c, const RayOT& ray, int iteration, i
         if (boxIntersection(box, r, 0.f, minDistance))
         {
             if (c.si.renderBoxes != 0)
-                colorBox += v4(c.mats[box.startIndex % B200_NB_MAX_MATERIALS].color) / 200.f;
+            {
+                // the reference's device material array always has NB_MAX_MATERIALS slots; unset ones read as 0
+                const int m = box.startIndex % B200_NB_MAX_MATERIALS;
+                if (m < c.nbMats) colorBox += v4(c.mats[m].color) / 200.f;
+                else colorBox += V4{0.f, 0.f, 0.f, 0.f} / 200.f;
+            }
             else
             {
                 for (int cpt = 0; cpt < box.nbPrimitives; ++cpt)
@@ -1302,7 +1307,7 @@ void oracle_render(const oracle_Scene* s, const b200_SceneInfo* sceneInfo, const
     {
         oracle_Counters local;
         memset(&local, 0, sizeof(local));
-        Ctx c = {*sceneInfo, *postInfo, s->boxes, s->nbBoxes, s->primitives, s->nbPrimitives, s->materials,
+        Ctx c = {*sceneInfo, *postInfo, s->boxes, s->nbBoxes, s->primitives, s->nbPrimitives, s->materials, s->nbMaterials,
                  s->lightInformation, s->lightInformationSize, s->nbLamps, s->textures, s->randoms, s->randomTableSize, &local};
 #pragma omp for schedule(dynamic, 1)
         for (int k = 0; k < nRows; ++k)

@@ -319,6 +319,61 @@ void unregisterHost()
 }
 } // namespace
 
+
+// Box re-layout shared by h2d_scene and the host-only debug entry point (tests check it without a GPU).
+static int relayoutBoxes(const b200_BoundingBox* boxes, int nbBoxes, std::vector<float4>& packed)
+{
+    // 1. survivors of the chain collapse
+    std::vector<unsigned char> keep(nbBoxes, 1);
+    for (int i = 0; i < nbBoxes; ++i)
+    {
+        const b200_BoundingBox& b = boxes[i];
+        const int skip = b.indexForNextBox.x;
+        if (b.nbPrimitives != 0 || skip <= 1 || i + 1 >= nbBoxes || i + skip > nbBoxes) continue;
+        const b200_BoundingBox& c = boxes[i + 1];
+        if (c.indexForNextBox.x != skip - 1) continue; // more than one child
+        const bool contained = b.parameters[0].x <= c.parameters[0].x && b.parameters[0].y <= c.parameters[0].y &&
+                               b.parameters[0].z <= c.parameters[0].z && b.parameters[1].x >= c.parameters[1].x &&
+                               b.parameters[1].y >= c.parameters[1].y && b.parameters[1].z >= c.parameters[1].z;
+        if (contained) keep[i] = 0;
+    }
+    // 2. new positions; a leaf whose reference skip is not 1 (lights box with children, GPUKernel.cpp:1248-1251)
+    //    is emitted as an inner box with identical bounds followed by the leaf.
+    std::vector<int> pos(nbBoxes + 1, 0);
+    for (int i = 0; i < nbBoxes; ++i)
+    {
+        int n = keep[i] ? 1 : 0;
+        if (keep[i] && boxes[i].nbPrimitives > 0 && boxes[i].indexForNextBox.x != 1) n = 2;
+        pos[i + 1] = pos[i] + n;
+    }
+    const int nOut = pos[nbBoxes];
+    packed.assign(2 * (size_t)nOut, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int i = 0; i < nbBoxes; ++i)
+    {
+        if (!keep[i]) continue;
+        const b200_BoundingBox& b = boxes[i];
+        int end = i + b.indexForNextBox.x;
+        if (end > nbBoxes) end = nbBoxes;
+        if (end <= i) end = i + 1; // a zero/negative skip would never terminate in the reference; advance instead
+        int o = pos[i];
+        const float4 lo = make_float4(b.parameters[0].x, b.parameters[0].y, b.parameters[0].z, 0.f);
+        const float4 hi = make_float4(b.parameters[1].x, b.parameters[1].y, b.parameters[1].z, 0.f);
+        auto put = [&](int at, int w0, int w1) {
+            packed[2 * (size_t)at] = lo; packed[2 * (size_t)at + 1] = hi;
+            packed[2 * (size_t)at].w = intBits(w0); packed[2 * (size_t)at + 1].w = intBits(w1);
+        };
+        if (b.nbPrimitives > 0)
+        {
+            if (b.indexForNextBox.x != 1) { put(o, pos[end] - o, 0); ++o; }
+            put(o, b.startIndex, b.nbPrimitives);
+        }
+        else
+            put(o, pos[end] - o, 0);
+    }
+
+    return nOut;
+}
+
 // ----------------------------------------------------------------------------------------------------
 // the seam
 // ----------------------------------------------------------------------------------------------------
@@ -415,53 +470,8 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     if (nbBoxes < 0 || nbPrims < 0) { latch(-5, "b200_h2d_scene", "negative count"); return; }
     G.nbBoxesIn = nbBoxes;
 
-    // 1. survivors of the chain collapse
-    std::vector<unsigned char> keep(nbBoxes, 1);
-    for (int i = 0; i < nbBoxes; ++i)
-    {
-        const b200_BoundingBox& b = boxes[i];
-        const int skip = b.indexForNextBox.x;
-        if (b.nbPrimitives != 0 || skip <= 1 || i + 1 >= nbBoxes || i + skip > nbBoxes) continue;
-        const b200_BoundingBox& c = boxes[i + 1];
-        if (c.indexForNextBox.x != skip - 1) continue; // more than one child
-        const bool contained = b.parameters[0].x <= c.parameters[0].x && b.parameters[0].y <= c.parameters[0].y &&
-                               b.parameters[0].z <= c.parameters[0].z && b.parameters[1].x >= c.parameters[1].x &&
-                               b.parameters[1].y >= c.parameters[1].y && b.parameters[1].z >= c.parameters[1].z;
-        if (contained) keep[i] = 0;
-    }
-    // 2. new positions; a leaf whose reference skip is not 1 (lights box with children, GPUKernel.cpp:1248-1251)
-    //    is emitted as an inner box with identical bounds followed by the leaf.
-    std::vector<int> pos(nbBoxes + 1, 0);
-    for (int i = 0; i < nbBoxes; ++i)
-    {
-        int n = keep[i] ? 1 : 0;
-        if (keep[i] && boxes[i].nbPrimitives > 0 && boxes[i].indexForNextBox.x != 1) n = 2;
-        pos[i + 1] = pos[i] + n;
-    }
-    const int nOut = pos[nbBoxes];
-    std::vector<float4> packed(2 * (size_t)nOut);
-    for (int i = 0; i < nbBoxes; ++i)
-    {
-        if (!keep[i]) continue;
-        const b200_BoundingBox& b = boxes[i];
-        int end = i + b.indexForNextBox.x;
-        if (end > nbBoxes) end = nbBoxes;
-        if (end <= i) end = i + 1; // a zero/negative skip would never terminate in the reference; advance instead
-        int o = pos[i];
-        const float4 lo = make_float4(b.parameters[0].x, b.parameters[0].y, b.parameters[0].z, 0.f);
-        const float4 hi = make_float4(b.parameters[1].x, b.parameters[1].y, b.parameters[1].z, 0.f);
-        auto put = [&](int at, int w0, int w1) {
-            packed[2 * (size_t)at] = lo; packed[2 * (size_t)at + 1] = hi;
-            packed[2 * (size_t)at].w = intBits(w0); packed[2 * (size_t)at + 1].w = intBits(w1);
-        };
-        if (b.nbPrimitives > 0)
-        {
-            if (b.indexForNextBox.x != 1) { put(o, pos[end] - o, 0); ++o; }
-            put(o, b.startIndex, b.nbPrimitives);
-        }
-        else
-            put(o, pos[end] - o, 0);
-    }
+    std::vector<float4> packed;
+    const int nOut = relayoutBoxes(boxes, nbBoxes, packed);
 
     // 3. primitives
     std::vector<float4> geo(4 * (size_t)nbPrims);
@@ -509,9 +519,12 @@ void b200_h2d_materials(b200_int2, const b200_Material* materials, int n)
     if (!ensureDevice() || n <= 0) return;
     if ((size_t)n > G.capMats)
     {
+        // always NB_MAX_MATERIALS slots, zero-filled, like the reference's device array (CudaRayTracer.cu:1459-1462):
+        // the box-debug view indexes it with startIndex % NB_MAX_MATERIALS
         freeDev(G.dMats);
-        G.capMats = (size_t)n + 64;
+        G.capMats = (size_t)(n > B200_NB_MAX_MATERIALS ? n : B200_NB_MAX_MATERIALS) + 1;
         CK(cudaMalloc(&G.dMats, G.capMats * sizeof(b200_Material)));
+        CK(cudaMemset(G.dMats, 0, G.capMats * sizeof(b200_Material)));
     }
     CK(cudaMemcpyAsync(G.dMats, materials, (size_t)n * sizeof(b200_Material), cudaMemcpyHostToDevice, G.stream));
     CK(cudaStreamSynchronize(G.stream));
@@ -688,6 +701,14 @@ void b200_scene_stats(int* in, int* dev, int* prims, int* reserved)
     if (dev) *dev = G.nbBoxes;
     if (prims) *prims = G.nbPrims;
     if (reserved) *reserved = G.numSMs * G.ctasPerSM;
+}
+
+int b200_debug_relayout_boxes(const b200_BoundingBox* boxes, int nbBoxes, float* outPacked, int capacityBoxes)
+{
+    std::vector<float4> packed;
+    const int nOut = relayoutBoxes(boxes, nbBoxes, packed);
+    if (outPacked && nOut <= capacityBoxes) memcpy(outPacked, packed.data(), packed.size() * sizeof(float4));
+    return nOut;
 }
 
 void b200_synchronize(void)

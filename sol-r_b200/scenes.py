@@ -23,11 +23,12 @@ MAT_I = 11
 
 def material(r, g, b, reflection=0.0, refraction=0.0, transparency=0.0, opacity=0.0, spec_value=1.0,
              spec_power=100.0, spec_coef=0.0, inner=0.0, diffusion=0.0, propagation=0.0, noise=0.0,
-             procedural=0, wireframe=0, wireframe_width=0, fast_transparency=0):
+             procedural=0, wireframe=0, wireframe_width=0, fast_transparency=0, textures=None):
+    """textures: optional 7 ids (diffuse, normal, bump, specular, reflection, transparent, ambient occlusion)."""
     f = np.array([r, g, b, noise, reflection, refraction, transparency, opacity, spec_value, spec_power,
                   spec_coef, inner, diffusion, propagation], dtype=np.float32)
-    i = np.array([procedural, wireframe, wireframe_width] + [wire.TEXTURE_NONE] * 7 + [fast_transparency],
-                 dtype=np.int32)
+    tex = list(textures) if textures is not None else [wire.TEXTURE_NONE] * 7
+    i = np.array([procedural, wireframe, wireframe_width] + tex + [fast_transparency], dtype=np.int32)
     return f, i
 
 
@@ -40,6 +41,8 @@ class Scene:
     prim_v: np.ndarray           # [N, 12] float32: p0, p1, p2, size
     prim_mat: np.ndarray         # [N] int32
     normals: dict = field(default_factory=dict)   # index -> 9 floats
+    textures: list = field(default_factory=list)  # [(index, uint8[h, w, depth])], set before the materials
+    bulk_normals: object = None                   # float32[n, 9] for primitives 0..n-1
     eye: tuple = (0.0, 0.0, -15000.0)
     target: tuple = (0.0, 0.0, 0.0)
     angles: tuple = (0.0, 0.0, 0.0, 6400.0)
@@ -50,11 +53,22 @@ class Scene:
 
     def replay(self, builder):
         """Replay through an object with add_materials/add_primitives/set_normals/compact_boxes."""
+        for idx, texels in self.textures:
+            builder.set_texture(idx, texels)
         builder.add_materials(self.mat_f, self.mat_i)
         builder.add_primitives(self.prim_type, self.prim_v, self.prim_mat)
+        if self.bulk_normals is not None:
+            builder.set_normals_bulk(0, self.bulk_normals)
         for idx, n in self.normals.items():
             builder.set_normals(idx, np.asarray(n, dtype=np.float32))
         return builder.compact_boxes()
+
+    def texture_atlas(self):
+        """The flat texel array as GPUKernel::processTextureOffsets lays it out (GPUKernel.cpp:2691-2705)."""
+        if not self.textures:
+            return None
+        parts = [np.ascontiguousarray(t, np.uint8).reshape(-1) for _, t in sorted(self.textures, key=lambda x: x[0])]
+        return np.concatenate(parts + [np.zeros(16, np.uint8)])
 
 
 def _pack(name, mats, prims, **kw):
@@ -227,6 +241,5 @@ def triangle_mesh(n_target=1_000_000, seed=SEED + 3, name="config3_mesh"):
     em = np.array([e[2] for e in extra], dtype=np.int32)
     mat_f = np.stack([x[0] for x in mats]).astype(np.float32)
     mat_i = np.stack([x[1] for x in mats]).astype(np.int32)
-    sc = Scene(name, mat_f, mat_i, np.concatenate([t, et]), np.concatenate([vprim, ev]), np.concatenate([m, em]))
-    sc.bulk_normals = tri_n  # [n, 9] for the first n primitives
-    return sc
+    return Scene(name, mat_f, mat_i, np.concatenate([t, et]), np.concatenate([vprim, ev]), np.concatenate([m, em]),
+                 bulk_normals=tri_n)

@@ -40,6 +40,8 @@ def load(kind="cpu"):
         lib.refh_add_primitives.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.refh_set_primitive_normals.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.refh_set_normals_bulk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.refh_set_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.refh_set_material_raw.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.refh_compact_boxes.argtypes = [C.c_void_p]
         lib.refh_compact_boxes.restype = C.c_int
         lib.refh_get_scene.argtypes = [C.c_void_p, C.POINTER(RefhScene)]
@@ -87,7 +89,12 @@ class RefScene:
         normals = np.ascontiguousarray(normals, np.float32)
         self.lib.refh_set_normals_bulk(self.h, first, normals.shape[0], _ptr(normals))
 
-    def compact_boxes(self):
+    def set_texture(self, index, texels):
+        t = np.ascontiguousarray(texels, np.uint8)
+        self._tex = getattr(self, "_tex", []) + [t]
+        self.lib.refh_set_texture(self.h, index, _ptr(t), t.shape[1], t.shape[0], t.shape[2])
+
+    def compact_boxes(self, reconstruct=True):
         return self.lib.refh_compact_boxes(self.h)
 
     def arrays(self):

@@ -1,0 +1,92 @@
+"""SceneHost (setters + box compaction) against the reference's own builder: golden hashes always, the
+reference built from source when oracle/_ref exists."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import golden_scenes as gs
+import refh
+from solr_b200 import host, scenes, wire
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def lights_defined(a):
+    li = a["lightInformation"].reshape(-1, 48)
+    return np.concatenate([li[:, :20], li[:, 32:]], 1)  # bytes 20..31 are padding the reference leaves unset
+
+
+@pytest.mark.parametrize("name", sorted(gs.CASES))
+def test_flattened_arrays_match_reference_golden_hashes(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sc, si, *_ = gs.case_setup(name)
+    h = host.SceneHost(si)
+    nb = sc.replay(h)
+    a = h.arrays()
+    assert nb == int(g["nbBoxes"]) == a["nbBoxes"]
+    assert a["nbPrimitives"] == int(g["nbPrimitives"]) == sc.nb_primitives
+    assert sha(a["boxes"]) == str(g["boxes_sha"])
+    assert sha(a["primitives"]) == str(g["primitives_sha"])
+    assert sha(a["materials"]) == str(g["materials_sha"])
+    assert sha(lights_defined(a)) == str(g["lights_sha"])
+    h.close()
+
+
+@pytest.mark.skipif(not refh.available("cpu"), reason="reference not built (oracle/_ref)")
+@pytest.mark.parametrize("maker", [lambda: scenes.config1(1000), lambda: scenes.config1(3), lambda: scenes.config1(1),
+                                   lambda: scenes.molecule(cells=2), lambda: scenes.triangle_mesh(5000),
+                                   lambda: scenes.random_spheres(20000, 20000.0, 20.0, 60.0, 5, "s20k")])
+def test_flattened_arrays_match_reference_live(maker):
+    sc = maker()
+    si = wire.default_scene_info(64, 48)
+    r = refh.RefScene(si, "cpu"); nr = sc.replay(r); a = r.arrays()
+    h = host.SceneHost(si); nh = sc.replay(h); b = h.arrays()
+    assert nr == nh
+    for k in ("boxes", "primitives", "materials", "lamps", "bounds"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(lights_defined(a), lights_defined(b))
+    r.close(); h.close()
+
+
+def test_skip_counts_are_consistent():
+    sc = scenes.config1(500)
+    h = host.SceneHost(wire.default_scene_info(64, 48)); n = sc.replay(h); a = h.arrays(); h.close()
+    boxes = np.frombuffer(a["boxes"].tobytes(), dtype=np.dtype([("lo", "3f4"), ("hi", "3f4"), ("n", "i4"), ("start", "i4"),
+                                                                  ("skip", "2i4"), ("pad", "2i4")]))
+    assert len(boxes) == n
+    skip = boxes["skip"][:, 0]
+    assert (skip >= 1).all() and (np.arange(n) + skip <= n).all()
+    leaves = boxes[boxes["n"] > 0]
+    # every primitive appears in exactly one leaf range, ranges are contiguous in array order
+    covered = np.zeros(a["nbPrimitives"], int)
+    for b in leaves:
+        covered[b["start"]: b["start"] + b["n"]] += 1
+    assert (covered == 1).all()
+    assert boxes[0]["n"] == 1 and boxes[0]["start"] == 0  # box 0 = the lights leaf (GPUKernel.cpp:1177-1190)
+
+
+def test_empty_and_tiny_scenes():
+    si = wire.default_scene_info(32, 24)
+    h = host.SceneHost(si)
+    assert h.compact_boxes() >= 0 and h.arrays()["nbPrimitives"] == 0   # no primitive at all
+    h.close()
+    sc = scenes.config1(0)   # light + 2 ground triangles only
+    h = host.SceneHost(si); sc.replay(h); a = h.arrays()
+    assert a["nbPrimitives"] == 3 and a["nbLamps"] == 1 and a["lightInformationSize"] == 1
+    h.close()
+
+
+def test_setter_bounds_are_checked_like_the_reference():
+    si = wire.default_scene_info(32, 24)
+    h = host.SceneHost(si)
+    lib = host.load()
+    v = np.zeros(12, np.float32)
+    lib.b200h_set_primitive(h.h, 99, v.ctypes.data, 0)   # index > size: logged and ignored (GPUKernel.cpp:680-683)
+    assert h.arrays()["nbPrimitives"] == 0
+    h.close()
