@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of Sol-R's ray-propagation hot path on B200 (contract: see the task's bench section).
+
+A *step* is one full frame of the workload through the hot path: per-pixel ray generation, box-list walk,
+primitive tests, shading with shadow rays, reflection/refraction bounce loop, accumulation, RGB8 pack.
+A *ray* is one box-list walk (closest-hit or shadow), SURVEY.md §8(d).
+
+  workload (N=1 and N>1): BASELINE.json configs[1] — the molecule scene (105 k atom spheres + bond cylinders +
+  ground + light = 216 k primitives), 1920x1080, 1 spp, shadows, 3 bounces (glFull, nbRayIterations=3),
+  synthetic (the reference's 486-atom PDB file does not travel; sol-r_b200/scenes.py generates the lattice).
+
+  value   whole-job Mrays/s with scene and frame state resident in HBM: K x b200_render, CUDA events on the
+          render stream around each frame, L2 flushed (256 MiB memset) between frames, max over ranks.
+          N>1: ONE frame is split across the N GPUs as interleaved 8x4-pixel tiles (strong scaling) and the
+          per-rank partial bitmaps are summed onto rank 0 with NCCL inside the timed region.
+  e2e     the same metric through the host-side drop-in (SceneHost.render_begin + render_end = the calls
+          CudaKernel makes): per-frame parameter upload, kernel, device->host copy of RGB8 + id buffer into
+          caller-owned host memory, wall clock.
+  roofline  FP32 CUDA-core roofline (north_star: compute-bound, no tensor cores): algorithmic flops counted by
+          the oracle in REFERENCE traversal order (SURVEY §8(d) constants) / device time / (148 SM x 128 lanes x
+          2 x sm_max_mhz).  HBM traffic is reported beside it.
+  cpu_baseline / --impl reference: the reference's own code on the host cores (oracle/_ref/libsolr_ref_cpu.so =
+          its CUDA source compiled for the host, OpenMP over blocks) when that library travelled, else the
+          oracle port; bounded sample = the same scene/camera at 480x270 (1/16 of the pixels).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+W, H, NB_RAY_ITERATIONS = 1920, 1080, 3
+SAMPLE_W, SAMPLE_H = 480, 270
+WORKLOAD = "config2_molecule_216k_primitives_1920x1080_glFull_3_bounces"
+SM_COUNT, LANES_PER_SM = 148, 128
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update(hbm_gbs=float(m["hbm_gbs"]), sm_max_mhz=float(m.get("sm_max_mhz", 1965.0)), source="measured")
+    except Exception:
+        pass
+    p["fp32_tflops"] = SM_COUNT * LANES_PER_SM * 2 * p["sm_max_mhz"] * 1e6 / 1e12
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def scene_and_info(width, height):
+    from solr_b200 import scenes, wire
+    sc = scenes.config2()
+    si = wire.default_scene_info(width, height, graphics_level=wire.GL_FULL, nb_ray_iterations=NB_RAY_ITERATIONS)
+    return sc, si
+
+
+def cpu_reference_run(steps, warmup, want_counts=True):
+    """The reference arm / cpu_baseline: the path on host cores at SAMPLE_W x SAMPLE_H."""
+    import oracle
+    import refh
+    from solr_b200 import host, wire
+    sc, si = scene_and_info(SAMPLE_W, SAMPLE_H)
+    h = host.SceneHost(si)
+    sc.replay(h)
+    a = h.arrays()
+    h.close()
+    rnd = np.zeros(wire.REF_MAX_BITMAP_SIZE, np.float32)
+    cores = os.cpu_count() or 1
+    o = oracle.Oracle(a, SAMPLE_W, SAMPLE_H, randoms=rnd)
+    t0 = time.perf_counter()
+    o.render(si, sc.eye, sc.target, sc.angles, threads=cores)
+    t_port = time.perf_counter() - t0
+    counters = o.counters.as_dict()
+    rays = counters["rays"]
+    kind, times = "port", []
+    if refh.available("cpu"):
+        kind = "reference"
+        r = refh.RefScene(si, "cpu")
+        sc.replay(r)
+        for k in range(warmup + steps):
+            t0 = time.perf_counter()
+            r.render(si, sc.eye, sc.target, sc.angles, randoms=rnd, block=(16, 8), want_post=False)
+            if k >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        for k in range(warmup + steps):
+            o2 = oracle.Oracle(a, SAMPLE_W, SAMPLE_H, randoms=rnd)
+            t0 = time.perf_counter()
+            o2.render(si, sc.eye, sc.target, sc.angles, threads=cores)
+            if k >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"kind": kind, "cores": cores, "rays_per_frame": rays, "sec_per_frame": sec, "mrays_s": rays / sec / 1e6,
+            "port_sec_per_frame": t_port, "flops_per_frame": o.flops(), "counters": counters,
+            "sample": "%dx%d frame of the same scene and camera (1/16 of the pixels), %d timed frames" % (SAMPLE_W, SAMPLE_H, len(times))}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "Mrays/s", "value": r["mrays_s"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["sec_per_frame"] * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bench_sample": r["sample"]},
+            "cpu_baseline": {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+
+    from _solr_b200_import import solr_b200  # noqa: F401
+    import __graft_entry__ as graft
+    graft.build(quiet=True)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from solr_b200 import engine, host, partition, wire
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this engine has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    pk = peaks()
+    sc, si = scene_and_info(W, H)
+    rnd = np.zeros(wire.REF_MAX_BITMAP_SIZE, np.float32)
+
+    # ---- the drop-in host path (SceneHost -> C ABI) owns the engine in this process --------------------
+    h = host.SceneHost(si, rank=rank, world=world, device=local_rank)
+    sc.replay(h)
+    h.set_randoms(rnd, 0)
+    h.set_camera(sc.eye, sc.target, sc.angles)
+    stream = torch.cuda.Stream()
+    lib = engine.load()
+    h.init_buffers()
+    lib.b200_set_stream(stream.cuda_stream)
+    si_live = h.scene_info
+    si_live.maxPathTracingIterations = 1 << 30   # keep m_refresh true: every render_begin renders a frame
+
+    def frame_e2e():
+        si_live.pathTracingIteration = 0
+        h.set_scene_info(si_live)
+        h.render_begin(0.0)
+        h.render_end()
+
+    frame_e2e()   # uploads the scene (dirty flags), first frame
+    torch.cuda.synchronize()
+    eng = engine.Engine.__new__(engine.Engine)   # thin view on the already-initialised library for counters etc.
+    eng.lib = lib
+    eng.counters(reset=True)
+    a = h.arrays()
+    objects = wire.Int4(a["nbBoxes"], a["nbPrimitives"], a["nbLamps"], a["lightInformationSize"])
+    occ = wire.Int2(1, 1)
+    eye, target, angles = wire.Float3(*sc.eye), wire.Float3(*sc.target), wire.Float4(*sc.angles)
+    pp = wire.PostProcessingInfo()
+    si0 = wire.default_scene_info(W, H, graphics_level=wire.GL_FULL, nb_ray_iterations=NB_RAY_ITERATIONS)
+    bitmap_t, ids_t = partition.device_tensors(eng, W, H)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def frame_device():
+        lib.b200_render(occ, wire.Int4(8, 4, 1, 0), si0, objects, pp, eye, target, angles)
+        if world > 1:
+            dist.reduce(bitmap_t, dst=0, op=dist.ReduceOp.SUM)   # the path's one exchange step (NVLink)
+
+    # ---- device-resident timing --------------------------------------------------------------------------
+    launches0 = eng.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush.zero_()
+            frame_device()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.counters(reset=True)
+        launches0 = eng.kernel_launches()
+        sampler.start()
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()                                  # L2 flush, outside the timed region
+            if world > 1:
+                dist.barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            frame_device()
+            e.record(stream)
+            evs.append((s, e))
+        stream.synchronize()
+        torch.cuda.synchronize()
+    clocks = sampler.summary()
+    ms = [s.elapsed_time(e) for s, e in evs]
+    launches = eng.kernel_launches() - launches0
+    rays_local, px_local = eng.counters(reset=True)
+    t = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+    r = torch.tensor([float(rays_local), float(px_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    rays_total, px_total = float(r[0].item()), float(r[1].item())
+    ms_per_step = total_ms / args.steps
+    value = rays_total / (total_ms * 1e-3) / 1e6
+    kernel_ms = float(lib.b200_last_render_ms())
+
+    # ---- end to end through the host drop-in -------------------------------------------------------------
+    # The merged frame of a multi-GPU run lives on rank 0's device; e2e is reported for the single-GPU drop-in.
+    e2e = None
+    if world == 1:
+        for _ in range(3):
+            frame_e2e()
+        torch.cuda.synchronize()
+        eng.counters(reset=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            frame_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        rays_e2e, _ = eng.counters(reset=True)
+        e2e = {"value": rays_e2e / dt / 1e6, "unit": "Mrays/s", "ms_per_frame": dt / args.steps * 1e3,
+               "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()),   # scene-info + camera + pointers block, per frame
+               "d2h_bytes_per_step": W * H * 3 + W * H * 16}   # RGB8 + PrimitiveXYIdBuffer, as d2h_bitmap copies
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "rays_per_frame": rays_total / args.steps, "mpixels_per_s": px_total / (total_ms * 1e-3) / 1e6,
+                           "l2": "flushed between timed frames (256 MiB memset outside the timed region)",
+                           "parallelism": "one frame, interleaved 8x4 tiles over %d GPU(s), NCCL sum-reduce of RGB8 to rank 0" % world},
+                "clocks": clocks, "gpu_launches": int(launches), "kernel_ms_last_frame": kernel_ms}
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_run(1, 0)
+            flops_frame = cb["flops_per_frame"] * (W * H) / float(SAMPLE_W * SAMPLE_H)   # per-pixel mean of the 1/16 sample
+            achieved = flops_frame / (ms_per_step * 1e-3) / 1e12
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "ncu_summary_latest.json")) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+            line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
+                                "frac": achieved / pk["fp32_tflops"], "traffic": traffic,
+                                "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json)" % pk["source"],
+                                "algorithmic_gflop_per_frame": flops_frame / 1e9,
+                                "hbm": {"peak_gbs": pk["hbm_gbs"], "mandatory_bytes_per_frame": W * H * (32 + 16 + 3) * 2}}
+            line["cpu_baseline"] = {"value": cb["mrays_s"], "unit": "Mrays/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,9 @@ void b200_get_counters(unsigned long long* rays, unsigned long long* pixels, int
 float b200_last_render_ms(void);
 /* Number of kernels this library launched since initialize_scene. */
 unsigned long long b200_kernel_launches(void);
+/* Bytes b200_render copies host->device per frame (scene-info, camera and buffer pointers: the kernel's
+ * constant-memory parameter block). */
+int b200_frame_parameter_bytes(void);
 /* Compacted scene statistics of the last h2d_scene: boxes kept after single-child chain collapse etc. */
 void b200_scene_stats(int* nbBoxesIn, int* nbBoxesDevice, int* nbPrimitives, int* reserved);
 /* Host-only (no CUDA call): the box re-layout h2d_scene applies — single-child chains collapsed, skip counts

@@ -694,6 +694,7 @@ float b200_last_render_ms(void)
 }
 
 unsigned long long b200_kernel_launches(void) { return G.launches; }
+int b200_frame_parameter_bytes(void) { return (int)sizeof(RenderParams); }
 
 void b200_scene_stats(int* in, int* dev, int* prims, int* reserved)
 {

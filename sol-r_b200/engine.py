@@ -50,6 +50,7 @@ def load():
     lib.b200_d2h_post.restype = None
     lib.b200_debug_relayout_boxes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.b200_debug_relayout_boxes.restype = C.c_int
+    lib.b200_frame_parameter_bytes.restype = C.c_int
     lib.b200_last_render_ms.restype = C.c_float
     lib.b200_kernel_launches.restype = C.c_ulonglong
     lib.b200_scene_stats.argtypes = [C.POINTER(C.c_int)] * 4
@@ -67,7 +68,7 @@ ABI_SYMBOLS = [
     "b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
     "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
     "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_stream", "b200_set_limits", "b200_set_partition",
-    "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
+    "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
     "b200_synchronize",
 ]
 

@@ -9,6 +9,9 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+from _solr_b200_import import solr_b200  # noqa: E402,F401  (registers the package dir `sol-r_b200/` as `solr_b200`)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
