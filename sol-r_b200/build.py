@@ -19,7 +19,9 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = "/usr/bin/g++"
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "--use_fast_math", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-ccbin", CXX, "-cudart", "static", "-shared"]
+              "-Xcompiler", "-fPIC", "-ccbin", CXX, "-cudart", "static", "-shared",
+              # keep the statically linked CUDA runtime private: another libcudart (PyTorch's) may share the process
+              "-Xlinker", "-Bsymbolic", "-Xlinker", "--exclude-libs=ALL"]
 
 
 def _stale(target, sources):

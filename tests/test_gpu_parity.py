@@ -194,7 +194,7 @@ def test_host_frame_protocol_equals_direct_seam_calls():
     bm1, ids1 = h.bitmap().copy(), h.primitive_ids().copy()
     h.render_begin(0.0); h.render_end()   # m_refresh is false now (iteration 0 == max-1): frame must persist
     assert np.array_equal(bm1, h.bitmap()) and np.array_equal(ids1, h.primitive_ids())
-    assert h.get_primitive_at(48, 36) == (ids1[36, 48, 0] & 0xFFFFFFFF)
+    assert h.get_primitive_at(48, 36) == (int(ids1[36, 48, 0]) & 0xFFFFFFFF)
     a = h.arrays()
     h.close()
     e = engine.Engine(si)
