@@ -320,8 +320,8 @@ void unregisterHost()
 } // namespace
 
 
-// Box re-layout shared by h2d_scene and the host-only debug entry point (tests check it without a GPU).
-static int relayoutBoxes(const b200_BoundingBox* boxes, int nbBoxes, std::vector<float4>& packed)
+// Literal box re-layout (fallback): the reference's own hierarchy with single-child chains collapsed.
+static int relayoutBoxesLiteral(const b200_BoundingBox* boxes, int nbBoxes, std::vector<float4>& packed)
 {
     // 1. survivors of the chain collapse
     std::vector<unsigned char> keep(nbBoxes, 1);
@@ -374,6 +374,148 @@ static int relayoutBoxes(const b200_BoundingBox* boxes, int nbBoxes, std::vector
     return nOut;
 }
 
+
+// ----------------------------------------------------------------------------------------------------
+// Ordered BVH over the reference's leaves.
+//
+// Only the LEAVES of the reference's flattened hierarchy are observable: a ray tests a leaf's primitives iff
+// the leaf box and every ancestor pass the slab test, each against the closest distance known when it is
+// reached (GeometryIntersections.cuh:687-770).  Ancestors contain their leaves (GPUKernel.cpp:841-892 builds
+// them as min/max unions), the slab arithmetic is monotone in the corner coordinates, and the closest distance
+// only shrinks along a walk — so an ancestor can never reject a ray its leaf would accept: the reference
+// visits exactly {leaves whose OWN box passes}, in array order.  Any hierarchy over the same leaf sequence
+// whose inner boxes contain their leaves therefore reproduces the reference's walk bit for bit, and we are
+// free to build a good one: a binary tree over contiguous runs of the (spatially coherent, depth-first grid
+// order) leaf sequence, split by the surface-area heuristic, laid out depth-first with skip counts so the
+// device walk stays a stackless list walk.  The reference's own levels are uniform grids of N/4^k cells
+// whose top levels have hundreds of siblings that every ray must scan.
+// Containment of every leaf in all of its reference ancestors is verified; if it fails the literal layout
+// is used instead.
+// ----------------------------------------------------------------------------------------------------
+namespace
+{
+struct Aabb
+{
+    float lo[3], hi[3];
+    void grow(const Aabb& o)
+    {
+        for (int k = 0; k < 3; ++k) { lo[k] = o.lo[k] < lo[k] ? o.lo[k] : lo[k]; hi[k] = o.hi[k] > hi[k] ? o.hi[k] : hi[k]; }
+    }
+    double area() const
+    {
+        const double x = (double)hi[0] - lo[0], y = (double)hi[1] - lo[1], z = (double)hi[2] - lo[2];
+        return (x < 0 || y < 0 || z < 0) ? 0.0 : 2.0 * (x * y + y * z + z * x);
+    }
+    bool contains(const Aabb& o) const
+    {
+        for (int k = 0; k < 3; ++k) if (!(lo[k] <= o.lo[k] && hi[k] >= o.hi[k])) return false;
+        return true;
+    }
+};
+Aabb aabbOf(const b200_BoundingBox& b)
+{
+    Aabb a;
+    a.lo[0] = b.parameters[0].x; a.lo[1] = b.parameters[0].y; a.lo[2] = b.parameters[0].z;
+    a.hi[0] = b.parameters[1].x; a.hi[1] = b.parameters[1].y; a.hi[2] = b.parameters[1].z;
+    return a;
+}
+struct LeafRec { Aabb box; int start, count; };
+
+struct BvhBuilder
+{
+    const std::vector<LeafRec>& leaves;
+    std::vector<float4>& out;
+    std::vector<Aabb> suffix;
+    BvhBuilder(const std::vector<LeafRec>& l, std::vector<float4>& o) : leaves(l), out(o), suffix(l.size() + 1) {}
+
+    int emit(const Aabb& b, int w0, int w1)
+    {
+        const int at = (int)(out.size() / 2);
+        out.push_back(make_float4(b.lo[0], b.lo[1], b.lo[2], intBits(w0)));
+        out.push_back(make_float4(b.hi[0], b.hi[1], b.hi[2], intBits(w1)));
+        return at;
+    }
+    // nodes for leaves [i, j), depth-first; returns the range's bounds
+    Aabb build(int i, int j, int depth)
+    {
+        if (j - i == 1)
+        {
+            emit(leaves[i].box, leaves[i].start, leaves[i].count);
+            return leaves[i].box;
+        }
+        // surface-area heuristic over the j-i-1 contiguous splits
+        int split = (i + j) / 2;
+        Aabb all = leaves[i].box;
+        for (int k = i + 1; k < j; ++k) all.grow(leaves[k].box);
+        if (depth < 56 && j - i > 2)
+        {
+            suffix[j - 1] = leaves[j - 1].box;
+            for (int k = j - 2; k > i; --k) { suffix[k] = leaves[k].box; suffix[k].grow(suffix[k + 1]); }
+            Aabb prefix = leaves[i].box;
+            double best = 1e300;
+            for (int k = i + 1; k < j; ++k) // left = [i, k), right = [k, j)
+            {
+                const double cost = prefix.area() * (k - i) + suffix[k].area() * (j - k);
+                if (cost < best) { best = cost; split = k; }
+                prefix.grow(leaves[k].box);
+            }
+        }
+        const int at = emit(all, 0, 0);
+        build(i, split, depth + 1);
+        build(split, j, depth + 1);
+        out[2 * (size_t)at].w = intBits((int)(out.size() / 2) - at); // skip = subtree size
+        return all;
+    }
+};
+
+// returns false if some leaf is not contained in one of its reference ancestors
+bool collectLeaves(const b200_BoundingBox* boxes, int nbBoxes, std::vector<LeafRec>& leaves)
+{
+    struct Anc { int end; Aabb box; };
+    std::vector<Anc> stack;
+    bool ok = true;
+    for (int i = 0; i < nbBoxes; ++i)
+    {
+        while (!stack.empty() && stack.back().end <= i) stack.pop_back();
+        const b200_BoundingBox& b = boxes[i];
+        const Aabb box = aabbOf(b);
+        int skip = b.indexForNextBox.x;
+        if (skip < 1) skip = 1;
+        if (b.nbPrimitives > 0)
+        {
+            for (const Anc& a : stack) if (!a.box.contains(box)) ok = false;
+            LeafRec l; l.box = box; l.start = b.startIndex; l.count = b.nbPrimitives;
+            leaves.push_back(l);
+        }
+        if (skip > 1) { Anc a; a.end = i + skip; a.box = box; stack.push_back(a); }
+    }
+    return ok;
+}
+
+int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
+} // namespace
+
+// Box re-layout shared by h2d_scene and the host-only debug entry point (tests check it without a GPU).
+static int relayoutBoxes(const b200_BoundingBox* boxes, int nbBoxes, std::vector<float4>& packed, int* layoutUsed = nullptr)
+{
+    if (g_boxLayout != 1)
+    {
+        std::vector<LeafRec> leaves;
+        const bool contained = collectLeaves(boxes, nbBoxes, leaves);
+        if ((contained || g_boxLayout == 2) && !leaves.empty())
+        {
+            packed.clear();
+            packed.reserve(4 * leaves.size());
+            BvhBuilder builder(leaves, packed);
+            builder.build(0, (int)leaves.size(), 0);
+            if (layoutUsed) *layoutUsed = 2;
+            return (int)(packed.size() / 2);
+        }
+    }
+    if (layoutUsed) *layoutUsed = 1;
+    return relayoutBoxesLiteral(boxes, nbBoxes, packed);
+}
+
 // ----------------------------------------------------------------------------------------------------
 // the seam
 // ----------------------------------------------------------------------------------------------------
@@ -382,6 +524,11 @@ extern "C" {
 void b200_set_device(int device) { G.device = device; }
 void b200_set_stream(void* s) { G.stream = s ? (cudaStream_t)s : G.ownStream; }
 void b200_set_limits(int w, int h) { if (w > 0 && h > 0) { G.maxW = w; G.maxH = h; } }
+void b200_set_option(int key, int value)
+{
+    if (key == 1 && value >= 0 && value <= 2) g_boxLayout = value;
+    else latch(-11, "b200_set_option", "unknown option");
+}
 void b200_set_partition(int rank, int world)
 {
     if (world < 1 || rank < 0 || rank >= world) { latch(-2, "b200_set_partition", "rank/world out of range"); return; }

@@ -43,6 +43,8 @@ def load():
     lib.b200_set_device.argtypes = [C.c_int]
     lib.b200_set_stream.argtypes = [C.c_void_p]
     lib.b200_set_limits.argtypes = [C.c_int, C.c_int]
+    lib.b200_set_option.argtypes = [C.c_int, C.c_int]
+    lib.b200_set_option.restype = None
     lib.b200_set_partition.argtypes = [C.c_int, C.c_int]
     lib.b200_device_buffers.argtypes = [C.POINTER(C.c_void_p)] * 3
     lib.b200_get_counters.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
@@ -56,7 +58,7 @@ def load():
     lib.b200_scene_stats.argtypes = [C.POINTER(C.c_int)] * 4
     for f in ("b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
               "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
-              "b200_set_device", "b200_set_stream", "b200_set_limits", "b200_set_partition", "b200_device_buffers",
+              "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition", "b200_device_buffers",
               "b200_get_counters", "b200_scene_stats", "b200_synchronize", "b200_clear_error"):
         getattr(lib, f).restype = None
     _lib = lib
@@ -67,7 +69,7 @@ def load():
 ABI_SYMBOLS = [
     "b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
     "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
-    "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_stream", "b200_set_limits", "b200_set_partition",
+    "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition",
     "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
     "b200_synchronize",
 ]
@@ -77,12 +79,17 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def relayout_boxes(boxes_u8, nb_boxes):
+BOX_LAYOUT_AUTO, BOX_LAYOUT_LITERAL, BOX_LAYOUT_BVH = 0, 1, 2
+
+
+def relayout_boxes(boxes_u8, nb_boxes, layout=BOX_LAYOUT_AUTO):
     """Host-only: the compact device box list (float32 [n', 8]) for a flattened reference box array."""
     lib = load()
+    lib.b200_set_option(1, layout)
     b = np.ascontiguousarray(boxes_u8)
     out = np.zeros((max(2 * nb_boxes, 1), 8), np.float32)
     n = lib.b200_debug_relayout_boxes(_ptr(b), nb_boxes, _ptr(out), out.shape[0])
+    lib.b200_set_option(1, BOX_LAYOUT_AUTO)
     return out[:n].copy()
 
 
