@@ -18,7 +18,11 @@
 #define TILE_W 8
 #define TILE_H 4
 #define CTA_THREADS 128
-#define MIN_CTAS_PER_SM 4
+// 8 CTAs x 128 threads = 32 warps/SM (64 registers): the walks are bound by dependent-load latency, and the extra
+// resident warps hide it better than the extra registers help (measured: 4 -> 11.9 ms, 6 -> 9.5 ms, 8 -> 8.4 ms, 12 -> 8.4 ms on config 2)
+#ifndef MIN_CTAS_PER_SM
+#define MIN_CTAS_PER_SM 8
+#endif
 
 // GeometryShaders.cuh:132-165 (makeColor) fused with k_default's averaging (CudaRayTracer.cu:1068-1072)
 SB_DEV void packPixel(float4 color, unsigned char* bitmap, const int index)
@@ -48,15 +52,18 @@ SB_DEV void packPixel(float4 color, unsigned char* bitmap, const int index)
 // (anaglyph), followed by k_default for that pixel.  The cameras differ only in how many ray trees a
 // pixel owns and how they are combined, so they share one loop around a single launchRayTracing site:
 //   standard/orthographic: 1 sample; antialiased: 4 offset samples + 1; anaglyph: left eye, right eye.
-SB_DEV void renderPixel(const Rotation& rot, const int x, const int y, Counters& cnt, unsigned int& pixelsTraced)
+SB_DEV void renderPixel(const Rotation& rot, const bool inFrame, const int xIn, const int yIn, Counters& cnt, unsigned int& pixelsTraced)
 {
     const int W = cSI.size.x, H = cSI.size.y;
+    const int x = inFrame ? xIn : 0, y = inFrame ? yIn : 0;
     const int index = y * W + x;
     const int iter = cSI.pathTracingIteration;
     int4 id = cP.ids[index];
-    // pixels whose ray tree ended before this deepening pass need no work (:454-458)
-    if (iter > id.y && id.w == 0 && iter > 0 && iter <= B200_NB_MAX_ITERATIONS) return;
-    pixelsTraced++;
+    // pixels whose ray tree ended before this deepening pass need no work (:454-458); the lane still walks
+    // along with its warp (valid == false) because the walks are warp-synchronous
+    const bool valid = inFrame && !(iter > id.y && id.w == 0 && iter > 0 && iter <= B200_NB_MAX_ITERATIONS);
+    if (!__any_sync(FULL_MASK, valid)) return;
+    if (valid) pixelsTraced++;
     const int camera = cSI.cameraType;
     const float3 rotationCenter = (camera == B200_CT_VR) ? cP.eye : f3(0.f, 0.f, 0.f);
     float dof = 0.f;
@@ -122,11 +129,12 @@ SB_DEV void renderPixel(const Rotation& rot, const int x, const int y, Counters&
             o.x += (s == 0) ? 3.f : (s == 1) ? 5.f : (s == 2) ? -3.f : -5.f;
             o.y += (s == 0) ? 5.f : (s == 1) ? -3.f : (s == 2) ? -5.f : 3.f;
         }
-        const float4 c = launchRayTracing(index, o, t, dof, id, cnt);
+        const float4 c = launchRayTracing(valid, index, o, t, dof, id, cnt);
         if (anaglyph && s == 0) left = c;
         else color += c;
     }
 
+    if (!valid) return;
     float4 sinfo = *reinterpret_cast<float4*>(&cP.post[index].sceneInfo);
     if (iter == 0) stored.w = dof;
     if (anaglyph)
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_render()
         const int tx = tile % cP.tilesX, ty = tile / cP.tilesX;
         const int x = tx * TILE_W + (lane & (TILE_W - 1));
         const int y = ty * TILE_H + (lane / TILE_W);
-        if (x < cSI.size.x && y < cSI.size.y) renderPixel(rot, x, y, cnt, pixelsTraced);
+        renderPixel(rot, x < cSI.size.x && y < cSI.size.y, x, y, cnt, pixelsTraced);
         __syncwarp();
     }
     // one atomic per warp for the work counters
@@ -221,7 +229,7 @@ struct Engine
     int rank = 0, world = 1;
     int numSMs = 0, ctasPerSM = 0;
     // scene
-    float4* dBoxes = nullptr; int nbBoxes = 0; int nbBoxesIn = 0;
+    float4* dBoxes = nullptr; int nbBoxes = 0; int nbBoxesIn = 0; int boxLayoutUsed = 0;
     float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
     b200_BoundingBox* dRawBoxes = nullptr;
     b200_Material* dMats = nullptr; int nbMats = 0;
@@ -492,6 +500,7 @@ bool collectLeaves(const b200_BoundingBox* boxes, int nbBoxes, std::vector<LeafR
     return ok;
 }
 
+int g_packetMask = 0x1; // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
 } // namespace
 
@@ -522,11 +531,17 @@ static int relayoutBoxes(const b200_BoundingBox* boxes, int nbBoxes, std::vector
 extern "C" {
 
 void b200_set_device(int device) { G.device = device; }
-void b200_set_stream(void* s) { G.stream = s ? (cudaStream_t)s : G.ownStream; }
+void b200_set_stream(void* s)
+{
+    // work already queued (buffer clears, uploads) must be visible to whatever runs on the new stream
+    if (G.stream && ensureDevice()) CK(cudaStreamSynchronize(G.stream));
+    G.stream = s ? (cudaStream_t)s : G.ownStream;
+}
 void b200_set_limits(int w, int h) { if (w > 0 && h > 0) { G.maxW = w; G.maxH = h; } }
 void b200_set_option(int key, int value)
 {
     if (key == 1 && value >= 0 && value <= 2) g_boxLayout = value;
+    else if (key == 2) g_packetMask = value & 0xF;
     else latch(-11, "b200_set_option", "unknown option");
 }
 void b200_set_partition(int rank, int world)
@@ -555,9 +570,9 @@ void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
     CK(cudaEventCreate(&G.evStop));
     CK(cudaMalloc(&G.dTileCounter, sizeof(unsigned int)));
     CK(cudaMalloc(&G.dWork, 2 * sizeof(unsigned long long)));
-    CK(cudaMemset(G.dWork, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(G.dWork, 0, 2 * sizeof(unsigned long long), G.stream));
     CK(cudaMalloc(&G.dLights, B200_NB_MAX_LIGHTINFORMATIONS * sizeof(b200_LightInformation)));
-    CK(cudaMemset(G.dLights, 0, B200_NB_MAX_LIGHTINFORMATIONS * sizeof(b200_LightInformation)));
+    CK(cudaMemsetAsync(G.dLights, 0, B200_NB_MAX_LIGHTINFORMATIONS * sizeof(b200_LightInformation), G.stream));
     int perSM = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render, CTA_THREADS, 0));
     G.ctasPerSM = perSM > 0 ? perSM : 1;
@@ -592,13 +607,14 @@ void b200_reshape_scene(b200_int2, b200_SceneInfo)
     freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
     unregisterHost();
     CK(cudaMalloc(&G.dRandoms, (px + 4) * sizeof(float)));
-    CK(cudaMemset(G.dRandoms, 0, (px + 4) * sizeof(float)));
+    CK(cudaMemsetAsync(G.dRandoms, 0, (px + 4) * sizeof(float), G.stream));
     CK(cudaMalloc(&G.dPost, px * sizeof(b200_PostProcessingBuffer)));
-    CK(cudaMemset(G.dPost, 0, px * sizeof(b200_PostProcessingBuffer)));
+    CK(cudaMemsetAsync(G.dPost, 0, px * sizeof(b200_PostProcessingBuffer), G.stream));
     CK(cudaMalloc(&G.dIds, px * sizeof(int4)));
-    CK(cudaMemset(G.dIds, 0, px * sizeof(int4)));
+    CK(cudaMemsetAsync(G.dIds, 0, px * sizeof(int4), G.stream));
     CK(cudaMalloc(&G.dBitmap, px * B200_COLOR_DEPTH));
-    CK(cudaMemset(G.dBitmap, 0, px * B200_COLOR_DEPTH));
+    CK(cudaMemsetAsync(G.dBitmap, 0, px * B200_COLOR_DEPTH, G.stream));
+    CK(cudaStreamSynchronize(G.stream));
     G.pixelsCap = px;
 }
 
@@ -618,7 +634,7 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     G.nbBoxesIn = nbBoxes;
 
     std::vector<float4> packed;
-    const int nOut = relayoutBoxes(boxes, nbBoxes, packed);
+    const int nOut = relayoutBoxes(boxes, nbBoxes, packed, &G.boxLayoutUsed);
 
     // 3. primitives
     std::vector<float4> geo(4 * (size_t)nbPrims);
@@ -671,7 +687,7 @@ void b200_h2d_materials(b200_int2, const b200_Material* materials, int n)
         freeDev(G.dMats);
         G.capMats = (size_t)(n > B200_NB_MAX_MATERIALS ? n : B200_NB_MAX_MATERIALS) + 1;
         CK(cudaMalloc(&G.dMats, G.capMats * sizeof(b200_Material)));
-        CK(cudaMemset(G.dMats, 0, G.capMats * sizeof(b200_Material)));
+        CK(cudaMemsetAsync(G.dMats, 0, G.capMats * sizeof(b200_Material), G.stream));
     }
     CK(cudaMemcpyAsync(G.dMats, materials, (size_t)n * sizeof(b200_Material), cudaMemcpyHostToDevice, G.stream));
     CK(cudaStreamSynchronize(G.stream));
@@ -703,7 +719,7 @@ void b200_h2d_textures(b200_int2, int nbTextures, const b200_TextureInfo* infos)
     G.texBytes = total;
     if (!total) return;
     CK(cudaMalloc(&G.dTex, total + 16));
-    CK(cudaMemset(G.dTex, 0, total + 16));
+    CK(cudaMemsetAsync(G.dTex, 0, total + 16, G.stream));
     for (int i = 0; i < nbTextures; ++i)
         if (infos[i].buffer)
             CK(cudaMemcpyAsync(G.dTex + infos[i].offset, infos[i].buffer, (size_t)infos[i].size.x * infos[i].size.y * infos[i].size.z,
@@ -760,6 +776,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.tilesY = (si.size.y + TILE_H - 1) / TILE_H;
     const int nbTiles = P.tilesX * P.tilesY;
     P.rank = G.rank; P.worldSize = G.world;
+    P.packetMask = (G.boxLayoutUsed == 2) ? g_packetMask : 0; // packets need the ordered BVH (only leaf tests observable)
     P.nbLocalTiles = (nbTiles - G.rank + G.world - 1) / G.world;
 
     CK(cudaEventRecord(G.evStart, G.stream));
@@ -808,7 +825,8 @@ void b200_d2h_post(b200_SceneInfo si, b200_PostProcessingBuffer* post)
     const size_t px = (size_t)si.size.x * si.size.y;
     if (px > G.pixelsCap) { latch(-6, "b200_d2h_post", "frame larger than the limits"); return; }
     CK(cudaStreamSynchronize(G.stream));
-    CK(cudaMemcpy(post, G.dPost, px * sizeof(b200_PostProcessingBuffer), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(post, G.dPost, px * sizeof(b200_PostProcessingBuffer), cudaMemcpyDeviceToHost, G.stream));
+    CK(cudaStreamSynchronize(G.stream));
 }
 
 void b200_device_buffers(void** bitmap, void** ids, void** post)
@@ -824,8 +842,9 @@ void b200_get_counters(unsigned long long* rays, unsigned long long* pixels, int
     if (G.dWork && ensureDevice())
     {
         CK(cudaStreamSynchronize(G.stream));
-        CK(cudaMemcpy(h, G.dWork, sizeof(h), cudaMemcpyDeviceToHost));
-        if (reset) CK(cudaMemset(G.dWork, 0, sizeof(h)));
+        CK(cudaMemcpyAsync(h, G.dWork, sizeof(h), cudaMemcpyDeviceToHost, G.stream));
+        CK(cudaStreamSynchronize(G.stream));
+        if (reset) CK(cudaMemsetAsync(G.dWork, 0, sizeof(h), G.stream));
     }
     if (rays) *rays = h[0];
     if (pixels) *pixels = h[1];

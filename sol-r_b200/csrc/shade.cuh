@@ -257,97 +257,136 @@ SB_DEV float4 intersectionShader(const b200_Primitive& p, const b200_Material& m
 
 SB_DEV float rnd(const int i) { return __ldg(cS.randoms + i); }
 
-// GeometryIntersections.cuh:916-1080
-SB_DEV float4 primitiveShader(const int index, const float3 origin, float3& normal,
-                              const int objectId, const float3 I, const float3 areas, float4& closestColor, const int iteration,
-                              float& shadowIntensity, float4& totalBlinn, float4& attributes, Counters& cnt)
+// Shadow ray of one shaded hit: packet walk when the policy says so for this ray class, else per lane.
+SB_DEV float4 traceShadow(const float3 center, const float3 I, const int lightId, const int iteration, const int objectId,
+                          const bool need, const bool packet, Counters& cnt)
 {
-    const b200_Primitive& primitive = cS.prims[objectId];
-    const b200_Material& material = cS.mats[primitive.materialId];
-    const int primIndex = primitive.index;
-    const float4 mInner = *reinterpret_cast<const float4*>(&material.innerIllumination);
+    float4 sh = f4(0.f, 0.f, 0.f, 0.f);
+    if (need) cnt.rays++;
+    if (packet)
+    {
+        if (__any_sync(FULL_MASK, need)) sh = shadowWalkPacket(center, I, lightId, iteration, objectId, need);
+    }
+    else if (need)
+        sh = shadowWalk(center, I, lightId, iteration, objectId);
+    return sh;
+}
+
+// GeometryIntersections.cuh:916-1080.  Warp-uniform form: every lane of the warp calls it, `act` says whether
+// this lane has a hit to shade; the shadow walk in the lamp loop is hoisted out of the per-lane conditions so
+// that the 32 shadow rays of a tile can be walked as one packet.
+SB_DEV float4 primitiveShader(const bool act, const int index, const float3 origin, float3& normal, const int objectIdIn, const float3 I,
+                              const float3 areas, float4& closestColor, const int iteration, float& shadowIntensity, float4& totalBlinn,
+                              float4& attributes, const bool packetShadow, Counters& cnt)
+{
+    const int objectId = objectIdIn;
+    int primIndex = -1;
+    float4 mInner = f4(0.f, 0.f, 0.f, 0.f);
+    float matTransparency = 0.f;
+    bool aoMapped = false;
     float4 lampsColor = f4(0.f, 0.f, 0.f, 0.f);
-    shadowIntensity = 0.f;
-    float3 bumpNormal = f3(0.f, 0.f, 0.f);
+    float4 intersectionColor = f4(0.f, 0.f, 0.f, 0.f);
     float4 adv = f4(0.f, 0.f, 0.f, 0.f);
-    float4 specular = f4(material.specular.x, material.specular.y, material.specular.z, 0.f);
-    const float4 intersectionColor = intersectionShader(primitive, material, I, areas, bumpNormal, specular, attributes, adv);
-    normal += bumpNormal;
-    normal = normalize(normal);
-    if (material.attributes.z == 1) return intersectionColor;
+    float4 specular = f4(0.f, 0.f, 0.f, 0.f);
+    bool lit = false; // this lane runs the lamp loop
+    if (act)
+    {
+        const b200_Primitive& primitive = cS.prims[objectId];
+        const b200_Material& material = cS.mats[primitive.materialId];
+        primIndex = primitive.index;
+        mInner = *reinterpret_cast<const float4*>(&material.innerIllumination);
+        matTransparency = material.transparency;
+        aoMapped = material.advancedTextureIds.z != B200_TEXTURE_NONE;
+        specular = f4(material.specular.x, material.specular.y, material.specular.z, 0.f);
+        shadowIntensity = 0.f;
+        float3 bumpNormal = f3(0.f, 0.f, 0.f);
+        intersectionColor = intersectionShader(primitive, material, I, areas, bumpNormal, specular, attributes, adv);
+        normal += bumpNormal;
+        normal = normalize(normal);
+        lit = material.attributes.z != 1; // wireframe returns the constant colour (:947-951)
+    }
     if (cSI.graphicsLevel > B200_GL_NO_SHADING)
     {
-        closestColor *= mInner.x;
-        for (int cpt = 0; cpt < cS.lightInfoSize; ++cpt)
+        if (lit) closestColor *= mInner.x;
+        const int nbLights = cS.lightInfoSize;
+        for (int cpt = 0; cpt < nbLights; ++cpt)
         {
-            const int cptLamp = (cSI.pathTracingIteration >= B200_NB_MAX_ITERATIONS) ? (cSI.pathTracingIteration % cS.lightInfoSize) : 0;
+            // the reference's lamp loop runs lightInformationSize passes over the SAME lamp (:956-960)
+            const int cptLamp = (cSI.pathTracingIteration >= B200_NB_MAX_ITERATIONS) ? (cSI.pathTracingIteration % nbLights) : 0;
             const b200_LightInformation& li = cS.lights[cptLamp];
             const float4 liColor = *reinterpret_cast<const float4*>(&li.color);
-            if (li.primitiveId != primIndex)
+            const int lightPrimId = li.primitiveId;
+            const b200_Material& m = cS.mats[li.materialId];
+            const float4 lInner = *reinterpret_cast<const float4*>(&m.innerIllumination);
+            const int t = (index + cSI.timestamp) % (cS.randomTableSize - 3);
+            float3 center = f3(li.location.x, li.location.y, li.location.z);
+            float3 lightRay = f3(0.f, 0.f, 0.f);
+            float lightRayLength = 0.f, lambert = 0.f;
+            bool inRange = false, needShadow = false;
+            if (lit && lightPrimId != primIndex)
             {
-                float3 center = f3(li.location.x, li.location.y, li.location.z);
-                const int t = (index + cSI.timestamp) % (cS.randomTableSize - 3);
-                const b200_Material& m = cS.mats[li.materialId];
-                const float4 lInner = *reinterpret_cast<const float4*>(&m.innerIllumination);
                 if (cSI.pathTracingIteration >= B200_NB_MAX_ITERATIONS)
                 {
                     const float a = lInner.y * 10.f * cSI.pathTracingIteration / cSI.maxPathTracingIterations;
                     center.x += rnd(t) * a; center.y += rnd(t + 1) * a; center.z += rnd(t + 2) * a;
                 }
-                float3 lightRay = center - I;
-                const float lightRayLength = length(lightRay);
-                if (lightRayLength < lInner.z)
+                lightRay = center - I;
+                lightRayLength = length(lightRay);
+                inRange = lightRayLength < lInner.z;
+                if (inRange)
                 {
-                    float4 shadowColor = f4(0.f, 0.f, 0.f, 0.f);
                     lightRay = normalize(lightRay);
-                    float lambert = mInner.x + dot(normal, lightRay);
-                    if (lambert > 0.f && cSI.graphicsLevel > 3 && iteration < 4 && mInner.x == 0.f)
+                    lambert = mInner.x + dot(normal, lightRay);
+                    needShadow = lambert > 0.f && cSI.graphicsLevel > 3 && iteration < 4 && mInner.x == 0.f;
+                }
+            }
+            const float4 sh = traceShadow(center, I, lightPrimId, iteration, objectId, needShadow, packetShadow, cnt);
+            if (inRange)
+            {
+                float4 shadowColor = f4(0.f, 0.f, 0.f, 0.f);
+                if (needShadow) { shadowColor.x = sh.x; shadowColor.y = sh.y; shadowColor.z = sh.z; shadowIntensity = sh.w; }
+                float photonEnergy = sqrtf(lightRayLength / lInner.z);
+                photonEnergy = (photonEnergy > 1.f) ? 1.f : photonEnergy;
+                photonEnergy = (photonEnergy < 0.f) ? 0.f : photonEnergy;
+                lambert *= (lambert < 0.f) ? -matTransparency : 1.f;
+                if (li.materialId != B200_MATERIAL_NONE)
+                    lambert *= lInner.x;
+                else
+                    lambert *= liColor.w;
+                if (mInner.w != 0.f) lambert *= (1.f + rnd(t) * mInner.w * 100.f);
+                lambert *= (1.f - shadowIntensity);
+                lambert += cSI.backgroundColor.w;
+                lambert *= (1.f - photonEnergy);
+                lampsColor += lambert * liColor - shadowColor;
+                if (cSI.graphicsLevel > 1 && shadowIntensity < cSI.shadowIntensity)
+                {
+                    const float3 viewRay = normalize(I - origin);
+                    float3 blinnDir = lightRay - viewRay;
+                    const float temp = sqrtf(dot(blinnDir, blinnDir));
+                    if (temp != 0.f)
                     {
-                        cnt.rays++;
-                        const float4 sh = shadowWalk(center, I, li.primitiveId, iteration, objectId);
-                        shadowColor.x = sh.x; shadowColor.y = sh.y; shadowColor.z = sh.z;
-                        shadowIntensity = sh.w;
-                    }
-                    float photonEnergy = sqrtf(lightRayLength / lInner.z);
-                    photonEnergy = (photonEnergy > 1.f) ? 1.f : photonEnergy;
-                    photonEnergy = (photonEnergy < 0.f) ? 0.f : photonEnergy;
-                    lambert *= (lambert < 0.f) ? -material.transparency : 1.f;
-                    if (li.materialId != B200_MATERIAL_NONE)
-                        lambert *= lInner.x;
-                    else
-                        lambert *= liColor.w;
-                    if (mInner.w != 0.f) lambert *= (1.f + rnd(t) * mInner.w * 100.f);
-                    lambert *= (1.f - shadowIntensity);
-                    lambert += cSI.backgroundColor.w;
-                    lambert *= (1.f - photonEnergy);
-                    lampsColor += lambert * liColor - shadowColor;
-                    if (cSI.graphicsLevel > 1 && shadowIntensity < cSI.shadowIntensity)
-                    {
-                        const float3 viewRay = normalize(I - origin);
-                        float3 blinnDir = lightRay - viewRay;
-                        const float temp = sqrtf(dot(blinnDir, blinnDir));
-                        if (temp != 0.f)
-                        {
-                            blinnDir = (1.f / temp) * blinnDir;
-                            float blinnTerm = dot(blinnDir, normal);
-                            blinnTerm = (blinnTerm < 0.f) ? 0.f : blinnTerm;
-                            blinnTerm = specular.x * powf(blinnTerm, specular.y);
-                            blinnTerm *= (1.f - photonEnergy);
-                            totalBlinn += liColor * liColor.w * blinnTerm;
-                            totalBlinn.w = specular.z;
-                        }
+                        blinnDir = (1.f / temp) * blinnDir;
+                        float blinnTerm = dot(blinnDir, normal);
+                        blinnTerm = (blinnTerm < 0.f) ? 0.f : blinnTerm;
+                        blinnTerm = specular.x * powf(blinnTerm, specular.y);
+                        blinnTerm *= (1.f - photonEnergy);
+                        totalBlinn += liColor * liColor.w * blinnTerm;
+                        totalBlinn.w = specular.z;
                     }
                 }
             }
-            closestColor += intersectionColor * lampsColor;
-            if (material.advancedTextureIds.z != B200_TEXTURE_NONE) closestColor *= adv.x;
-            saturate4(closestColor);
-            saturate4(totalBlinn);
+            if (lit)
+            {
+                closestColor += intersectionColor * lampsColor;
+                if (aoMapped) closestColor *= adv.x;
+                saturate4(closestColor);
+                saturate4(totalBlinn);
+            }
         }
     }
-    else
+    else if (lit)
         closestColor = intersectionColor;
-    return closestColor;
+    return (act && !lit) ? intersectionColor : closestColor;
 }
 
 SB_DEV void vectorReflection(float3& r, const float3 i, const float3 n) { r = i - 2.f * dot(i, n) * n; } // VectorUtils.cuh:61-64
@@ -380,10 +419,29 @@ SB_DEV void vectorRotation(float3& v, const float3 c, const Rotation& R)
     v.x = res.x + c.x; v.y = res.y + c.y; v.z = res.z + c.z;
 }
 
-// CudaRayTracer.cu:69-408 — the bounce loop.  colors[]/colorContributions[] of the reference (11-entry
-// local arrays folded back to front at :382-385) stay local arrays here; only `iteration` entries are live.
-SB_DEV float4 launchRayTracing(const int index, const float3 rayO, const float3 rayT,
-                                   float& depthOfField, int4& id, Counters& cnt)
+// Closest-hit walk of one ray class: packet walk when the policy says so, else per lane.
+SB_DEV Hit traceClosest(const float3 o, const float3 t, const int iteration, const int matId, const bool need, const bool packet,
+                        float3& rayNd, Counters& cnt)
+{
+    Hit hit;
+    hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
+    if (need) { cnt.rays++; rayNd = normalize(t - o); }
+    if (packet)
+    {
+        if (__any_sync(FULL_MASK, need)) hit = closestHitPacket(o, t, iteration, matId, need);
+    }
+    else if (need)
+        hit = closestHit(o, t, iteration, matId);
+    return hit;
+}
+
+// CudaRayTracer.cu:69-408 — the bounce loop, in warp-uniform form: the 32 lanes of a warp (one 8x4-pixel
+// tile) step through the bounce iterations together; `valid` says whether this lane owns a pixel, and a lane
+// whose ray tree has ended simply stops taking part (act == false) while the warp finishes.  That keeps the
+// warp converged at every walk, so the walks can run as packets.  colors[]/colorContributions[] (the
+// reference's 11-entry local arrays folded back to front at :382-385) stay local arrays.
+SB_DEV float4 launchRayTracing(const bool valid, const int index, const float3 rayO, const float3 rayT, float& depthOfField, int4& id,
+                               Counters& cnt)
 {
     float4 intersectionColor = f4(0.f, 0.f, 0.f, 0.f);
     float3 normal = f3(0.f, 0.f, 0.f);
@@ -414,61 +472,73 @@ SB_DEV float4 launchRayTracing(const int index, const float3 rayO, const float3 
     float4 rBlinn = f4(0.f, 0.f, 0.f, 0.f);
     int currentMaxIteration = (cSI.graphicsLevel < B200_GL_REFLECTIONS) ? 1 : cSI.nbRayIterations + cSI.pathTracingIteration;
     currentMaxIteration = (currentMaxIteration > B200_NB_MAX_ITERATIONS) ? B200_NB_MAX_ITERATIONS : currentMaxIteration;
+    const bool debugBoxes = cSI.renderBoxes != 0;
+    const int packetMask = cP.packetMask;
     Hit hit;
     hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
     float3 rayNd = f3(0.f, 0.f, 0.f); // normalize(target - origin) of the walk that produced `hit`
+    const float4 bg = f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w);
 
-    while (iteration < currentMaxIteration && rayLength < cSI.viewDistance && carryon)
+    for (int pass = 0; pass < currentMaxIteration; ++pass)
     {
+        // a lane takes part in pass p iff its own loop condition (:125) holds; then iteration == p
+        const bool act = valid && carryon && rayLength < cSI.viewDistance;
+        if (!__any_sync(FULL_MASK, act)) break;
         float3 areas = f3(0.f, 0.f, 0.f);
-        if (cSI.renderBoxes != 0)
+        bool found = false;
+        if (debugBoxes)
         {
-            cnt.rays++;
-            boxDebugWalk(curO, curT, iteration, colorBox);
-            carryon = false;
+            if (act) { cnt.rays++; boxDebugWalk(curO, curT, iteration, colorBox); }
         }
         else
         {
-            cnt.rays++;
-            hit = closestHit(curO, curT, iteration, currentMaterialId);
-            rayNd = normalize(curT - curO);
-            carryon = hit.prim >= 0;
+            hit = traceClosest(curO, curT, pass, currentMaterialId, act, (packetMask & (pass == 0 ? 1 : 2)) != 0, rayNd, cnt);
+            found = act && hit.prim >= 0;
         }
-        if (carryon)
+        if (act) carryon = found;
+        float4 attributes = f4(0.f, 0.f, 0.f, 0.f);
+        float matInnerX = 0.f, matColorW = 0.f;
+        int matId = 0;
+        if (found)
         {
             const int meta = __ldg(cS.meta + hit.prim);
             hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
-            const int matId = PM_MATERIAL(meta);
+            matId = PM_MATERIAL(meta);
             const b200_Material& mat = cS.mats[matId];
             currentMaterialId = matId;
             const float4 rrto = *reinterpret_cast<const float4*>(&mat.reflection); // reflection, refraction, transparency, opacity
-            float4 attributes = f4(rrto.x, rrto.z, rrto.y, rrto.w);
-            const float matInnerX = mat.innerIllumination.x;
-            const float3 closestIntersection = hit.p;
-            if (iteration == 0)
+            attributes = f4(rrto.x, rrto.z, rrto.y, rrto.w);
+            matInnerX = mat.innerIllumination.x;
+            matColorW = mat.color.w;
+            if (pass == 0)
             {
                 colors[0] = f4(0.f, 0.f, 0.f, 0.f);
                 colorContributions[0] = 1.f;
-                latestIntersection = closestIntersection;
-                depthOfField = length(closestIntersection - rayO);
+                latestIntersection = hit.p;
+                depthOfField = length(hit.p - rayO);
                 if (matInnerX == 0.f && (cSI.advancedIllumination == B200_AI_BASIC || cSI.advancedIllumination == B200_AI_FULL))
                 {
                     const int t = (index + cSI.pathTracingIteration * 100 + cSI.timestamp) % (cS.randomTableSize - 3);
-                    giO = closestIntersection + normal * cSI.rayEpsilon;
+                    giO = hit.p + normal * cSI.rayEpsilon;
                     giT.x = normal.x + 100.f * rnd(t);
                     giT.y = normal.y + 100.f * rnd(t + 1);
                     giT.z = normal.z + 100.f * rnd(t + 2);
                     const float cos_theta = dot(normalize(giT), normal);
                     if (cos_theta < 0.f) giT = -giT;
-                    giT += closestIntersection;
+                    giT += hit.p;
                     pathTracingRatio = (1.f - attributes.y) * fabsf(cos_theta);
                     useGlobalIllumination = true;
                 }
                 id.x = __ldg(&cS.prims[hit.prim].index);
             }
             rBlinn.w = attributes.y;
-            colors[iteration] = primitiveShader(index, curO, normal, hit.prim, closestIntersection, areas, closestColor, iteration,
-                                                shadowIntensity, rBlinn, attributes, cnt);
+        }
+        const float4 shaded = primitiveShader(found, index, curO, normal, hit.prim, hit.p, areas, closestColor, pass, shadowIntensity,
+                                              rBlinn, attributes, (packetMask & (pass == 0 ? 4 : 8)) != 0, cnt);
+        if (found)
+        {
+            const float3 closestIntersection = hit.p;
+            colors[pass] = shaded;
             id.z += matInnerX * 256;
             const float segmentLength = length(closestIntersection - latestIntersection);
             latestIntersection = closestIntersection;
@@ -484,11 +554,11 @@ SB_DEV float4 launchRayTracing(const int index, const float3 rayO, const float3 
                     rayLength += len;
                     rayLength = (rayLength > cSI.viewDistance) ? cSI.viewDistance : rayLength;
                     a = (rayLength / cSI.viewDistance);
-                    colors[iteration].x -= a; colors[iteration].y -= a; colors[iteration].z -= a;
+                    colors[pass].x -= a; colors[pass].y -= a; colors[pass].z -= a;
                 }
                 const float3 O_E = normalize(closestIntersection - curO);
                 vectorRefraction(reflectedTarget, O_E, refraction, normal, initialRefraction);
-                colorContributions[iteration] = transparency - a;
+                colorContributions[pass] = transparency - a;
                 initialRefraction = refraction;
                 if (reflectedRays == -1 && attributes.x != 0.f)
                 {
@@ -497,29 +567,29 @@ SB_DEV float4 launchRayTracing(const int index, const float3 rayO, const float3 
                     reflO = closestIntersection + rd * cSI.rayEpsilon;
                     reflT = closestIntersection + rd;
                     reflectedRatio = attributes.x;
-                    reflectedRays = iteration;
+                    reflectedRays = pass;
                 }
             }
             else if (attributes.x != 0.f)
             {
                 const float3 O_E = normalize(closestIntersection - curO);
                 vectorReflection(reflectedTarget, O_E, normal);
-                colorContributions[iteration] = attributes.x;
+                colorContributions[pass] = attributes.x;
             }
             else
             {
                 carryon = false;
-                colorContributions[iteration] = 1.f;
+                colorContributions[pass] = 1.f;
             }
-            rBlinn /= (float)(iteration + 1);
+            rBlinn /= (float)(pass + 1);
             recursiveBlinn.x = (rBlinn.x > recursiveBlinn.x) ? rBlinn.x : recursiveBlinn.x;
             recursiveBlinn.y = (rBlinn.y > recursiveBlinn.y) ? rBlinn.y : recursiveBlinn.y;
             recursiveBlinn.z = (rBlinn.z > recursiveBlinn.z) ? rBlinn.z : recursiveBlinn.z;
             curO = closestIntersection + reflectedTarget * cSI.rayEpsilon;
             curT = closestIntersection + reflectedTarget;
-            if (cSI.pathTracingIteration != 0 && mat.color.w != 0.f)
+            if (cSI.pathTracingIteration != 0 && matColorW != 0.f)
             {
-                float ratio = mat.color.w;
+                float ratio = matColorW;
                 ratio *= (attributes.y == 0.f) ? 1000.f : 1.f;
                 const int rindex = (index + cSI.timestamp) % (cS.randomTableSize - 3);
                 curT.x += rnd(rindex) * ratio;
@@ -527,12 +597,12 @@ SB_DEV float4 launchRayTracing(const int index, const float3 rayO, const float3 
                 curT.z += rnd(rindex + 2) * ratio;
             }
         }
-        else
+        else if (act)
         {
             if (cSI.skyboxMaterialId != B200_MATERIAL_NONE)
             {
-                colors[iteration] = skyboxMapping(curO, curT);
-                const float rad = colors[iteration].x + colors[iteration].y + colors[iteration].z;
+                colors[pass] = skyboxMapping(curO, curT);
+                const float rad = colors[pass].x + colors[pass].y + colors[pass].z;
                 id.z += (rad > 2.5f) ? rad * 256.f : 0.f;
             }
             else if (cSI.gradientBackground)
@@ -541,37 +611,46 @@ SB_DEV float4 launchRayTracing(const int index, const float3 rayO, const float3 
                 const float3 dir = normalize(curT - curO);
                 float angle = 0.5f - dot(up, dir);
                 angle = (angle > 1.f) ? 1.f : angle;
-                colors[iteration] = (1.f - angle) * f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w);
+                colors[pass] = (1.f - angle) * bg;
             }
             else
-                colors[iteration] = f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w);
-            colorContributions[iteration] = 1.f;
+                colors[pass] = bg;
+            colorContributions[pass] = 1.f;
         }
-        iteration++;
+        if (act) iteration = pass + 1;
     }
 
     // extra reflected ray of the first transparent + reflective hit (:296-315)
-    if (cSI.graphicsLevel >= B200_GL_REFLECTIONS && reflectedRays != -1 && cSI.renderBoxes == 0)
     {
-        cnt.rays++;
-        hit = closestHit(reflO, reflT, reflectedRays, currentMaterialId);
-        rayNd = normalize(reflT - reflO);
-        if (hit.prim >= 0)
+        const bool want = valid && cSI.graphicsLevel >= B200_GL_REFLECTIONS && reflectedRays != -1;
+        if (__any_sync(FULL_MASK, want))
         {
-            float3 areas;
-            const int meta = __ldg(cS.meta + hit.prim);
-            hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
-            float4 attributes = f4(cS.mats[PM_MATERIAL(meta)].reflection, 0.f, 0.f, 0.f);
-            const float4 color = primitiveShader(index, reflO, normal, hit.prim, hit.p, areas, closestColor, reflectedRays,
-                                                 shadowIntensity, rBlinn, attributes, cnt);
-            colors[reflectedRays] += color * reflectedRatio;
-            id.w = shadowIntensity * 255;
+            float3 areas = f3(0.f, 0.f, 0.f);
+            bool found = false;
+            if (debugBoxes)
+            {
+                if (want) { cnt.rays++; boxDebugWalk(reflO, reflT, reflectedRays, colorBox); }
+            }
+            else
+            {
+                hit = traceClosest(reflO, reflT, reflectedRays, currentMaterialId, want, (packetMask & 2) != 0, rayNd, cnt);
+                found = want && hit.prim >= 0;
+            }
+            float4 attributes = f4(0.f, 0.f, 0.f, 0.f);
+            if (found)
+            {
+                const int meta = __ldg(cS.meta + hit.prim);
+                hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
+                attributes.x = cS.mats[PM_MATERIAL(meta)].reflection;
+            }
+            const float4 color = primitiveShader(found, index, reflO, normal, hit.prim, hit.p, areas, closestColor, reflectedRays,
+                                                 shadowIntensity, rBlinn, attributes, (packetMask & 8) != 0, cnt);
+            if (found)
+            {
+                colors[reflectedRays] += color * reflectedRatio;
+                id.w = shadowIntensity * 255;
+            }
         }
-    }
-    else if (cSI.graphicsLevel >= B200_GL_REFLECTIONS && reflectedRays != -1)
-    {
-        cnt.rays++;
-        boxDebugWalk(reflO, reflT, reflectedRays, colorBox);
     }
 
     bool test = true;
@@ -579,55 +658,60 @@ SB_DEV float4 launchRayTracing(const int index, const float3 rayO, const float3 
         cSI.pathTracingIteration >= B200_NB_MAX_ITERATIONS)
     {
         // global-illumination ray (:317-378)
-        if (useGlobalIllumination && cSI.advancedIllumination == B200_AI_FULL)
+        const bool giFull = cSI.advancedIllumination == B200_AI_FULL;
+        const bool want = valid && useGlobalIllumination && giFull;
+        float3 areas = f3(0.f, 0.f, 0.f);
+        bool giHit = false;
+        if (giFull)
         {
-            bool giHit = false;
-            if (cSI.renderBoxes != 0) { cnt.rays++; boxDebugWalk(giO, giT, 30, colorBox); }
+            if (debugBoxes)
+            {
+                if (want) { cnt.rays++; boxDebugWalk(giO, giT, 30, colorBox); }
+            }
             else
             {
-                cnt.rays++;
-                hit = closestHit(giO, giT, 30, B200_MATERIAL_NONE);
-                rayNd = normalize(giT - giO);
-                giHit = hit.prim >= 0;
-            }
-            if (giHit)
-            {
-                float3 areas;
-                const int meta = __ldg(cS.meta + hit.prim);
-                hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
-                const b200_Material& material = cS.mats[PM_MATERIAL(meta)];
-                const float4 mc = f4(material.color.x, material.color.y, material.color.z, material.color.w);
-                if (cS.prims[hit.prim].materialId != B200_MATERIAL_NONE)
-                {
-                    if (material.innerIllumination.x == 0.f)
-                    {
-                        colors[0] = mc * material.innerIllumination.x * pathTracingRatio;
-                        test = false;
-                    }
-                    else
-                        colors[0] = mc * pathTracingRatio;
-                }
-                if (test)
-                {
-                    pathTracingRatio *= 0.1f; // STANDARD_LUNINANCE_STRENGTH (Consts.h:52)
-                    float4 attributes = f4(0.f, 0.f, 0.f, 0.f);
-                    if (material.innerIllumination.x == 0.f)
-                        colors[0] -= cSI.shadowIntensity;
-                    else
-                        pathTracingColor = primitiveShader(index, giO, normal, hit.prim, hit.p, areas, closestColor, iteration,
-                                                           shadowIntensity, rBlinn, attributes, cnt);
-                }
-            }
-            else if (cSI.skyboxMaterialId != B200_MATERIAL_NONE)
-            {
-                pathTracingColor = skyboxMapping(giO, giT);
-                pathTracingRatio *= 0.2f; // SKYBOX_LUNINANCE_STRENGTH (Consts.h:53)
+                hit = traceClosest(giO, giT, 30, B200_MATERIAL_NONE, want, (packetMask & 2) != 0, rayNd, cnt);
+                giHit = want && hit.prim >= 0;
             }
         }
-        else if (cSI.skyboxMaterialId != B200_MATERIAL_NONE)
+        bool shadeGi = false;
+        float4 attributes = f4(0.f, 0.f, 0.f, 0.f);
+        if (giHit)
         {
+            const int meta = __ldg(cS.meta + hit.prim);
+            hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
+            const b200_Material& material = cS.mats[PM_MATERIAL(meta)];
+            const float4 mc = f4(material.color.x, material.color.y, material.color.z, material.color.w);
+            if (cS.prims[hit.prim].materialId != B200_MATERIAL_NONE)
+            {
+                if (material.innerIllumination.x == 0.f)
+                {
+                    colors[0] = mc * material.innerIllumination.x * pathTracingRatio;
+                    test = false;
+                }
+                else
+                    colors[0] = mc * pathTracingRatio;
+            }
+            if (test)
+            {
+                pathTracingRatio *= 0.1f; // STANDARD_LUNINANCE_STRENGTH (Consts.h:52)
+                if (material.innerIllumination.x == 0.f)
+                    colors[0] -= cSI.shadowIntensity;
+                else
+                    shadeGi = true;
+            }
+        }
+        if (giFull)
+        {
+            const float4 c = primitiveShader(shadeGi, index, giO, normal, hit.prim, hit.p, areas, closestColor, iteration, shadowIntensity,
+                                             rBlinn, attributes, (packetMask & 8) != 0, cnt);
+            if (shadeGi) pathTracingColor = c;
+        }
+        if (valid && !giHit && cSI.skyboxMaterialId != B200_MATERIAL_NONE)
+        {
+            // no GI hit, or aiBasic (where the reference maps an uninitialised ray, :369-375; zero here)
             pathTracingColor = skyboxMapping(giO, giT);
-            pathTracingRatio *= 0.2f;
+            pathTracingRatio *= 0.2f; // SKYBOX_LUNINANCE_STRENGTH (Consts.h:53)
         }
         if (test) colors[0] += pathTracingColor * pathTracingRatio;
     }
@@ -648,7 +732,7 @@ SB_DEV float4 launchRayTracing(const int index, const float3 rayO, const float3 
         const float D2 = cSI.viewDistance * 0.05f;
         const float a = depthOfField - D1;
         const float b = 1.f - (a / D2);
-        intersectionColor = intersectionColor * b + f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w) * (1.f - b);
+        intersectionColor = intersectionColor * b + bg * (1.f - b);
     }
     id.y = iteration;
     intersectionColor -= colorBox;

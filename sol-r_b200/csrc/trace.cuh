@@ -42,6 +42,11 @@ struct SceneDev
     int nbRawBoxes;
 };
 
+// The walks are kept out of line by default (one copy each, own register allocation); -DWALK_INLINE=__forceinline__ to compare.
+#ifndef WALK_INLINE
+#define WALK_INLINE __noinline__
+#endif
+
 struct RenderParams
 {
     SceneDev scene;
@@ -56,6 +61,7 @@ struct RenderParams
     unsigned long long* workCounters; // [0] rays, [1] pixels
     int tilesX, tilesY, nbLocalTiles;
     int rank, worldSize;
+    int packetMask; // which walks run warp-synchronously: bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow
 };
 
 // One frame's parameters live in constant memory (uploaded on the render stream before the launch):
@@ -458,7 +464,7 @@ SB_DEV int nextLeaf(const float4* __restrict__ boxes, const int nbBoxes, int& bo
 // GeometryIntersections.cuh:667-772 — closest hit over the compacted box list.  Out of line and by value:
 // one copy of the walk serves the bounce loop, the extra reflected ray and the GI ray, with its own
 // register allocation.  hit.prim = -1: no hit.
-__device__ __noinline__ Hit closestHit(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)
+__device__ WALK_INLINE Hit closestHit(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)
 {
     Hit hit;
     hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
@@ -528,7 +534,7 @@ __device__ __noinline__ void boxDebugWalk(const float3 origin, const float3 targ
 
 // GeometryIntersections.cuh:798-908 — shadow walk: accumulates blocker opacity until it saturates.
 // Returns (tint.xyz, shadow intensity).
-__device__ __noinline__ float4 shadowWalk(const float3 lampCenter, const float3 origin, const int lightId, const int iteration, const int objectId)
+__device__ WALK_INLINE float4 shadowWalk(const float3 lampCenter, const float3 origin, const int lightId, const int iteration, const int objectId)
 {
     float result = 0.f;
     float3 color = f3(0.f, 0.f, 0.f);
@@ -594,6 +600,155 @@ __device__ __noinline__ float4 shadowWalk(const float3 lampCenter, const float3 
                 }
             }
         }
+    }
+    result = fmaxf(0.f, fminf(result, shadowLimit));
+    return f4(color.x, color.y, color.z, result);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Warp-synchronous ("packet") walks.  The 32 rays of an 8x4-pixel tile pierce almost the same boxes, so the
+// warp walks the node list ONCE: every lane tests its own ray against the same node, a vote decides whether
+// the warp descends, and at a leaf every lane whose own ray enters the leaf box (own closest distance: the
+// exact reference test) tests the same primitive.  Node and primitive loads are warp-uniform (one
+// transaction), the primitive type switch is uniform, and control flow is driven by votes only, so there is
+// no divergence to re-converge from.  Inner-node votes are conservative by construction (see the ordered-BVH
+// note in engine.cu): only leaf-box tests are observable, and those stay per lane.
+// All 32 lanes must call these together; `active` = this lane carries a ray.
+// ---------------------------------------------------------------------------------------------------
+#define FULL_MASK 0xffffffffu
+
+__device__ WALK_INLINE Hit closestHitPacket(const float3 origin, const float3 target, const int iteration, const int currentMaterialId,
+                                             const bool active)
+{
+    Hit hit;
+    hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
+    float minDistance = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
+    Ray r;
+    makeRay(r, origin, target - origin);
+    const float eps = cSI.geometryEpsilon;
+    const float4* __restrict__ boxes = cS.boxes;
+    const int* __restrict__ metas = cS.meta;
+    const int nbBoxes = cS.nbBoxes;
+    int box = 0;
+    while (box < nbBoxes)
+    {
+        const float4 lo = __ldg(boxes + 2 * box);
+        const float4 hi = __ldg(boxes + 2 * box + 1);
+        const int w0 = __float_as_int(lo.w), w1 = __float_as_int(hi.w);
+        const bool h = active & slab(lo, hi, r, minDistance);
+        const bool any = __any_sync(FULL_MASK, h);
+        if (w1 > 0)
+        {
+            if (any)
+            {
+                for (int k = 0; k < w1; ++k)
+                {
+                    const int idx = w0 + k;
+                    const int meta = __ldg(metas + idx);
+                    const int fast = PM_FAST(meta);
+                    if (h && (fast == 0 || (fast == 1 && currentMaterialId != PM_MATERIAL(meta))))
+                    {
+                        float3 I;
+                        int flags;
+                        float planeShadow;
+                        if (primitiveTest(idx, meta, r, I, flags, planeShadow))
+                        {
+                            const float distance = length(I - r.o);
+                            if (distance > eps && distance < minDistance)
+                            {
+                                minDistance = distance;
+                                hit.prim = idx; hit.p = I; hit.flags = flags;
+                            }
+                        }
+                    }
+                }
+            }
+            box += 1;
+        }
+        else
+            box += any ? 1 : w0;
+    }
+    return hit;
+}
+
+__device__ WALK_INLINE float4 shadowWalkPacket(const float3 lampCenter, const float3 origin, const int lightId, const int iteration,
+                                                const int objectId, const bool active)
+{
+    float result = 0.f;
+    float3 color = f3(0.f, 0.f, 0.f);
+    Ray r;
+    const float3 dirv = lampCenter - origin;
+    makeRay(r, origin + normalize(dirv) * cSI.rayEpsilon, dirv);
+    const float minDistance = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
+    const float eps = cSI.geometryEpsilon;
+    const float shadowLimit = cSI.shadowIntensity;
+    const float lenOL = length(r.d);
+    const float4* __restrict__ boxes = cS.boxes;
+    const int* __restrict__ metas = cS.meta;
+    const int nbBoxes = cS.nbBoxes;
+    const bool extended = cSI.extendedGeometry != 0;
+    int box = 0;
+    // a lane drops out once its shadow saturates (:815,:821); the warp walks on while any lane is still open
+    while (box < nbBoxes && __any_sync(FULL_MASK, active && result < shadowLimit))
+    {
+        const float4 lo = __ldg(boxes + 2 * box);
+        const float4 hi = __ldg(boxes + 2 * box + 1);
+        const int w0 = __float_as_int(lo.w), w1 = __float_as_int(hi.w);
+        const bool h = active & (result < shadowLimit) & slab(lo, hi, r, minDistance);
+        const bool any = __any_sync(FULL_MASK, h);
+        if (w1 > 0)
+        {
+            if (any)
+            {
+                for (int k = 0; k < w1; ++k)
+                {
+                    const int idx = w0 + k;
+                    const int meta = __ldg(metas + idx);
+                    const int origIndex = __ldg(&cS.prims[idx].index);
+                    const int type = extended ? PM_TYPE(meta) : B200_PT_TRIANGLE;
+                    bool test = h && result < shadowLimit && PM_FAST(meta) == 0 && origIndex != lightId && origIndex != objectId &&
+                                type != B200_PT_CAMERA && type != B200_PT_ENVIRONMENT;
+                    if (test)
+                    {
+                        float3 I;
+                        int flags = 0;
+                        float shadowIntensity = 1.f;
+                        bool hitp = primitiveTest(idx, meta, r, I, flags, shadowIntensity);
+                        if (hitp && type == B200_PT_TRIANGLE && cSI.doubleSidedTriangles) hitp = false;
+                        if (hitp)
+                        {
+                            const float l = length(I - r.o);
+                            if (l > eps && l < lenOL)
+                            {
+                                float3 normal = f3(0.f, 0.f, 0.f), areas;
+                                const bool transparent = PM_TRANSPARENT(meta);
+                                if (transparent) hitNormal(idx, meta, I, flags, r.nd, normal, areas);
+                                if (type == B200_PT_SPHERE)
+                                    shadowIntensity = transparent ? (1.f - fabsf(dot(r.nd, normal))) : 1.f;
+                                else if (type < B200_PT_CHECKBOARD || type == B200_PT_ELLIPSOID || type == B200_PT_CONE)
+                                    shadowIntensity = 1.f;
+                                float ratio = shadowIntensity * shadowLimit;
+                                if (transparent)
+                                {
+                                    const b200_Material& m = cS.mats[PM_MATERIAL(meta)];
+                                    const float3 O_L = normalize(r.d);
+                                    const float a = fabsf(dot(O_L, normal));
+                                    const float rr = (m.transparency == 0.f) ? 1.f : (1.f - m.transparency);
+                                    ratio *= rr * a;
+                                    color.x += ratio * (0.3f - 0.3f * m.color.x);
+                                    color.y += ratio * (0.3f - 0.3f * m.color.y);
+                                    color.z += ratio * (0.3f - 0.3f * m.color.z);
+                                }
+                                result += ratio;
+                            }
+                        }
+                    }
+                }
+            }
+            box += 1;
+        }
+        else
+            box += any ? 1 : w0;
     }
     result = fmaxf(0.f, fminf(result, shadowLimit));
     return f4(color.x, color.y, color.z, result);

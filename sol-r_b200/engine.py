@@ -187,6 +187,9 @@ class Engine:
         self.lib.b200_device_buffers(C.byref(b), C.byref(i), C.byref(p))
         return b.value, i.value, p.value
 
+    def set_option(self, key, value):
+        self.lib.b200_set_option(key, value)
+
     def set_stream(self, stream):
         self.lib.b200_set_stream(C.c_void_p(stream) if stream else None)
 
