@@ -1,0 +1,51 @@
+/* B200Kernel.h — the engine host class a Sol-R maintainer adds as solr/engines/b200/B200Kernel.h.
+ *
+ * A sibling of solr::CudaKernel (solr/engines/cuda/CudaKernel.h:28-72): same GPUKernel virtuals, same dirty-flag
+ * protocol, but the device work goes through the C ABI of libsolr_b200 (include/solr_b200.h) instead of
+ * CudaRayTracer.h.  It compiles against the UNMODIFIED reference headers; tests/test_integration.py builds it
+ * together with the reference's own host sources and drives it with the reference's own setters.
+ * INTEGRATION.md lists the three one-line edits that make SOLR_ENGINE=B200 select it.
+ */
+#pragma once
+
+#include <DLL_API.h>
+#include <engines/GPUKernel.h>
+
+namespace solr
+{
+class SOLR_API B200Kernel : public GPUKernel
+{
+public:
+    B200Kernel();
+    ~B200Kernel();
+
+    void initBuffers() override;
+    void cleanup() override;
+
+    void setPlatformId(const int) override {}
+    void setDeviceId(const int device) override;
+    void setKernelFilename(const std::string &) override {}
+    void queryDevice() override;
+    void recompileKernels() override {}
+
+    void render_begin(const float timer) override;
+    void render_end() override;
+    std::string getGPUDescription() override { return m_gpuDescription; }
+
+    /* frame-size limits beyond the reference's 1920x1080 (Consts.h:39-41) and the multi-GPU frame split */
+    void setLimits(int maxWidth, int maxHeight);
+    void setPartition(int rank, int worldSize);
+    /* fixes what GPUKernel::render_begin draws from rand() (GPUKernel.cpp:2719-2727): deterministic frames */
+    void setRandoms(const float *randoms, size_t count, int timestamp);
+
+private:
+    void initializeDevice();
+    void releaseDevice();
+    bool m_deviceInitialized;
+    bool m_fixedRandoms;
+    int m_fixedTimestamp;
+    int m_maxWidth, m_maxHeight;
+    std::vector<unsigned char> m_bigBitmap; /* used instead of m_bitmap when the limits exceed the reference's */
+    std::vector<PrimitiveXYIdBuffer> m_bigIds;
+};
+}

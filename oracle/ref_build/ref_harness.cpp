@@ -21,16 +21,27 @@
 #include <types.h>
 #include <engines/cuda/CudaKernel.h>
 #include <engines/cuda/CudaRayTracer.h>
+#ifdef REFH_B200
+// Variant: the reference's host library driving the B200 engine through integration/B200Kernel (the class a
+// maintainer adds to the reference tree).  Same C API; refh_render goes through render_begin/render_end.
+#include <B200Kernel.h>
+#include <solr_b200.h>
+#define REFH_BASE solr::B200Kernel
+#else
+#define REFH_BASE solr::CudaKernel
+#endif
 #include <io/PDBReader.h>
 #include <io/OBJReader.h>
 
+#ifndef REFH_B200
 // Non-static globals of the reference engine (CudaRayTracer.cu:38,40); read back for parity on the
 // float accumulation buffer, which the seam itself never returns.
 extern PostProcessingBuffer* d_postProcessingBuffer[MAX_GPU_COUNT];
+#endif
 
 namespace
 {
-class HarnessKernel : public solr::CudaKernel
+class HarnessKernel : public REFH_BASE
 {
 public:
     BoundingBox* boxes() { return m_hBoundingBoxes; }
@@ -200,6 +211,31 @@ void refh_get_scene(void* h, RefhScene* out)
     k->sceneBounds(out->bounds);
 }
 
+#ifdef REFH_B200
+// One frame through the reference's own frame protocol (GPUKernel::setSceneInfo / setCamera / render_begin /
+// render_end / getBitmap) with B200Kernel as the engine host class — the drop-in path.
+void refh_render(void* h, const SceneInfo* sceneInfo, const PostProcessingInfo* post, const float* eye,
+                 const float* target, const float* angles, const float* randoms, const int* block,
+                 unsigned char* bitmap, int* ids, float* postBuffer)
+{
+    HarnessKernel* k = static_cast<HarnessKernel*>(h);
+    SceneInfo si = *sceneInfo;
+    si.maxPathTracingIterations = si.pathTracingIteration + 1; // keep m_refresh true for this frame
+    k->setSceneInfo(si);
+    k->setPostProcessingInfo(*post);
+    k->setRandoms(randoms, static_cast<size_t>(MAX_BITMAP_WIDTH) * MAX_BITMAP_HEIGHT, sceneInfo->timestamp);
+    k->setCamera(make_vec3f(eye[0], eye[1], eye[2]), make_vec3f(target[0], target[1], target[2]),
+                 make_vec4f(angles[0], angles[1], angles[2], angles[3]));
+    k->render_begin(0.f);
+    k->render_end();
+    const size_t px = static_cast<size_t>(sceneInfo->size.x) * sceneInfo->size.y;
+    memcpy(bitmap, k->getBitmap(), px * gColorDepth);
+    for (int y = 0; y < sceneInfo->size.y; ++y)
+        for (int x = 0; x < sceneInfo->size.x; ++x)
+            ids[4 * (y * sceneInfo->size.x + x)] = static_cast<int>(k->getPrimitiveAt(x, y));
+    if (postBuffer) b200_d2h_post(*reinterpret_cast<const b200_SceneInfo*>(sceneInfo), reinterpret_cast<b200_PostProcessingBuffer*>(postBuffer));
+}
+#else
 // One frame through the reference engine's seam.  randoms must hold MAX_BITMAP_WIDTH*MAX_BITMAP_HEIGHT
 // floats (h2d_randoms copies exactly that many, CudaRayTracer.cu:1572-1574).  block = {bx, by}; the
 // reference's 12x12 (CudaKernel.cpp:85-87) makes threads with x >= width alias the next row's first
@@ -227,6 +263,8 @@ void refh_render(void* h, const SceneInfo* sceneInfo, const PostProcessingInfo* 
         cudaMemcpy(postBuffer, d_postProcessingBuffer[0],
                    sizeof(PostProcessingBuffer) * sceneInfo->size.x * sceneInfo->size.y, cudaMemcpyDeviceToHost);
 }
+
+#endif
 
 // Struct sizes as the reference compiles them — lets tests assert the wire format of include/*.h.
 void refh_struct_sizes(int* out)

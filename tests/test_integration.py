@@ -1,0 +1,58 @@
+"""The drop-in: the reference's own host library (GPUKernel setters, compactBoxes, frame protocol) with
+integration/B200Kernel.cpp as its engine host class, linked against libsolr_b200 — built by
+oracle/ref_build/Makefile (`make b200`) where /root/reference exists, travels to the GPU box as
+oracle/_ref/libsolr_ref_b200.so."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_scenes as gs
+import refh
+from solr_b200 import host
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/solr"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_b200kernel_compiles_against_unmodified_reference_headers(tmp_path):
+    out = tmp_path / "B200Kernel.o"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-fPIC", "-w", "-c", os.path.join(ROOT, "integration", "B200Kernel.cpp"),
+                           "-I" + os.path.join(ROOT, "oracle", "ref_build", "stubs"), "-I" + REF, "-I/usr/local/cuda/include",
+                           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "integration"), "-o", str(out)])
+    assert out.exists()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not refh.available("b200"), reason="oracle/_ref/libsolr_ref_b200.so did not travel")
+@pytest.mark.parametrize("name", ["mixed_full", "molecule_full", "spheres_progressive"])
+def test_reference_host_drives_the_engine_unchanged(name):
+    """Reference GPUKernel (its setters, its compactBoxes, its render_begin/render_end protocol) + B200Kernel
+    == this repo's SceneHost + the same engine, bit for bit."""
+    sc, si, eye, target, angles, rnd, frames = gs.case_setup(name)
+    h = host.SceneHost(si)
+    sc.replay(h)
+    h.set_randoms(rnd, si.timestamp)
+    h.set_camera(eye, target, angles)
+    h.init_buffers()
+    for it in frames:
+        si.pathTracingIteration = it
+        si.maxPathTracingIterations = it + 1
+        h.set_scene_info(si)
+        h.set_camera(eye, target, angles)
+        h.render_begin(0.0)
+        h.render_end()
+    bm1, ids1 = h.bitmap().copy(), h.primitive_ids().copy()
+    h.close()
+
+    sc, si, eye, target, angles, rnd, frames = gs.case_setup(name)
+    r = refh.RefScene(si, "b200")
+    sc.replay(r)
+    for it in frames:
+        si.pathTracingIteration = it
+        bm2, ids2, _ = r.render(si, eye, target, angles, randoms=rnd, want_post=False)
+    r.close()
+    assert np.array_equal(bm1, bm2)
+    assert np.array_equal(ids1[..., 0], ids2[..., 0])
