@@ -69,7 +69,8 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
 /* Engine options.  key 1 = device box layout: 0 auto (ordered BVH over the reference's leaves when provably
  * equivalent, else literal), 1 literal (the reference's hierarchy, single-child chains collapsed), 2 ordered BVH.
  * key 2 = which walks run warp-synchronously as packets (bit0 primary rays, bit1 secondary rays, bit2 shadow rays
- * of primary hits, bit3 other shadow rays); packets are only used with the ordered BVH. */
+ * of primary hits, bit3 other shadow rays); packets are only used with the ordered BVH.
+ * key 3 = per-lane walks over the 4-wide form of the ordered BVH (1, default) or over the binary list (0). */
 void b200_set_option(int key, int value);
 /* Multi-GPU frame split: this process renders tiles t with t % worldSize == rank (interleaved 8x4-pixel
  * tiles). Non-owned pixels of the device bitmap/ids stay zero so frames merge by summation. */

@@ -230,6 +230,7 @@ struct Engine
     int numSMs = 0, ctasPerSM = 0;
     // scene
     float4* dBoxes = nullptr; int nbBoxes = 0; int nbBoxesIn = 0; int boxLayoutUsed = 0;
+    float4* dWide = nullptr; float4* dLeafRecs = nullptr; int nbWide = 0; size_t capWide = 0, capLeafRecs = 0;
     float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
     b200_BoundingBox* dRawBoxes = nullptr;
     b200_Material* dMats = nullptr; int nbMats = 0;
@@ -500,7 +501,100 @@ bool collectLeaves(const b200_BoundingBox* boxes, int nbBoxes, std::vector<LeafR
     return ok;
 }
 
-int g_packetMask = 0x1; // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
+// 4-wide collapse of the binary list (depth-first, skip counts): a node adopts its grandchildren, largest surface
+// area first and keeping array order, until it has four children.
+struct WideBuilder
+{
+    const std::vector<float4>& bin;  // 2 float4 per binary node
+    std::vector<float4>& wide;       // 8 float4 per wide node
+    std::vector<int> leafOrdinal;    // binary node index -> leaf ordinal
+    WideBuilder(const std::vector<float4>& b, std::vector<float4>& w) : bin(b), wide(w) {}
+    int w0(int i) const { int v; memcpy(&v, &bin[2 * (size_t)i].w, 4); return v; }
+    int w1(int i) const { int v; memcpy(&v, &bin[2 * (size_t)i + 1].w, 4); return v; }
+    bool isLeaf(int i) const { return w1(i) > 0; }
+    int size(int i) const { return isLeaf(i) ? 1 : w0(i); }
+    double area(int i) const
+    {
+        const float4 lo = bin[2 * (size_t)i], hi = bin[2 * (size_t)i + 1];
+        const double x = (double)hi.x - lo.x, y = (double)hi.y - lo.y, z = (double)hi.z - lo.z;
+        return (x < 0 || y < 0 || z < 0) ? 0.0 : 2.0 * (x * y + y * z + z * x);
+    }
+    int build(int i) // i: inner binary node
+    {
+        int kids[4], n = 2;
+        kids[0] = i + 1;
+        kids[1] = i + 1 + size(i + 1);
+        while (n < 4)
+        {
+            int best = -1;
+            double bestArea = -1.0;
+            for (int k = 0; k < n; ++k)
+                if (!isLeaf(kids[k]) && area(kids[k]) > bestArea) { bestArea = area(kids[k]); best = k; }
+            if (best < 0) break;
+            const int c = kids[best];
+            for (int k = n; k > best + 1; --k) kids[k] = kids[k - 1];
+            kids[best] = c + 1;
+            kids[best + 1] = c + 1 + size(c + 1);
+            ++n;
+        }
+        const int at = (int)(wide.size() / 8);
+        wide.resize(wide.size() + 8);
+        float rows[8][4];
+        int refs[4];
+        for (int k = 0; k < 4; ++k)
+        {
+            if (k < n)
+            {
+                const float4 lo = bin[2 * (size_t)kids[k]], hi = bin[2 * (size_t)kids[k] + 1];
+                rows[0][k] = lo.x; rows[1][k] = lo.y; rows[2][k] = lo.z; rows[3][k] = hi.x; rows[4][k] = hi.y; rows[5][k] = hi.z;
+            }
+            else
+            {
+                rows[0][k] = rows[1][k] = rows[2][k] = 3.0e38f; rows[3][k] = rows[4][k] = rows[5][k] = -3.0e38f;
+                refs[k] = (int)0x80000000;
+            }
+        }
+        for (int k = 0; k < n; ++k) refs[k] = isLeaf(kids[k]) ? ~leafOrdinal[kids[k]] : build(kids[k]);
+        for (int r = 0; r < 6; ++r) wide[8 * (size_t)at + r] = make_float4(rows[r][0], rows[r][1], rows[r][2], rows[r][3]);
+        wide[8 * (size_t)at + 6] = make_float4(intBits(refs[0]), intBits(refs[1]), intBits(refs[2]), intBits(refs[3]));
+        wide[8 * (size_t)at + 7] = make_float4(intBits(n), 0.f, 0.f, 0.f);
+        return at;
+    }
+};
+
+// wide nodes + leaf records from the ordered binary list; returns the number of wide nodes
+int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::vector<float4>& leafRecs)
+{
+    wide.clear(); leafRecs.clear();
+    const int nb = (int)(bin.size() / 2);
+    if (nb == 0) return 0;
+    WideBuilder b(bin, wide);
+    b.leafOrdinal.assign(nb, -1);
+    for (int i = 0; i < nb; ++i)
+        if (b.isLeaf(i))
+        {
+            b.leafOrdinal[i] = (int)(leafRecs.size() / 2);
+            leafRecs.push_back(bin[2 * (size_t)i]);
+            leafRecs.push_back(bin[2 * (size_t)i + 1]);
+        }
+    if (b.isLeaf(0))
+    {
+        // a single leaf: one wide node with one child
+        wide.resize(8);
+        const float4 lo = bin[0], hi = bin[1];
+        const float big = 3.0e38f;
+        wide[0] = make_float4(lo.x, big, big, big); wide[1] = make_float4(lo.y, big, big, big); wide[2] = make_float4(lo.z, big, big, big);
+        wide[3] = make_float4(hi.x, -big, -big, -big); wide[4] = make_float4(hi.y, -big, -big, -big); wide[5] = make_float4(hi.z, -big, -big, -big);
+        wide[6] = make_float4(intBits(~0), intBits((int)0x80000000), intBits((int)0x80000000), intBits((int)0x80000000));
+        wide[7] = make_float4(intBits(1), 0.f, 0.f, 0.f);
+        return 1;
+    }
+    b.build(0);
+    return (int)(wide.size() / 8);
+}
+
+int g_useWide = 1;
+int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
 } // namespace
 
@@ -542,6 +636,7 @@ void b200_set_option(int key, int value)
 {
     if (key == 1 && value >= 0 && value <= 2) g_boxLayout = value;
     else if (key == 2) g_packetMask = value & 0xF;
+    else if (key == 3) g_useWide = value != 0;
     else latch(-11, "b200_set_option", "unknown option");
 }
 void b200_set_partition(int rank, int world)
@@ -586,6 +681,7 @@ void b200_finalize_scene(b200_int2)
     if (!ensureDevice()) return;
     cudaDeviceSynchronize();
     unregisterHost();
+    freeDev(G.dWide); freeDev(G.dLeafRecs); G.capWide = G.capLeafRecs = 0; G.nbWide = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
     freeDev(G.dTileCounter); freeDev(G.dWork);
@@ -635,6 +731,15 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
 
     std::vector<float4> packed;
     const int nOut = relayoutBoxes(boxes, nbBoxes, packed, &G.boxLayoutUsed);
+
+    // 2b. the 4-wide form of the ordered BVH for the per-lane walks
+    std::vector<float4> wide, leafRecs;
+    G.nbWide = (G.boxLayoutUsed == 2) ? buildWide(packed, wide, leafRecs) : 0;
+    if (wide.size() > G.capWide) { freeDev(G.dWide); G.capWide = wide.size() + 1024; CK(cudaMalloc(&G.dWide, G.capWide * sizeof(float4))); }
+    if (leafRecs.size() > G.capLeafRecs) { freeDev(G.dLeafRecs); G.capLeafRecs = leafRecs.size() + 1024; CK(cudaMalloc(&G.dLeafRecs, G.capLeafRecs * sizeof(float4))); }
+    if (!wide.empty()) CK(cudaMemcpyAsync(G.dWide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+    if (!leafRecs.empty()) CK(cudaMemcpyAsync(G.dLeafRecs, leafRecs.data(), leafRecs.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+    CK(cudaStreamSynchronize(G.stream));
 
     // 3. primitives
     std::vector<float4> geo(4 * (size_t)nbPrims);
@@ -765,6 +870,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.scene.geo = G.dGeo; P.scene.meta = G.dMeta; P.scene.prims = G.dPrims; P.scene.nbPrimitives = objects.y;
     P.scene.mats = G.dMats; P.scene.lights = G.dLights; P.scene.lightInfoSize = objects.w; P.scene.nbLamps = objects.z;
     P.scene.tex = G.dTex; P.scene.randoms = G.dRandoms; P.scene.randomTableSize = G.maxW * G.maxH;
+    P.scene.wnodes = G.dWide; P.scene.leafRecs = G.dLeafRecs; P.scene.nbWide = g_useWide ? G.nbWide : 0;
     P.scene.rawBoxes = G.dRawBoxes; P.scene.nbRawBoxes = objects.x < G.nbBoxesIn ? objects.x : G.nbBoxesIn;
     P.si = si; P.pp = pp;
     P.eye = make_float3(origin.x, origin.y, origin.z);

@@ -268,7 +268,7 @@ SB_DEV float4 traceShadow(const float3 center, const float3 I, const int lightId
         if (__any_sync(FULL_MASK, need)) sh = shadowWalkPacket(center, I, lightId, iteration, objectId, need);
     }
     else if (need)
-        sh = shadowWalk(center, I, lightId, iteration, objectId);
+        sh = (cS.nbWide > 0) ? shadowWalkWide(center, I, lightId, iteration, objectId) : shadowWalk(center, I, lightId, iteration, objectId);
     return sh;
 }
 
@@ -431,7 +431,7 @@ SB_DEV Hit traceClosest(const float3 o, const float3 t, const int iteration, con
         if (__any_sync(FULL_MASK, need)) hit = closestHitPacket(o, t, iteration, matId, need);
     }
     else if (need)
-        hit = closestHit(o, t, iteration, matId);
+        hit = (cS.nbWide > 0) ? closestHitWide(o, t, iteration, matId) : closestHit(o, t, iteration, matId);
     return hit;
 }
 

@@ -40,6 +40,12 @@ struct SceneDev
     int randomTableSize;               // the reference's MAX_BITMAP_SIZE
     const b200_BoundingBox* __restrict__ rawBoxes; // uncollapsed list, only walked when renderBoxes != 0
     int nbRawBoxes;
+    // 4-wide form of the ordered BVH (engine.cu buildWide): one 128-byte record per inner node holding its (up to) four
+    // children's boxes by axis — rows lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] refs[4] — so one dependent load
+    // tests four boxes; ref >= 0: inner node, ref < 0: leaf ~ref in leafRecs, INT_MIN: empty slot.
+    const float4* __restrict__ wnodes;
+    const float4* __restrict__ leafRecs; // [2*nbLeaves] (min.xyz, first primitive) (max.xyz, count): the reference's leaf boxes, in array order
+    int nbWide;
 };
 
 // The walks are kept out of line by default (one copy each, own register allocation); -DWALK_INLINE=__forceinline__ to compare.
@@ -345,7 +351,10 @@ __device__ __noinline__ bool planeTest(const int primIdx, const Ray& r, float3& 
 }
 
 // One primitive of a leaf: dispatch on type (GeometryIntersections.cuh:712-747).  Returns hit + point.
-SB_DEV bool primitiveTest(const int idx, const int meta, const Ray& r, float3& I,
+#ifndef PRIMTEST_INLINE
+#define PRIMTEST_INLINE __forceinline__
+#endif
+__device__ PRIMTEST_INLINE bool primitiveTest(const int idx, const int meta, const Ray& r, float3& I,
                           int& flags, float& planeShadow)
 {
     const float eps = cSI.geometryEpsilon;
@@ -749,6 +758,229 @@ __device__ WALK_INLINE float4 shadowWalkPacket(const float3 lampCenter, const fl
         }
         else
             box += any ? 1 : w0;
+    }
+    result = fmaxf(0.f, fminf(result, shadowLimit));
+    return f4(color.x, color.y, color.z, result);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-lane walks over the 4-wide ordered BVH.  Children are visited in array order (pushed in reverse, popped
+// in order), so leaves are reached in exactly the reference's order; inner tests are conservative by
+// construction, the leaf box is re-tested with the reference's arithmetic against the closest distance known
+// when the leaf is reached.  Compared with the list walk: one dependent 128-byte load per four boxes, no
+// per-box sign selects (the near/far rows are picked once per ray), a third of the loop iterations.
+// ---------------------------------------------------------------------------------------------------
+#define WIDE_STACK 96
+#ifndef WIDE_DEFER
+#define WIDE_DEFER 4
+#endif
+#define WIDE_NONE 0x7fffffff
+
+struct WideRay
+{
+    int nx, ny, nz, fx, fy, fz; // row indices of the near / far planes for this ray's direction signs
+};
+
+SB_DEV void wideRows(WideRay& w, const Ray& r)
+{
+    const bool sx = r.inv.x < 0.f, sy = r.inv.y < 0.f, sz = r.inv.z < 0.f;
+    w.nx = sx ? 3 : 0; w.fx = sx ? 0 : 3;
+    w.ny = sy ? 4 : 1; w.fy = sy ? 1 : 4;
+    w.nz = sz ? 5 : 2; w.fz = sz ? 2 : 5;
+}
+
+// tests the four children of node `n`; returns the first hit child (array order) and pushes the others
+SB_DEV int wideStep(const float4* __restrict__ n, const WideRay& w, const Ray& r, const float minDistance, int* stack, int& sp)
+{
+    const float4 ax = __ldg(n + w.nx), bx = __ldg(n + w.fx);
+    const float4 ay = __ldg(n + w.ny), by = __ldg(n + w.fy);
+    const float4 az = __ldg(n + w.nz), bz = __ldg(n + w.fz);
+    const int4 refs = __ldg(reinterpret_cast<const int4*>(n + 6));
+    int next = WIDE_NONE;
+#define WIDE_CHILD(C, REF)                                                                                           \
+    {                                                                                                                \
+        const float tnx = (ax.C - r.o.x) * r.inv.x, tfx = (bx.C - r.o.x) * r.inv.x;                                  \
+        const float tny = (ay.C - r.o.y) * r.inv.y, tfy = (by.C - r.o.y) * r.inv.y;                                  \
+        const float tnz = (az.C - r.o.z) * r.inv.z, tfz = (bz.C - r.o.z) * r.inv.z;                                  \
+        const float tmin = fmaxf(fmaxf(tnx, tny), tnz), tmax = fminf(fminf(tfx, tfy), tfz);                          \
+        if ((tmin <= tmax) & (tmin < minDistance) & (tmax > 0.f))                                                    \
+        {                                                                                                            \
+            if (next != WIDE_NONE) stack[sp++] = next;                                                               \
+            next = REF;                                                                                              \
+        }                                                                                                            \
+    }
+    WIDE_CHILD(w, refs.w)
+    WIDE_CHILD(z, refs.z)
+    WIDE_CHILD(y, refs.y)
+    WIDE_CHILD(x, refs.x)
+#undef WIDE_CHILD
+    return next;
+}
+
+__device__ WALK_INLINE Hit closestHitWide(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)
+{
+    Hit hit;
+    hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
+    float minDistance = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
+    Ray r;
+    makeRay(r, origin, target - origin);
+    WideRay w;
+    wideRows(w, r);
+    const float eps = cSI.geometryEpsilon;
+    const float4* __restrict__ wnodes = cS.wnodes;
+    const float4* __restrict__ leafRecs = cS.leafRecs;
+    const int* __restrict__ metas = cS.meta;
+    int stack[WIDE_STACK];
+    int sp = 0;
+    int cur = 0;
+    int pend[WIDE_DEFER]; // leaves reached but not yet tested (array order)
+    int np = 0;
+    while (true)
+    {
+        // inner phase: walk on past up to WIDE_DEFER leaves (with the closest distance known so far — conservative)
+        // so the lanes of a warp switch between the two phases a few times per ray instead of once per leaf
+        while (cur != WIDE_NONE && np < WIDE_DEFER)
+        {
+            if (cur >= 0)
+            {
+                const int next = wideStep(wnodes + 8 * cur, w, r, minDistance, stack, sp);
+                cur = (next != WIDE_NONE) ? next : (sp > 0 ? stack[--sp] : WIDE_NONE);
+            }
+            else
+            {
+                pend[np++] = cur;
+                cur = (sp > 0) ? stack[--sp] : WIDE_NONE;
+            }
+        }
+        if (np == 0) break;
+        // leaf phase, in order: the reference's own test of each leaf box against the closest distance known
+        // when that leaf is reached, then its primitives
+        for (int j = 0; j < np; ++j)
+        {
+            const int leaf = ~pend[j];
+            const float4 lo = __ldg(leafRecs + 2 * leaf);
+            const float4 hi = __ldg(leafRecs + 2 * leaf + 1);
+            if (slab(lo, hi, r, minDistance))
+            {
+                const int start = __float_as_int(lo.w), count = __float_as_int(hi.w);
+                for (int k = 0; k < count; ++k)
+                {
+                    const int idx = start + k;
+                    const int meta = __ldg(metas + idx);
+                    const int fast = PM_FAST(meta);
+                    if (fast == 0 || (fast == 1 && currentMaterialId != PM_MATERIAL(meta)))
+                    {
+                        float3 I;
+                        int flags;
+                        float planeShadow;
+                        if (primitiveTest(idx, meta, r, I, flags, planeShadow))
+                        {
+                            const float distance = length(I - r.o);
+                            if (distance > eps && distance < minDistance)
+                            {
+                                minDistance = distance;
+                                hit.prim = idx; hit.p = I; hit.flags = flags;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        np = 0;
+    }
+    return hit;
+}
+
+__device__ WALK_INLINE float4 shadowWalkWide(const float3 lampCenter, const float3 origin, const int lightId, const int iteration,
+                                             const int objectId)
+{
+    float result = 0.f;
+    float3 color = f3(0.f, 0.f, 0.f);
+    Ray r;
+    const float3 dirv = lampCenter - origin;
+    makeRay(r, origin + normalize(dirv) * cSI.rayEpsilon, dirv);
+    WideRay w;
+    wideRows(w, r);
+    const float minDistance = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
+    const float eps = cSI.geometryEpsilon;
+    const float shadowLimit = cSI.shadowIntensity;
+    const float lenOL = length(r.d);
+    const float4* __restrict__ wnodes = cS.wnodes;
+    const float4* __restrict__ leafRecs = cS.leafRecs;
+    const int* __restrict__ metas = cS.meta;
+    const bool extended = cSI.extendedGeometry != 0;
+    int stack[WIDE_STACK];
+    int sp = 0;
+    int cur = 0;
+    int pend[WIDE_DEFER];
+    int np = 0;
+    while (result < shadowLimit)
+    {
+        while (cur != WIDE_NONE && np < WIDE_DEFER)
+        {
+            if (cur >= 0)
+            {
+                const int next = wideStep(wnodes + 8 * cur, w, r, minDistance, stack, sp);
+                cur = (next != WIDE_NONE) ? next : (sp > 0 ? stack[--sp] : WIDE_NONE);
+            }
+            else
+            {
+                pend[np++] = cur;
+                cur = (sp > 0) ? stack[--sp] : WIDE_NONE;
+            }
+        }
+        if (np == 0) break;
+        for (int j = 0; j < np && result < shadowLimit; ++j)
+        {
+            const int leaf = ~pend[j];
+            const float4 lo = __ldg(leafRecs + 2 * leaf);
+            const float4 hi = __ldg(leafRecs + 2 * leaf + 1);
+            if (!slab(lo, hi, r, minDistance)) continue;
+            const int start = __float_as_int(lo.w), count = __float_as_int(hi.w);
+            for (int k = 0; k < count && result < shadowLimit; ++k)
+            {
+                const int idx = start + k;
+                const int meta = __ldg(metas + idx);
+                if (PM_FAST(meta) != 0) continue;
+                const int origIndex = __ldg(&cS.prims[idx].index);
+                if (origIndex == lightId || origIndex == objectId) continue;
+                const int type = extended ? PM_TYPE(meta) : B200_PT_TRIANGLE;
+                if (type == B200_PT_CAMERA || type == B200_PT_ENVIRONMENT) continue;
+                float3 I;
+                int flags = 0;
+                float shadowIntensity = 1.f;
+                bool hitp = primitiveTest(idx, meta, r, I, flags, shadowIntensity);
+                if (hitp && type == B200_PT_TRIANGLE && cSI.doubleSidedTriangles) hitp = false;
+                if (hitp)
+                {
+                    const float l = length(I - r.o);
+                    if (l > eps && l < lenOL)
+                    {
+                        float3 normal = f3(0.f, 0.f, 0.f), areas;
+                        const bool transparent = PM_TRANSPARENT(meta);
+                        if (transparent) hitNormal(idx, meta, I, flags, r.nd, normal, areas);
+                        if (type == B200_PT_SPHERE)
+                            shadowIntensity = transparent ? (1.f - fabsf(dot(r.nd, normal))) : 1.f;
+                        else if (type < B200_PT_CHECKBOARD || type == B200_PT_ELLIPSOID || type == B200_PT_CONE)
+                            shadowIntensity = 1.f;
+                        float ratio = shadowIntensity * shadowLimit;
+                        if (transparent)
+                        {
+                            const b200_Material& m = cS.mats[PM_MATERIAL(meta)];
+                            const float3 O_L = normalize(r.d);
+                            const float a = fabsf(dot(O_L, normal));
+                            const float rr = (m.transparency == 0.f) ? 1.f : (1.f - m.transparency);
+                            ratio *= rr * a;
+                            color.x += ratio * (0.3f - 0.3f * m.color.x);
+                            color.y += ratio * (0.3f - 0.3f * m.color.y);
+                            color.z += ratio * (0.3f - 0.3f * m.color.z);
+                        }
+                        result += ratio;
+                    }
+                }
+            }
+        }
+        np = 0;
     }
     result = fmaxf(0.f, fminf(result, shadowLimit));
     return f4(color.x, color.y, color.z, result);
