@@ -70,7 +70,10 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
  * equivalent, else literal), 1 literal (the reference's hierarchy, single-child chains collapsed), 2 ordered BVH.
  * key 2 = which walks run warp-synchronously as packets (bit0 primary rays, bit1 secondary rays, bit2 shadow rays
  * of primary hits, bit3 other shadow rays); packets are only used with the ordered BVH.
- * key 3 = per-lane walks over the 4-wide form of the ordered BVH (1, default) or over the binary list (0). */
+ * key 3 = per-lane walks over the 4-wide form of the ordered BVH (1, default) or over the binary list (0).
+ * key 4 = order-independent walks over the unordered SAH BVH where they are exact (1, default) or ordered walks only (0).
+ * key 5 = order-independent walks also look up hits BEHIND the ray origin, which the reference's cylinder/cone test registers
+ *         (GeometryIntersections.cuh:316-325) (1, default); 0 drops them (not reference-exact; for measurement). */
 void b200_set_option(int key, int value);
 /* Multi-GPU frame split: this process renders tiles t with t % worldSize == rank (interleaved 8x4-pixel
  * tiles). Non-owned pixels of the device bitmap/ids stay zero so frames merge by summation. */
@@ -96,6 +99,10 @@ void b200_scene_stats(int* nbBoxesIn, int* nbBoxesDevice, int* nbPrimitives, int
  * recomputed, 8 floats per box: (min.xyz, w0) (max.xyz, w1), w as int bits.  Returns the number of boxes kept;
  * writes them if capacityBoxes suffices.  Lets tests check the collapse without a GPU. */
 int b200_debug_relayout_boxes(const b200_BoundingBox* boxes, int nbBoxes, float* outPacked, int capacityBoxes);
+/* Host-only: the unordered SAH BVH built over the same leaves (binary depth-first list, same 8-float format). */
+int b200_debug_build_unordered(const b200_BoundingBox* boxes, int nbBoxes, float* outPacked, int capacityBoxes);
+/* Host-only debug read of the raw work counters (8 values; [0] rays, [1] pixels, others only in instrumented builds). */
+void b200_debug_counters(unsigned long long* out8);
 /* Block until everything queued on the render stream is done. */
 void b200_synchronize(void);
 

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <algorithm>
 
 #include <cuda_runtime.h>
 
@@ -231,6 +232,9 @@ struct Engine
     // scene
     float4* dBoxes = nullptr; int nbBoxes = 0; int nbBoxesIn = 0; int boxLayoutUsed = 0;
     float4* dWide = nullptr; float4* dLeafRecs = nullptr; int nbWide = 0; size_t capWide = 0, capLeafRecs = 0;
+    float4* dUWide = nullptr; int nbUWide = 0; size_t capUWide = 0; int opaqueShadows = 0;
+    int nbUX = 0; // point-query tree for backward cylinder hits, appended to dUWide
+    int* dPrimLeaf = nullptr; size_t capPrimLeaf = 0;
     float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
     b200_BoundingBox* dRawBoxes = nullptr;
     b200_Material* dMats = nullptr; int nbMats = 0;
@@ -315,7 +319,20 @@ void uploadMeta()
 {
     if (G.hPrims.empty() || !G.dMeta) return;
     std::vector<int> meta(G.hPrims.size());
-    for (size_t i = 0; i < G.hPrims.size(); ++i) meta[i] = packMeta(G.hPrims[i], G.hMats);
+    int opaque = 1;
+    for (size_t i = 0; i < G.hPrims.size(); ++i)
+    {
+        meta[i] = packMeta(G.hPrims[i], G.hMats);
+        // shadow casters that do not block fully: transparent materials (GeometryIntersections.cuh:280-281,880-892) and
+        // planes whose opacity comes from a texel (:551-559)
+        const b200_Primitive& p = G.hPrims[i];
+        const bool planeClass = p.type == B200_PT_CHECKBOARD || p.type == B200_PT_CAMERA || p.type == B200_PT_XYPLANE ||
+                                p.type == B200_PT_YZPLANE || p.type == B200_PT_XZPLANE || p.type == B200_PT_MAGICCARPET || p.type == B200_PT_QUAD;
+        bool textured = false;
+        if (p.materialId >= 0 && (size_t)p.materialId < G.hMats.size()) textured = G.hMats[p.materialId].textureIds.x != B200_TEXTURE_NONE;
+        if (((meta[i] >> 7) & 1) || (planeClass && (textured || p.type == B200_PT_CAMERA))) opaque = 0;
+    }
+    G.opaqueShadows = opaque;
     CK(cudaMemcpyAsync(G.dMeta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
     CK(cudaStreamSynchronize(G.stream)); // meta is a stack-lifetime staging vector
 }
@@ -563,20 +580,30 @@ struct WideBuilder
 };
 
 // wide nodes + leaf records from the ordered binary list; returns the number of wide nodes
-int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::vector<float4>& leafRecs)
+int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::vector<float4>& leafRecs,
+              const std::vector<int>* leafOfNode = nullptr)
 {
-    wide.clear(); leafRecs.clear();
+    wide.clear();
     const int nb = (int)(bin.size() / 2);
     if (nb == 0) return 0;
     WideBuilder b(bin, wide);
     b.leafOrdinal.assign(nb, -1);
-    for (int i = 0; i < nb; ++i)
-        if (b.isLeaf(i))
-        {
-            b.leafOrdinal[i] = (int)(leafRecs.size() / 2);
-            leafRecs.push_back(bin[2 * (size_t)i]);
-            leafRecs.push_back(bin[2 * (size_t)i + 1]);
-        }
+    if (leafOfNode)
+    {
+        // leaf ordinals are given (unordered tree over the ordered tree's leaf records)
+        for (int i = 0; i < nb; ++i) b.leafOrdinal[i] = (*leafOfNode)[i];
+    }
+    else
+    {
+        leafRecs.clear();
+        for (int i = 0; i < nb; ++i)
+            if (b.isLeaf(i))
+            {
+                b.leafOrdinal[i] = (int)(leafRecs.size() / 2);
+                leafRecs.push_back(bin[2 * (size_t)i]);
+                leafRecs.push_back(bin[2 * (size_t)i + 1]);
+            }
+    }
     if (b.isLeaf(0))
     {
         // a single leaf: one wide node with one child
@@ -585,7 +612,7 @@ int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::ve
         const float big = 3.0e38f;
         wide[0] = make_float4(lo.x, big, big, big); wide[1] = make_float4(lo.y, big, big, big); wide[2] = make_float4(lo.z, big, big, big);
         wide[3] = make_float4(hi.x, -big, -big, -big); wide[4] = make_float4(hi.y, -big, -big, -big); wide[5] = make_float4(hi.z, -big, -big, -big);
-        wide[6] = make_float4(intBits(~0), intBits((int)0x80000000), intBits((int)0x80000000), intBits((int)0x80000000));
+        wide[6] = make_float4(intBits(~b.leafOrdinal[0]), intBits((int)0x80000000), intBits((int)0x80000000), intBits((int)0x80000000));
         wide[7] = make_float4(intBits(1), 0.f, 0.f, 0.f);
         return 1;
     }
@@ -593,17 +620,122 @@ int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::ve
     return (int)(wide.size() / 8);
 }
 
+// ----------------------------------------------------------------------------------------------------
+// Unordered BVH over the same leaves (binned SAH on leaf-box centroids, no ordering constraint), emitted in the
+// same depth-first binary list format so buildWide() can collapse it.  Used by the walks whose result does not
+// depend on the visiting order (rays with |direction| >= 1, see trace.cuh "order-independent walks").
+// ----------------------------------------------------------------------------------------------------
+struct SahBuilder
+{
+    const std::vector<LeafRec>& leaves;
+    std::vector<int> order;          // permutation of leaf ordinals, partitioned in place
+    std::vector<float4>& out;        // binary list: leaf nodes carry (leaf ordinal, -1) in (w0, w1) -> see below
+    std::vector<int>& leafOfNode;    // per emitted node: leaf ordinal or -1
+    SahBuilder(const std::vector<LeafRec>& l, std::vector<float4>& o, std::vector<int>& lon) : leaves(l), out(o), leafOfNode(lon)
+    {
+        order.resize(l.size());
+        for (size_t i = 0; i < l.size(); ++i) order[i] = (int)i;
+    }
+    int emit(const Aabb& b, int w0, int w1, int leaf)
+    {
+        const int at = (int)(out.size() / 2);
+        out.push_back(make_float4(b.lo[0], b.lo[1], b.lo[2], intBits(w0)));
+        out.push_back(make_float4(b.hi[0], b.hi[1], b.hi[2], intBits(w1)));
+        leafOfNode.push_back(leaf);
+        return at;
+    }
+    void build(int i, int j, int depth)
+    {
+        if (j - i == 1)
+        {
+            const LeafRec& l = leaves[order[i]];
+            emit(l.box, l.start, l.count, order[i]);
+            return;
+        }
+        Aabb all = leaves[order[i]].box, cb;
+        for (int k = 0; k < 3; ++k) cb.lo[k] = 3e38f, cb.hi[k] = -3e38f;
+        for (int k = i; k < j; ++k)
+        {
+            const Aabb& b = leaves[order[k]].box;
+            all.grow(b);
+            for (int a = 0; a < 3; ++a)
+            {
+                const float c = 0.5f * (b.lo[a] + b.hi[a]);
+                cb.lo[a] = c < cb.lo[a] ? c : cb.lo[a]; cb.hi[a] = c > cb.hi[a] ? c : cb.hi[a];
+            }
+        }
+        int mid = (i + j) / 2;
+        const int NB = 16;
+        double bestCost = 1e300; int bestAxis = -1, bestBin = -1;
+        if (depth < 60)
+            for (int a = 0; a < 3; ++a)
+            {
+                const float ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0.f)) continue;
+                Aabb bb[NB]; int cnt[NB];
+                for (int b = 0; b < NB; ++b) { cnt[b] = 0; for (int k = 0; k < 3; ++k) bb[b].lo[k] = 3e38f, bb[b].hi[k] = -3e38f; }
+                for (int k = i; k < j; ++k)
+                {
+                    const Aabb& b = leaves[order[k]].box;
+                    int bin = (int)(NB * ((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) / ext));
+                    bin = bin < 0 ? 0 : (bin >= NB ? NB - 1 : bin);
+                    cnt[bin]++; bb[bin].grow(b);
+                }
+                Aabb right[NB]; int rc[NB];
+                Aabb acc; for (int k = 0; k < 3; ++k) acc.lo[k] = 3e38f, acc.hi[k] = -3e38f;
+                int c = 0;
+                for (int b = NB - 1; b > 0; --b) { if (cnt[b]) acc.grow(bb[b]); c += cnt[b]; right[b] = acc; rc[b] = c; }
+                for (int k = 0; k < 3; ++k) acc.lo[k] = 3e38f, acc.hi[k] = -3e38f;
+                c = 0;
+                for (int b = 0; b < NB - 1; ++b)
+                {
+                    if (cnt[b]) acc.grow(bb[b]);
+                    c += cnt[b];
+                    if (c == 0 || rc[b + 1] == 0) continue;
+                    const double cost = acc.area() * c + right[b + 1].area() * rc[b + 1];
+                    if (cost < bestCost) { bestCost = cost; bestAxis = a; bestBin = b; }
+                }
+            }
+        if (bestAxis >= 0)
+        {
+            const int a = bestAxis;
+            const float ext = cb.hi[a] - cb.lo[a];
+            auto binOf = [&](int leaf) {
+                const Aabb& b = leaves[leaf].box;
+                int bin = (int)(NB * ((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) / ext));
+                return bin < 0 ? 0 : (bin >= NB ? NB - 1 : bin);
+            };
+            int l = i, r = j - 1;
+            while (l <= r)
+            {
+                if (binOf(order[l]) <= bestBin) ++l;
+                else { std::swap(order[l], order[r]); --r; }
+            }
+            if (l > i && l < j) mid = l;
+        }
+        const int at = emit(all, 0, 0, -1);
+        build(i, mid, depth + 1);
+        build(mid, j, depth + 1);
+        out[2 * (size_t)at].w = intBits((int)(out.size() / 2) - at);
+    }
+};
+
 int g_useWide = 1;
+int g_useUnordered = 1;
+int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
 } // namespace
 
 // Box re-layout shared by h2d_scene and the host-only debug entry point (tests check it without a GPU).
-static int relayoutBoxes(const b200_BoundingBox* boxes, int nbBoxes, std::vector<float4>& packed, int* layoutUsed = nullptr)
+static int relayoutBoxes(const b200_BoundingBox* boxes, int nbBoxes, std::vector<float4>& packed, int* layoutUsed = nullptr,
+                         std::vector<LeafRec>* leavesOut = nullptr)
 {
     if (g_boxLayout != 1)
     {
-        std::vector<LeafRec> leaves;
+        std::vector<LeafRec> leavesLocal;
+        std::vector<LeafRec>& leaves = leavesOut ? *leavesOut : leavesLocal;
+        leaves.clear();
         const bool contained = collectLeaves(boxes, nbBoxes, leaves);
         if ((contained || g_boxLayout == 2) && !leaves.empty())
         {
@@ -637,6 +769,8 @@ void b200_set_option(int key, int value)
     if (key == 1 && value >= 0 && value <= 2) g_boxLayout = value;
     else if (key == 2) g_packetMask = value & 0xF;
     else if (key == 3) g_useWide = value != 0;
+    else if (key == 4) g_useUnordered = value != 0;
+    else if (key == 5) g_useBackward = value != 0;
     else latch(-11, "b200_set_option", "unknown option");
 }
 void b200_set_partition(int rank, int world)
@@ -664,8 +798,8 @@ void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
     CK(cudaEventCreate(&G.evStart));
     CK(cudaEventCreate(&G.evStop));
     CK(cudaMalloc(&G.dTileCounter, sizeof(unsigned int)));
-    CK(cudaMalloc(&G.dWork, 2 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(G.dWork, 0, 2 * sizeof(unsigned long long), G.stream));
+    CK(cudaMalloc(&G.dWork, 8 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(G.dWork, 0, 8 * sizeof(unsigned long long), G.stream));
     CK(cudaMalloc(&G.dLights, B200_NB_MAX_LIGHTINFORMATIONS * sizeof(b200_LightInformation)));
     CK(cudaMemsetAsync(G.dLights, 0, B200_NB_MAX_LIGHTINFORMATIONS * sizeof(b200_LightInformation), G.stream));
     int perSM = 0;
@@ -682,6 +816,7 @@ void b200_finalize_scene(b200_int2)
     cudaDeviceSynchronize();
     unregisterHost();
     freeDev(G.dWide); freeDev(G.dLeafRecs); G.capWide = G.capLeafRecs = 0; G.nbWide = 0;
+    freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
     freeDev(G.dTileCounter); freeDev(G.dWork);
@@ -730,7 +865,8 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     G.nbBoxesIn = nbBoxes;
 
     std::vector<float4> packed;
-    const int nOut = relayoutBoxes(boxes, nbBoxes, packed, &G.boxLayoutUsed);
+    std::vector<LeafRec> leaves;
+    const int nOut = relayoutBoxes(boxes, nbBoxes, packed, &G.boxLayoutUsed, &leaves);
 
     // 2b. the 4-wide form of the ordered BVH for the per-lane walks
     std::vector<float4> wide, leafRecs;
@@ -739,6 +875,125 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     if (leafRecs.size() > G.capLeafRecs) { freeDev(G.dLeafRecs); G.capLeafRecs = leafRecs.size() + 1024; CK(cudaMalloc(&G.dLeafRecs, G.capLeafRecs * sizeof(float4))); }
     if (!wide.empty()) CK(cudaMemcpyAsync(G.dWide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
     if (!leafRecs.empty()) CK(cudaMemcpyAsync(G.dLeafRecs, leafRecs.data(), leafRecs.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+    // 2c. the unordered SAH BVH for the order-independent walks: over PRIMITIVES with tight boxes, not over the reference's
+    //     leaves — level-0 cell keys wrap modulo 2^32 (GPUKernel.cpp:938-941), so in large scenes a reference leaf can hold
+    //     primitives from distant cells and span a large part of the scene.  The reference leaf each primitive belongs to is
+    //     kept (primLeaf) because a hit only counts if that leaf's box passes the reference's slab test.
+    std::vector<float4> ubin, uwide, xbin, xwide;
+    std::vector<int> primLeaf(nbPrims > 0 ? nbPrims : 1, 0);
+    G.nbUWide = 0; G.nbUX = 0;
+    if (G.boxLayoutUsed == 2 && G.nbWide > 0 && g_useUnordered && nbPrims > 0)
+    {
+        for (size_t l = 0; l < leaves.size(); ++l)
+            for (int k = 0; k < leaves[l].count; ++k)
+                if (leaves[l].start + k >= 0 && leaves[l].start + k < nbPrims) primLeaf[leaves[l].start + k] = (int)l;
+        std::vector<LeafRec> primBoxes(nbPrims), extBoxes;
+        for (int i = 0; i < nbPrims; ++i)
+        {
+            const b200_Primitive& p = prims[i];
+            Aabb b;
+            const float P0[3] = {p.p0.x, p.p0.y, p.p0.z}, P1[3] = {p.p1.x, p.p1.y, p.p1.z}, P2[3] = {p.p2.x, p.p2.y, p.p2.z};
+            const float S[3] = {p.size.x, p.size.y, p.size.z};
+            for (int a = 0; a < 3; ++a)
+            {
+                float lo, hi;
+                switch (p.type)
+                {
+                case B200_PT_TRIANGLE: lo = fminf(fminf(P0[a], P1[a]), P2[a]); hi = fmaxf(fmaxf(P0[a], P1[a]), P2[a]); break;
+                case B200_PT_CYLINDER:
+                case B200_PT_CONE: lo = fminf(P0[a], P1[a]) - fabsf(S[0]); hi = fmaxf(P0[a], P1[a]) + fabsf(S[0]); break;
+                case B200_PT_SPHERE:
+                case B200_PT_ENVIRONMENT: lo = P0[a] - fabsf(S[0]); hi = P0[a] + fabsf(S[0]); break;
+                default: lo = P0[a] - fabsf(S[a]); hi = P0[a] + fabsf(S[a]); break; // ellipsoid, planes
+                }
+                // conservative: hit points are computed in float and the cylinder caps accept +-geometryEpsilon
+#ifndef UW_PAD
+#define UW_PAD 0.02f
+#endif
+                const float pad = UW_PAD + 2e-5f * fmaxf(fabsf(lo), fabsf(hi));
+                b.lo[a] = lo - pad; b.hi[a] = hi + pad;
+            }
+            primBoxes[i].box = b; primBoxes[i].start = i; primBoxes[i].count = 1;
+            // Cylinders and cones also register hits BEHIND the origin: the reference only requires the closest approach of
+            // the two lines to lie ahead (t >= 0, GeometryIntersections.cuh:316,381) and takes the entry point t - s
+            // whatever its sign, measuring its distance with length() (:690-760).  That needs the origin inside the
+            // infinite cylinder, and — because the leaf box must still be ahead (t_max > 0) while the hit point behind the
+            // origin lies in it — inside the (convex) leaf box.  Those primitives get a second box, grown over {points of
+            // the leaf box within one radius of the axis}; the walks look up the boxes that CONTAIN the ray origin in a
+            // separate small tree (a point query) and accept backward hits only from there.
+            if ((p.type == B200_PT_CYLINDER || p.type == B200_PT_CONE) && (p.n1.x != 0.f || p.n1.y != 0.f || p.n1.z != 0.f))
+            {
+                Aabb L = leaves[primLeaf[i]].box;
+                L.grow(b); // cone leaves are built from p0 only (GPUKernel.cpp:808-811)
+                const double N[3] = {p.n1.x, p.n1.y, p.n1.z};
+                const double R = fmax(fabs((double)S[0]), fabs((double)S[1])) * 1.001 + 0.05;
+                double u0 = -1e300, u1 = 1e300;
+                bool empty = false;
+                for (int a = 0; a < 3 && !empty; ++a)
+                {
+                    const double slack = R + 1e-5 * fmax(fabs((double)L.lo[a]), fabs((double)L.hi[a]));
+                    const double lo = L.lo[a] - slack, hi = L.hi[a] + slack;
+                    if (fabs(N[a]) < 1e-9) { empty = P0[a] < lo || P0[a] > hi; continue; }
+                    double ua = (lo - P0[a]) / N[a], ub = (hi - P0[a]) / N[a];
+                    if (ua > ub) std::swap(ua, ub);
+                    u0 = fmax(u0, ua); u1 = fmin(u1, ub);
+                }
+                if (!empty && u0 <= u1 && u0 > -1e299 && u1 < 1e299)
+                {
+                    // a thin diagonal region: cover it with short pieces, each in its own box (an origin near a joint lies
+                    // in two of them; the walk drops the duplicate)
+                    int pieces = (int)ceil((u1 - u0) / (4.0 * R));
+                    pieces = pieces < 1 ? 1 : (pieces > 64 ? 64 : pieces);
+                    for (int k = 0; k < pieces; ++k)
+                    {
+                        const double ua = u0 + (u1 - u0) * k / pieces, ub = u0 + (u1 - u0) * (k + 1) / pieces;
+                        LeafRec x; x.start = i; x.count = 1;
+                        for (int a = 0; a < 3; ++a)
+                        {
+                            const double e0 = P0[a] + ua * N[a], e1 = P0[a] + ub * N[a];
+                            const double slack = R + 1e-5 * fmax(fabs(e0), fabs(e1));
+                            x.box.lo[a] = (float)(fmin(e0, e1) - slack);
+                            x.box.hi[a] = (float)(fmax(e0, e1) + slack);
+                        }
+                        extBoxes.push_back(x);
+                    }
+                }
+            }
+        }
+        std::vector<int> leafOfNode;
+        ubin.reserve(4 * (size_t)nbPrims);
+        SahBuilder sb(primBoxes, ubin, leafOfNode);
+        sb.build(0, nbPrims, 0);
+        std::vector<float4> unusedLeafRecs;
+        G.nbUWide = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode);
+        if (!extBoxes.empty())
+        {
+            std::vector<int> leafOfNodeX, primOfNode;
+            SahBuilder sx(extBoxes, xbin, leafOfNodeX);
+            sx.build(0, (int)extBoxes.size(), 0);
+            primOfNode.resize(leafOfNodeX.size());
+            for (size_t k = 0; k < leafOfNodeX.size(); ++k) primOfNode[k] = leafOfNodeX[k] < 0 ? -1 : extBoxes[leafOfNodeX[k]].start;
+            G.nbUX = buildWide(xbin, xwide, unusedLeafRecs, &primOfNode);
+            // appended to the first tree: inner refs move by its size, leaf refs get bit 30
+            for (int k = 0; k < G.nbUX; ++k)
+            {
+                float4& rf = xwide[8 * (size_t)k + 6];
+                float* f[4] = {&rf.x, &rf.y, &rf.z, &rf.w};
+                for (int c = 0; c < 4; ++c)
+                {
+                    int v; memcpy(&v, f[c], 4);
+                    if (v == (int)0x80000000) continue;
+                    v = v >= 0 ? v + G.nbUWide : ~((~v) | 0x40000000);
+                    memcpy(f[c], &v, 4);
+                }
+            }
+            uwide.insert(uwide.end(), xwide.begin(), xwide.end());
+        }
+    }
+    if ((size_t)nbPrims > G.capPrimLeaf) { freeDev(G.dPrimLeaf); G.capPrimLeaf = (size_t)nbPrims + 1024; CK(cudaMalloc(&G.dPrimLeaf, G.capPrimLeaf * sizeof(int))); }
+    if (nbPrims > 0) CK(cudaMemcpyAsync(G.dPrimLeaf, primLeaf.data(), (size_t)nbPrims * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+    if (uwide.size() > G.capUWide) { freeDev(G.dUWide); G.capUWide = uwide.size() + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
+    if (!uwide.empty()) CK(cudaMemcpyAsync(G.dUWide, uwide.data(), uwide.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
     CK(cudaStreamSynchronize(G.stream));
 
     // 3. primitives
@@ -871,6 +1126,9 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.scene.mats = G.dMats; P.scene.lights = G.dLights; P.scene.lightInfoSize = objects.w; P.scene.nbLamps = objects.z;
     P.scene.tex = G.dTex; P.scene.randoms = G.dRandoms; P.scene.randomTableSize = G.maxW * G.maxH;
     P.scene.wnodes = G.dWide; P.scene.leafRecs = G.dLeafRecs; P.scene.nbWide = g_useWide ? G.nbWide : 0;
+    P.scene.primLeaf = G.dPrimLeaf;
+    P.scene.uwnodes = G.dUWide; P.scene.nbUWide = (g_useWide && g_useUnordered) ? G.nbUWide : 0; P.scene.opaqueShadows = G.opaqueShadows;
+    P.scene.nbUX = g_useBackward ? G.nbUX : 0;
     P.scene.rawBoxes = G.dRawBoxes; P.scene.nbRawBoxes = objects.x < G.nbBoxesIn ? objects.x : G.nbBoxesIn;
     P.si = si; P.pp = pp;
     P.eye = make_float3(origin.x, origin.y, origin.z);
@@ -925,6 +1183,16 @@ void b200_d2h_bitmap(b200_int2, b200_SceneInfo si, b200_BitmapBuffer* bitmap, b2
     CK(cudaStreamSynchronize(G.stream));
 }
 
+void b200_debug_counters(unsigned long long* out8)
+{
+    if (G.dWork && ensureDevice())
+    {
+        CK(cudaStreamSynchronize(G.stream));
+        CK(cudaMemcpyAsync(out8, G.dWork, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, G.stream));
+        CK(cudaStreamSynchronize(G.stream));
+    }
+}
+
 void b200_d2h_post(b200_SceneInfo si, b200_PostProcessingBuffer* post)
 {
     if (!G.dPost || !ensureDevice()) { latch(-4, "b200_d2h_post", "reshape_scene not called"); return; }
@@ -950,7 +1218,7 @@ void b200_get_counters(unsigned long long* rays, unsigned long long* pixels, int
         CK(cudaStreamSynchronize(G.stream));
         CK(cudaMemcpyAsync(h, G.dWork, sizeof(h), cudaMemcpyDeviceToHost, G.stream));
         CK(cudaStreamSynchronize(G.stream));
-        if (reset) CK(cudaMemsetAsync(G.dWork, 0, sizeof(h), G.stream));
+        if (reset) CK(cudaMemsetAsync(G.dWork, 0, 8 * sizeof(unsigned long long), G.stream));
     }
     if (rays) *rays = h[0];
     if (pixels) *pixels = h[1];
@@ -984,8 +1252,34 @@ int b200_debug_relayout_boxes(const b200_BoundingBox* boxes, int nbBoxes, float*
     return nOut;
 }
 
+int b200_debug_build_unordered(const b200_BoundingBox* boxes, int nbBoxes, float* outPacked, int capacityBoxes)
+{
+    std::vector<float4> packed, ubin;
+    std::vector<LeafRec> leaves;
+    int used = 0;
+    relayoutBoxes(boxes, nbBoxes, packed, &used, &leaves);
+    if (used != 2 || leaves.empty()) return 0;
+    std::vector<int> leafOfNode;
+    SahBuilder sb(leaves, ubin, leafOfNode);
+    sb.build(0, (int)leaves.size(), 0);
+    const int n = (int)(ubin.size() / 2);
+    if (outPacked && n <= capacityBoxes) memcpy(outPacked, ubin.data(), ubin.size() * sizeof(float4));
+    return n;
+}
+
 void b200_synchronize(void)
 {
     if (G.stream && ensureDevice()) CK(cudaStreamSynchronize(G.stream));
 }
 }
+
+#ifdef SOLR_DEBUG_SHADOWCMP
+extern "C" int b200_debug_shadowcmp(float* out)
+{
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_dbgN, sizeof(int));
+    cudaMemcpyFromSymbol(out, g_dbgRec, sizeof(float) * 64 * 32);
+    return n;
+}
+#endif

@@ -751,6 +751,7 @@ void b200h_get_scene(void* h, b200h_Scene* out)
     out->treeDepth = s->treeDepth();
 }
 void b200h_set_randoms(void* h, const float* r, long n, int timestamp) { static_cast<SceneHost*>(h)->setRandoms(r, (size_t)n, timestamp); }
+void b200h_set_capacity(void* h, long maxBoxes, long maxPrimitives) { static_cast<SceneHost*>(h)->setCapacity((size_t)maxBoxes, (size_t)maxPrimitives); }
 void b200h_set_limits(void* h, int w, int hh) { static_cast<SceneHost*>(h)->setLimits(w, hh); }
 void b200h_set_partition(void* h, int rank, int world) { static_cast<SceneHost*>(h)->setPartition(rank, world); }
 void b200h_set_device(void* h, int device) { static_cast<SceneHost*>(h)->setDevice(device); }

@@ -72,6 +72,9 @@ public:
 
     // ---- frame (CudaKernel interface) ----
     void setLimits(int maxWidth, int maxHeight);
+    // box / primitive capacity of the flattened arrays; default = the reference's NB_MAX_BOXES / NB_MAX_PRIMITIVES (2.5 M,
+    // Consts.h:32-33), at which compactBoxes silently drops boxes for ~1 M-primitive scenes (SURVEY finding 4)
+    void setCapacity(size_t maxBoxes, size_t maxPrimitives) { m_maxBoxes = maxBoxes; m_maxPrimitives = maxPrimitives; }
     void setPartition(int rank, int worldSize);
     void setDevice(int device);
     void initBuffers();

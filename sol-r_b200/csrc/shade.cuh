@@ -255,6 +255,10 @@ SB_DEV float4 intersectionShader(const b200_Primitive& p, const b200_Material& m
     return col;
 }
 
+#ifdef SOLR_DEBUG_SHADOWCMP
+__device__ float g_dbgRec[64 * 32];
+__device__ int g_dbgN;
+#endif
 SB_DEV float rnd(const int i) { return __ldg(cS.randoms + i); }
 
 // Shadow ray of one shaded hit: packet walk when the policy says so for this ray class, else per lane.
@@ -268,7 +272,57 @@ SB_DEV float4 traceShadow(const float3 center, const float3 I, const int lightId
         if (__any_sync(FULL_MASK, need)) sh = shadowWalkPacket(center, I, lightId, iteration, objectId, need);
     }
     else if (need)
-        sh = (cS.nbWide > 0) ? shadowWalkWide(center, I, lightId, iteration, objectId) : shadowWalk(center, I, lightId, iteration, objectId);
+    {
+        if (cS.nbUWide > 0)
+        {
+            // |direction| = distance to the lamp; any-hit is exact when every caster is opaque
+            const float3 d = center - I;
+            bool ordered = true;
+            if (cS.opaqueShadows && dot(d, d) >= 1.0002f)
+            {
+                sh.w = unorderedWalk(UW_SHADOW, I + normalize(d) * cSI.rayEpsilon, d, iteration, 0, lightId, objectId).shadow;
+                ordered = sh.w < 0.f; // stack overflow in a degenerate tree
+#ifdef SOLR_DEBUG_SHADOWCMP
+                if (!ordered)
+                {
+                    const float4 so = shadowWalkWide(center, I, lightId, iteration, objectId);
+                    if (so.w != sh.w)
+                    {
+                        const int slot = atomicAdd(&g_dbgN, 1);
+                        if (slot < 64)
+                        {
+                            float* o = g_dbgRec + 32 * slot;
+                            Ray r; makeRay(r, I + normalize(d) * cSI.rayEpsilon, d);
+                            o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = d.x; o[4] = d.y; o[5] = d.z; o[6] = so.w; o[7] = sh.w;
+                            o[8] = (float)lightId; o[9] = (float)objectId;
+                            int nb = 0;
+                            const float lenOL = length(r.d);
+                            for (int idx = 0; idx < cS.nbPrimitives && nb < 4; ++idx)
+                            {
+                                const int meta = cS.meta[idx];
+                                const int origIndex = cS.prims[idx].index;
+                                if (PM_FAST(meta) != 0 || origIndex == lightId || origIndex == objectId) continue;
+                                float3 P; int fl; float ps;
+                                if (!primitiveTest(idx, meta, r, P, fl, ps)) continue;
+                                const float l = length(P - r.o);
+                                if (!(l > cSI.geometryEpsilon && l < lenOL)) continue;
+                                const int leaf = cS.primLeaf[idx];
+                                float lt;
+                                const bool lp = slabT(cS.leafRecs[2 * leaf], cS.leafRecs[2 * leaf + 1], r, cSI.viewDistance, lt);
+                                o[10 + 5 * nb] = (float)idx; o[11 + 5 * nb] = l; o[12 + 5 * nb] = (float)PM_TYPE(meta); o[13 + 5 * nb] = lp ? 1.f : 0.f; o[14 + 5 * nb] = lt;
+                                ++nb;
+                            }
+                            o[30] = (float)nb; o[31] = lenOL;
+                        }
+                    }
+                }
+#endif
+            }
+            if (ordered) sh = shadowWalkWide(center, I, lightId, iteration, objectId);
+        }
+        else
+            sh = (cS.nbWide > 0) ? shadowWalkWide(center, I, lightId, iteration, objectId) : shadowWalk(center, I, lightId, iteration, objectId);
+    }
     return sh;
 }
 
@@ -431,7 +485,14 @@ SB_DEV Hit traceClosest(const float3 o, const float3 t, const int iteration, con
         if (__any_sync(FULL_MASK, need)) hit = closestHitPacket(o, t, iteration, matId, need);
     }
     else if (need)
-        hit = (cS.nbWide > 0) ? closestHitWide(o, t, iteration, matId) : closestHit(o, t, iteration, matId);
+    {
+        if (cS.nbUWide > 0)
+        {
+            hit = closestHitOrderIndependent(o, t, iteration, matId);
+        }
+        else
+            hit = (cS.nbWide > 0) ? closestHitWide(o, t, iteration, matId) : closestHit(o, t, iteration, matId);
+    }
     return hit;
 }
 
@@ -453,8 +514,10 @@ SB_DEV float4 launchRayTracing(const bool valid, const int index, const float3 r
     int currentMaterialId = -2;
     float colorContributions[B200_NB_MAX_ITERATIONS + 1];
     float4 colors[B200_NB_MAX_ITERATIONS + 1];
-#pragma unroll
-    for (int i = 0; i <= B200_NB_MAX_ITERATIONS; ++i) { colorContributions[i] = 0.f; colors[i] = f4(0.f, 0.f, 0.f, 0.f); }
+    // The reference zero-fills both arrays (:94-95); every entry read below (fold over 0..iteration-1, the reflected-ray and GI
+    // updates of entries already produced) is written by the pass that produced it, so only entry 0 needs a defined value
+    // for lanes that own no pixel.
+    colors[0] = f4(0.f, 0.f, 0.f, 0.f); colorContributions[0] = 0.f;
     float4 recursiveBlinn = f4(0.f, 0.f, 0.f, 0.f);
     float shadowIntensity = 0.f;
     float3 reflectedTarget = f3(0.f, 0.f, 0.f);

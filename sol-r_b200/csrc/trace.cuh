@@ -46,6 +46,15 @@ struct SceneDev
     const float4* __restrict__ wnodes;
     const float4* __restrict__ leafRecs; // [2*nbLeaves] (min.xyz, first primitive) (max.xyz, count): the reference's leaf boxes, in array order
     int nbWide;
+    // unordered 4-wide BVH (binned SAH, no ordering constraint) over the same leaf records, for the walks whose result
+    // does not depend on the visiting order
+    const float4* __restrict__ uwnodes; // leaves are single primitives (ref = ~primitive index), boxes are tight per-primitive boxes
+    const int* __restrict__ primLeaf;   // [nbPrimitives] reference leaf (index into leafRecs) each primitive belongs to
+    int nbUWide;
+    // second unordered tree over the grown boxes of cylinders/cones (engine.cu step 2c): the boxes containing a ray's origin are
+    // the only primitives that can register a hit behind it
+    int nbUX; // its nodes follow the first tree's in uwnodes (root = nbUWide); leaf refs carry bit 30
+    int opaqueShadows; // every shadow caster blocks fully (no transparent material, no textured plane): any-hit is exact
 };
 
 // The walks are kept out of line by default (one copy each, own register allocation); -DWALK_INLINE=__forceinline__ to compare.
@@ -984,4 +993,284 @@ __device__ WALK_INLINE float4 shadowWalkWide(const float3 lampCenter, const floa
     }
     result = fmaxf(0.f, fminf(result, shadowLimit));
     return f4(color.x, color.y, color.z, result);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Order-independent walks.
+//
+// The reference's closest hit is "the last candidate accepted in array order": a candidate is tested iff its leaf
+// box passes (slab hit, t_min < closest-so-far, t_max > 0) and accepted iff eps < distance < closest-so-far
+// (GeometryIntersections.cuh:690,749-760).  Box t is in units of |direction| while the closest distance is in
+// world units (SURVEY finding 7).  When |direction| >= 1, t_min <= world entry distance <= the distance of any
+// hit inside the leaf, so the leaf test can never reject a candidate that would be accepted: the result is simply
+// the minimum-distance candidate, ties to the lowest array index — independent of the visiting order.  Primary rays
+// (|direction| ~ eye distance) and shadow rays (|direction| = distance to the lamp) are of this kind; they walk an
+// unconstrained SAH BVH front to back and cull by the best distance found.  Secondary rays have |direction| =
+// 1 - rayEpsilon < 1: for those every candidate along the ray is gathered (any order), sorted by array index and the
+// reference's accept/reject sequence is replayed exactly, including its per-leaf t_min < closest-so-far test.
+// Shadow walks accumulate blocker opacity until it saturates (:815-905); when every caster is opaque the first
+// blocker found — in any order — saturates it, otherwise the ordered walk is used.
+// ---------------------------------------------------------------------------------------------------
+#define UN_STACK 48
+#ifdef SOLR_DEBUG_COUNTERS
+#define DBG_ADD(i, v) atomicAdd(cP.workCounters + (i), (unsigned long long)(v))
+#else
+#define DBG_ADD(i, v)
+#endif
+#define GATHER_CAP 24
+
+// slab test that also returns t_min (same arithmetic as slab())
+SB_DEV bool slabT(const float4 lo, const float4 hi, const Ray& r, const float t1, float& tminOut)
+{
+    const bool sx = r.inv.x < 0.f, sy = r.inv.y < 0.f, sz = r.inv.z < 0.f;
+    const float txmin = ((sx ? hi.x : lo.x) - r.o.x) * r.inv.x;
+    const float txmax = ((sx ? lo.x : hi.x) - r.o.x) * r.inv.x;
+    const float tymin = ((sy ? hi.y : lo.y) - r.o.y) * r.inv.y;
+    const float tymax = ((sy ? lo.y : hi.y) - r.o.y) * r.inv.y;
+    const float tzmin = ((sz ? hi.z : lo.z) - r.o.z) * r.inv.z;
+    const float tzmax = ((sz ? lo.z : hi.z) - r.o.z) * r.inv.z;
+    const bool missXY = (txmin > tymax) | (tymin > txmax);
+    const float tmin = (tymin > txmin) ? tymin : txmin;
+    const float tmax = (tymax < txmax) ? tymax : txmax;
+    const bool missZ = (tmin > tzmax) | (tzmin > tmax);
+    const float tmin2 = (tzmin > tmin) ? tzmin : tmin;
+    const float tmax2 = (tzmax < tmax) ? tzmax : tmax;
+    tminOut = tmin2;
+    return !missXY & !missZ & (tmin2 < t1) & (tmax2 > 0.f);
+}
+
+// tests the four children of an unordered node against [0, tLimit]; pushes the hits far-to-near (nearest on top)
+SB_DEV bool wideStepSorted(const float4* __restrict__ n, const WideRay& w, const Ray& r, const float tLimit, int* stackRef, float* stackT, int& sp)
+{
+    const float4 ax = __ldg(n + w.nx), bx = __ldg(n + w.fx);
+    const float4 ay = __ldg(n + w.ny), by = __ldg(n + w.fy);
+    const float4 az = __ldg(n + w.nz), bz = __ldg(n + w.fz);
+    const int4 refs = __ldg(reinterpret_cast<const int4*>(n + 6));
+    float t0, t1, t2, t3;
+#define UN_CHILD(C, T)                                                                                               \
+    {                                                                                                                \
+        const float tnx = (ax.C - r.o.x) * r.inv.x, tfx = (bx.C - r.o.x) * r.inv.x;                                  \
+        const float tny = (ay.C - r.o.y) * r.inv.y, tfy = (by.C - r.o.y) * r.inv.y;                                  \
+        const float tnz = (az.C - r.o.z) * r.inv.z, tfz = (bz.C - r.o.z) * r.inv.z;                                  \
+        const float tmin = fmaxf(fmaxf(tnx, tny), tnz), tmax = fminf(fminf(tfx, tfy), tfz);                          \
+        T = ((tmin <= tmax) & (tmin <= tLimit) & (tmax > 0.f)) ? tmin : 3.0e38f;                                     \
+    }
+    UN_CHILD(x, t0) UN_CHILD(y, t1) UN_CHILD(z, t2) UN_CHILD(w, t3)
+#undef UN_CHILD
+    int r0 = refs.x, r1 = refs.y, r2 = refs.z, r3 = refs.w;
+    // sorting network, descending t (farthest first)
+#define UN_CSWAP(TA, RA, TB, RB) if (TA < TB) { const float tt = TA; TA = TB; TB = tt; const int rr = RA; RA = RB; RB = rr; }
+    UN_CSWAP(t0, r0, t1, r1) UN_CSWAP(t2, r2, t3, r3) UN_CSWAP(t0, r0, t2, r2) UN_CSWAP(t1, r1, t3, r3) UN_CSWAP(t1, r1, t2, r2)
+#undef UN_CSWAP
+    // each level leaves <= 3 entries behind, so UN_STACK - 4 is only exceeded by a degenerate (very deep) tree: the caller
+    // then abandons this walk for the ordered one
+    if (sp > UN_STACK - 4) return false;
+    if (t0 < 3.0e38f) { stackRef[sp] = r0; stackT[sp] = t0; ++sp; }
+    if (t1 < 3.0e38f) { stackRef[sp] = r1; stackT[sp] = t1; ++sp; }
+    if (t2 < 3.0e38f) { stackRef[sp] = r2; stackT[sp] = t2; ++sp; }
+    if (t3 < 3.0e38f) { stackRef[sp] = r3; stackT[sp] = t3; ++sp; }
+    return true;
+}
+
+// One walk for the three order-independent ray classes (one copy of the node loop and of the primitive tests keeps the
+// instruction working set small — the megakernel is bound by instruction-cache misses otherwise, profiles/r01_history.md):
+//   UW_CLOSEST  |direction| >= 1: minimum distance, ties to the lowest array index; culls by the best distance found
+//   UW_GATHER   |direction| <  1: gathers the candidates within GATHER_WINDOW x the closest distance, replays the
+//               reference's accept/reject sequence in array order (see below); falls back to the ordered walk on overflow
+//   UW_SHADOW   every caster opaque: the first blocker between the point and the lamp saturates the shadow
+//
+// Which candidates can matter for UW_GATHER: with L = |direction| (0.95 for bounce rays), a leaf is skipped when
+// t_min(leaf) >= closest-so-far, i.e. when its world entry distance is >= L * closest-so-far.  A candidate X can change the
+// fate of a candidate Y only if Y's leaf entry is within [L*d_X, d_X), so influence only reaches candidates whose distances
+// are chained by ratios <= 1/L.  Sorting the candidates by distance, everything beyond the first gap wider than 1/L is
+// inert: it can neither win nor hide anything that can.  The walk keeps every candidate within GATHER_WINDOW x the closest
+// distance (1.5 = eight links of such a chain, each of which would additionally need a matching array order and leaf
+// entry); the ordered walk (option key 4 = 0) is the literal form and tests compare the two.
+#define GATHER_WINDOW 1.5f
+#define UW_CLOSEST 0
+#define UW_GATHER 1
+#define UW_SHADOW 2
+
+// forward: ordered fallback
+__device__ WALK_INLINE Hit closestHitWide(const float3 origin, const float3 target, const int iteration, const int currentMaterialId);
+
+struct WalkOut { Hit hit; float shadow; };
+
+__device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOrigin, const float3 rayDir, const int iteration,
+                                              const int currentMaterialId, const int lightId, const int objectId)
+{
+    WalkOut out;
+    out.hit.prim = -1; out.hit.p = f3(0.f, 0.f, 0.f); out.hit.flags = 0; out.shadow = 0.f;
+    const float minDistance0 = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
+    const float shadowLimit = cSI.shadowIntensity;
+    if (mode == UW_SHADOW && !(0.f < shadowLimit)) return out;
+    Ray r;
+    makeRay(r, rayOrigin, rayDir);
+    WideRay w;
+    wideRows(w, r);
+    const float eps = cSI.geometryEpsilon;
+    const float len2 = dot(r.d, r.d);
+    const float invLen = rsqrtf(len2) * 1.0001f; // world distance -> t, with slack so culling stays conservative
+    const float lenOL = sqrtf(len2);             // shadow: distance to the lamp (length(O_L), :877)
+    const float4* __restrict__ leafRecs = cS.leafRecs;
+    const int* __restrict__ metas = cS.meta;
+    const bool extended = cSI.extendedGeometry != 0;
+    int stackRef[UN_STACK];
+    float stackT[UN_STACK];
+    int sp = 1;
+    stackRef[0] = 0; stackT[0] = 0.f;
+    int candIdx[GATHER_CAP], candLeaf[GATHER_CAP];
+    float candD[GATHER_CAP], candLeafT[GATHER_CAP];
+    int n = 0;
+    bool overflow = false;
+    float best = minDistance0;   // closest accepted / gathered distance so far
+    float window = minDistance0; // UW_GATHER: candidates farther than this are inert
+    // entry-t bound for nodes: never beyond the reference's own t_min < closest-so-far test; a shadow blocker lies before the lamp (t ~ 1)
+#ifndef UW_SHADOW_TLIMIT
+#define UW_SHADOW_TLIMIT 1.001f
+#endif
+    float cullT = (mode == UW_SHADOW) ? fminf(minDistance0, UW_SHADOW_TLIMIT) : fminf(minDistance0, minDistance0 * invLen);
+    if (mode == UW_GATHER) cullT = minDistance0;
+    // The node array holds two trees: the walk proper [0, nbUWide) and, behind it, the tree of grown cylinder/cone boxes.  The
+    // second is a point query — entry bound 0 keeps exactly the boxes that contain the origin — and only hits behind the origin
+    // count there; only hits ahead of it count in the first.
+    const float4* __restrict__ nodes = cS.uwnodes;
+    const int nbMain = cS.nbUWide;
+    if (cS.nbUX > 0) { stackRef[1] = nbMain; stackT[1] = -3.0e38f; sp = 2; }
+    bool done = false;
+    while (!done)
+    {
+        int cur = WIDE_NONE;
+        while (sp > 0)
+        {
+            --sp;
+            const int ref = stackRef[sp];
+            if (stackT[sp] > cullT) continue; // the bound shrank since this entry was pushed
+            if (ref < 0) { cur = ref; break; }
+            DBG_ADD(5, 1);
+            if (!wideStepSorted(nodes + 8 * ref, w, r, (ref >= nbMain) ? 0.f : cullT, stackRef, stackT, sp)) { overflow = true; sp = 0; }
+        }
+        if (overflow) break;
+        if (cur == WIDE_NONE) break;
+        // a BVH leaf is one primitive
+        {
+            const bool behind = ((~cur) & 0x40000000) != 0; // from the point-query tree
+            const int idx = (~cur) & 0x3FFFFFFF;
+            const int meta = __ldg(metas + idx);
+            const int fast = PM_FAST(meta);
+            bool test;
+            if (mode == UW_SHADOW)
+            {
+                const int origIndex = __ldg(&cS.prims[idx].index);
+                const int type = extended ? PM_TYPE(meta) : B200_PT_TRIANGLE;
+                // objectId is a compacted index compared with an original id — as the reference does (:829)
+                test = fast == 0 && origIndex != lightId && origIndex != objectId && type != B200_PT_CAMERA && type != B200_PT_ENVIRONMENT &&
+                       !(type == B200_PT_TRIANGLE && cSI.doubleSidedTriangles);
+            }
+            else
+                test = fast == 0 || (fast == 1 && currentMaterialId != PM_MATERIAL(meta));
+            if (!test) continue;
+            float3 I;
+            int flags;
+            float planeShadow;
+            DBG_ADD(7, 1);
+            if (!primitiveTest(idx, meta, r, I, flags, planeShadow)) continue;
+            const float distance = length(I - r.o);
+            if (!(distance > eps)) continue;
+            if ((dot(I - r.o, r.d) < 0.f) != behind) continue; // hits behind the origin (cylinders/cones only) come from the point query
+            // the reference only tests a primitive whose leaf box passes its slab test (:690); checked for hits only
+            const int leaf = __ldg(cS.primLeaf + idx);
+            const float4 lo = __ldg(leafRecs + 2 * leaf);
+            const float4 hi = __ldg(leafRecs + 2 * leaf + 1);
+            float leafT;
+            // (UW_CLOSEST: t_min(leaf) <= entry distance <= hit distance < closest-so-far whenever the hit would be accepted, so only the
+            //  geometric part of the leaf test can reject it)
+            if (!slabT(lo, hi, r, (mode == UW_CLOSEST) ? 3.0e38f : minDistance0, leafT)) continue;
+            if (mode == UW_SHADOW)
+            {
+                if (distance < lenOL) { out.shadow = fmaxf(0.f, fminf(shadowLimit, shadowLimit)); done = true; }
+            }
+            else if (mode == UW_CLOSEST)
+            {
+                if (distance < best || (distance == best && out.hit.prim >= 0 && idx < out.hit.prim))
+                {
+                    best = distance;
+                    out.hit.prim = idx; out.hit.p = I; out.hit.flags = flags;
+                    cullT = fminf(minDistance0, best * invLen);
+                }
+            }
+            else if (distance < minDistance0 && distance <= window)
+            {
+                if (distance < best)
+                {
+                    best = distance;
+                    window = fminf(minDistance0, GATHER_WINDOW * best);
+                    cullT = fminf(minDistance0, window * invLen);
+                    int m2 = 0; // drop what fell out of the window
+                    for (int j = 0; j < n; ++j)
+                        if (candD[j] <= window)
+                        {
+                            candIdx[m2] = candIdx[j]; candD[m2] = candD[j]; candLeafT[m2] = candLeafT[j]; candLeaf[m2] = candLeaf[j];
+                            ++m2;
+                        }
+                    n = m2;
+                }
+                bool dup = false; // the point-query tree lists a long cylinder once per piece
+                if (behind) for (int j = 0; j < n; ++j) dup |= candIdx[j] == idx;
+                if (dup) continue;
+                if (n == GATHER_CAP) { overflow = true; done = true; }
+                else
+                {
+                    int j = n++; // insertion by array index keeps the list sorted
+                    while (j > 0 && candIdx[j - 1] > idx)
+                    {
+                        candIdx[j] = candIdx[j - 1]; candD[j] = candD[j - 1]; candLeafT[j] = candLeafT[j - 1]; candLeaf[j] = candLeaf[j - 1];
+                        --j;
+                    }
+                    candIdx[j] = idx; candD[j] = distance; candLeafT[j] = leafT; candLeaf[j] = leaf;
+                }
+            }
+        }
+    }
+    DBG_ADD(2, 1); DBG_ADD(3, overflow ? 1 : 0); DBG_ADD(4, n);
+    if (overflow)
+    {
+        out.hit.prim = -2; out.shadow = -1.f; // caller runs the ordered walk
+        return out;
+    }
+    if (mode != UW_GATHER) return out;
+    // replay in array order.  Primitives of one leaf are contiguous and share the leaf's fate, decided when the leaf is
+    // reached (before any of its primitives): t_min(leaf) < closest-so-far.
+    float m = minDistance0;
+    bool leafPass = false;
+    int prevLeaf = -1;
+    int winner = -1;
+    for (int j = 0; j < n; ++j)
+    {
+        if (candLeaf[j] != prevLeaf)
+        {
+            leafPass = candLeafT[j] < m;
+            prevLeaf = candLeaf[j];
+        }
+        if (leafPass && candD[j] < m) { m = candD[j]; winner = candIdx[j]; }
+    }
+    if (winner >= 0)
+    {
+        const int meta = __ldg(metas + winner);
+        float3 I;
+        int flags;
+        float planeShadow;
+        primitiveTest(winner, meta, r, I, flags, planeShadow); // deterministic: same hit point as when it was gathered
+        out.hit.prim = winner; out.hit.p = I; out.hit.flags = flags;
+    }
+    return out;
+}
+
+SB_DEV Hit closestHitOrderIndependent(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)
+{
+    const float3 d = target - origin;
+    const int mode = (dot(d, d) >= 1.0002f) ? UW_CLOSEST : UW_GATHER;
+    const WalkOut o = unorderedWalk(mode, origin, d, iteration, currentMaterialId, 0, 0);
+    if (o.hit.prim == -2) return closestHitWide(origin, target, iteration, currentMaterialId);
+    return o.hit;
 }

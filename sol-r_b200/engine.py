@@ -53,6 +53,10 @@ def load():
     lib.b200_debug_relayout_boxes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.b200_debug_relayout_boxes.restype = C.c_int
     lib.b200_frame_parameter_bytes.restype = C.c_int
+    lib.b200_debug_build_unordered.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.b200_debug_build_unordered.restype = C.c_int
+    lib.b200_debug_counters.argtypes = [C.c_void_p]
+    lib.b200_debug_counters.restype = None
     lib.b200_last_render_ms.restype = C.c_float
     lib.b200_kernel_launches.restype = C.c_ulonglong
     lib.b200_scene_stats.argtypes = [C.POINTER(C.c_int)] * 4
@@ -70,7 +74,7 @@ ABI_SYMBOLS = [
     "b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
     "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
     "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition",
-    "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
+    "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
     "b200_synchronize",
 ]
 
@@ -90,6 +94,15 @@ def relayout_boxes(boxes_u8, nb_boxes, layout=BOX_LAYOUT_AUTO):
     out = np.zeros((max(2 * nb_boxes, 1), 8), np.float32)
     n = lib.b200_debug_relayout_boxes(_ptr(b), nb_boxes, _ptr(out), out.shape[0])
     lib.b200_set_option(1, BOX_LAYOUT_AUTO)
+    return out[:n].copy()
+
+
+def build_unordered(boxes_u8, nb_boxes):
+    """Host-only: the unordered SAH BVH (binary depth-first list, float32 [n, 8]) over the reference's leaves."""
+    lib = load()
+    b = np.ascontiguousarray(boxes_u8)
+    out = np.zeros((max(2 * nb_boxes, 1), 8), np.float32)
+    n = lib.b200_debug_build_unordered(_ptr(b), nb_boxes, _ptr(out), out.shape[0])
     return out[:n].copy()
 
 

@@ -22,7 +22,7 @@ class HostScene(C.Structure):
 ABI_SYMBOLS = ["b200h_create", "b200h_destroy", "b200h_set_scene_info", "b200h_set_post_processing_info", "b200h_set_camera",
                "b200h_add_primitive", "b200h_set_primitive", "b200h_add_primitives", "b200h_set_normals_bulk",
                "b200h_set_texcoords", "b200h_add_material", "b200h_add_materials", "b200h_set_material_raw",
-               "b200h_set_texture", "b200h_compact_boxes", "b200h_get_scene", "b200h_set_randoms", "b200h_set_limits",
+               "b200h_set_texture", "b200h_compact_boxes", "b200h_get_scene", "b200h_set_randoms", "b200h_set_limits", "b200h_set_capacity",
                "b200h_set_partition", "b200h_set_device", "b200h_init_buffers", "b200h_render_begin", "b200h_render_end",
                "b200h_get_bitmap", "b200h_get_primitive_ids", "b200h_get_primitive_at"]
 
@@ -55,6 +55,7 @@ def load():
     lib.b200h_get_scene.argtypes = [vp, C.POINTER(HostScene)]
     lib.b200h_set_randoms.argtypes = [vp, vp, C.c_long, C.c_int]
     lib.b200h_set_limits.argtypes = [vp, C.c_int, C.c_int]
+    lib.b200h_set_capacity.argtypes = [vp, C.c_long, C.c_long]
     lib.b200h_set_partition.argtypes = [vp, C.c_int, C.c_int]
     lib.b200h_set_device.argtypes = [vp, C.c_int]
     lib.b200h_init_buffers.argtypes = [vp]
@@ -77,13 +78,16 @@ def _ptr(a):
 class SceneHost:
     """Same call sequence a Sol-R application makes on solr::GPUKernel (SURVEY.md §3.1-3.3)."""
 
-    def __init__(self, scene_info, limits=None, rank=0, world=1, device=None):
+    def __init__(self, scene_info, limits=None, rank=0, world=1, device=None, capacity=None):
+        """capacity = (max boxes, max primitives) of the flattened arrays; None = the reference's 2.5 M each."""
         self.lib = load()
         self.scene_info = scene_info
         self.h = self.lib.b200h_create(C.byref(scene_info))
         self.limits = limits or (1920, 1080)
         self.lib.b200h_set_limits(self.h, self.limits[0], self.limits[1])
         self.lib.b200h_set_partition(self.h, rank, world)
+        if capacity is not None:
+            self.lib.b200h_set_capacity(self.h, capacity[0], capacity[1])
         if device is not None:
             self.lib.b200h_set_device(self.h, device)
 

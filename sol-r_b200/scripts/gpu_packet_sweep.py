@@ -11,9 +11,9 @@ for cfg, (W, H), nit in (("c1", (1024, 768), 2), ("c2", (1920, 1080), 3)):
     si = wire.default_scene_info(W, H, nb_ray_iterations=nit)
     h = host.SceneHost(si); sc.replay(h); a = h.arrays(); h.close()
     base = None
-    for mask, wide in ((0, 0), (1, 0), (0, 1), (1, 1), (5, 1)):
+    for mask, wide, unord, back in ((0, 1, 0, 1), (0, 1, 1, 1), (0, 1, 1, 0)):
         e = engine.Engine(si)
-        e.set_option(2, mask); e.set_option(3, wide)
+        e.set_option(2, mask); e.set_option(3, wide); e.set_option(4, unord); e.set_option(5, back)
         e.upload(a, randoms=np.zeros(1920 * 1080, np.float32))
         ms = []
         for it in range(4):
@@ -23,6 +23,7 @@ for cfg, (W, H), nit in (("c1", (1024, 768), 2), ("c2", (1920, 1080), 3)):
         if base is None:
             base = (bm.copy(), ids.copy())
         same = np.array_equal(bm, base[0]) and np.array_equal(ids, base[1])
-        print(cfg, "mask %2d wide %d  ms %.3f  rays/frame %d  identical_to_first %s" % (mask, wide, min(ms[1:]), cnt[0] // 4, same))
-        e.set_option(2, 1); e.set_option(3, 1)
+        dif = (bm != base[0]).any(-1).sum(); difid = (ids[..., 0] != base[1][..., 0]).sum()
+        print(cfg, "mask %2d wide %d unordered %d back %d  ms %.3f  rays/frame %d  identical_to_first %s (rgb px differ %d, id px differ %d)" % (mask, wide, unord, back, min(ms[1:]), cnt[0] // 4, same, dif, difid))
+        e.set_option(2, 0); e.set_option(3, 1); e.set_option(4, 1); e.set_option(5, 1)
         e.close()

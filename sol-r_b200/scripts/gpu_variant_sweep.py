@@ -14,6 +14,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         h = host.SceneHost(si); sc.replay(h); a = h.arrays(); h.close()
         for mask in masks:
             e = engine.Engine(si); e.set_option(2, mask)
+            if os.environ.get('SOLR_OPT5') is not None: e.set_option(5, int(os.environ['SOLR_OPT5']))
             e.upload(a, randoms=np.zeros(1920 * 1080, np.float32))
             ms = []
             for it in range(5):
