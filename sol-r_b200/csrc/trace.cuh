@@ -1206,7 +1206,10 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
                     best = distance;
                     window = fminf(minDistance0, GATHER_WINDOW * best);
                     cullT = fminf(minDistance0, window * invLen);
-                    int m2 = 0; // drop what fell out of the window
+                }
+                if (n == GATHER_CAP)
+                {
+                    int m2 = 0; // full: drop what fell out of the window meanwhile
                     for (int j = 0; j < n; ++j)
                         if (candD[j] <= window)
                         {
@@ -1215,19 +1218,12 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
                         }
                     n = m2;
                 }
-                bool dup = false; // the point-query tree lists a long cylinder once per piece
-                if (behind) for (int j = 0; j < n; ++j) dup |= candIdx[j] == idx;
-                if (dup) continue;
                 if (n == GATHER_CAP) { overflow = true; done = true; }
                 else
                 {
-                    int j = n++; // insertion by array index keeps the list sorted
-                    while (j > 0 && candIdx[j - 1] > idx)
-                    {
-                        candIdx[j] = candIdx[j - 1]; candD[j] = candD[j - 1]; candLeafT[j] = candLeafT[j - 1]; candLeaf[j] = candLeaf[j - 1];
-                        --j;
-                    }
-                    candIdx[j] = idx; candD[j] = distance; candLeafT[j] = leafT; candLeaf[j] = leaf;
+                    // appended in visiting order; the replay below picks them in array order
+                    candIdx[n] = idx; candD[n] = distance; candLeafT[n] = leafT; candLeaf[n] = leaf;
+                    ++n;
                 }
             }
         }
@@ -1239,20 +1235,30 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
         return out;
     }
     if (mode != UW_GATHER) return out;
-    // replay in array order.  Primitives of one leaf are contiguous and share the leaf's fate, decided when the leaf is
-    // reached (before any of its primitives): t_min(leaf) < closest-so-far.
+    // replay in array order (selection by ascending index: the list is short and every lane of the warp is here at the
+    // same time; a cylinder listed twice by the point query is taken once).  Primitives of one leaf are contiguous and
+    // share the leaf's fate, decided when the leaf is reached (before any of its primitives): t_min(leaf) < closest-so-far.
     float m = minDistance0;
     bool leafPass = false;
     int prevLeaf = -1;
     int winner = -1;
-    for (int j = 0; j < n; ++j)
+    int last = -1;
+    for (int pass = 0; pass < n; ++pass)
     {
-        if (candLeaf[j] != prevLeaf)
+        int bj = -1, bi = 0x7fffffff;
+        for (int j = 0; j < n; ++j)
         {
-            leafPass = candLeafT[j] < m;
-            prevLeaf = candLeaf[j];
+            const int ci = candIdx[j];
+            if (ci > last && ci < bi && candD[j] <= window) { bi = ci; bj = j; }
         }
-        if (leafPass && candD[j] < m) { m = candD[j]; winner = candIdx[j]; }
+        if (bj < 0) break;
+        last = bi;
+        if (candLeaf[bj] != prevLeaf)
+        {
+            leafPass = candLeafT[bj] < m;
+            prevLeaf = candLeaf[bj];
+        }
+        if (leafPass && candD[bj] < m) { m = candD[bj]; winner = bi; }
     }
     if (winner >= 0)
     {
