@@ -5,7 +5,7 @@ import numpy as np
 from _solr_b200_import import solr_b200  # noqa
 from solr_b200 import wire, scenes, engine, host
 engine.LIB_PATH = os.path.join(ROOT, "sol-r_b200", "csrc", "libvar_dbg.so")
-for cfg, (W, H), gl, nit in (("c2", (1920, 1080), 0, 1), ("c2", (1920, 1080), 4, 3), ("c4", (1920, 1080), 0, 1), ("c4", (1920, 1080), 4, 3)):
+for cfg, (W, H), gl, nit in (("c2", (1920, 1080), 0, 1), ("c2", (1920, 1080), 4, 1), ("c2", (1920, 1080), 3, 3), ("c2", (1920, 1080), 4, 3)):
     sc = scenes.config2() if cfg == "c2" else scenes.random_spheres(1_000_000, 20000.0, 20.0, 60.0, scenes.SEED + 4, "c4")
     si = wire.default_scene_info(W, H, graphics_level=gl, nb_ray_iterations=nit)
     h = host.SceneHost(si, capacity=(16_000_000, 4_000_000)); sc.replay(h); a = h.arrays(); h.close()
