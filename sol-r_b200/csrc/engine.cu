@@ -49,6 +49,99 @@ SB_DEV void packPixel(float4 color, unsigned char* bitmap, const int index)
     }
 }
 
+// Primary ray of a pixel for the standard / orthographic / antialiased cameras (CudaRayTracer.cu:462-522): eye and look-at
+// target, the target shifted per pixel, both rotated; depth-of-field and rotated-grid jitter of the accumulation passes.
+SB_DEV void primaryRay(const Rotation& rot, const int x, const int y, const int index, const float storedDepth, float3& o, float3& t)
+{
+    const int W = cSI.size.x, H = cSI.size.y;
+    const int iter = cSI.pathTracingIteration;
+    const int camera = cSI.cameraType;
+    const float3 rotationCenter = (camera == B200_CT_VR) ? cP.eye : f3(0.f, 0.f, 0.f);
+    const float ratio = (float)W / (float)H;
+    const float stepx = ratio * cP.angles.w / (float)W, stepy = cP.angles.w / (float)H;
+    o = cP.eye; t = cP.target;
+    // NATURAL_DEPTHOFFIELD (Consts.h:54; CudaRayTracer.cu:470-479), precedence as written there
+    if (cP.pp.type != B200_PPE_DEPTH_OF_FIELD && iter >= B200_NB_MAX_ITERATIONS)
+    {
+        const float a = (cP.pp.param1 / 20000.f);
+        const int rindex = index + cSI.timestamp % (cS.randomTableSize - 2);
+        const bool in = rindex + 1 < cS.randomTableSize + 4;
+        o.x += (in ? rnd(rindex) : 0.f) * storedDepth * a;
+        o.y += (in ? rnd(rindex + 1) : 0.f) * storedDepth * a;
+    }
+    if (camera == B200_CT_ORTHOGRAPHIC)
+    {
+        t.x = o.z * 0.001f * (x - (W / 2));
+        t.y = -o.z * 0.001f * (y - (H / 2));
+        o.x = t.x;
+        o.y = t.y;
+    }
+    else
+    {
+        t.x = t.x - stepx * (x - (W / 2));
+        t.y = t.y + stepy * (y - (H / 2));
+    }
+    vectorRotation(o, rotationCenter, rot);
+    vectorRotation(t, rotationCenter, rot);
+    if (camera != B200_CT_ANTIALIASED && iter >= B200_NB_MAX_ITERATIONS)
+    {
+        // rotated-grid jitter of the accumulation passes (:515-522), applied after the rotation
+        const int k = iter % 4;
+        t.x += (k == 0) ? 3.f : (k == 1) ? 5.f : (k == 2) ? -3.f : -5.f;
+        t.y += (k == 0) ? 5.f : (k == 1) ? -3.f : (k == 2) ? -5.f : 3.f;
+    }
+}
+
+// What a pixel keeps of its ray tree(s) (:537-562, anaglyph :903-925), followed by k_default for that pixel.
+SB_DEV void resolvePixel(const int index, float4 color, const float4 left, const int4 id, const float dof, float4 stored)
+{
+    const int iter = cSI.pathTracingIteration;
+    const int camera = cSI.cameraType;
+    float4 sinfo = *reinterpret_cast<float4*>(&cP.post[index].sceneInfo);
+    if (iter == 0) stored.w = dof;
+    if (camera == B200_CT_ANAGLYPH)
+    {
+        // left eye -> luma in red, right eye -> green/blue (:903-925); sceneInfo is not written
+        const float r1 = left.x * 0.299f + left.y * 0.587f + left.z * 0.114f;
+        const float g2 = color.y, b2 = color.z;
+        if (iter <= B200_NB_MAX_ITERATIONS) { stored.x = r1 + 0.f; stored.y = 0.f + g2; stored.z = 0.f + b2; }
+        else { stored.x += r1 + 0.f; stored.y += 0.f + g2; stored.z += 0.f + b2; }
+    }
+    else
+    {
+        if (cSI.advancedIllumination == B200_AI_RANDOM)
+        {
+            const int rindex = (index + cSI.timestamp) % cS.randomTableSize;
+            color += f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w) * rnd(rindex) * 5.f;
+        }
+        if (camera == B200_CT_ANTIALIASED) color /= 5.f;
+        if (iter <= B200_NB_MAX_ITERATIONS)
+        {
+            stored.x = color.x; stored.y = color.y; stored.z = color.z;
+            sinfo.x = color.x; sinfo.y = color.y; sinfo.z = color.z;
+        }
+        else
+        {
+            // accumulation passes (:550-562)
+            sinfo.x = (id.z > 0) ? fmaxf(sinfo.x, color.x) : color.x;
+            sinfo.y = (id.z > 0) ? fmaxf(sinfo.y, color.y) : color.y;
+            sinfo.z = (id.z > 0) ? fmaxf(sinfo.z, color.z) : color.z;
+            stored.x += sinfo.x; stored.y += sinfo.y; stored.z += sinfo.z;
+        }
+        *reinterpret_cast<float4*>(&cP.post[index].sceneInfo) = sinfo;
+    }
+    *reinterpret_cast<float4*>(&cP.post[index].colorInfo) = stored;
+    cP.ids[index] = id;
+    packPixel(stored, cP.bitmap, index);
+}
+
+// pixels whose ray tree ended before this deepening pass need no work (:454-458)
+SB_DEV bool pixelNeedsWork(const int4 id)
+{
+    const int iter = cSI.pathTracingIteration;
+    return !(iter > id.y && id.w == 0 && iter > 0 && iter <= B200_NB_MAX_ITERATIONS);
+}
+
 // One pixel: CudaRayTracer.cu:437-563 (standard / orthographic / antialiased cameras) and :840-926
 // (anaglyph), followed by k_default for that pixel.  The cameras differ only in how many ray trees a
 // pixel owns and how they are combined, so they share one loop around a single launchRayTracing site:
@@ -58,55 +151,21 @@ SB_DEV void renderPixel(const Rotation& rot, const bool inFrame, const int xIn, 
     const int W = cSI.size.x, H = cSI.size.y;
     const int x = inFrame ? xIn : 0, y = inFrame ? yIn : 0;
     const int index = y * W + x;
-    const int iter = cSI.pathTracingIteration;
     int4 id = cP.ids[index];
-    // pixels whose ray tree ended before this deepening pass need no work (:454-458); the lane still walks
-    // along with its warp (valid == false) because the walks are warp-synchronous
-    const bool valid = inFrame && !(iter > id.y && id.w == 0 && iter > 0 && iter <= B200_NB_MAX_ITERATIONS);
+    // a lane without work still walks along with its warp (valid == false) because the walks are warp-synchronous
+    const bool valid = inFrame && pixelNeedsWork(id);
     if (!__any_sync(FULL_MASK, valid)) return;
     if (valid) pixelsTraced++;
     const int camera = cSI.cameraType;
     const float3 rotationCenter = (camera == B200_CT_VR) ? cP.eye : f3(0.f, 0.f, 0.f);
     float dof = 0.f;
-    float4 stored = *reinterpret_cast<float4*>(&cP.post[index].colorInfo);
+    const float4 stored = *reinterpret_cast<float4*>(&cP.post[index].colorInfo);
     const float ratio = (float)W / (float)H;
     const float stepx = ratio * cP.angles.w / (float)W, stepy = cP.angles.w / (float)H;
     const bool anaglyph = camera == B200_CT_ANAGLYPH, antialiased = camera == B200_CT_ANTIALIASED;
 
     float3 o = cP.eye, t = cP.target;
-    if (!anaglyph)
-    {
-        // NATURAL_DEPTHOFFIELD (Consts.h:54; CudaRayTracer.cu:470-479), precedence as written there
-        if (cP.pp.type != B200_PPE_DEPTH_OF_FIELD && iter >= B200_NB_MAX_ITERATIONS)
-        {
-            const float a = (cP.pp.param1 / 20000.f);
-            const int rindex = index + cSI.timestamp % (cS.randomTableSize - 2);
-            const bool in = rindex + 1 < cS.randomTableSize + 4;
-            o.x += (in ? rnd(rindex) : 0.f) * stored.w * a;
-            o.y += (in ? rnd(rindex + 1) : 0.f) * stored.w * a;
-        }
-        if (camera == B200_CT_ORTHOGRAPHIC)
-        {
-            t.x = o.z * 0.001f * (x - (W / 2));
-            t.y = -o.z * 0.001f * (y - (H / 2));
-            o.x = t.x;
-            o.y = t.y;
-        }
-        else
-        {
-            t.x = t.x - stepx * (x - (W / 2));
-            t.y = t.y + stepy * (y - (H / 2));
-        }
-        vectorRotation(o, rotationCenter, rot);
-        vectorRotation(t, rotationCenter, rot);
-        if (!antialiased && iter >= B200_NB_MAX_ITERATIONS)
-        {
-            // rotated-grid jitter of the accumulation passes (:515-522), applied after the rotation
-            const int k = iter % 4;
-            t.x += (k == 0) ? 3.f : (k == 1) ? 5.f : (k == 2) ? -3.f : -5.f;
-            t.y += (k == 0) ? 5.f : (k == 1) ? -3.f : (k == 2) ? -5.f : 3.f;
-        }
-    }
+    if (!anaglyph) primaryRay(rot, x, y, index, stored.w, o, t);
 
     const int nSamples = anaglyph ? 2 : (antialiased ? 5 : 1);
     float4 color = f4(0.f, 0.f, 0.f, 0.f);
@@ -136,42 +195,7 @@ SB_DEV void renderPixel(const Rotation& rot, const bool inFrame, const int xIn, 
     }
 
     if (!valid) return;
-    float4 sinfo = *reinterpret_cast<float4*>(&cP.post[index].sceneInfo);
-    if (iter == 0) stored.w = dof;
-    if (anaglyph)
-    {
-        // left eye -> luma in red, right eye -> green/blue (:903-925); sceneInfo is not written
-        const float r1 = left.x * 0.299f + left.y * 0.587f + left.z * 0.114f;
-        const float g2 = color.y, b2 = color.z;
-        if (iter <= B200_NB_MAX_ITERATIONS) { stored.x = r1 + 0.f; stored.y = 0.f + g2; stored.z = 0.f + b2; }
-        else { stored.x += r1 + 0.f; stored.y += 0.f + g2; stored.z += 0.f + b2; }
-    }
-    else
-    {
-        if (cSI.advancedIllumination == B200_AI_RANDOM)
-        {
-            const int rindex = (index + cSI.timestamp) % cS.randomTableSize;
-            color += f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w) * rnd(rindex) * 5.f;
-        }
-        if (antialiased) color /= 5.f;
-        if (iter <= B200_NB_MAX_ITERATIONS)
-        {
-            stored.x = color.x; stored.y = color.y; stored.z = color.z;
-            sinfo.x = color.x; sinfo.y = color.y; sinfo.z = color.z;
-        }
-        else
-        {
-            // accumulation passes (:550-562)
-            sinfo.x = (id.z > 0) ? fmaxf(sinfo.x, color.x) : color.x;
-            sinfo.y = (id.z > 0) ? fmaxf(sinfo.y, color.y) : color.y;
-            sinfo.z = (id.z > 0) ? fmaxf(sinfo.z, color.z) : color.z;
-            stored.x += sinfo.x; stored.y += sinfo.y; stored.z += sinfo.z;
-        }
-        *reinterpret_cast<float4*>(&cP.post[index].sceneInfo) = sinfo;
-    }
-    *reinterpret_cast<float4*>(&cP.post[index].colorInfo) = stored;
-    cP.ids[index] = id;
-    packPixel(stored, cP.bitmap, index);
+    resolvePixel(index, color, left, id, dof, stored);
 }
 
 // Persistent CTAs: every warp pulls 8x4-pixel tiles from one atomic queue until the frame is drained, so
@@ -216,6 +240,215 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_render()
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Staged kernels.  In the kernel above a lane owns its pixel to the end of the ray tree, so after the first pass
+// only the lanes whose hit reflects or refracts (a third of them on the molecule scene, fewer each bounce) still carry
+// a ray while the registers of the others sit idle — and the walks are latency-bound, so useful resident lanes are
+// what sets the ray rate.  Here each pass is its own launch over a compacted queue of the paths that are still alive:
+//   k_stage_primary    pass 0 of every pixel of the owned tiles (tile queue, as above)
+//   k_stage_pass(p)    pass p of the paths queued by pass p - 1
+//   k_stage_reflected  the extra reflected ray of transparent + reflective first hits (CudaRayTracer.cu:296-315)
+// A path that ends is folded and written (resolvePixel) by the stage that ends it.  Between stages a path is ~40 words
+// in pathWords[word][slot] plus its colors[pass] / colorContributions[pass], slot = tile-major pixel number, so a
+// warp's loads and stores are contiguous in stage 0 and sector-contiguous afterwards (queues keep tile order within
+// a warp's push).  Same device functions as the megakernel (pathPass / pathReflectedRay / pathFinish), same results.
+// Used for the one-ray-tree-per-pixel cameras without box-debug / global-illumination rays; the rest take k_render.
+// ----------------------------------------------------------------------------------------------------
+#define PATH_WORDS 38
+SB_DEV void storePath(const size_t slot, const PathState& s, const int index)
+{
+    float* w = cP.pathWords + slot;
+    const size_t n = cP.pathStride;
+    int k = 0;
+#define PUT(v) w[(size_t)(k++) * n] = (v)
+#define PUTI(v) w[(size_t)(k++) * n] = __int_as_float(v)
+    PUT(s.curO.x); PUT(s.curO.y); PUT(s.curO.z); PUT(s.curT.x); PUT(s.curT.y); PUT(s.curT.z);
+    PUT(s.initialRefraction); PUTI(s.currentMaterialId);
+    PUT(s.closestColor.x); PUT(s.closestColor.y); PUT(s.closestColor.z); PUT(s.closestColor.w);
+    PUT(s.shadowIntensity);
+    PUT(s.rBlinn.x); PUT(s.rBlinn.y); PUT(s.rBlinn.z); PUT(s.rBlinn.w);
+    PUT(s.recursiveBlinn.x); PUT(s.recursiveBlinn.y); PUT(s.recursiveBlinn.z);
+    PUT(s.latestIntersection.x); PUT(s.latestIntersection.y); PUT(s.latestIntersection.z);
+    PUT(s.rayLength); PUT(s.depthOfField);
+    PUTI(s.reflectedRays);
+    PUT(s.reflO.x); PUT(s.reflO.y); PUT(s.reflO.z); PUT(s.reflT.x); PUT(s.reflT.y); PUT(s.reflT.z);
+    PUT(s.reflectedRatio);
+    PUTI(s.idx); PUTI(s.idz); PUTI(s.idw); PUTI(s.iteration); PUTI(index);
+#undef PUT
+#undef PUTI
+}
+
+SB_DEV void loadPath(const size_t slot, PathState& s, int& index)
+{
+    const float* w = cP.pathWords + slot;
+    const size_t n = cP.pathStride;
+    int k = 0;
+#define GET() w[(size_t)(k++) * n]
+#define GETI() __float_as_int(w[(size_t)(k++) * n])
+    s.curO.x = GET(); s.curO.y = GET(); s.curO.z = GET(); s.curT.x = GET(); s.curT.y = GET(); s.curT.z = GET();
+    s.initialRefraction = GET(); s.currentMaterialId = GETI();
+    s.closestColor.x = GET(); s.closestColor.y = GET(); s.closestColor.z = GET(); s.closestColor.w = GET();
+    s.shadowIntensity = GET();
+    s.rBlinn.x = GET(); s.rBlinn.y = GET(); s.rBlinn.z = GET(); s.rBlinn.w = GET();
+    s.recursiveBlinn.x = GET(); s.recursiveBlinn.y = GET(); s.recursiveBlinn.z = GET(); s.recursiveBlinn.w = 0.f;
+    s.latestIntersection.x = GET(); s.latestIntersection.y = GET(); s.latestIntersection.z = GET();
+    s.rayLength = GET(); s.depthOfField = GET();
+    s.reflectedRays = GETI();
+    s.reflO.x = GET(); s.reflO.y = GET(); s.reflO.z = GET(); s.reflT.x = GET(); s.reflT.y = GET(); s.reflT.z = GET();
+    s.reflectedRatio = GET();
+    s.idx = GETI(); s.idz = GETI(); s.idw = GETI(); s.iteration = GETI(); index = GETI();
+#undef GET
+#undef GETI
+    s.carryon = true;
+    s.giO = f3(0.f, 0.f, 0.f); s.giT = f3(0.f, 0.f, 0.f); s.pathTracingRatio = 0.f; s.useGlobalIllumination = false;
+    s.colorBox = f4(0.f, 0.f, 0.f, 0.f);
+}
+
+// warp-aggregated push of the lanes with `want` onto queue q
+SB_DEV void pushPaths(const int q, const bool want, const size_t slot)
+{
+    const unsigned int m = __ballot_sync(FULL_MASK, want);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(cP.queueCounters + 2 * q, (unsigned int)__popc(m));
+    base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
+    if (want) cP.pathQueues[(size_t)q * cP.pathStride + base + __popc(m & ((1u << lane) - 1u))] = (int)slot;
+}
+
+// after pass `pass` of a path (all 32 lanes call; `has` = this lane carries one): queue it for the next stage, or end it
+SB_DEV void routePath(const bool has, const PathState& s, const GlobalColors& C, const int pass, const size_t slot, const int index)
+{
+    const bool cont = has && s.carryon && s.rayLength < cSI.viewDistance && pass + 1 < cP.maxIteration;
+    const bool refl = has && !cont && cSI.graphicsLevel >= B200_GL_REFLECTIONS && s.reflectedRays != -1;
+    if (cont || refl) storePath(slot, s, index);
+    pushPaths(pass + 1, cont, slot);
+    pushPaths(cP.maxIteration, refl, slot);
+    if (has && !cont && !refl)
+    {
+        const float4 color = pathFinish(s, C, true);
+        const int4 id = make_int4(s.idx, s.iteration, s.idz, s.idw);
+        resolvePixel(index, color, f4(0.f, 0.f, 0.f, 0.f), id, s.depthOfField, *reinterpret_cast<float4*>(&cP.post[index].colorInfo));
+    }
+}
+
+SB_DEV void flushCounters(const unsigned int raysIn, const unsigned int pxIn)
+{
+    unsigned int rays = raysIn, px = pxIn;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        rays += __shfl_xor_sync(0xffffffffu, rays, o);
+        px += __shfl_xor_sync(0xffffffffu, px, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (rays) atomicAdd(cP.workCounters, (unsigned long long)rays);
+        if (px) atomicAdd(cP.workCounters + 1, (unsigned long long)px);
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_primary()
+{
+    const int lane = threadIdx.x & 31;
+    Counters cnt;
+    cnt.rays = 0;
+    unsigned int pixelsTraced = 0;
+    Rotation rot;
+    rot.cx = cosf(cP.angles.x); rot.cy = cosf(cP.angles.y); rot.cz = cosf(cP.angles.z);
+    rot.sx = sinf(cP.angles.x); rot.sy = sinf(cP.angles.y); rot.sz = sinf(cP.angles.z);
+    while (true)
+    {
+        unsigned int k = 0;
+        if (lane == 0) k = atomicAdd(cP.tileCounter, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= (unsigned int)cP.nbLocalTiles) break;
+        const int tile = k * cP.worldSize + cP.rank;
+        const int tx = tile % cP.tilesX, ty = tile / cP.tilesX;
+        const int xIn = tx * TILE_W + (lane & (TILE_W - 1));
+        const int yIn = ty * TILE_H + (lane / TILE_W);
+        const bool inFrame = xIn < cSI.size.x && yIn < cSI.size.y;
+        const int x = inFrame ? xIn : 0, y = inFrame ? yIn : 0;
+        const int index = y * cSI.size.x + x;
+        const int4 id = cP.ids[index];
+        const bool valid = inFrame && pixelNeedsWork(id);
+        if (!__any_sync(FULL_MASK, valid)) continue;
+        if (valid) pixelsTraced++;
+        float3 o, t;
+        primaryRay(rot, x, y, index, cP.post[index].colorInfo.w, o, t);
+        const size_t slot = (size_t)k * 32 + lane;
+        PathState s;
+        pathInit(s, o, t);
+        GlobalColors C;
+        C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
+        pathPass(s, C, 0, valid, index, o, cP.packetMask, cnt);
+        routePath(valid, s, C, 0, slot, index);
+        __syncwarp();
+    }
+    flushCounters(cnt.rays, pixelsTraced);
+}
+
+// pass >= 1: 32 queue entries per warp at a time
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_pass(const int pass)
+{
+    const int lane = threadIdx.x & 31;
+    Counters cnt;
+    cnt.rays = 0;
+    const unsigned int count = cP.queueCounters[2 * pass];
+    while (true)
+    {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(cP.queueCounters + 2 * pass + 1, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const bool has = base + lane < count;
+        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)pass * cP.pathStride + base + lane] : 0;
+        PathState s;
+        int index = 0;
+        loadPath(slot, s, index);
+        if (!has) index = 0;
+        GlobalColors C;
+        C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
+        pathPass(s, C, pass, has, index, f3(0.f, 0.f, 0.f), 0, cnt);
+        routePath(has, s, C, pass, slot, index);
+        __syncwarp();
+    }
+    flushCounters(cnt.rays, 0);
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflected()
+{
+    const int lane = threadIdx.x & 31;
+    Counters cnt;
+    cnt.rays = 0;
+    const int q = cP.maxIteration;
+    const unsigned int count = cP.queueCounters[2 * q];
+    while (true)
+    {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(cP.queueCounters + 2 * q + 1, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const bool has = base + lane < count;
+        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)q * cP.pathStride + base + lane] : 0;
+        PathState s;
+        int index = 0;
+        loadPath(slot, s, index);
+        if (!has) index = 0;
+        GlobalColors C;
+        C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
+        pathReflectedRay(s, C, has, index, 0, cnt);
+        if (has)
+        {
+            const float4 color = pathFinish(s, C, true);
+            const int4 id = make_int4(s.idx, s.iteration, s.idz, s.idw);
+            resolvePixel(index, color, f4(0.f, 0.f, 0.f, 0.f), id, s.depthOfField, *reinterpret_cast<float4*>(&cP.post[index].colorInfo));
+        }
+        __syncwarp();
+    }
+    flushCounters(cnt.rays, 0);
+}
+
+// ----------------------------------------------------------------------------------------------------
 // host state
 // ----------------------------------------------------------------------------------------------------
 namespace
@@ -235,6 +468,10 @@ struct Engine
     float4* dUWide = nullptr; int nbUWide = 0; size_t capUWide = 0; int opaqueShadows = 0;
     int nbUX = 0; // point-query tree for backward cylinder hits, appended to dUWide
     int* dPrimLeaf = nullptr; size_t capPrimLeaf = 0;
+    // staged rendering
+    float* dPathWords = nullptr; float4* dPathColors = nullptr; float* dPathContrib = nullptr; int* dPathQueues = nullptr;
+    unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
+    int ctasPerSMStage[3] = {0, 0, 0};
     float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
     b200_BoundingBox* dRawBoxes = nullptr;
     b200_Material* dMats = nullptr; int nbMats = 0;
@@ -722,6 +959,7 @@ struct SahBuilder
 
 int g_useWide = 1;
 int g_useUnordered = 1;
+int g_useStaged = 1;   // one launch per pass over compacted path queues where the camera allows it (0: always the single kernel)
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
@@ -771,6 +1009,7 @@ void b200_set_option(int key, int value)
     else if (key == 3) g_useWide = value != 0;
     else if (key == 4) g_useUnordered = value != 0;
     else if (key == 5) g_useBackward = value != 0;
+    else if (key == 6) g_useStaged = value != 0;
     else latch(-11, "b200_set_option", "unknown option");
 }
 void b200_set_partition(int rank, int world)
@@ -805,6 +1044,9 @@ void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
     int perSM = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render, CTA_THREADS, 0));
     G.ctasPerSM = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_primary, CTA_THREADS, 0)); G.ctasPerSMStage[0] = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_pass, CTA_THREADS, 0)); G.ctasPerSMStage[1] = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_reflected, CTA_THREADS, 0)); G.ctasPerSMStage[2] = perSM > 0 ? perSM : 1;
     G.initialised = true;
     G.launches = 0;
 }
@@ -820,6 +1062,8 @@ void b200_finalize_scene(b200_int2)
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
     freeDev(G.dTileCounter); freeDev(G.dWork);
+    freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters);
+    G.pathStride = 0; G.pathIterations = 0;
     if (G.evStart) { cudaEventDestroy(G.evStart); G.evStart = nullptr; }
     if (G.evStop) { cudaEventDestroy(G.evStop); G.evStop = nullptr; }
     if (G.stream == G.ownStream) G.stream = nullptr;
@@ -1143,6 +1387,31 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.packetMask = (G.boxLayoutUsed == 2) ? g_packetMask : 0; // packets need the ordered BVH (only leaf tests observable)
     P.nbLocalTiles = (nbTiles - G.rank + G.world - 1) / G.world;
 
+    // staged rendering where a pixel owns one ray tree and more than one pass can happen
+    int maxIteration = (si.graphicsLevel < B200_GL_REFLECTIONS) ? 1 : si.nbRayIterations + si.pathTracingIteration;
+    maxIteration = maxIteration > B200_NB_MAX_ITERATIONS ? B200_NB_MAX_ITERATIONS : maxIteration;
+    const bool giRays = (si.advancedIllumination == B200_AI_BASIC || si.advancedIllumination == B200_AI_FULL);
+    const bool staged = g_useStaged && maxIteration > 1 && !giRays && si.renderBoxes == 0 &&
+                        (si.cameraType == B200_CT_PERSPECTIVE || si.cameraType == B200_CT_ORTHOGRAPHIC);
+    if (staged)
+    {
+        const size_t stride = (((size_t)P.nbLocalTiles * 32) + 63) & ~(size_t)63;
+        if (stride > G.pathStride || maxIteration > G.pathIterations)
+        {
+            CK(cudaStreamSynchronize(G.stream));
+            freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues);
+            G.pathStride = stride > G.pathStride ? stride : G.pathStride;
+            G.pathIterations = maxIteration > G.pathIterations ? maxIteration : G.pathIterations;
+            CK(cudaMalloc(&G.dPathWords, PATH_WORDS * G.pathStride * sizeof(float)));
+            CK(cudaMalloc(&G.dPathColors, (size_t)G.pathIterations * G.pathStride * sizeof(float4)));
+            CK(cudaMalloc(&G.dPathContrib, (size_t)G.pathIterations * G.pathStride * sizeof(float)));
+            CK(cudaMalloc(&G.dPathQueues, (size_t)(G.pathIterations + 1) * G.pathStride * sizeof(int)));
+        }
+        if (!G.dQueueCounters) CK(cudaMalloc(&G.dQueueCounters, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int)));
+        P.pathWords = G.dPathWords; P.pathColors = G.dPathColors; P.pathContributions = G.dPathContrib; P.pathQueues = G.dPathQueues;
+        P.queueCounters = G.dQueueCounters; P.pathStride = G.pathStride; P.maxIteration = maxIteration;
+    }
+
     CK(cudaEventRecord(G.evStart, G.stream));
     CK(cudaMemsetAsync(G.dTileCounter, 0, sizeof(unsigned int), G.stream));
     const int warpsPerCta = CTA_THREADS / 32;
@@ -1150,10 +1419,24 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     const int needed = (P.nbLocalTiles + warpsPerCta - 1) / warpsPerCta;
     if (grid > needed) grid = needed > 0 ? needed : 1;
     CK(cudaMemcpyToSymbolAsync(cP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, G.stream));
-    k_render<<<grid, CTA_THREADS, 0, G.stream>>>();
+    if (!staged)
+    {
+        k_render<<<grid, CTA_THREADS, 0, G.stream>>>();
+        G.launches++;
+    }
+    else
+    {
+        CK(cudaMemsetAsync(G.dQueueCounters, 0, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int), G.stream));
+        int g0 = G.numSMs * G.ctasPerSMStage[0];
+        if (g0 > needed) g0 = needed > 0 ? needed : 1;
+        k_stage_primary<<<g0, CTA_THREADS, 0, G.stream>>>();
+        // queue lengths are only known on the device: persistent grids sized for the device, each warp takes 32 entries at a time
+        for (int pass = 1; pass < maxIteration; ++pass) k_stage_pass<<<G.numSMs * G.ctasPerSMStage[1], CTA_THREADS, 0, G.stream>>>(pass);
+        k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
+        G.launches += maxIteration + 1;
+    }
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) latch((int)e, "k_render launch", cudaGetErrorString(e));
-    G.launches++;
+    if (e != cudaSuccess) latch((int)e, "render kernel launch", cudaGetErrorString(e));
     CK(cudaEventRecord(G.evStop, G.stream));
     G.timed = true;
 }

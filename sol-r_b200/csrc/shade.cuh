@@ -496,224 +496,338 @@ SB_DEV Hit traceClosest(const float3 o, const float3 t, const int iteration, con
     return hit;
 }
 
-// CudaRayTracer.cu:69-408 — the bounce loop, in warp-uniform form: the 32 lanes of a warp (one 8x4-pixel
-// tile) step through the bounce iterations together; `valid` says whether this lane owns a pixel, and a lane
-// whose ray tree has ended simply stops taking part (act == false) while the warp finishes.  That keeps the
-// warp converged at every walk, so the walks can run as packets.  colors[]/colorContributions[] (the
-// reference's 11-entry local arrays folded back to front at :382-385) stay local arrays.
+// ---------------------------------------------------------------------------------------------------
+// CudaRayTracer.cu:69-408 — the bounce loop.  Its state is a struct and its body one function per stage
+// so that two drivers can run it:
+//   * launchRayTracing (below): one thread owns a pixel from the first ray to the last, the 32 lanes of a warp (one
+//     8x4-pixel tile) step through the passes together (warp-uniform, so the walks can run as packets);
+//   * the staged kernels of engine.cu: one launch per pass over a compacted queue of the paths that are still
+//     alive, the state parked in global memory in between, so that every lane of every warp carries a ray.
+// colors[] / colorContributions[] are the reference's 11-entry local arrays (:92-95), folded back to front at
+// :382-385; the store is a template parameter (thread-local arrays, or one global array per pass).
+// ---------------------------------------------------------------------------------------------------
+struct PathState
+{
+    float3 curO, curT;
+    float initialRefraction;
+    int currentMaterialId;
+    float4 closestColor;
+    float shadowIntensity;
+    float4 rBlinn, recursiveBlinn;
+    float3 latestIntersection;
+    float rayLength;
+    float depthOfField;
+    int reflectedRays; // pass of the first transparent + reflective hit, or -1
+    float3 reflO, reflT;
+    float reflectedRatio;
+    bool carryon;
+    int iteration;
+    int idx, idz, idw; // PrimitiveXYIdBuffer x, z, w
+    // global-illumination ray of the first hit (:163-175)
+    float3 giO, giT;
+    float pathTracingRatio;
+    bool useGlobalIllumination;
+    float4 colorBox;
+};
+
+struct LocalColors
+{
+    float4 c[B200_NB_MAX_ITERATIONS + 1];
+    float k[B200_NB_MAX_ITERATIONS + 1];
+    SB_DEV float4 color(const int i) const { return c[i]; }
+    SB_DEV float contribution(const int i) const { return k[i]; }
+    SB_DEV void setColor(const int i, const float4 v) { c[i] = v; }
+    SB_DEV void setContribution(const int i, const float v) { k[i] = v; }
+};
+
+// one float4 / float array per pass, indexed by path slot
+struct GlobalColors
+{
+    float4* c;
+    float* k;
+    size_t slot, stride;
+    SB_DEV float4 color(const int i) const { return c[(size_t)i * stride + slot]; }
+    SB_DEV float contribution(const int i) const { return k[(size_t)i * stride + slot]; }
+    SB_DEV void setColor(const int i, const float4 v) { c[(size_t)i * stride + slot] = v; }
+    SB_DEV void setContribution(const int i, const float v) { k[(size_t)i * stride + slot] = v; }
+};
+
+SB_DEV int pathMaxIteration()
+{
+    int m = (cSI.graphicsLevel < B200_GL_REFLECTIONS) ? 1 : cSI.nbRayIterations + cSI.pathTracingIteration;
+    return (m > B200_NB_MAX_ITERATIONS) ? B200_NB_MAX_ITERATIONS : m;
+}
+
+SB_DEV void pathInit(PathState& s, const float3 rayO, const float3 rayT)
+{
+    s.curO = rayO; s.curT = rayT;
+    s.initialRefraction = 1.f;
+    s.currentMaterialId = -2;
+    s.closestColor = f4(0.f, 0.f, 0.f, 0.f);
+    s.shadowIntensity = 0.f;
+    s.rBlinn = f4(0.f, 0.f, 0.f, 0.f);
+    s.recursiveBlinn = f4(0.f, 0.f, 0.f, 0.f);
+    s.latestIntersection = rayO;
+    s.rayLength = 0.f;
+    s.depthOfField = cSI.viewDistance;
+    s.reflectedRays = -1;
+    s.reflO = f3(0.f, 0.f, 0.f); s.reflT = f3(0.f, 0.f, 0.f);
+    s.reflectedRatio = 0.f;
+    s.carryon = true;
+    s.iteration = 0;
+    s.idx = -1; s.idz = 0; s.idw = 0;
+    s.giO = f3(0.f, 0.f, 0.f); s.giT = f3(0.f, 0.f, 0.f);
+    s.pathTracingRatio = 0.f;
+    s.useGlobalIllumination = false;
+    s.colorBox = f4(0.f, 0.f, 0.f, 0.f);
+}
+
+// One pass of the loop at :125-294 for a lane whose own loop condition holds (act); lanes with act == false only keep the
+// warp-synchronous walks company.  rayO is the primary origin (first-hit depth).
+template <class Colors>
+SB_DEV void pathPass(PathState& s, Colors& C, const int pass, const bool act, const int index, const float3 rayO, const int packetMask,
+                     Counters& cnt)
+{
+    const bool debugBoxes = cSI.renderBoxes != 0;
+    float3 areas = f3(0.f, 0.f, 0.f);
+    float3 normal = f3(0.f, 0.f, 0.f);
+    float3 rayNd = f3(0.f, 0.f, 0.f); // normalize(target - origin) of the walk that produced `hit`
+    Hit hit;
+    hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
+    bool found = false;
+    if (debugBoxes)
+    {
+        if (act) { cnt.rays++; boxDebugWalk(s.curO, s.curT, s.iteration, s.colorBox); }
+    }
+    else
+    {
+        hit = traceClosest(s.curO, s.curT, pass, s.currentMaterialId, act, (packetMask & (pass == 0 ? 1 : 2)) != 0, rayNd, cnt);
+        found = act && hit.prim >= 0;
+    }
+    if (act) s.carryon = found;
+    float4 attributes = f4(0.f, 0.f, 0.f, 0.f);
+    float matInnerX = 0.f, matColorW = 0.f;
+    if (found)
+    {
+        const int meta = __ldg(cS.meta + hit.prim);
+        hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
+        const int matId = PM_MATERIAL(meta);
+        const b200_Material& mat = cS.mats[matId];
+        s.currentMaterialId = matId;
+        const float4 rrto = *reinterpret_cast<const float4*>(&mat.reflection); // reflection, refraction, transparency, opacity
+        attributes = f4(rrto.x, rrto.z, rrto.y, rrto.w);
+        matInnerX = mat.innerIllumination.x;
+        matColorW = mat.color.w;
+        if (pass == 0)
+        {
+            C.setColor(0, f4(0.f, 0.f, 0.f, 0.f));
+            C.setContribution(0, 1.f);
+            s.latestIntersection = hit.p;
+            s.depthOfField = length(hit.p - rayO);
+            if (matInnerX == 0.f && (cSI.advancedIllumination == B200_AI_BASIC || cSI.advancedIllumination == B200_AI_FULL))
+            {
+                const int t = (index + cSI.pathTracingIteration * 100 + cSI.timestamp) % (cS.randomTableSize - 3);
+                s.giO = hit.p + normal * cSI.rayEpsilon;
+                s.giT.x = normal.x + 100.f * rnd(t);
+                s.giT.y = normal.y + 100.f * rnd(t + 1);
+                s.giT.z = normal.z + 100.f * rnd(t + 2);
+                const float cos_theta = dot(normalize(s.giT), normal);
+                if (cos_theta < 0.f) s.giT = -s.giT;
+                s.giT += hit.p;
+                s.pathTracingRatio = (1.f - attributes.y) * fabsf(cos_theta);
+                s.useGlobalIllumination = true;
+            }
+            s.idx = __ldg(&cS.prims[hit.prim].index);
+        }
+        s.rBlinn.w = attributes.y;
+    }
+    const float4 shaded = primitiveShader(found, index, s.curO, normal, hit.prim, hit.p, areas, s.closestColor, pass, s.shadowIntensity,
+                                          s.rBlinn, attributes, (packetMask & (pass == 0 ? 4 : 8)) != 0, cnt);
+    if (found)
+    {
+        const float3 closestIntersection = hit.p;
+        float4 colorOfPass = shaded;
+        float contribution;
+        float3 reflectedTarget = f3(0.f, 0.f, 0.f);
+        s.idz += matInnerX * 256;
+        const float segmentLength = length(closestIntersection - s.latestIntersection);
+        s.latestIntersection = closestIntersection;
+        const float transparency = attributes.y;
+        float a = 0.f;
+        if (attributes.y != 0.f)
+        {
+            float refraction = attributes.z;
+            if (s.initialRefraction == refraction)
+            {
+                refraction = 1.f;
+                const float len = segmentLength * (attributes.w * (1.f - transparency));
+                s.rayLength += len;
+                s.rayLength = (s.rayLength > cSI.viewDistance) ? cSI.viewDistance : s.rayLength;
+                a = (s.rayLength / cSI.viewDistance);
+                colorOfPass.x -= a; colorOfPass.y -= a; colorOfPass.z -= a;
+            }
+            const float3 O_E = normalize(closestIntersection - s.curO);
+            vectorRefraction(reflectedTarget, O_E, refraction, normal, s.initialRefraction);
+            contribution = transparency - a;
+            s.initialRefraction = refraction;
+            if (s.reflectedRays == -1 && attributes.x != 0.f)
+            {
+                float3 rd;
+                vectorReflection(rd, O_E, normal);
+                s.reflO = closestIntersection + rd * cSI.rayEpsilon;
+                s.reflT = closestIntersection + rd;
+                s.reflectedRatio = attributes.x;
+                s.reflectedRays = pass;
+            }
+        }
+        else if (attributes.x != 0.f)
+        {
+            const float3 O_E = normalize(closestIntersection - s.curO);
+            vectorReflection(reflectedTarget, O_E, normal);
+            contribution = attributes.x;
+        }
+        else
+        {
+            s.carryon = false;
+            contribution = 1.f;
+        }
+        C.setColor(pass, colorOfPass);
+        C.setContribution(pass, contribution);
+        s.rBlinn /= (float)(pass + 1);
+        s.recursiveBlinn.x = (s.rBlinn.x > s.recursiveBlinn.x) ? s.rBlinn.x : s.recursiveBlinn.x;
+        s.recursiveBlinn.y = (s.rBlinn.y > s.recursiveBlinn.y) ? s.rBlinn.y : s.recursiveBlinn.y;
+        s.recursiveBlinn.z = (s.rBlinn.z > s.recursiveBlinn.z) ? s.rBlinn.z : s.recursiveBlinn.z;
+        s.curO = closestIntersection + reflectedTarget * cSI.rayEpsilon;
+        s.curT = closestIntersection + reflectedTarget;
+        if (cSI.pathTracingIteration != 0 && matColorW != 0.f)
+        {
+            float ratio = matColorW;
+            ratio *= (attributes.y == 0.f) ? 1000.f : 1.f;
+            const int rindex = (index + cSI.timestamp) % (cS.randomTableSize - 3);
+            s.curT.x += rnd(rindex) * ratio;
+            s.curT.y += rnd(rindex + 1) * ratio;
+            s.curT.z += rnd(rindex + 2) * ratio;
+        }
+    }
+    else if (act)
+    {
+        float4 c;
+        if (cSI.skyboxMaterialId != B200_MATERIAL_NONE)
+        {
+            c = skyboxMapping(s.curO, s.curT);
+            const float rad = c.x + c.y + c.z;
+            s.idz += (rad > 2.5f) ? rad * 256.f : 0.f;
+        }
+        else if (cSI.gradientBackground)
+        {
+            const float3 up = f3(0.f, 1.f, 0.f);
+            const float3 dir = normalize(s.curT - s.curO);
+            float angle = 0.5f - dot(up, dir);
+            angle = (angle > 1.f) ? 1.f : angle;
+            c = (1.f - angle) * f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w);
+        }
+        else
+            c = f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w);
+        C.setColor(pass, c);
+        C.setContribution(pass, 1.f);
+    }
+    if (act) s.iteration = pass + 1;
+}
+
+// extra reflected ray of the first transparent + reflective hit (:296-315)
+template <class Colors>
+SB_DEV void pathReflectedRay(PathState& s, Colors& C, const bool want, const int index, const int packetMask, Counters& cnt)
+{
+    const bool debugBoxes = cSI.renderBoxes != 0;
+    float3 areas = f3(0.f, 0.f, 0.f);
+    float3 normal = f3(0.f, 0.f, 0.f);
+    float3 rayNd = f3(0.f, 0.f, 0.f);
+    Hit hit;
+    hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
+    bool found = false;
+    if (debugBoxes)
+    {
+        if (want) { cnt.rays++; boxDebugWalk(s.reflO, s.reflT, s.reflectedRays, s.colorBox); }
+    }
+    else
+    {
+        hit = traceClosest(s.reflO, s.reflT, s.reflectedRays, s.currentMaterialId, want, (packetMask & 2) != 0, rayNd, cnt);
+        found = want && hit.prim >= 0;
+    }
+    float4 attributes = f4(0.f, 0.f, 0.f, 0.f);
+    if (found)
+    {
+        const int meta = __ldg(cS.meta + hit.prim);
+        hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
+        attributes.x = cS.mats[PM_MATERIAL(meta)].reflection;
+    }
+    const float4 color = primitiveShader(found, index, s.reflO, normal, hit.prim, hit.p, areas, s.closestColor, s.reflectedRays,
+                                         s.shadowIntensity, s.rBlinn, attributes, (packetMask & 8) != 0, cnt);
+    if (found)
+    {
+        C.setColor(s.reflectedRays, C.color(s.reflectedRays) + color * s.reflectedRatio);
+        s.idw = s.shadowIntensity * 255;
+    }
+}
+
+// back-to-front fold (:382-385), Blinn, fog (:391-400), box-debug tint
+template <class Colors>
+SB_DEV float4 pathFinish(const PathState& s, const Colors& C, const bool folded)
+{
+    float4 intersectionColor;
+    if (folded)
+    {
+        // colors[i] = colors[i] (1 - k[i]) + colors[i + 1] k[i] for i = iteration - 2 .. 0, carried in a register
+        float4 acc = (s.iteration > 0) ? C.color(s.iteration - 1) : f4(0.f, 0.f, 0.f, 0.f);
+        for (int i = s.iteration - 2; i >= 0; --i)
+        {
+            const float k = C.contribution(i);
+            acc = C.color(i) * (1.f - k) + acc * k;
+        }
+        intersectionColor = acc;
+        intersectionColor += s.recursiveBlinn;
+    }
+    else
+        intersectionColor = C.color(0);
+    const float D1 = cSI.viewDistance * 0.95f;
+    if (cSI.atmosphericEffect == B200_AE_FOG && s.depthOfField > D1)
+    {
+        const float D2 = cSI.viewDistance * 0.05f;
+        const float a = s.depthOfField - D1;
+        const float b = 1.f - (a / D2);
+        intersectionColor = intersectionColor * b + f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w) * (1.f - b);
+    }
+    intersectionColor -= s.colorBox;
+    return intersectionColor;
+}
+
+// The whole ray tree of one pixel in one thread, warp-uniform: `valid` says whether this lane owns a pixel, and a lane
+// whose ray tree has ended simply stops taking part (act == false) while the warp finishes.
 SB_DEV float4 launchRayTracing(const bool valid, const int index, const float3 rayO, const float3 rayT, float& depthOfField, int4& id,
                                Counters& cnt)
 {
-    float4 intersectionColor = f4(0.f, 0.f, 0.f, 0.f);
-    float3 normal = f3(0.f, 0.f, 0.f);
-    bool carryon = true;
-    float3 curO = rayO, curT = rayT;
-    float initialRefraction = 1.f;
-    int iteration = 0;
-    id.x = -1; id.z = 0; id.w = 0;
-    int currentMaterialId = -2;
-    float colorContributions[B200_NB_MAX_ITERATIONS + 1];
-    float4 colors[B200_NB_MAX_ITERATIONS + 1];
-    // The reference zero-fills both arrays (:94-95); every entry read below (fold over 0..iteration-1, the reflected-ray and GI
-    // updates of entries already produced) is written by the pass that produced it, so only entry 0 needs a defined value
-    // for lanes that own no pixel.
-    colors[0] = f4(0.f, 0.f, 0.f, 0.f); colorContributions[0] = 0.f;
-    float4 recursiveBlinn = f4(0.f, 0.f, 0.f, 0.f);
-    float shadowIntensity = 0.f;
-    float3 reflectedTarget = f3(0.f, 0.f, 0.f);
-    float4 closestColor = f4(0.f, 0.f, 0.f, 0.f), colorBox = f4(0.f, 0.f, 0.f, 0.f);
-    float3 latestIntersection = rayO;
-    float rayLength = 0.f;
-    depthOfField = cSI.viewDistance;
-    int reflectedRays = -1;
-    float3 reflO = f3(0.f, 0.f, 0.f), reflT = f3(0.f, 0.f, 0.f);
-    float reflectedRatio = 0.f;
-    float3 giO = f3(0.f, 0.f, 0.f), giT = f3(0.f, 0.f, 0.f);
-    float pathTracingRatio = 0.f;
-    float4 pathTracingColor = f4(0.f, 0.f, 0.f, 0.f);
-    bool useGlobalIllumination = false;
-    float4 rBlinn = f4(0.f, 0.f, 0.f, 0.f);
-    int currentMaxIteration = (cSI.graphicsLevel < B200_GL_REFLECTIONS) ? 1 : cSI.nbRayIterations + cSI.pathTracingIteration;
-    currentMaxIteration = (currentMaxIteration > B200_NB_MAX_ITERATIONS) ? B200_NB_MAX_ITERATIONS : currentMaxIteration;
+    PathState s;
+    pathInit(s, rayO, rayT);
+    LocalColors C;
+    // The reference zero-fills both arrays (:94-95); every entry read later (the fold over 0..iteration-1, the reflected-ray and
+    // GI updates of entries already produced) is written by the pass that produced it, so only entry 0 needs a defined
+    // value for lanes that own no pixel.
+    C.c[0] = f4(0.f, 0.f, 0.f, 0.f); C.k[0] = 0.f;
+    const int currentMaxIteration = pathMaxIteration();
     const bool debugBoxes = cSI.renderBoxes != 0;
     const int packetMask = cP.packetMask;
-    Hit hit;
-    hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
-    float3 rayNd = f3(0.f, 0.f, 0.f); // normalize(target - origin) of the walk that produced `hit`
-    const float4 bg = f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w);
 
     for (int pass = 0; pass < currentMaxIteration; ++pass)
     {
         // a lane takes part in pass p iff its own loop condition (:125) holds; then iteration == p
-        const bool act = valid && carryon && rayLength < cSI.viewDistance;
+        const bool act = valid && s.carryon && s.rayLength < cSI.viewDistance;
         if (!__any_sync(FULL_MASK, act)) break;
-        float3 areas = f3(0.f, 0.f, 0.f);
-        bool found = false;
-        if (debugBoxes)
-        {
-            if (act) { cnt.rays++; boxDebugWalk(curO, curT, iteration, colorBox); }
-        }
-        else
-        {
-            hit = traceClosest(curO, curT, pass, currentMaterialId, act, (packetMask & (pass == 0 ? 1 : 2)) != 0, rayNd, cnt);
-            found = act && hit.prim >= 0;
-        }
-        if (act) carryon = found;
-        float4 attributes = f4(0.f, 0.f, 0.f, 0.f);
-        float matInnerX = 0.f, matColorW = 0.f;
-        int matId = 0;
-        if (found)
-        {
-            const int meta = __ldg(cS.meta + hit.prim);
-            hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
-            matId = PM_MATERIAL(meta);
-            const b200_Material& mat = cS.mats[matId];
-            currentMaterialId = matId;
-            const float4 rrto = *reinterpret_cast<const float4*>(&mat.reflection); // reflection, refraction, transparency, opacity
-            attributes = f4(rrto.x, rrto.z, rrto.y, rrto.w);
-            matInnerX = mat.innerIllumination.x;
-            matColorW = mat.color.w;
-            if (pass == 0)
-            {
-                colors[0] = f4(0.f, 0.f, 0.f, 0.f);
-                colorContributions[0] = 1.f;
-                latestIntersection = hit.p;
-                depthOfField = length(hit.p - rayO);
-                if (matInnerX == 0.f && (cSI.advancedIllumination == B200_AI_BASIC || cSI.advancedIllumination == B200_AI_FULL))
-                {
-                    const int t = (index + cSI.pathTracingIteration * 100 + cSI.timestamp) % (cS.randomTableSize - 3);
-                    giO = hit.p + normal * cSI.rayEpsilon;
-                    giT.x = normal.x + 100.f * rnd(t);
-                    giT.y = normal.y + 100.f * rnd(t + 1);
-                    giT.z = normal.z + 100.f * rnd(t + 2);
-                    const float cos_theta = dot(normalize(giT), normal);
-                    if (cos_theta < 0.f) giT = -giT;
-                    giT += hit.p;
-                    pathTracingRatio = (1.f - attributes.y) * fabsf(cos_theta);
-                    useGlobalIllumination = true;
-                }
-                id.x = __ldg(&cS.prims[hit.prim].index);
-            }
-            rBlinn.w = attributes.y;
-        }
-        const float4 shaded = primitiveShader(found, index, curO, normal, hit.prim, hit.p, areas, closestColor, pass, shadowIntensity,
-                                              rBlinn, attributes, (packetMask & (pass == 0 ? 4 : 8)) != 0, cnt);
-        if (found)
-        {
-            const float3 closestIntersection = hit.p;
-            colors[pass] = shaded;
-            id.z += matInnerX * 256;
-            const float segmentLength = length(closestIntersection - latestIntersection);
-            latestIntersection = closestIntersection;
-            const float transparency = attributes.y;
-            float a = 0.f;
-            if (attributes.y != 0.f)
-            {
-                float refraction = attributes.z;
-                if (initialRefraction == refraction)
-                {
-                    refraction = 1.f;
-                    const float len = segmentLength * (attributes.w * (1.f - transparency));
-                    rayLength += len;
-                    rayLength = (rayLength > cSI.viewDistance) ? cSI.viewDistance : rayLength;
-                    a = (rayLength / cSI.viewDistance);
-                    colors[pass].x -= a; colors[pass].y -= a; colors[pass].z -= a;
-                }
-                const float3 O_E = normalize(closestIntersection - curO);
-                vectorRefraction(reflectedTarget, O_E, refraction, normal, initialRefraction);
-                colorContributions[pass] = transparency - a;
-                initialRefraction = refraction;
-                if (reflectedRays == -1 && attributes.x != 0.f)
-                {
-                    float3 rd;
-                    vectorReflection(rd, O_E, normal);
-                    reflO = closestIntersection + rd * cSI.rayEpsilon;
-                    reflT = closestIntersection + rd;
-                    reflectedRatio = attributes.x;
-                    reflectedRays = pass;
-                }
-            }
-            else if (attributes.x != 0.f)
-            {
-                const float3 O_E = normalize(closestIntersection - curO);
-                vectorReflection(reflectedTarget, O_E, normal);
-                colorContributions[pass] = attributes.x;
-            }
-            else
-            {
-                carryon = false;
-                colorContributions[pass] = 1.f;
-            }
-            rBlinn /= (float)(pass + 1);
-            recursiveBlinn.x = (rBlinn.x > recursiveBlinn.x) ? rBlinn.x : recursiveBlinn.x;
-            recursiveBlinn.y = (rBlinn.y > recursiveBlinn.y) ? rBlinn.y : recursiveBlinn.y;
-            recursiveBlinn.z = (rBlinn.z > recursiveBlinn.z) ? rBlinn.z : recursiveBlinn.z;
-            curO = closestIntersection + reflectedTarget * cSI.rayEpsilon;
-            curT = closestIntersection + reflectedTarget;
-            if (cSI.pathTracingIteration != 0 && matColorW != 0.f)
-            {
-                float ratio = matColorW;
-                ratio *= (attributes.y == 0.f) ? 1000.f : 1.f;
-                const int rindex = (index + cSI.timestamp) % (cS.randomTableSize - 3);
-                curT.x += rnd(rindex) * ratio;
-                curT.y += rnd(rindex + 1) * ratio;
-                curT.z += rnd(rindex + 2) * ratio;
-            }
-        }
-        else if (act)
-        {
-            if (cSI.skyboxMaterialId != B200_MATERIAL_NONE)
-            {
-                colors[pass] = skyboxMapping(curO, curT);
-                const float rad = colors[pass].x + colors[pass].y + colors[pass].z;
-                id.z += (rad > 2.5f) ? rad * 256.f : 0.f;
-            }
-            else if (cSI.gradientBackground)
-            {
-                const float3 up = f3(0.f, 1.f, 0.f);
-                const float3 dir = normalize(curT - curO);
-                float angle = 0.5f - dot(up, dir);
-                angle = (angle > 1.f) ? 1.f : angle;
-                colors[pass] = (1.f - angle) * bg;
-            }
-            else
-                colors[pass] = bg;
-            colorContributions[pass] = 1.f;
-        }
-        if (act) iteration = pass + 1;
+        pathPass(s, C, pass, act, index, rayO, packetMask, cnt);
     }
 
-    // extra reflected ray of the first transparent + reflective hit (:296-315)
     {
-        const bool want = valid && cSI.graphicsLevel >= B200_GL_REFLECTIONS && reflectedRays != -1;
-        if (__any_sync(FULL_MASK, want))
-        {
-            float3 areas = f3(0.f, 0.f, 0.f);
-            bool found = false;
-            if (debugBoxes)
-            {
-                if (want) { cnt.rays++; boxDebugWalk(reflO, reflT, reflectedRays, colorBox); }
-            }
-            else
-            {
-                hit = traceClosest(reflO, reflT, reflectedRays, currentMaterialId, want, (packetMask & 2) != 0, rayNd, cnt);
-                found = want && hit.prim >= 0;
-            }
-            float4 attributes = f4(0.f, 0.f, 0.f, 0.f);
-            if (found)
-            {
-                const int meta = __ldg(cS.meta + hit.prim);
-                hitNormal(hit.prim, meta, hit.p, hit.flags, rayNd, normal, areas);
-                attributes.x = cS.mats[PM_MATERIAL(meta)].reflection;
-            }
-            const float4 color = primitiveShader(found, index, reflO, normal, hit.prim, hit.p, areas, closestColor, reflectedRays,
-                                                 shadowIntensity, rBlinn, attributes, (packetMask & 8) != 0, cnt);
-            if (found)
-            {
-                colors[reflectedRays] += color * reflectedRatio;
-                id.w = shadowIntensity * 255;
-            }
-        }
+        const bool want = valid && cSI.graphicsLevel >= B200_GL_REFLECTIONS && s.reflectedRays != -1;
+        if (__any_sync(FULL_MASK, want)) pathReflectedRay(s, C, want, index, packetMask, cnt);
     }
 
     bool test = true;
@@ -722,18 +836,23 @@ SB_DEV float4 launchRayTracing(const bool valid, const int index, const float3 r
     {
         // global-illumination ray (:317-378)
         const bool giFull = cSI.advancedIllumination == B200_AI_FULL;
-        const bool want = valid && useGlobalIllumination && giFull;
+        const bool want = valid && s.useGlobalIllumination && giFull;
         float3 areas = f3(0.f, 0.f, 0.f);
+        float3 normal = f3(0.f, 0.f, 0.f);
+        float3 rayNd = f3(0.f, 0.f, 0.f);
+        Hit hit;
+        hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
         bool giHit = false;
+        float4 pathTracingColor = f4(0.f, 0.f, 0.f, 0.f);
         if (giFull)
         {
             if (debugBoxes)
             {
-                if (want) { cnt.rays++; boxDebugWalk(giO, giT, 30, colorBox); }
+                if (want) { cnt.rays++; boxDebugWalk(s.giO, s.giT, 30, s.colorBox); }
             }
             else
             {
-                hit = traceClosest(giO, giT, 30, B200_MATERIAL_NONE, want, (packetMask & 2) != 0, rayNd, cnt);
+                hit = traceClosest(s.giO, s.giT, 30, B200_MATERIAL_NONE, want, (packetMask & 2) != 0, rayNd, cnt);
                 giHit = want && hit.prim >= 0;
             }
         }
@@ -749,55 +868,38 @@ SB_DEV float4 launchRayTracing(const bool valid, const int index, const float3 r
             {
                 if (material.innerIllumination.x == 0.f)
                 {
-                    colors[0] = mc * material.innerIllumination.x * pathTracingRatio;
+                    C.c[0] = mc * material.innerIllumination.x * s.pathTracingRatio;
                     test = false;
                 }
                 else
-                    colors[0] = mc * pathTracingRatio;
+                    C.c[0] = mc * s.pathTracingRatio;
             }
             if (test)
             {
-                pathTracingRatio *= 0.1f; // STANDARD_LUNINANCE_STRENGTH (Consts.h:52)
+                s.pathTracingRatio *= 0.1f; // STANDARD_LUNINANCE_STRENGTH (Consts.h:52)
                 if (material.innerIllumination.x == 0.f)
-                    colors[0] -= cSI.shadowIntensity;
+                    C.c[0] -= cSI.shadowIntensity;
                 else
                     shadeGi = true;
             }
         }
         if (giFull)
         {
-            const float4 c = primitiveShader(shadeGi, index, giO, normal, hit.prim, hit.p, areas, closestColor, iteration, shadowIntensity,
-                                             rBlinn, attributes, (packetMask & 8) != 0, cnt);
+            const float4 c = primitiveShader(shadeGi, index, s.giO, normal, hit.prim, hit.p, areas, s.closestColor, s.iteration, s.shadowIntensity,
+                                             s.rBlinn, attributes, (packetMask & 8) != 0, cnt);
             if (shadeGi) pathTracingColor = c;
         }
         if (valid && !giHit && cSI.skyboxMaterialId != B200_MATERIAL_NONE)
         {
             // no GI hit, or aiBasic (where the reference maps an uninitialised ray, :369-375; zero here)
-            pathTracingColor = skyboxMapping(giO, giT);
-            pathTracingRatio *= 0.2f; // SKYBOX_LUNINANCE_STRENGTH (Consts.h:53)
+            pathTracingColor = skyboxMapping(s.giO, s.giT);
+            s.pathTracingRatio *= 0.2f; // SKYBOX_LUNINANCE_STRENGTH (Consts.h:53)
         }
-        if (test) colors[0] += pathTracingColor * pathTracingRatio;
+        if (test) C.c[0] += pathTracingColor * s.pathTracingRatio;
     }
 
-    if (test)
-    {
-        for (int i = iteration - 2; i >= 0; --i)
-            colors[i] = colors[i] * (1.f - colorContributions[i]) + colors[i + 1] * colorContributions[i];
-        intersectionColor = colors[0];
-        intersectionColor += recursiveBlinn;
-    }
-    else
-        intersectionColor = colors[0];
-
-    const float D1 = cSI.viewDistance * 0.95f;
-    if (cSI.atmosphericEffect == B200_AE_FOG && depthOfField > D1)
-    {
-        const float D2 = cSI.viewDistance * 0.05f;
-        const float a = depthOfField - D1;
-        const float b = 1.f - (a / D2);
-        intersectionColor = intersectionColor * b + bg * (1.f - b);
-    }
-    id.y = iteration;
-    intersectionColor -= colorBox;
+    const float4 intersectionColor = pathFinish(s, C, test);
+    depthOfField = s.depthOfField;
+    id.x = s.idx; id.y = s.iteration; id.z = s.idz; id.w = s.idw;
     return intersectionColor;
 }

@@ -77,6 +77,14 @@ struct RenderParams
     int tilesX, tilesY, nbLocalTiles;
     int rank, worldSize;
     int packetMask; // which walks run warp-synchronously: bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow
+    // staged rendering (engine.cu "staged kernels"): path state parked between passes, one array per word / per pass
+    float* pathWords;          // [PATH_WORDS][pathStride]
+    float4* pathColors;        // [maxIteration][pathStride]
+    float* pathContributions;  // [maxIteration][pathStride]
+    int* pathQueues;           // [maxIteration + 1][pathStride] path slots; queue q feeds pass q, queue maxIteration the reflected-ray stage
+    unsigned int* queueCounters; // [2 * (B200_NB_MAX_ITERATIONS + 2)]: entries pushed, entries handed out
+    size_t pathStride;
+    int maxIteration;
 };
 
 // One frame's parameters live in constant memory (uploaded on the render stream before the launch):
