@@ -1041,7 +1041,7 @@ struct SahBuilder
 
 int g_useWide = 1;
 int g_useUnordered = 1;
-int g_useStaged = 2;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: also the closest-hit walks in their own kernel
+int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: also the closest-hit walks in their own kernel
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)

@@ -1048,19 +1048,33 @@ SB_DEV bool slabT(const float4 lo, const float4 hi, const Ray& r, const float t1
     return !missXY & !missZ & (tmin2 < t1) & (tmax2 > 0.f);
 }
 
-// tests the four children of an unordered node against [0, tLimit]; pushes the hits far-to-near (nearest on top)
-SB_DEV bool wideStepSorted(const float4* __restrict__ n, const WideRay& w, const Ray& r, const float tLimit, int* stackRef, float* stackT, int& sp)
+// tests the four children of an unordered node against [0, tLimit]; pushes the hits far-to-near (nearest on top).
+// These boxes only steer the walk (a hit is re-checked against its reference leaf box with the reference's arithmetic), and
+// they are padded (engine.cu step 2c), so the test is written for instruction count: slab distances as one FMA
+// b * inv - o * inv (o * inv once per ray; the rounding differs from (b - o) * inv by <= 1e-7 |o| in position, far inside
+// the padding), rows loaded at fixed offsets from one address and near / far picked by the direction's sign.
+struct NodeRay
 {
-    const float4 ax = __ldg(n + w.nx), bx = __ldg(n + w.fx);
-    const float4 ay = __ldg(n + w.ny), by = __ldg(n + w.fy);
-    const float4 az = __ldg(n + w.nz), bz = __ldg(n + w.fz);
+    float ix, iy, iz;    // inverse direction
+    float nox, noy, noz; // -origin * inverse direction
+};
+SB_DEV void nodeRay(NodeRay& q, const Ray& r)
+{
+    q.ix = r.inv.x; q.iy = r.inv.y; q.iz = r.inv.z;
+    q.nox = -r.o.x * r.inv.x; q.noy = -r.o.y * r.inv.y; q.noz = -r.o.z * r.inv.z;
+}
+SB_DEV bool wideStepSorted(const float4* __restrict__ n, const NodeRay& q, const float tLimit, int* stackRef, float* stackT, int& sp)
+{
+    const float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2);
+    const float4 hx = __ldg(n + 3), hy = __ldg(n + 4), hz = __ldg(n + 5);
     const int4 refs = __ldg(reinterpret_cast<const int4*>(n + 6));
+    const bool sx = q.ix < 0.f, sy = q.iy < 0.f, sz = q.iz < 0.f;
     float t0, t1, t2, t3;
 #define UN_CHILD(C, T)                                                                                               \
     {                                                                                                                \
-        const float tnx = (ax.C - r.o.x) * r.inv.x, tfx = (bx.C - r.o.x) * r.inv.x;                                  \
-        const float tny = (ay.C - r.o.y) * r.inv.y, tfy = (by.C - r.o.y) * r.inv.y;                                  \
-        const float tnz = (az.C - r.o.z) * r.inv.z, tfz = (bz.C - r.o.z) * r.inv.z;                                  \
+        const float tnx = __fmaf_rn(sx ? hx.C : lx.C, q.ix, q.nox), tfx = __fmaf_rn(sx ? lx.C : hx.C, q.ix, q.nox);  \
+        const float tny = __fmaf_rn(sy ? hy.C : ly.C, q.iy, q.noy), tfy = __fmaf_rn(sy ? ly.C : hy.C, q.iy, q.noy);  \
+        const float tnz = __fmaf_rn(sz ? hz.C : lz.C, q.iz, q.noz), tfz = __fmaf_rn(sz ? lz.C : hz.C, q.iz, q.noz);  \
         const float tmin = fmaxf(fmaxf(tnx, tny), tnz), tmax = fminf(fminf(tfx, tfy), tfz);                          \
         T = ((tmin <= tmax) & (tmin <= tLimit) & (tmax > 0.f)) ? tmin : 3.0e38f;                                     \
     }
@@ -1115,8 +1129,8 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
     if (mode == UW_SHADOW && !(0.f < shadowLimit)) return out;
     Ray r;
     makeRay(r, rayOrigin, rayDir);
-    WideRay w;
-    wideRows(w, r);
+    NodeRay q;
+    nodeRay(q, r);
     const float eps = cSI.geometryEpsilon;
     const float len2 = dot(r.d, r.d);
     const float invLen = rsqrtf(len2) * 1.0001f; // world distance -> t, with slack so culling stays conservative
@@ -1157,7 +1171,7 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
             if (stackT[sp] > cullT) continue; // the bound shrank since this entry was pushed
             if (ref < 0) { cur = ref; break; }
             DBG_ADD(5, 1);
-            if (!wideStepSorted(nodes + 8 * ref, w, r, (ref >= nbMain) ? 0.f : cullT, stackRef, stackT, sp)) { overflow = true; sp = 0; }
+            if (!wideStepSorted(nodes + 8 * ref, q, (ref >= nbMain) ? 0.f : cullT, stackRef, stackT, sp)) { overflow = true; sp = 0; }
         }
         if (overflow) break;
         if (cur == WIDE_NONE) break;

@@ -18,6 +18,12 @@
 #ifndef TRACE_REFILL_IDLE
 #define TRACE_REFILL_IDLE 1 // refill as soon as this many lanes are idle
 #endif
+#ifndef TRACE_LEAF_VOTE
+#define TRACE_LEAF_VOTE 12 // lanes holding a leaf that end the node rounds
+#endif
+#ifndef TRACE_RETIRE_VOTE
+#define TRACE_RETIRE_VOTE 8 // lanes out of work that end the node rounds (while the queue still has rays)
+#endif
 
 __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int pass)
 {
@@ -56,7 +62,7 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
     bool active = false;
     size_t slot = 0;
     Ray r;
-    WideRay w;
+    NodeRay q;
     int mode = UW_CLOSEST, currentMaterialId = 0;
     float invLen = 0.f, best = 0.f, window = 0.f, cullT = 0.f;
     int stackRef[UN_STACK];
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
     Hit out;
     out.prim = -1; out.p = f3(0.f, 0.f, 0.f); out.flags = 0;
     r.o = r.d = r.nd = r.inv = f3(0.f, 0.f, 0.f);
-    w.nx = w.ny = w.nz = w.fx = w.fy = w.fz = 0;
+    q.ix = q.iy = q.iz = q.nox = q.noy = q.noz = 0.f;
     bool exhausted = false; // warp-uniform: the queue has been handed out
 
     while (true)
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
                     currentMaterialId = __float_as_int(pw[7 * stride]);
                     const float3 d = t - o;
                     makeRay(r, o, d);
-                    wideRows(w, r);
+                    nodeRay(q, r);
                     const float len2 = dot(d, d);
                     mode = (len2 >= 1.0002f) ? UW_CLOSEST : UW_GATHER;
                     invLen = rsqrtf(len2) * 1.0001f;
@@ -112,23 +118,32 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
         }
         if (!__any_sync(FULL_MASK, active)) break;
 
-        // ---- node loop: until this lane holds a leaf or its stack is empty
+        // ---- node rounds: every lane without a leaf in hand pops one entry per round.  The rounds stop when enough lanes
+        //      hold a leaf (they wait meanwhile), enough lanes have run out of work (they wait for the refill), or nobody
+        //      is searching — so neither phase runs for the sake of a few stragglers.
         int cur = WIDE_NONE;
-        if (active)
+        while (true)
         {
-            while (sp > 0)
+            const bool searching = active && cur == WIDE_NONE && sp > 0 && !overflow;
+            const unsigned int ms = __ballot_sync(FULL_MASK, searching);
+            const unsigned int ml = __ballot_sync(FULL_MASK, active && cur != WIDE_NONE);
+            const unsigned int md = __ballot_sync(FULL_MASK, active && cur == WIDE_NONE && (sp == 0 || overflow));
+            if (ms == 0 || __popc(ml) >= TRACE_LEAF_VOTE || (__popc(md) >= TRACE_RETIRE_VOTE && !exhausted)) break;
+            if (searching)
             {
                 --sp;
                 const int ref = stackRef[sp];
-                if (stackT[sp] > cullT) continue; // the bound shrank since this entry was pushed
-                if (ref < 0) { cur = ref; break; }
-                if (!wideStepSorted(nodes + 8 * ref, w, r, (ref >= nbMain) ? 0.f : cullT, stackRef, stackT, sp)) { overflow = true; sp = 0; }
+                if (!(stackT[sp] > cullT)) // else: the bound shrank since this entry was pushed
+                {
+                    if (ref < 0) cur = ref;
+                    else if (!wideStepSorted(nodes + 8 * ref, q, (ref >= nbMain) ? 0.f : cullT, stackRef, stackT, sp)) { overflow = true; sp = 0; }
+                }
             }
         }
 
         __syncwarp(); // lanes leave the node loop at different times; the primitive test below should find them together
         // ---- leaf: one primitive
-        bool finished = active && (cur == WIDE_NONE || overflow);
+        bool finished = active && ((cur == WIDE_NONE && sp == 0) || overflow);
         if (active && cur != WIDE_NONE && !overflow)
         {
             const bool behind = ((~cur) & 0x40000000) != 0; // from the point-query tree
