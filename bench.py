@@ -42,6 +42,9 @@ import numpy as np  # noqa: E402
 W, H, NB_RAY_ITERATIONS = 1920, 1080, 3
 SAMPLE_W, SAMPLE_H = 480, 270
 WORKLOAD = "config2_molecule_216k_primitives_1920x1080_glFull_3_bounces"
+# algorithmic work of one frame of this workload (SURVEY.md 8(d) flop weights x the oracle's counts in the reference's traversal
+# order, full 1920x1080 frame; the N=1 run re-counts it live on the CPU sample)
+ALGORITHMIC_GFLOP_PER_FRAME = 37.2087
 SM_COUNT, LANES_PER_SM = 148, 128
 
 
@@ -268,22 +271,42 @@ def main():
     kernel_ms = float(lib.b200_last_render_ms())
 
     # ---- end to end through the host drop-in -------------------------------------------------------------
-    # The merged frame of a multi-GPU run lives on rank 0's device; e2e is reported for the single-GPU drop-in.
-    e2e = None
-    if world == 1:
-        for _ in range(3):
-            frame_e2e()
-        torch.cuda.synchronize()
-        eng.counters(reset=True)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            frame_e2e()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        rays_e2e, _ = eng.counters(reset=True)
-        e2e = {"value": rays_e2e / dt / 1e6, "unit": "Mrays/s", "ms_per_frame": dt / args.steps * 1e3,
-               "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()),   # scene-info + camera + pointers block, per frame
-               "d2h_bytes_per_step": W * H * 3 + W * H * 16}   # RGB8 + PrimitiveXYIdBuffer, as d2h_bitmap copies
+    # Every rank runs the host drop-in for its tiles (render_begin: per-frame parameter upload + launch); the partial RGB8
+    # frames are summed onto rank 0 over NVLink (the path's one exchange step) and rank 0 reads the merged frame and its
+    # ids back to host memory (render_end = d2h_bitmap).  Wall clock around K frames, max over ranks.
+    def frame_e2e_all():
+        si_live.pathTracingIteration = 0
+        h.set_scene_info(si_live)
+        h.render_begin(0.0)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.reduce(bitmap_t, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            h.render_end()
+        else:
+            stream.synchronize()
+
+    for _ in range(3):
+        frame_e2e_all()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    eng.counters(reset=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame_e2e_all()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    rays_e2e, _ = eng.counters(reset=True)
+    te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    re_ = torch.tensor([float(rays_e2e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(re_, op=dist.ReduceOp.SUM)
+    dt = float(te.item())
+    e2e = {"value": float(re_.item()) / dt / 1e6, "unit": "Mrays/s", "ms_per_frame": dt / args.steps * 1e3,
+           "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()) * world,   # scene-info + camera + pointers block, per frame and rank
+           "d2h_bytes_per_step": W * H * 3 + W * H * 16}   # RGB8 + PrimitiveXYIdBuffer, as d2h_bitmap copies (rank 0)
 
     if world > 1:
         dist.barrier()
@@ -295,24 +318,28 @@ def main():
                            "l2": "flushed between timed frames (256 MiB memset outside the timed region)",
                            "parallelism": "one frame, interleaved 8x4 tiles over %d GPU(s), NCCL sum-reduce of RGB8 to rank 0" % world},
                 "clocks": clocks, "gpu_launches": int(launches), "kernel_ms_last_frame": kernel_ms}
-        if e2e:
-            line["e2e"] = e2e
+        line["e2e"] = e2e
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_summary_latest.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        flops_frame = ALGORITHMIC_GFLOP_PER_FRAME * 1e9
+        flops_source = "oracle count in reference traversal order, full frame (recorded)"
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_run(1, 0)
             flops_frame = cb["flops_per_frame"] * (W * H) / float(SAMPLE_W * SAMPLE_H)   # per-pixel mean of the 1/16 sample
-            achieved = flops_frame / (ms_per_step * 1e-3) / 1e12
-            traffic = None
-            try:
-                with open(os.path.join(ROOT, "profiles", "ncu_summary_latest.json")) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
-            except Exception:
-                pass
-            line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
-                                "frac": achieved / pk["fp32_tflops"], "traffic": traffic,
-                                "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json)" % pk["source"],
-                                "algorithmic_gflop_per_frame": flops_frame / 1e9,
-                                "hbm": {"peak_gbs": pk["hbm_gbs"], "mandatory_bytes_per_frame": W * H * (32 + 16 + 3) * 2}}
+            flops_source = "oracle count in reference traversal order, live on the %dx%d sample, scaled by pixels" % (SAMPLE_W, SAMPLE_H)
             line["cpu_baseline"] = {"value": cb["mrays_s"], "unit": "Mrays/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+        # the frame is a handful of kernels of one code base (k_stage_primary, k_stage_pass per bounce, ...): the roofline is
+        # taken over the timed region they fill, per GPU
+        achieved = flops_frame / (ms_per_step * 1e-3) / 1e12 / world
+        line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
+                            "frac": achieved / pk["fp32_tflops"], "traffic": traffic,
+                            "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json), per GPU" % pk["source"],
+                            "algorithmic_gflop_per_frame": flops_frame / 1e9, "algorithmic_flops_source": flops_source,
+                            "hbm": {"peak_gbs": pk["hbm_gbs"], "mandatory_bytes_per_frame": W * H * (32 + 16 + 3) * 2}}
         print(json.dumps(line))
     h.close()
     if world > 1:
