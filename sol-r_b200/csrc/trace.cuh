@@ -1053,6 +1053,31 @@ SB_DEV bool slabT(const float4 lo, const float4 hi, const Ray& r, const float t1
 // they are padded (engine.cu step 2c), so the test is written for instruction count: slab distances as one FMA
 // b * inv - o * inv (o * inv once per ray; the rounding differs from (b - o) * inv by <= 1e-7 |o| in position, far inside
 // the padding), rows loaded at fixed offsets from one address and near / far picked by the direction's sign.
+// Traversal stack: the first SM_STACK entries of every lane live in shared memory ([entry][thread], 8 bytes each, so a warp's
+// push or pop is one conflict-free access), deeper entries in a thread-local array.  The pop is on the critical path of
+// the walk (its result is the next node's address) and thread-local arrays are L1-thrashing global memory here: 32 warps
+// x ~1.5 KB of stack + spills per SM do not stay in L1, ncu showed ~4 GB of local-memory traffic reaching DRAM per frame.
+#ifndef SM_STACK
+#define SM_STACK 12
+#endif
+#define WALK_THREADS 128
+struct WalkStack
+{
+    int2* sm;   // this thread's column of the shared stack
+    int* lref;  // overflow, thread-local
+    float* lt;
+    SB_DEV void push(const int sp, const int ref, const float t) const
+    {
+        if (sp < SM_STACK) sm[sp * WALK_THREADS] = make_int2(ref, __float_as_int(t));
+        else { lref[sp - SM_STACK] = ref; lt[sp - SM_STACK] = t; }
+    }
+    SB_DEV void pop(const int sp, int& ref, float& t) const
+    {
+        if (sp < SM_STACK) { const int2 v = sm[sp * WALK_THREADS]; ref = v.x; t = __int_as_float(v.y); }
+        else { ref = lref[sp - SM_STACK]; t = lt[sp - SM_STACK]; }
+    }
+};
+
 struct NodeRay
 {
     float ix, iy, iz;    // inverse direction
@@ -1063,7 +1088,7 @@ SB_DEV void nodeRay(NodeRay& q, const Ray& r)
     q.ix = r.inv.x; q.iy = r.inv.y; q.iz = r.inv.z;
     q.nox = -r.o.x * r.inv.x; q.noy = -r.o.y * r.inv.y; q.noz = -r.o.z * r.inv.z;
 }
-SB_DEV bool wideStepSorted(const float4* __restrict__ n, const NodeRay& q, const float tLimit, int* stackRef, float* stackT, int& sp)
+SB_DEV bool wideStepSorted(const float4* __restrict__ n, const NodeRay& q, const float tLimit, const WalkStack& st, int& sp)
 {
     const float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2);
     const float4 hx = __ldg(n + 3), hy = __ldg(n + 4), hz = __ldg(n + 5);
@@ -1088,10 +1113,10 @@ SB_DEV bool wideStepSorted(const float4* __restrict__ n, const NodeRay& q, const
     // each level leaves <= 3 entries behind, so UN_STACK - 4 is only exceeded by a degenerate (very deep) tree: the caller
     // then abandons this walk for the ordered one
     if (sp > UN_STACK - 4) return false;
-    if (t0 < 3.0e38f) { stackRef[sp] = r0; stackT[sp] = t0; ++sp; }
-    if (t1 < 3.0e38f) { stackRef[sp] = r1; stackT[sp] = t1; ++sp; }
-    if (t2 < 3.0e38f) { stackRef[sp] = r2; stackT[sp] = t2; ++sp; }
-    if (t3 < 3.0e38f) { stackRef[sp] = r3; stackT[sp] = t3; ++sp; }
+    if (t0 < 3.0e38f) { st.push(sp, r0, t0); ++sp; }
+    if (t1 < 3.0e38f) { st.push(sp, r1, t1); ++sp; }
+    if (t2 < 3.0e38f) { st.push(sp, r2, t2); ++sp; }
+    if (t3 < 3.0e38f) { st.push(sp, r3, t3); ++sp; }
     return true;
 }
 
@@ -1138,10 +1163,13 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
     const float4* __restrict__ leafRecs = cS.leafRecs;
     const int* __restrict__ metas = cS.meta;
     const bool extended = cSI.extendedGeometry != 0;
-    int stackRef[UN_STACK];
-    float stackT[UN_STACK];
+    __shared__ int2 s_stack[SM_STACK * WALK_THREADS];
+    int stackRef[UN_STACK - SM_STACK];
+    float stackT[UN_STACK - SM_STACK];
+    WalkStack st;
+    st.sm = s_stack + threadIdx.x; st.lref = stackRef; st.lt = stackT;
     int sp = 1;
-    stackRef[0] = 0; stackT[0] = 0.f;
+    st.push(0, 0, 0.f);
     int candIdx[GATHER_CAP], candLeaf[GATHER_CAP];
     float candD[GATHER_CAP], candLeafT[GATHER_CAP];
     int n = 0;
@@ -1159,7 +1187,7 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
     // count there; only hits ahead of it count in the first.
     const float4* __restrict__ nodes = cS.uwnodes;
     const int nbMain = cS.nbUWide;
-    if (cS.nbUX > 0) { stackRef[1] = nbMain; stackT[1] = -3.0e38f; sp = 2; }
+    if (cS.nbUX > 0) { st.push(1, nbMain, -3.0e38f); sp = 2; }
     bool done = false;
     while (!done)
     {
@@ -1167,11 +1195,13 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
         while (sp > 0)
         {
             --sp;
-            const int ref = stackRef[sp];
-            if (stackT[sp] > cullT) continue; // the bound shrank since this entry was pushed
+            int ref;
+            float tEntry;
+            st.pop(sp, ref, tEntry);
+            if (tEntry > cullT) continue; // the bound shrank since this entry was pushed
             if (ref < 0) { cur = ref; break; }
             DBG_ADD(5, 1);
-            if (!wideStepSorted(nodes + 8 * ref, q, (ref >= nbMain) ? 0.f : cullT, stackRef, stackT, sp)) { overflow = true; sp = 0; }
+            if (!wideStepSorted(nodes + 8 * ref, q, (ref >= nbMain) ? 0.f : cullT, st, sp)) { overflow = true; sp = 0; }
         }
         if (overflow) break;
         if (cur == WIDE_NONE) break;

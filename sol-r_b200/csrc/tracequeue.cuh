@@ -65,8 +65,11 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
     NodeRay q;
     int mode = UW_CLOSEST, currentMaterialId = 0;
     float invLen = 0.f, best = 0.f, window = 0.f, cullT = 0.f;
-    int stackRef[UN_STACK];
-    float stackT[UN_STACK];
+    __shared__ int2 s_stack[SM_STACK * WALK_THREADS];
+    int stackRef[UN_STACK - SM_STACK];
+    float stackT[UN_STACK - SM_STACK];
+    WalkStack st;
+    st.sm = s_stack + threadIdx.x; st.lref = stackRef; st.lt = stackT;
     int sp = 0;
     int candIdx[GATHER_CAP], candLeaf[GATHER_CAP];
     float candD[GATHER_CAP], candLeafT[GATHER_CAP];
@@ -107,8 +110,8 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
                     invLen = rsqrtf(len2) * 1.0001f;
                     best = minDistance0; window = minDistance0;
                     cullT = (mode == UW_GATHER) ? minDistance0 : fminf(minDistance0, minDistance0 * invLen);
-                    stackRef[0] = 0; stackT[0] = 0.f; sp = 1;
-                    if (pointQuery) { stackRef[1] = nbMain; stackT[1] = -3.0e38f; sp = 2; }
+                    st.push(0, 0, 0.f); sp = 1;
+                    if (pointQuery) { st.push(1, nbMain, -3.0e38f); sp = 2; }
                     n = 0; overflow = false;
                     out.prim = -1; out.p = f3(0.f, 0.f, 0.f); out.flags = 0;
                     active = true;
@@ -132,11 +135,13 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
             if (searching)
             {
                 --sp;
-                const int ref = stackRef[sp];
-                if (!(stackT[sp] > cullT)) // else: the bound shrank since this entry was pushed
+                int ref;
+                float tEntry;
+                st.pop(sp, ref, tEntry);
+                if (!(tEntry > cullT)) // else: the bound shrank since this entry was pushed
                 {
                     if (ref < 0) cur = ref;
-                    else if (!wideStepSorted(nodes + 8 * ref, q, (ref >= nbMain) ? 0.f : cullT, stackRef, stackT, sp)) { overflow = true; sp = 0; }
+                    else if (!wideStepSorted(nodes + 8 * ref, q, (ref >= nbMain) ? 0.f : cullT, st, sp)) { overflow = true; sp = 0; }
                 }
             }
         }
