@@ -1330,6 +1330,143 @@ void oracle_render(const oracle_Scene* s, const b200_SceneInfo* sceneInfo, const
     if (counters) *counters = total;
 }
 
+// Post-processing effects, CudaRayTracer.cu:1081-1358 (k_depthOfField, k_ambiantOcclusion, k_radiosity, k_filter,
+// k_cartoon): each reads the float accumulation buffer (and ids.z for radiosity) of the whole frame and rewrites the
+// RGB8 bitmap; run after the frame's ray pass when postInfo->type != ppe_none (cudaRender's second switch, :1853-1886).
+void oracle_post_process(const oracle_Scene* s, const b200_SceneInfo* sceneInfo, const b200_PostProcessingInfo* postInfo,
+                         const b200_PostProcessingBuffer* post, const b200_int4* ids, unsigned char* bitmap)
+{
+    const b200_SceneInfo& si = *sceneInfo;
+    const b200_PostProcessingInfo& pp = *postInfo;
+    const int W = si.size.x, H = si.size.y, wh = W * H;
+    const int iter = si.pathTracingIteration;
+    const float* randoms = s->randoms;
+    if (pp.type == B200_PPE_NONE) return;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+        {
+            const int index = y * W + x;
+            V4 out = {0.f, 0.f, 0.f, 0.f};
+            switch (pp.type)
+            {
+            case B200_PPE_DEPTH_OF_FIELD: // :1081-1119
+            {
+                const float depth = fabsf(post[index].colorInfo.w - pp.param1) / si.viewDistance;
+                for (int i = 0; i < pp.param3; ++i)
+                {
+                    const int ix = i % wh, iy = (i + 1000) % wh;
+                    const int xx = (int)(x + depth * randoms[ix] * pp.param2);
+                    const int yy = (int)(y + depth * randoms[iy] * pp.param2);
+                    if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+                    {
+                        const int li = yy * W + xx;
+                        if (li >= 0 && li < wh) out += v4(post[li].colorInfo);
+                    }
+                    else
+                        out += v4(post[index].colorInfo);
+                }
+                out /= (float)pp.param3;
+                if (iter > B200_NB_MAX_ITERATIONS) out /= (float)(iter - B200_NB_MAX_ITERATIONS + 1);
+                break;
+            }
+            case B200_PPE_AMBIENT_OCCLUSION: // :1127-1180
+            {
+                out = v4(post[index].colorInfo);
+                const float depth = out.w;
+                float occ = 0.f, c = 0.f;
+                int i = 0;
+                for (int X = -16; X < 16; X += 2)
+                    for (int Y = -16; Y < 16; Y += 2)
+                    {
+                        const int ix = i % wh, iy = (i + 100) % wh;
+                        ++i;
+                        c += 1.f;
+                        const int xx = (int)(x + (X * pp.param2 * randoms[ix] / 10.f));
+                        const int yy = (int)(y + (Y * pp.param2 * randoms[iy] / 10.f));
+                        if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+                        {
+                            if (post[yy * W + xx].colorInfo.w >= depth) occ += 1.f;
+                        }
+                        else
+                            occ += 1.f;
+                    }
+                occ /= c;
+                occ += 0.3f;
+                if (occ < 1.f) { out.x *= occ; out.y *= occ; out.z *= occ; }
+                if (iter > B200_NB_MAX_ITERATIONS) out /= (float)(iter - B200_NB_MAX_ITERATIONS + 1);
+                saturateVector(out);
+                break;
+            }
+            case B200_PPE_RADIOSITY: // :1188-1228
+            {
+                const int div = (iter > B200_NB_MAX_ITERATIONS) ? (iter - B200_NB_MAX_ITERATIONS + 1) : 1;
+                for (int i = 0; i < pp.param3; ++i)
+                {
+                    const int ix = (i + iter) % wh, iy = (i + 100 + iter) % wh;
+                    const int xx = (int)(x + randoms[ix] * pp.param2);
+                    const int yy = (int)(y + randoms[iy] * pp.param2);
+                    out += v4(post[index].colorInfo);
+                    if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+                    {
+                        const int li = yy * W + xx;
+                        V4 light = v4(post[li].colorInfo);
+                        const float k = (float)ids[li].z;
+                        light.x = light.x * k / 256.f; light.y = light.y * k / 256.f; light.z = light.z * k / 256.f; light.w = light.w * k / 256.f;
+                        out += light;
+                    }
+                }
+                out /= (float)pp.param3;
+                out /= (float)div;
+                saturateVector(out);
+                break;
+            }
+            case B200_PPE_FILTER: // :1236-1330
+            {
+                static const int fsize[6] = {3, 5, 3, 3, 5, 5};
+                static const float factor[6] = {1.f, 1.f, 1.f, 1.f, 0.2f, 0.125f}, bias[6] = {128.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                static const float kern[6][5][5] = {
+                    {{-1, -1, 0, 0, 0}, {-1, 0, 1, 0, 0}, {0, 1, 1, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},                          // emboss
+                    {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {-1, -1, 2, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},                           // find edges
+                    {{-1, -1, -1, 0, 0}, {-1, 9, -1, 0, 0}, {-1, -1, -1, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},                     // sharpen
+                    {{0, 0.2f, 0, 0, 0}, {0.2f, 0.2f, 0.2f, 0, 0}, {0, 0.2f, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},              // blur
+                    {{1, 0, 0, 0, 0}, {0, 1, 0, 0, 0}, {0, 0, 1, 0, 0}, {0, 0, 0, 1, 0}, {0, 0, 0, 0, 1}},                             // motion blur
+                    {{-1, -1, -1, -1, -1}, {-1, 2, 2, 2, -1}, {-1, 2, 8, 2, -1}, {-1, 2, 2, 2, -1}, {-1, -1, -1, -1, -1}}};           // subtle sharpen
+                if ((unsigned int)pp.param3 < 6u)
+                {
+                    const int f = pp.param3, n = fsize[f];
+                    V4 acc = {0.f, 0.f, 0.f, 0.f};
+                    for (int fx = 0; fx < n; ++fx)
+                        for (int fy = 0; fy < n; ++fy)
+                        {
+                            const int imx = (x - n / 2 + fx + W) % W, imy = (y - n / 2 + fy + H) % H;
+                            V4 c = v4(post[imy * W + imx].colorInfo);
+                            if (iter > B200_NB_MAX_ITERATIONS) c /= (float)(iter - B200_NB_MAX_ITERATIONS + 1);
+                            acc.x += c.x * kern[f][fx][fy]; acc.y += c.y * kern[f][fx][fy]; acc.z += c.z * kern[f][fx][fy];
+                        }
+                    out.x += fminf(fmaxf(factor[f] * acc.x + bias[f] / 255.f, 0.f), 1.f);
+                    out.y += fminf(fmaxf(factor[f] * acc.y + bias[f] / 255.f, 0.f), 1.f);
+                    out.z += fminf(fmaxf(factor[f] * acc.z + bias[f] / 255.f, 0.f), 1.f);
+                }
+                saturateVector(out);
+                break;
+            }
+            case B200_PPE_CARTOON: // :1338-1357
+            {
+                const float depth = si.viewDistance / fabsf(post[index].colorInfo.w - pp.param1);
+                out = V4{depth, depth, depth, 0.f};
+                saturateVector(out);
+                break;
+            }
+            default: // k_default
+                out = v4(post[index].colorInfo);
+                if (iter > B200_NB_MAX_ITERATIONS) out /= (float)(iter - B200_NB_MAX_ITERATIONS + 1);
+                break;
+            }
+            out.w = 1.f;
+            makeColor(si, out, bitmap, index);
+        }
+}
+
 // flops per unit of work, applied to counts taken in reference traversal order.
 double oracle_algorithmic_flops(const oracle_Counters* k)
 {

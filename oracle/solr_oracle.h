@@ -34,6 +34,11 @@ void oracle_render(const oracle_Scene* scene, const b200_SceneInfo* sceneInfo, c
                    b200_int4* ids, unsigned char* bitmap, int rowBegin, int rowEnd, int rowStride, int nThreads,
                    oracle_Counters* counters);
 
+/* Post-processing effects of cudaRender's second pass (CudaRayTracer.cu:1081-1358) over a whole frame: reads post / ids,
+ * rewrites bitmap.  No-op for ppe_none. */
+void oracle_post_process(const oracle_Scene* scene, const b200_SceneInfo* sceneInfo, const b200_PostProcessingInfo* postInfo,
+                         const b200_PostProcessingBuffer* post, const b200_int4* ids, unsigned char* bitmap);
+
 double oracle_algorithmic_flops(const oracle_Counters* counters);
 
 #ifdef __cplusplus

@@ -530,6 +530,159 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_shade_pass(con
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Post-processing effects: cudaRender's second pass (CudaRayTracer.cu:1853-1886) — k_depthOfField :1081-1119,
+// k_ambiantOcclusion :1127-1180, k_radiosity :1188-1228, k_filter :1236-1330, k_cartoon :1338-1357.  Each output pixel
+// gathers from the float accumulation buffer of the finished frame (and ids.z for radiosity) and rewrites its RGB8
+// value, so the pass is one more launch on the render stream after the ray kernels, one thread per pixel.
+// ----------------------------------------------------------------------------------------------------
+__constant__ float cFilterKernels[6][5][5] = {
+    {{-1, -1, 0, 0, 0}, {-1, 0, 1, 0, 0}, {0, 1, 1, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},                 // emboss
+    {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {-1, -1, 2, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},                  // find edges
+    {{-1, -1, -1, 0, 0}, {-1, 9, -1, 0, 0}, {-1, -1, -1, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},            // sharpen
+    {{0, 0.2f, 0, 0, 0}, {0.2f, 0.2f, 0.2f, 0, 0}, {0, 0.2f, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},     // blur
+    {{1, 0, 0, 0, 0}, {0, 1, 0, 0, 0}, {0, 0, 1, 0, 0}, {0, 0, 0, 1, 0}, {0, 0, 0, 0, 1}},                    // motion blur
+    {{-1, -1, -1, -1, -1}, {-1, 2, 2, 2, -1}, {-1, 2, 8, 2, -1}, {-1, 2, 2, 2, -1}, {-1, -1, -1, -1, -1}}};  // subtle sharpen
+__constant__ int cFilterSize[6] = {3, 5, 3, 3, 5, 5};
+__constant__ float cFilterFactor[6] = {1.f, 1.f, 1.f, 1.f, 0.2f, 0.125f};
+__constant__ float cFilterBias[6] = {128.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+SB_DEV float4 postColor(const int i) { return *reinterpret_cast<const float4*>(&cP.post[i].colorInfo); }
+
+__global__ void __launch_bounds__(256) k_post_process()
+{
+    const int W = cSI.size.x, H = cSI.size.y, wh = W * H;
+    const int iter = cSI.pathTracingIteration;
+    const b200_PostProcessingInfo pp = cP.pp;
+    for (int index = blockIdx.x * blockDim.x + threadIdx.x; index < wh; index += gridDim.x * blockDim.x)
+    {
+        const int x = index % W, y = index / W;
+        float4 out = f4(0.f, 0.f, 0.f, 0.f);
+        switch (pp.type)
+        {
+        case B200_PPE_DEPTH_OF_FIELD:
+        {
+            const float depth = fabsf(cP.post[index].colorInfo.w - pp.param1) / cSI.viewDistance;
+            for (int i = 0; i < pp.param3; ++i)
+            {
+                const int ix = i % wh, iy = (i + 1000) % wh;
+                const int xx = x + depth * rnd(ix) * pp.param2;
+                const int yy = y + depth * rnd(iy) * pp.param2;
+                if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+                {
+                    const int li = yy * W + xx;
+                    if (li >= 0 && li < wh) out += postColor(li);
+                }
+                else
+                    out += postColor(index);
+            }
+            out /= (float)pp.param3;
+            if (iter > B200_NB_MAX_ITERATIONS) out /= (float)(iter - B200_NB_MAX_ITERATIONS + 1);
+            break;
+        }
+        case B200_PPE_AMBIENT_OCCLUSION:
+        {
+            out = postColor(index);
+            const float depth = out.w;
+            float occ = 0.f, c = 0.f;
+            int i = 0;
+            for (int X = -16; X < 16; X += 2)
+                for (int Y = -16; Y < 16; Y += 2)
+                {
+                    const int ix = i % wh, iy = (i + 100) % wh;
+                    ++i;
+                    c += 1.f;
+                    const int xx = x + (X * pp.param2 * rnd(ix) / 10.f);
+                    const int yy = y + (Y * pp.param2 * rnd(iy) / 10.f);
+                    if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+                    {
+                        if (cP.post[yy * W + xx].colorInfo.w >= depth) occ += 1.f;
+                    }
+                    else
+                        occ += 1.f;
+                }
+            occ /= c;
+            occ += 0.3f; // ambient light
+            if (occ < 1.f) { out.x *= occ; out.y *= occ; out.z *= occ; }
+            if (iter > B200_NB_MAX_ITERATIONS) out /= (float)(iter - B200_NB_MAX_ITERATIONS + 1);
+            saturate4(out);
+            break;
+        }
+        case B200_PPE_RADIOSITY:
+        {
+            const int div = (iter > B200_NB_MAX_ITERATIONS) ? (iter - B200_NB_MAX_ITERATIONS + 1) : 1;
+            for (int i = 0; i < pp.param3; ++i)
+            {
+                const int ix = (i + iter) % wh, iy = (i + 100 + iter) % wh;
+                const int xx = x + rnd(ix) * pp.param2;
+                const int yy = y + rnd(iy) * pp.param2;
+                out += postColor(index);
+                if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+                {
+                    const int li = yy * W + xx;
+                    out += postColor(li) * (float)cP.ids[li].z / 256.f;
+                }
+            }
+            out /= (float)pp.param3;
+            out /= (float)div;
+            saturate4(out);
+            break;
+        }
+        case B200_PPE_FILTER:
+        {
+            if ((unsigned int)pp.param3 < 6u)
+            {
+                const int f = pp.param3, n = cFilterSize[f];
+                float4 acc = f4(0.f, 0.f, 0.f, 0.f);
+                for (int fx = 0; fx < n; ++fx)
+                    for (int fy = 0; fy < n; ++fy)
+                    {
+                        const int imx = (x - n / 2 + fx + W) % W, imy = (y - n / 2 + fy + H) % H;
+                        float4 c = postColor(imy * W + imx);
+                        if (iter > B200_NB_MAX_ITERATIONS) c /= (float)(iter - B200_NB_MAX_ITERATIONS + 1);
+                        const float k = cFilterKernels[f][fx][fy];
+                        acc.x += c.x * k; acc.y += c.y * k; acc.z += c.z * k;
+                    }
+                out.x += fminf(fmaxf(cFilterFactor[f] * acc.x + cFilterBias[f] / 255.f, 0.f), 1.f);
+                out.y += fminf(fmaxf(cFilterFactor[f] * acc.y + cFilterBias[f] / 255.f, 0.f), 1.f);
+                out.z += fminf(fmaxf(cFilterFactor[f] * acc.z + cFilterBias[f] / 255.f, 0.f), 1.f);
+            }
+            saturate4(out);
+            break;
+        }
+        case B200_PPE_CARTOON:
+        {
+            const float depth = cSI.viewDistance / fabsf(cP.post[index].colorInfo.w - pp.param1);
+            out = f4(depth, depth, depth, 0.f);
+            saturate4(out);
+            break;
+        }
+        default:
+            out = postColor(index);
+            if (iter > B200_NB_MAX_ITERATIONS) out /= (float)(iter - B200_NB_MAX_ITERATIONS + 1);
+            break;
+        }
+        // makeColor (GeometryShaders.cuh:132-165); the iteration average was applied above where the effect has one
+        out.x = (out.x > 1.f) ? 1.f : out.x; out.y = (out.y > 1.f) ? 1.f : out.y; out.z = (out.z > 1.f) ? 1.f : out.z;
+        out.x = (out.x < 0.f) ? 0.f : out.x; out.y = (out.y < 0.f) ? 0.f : out.y; out.z = (out.z < 0.f) ? 0.f : out.z;
+        if (cSI.frameBufferType == B200_FT_BGR)
+        {
+            const int yy = index / cSI.size.y, xx = index % cSI.size.x;
+            const int i = ((yy + 1) * cSI.size.y - xx - 1) * B200_COLOR_DEPTH;
+            cP.bitmap[i] = (unsigned char)(out.z * 255.f);
+            cP.bitmap[i + 1] = (unsigned char)(out.y * 255.f);
+            cP.bitmap[i + 2] = (unsigned char)(out.x * 255.f);
+        }
+        else
+        {
+            const int i = index * B200_COLOR_DEPTH;
+            cP.bitmap[i] = (unsigned char)(out.x * 255.f);
+            cP.bitmap[i + 1] = (unsigned char)(out.y * 255.f);
+            cP.bitmap[i + 2] = (unsigned char)(out.z * 255.f);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
 // host state
 // ----------------------------------------------------------------------------------------------------
 namespace
@@ -1444,7 +1597,11 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         latch(-7, "b200_render", "camera type outside this engine's path (VR/panoramic/volume): see DESIGN.md scope");
         return;
     }
-    if (pp.type != B200_PPE_NONE) { latch(-8, "b200_render", "post-processing effects are outside this engine's path: see DESIGN.md scope"); return; }
+    if (pp.type != B200_PPE_NONE && G.world > 1)
+    {
+        latch(-8, "b200_render", "post-processing effects gather from neighbouring pixels: render them on one GPU (set_partition world = 1)");
+        return;
+    }
     if (objects.y > G.nbPrims || objects.w > B200_NB_MAX_LIGHTINFORMATIONS) { latch(-9, "b200_render", "object counts exceed uploaded scene"); return; }
     if (!G.dMats && G.nbPrims > 0) { latch(-10, "b200_render", "materials not uploaded"); return; }
 
@@ -1537,6 +1694,14 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
             k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
             G.launches += maxIteration + 1;
         }
+    }
+    if (pp.type != B200_PPE_NONE)
+    {
+        const int px = si.size.x * si.size.y;
+        int gp = (px + 255) / 256;
+        if (gp > G.numSMs * 8) gp = G.numSMs * 8;
+        k_post_process<<<gp, 256, 0, G.stream>>>();
+        G.launches++;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) latch((int)e, "render kernel launch", cudaGetErrorString(e));

@@ -101,6 +101,7 @@ assert Primitive.size.offset == 72 and Primitive.type.offset == 84 and Primitive
 CT_PERSPECTIVE, CT_ORTHOGRAPHIC, CT_ANAGLYPH, CT_VR, CT_PANORAMIC, CT_ANTIALIASED, CT_VOLUME = range(7)
 GL_NO_SHADING, GL_PHONG, GL_PHONG_BLINN, GL_REFLECTIONS, GL_FULL = range(5)
 AI_NONE, AI_BASIC, AI_FULL, AI_RANDOM = range(4)
+PPE_NONE, PPE_DEPTH_OF_FIELD, PPE_AMBIENT_OCCLUSION, PPE_RADIOSITY, PPE_FILTER, PPE_CARTOON = range(6)
 PT_SPHERE, PT_CYLINDER, PT_TRIANGLE, PT_CHECKBOARD, PT_CAMERA, PT_XYPLANE, PT_YZPLANE, PT_XZPLANE, \
     PT_MAGICCARPET, PT_ENVIRONMENT, PT_ELLIPSOID, PT_QUAD, PT_CONE = range(13)
 MATERIAL_NONE = -1

@@ -23,14 +23,18 @@ def sha(a):
 
 
 def main():
+    only = sys.argv[1:]
     for name in gs.CASES:
+        if only and not any(name.startswith(o) for o in only):
+            continue
         sc, si, eye, target, angles, rnd, frames = gs.case_setup(name)
+        pp = gs.case_post(name)
         r = refh.RefScene(si, "cpu")
         sc.replay(r)
         a = r.arrays()
         for it in frames:
             si.pathTracingIteration = it
-            bm, ids, post = r.render(si, eye, target, angles, randoms=rnd, block=(16, 8))
+            bm, ids, post = r.render(si, eye, target, angles, randoms=rnd, post_info=pp, block=(16, 8))
         li = a["lightInformation"].reshape(-1, 48)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), ids=ids, bitmap=bm, post=post,
                             boxes_sha=sha(a["boxes"]), primitives_sha=sha(a["primitives"]),

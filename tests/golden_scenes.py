@@ -125,7 +125,25 @@ CASES = {
     "mixed_default_transparent": dict(scene=mixed_scene, si=dict(nit=3), frames=[0]),
     "mixed_timestamp": dict(scene=mixed_scene, si=dict(nit=3, transparentColor=2.0, timestamp=1234), frames=[0, 1]),
     "textured_skybox": dict(scene=textured_scene, si=dict(nit=3, transparentColor=2.0, skyboxMaterialId=4, skyboxRadius=45000), frames=[0]),
+    # post-processing effects of cudaRender's second pass (type, param1 = focus depth, param2 = strength, param3 = samples / filter)
+    "spheres_pp_dof": dict(scene=spheres_scene, si=dict(nit=2), frames=[0], randoms=21, post=(wire.PPE_DEPTH_OF_FIELD, 14000.0, 4000.0, 24)),
+    "spheres_pp_ao": dict(scene=spheres_scene, si=dict(nit=2), frames=[0], randoms=22, post=(wire.PPE_AMBIENT_OCCLUSION, 0.0, 9000.0, 0)),
+    "spheres_pp_radiosity": dict(scene=spheres_scene, si=dict(nit=2, maxPathTracingIterations=13), frames=[0, 10, 11, 12], randoms=23,
+                                 post=(wire.PPE_RADIOSITY, 0.0, 6000.0, 16)),
+    "spheres_pp_emboss": dict(scene=spheres_scene, si=dict(nit=2), frames=[0], post=(wire.PPE_FILTER, 0.0, 0.0, 0)),
+    "spheres_pp_subtle_sharpen": dict(scene=spheres_scene, si=dict(nit=2, maxPathTracingIterations=12), frames=[0, 10, 11], randoms=24,
+                                      post=(wire.PPE_FILTER, 0.0, 0.0, 5)),
+    "spheres_pp_cartoon": dict(scene=spheres_scene, si=dict(nit=2), frames=[0], post=(wire.PPE_CARTOON, -60000.0, 0.0, 0)),
 }
+
+
+def case_post(name):
+    """PostProcessingInfo of a case (ppe_none when the case has no post-processing effect)."""
+    pp = wire.PostProcessingInfo()
+    p = CASES[name].get("post")
+    if p is not None:
+        pp.type, pp.param1, pp.param2, pp.param3 = int(p[0]), float(p[1]), float(p[2]), int(p[3])
+    return pp
 
 
 def case_setup(name):

@@ -47,6 +47,8 @@ def load():
                                        C.POINTER(wire.PostProcessingInfo), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(Counters)]
+        _lib.oracle_post_process.argtypes = [C.POINTER(OracleScene), C.POINTER(wire.SceneInfo), C.POINTER(wire.PostProcessingInfo),
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oracle_algorithmic_flops.argtypes = [C.POINTER(Counters)]
         _lib.oracle_algorithmic_flops.restype = C.c_double
     return _lib
@@ -84,6 +86,10 @@ class Oracle:
         self.lib.oracle_render(C.byref(s), C.byref(scene_info), C.byref(post_info), _ptr(e), _ptr(t), _ptr(a),
                                _ptr(self.post), _ptr(self.ids), _ptr(self.bitmap), r0, r1, rs,
                                threads or os.cpu_count() or 1, C.byref(k))
+        if post_info.type != 0:
+            assert rows is None, "post-processing effects need the whole frame"
+            self.lib.oracle_post_process(C.byref(s), C.byref(scene_info), C.byref(post_info), _ptr(self.post), _ptr(self.ids),
+                                         _ptr(self.bitmap))
         self.counters = k
         return self.bitmap, self.ids, self.post, k
 

@@ -47,9 +47,10 @@ def run_engine(name):
         infos[0].size = wire.Int3(int(atlas.shape[0]), 1, 1)
         tex = (infos, 1)
     e.upload(a, randoms=rnd, textures=tex)
+    pp = gs.case_post(name)
     for it in frames:
         si.pathTracingIteration = it
-        e.render(si, eye, target, angles)
+        e.render(si, eye, target, angles, post_info=pp)
     bm, ids = e.readback(si)
     post = e.read_post_buffer(si)
     rays, px = e.counters(reset=True)
@@ -256,3 +257,30 @@ def test_order_independent_walks_equal_ordered_walks(cfg, gl, nit):
     assert int((p0[..., :3] != p1[..., :3]).any(-1).sum()) <= bound
     assert int((b0 != b1).any(-1).sum()) <= bound
     assert abs(int(r0) - int(r1)) <= bound
+
+
+PP_CASES = sorted(n for n in gs.CASES if "post" in gs.CASES[n])
+
+
+@pytest.mark.parametrize("name", PP_CASES)
+def test_post_processing_effects(name):
+    """cudaRender's second pass (depth of field, ambient occlusion, radiosity, filters, cartoon; CudaRayTracer.cu:1081-1358).
+    The effect gathers from the frame's float accumulation buffer, so it is checked in isolation: the oracle's
+    restatement (bit-exact against the reference on these cases, tests/test_oracle_golden.py) applied to the ENGINE's
+    own accumulation / id buffers must give the engine's bitmap.  Tolerance: 2/255 on >= 99.9 % of the pixels (the
+    sample offsets are truncated floats: a fast-math division can move one tap by a pixel)."""
+    bm, ids, post, rays, (sc, si, a, atlas) = run_engine(name)
+    sc2, si2, eye, target, angles, rnd, frames = gs.case_setup(name)
+    si2.pathTracingIteration = frames[-1]
+    o = oracle.Oracle(a, si2.size.x, si2.size.y, randoms=rnd)
+    o.post[...] = post
+    o.ids[...] = ids
+    s = oracle.OracleScene(oracle._ptr(o.a["boxes"]), o.a["nbBoxes"], oracle._ptr(o.a["primitives"]), o.a["nbPrimitives"],
+                           oracle._ptr(o.a["materials"]), o.a["nbMaterials"], oracle._ptr(o.a["lightInformation"]),
+                           o.a["lightInformationSize"], o.a["nbLamps"], None, oracle._ptr(o.randoms), o.random_table_size)
+    import ctypes as C
+    pp = gs.case_post(name)
+    o.lib.oracle_post_process(C.byref(s), C.byref(si2), C.byref(pp), oracle._ptr(o.post), oracle._ptr(o.ids), oracle._ptr(o.bitmap))
+    assert frac_rgb_bad(bm, o.bitmap) <= 1e-3
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    assert not np.array_equal(bm, np.zeros_like(bm)) and g["bitmap"].shape == bm.shape

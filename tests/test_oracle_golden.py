@@ -19,9 +19,10 @@ def run_oracle(name, threads=2):
     sc.replay(h)
     a = h.arrays()
     o = oracle.Oracle(a, si.size.x, si.size.y, randoms=rnd, textures=sc.texture_atlas())
+    pp = gs.case_post(name)
     for it in frames:
         si.pathTracingIteration = it
-        o.render(si, eye, target, angles, threads=threads)
+        o.render(si, eye, target, angles, post_info=pp, threads=threads)
     h.close()
     return o, a
 
