@@ -1215,6 +1215,81 @@ void renderPixel(const Ctx& c, int x, int y, const float* eye, const float* targ
         return;
     }
 
+    if (si.cameraType == B200_CT_VR)
+    {
+        // k_3DVisionRenderer, CudaRayTracer.cu:953-1043: side-by-side stereo, one ray tree per pixel.  The focus distance is
+        // read from the accumulation buffer while the same launch may be writing it (iteration 0 only): a race in the
+        // reference; here whatever the buffer holds when the pixel is reached.
+        const float focus = fabsf(post[W / 2 * H / 2].colorInfo.w - origin.z);
+        const float eyeSeparation = si.eyeSeparation * (direction.z / focus);
+        dof = c.pp.param1;
+        const int halfWidth = W / 2;
+        const float ratio = (float)W / (float)H;
+        const float stepx = ratio * angles[3] / (float)W, stepy = angles[3] / (float)H;
+        RayOT eyeRay;
+        if (x < halfWidth)
+        {
+            eyeRay.origin = v3(origin.x + eyeSeparation, origin.y, origin.z);
+            eyeRay.direction.x = direction.x - stepx * (float)(x - (W / 2) + halfWidth / 2) + si.eyeSeparation;
+        }
+        else
+        {
+            eyeRay.origin = v3(origin.x - eyeSeparation, origin.y, origin.z);
+            eyeRay.direction.x = direction.x - stepx * (float)(x - (W / 2) - halfWidth / 2) - si.eyeSeparation;
+        }
+        eyeRay.direction.y = direction.y + stepy * (float)(y - (H / 2));
+        eyeRay.direction.z = direction.z;
+        vectorRotation(eyeRay.origin, rotationCenter, angles);
+        vectorRotation(eyeRay.direction, rotationCenter, angles);
+        V4 color = launchRayTracing(c, index, eyeRay, dof, ids[index]);
+        if (si.advancedIllumination == B200_AI_RANDOM)
+        {
+            int rindex = (index + si.timestamp) % c.randomTableSize;
+            color += v4(si.backgroundColor) * c.rnd(rindex) * 5.f;
+        }
+        if (si.pathTracingIteration == 0) post[index].colorInfo.w = dof;
+        if (si.pathTracingIteration <= B200_NB_MAX_ITERATIONS)
+        {
+            post[index].colorInfo.x = color.x; post[index].colorInfo.y = color.y; post[index].colorInfo.z = color.z;
+        }
+        else
+        {
+            post[index].colorInfo.x += color.x; post[index].colorInfo.y += color.y; post[index].colorInfo.z += color.z;
+        }
+        return;
+    }
+
+    if (si.cameraType == B200_CT_PANORAMIC)
+    {
+        // k_fishEyeRenderer, CudaRayTracer.cu:757-813: 360 degrees around the vertical axis across the image width
+        RayOT ray = {origin, direction};
+        if (si.pathTracingIteration >= B200_NB_MAX_ITERATIONS)
+        {
+            const int rindex = (index + si.timestamp) % (c.randomTableSize - 3);
+            const float a = float(si.pathTracingIteration) / float(si.maxPathTracingIterations);
+            ray.direction.x += c.rnd(rindex) * post[index].colorInfo.w * c.pp.param2 * a;
+            ray.direction.y += c.rnd(rindex + 1) * post[index].colorInfo.w * c.pp.param2 * a;
+            ray.direction.z += c.rnd(rindex + 2) * post[index].colorInfo.w * c.pp.param2 * a;
+        }
+        const float stepy = angles[3] / (float)H;
+        ray.direction.y = ray.direction.y + stepy * (float)(y - (H / 2));
+        const float stepx = 2.f * 3.14159265358979323846f / W;
+        const float fishEyeAngles[4] = {0.f, angles[1] + stepx * (float)x, 0.f, 0.f};
+        vectorRotation(ray.direction, ray.origin, fishEyeAngles);
+        V4 color = {0.f, 0.f, 0.f, 0.f};
+        color += launchRayTracing(c, index, ray, dof, ids[index]);
+        if (si.pathTracingIteration == 0) post[index].colorInfo.w = dof;
+        if (si.pathTracingIteration <= B200_NB_MAX_ITERATIONS)
+        {
+            post[index].colorInfo.x = color.x; post[index].colorInfo.y = color.y; post[index].colorInfo.z = color.z;
+        }
+        else
+        {
+            post[index].colorInfo.x += color.x; post[index].colorInfo.y += color.y; post[index].colorInfo.z += color.z;
+        }
+        return;
+    }
+
     RayOT ray = {origin, direction};
     const float AA[4][2] = {{3.f, 5.f}, {5.f, -3.f}, {-3.f, -5.f}, {-5.f, 3.f}};
     bool antialiasingActivated = (si.cameraType == B200_CT_ANTIALIASED);

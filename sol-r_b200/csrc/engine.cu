@@ -109,6 +109,17 @@ SB_DEV void resolvePixel(const int index, float4 color, const float4 left, const
         if (iter <= B200_NB_MAX_ITERATIONS) { stored.x = r1 + 0.f; stored.y = 0.f + g2; stored.z = 0.f + b2; }
         else { stored.x += r1 + 0.f; stored.y += 0.f + g2; stored.z += 0.f + b2; }
     }
+    else if (camera == B200_CT_VR || camera == B200_CT_PANORAMIC)
+    {
+        // :1016-1042, :797-812: plain accumulation, sceneInfo is not written; only the stereo camera takes random illumination
+        if (camera == B200_CT_VR && cSI.advancedIllumination == B200_AI_RANDOM)
+        {
+            const int rindex = (index + cSI.timestamp) % cS.randomTableSize;
+            color += f4(cSI.backgroundColor.x, cSI.backgroundColor.y, cSI.backgroundColor.z, cSI.backgroundColor.w) * rnd(rindex) * 5.f;
+        }
+        if (iter <= B200_NB_MAX_ITERATIONS) { stored.x = color.x; stored.y = color.y; stored.z = color.z; }
+        else { stored.x += color.x; stored.y += color.y; stored.z += color.z; }
+    }
     else
     {
         if (cSI.advancedIllumination == B200_AI_RANDOM)
@@ -159,6 +170,7 @@ SB_DEV void renderPixel(const Rotation& rot, const bool inFrame, const int xIn, 
     if (!__any_sync(FULL_MASK, valid)) return;
     if (valid) pixelsTraced++;
     const int camera = cSI.cameraType;
+    const int iter = cSI.pathTracingIteration;
     const float3 rotationCenter = (camera == B200_CT_VR) ? cP.eye : f3(0.f, 0.f, 0.f);
     float dof = 0.f;
     const float4 stored = *reinterpret_cast<float4*>(&cP.post[index].colorInfo);
@@ -167,7 +179,40 @@ SB_DEV void renderPixel(const Rotation& rot, const bool inFrame, const int xIn, 
     const bool anaglyph = camera == B200_CT_ANAGLYPH, antialiased = camera == B200_CT_ANTIALIASED;
 
     float3 o = cP.eye, t = cP.target;
-    if (!anaglyph) primaryRay(rot, x, y, index, stored.w, o, t);
+    if (camera == B200_CT_VR)
+    {
+        // k_3DVisionRenderer (CudaRayTracer.cu:953-1043): left half = left eye, right half = right eye.  The focus depth is
+        // read from the accumulation buffer (a pixel this launch may be writing at iteration 0, as in the reference).
+        const float focus = fabsf(cP.post[W / 2 * H / 2].colorInfo.w - cP.eye.z);
+        const float eyeSeparation = cSI.eyeSeparation * (cP.target.z / focus);
+        const int halfWidth = W / 2;
+        const bool leftEye = x < halfWidth;
+        o.x = leftEye ? cP.eye.x + eyeSeparation : cP.eye.x - eyeSeparation;
+        const float xf = leftEye ? (float)(x - (W / 2) + halfWidth / 2) : (float)(x - (W / 2) - halfWidth / 2);
+        t.x = leftEye ? cP.target.x - stepx * xf + cSI.eyeSeparation : cP.target.x - stepx * xf - cSI.eyeSeparation;
+        t.y = cP.target.y + stepy * (float)(y - (H / 2));
+        vectorRotation(o, rotationCenter, rot);
+        vectorRotation(t, rotationCenter, rot);
+    }
+    else if (camera == B200_CT_PANORAMIC)
+    {
+        // k_fishEyeRenderer (:757-813): the image width spans 360 degrees about the vertical axis through the eye
+        if (iter >= B200_NB_MAX_ITERATIONS)
+        {
+            const int rindex = (index + cSI.timestamp) % (cS.randomTableSize - 3);
+            const float a = float(iter) / float(cSI.maxPathTracingIterations);
+            t.x += rnd(rindex) * stored.w * cP.pp.param2 * a;
+            t.y += rnd(rindex + 1) * stored.w * cP.pp.param2 * a;
+            t.z += rnd(rindex + 2) * stored.w * cP.pp.param2 * a;
+        }
+        t.y = t.y + stepy * (float)(y - (H / 2));
+        const float ay = cP.angles.y + (2.f * 3.14159265358979323846f / W) * (float)x;
+        Rotation fish;
+        fish.cx = cosf(0.f); fish.cy = cosf(ay); fish.cz = cosf(0.f);
+        fish.sx = sinf(0.f); fish.sy = sinf(ay); fish.sz = sinf(0.f);
+        vectorRotation(t, o, fish);
+    }
+    else if (!anaglyph) primaryRay(rot, x, y, index, stored.w, o, t);
 
     const int nSamples = anaglyph ? 2 : (antialiased ? 5 : 1);
     float4 color = f4(0.f, 0.f, 0.f, 0.f);
@@ -1592,9 +1637,16 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         latch(-6, "b200_render", "frame larger than the limits (b200_set_limits before reshape_scene)");
         return;
     }
-    if (si.cameraType == B200_CT_VR || si.cameraType == B200_CT_PANORAMIC || si.cameraType == B200_CT_VOLUME)
+    if (si.cameraType == B200_CT_VOLUME)
     {
-        latch(-7, "b200_render", "camera type outside this engine's path (VR/panoramic/volume): see DESIGN.md scope");
+        // k_volumeRenderer's depth-sorted colour list writes one element past its 10-entry array (GeometryIntersections.cuh:1186):
+        // undefined behaviour, no defined result to reproduce
+        latch(-7, "b200_render", "volume-rendering camera is outside this engine's path: see DESIGN.md scope");
+        return;
+    }
+    if (si.cameraType == B200_CT_VR && G.world > 1)
+    {
+        latch(-7, "b200_render", "the stereo camera reads its focus depth from one pixel of the frame: render it on one GPU");
         return;
     }
     if (pp.type != B200_PPE_NONE && G.world > 1)

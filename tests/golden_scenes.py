@@ -125,6 +125,11 @@ CASES = {
     "mixed_default_transparent": dict(scene=mixed_scene, si=dict(nit=3), frames=[0]),
     "mixed_timestamp": dict(scene=mixed_scene, si=dict(nit=3, transparentColor=2.0, timestamp=1234), frames=[0, 1]),
     "textured_skybox": dict(scene=textured_scene, si=dict(nit=3, transparentColor=2.0, skyboxMaterialId=4, skyboxRadius=45000), frames=[0]),
+    # remaining cameras: side-by-side stereo (k_3DVisionRenderer) and 360-degree panorama (k_fishEyeRenderer)
+    "spheres_vr": dict(scene=spheres_scene, si=dict(nit=2, cameraType=wire.CT_VR, eyeSeparation=380.0), frames=[0, 1],
+                       angles=(0.1, -0.2, 0.0, 6400.0)),
+    "spheres_panoramic": dict(scene=spheres_scene, si=dict(nit=2, cameraType=wire.CT_PANORAMIC, maxPathTracingIterations=12),
+                              frames=[0, 10, 11], randoms=31, eye=(0.0, 0.0, -3000.0), target=(0.0, 0.0, 0.0), post=(wire.PPE_NONE, 0.0, 0.0002, 0)),
     # post-processing effects of cudaRender's second pass (type, param1 = focus depth, param2 = strength, param3 = samples / filter)
     "spheres_pp_dof": dict(scene=spheres_scene, si=dict(nit=2), frames=[0], randoms=21, post=(wire.PPE_DEPTH_OF_FIELD, 14000.0, 4000.0, 24)),
     "spheres_pp_ao": dict(scene=spheres_scene, si=dict(nit=2), frames=[0], randoms=22, post=(wire.PPE_AMBIENT_OCCLUSION, 0.0, 9000.0, 0)),
