@@ -10,6 +10,7 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <thread>
 
 #include <cuda_runtime.h>
 
@@ -1146,30 +1147,24 @@ struct SahBuilder
 {
     const std::vector<LeafRec>& leaves;
     std::vector<int> order;          // permutation of leaf ordinals, partitioned in place
-    std::vector<float4>& out;        // binary list: leaf nodes carry (leaf ordinal, -1) in (w0, w1) -> see below
+    std::vector<float4>& out;        // binary list: leaf nodes carry (first primitive, count) in (w0, w1), inner nodes the skip count
     std::vector<int>& leafOfNode;    // per emitted node: leaf ordinal or -1
     SahBuilder(const std::vector<LeafRec>& l, std::vector<float4>& o, std::vector<int>& lon) : leaves(l), out(o), leafOfNode(lon)
     {
         order.resize(l.size());
         for (size_t i = 0; i < l.size(); ++i) order[i] = (int)i;
     }
-    int emit(const Aabb& b, int w0, int w1, int leaf)
+    static void emit(std::vector<float4>& o, std::vector<int>& lon, const Aabb& b, int w0, int w1, int leaf)
     {
-        const int at = (int)(out.size() / 2);
-        out.push_back(make_float4(b.lo[0], b.lo[1], b.lo[2], intBits(w0)));
-        out.push_back(make_float4(b.hi[0], b.hi[1], b.hi[2], intBits(w1)));
-        leafOfNode.push_back(leaf);
-        return at;
+        o.push_back(make_float4(b.lo[0], b.lo[1], b.lo[2], intBits(w0)));
+        o.push_back(make_float4(b.hi[0], b.hi[1], b.hi[2], intBits(w1)));
+        lon.push_back(leaf);
     }
-    void build(int i, int j, int depth)
+    // bounds of [i, j) and the split position (binned SAH on box centroids, 16 bins per axis; median when no split helps)
+    int split(int i, int j, int depth, Aabb& all)
     {
-        if (j - i == 1)
-        {
-            const LeafRec& l = leaves[order[i]];
-            emit(l.box, l.start, l.count, order[i]);
-            return;
-        }
-        Aabb all = leaves[order[i]].box, cb;
+        all = leaves[order[i]].box;
+        Aabb cb;
         for (int k = 0; k < 3; ++k) cb.lo[k] = 3e38f, cb.hi[k] = -3e38f;
         for (int k = i; k < j; ++k)
         {
@@ -1230,11 +1225,40 @@ struct SahBuilder
             }
             if (l > i && l < j) mid = l;
         }
-        const int at = emit(all, 0, 0, -1);
-        build(i, mid, depth + 1);
-        build(mid, j, depth + 1);
-        out[2 * (size_t)at].w = intBits((int)(out.size() / 2) - at);
+        return mid;
     }
+    // depth-first list of the subtree over order[i, j) appended to (o, lon); skip counts are relative, so lists concatenate
+    void buildInto(std::vector<float4>& o, std::vector<int>& lon, int i, int j, int depth)
+    {
+        if (j - i == 1)
+        {
+            const LeafRec& l = leaves[order[i]];
+            emit(o, lon, l.box, l.start, l.count, order[i]);
+            return;
+        }
+        Aabb all;
+        const int mid = split(i, j, depth, all);
+        const size_t at = o.size() / 2;
+        emit(o, lon, all, 0, 0, -1);
+        if (depth < 4 && j - i > 8192)
+        {
+            // the two halves are independent (disjoint ranges of `order`): build the left one on another thread
+            std::vector<float4> lo_; std::vector<int> ll_;
+            std::thread worker([&]() { buildInto(lo_, ll_, i, mid, depth + 1); });
+            std::vector<float4> ro_; std::vector<int> rl_;
+            buildInto(ro_, rl_, mid, j, depth + 1);
+            worker.join();
+            o.insert(o.end(), lo_.begin(), lo_.end()); lon.insert(lon.end(), ll_.begin(), ll_.end());
+            o.insert(o.end(), ro_.begin(), ro_.end()); lon.insert(lon.end(), rl_.begin(), rl_.end());
+        }
+        else
+        {
+            buildInto(o, lon, i, mid, depth + 1);
+            buildInto(o, lon, mid, j, depth + 1);
+        }
+        o[2 * at].w = intBits((int)(o.size() / 2 - at));
+    }
+    void build(int i, int j, int depth) { buildInto(out, leafOfNode, i, j, depth); }
 };
 
 int g_useWide = 1;
@@ -1487,20 +1511,26 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
                 }
             }
         }
-        std::vector<int> leafOfNode;
-        ubin.reserve(4 * (size_t)nbPrims);
-        SahBuilder sb(primBoxes, ubin, leafOfNode);
-        sb.build(0, nbPrims, 0);
-        std::vector<float4> unusedLeafRecs;
-        G.nbUWide = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode);
-        if (!extBoxes.empty())
-        {
-            std::vector<int> leafOfNodeX, primOfNode;
+        // the two trees are independent: the point-query tree is built on a second thread
+        std::vector<int> leafOfNode, leafOfNodeX, primOfNode;
+        std::vector<float4> unusedLeafRecs, unusedLeafRecsX;
+        int nbUX = 0;
+        std::thread extThread([&]() {
+            if (extBoxes.empty()) return;
             SahBuilder sx(extBoxes, xbin, leafOfNodeX);
             sx.build(0, (int)extBoxes.size(), 0);
             primOfNode.resize(leafOfNodeX.size());
             for (size_t k = 0; k < leafOfNodeX.size(); ++k) primOfNode[k] = leafOfNodeX[k] < 0 ? -1 : extBoxes[leafOfNodeX[k]].start;
-            G.nbUX = buildWide(xbin, xwide, unusedLeafRecs, &primOfNode);
+            nbUX = buildWide(xbin, xwide, unusedLeafRecsX, &primOfNode);
+        });
+        ubin.reserve(4 * (size_t)nbPrims);
+        SahBuilder sb(primBoxes, ubin, leafOfNode);
+        sb.build(0, nbPrims, 0);
+        G.nbUWide = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode);
+        extThread.join();
+        if (!extBoxes.empty())
+        {
+            G.nbUX = nbUX;
             // appended to the first tree: inner refs move by its size, leaf refs get bit 30
             for (int k = 0; k < G.nbUX; ++k)
             {
