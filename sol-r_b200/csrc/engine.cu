@@ -450,13 +450,24 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_pass(con
         if (base >= count) break;
         const bool has = base + lane < count;
         const size_t slot = has ? (size_t)cP.pathQueues[(size_t)pass * cP.pathStride + base + lane] : 0;
+        // the walk first, with only the ray live: the rest of the path is loaded after it, so the call into the walk has
+        // next to nothing to save (call-boundary spills were most of the kernel's local-memory traffic)
+        Hit hit;
+        hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
+        const bool separateWalk = cS.nbUWide > 0 && cSI.renderBoxes == 0;
+        if (separateWalk && has)
+        {
+            const float* w = cP.pathWords + slot;
+            const size_t n = cP.pathStride;
+            hit = closestHitOrderIndependent(f3(w[0], w[n], w[2 * n]), f3(w[3 * n], w[4 * n], w[5 * n]), pass, __float_as_int(w[7 * n]));
+        }
         PathState s;
         int index = 0;
         loadPath(slot, s, index);
         if (!has) index = 0;
         GlobalColors C;
         C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
-        pathPass(s, C, pass, has, index, f3(0.f, 0.f, 0.f), 0, cnt);
+        pathPass(s, C, pass, has, index, f3(0.f, 0.f, 0.f), 0, cnt, separateWalk ? &hit : nullptr);
         routePath(has, s, C, pass, slot, index);
         __syncwarp();
     }
@@ -1264,6 +1275,7 @@ struct SahBuilder
 int g_useWide = 1;
 int g_useUnordered = 1;
 int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: also the closest-hit walks in their own kernel
+int g_traceCtasPerSM = 0; // experiment: resident CTAs per SM for the trace-queue kernel (0 = occupancy maximum)
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
@@ -1314,6 +1326,7 @@ void b200_set_option(int key, int value)
     else if (key == 4) g_useUnordered = value != 0;
     else if (key == 5) g_useBackward = value != 0;
     else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value;
+    else if (key == 7 && value >= 0) g_traceCtasPerSM = value;
     else latch(-11, "b200_set_option", "unknown option");
 }
 void b200_set_partition(int rank, int world)
@@ -1760,7 +1773,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
             k_gen_primary<<<gg, CTA_THREADS, 0, G.stream>>>();
             for (int pass = 0; pass < maxIteration; ++pass)
             {
-                k_trace_closest<<<G.numSMs * G.ctasPerSMStage[4], CTA_THREADS, 0, G.stream>>>(pass);
+                k_trace_closest<<<G.numSMs * ((g_traceCtasPerSM > 0 && g_traceCtasPerSM < G.ctasPerSMStage[4]) ? g_traceCtasPerSM : G.ctasPerSMStage[4]), CTA_THREADS, 0, G.stream>>>(pass);
                 k_shade_pass<<<G.numSMs * G.ctasPerSMStage[5], CTA_THREADS, 0, G.stream>>>(pass);
             }
             k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();

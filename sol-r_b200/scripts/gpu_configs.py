@@ -27,6 +27,8 @@ for cfg in which:
     h.set_camera(sc.eye, sc.target, sc.angles)
     h.init_buffers()
     lib = engine.load()
+    if os.environ.get('SOLR_OPT6') is not None: lib.b200_set_option(6, int(os.environ['SOLR_OPT6']))
+    if os.environ.get('SOLR_OPT4') is not None: lib.b200_set_option(4, int(os.environ['SOLR_OPT4']))
     e = engine.Engine.__new__(engine.Engine); e.lib = lib
     ms = []
     for it in frames:

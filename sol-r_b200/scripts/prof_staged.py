@@ -9,8 +9,10 @@ mode, gl, nit, frames = (int(v) for v in sys.argv[1:5])
 sc = scenes.config2(); W, H = 1920, 1080
 si = wire.default_scene_info(W, H, graphics_level=gl, nb_ray_iterations=nit)
 h = host.SceneHost(si); sc.replay(h); a = h.arrays(); h.close()
-e = engine.Engine(si); e.set_option(6, mode); e.upload(a, randoms=np.zeros(W * H, np.float32))
+e = engine.Engine(si); e.set_option(6, mode)
+if os.environ.get('SOLR_OPT7'): e.set_option(7, int(os.environ['SOLR_OPT7']))
+e.upload(a, randoms=np.zeros(W * H, np.float32))
 for it in range(frames):
     e.render(si, sc.eye, sc.target, sc.angles); e.synchronize()
     print("ms", e.last_render_ms(), e.counters(reset=True))
-e.set_option(6, 2); e.close()
+e.set_option(6, 1); e.set_option(7, 0); e.close()
