@@ -1047,14 +1047,16 @@ bool collectLeaves(const b200_BoundingBox* boxes, int nbBoxes, std::vector<LeafR
     return ok;
 }
 
-// 4-wide collapse of the binary list (depth-first, skip counts): a node adopts its grandchildren, largest surface
-// area first and keeping array order, until it has four children.
+// Wide collapse of the binary list (depth-first, skip counts): a node adopts its grandchildren, largest surface area
+// first and keeping array order, until it has `width` children (4, or 8 for the unordered trees).  A node is width/4
+// consecutive 128-byte records of four children each: lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] refs[4] (pad).
 struct WideBuilder
 {
     const std::vector<float4>& bin;  // 2 float4 per binary node
-    std::vector<float4>& wide;       // 8 float4 per wide node
+    std::vector<float4>& wide;       // 8 float4 per record
     std::vector<int> leafOrdinal;    // binary node index -> leaf ordinal
-    WideBuilder(const std::vector<float4>& b, std::vector<float4>& w) : bin(b), wide(w) {}
+    int width;
+    WideBuilder(const std::vector<float4>& b, std::vector<float4>& w, int wd) : bin(b), wide(w), width(wd) {}
     int w0(int i) const { int v; memcpy(&v, &bin[2 * (size_t)i].w, 4); return v; }
     int w1(int i) const { int v; memcpy(&v, &bin[2 * (size_t)i + 1].w, 4); return v; }
     bool isLeaf(int i) const { return w1(i) > 0; }
@@ -1065,12 +1067,40 @@ struct WideBuilder
         const double x = (double)hi.x - lo.x, y = (double)hi.y - lo.y, z = (double)hi.z - lo.z;
         return (x < 0 || y < 0 || z < 0) ? 0.0 : 2.0 * (x * y + y * z + z * x);
     }
+    void writeNode(int at, const int* kids, const int* refs, int n)
+    {
+        const int recs = width / 4;
+        for (int q = 0; q < recs; ++q)
+        {
+            float rows[6][4];
+            int rf[4];
+            for (int k = 0; k < 4; ++k)
+            {
+                const int c = 4 * q + k;
+                if (c < n)
+                {
+                    const float4 lo = bin[2 * (size_t)kids[c]], hi = bin[2 * (size_t)kids[c] + 1];
+                    rows[0][k] = lo.x; rows[1][k] = lo.y; rows[2][k] = lo.z; rows[3][k] = hi.x; rows[4][k] = hi.y; rows[5][k] = hi.z;
+                    rf[k] = refs[c];
+                }
+                else
+                {
+                    rows[0][k] = rows[1][k] = rows[2][k] = 3.0e38f; rows[3][k] = rows[4][k] = rows[5][k] = -3.0e38f;
+                    rf[k] = (int)0x80000000;
+                }
+            }
+            float4* rec = &wide[8 * ((size_t)at * recs + q)];
+            for (int r = 0; r < 6; ++r) rec[r] = make_float4(rows[r][0], rows[r][1], rows[r][2], rows[r][3]);
+            rec[6] = make_float4(intBits(rf[0]), intBits(rf[1]), intBits(rf[2]), intBits(rf[3]));
+            rec[7] = make_float4(intBits(n), 0.f, 0.f, 0.f);
+        }
+    }
     int build(int i) // i: inner binary node
     {
-        int kids[4], n = 2;
+        int kids[8], n = 2;
         kids[0] = i + 1;
         kids[1] = i + 1 + size(i + 1);
-        while (n < 4)
+        while (n < width)
         {
             int best = -1;
             double bestArea = -1.0;
@@ -1083,39 +1113,24 @@ struct WideBuilder
             kids[best + 1] = c + 1 + size(c + 1);
             ++n;
         }
-        const int at = (int)(wide.size() / 8);
-        wide.resize(wide.size() + 8);
-        float rows[8][4];
-        int refs[4];
-        for (int k = 0; k < 4; ++k)
-        {
-            if (k < n)
-            {
-                const float4 lo = bin[2 * (size_t)kids[k]], hi = bin[2 * (size_t)kids[k] + 1];
-                rows[0][k] = lo.x; rows[1][k] = lo.y; rows[2][k] = lo.z; rows[3][k] = hi.x; rows[4][k] = hi.y; rows[5][k] = hi.z;
-            }
-            else
-            {
-                rows[0][k] = rows[1][k] = rows[2][k] = 3.0e38f; rows[3][k] = rows[4][k] = rows[5][k] = -3.0e38f;
-                refs[k] = (int)0x80000000;
-            }
-        }
+        const int recs = width / 4;
+        const int at = (int)(wide.size() / (8 * (size_t)recs));
+        wide.resize(wide.size() + 8 * (size_t)recs);
+        int refs[8];
         for (int k = 0; k < n; ++k) refs[k] = isLeaf(kids[k]) ? ~leafOrdinal[kids[k]] : build(kids[k]);
-        for (int r = 0; r < 6; ++r) wide[8 * (size_t)at + r] = make_float4(rows[r][0], rows[r][1], rows[r][2], rows[r][3]);
-        wide[8 * (size_t)at + 6] = make_float4(intBits(refs[0]), intBits(refs[1]), intBits(refs[2]), intBits(refs[3]));
-        wide[8 * (size_t)at + 7] = make_float4(intBits(n), 0.f, 0.f, 0.f);
+        writeNode(at, kids, refs, n);
         return at;
     }
 };
 
-// wide nodes + leaf records from the ordered binary list; returns the number of wide nodes
+// wide nodes + leaf records from the binary list; returns the number of wide nodes
 int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::vector<float4>& leafRecs,
-              const std::vector<int>* leafOfNode = nullptr)
+              const std::vector<int>* leafOfNode = nullptr, int width = 4)
 {
     wide.clear();
     const int nb = (int)(bin.size() / 2);
     if (nb == 0) return 0;
-    WideBuilder b(bin, wide);
+    WideBuilder b(bin, wide, width);
     b.leafOrdinal.assign(nb, -1);
     if (leafOfNode)
     {
@@ -1133,20 +1148,17 @@ int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::ve
                 leafRecs.push_back(bin[2 * (size_t)i + 1]);
             }
     }
+    const int recs = width / 4;
     if (b.isLeaf(0))
     {
         // a single leaf: one wide node with one child
-        wide.resize(8);
-        const float4 lo = bin[0], hi = bin[1];
-        const float big = 3.0e38f;
-        wide[0] = make_float4(lo.x, big, big, big); wide[1] = make_float4(lo.y, big, big, big); wide[2] = make_float4(lo.z, big, big, big);
-        wide[3] = make_float4(hi.x, -big, -big, -big); wide[4] = make_float4(hi.y, -big, -big, -big); wide[5] = make_float4(hi.z, -big, -big, -big);
-        wide[6] = make_float4(intBits(~b.leafOrdinal[0]), intBits((int)0x80000000), intBits((int)0x80000000), intBits((int)0x80000000));
-        wide[7] = make_float4(intBits(1), 0.f, 0.f, 0.f);
+        wide.resize(8 * (size_t)recs);
+        const int kid = 0, ref = ~b.leafOrdinal[0];
+        b.writeNode(0, &kid, &ref, 1);
         return 1;
     }
     b.build(0);
-    return (int)(wide.size() / 8);
+    return (int)(wide.size() / (8 * (size_t)recs));
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -1534,20 +1546,20 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
             sx.build(0, (int)extBoxes.size(), 0);
             primOfNode.resize(leafOfNodeX.size());
             for (size_t k = 0; k < leafOfNodeX.size(); ++k) primOfNode[k] = leafOfNodeX[k] < 0 ? -1 : extBoxes[leafOfNodeX[k]].start;
-            nbUX = buildWide(xbin, xwide, unusedLeafRecsX, &primOfNode);
+            nbUX = buildWide(xbin, xwide, unusedLeafRecsX, &primOfNode, UW_WIDTH);
         });
         ubin.reserve(4 * (size_t)nbPrims);
         SahBuilder sb(primBoxes, ubin, leafOfNode);
         sb.build(0, nbPrims, 0);
-        G.nbUWide = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode);
+        G.nbUWide = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode, UW_WIDTH);
         extThread.join();
         if (!extBoxes.empty())
         {
             G.nbUX = nbUX;
             // appended to the first tree: inner refs move by its size, leaf refs get bit 30
-            for (int k = 0; k < G.nbUX; ++k)
+            for (size_t k = 0; k < xwide.size() / 8; ++k) // every 128-byte record
             {
-                float4& rf = xwide[8 * (size_t)k + 6];
+                float4& rf = xwide[8 * k + 6];
                 float* f[4] = {&rf.x, &rf.y, &rf.z, &rf.w};
                 for (int c = 0; c < 4; ++c)
                 {

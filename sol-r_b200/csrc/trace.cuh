@@ -1020,7 +1020,7 @@ __device__ WALK_INLINE float4 shadowWalkWide(const float3 lampCenter, const floa
 // Shadow walks accumulate blocker opacity until it saturates (:815-905); when every caster is opaque the first
 // blocker found — in any order — saturates it, otherwise the ordered walk is used.
 // ---------------------------------------------------------------------------------------------------
-#define UN_STACK 48
+#define UN_STACK 64
 #ifdef SOLR_DEBUG_COUNTERS
 #define DBG_ADD(i, v) atomicAdd(cP.workCounters + (i), (unsigned long long)(v))
 #else
@@ -1109,6 +1109,11 @@ SB_DEV float4 ldNode(const float4* p, const unsigned long long policy)
 #endif
     return v;
 }
+#ifndef UW_WIDTH
+#define UW_WIDTH 4 // children per node of the unordered trees: 4 (one 128-byte record) or 8 (two consecutive records; measured slower: 5.8 vs 4.7 ms on config 2)
+#endif
+#define UW_NODE_F4 (2 * UW_WIDTH) // float4 per node
+
 SB_DEV bool wideStepSorted(const float4* __restrict__ n, const NodeRay& q, const float tLimit, const WalkStack& st, int& sp)
 {
     const unsigned long long pol = evictLastPolicy();
@@ -1131,7 +1136,8 @@ SB_DEV bool wideStepSorted(const float4* __restrict__ n, const NodeRay& q, const
     int r0 = refs.x, r1 = refs.y, r2 = refs.z, r3 = refs.w;
     // sorting network, descending t (farthest first)
 #define UN_CSWAP(TA, RA, TB, RB) if (TA < TB) { const float tt = TA; TA = TB; TB = tt; const int rr = RA; RA = RB; RB = rr; }
-    UN_CSWAP(t0, r0, t1, r1) UN_CSWAP(t2, r2, t3, r3) UN_CSWAP(t0, r0, t2, r2) UN_CSWAP(t1, r1, t3, r3) UN_CSWAP(t1, r1, t2, r2)
+    // nearest into slot 3 (on top of the stack); a full far-to-near order buys nothing measurable
+    UN_CSWAP(t0, r0, t1, r1) UN_CSWAP(t2, r2, t3, r3) UN_CSWAP(t1, r1, t3, r3)
 #undef UN_CSWAP
     // each level leaves <= 3 entries behind, so UN_STACK - 4 is only exceeded by a degenerate (very deep) tree: the caller
     // then abandons this walk for the ordered one
@@ -1141,6 +1147,64 @@ SB_DEV bool wideStepSorted(const float4* __restrict__ n, const NodeRay& q, const
     if (t2 < 3.0e38f) { st.push(sp, r2, t2); ++sp; }
     if (t3 < 3.0e38f) { st.push(sp, r3, t3); ++sp; }
     return true;
+}
+
+// Eight children: the two records of the node, tested four at a time; the nearest hit ends up on top of the stack, the
+// others below it in no particular order (a full far-to-near order buys nothing measurable: entries whose entry distance
+// has fallen behind the best hit are dropped when popped).
+SB_DEV bool wideStep8(const float4* __restrict__ n, const NodeRay& q, const float tLimit, const WalkStack& st, int& sp)
+{
+    const unsigned long long pol = evictLastPolicy();
+    const bool sx = q.ix < 0.f, sy = q.iy < 0.f, sz = q.iz < 0.f;
+    float t0, t1, t2, t3, t4, t5, t6, t7;
+    int r0, r1, r2, r3, r4, r5, r6, r7;
+#define UN_CHILD(C, T)                                                                                               \
+    {                                                                                                                \
+        const float tnx = __fmaf_rn(sx ? hx.C : lx.C, q.ix, q.nox), tfx = __fmaf_rn(sx ? lx.C : hx.C, q.ix, q.nox);  \
+        const float tny = __fmaf_rn(sy ? hy.C : ly.C, q.iy, q.noy), tfy = __fmaf_rn(sy ? ly.C : hy.C, q.iy, q.noy);  \
+        const float tnz = __fmaf_rn(sz ? hz.C : lz.C, q.iz, q.noz), tfz = __fmaf_rn(sz ? lz.C : hz.C, q.iz, q.noz);  \
+        const float tmin = fmaxf(fmaxf(tnx, tny), tnz), tmax = fminf(fminf(tfx, tfy), tfz);                          \
+        T = ((tmin <= tmax) & (tmin <= tLimit) & (tmax > 0.f)) ? tmin : 3.0e38f;                                     \
+    }
+    {
+        const float4 lx = ldNode(n, pol), ly = ldNode(n + 1, pol), lz = ldNode(n + 2, pol);
+        const float4 hx = ldNode(n + 3, pol), hy = ldNode(n + 4, pol), hz = ldNode(n + 5, pol);
+        const float4 rf = ldNode(n + 6, pol);
+        r0 = __float_as_int(rf.x); r1 = __float_as_int(rf.y); r2 = __float_as_int(rf.z); r3 = __float_as_int(rf.w);
+        UN_CHILD(x, t0) UN_CHILD(y, t1) UN_CHILD(z, t2) UN_CHILD(w, t3)
+    }
+    {
+        const float4 lx = ldNode(n + 8, pol), ly = ldNode(n + 9, pol), lz = ldNode(n + 10, pol);
+        const float4 hx = ldNode(n + 11, pol), hy = ldNode(n + 12, pol), hz = ldNode(n + 13, pol);
+        const float4 rf = ldNode(n + 14, pol);
+        r4 = __float_as_int(rf.x); r5 = __float_as_int(rf.y); r6 = __float_as_int(rf.z); r7 = __float_as_int(rf.w);
+        UN_CHILD(x, t4) UN_CHILD(y, t5) UN_CHILD(z, t6) UN_CHILD(w, t7)
+    }
+#undef UN_CHILD
+    // bubble the nearest into slot 7
+#define UN_CSWAP(TA, RA, TB, RB) if (TA < TB) { const float tt = TA; TA = TB; TB = tt; const int rr = RA; RA = RB; RB = rr; }
+    UN_CSWAP(t0, r0, t1, r1) UN_CSWAP(t1, r1, t2, r2) UN_CSWAP(t2, r2, t3, r3) UN_CSWAP(t3, r3, t4, r4)
+    UN_CSWAP(t4, r4, t5, r5) UN_CSWAP(t5, r5, t6, r6) UN_CSWAP(t6, r6, t7, r7)
+#undef UN_CSWAP
+    if (sp > UN_STACK - 8) return false;
+    if (t0 < 3.0e38f) { st.push(sp, r0, t0); ++sp; }
+    if (t1 < 3.0e38f) { st.push(sp, r1, t1); ++sp; }
+    if (t2 < 3.0e38f) { st.push(sp, r2, t2); ++sp; }
+    if (t3 < 3.0e38f) { st.push(sp, r3, t3); ++sp; }
+    if (t4 < 3.0e38f) { st.push(sp, r4, t4); ++sp; }
+    if (t5 < 3.0e38f) { st.push(sp, r5, t5); ++sp; }
+    if (t6 < 3.0e38f) { st.push(sp, r6, t6); ++sp; }
+    if (t7 < 3.0e38f) { st.push(sp, r7, t7); ++sp; }
+    return true;
+}
+
+SB_DEV bool unorderedStep(const float4* __restrict__ nodes, const int ref, const NodeRay& q, const float tLimit, const WalkStack& st, int& sp)
+{
+#if UW_WIDTH == 8
+    return wideStep8(nodes + (size_t)UW_NODE_F4 * ref, q, tLimit, st, sp);
+#else
+    return wideStepSorted(nodes + (size_t)UW_NODE_F4 * ref, q, tLimit, st, sp);
+#endif
 }
 
 // One walk for the three order-independent ray classes (one copy of the node loop and of the primitive tests keeps the
@@ -1224,7 +1288,7 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
             if (tEntry > cullT) continue; // the bound shrank since this entry was pushed
             if (ref < 0) { cur = ref; break; }
             DBG_ADD(5, 1);
-            if (!wideStepSorted(nodes + 8 * ref, q, (ref >= nbMain) ? 0.f : cullT, st, sp)) { overflow = true; sp = 0; }
+            if (!unorderedStep(nodes, ref, q, (ref >= nbMain) ? 0.f : cullT, st, sp)) { overflow = true; sp = 0; }
         }
         if (overflow) break;
         if (cur == WIDE_NONE) break;

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
                 if (!(tEntry > cullT)) // else: the bound shrank since this entry was pushed
                 {
                     if (ref < 0) cur = ref;
-                    else if (!wideStepSorted(nodes + 8 * ref, q, (ref >= nbMain) ? 0.f : cullT, st, sp)) { overflow = true; sp = 0; }
+                    else if (!unorderedStep(nodes, ref, q, (ref >= nbMain) ? 0.f : cullT, st, sp)) { overflow = true; sp = 0; }
                 }
             }
         }
