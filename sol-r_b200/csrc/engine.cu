@@ -363,14 +363,15 @@ SB_DEV void pushPaths(const int q, const bool want, const size_t slot)
     if (want) cP.pathQueues[(size_t)q * cP.pathStride + base + __popc(m & ((1u << lane) - 1u))] = (int)slot;
 }
 
+
 // after pass `pass` of a path (all 32 lanes call; `has` = this lane carries one): queue it for the next stage, or end it
 SB_DEV void routePath(const bool has, const PathState& s, const GlobalColors& C, const int pass, const size_t slot, const int index)
 {
     const bool cont = has && s.carryon && s.rayLength < cSI.viewDistance && pass + 1 < cP.maxIteration;
     const bool refl = has && !cont && cSI.graphicsLevel >= B200_GL_REFLECTIONS && s.reflectedRays != -1;
     if (cont || refl) storePath(slot, s, index);
-    pushPaths(pass + 1, cont, slot);
-    pushPaths(cP.maxIteration, refl, slot);
+    pushPaths(passQueue(pass + 1), cont, slot);
+    pushPaths(reflectedQueue(), refl, slot);
     if (has && !cont && !refl)
     {
         const float4 color = pathFinish(s, C, true);
@@ -395,7 +396,13 @@ SB_DEV void flushCounters(const unsigned int raysIn, const unsigned int pxIn)
     }
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_primary()
+#ifndef MIN_CTAS_PRIMARY
+#define MIN_CTAS_PRIMARY MIN_CTAS_PER_SM
+#endif
+#ifndef MIN_CTAS_PASS
+#define MIN_CTAS_PASS MIN_CTAS_PER_SM
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PRIMARY) k_stage_primary()
 {
     const int lane = threadIdx.x & 31;
     Counters cnt;
@@ -436,20 +443,21 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_primary(
 }
 
 // pass >= 1: 32 queue entries per warp at a time
-__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_pass(const int pass)
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const int pass)
 {
     const int lane = threadIdx.x & 31;
     Counters cnt;
     cnt.rays = 0;
-    const unsigned int count = cP.queueCounters[2 * pass];
+    const int q = passQueue(pass);
+    const unsigned int count = cP.queueCounters[2 * q];
     while (true)
     {
         unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(cP.queueCounters + 2 * pass + 1, 32u);
+        if (lane == 0) base = atomicAdd(cP.queueCounters + 2 * q + 1, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) break;
         const bool has = base + lane < count;
-        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)pass * cP.pathStride + base + lane] : 0;
+        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)q * cP.pathStride + base + lane] : 0;
         // the walk first, with only the ray live: the rest of the path is loaded after it, so the call into the walk has
         // next to nothing to save (call-boundary spills were most of the kernel's local-memory traffic)
         Hit hit;
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
     const int lane = threadIdx.x & 31;
     Counters cnt;
     cnt.rays = 0;
-    const int q = cP.maxIteration;
+    const int q = reflectedQueue();
     const unsigned int count = cP.queueCounters[2 * q];
     while (true)
     {
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_gen_primary()
             w[7 * n] = __int_as_float(-2); // currentMaterialId before the first hit (pathInit)
             w[(size_t)(PATH_WORDS - 1) * n] = __int_as_float(index);
         }
-        pushPaths(0, valid, slot);
+        pushPaths(passQueue(0), valid, slot);
     }
     flushCounters(0, pixelsTraced);
 }
@@ -552,13 +560,14 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_shade_pass(con
     const int lane = threadIdx.x & 31;
     Counters cnt;
     cnt.rays = 0;
-    const unsigned int count = cP.queueCounters[2 * pass];
+    const int q = passQueue(pass);
+    const unsigned int count = cP.queueCounters[2 * q];
     const size_t n = cP.pathStride;
     const int warpsTotal = gridDim.x * (CTA_THREADS / 32);
     for (unsigned int base = 32u * (blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5)); base < count; base += 32u * warpsTotal)
     {
         const bool has = base + lane < count;
-        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)pass * n + base + lane] : 0;
+        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)q * n + base + lane] : 0;
         PathState s;
         int index = 0;
         float3 rayO = f3(0.f, 0.f, 0.f);
@@ -1754,7 +1763,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
             CK(cudaMalloc(&G.dPathWords, PATH_WORDS * G.pathStride * sizeof(float)));
             CK(cudaMalloc(&G.dPathColors, (size_t)G.pathIterations * G.pathStride * sizeof(float4)));
             CK(cudaMalloc(&G.dPathContrib, (size_t)G.pathIterations * G.pathStride * sizeof(float)));
-            CK(cudaMalloc(&G.dPathQueues, (size_t)(G.pathIterations + 1) * G.pathStride * sizeof(int)));
+            CK(cudaMalloc(&G.dPathQueues, ((size_t)G.pathIterations + 1) * G.pathStride * sizeof(int)));
             CK(cudaMalloc(&G.dHitWords, HIT_WORDS * G.pathStride * sizeof(float)));
         }
         if (!G.dQueueCounters) CK(cudaMalloc(&G.dQueueCounters, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int)));

@@ -108,6 +108,9 @@ struct Hit
 };
 
 struct Counters { unsigned int rays; };
+// queue ids of the staged renderer (engine.cu): one queue per pass, the reflected-ray stage after them
+SB_DEV int passQueue(const int pass) { return pass; }
+SB_DEV int reflectedQueue() { return cP.maxIteration; }
 
 SB_DEV void makeRay(Ray& r, float3 origin, float3 dir)
 {
@@ -1023,8 +1026,12 @@ __device__ WALK_INLINE float4 shadowWalkWide(const float3 lampCenter, const floa
 #define UN_STACK 64
 #ifdef SOLR_DEBUG_COUNTERS
 #define DBG_ADD(i, v) atomicAdd(cP.workCounters + (i), (unsigned long long)(v))
+#define DBG_MAX(i, v) atomicMax(cP.workCounters + (i), (unsigned long long)(v))
+#define DBG_DECL(x) x
 #else
 #define DBG_ADD(i, v)
+#define DBG_MAX(i, v)
+#define DBG_DECL(x)
 #endif
 #define GATHER_CAP 24
 
@@ -1276,6 +1283,7 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
     const int nbMain = cS.nbUWide;
     if (cS.nbUX > 0) { st.push(1, nbMain, -3.0e38f); sp = 2; }
     bool done = false;
+    DBG_DECL(int dbgVisits = 0;)
     while (!done)
     {
         int cur = WIDE_NONE;
@@ -1287,7 +1295,7 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
             st.pop(sp, ref, tEntry);
             if (tEntry > cullT) continue; // the bound shrank since this entry was pushed
             if (ref < 0) { cur = ref; break; }
-            DBG_ADD(5, 1);
+            DBG_ADD(5, 1); DBG_DECL(++dbgVisits;)
             if (!unorderedStep(nodes, ref, q, (ref >= nbMain) ? 0.f : cullT, st, sp)) { overflow = true; sp = 0; }
         }
         if (overflow) break;
@@ -1368,7 +1376,7 @@ __device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOr
             }
         }
     }
-    DBG_ADD(2, 1); DBG_ADD(3, overflow ? 1 : 0); DBG_ADD(4, n);
+    DBG_ADD(2, 1); DBG_ADD(3, overflow ? 1 : 0); DBG_ADD(4, n); DBG_MAX(6, dbgVisits); DBG_ADD(1, dbgVisits > 200 ? 1 : 0); DBG_ADD(0, dbgVisits > 1000 ? 1 : 0);
     if (overflow)
     {
         out.hit.prim = -2; out.shadow = -1.f; // caller runs the ordered walk

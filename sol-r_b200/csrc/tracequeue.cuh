@@ -30,11 +30,11 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
 #ifdef TRACE_VIA_CALL
     {
         // debug variant: the same queue, walked by calling unorderedWalk() per ray
-        const unsigned int count = cP.queueCounters[2 * pass];
+        const unsigned int count = cP.queueCounters[2 * passQueue(pass)];
         const size_t stride = cP.pathStride;
         for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
         {
-            const size_t slot = (size_t)cP.pathQueues[(size_t)pass * stride + i];
+            const size_t slot = (size_t)cP.pathQueues[(size_t)passQueue(pass) * stride + i];
             const float* pw = cP.pathWords + slot;
             const float3 o = f3(pw[0], pw[stride], pw[2 * stride]);
             const float3 t = f3(pw[3 * stride], pw[4 * stride], pw[5 * stride]);
@@ -47,8 +47,9 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
     }
 #endif
     const int lane = threadIdx.x & 31;
-    const unsigned int count = cP.queueCounters[2 * pass];
-    const int* __restrict__ queue = cP.pathQueues + (size_t)pass * cP.pathStride;
+    const int qid = passQueue(pass);
+    const unsigned int count = cP.queueCounters[2 * qid];
+    const int* __restrict__ queue = cP.pathQueues + (size_t)qid * cP.pathStride;
     const size_t stride = cP.pathStride;
     const float minDistance0 = (pass < 2) ? cSI.viewDistance : cSI.viewDistance / (pass + 1);
     const float eps = cSI.geometryEpsilon;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
             const int nIdle = __popc(idle);
             unsigned int base = 0;
             const int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(cP.queueCounters + 2 * pass + 1, (unsigned int)nIdle);
+            if (lane == leader) base = atomicAdd(cP.queueCounters + 2 * qid + 1, (unsigned int)nIdle);
             base = __shfl_sync(FULL_MASK, base, leader);
             if (!active)
             {
@@ -213,7 +214,14 @@ __global__ void __launch_bounds__(128, TRACE_MIN_CTAS) k_trace_closest(const int
         }
 
         __syncwarp();
-        // ---- a finished ray: replay (UW_GATHER), fallback, result
+        // ---- finished rays: replay (UW_GATHER), fallback, result.  Retired in groups: the code below is per-ray overhead, and
+        //      run for one lane at a time it costs as many issue slots as the ray's whole walk; a finished lane waits until
+        //      TRACE_RETIRE_VOTE lanes are finished, or nothing else in the warp can make progress.
+        {
+            const unsigned int mf = __ballot_sync(FULL_MASK, finished);
+            const unsigned int mp = __ballot_sync(FULL_MASK, active && !finished);
+            if (!(__popc(mf) >= TRACE_RETIRE_VOTE || mp == 0 || exhausted)) finished = false;
+        }
         if (finished)
         {
             if (overflow)

@@ -15,6 +15,7 @@ for cfg, (W, H), gl, nit in (("c2", (1920, 1080), 0, 1), ("c2", (1920, 1080), 4,
     out = (C.c_ulonglong * 8)()
     e.lib.b200_debug_counters(out)
     v = list(out)
+    print("   max visits", v[6], " walks > 200 visits", v[1], " > 1000", v[0] )
     print(cfg, "gl", gl, "nit", nit, "ms %.2f" % e.last_render_ms(), "rays %d | walks %d overflow %d cands %d | wide-node visits %d (%.1f/walk) leaf visits %d (%.1f/walk) prim tests %d (%.1f/walk)" % (
         v[0], v[2], v[3], v[4], v[5], v[5] / max(v[2], 1), v[6], v[6] / max(v[2], 1), v[7], v[7] / max(v[2], 1)), flush=True)
     e.close()
