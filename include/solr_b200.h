@@ -103,6 +103,12 @@ void b200_scene_stats(int* nbBoxesIn, int* nbBoxesDevice, int* nbPrimitives, int
 int b200_debug_relayout_boxes(const b200_BoundingBox* boxes, int nbBoxes, float* outPacked, int capacityBoxes);
 /* Host-only: the unordered SAH BVH built over the same leaves (binary depth-first list, same 8-float format). */
 int b200_debug_build_unordered(const b200_BoundingBox* boxes, int nbBoxes, float* outPacked, int capacityBoxes);
+/* Host-only: the trees h2d_scene builds for the order-independent walks: 128-byte records of four child boxes
+ * (rows lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4], then refs[4] as int bits: >= 0 node, < 0 leaf = ~primitive with bit 30 set
+ * in the point-query tree, INT_MIN empty); nbMain nodes of the tree over primitives, then nbExt nodes of the point-query tree.
+ * Returns the number of float4 (writes them if capacityFloat4 suffices); primLeafOut[nbPrimitives] = reference leaf per primitive. */
+int b200_debug_build_walk_trees(const b200_BoundingBox* boxes, int nbBoxes, const b200_Primitive* primitives, int nbPrimitives,
+                                float* outNodes, int capacityFloat4, int* primLeafOut, int* nbMainOut, int* nbExtOut);
 /* Host-only debug read of the raw work counters (8 values; [0] rays, [1] pixels, others only in instrumented builds). */
 void b200_debug_counters(unsigned long long* out8);
 /* Block until everything queued on the render stream is done. */

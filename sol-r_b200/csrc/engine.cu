@@ -1434,6 +1434,132 @@ void b200_reshape_scene(b200_int2, b200_SceneInfo)
     G.pixelsCap = px;
 }
 
+// The trees of the order-independent walks (h2d_scene step 2c; also behind the host-only b200_debug_build_walk_trees):
+// an unconstrained SAH BVH over PRIMITIVES with tight padded boxes — not over the reference's leaves: level-0 cell keys
+// wrap modulo 2^32 (GPUKernel.cpp:938-941), so in large scenes a reference leaf can hold primitives from distant cells and
+// span a large part of the scene — followed by the point-query tree of grown cylinder/cone boxes.  primLeaf keeps the
+// reference leaf each primitive belongs to, because a hit only counts if that leaf's box passes the reference's slab test.
+static void buildWalkTrees(const std::vector<LeafRec>& leaves, const b200_Primitive* prims, int nbPrims, std::vector<float4>& uwide,
+                           std::vector<int>& primLeaf, int& nbMain, int& nbExt)
+{
+    std::vector<float4> ubin, xbin, xwide;
+    uwide.clear();
+    primLeaf.assign(nbPrims > 0 ? nbPrims : 1, 0);
+    nbMain = 0; nbExt = 0;
+    if (nbPrims <= 0 || leaves.empty()) return;
+    for (size_t l = 0; l < leaves.size(); ++l)
+        for (int k = 0; k < leaves[l].count; ++k)
+            if (leaves[l].start + k >= 0 && leaves[l].start + k < nbPrims) primLeaf[leaves[l].start + k] = (int)l;
+    std::vector<LeafRec> primBoxes(nbPrims), extBoxes;
+    for (int i = 0; i < nbPrims; ++i)
+    {
+        const b200_Primitive& p = prims[i];
+        Aabb b;
+        const float P0[3] = {p.p0.x, p.p0.y, p.p0.z}, P1[3] = {p.p1.x, p.p1.y, p.p1.z}, P2[3] = {p.p2.x, p.p2.y, p.p2.z};
+        const float S[3] = {p.size.x, p.size.y, p.size.z};
+        for (int a = 0; a < 3; ++a)
+        {
+            float lo, hi;
+            switch (p.type)
+            {
+            case B200_PT_TRIANGLE: lo = fminf(fminf(P0[a], P1[a]), P2[a]); hi = fmaxf(fmaxf(P0[a], P1[a]), P2[a]); break;
+            case B200_PT_CYLINDER:
+            case B200_PT_CONE: lo = fminf(P0[a], P1[a]) - fabsf(S[0]); hi = fmaxf(P0[a], P1[a]) + fabsf(S[0]); break;
+            case B200_PT_SPHERE:
+            case B200_PT_ENVIRONMENT: lo = P0[a] - fabsf(S[0]); hi = P0[a] + fabsf(S[0]); break;
+            default: lo = P0[a] - fabsf(S[a]); hi = P0[a] + fabsf(S[a]); break; // ellipsoid, planes
+            }
+            // conservative: hit points are computed in float and the cylinder caps accept +-geometryEpsilon
+#ifndef UW_PAD
+#define UW_PAD 0.02f
+#endif
+            const float pad = UW_PAD + 2e-5f * fmaxf(fabsf(lo), fabsf(hi));
+            b.lo[a] = lo - pad; b.hi[a] = hi + pad;
+        }
+        primBoxes[i].box = b; primBoxes[i].start = i; primBoxes[i].count = 1;
+        // Cylinders and cones also register hits BEHIND the origin: the reference only requires the closest approach of
+        // the two lines to lie ahead (t >= 0, GeometryIntersections.cuh:316,381) and takes the entry point t - s
+        // whatever its sign, measuring its distance with length() (:690-760).  That needs the origin inside the
+        // infinite cylinder, and — because the leaf box must still be ahead (t_max > 0) while the hit point behind the
+        // origin lies in it — inside the (convex) leaf box.  Those primitives get a second box, grown over {points of
+        // the leaf box within one radius of the axis}; the walks look up the boxes that CONTAIN the ray origin in a
+        // separate small tree (a point query) and accept backward hits only from there.
+        if ((p.type == B200_PT_CYLINDER || p.type == B200_PT_CONE) && (p.n1.x != 0.f || p.n1.y != 0.f || p.n1.z != 0.f))
+        {
+            Aabb L = leaves[primLeaf[i]].box;
+            L.grow(b); // cone leaves are built from p0 only (GPUKernel.cpp:808-811)
+            const double N[3] = {p.n1.x, p.n1.y, p.n1.z};
+            const double R = fmax(fabs((double)S[0]), fabs((double)S[1])) * 1.001 + 0.05;
+            double u0 = -1e300, u1 = 1e300;
+            bool empty = false;
+            for (int a = 0; a < 3 && !empty; ++a)
+            {
+                const double slack = R + 1e-5 * fmax(fabs((double)L.lo[a]), fabs((double)L.hi[a]));
+                const double lo = L.lo[a] - slack, hi = L.hi[a] + slack;
+                if (fabs(N[a]) < 1e-9) { empty = P0[a] < lo || P0[a] > hi; continue; }
+                double ua = (lo - P0[a]) / N[a], ub = (hi - P0[a]) / N[a];
+                if (ua > ub) std::swap(ua, ub);
+                u0 = fmax(u0, ua); u1 = fmin(u1, ub);
+            }
+            if (!empty && u0 <= u1 && u0 > -1e299 && u1 < 1e299)
+            {
+                // a thin diagonal region: cover it with short pieces, each in its own box (an origin near a joint lies
+                // in two of them; the walk drops the duplicate)
+                int pieces = (int)ceil((u1 - u0) / (4.0 * R));
+                pieces = pieces < 1 ? 1 : (pieces > 64 ? 64 : pieces);
+                for (int k = 0; k < pieces; ++k)
+                {
+                    const double ua = u0 + (u1 - u0) * k / pieces, ub = u0 + (u1 - u0) * (k + 1) / pieces;
+                    LeafRec x; x.start = i; x.count = 1;
+                    for (int a = 0; a < 3; ++a)
+                    {
+                        const double e0 = P0[a] + ua * N[a], e1 = P0[a] + ub * N[a];
+                        const double slack = R + 1e-5 * fmax(fabs(e0), fabs(e1));
+                        x.box.lo[a] = (float)(fmin(e0, e1) - slack);
+                        x.box.hi[a] = (float)(fmax(e0, e1) + slack);
+                    }
+                    extBoxes.push_back(x);
+                }
+            }
+        }
+    }
+    // the two trees are independent: the point-query tree is built on a second thread
+    std::vector<int> leafOfNode, leafOfNodeX, primOfNode;
+    std::vector<float4> unusedLeafRecs, unusedLeafRecsX;
+    int nbUX = 0;
+    std::thread extThread([&]() {
+        if (extBoxes.empty()) return;
+        SahBuilder sx(extBoxes, xbin, leafOfNodeX);
+        sx.build(0, (int)extBoxes.size(), 0);
+        primOfNode.resize(leafOfNodeX.size());
+        for (size_t k = 0; k < leafOfNodeX.size(); ++k) primOfNode[k] = leafOfNodeX[k] < 0 ? -1 : extBoxes[leafOfNodeX[k]].start;
+        nbUX = buildWide(xbin, xwide, unusedLeafRecsX, &primOfNode, UW_WIDTH);
+    });
+    ubin.reserve(4 * (size_t)nbPrims);
+    SahBuilder sb(primBoxes, ubin, leafOfNode);
+    sb.build(0, nbPrims, 0);
+    nbMain = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode, UW_WIDTH);
+    extThread.join();
+    if (!extBoxes.empty())
+    {
+        nbExt = nbUX;
+        // appended to the first tree: inner refs move by its size, leaf refs get bit 30
+        for (size_t k = 0; k < xwide.size() / 8; ++k) // every 128-byte record
+        {
+            float4& rf = xwide[8 * k + 6];
+            float* f[4] = {&rf.x, &rf.y, &rf.z, &rf.w};
+            for (int c = 0; c < 4; ++c)
+            {
+                int v; memcpy(&v, f[c], 4);
+                if (v == (int)0x80000000) continue;
+                v = v >= 0 ? v + nbMain : ~((~v) | 0x40000000);
+                memcpy(f[c], &v, 4);
+            }
+        }
+        uwide.insert(uwide.end(), xwide.begin(), xwide.end());
+    }
+}
+
 // Scene re-layout.  Input: the flattened AoS arrays of GPUKernel::compactBoxes (GPUKernel.cpp:1085-1281):
 // boxes in depth-first order with "slots to skip on a miss" counts.  Output (DESIGN.md "Data layout"):
 //   boxes   float4[2n']  (min, w0) (max, w1)    leaf: w0 = first primitive, w1 = count
@@ -1460,127 +1586,11 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     if (leafRecs.size() > G.capLeafRecs) { freeDev(G.dLeafRecs); G.capLeafRecs = leafRecs.size() + 1024; CK(cudaMalloc(&G.dLeafRecs, G.capLeafRecs * sizeof(float4))); }
     if (!wide.empty()) CK(cudaMemcpyAsync(G.dWide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
     if (!leafRecs.empty()) CK(cudaMemcpyAsync(G.dLeafRecs, leafRecs.data(), leafRecs.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
-    // 2c. the unordered SAH BVH for the order-independent walks: over PRIMITIVES with tight boxes, not over the reference's
-    //     leaves — level-0 cell keys wrap modulo 2^32 (GPUKernel.cpp:938-941), so in large scenes a reference leaf can hold
-    //     primitives from distant cells and span a large part of the scene.  The reference leaf each primitive belongs to is
-    //     kept (primLeaf) because a hit only counts if that leaf's box passes the reference's slab test.
-    std::vector<float4> ubin, uwide, xbin, xwide;
+    // 2c. the trees of the order-independent walks
+    std::vector<float4> uwide;
     std::vector<int> primLeaf(nbPrims > 0 ? nbPrims : 1, 0);
     G.nbUWide = 0; G.nbUX = 0;
-    if (G.boxLayoutUsed == 2 && G.nbWide > 0 && g_useUnordered && nbPrims > 0)
-    {
-        for (size_t l = 0; l < leaves.size(); ++l)
-            for (int k = 0; k < leaves[l].count; ++k)
-                if (leaves[l].start + k >= 0 && leaves[l].start + k < nbPrims) primLeaf[leaves[l].start + k] = (int)l;
-        std::vector<LeafRec> primBoxes(nbPrims), extBoxes;
-        for (int i = 0; i < nbPrims; ++i)
-        {
-            const b200_Primitive& p = prims[i];
-            Aabb b;
-            const float P0[3] = {p.p0.x, p.p0.y, p.p0.z}, P1[3] = {p.p1.x, p.p1.y, p.p1.z}, P2[3] = {p.p2.x, p.p2.y, p.p2.z};
-            const float S[3] = {p.size.x, p.size.y, p.size.z};
-            for (int a = 0; a < 3; ++a)
-            {
-                float lo, hi;
-                switch (p.type)
-                {
-                case B200_PT_TRIANGLE: lo = fminf(fminf(P0[a], P1[a]), P2[a]); hi = fmaxf(fmaxf(P0[a], P1[a]), P2[a]); break;
-                case B200_PT_CYLINDER:
-                case B200_PT_CONE: lo = fminf(P0[a], P1[a]) - fabsf(S[0]); hi = fmaxf(P0[a], P1[a]) + fabsf(S[0]); break;
-                case B200_PT_SPHERE:
-                case B200_PT_ENVIRONMENT: lo = P0[a] - fabsf(S[0]); hi = P0[a] + fabsf(S[0]); break;
-                default: lo = P0[a] - fabsf(S[a]); hi = P0[a] + fabsf(S[a]); break; // ellipsoid, planes
-                }
-                // conservative: hit points are computed in float and the cylinder caps accept +-geometryEpsilon
-#ifndef UW_PAD
-#define UW_PAD 0.02f
-#endif
-                const float pad = UW_PAD + 2e-5f * fmaxf(fabsf(lo), fabsf(hi));
-                b.lo[a] = lo - pad; b.hi[a] = hi + pad;
-            }
-            primBoxes[i].box = b; primBoxes[i].start = i; primBoxes[i].count = 1;
-            // Cylinders and cones also register hits BEHIND the origin: the reference only requires the closest approach of
-            // the two lines to lie ahead (t >= 0, GeometryIntersections.cuh:316,381) and takes the entry point t - s
-            // whatever its sign, measuring its distance with length() (:690-760).  That needs the origin inside the
-            // infinite cylinder, and — because the leaf box must still be ahead (t_max > 0) while the hit point behind the
-            // origin lies in it — inside the (convex) leaf box.  Those primitives get a second box, grown over {points of
-            // the leaf box within one radius of the axis}; the walks look up the boxes that CONTAIN the ray origin in a
-            // separate small tree (a point query) and accept backward hits only from there.
-            if ((p.type == B200_PT_CYLINDER || p.type == B200_PT_CONE) && (p.n1.x != 0.f || p.n1.y != 0.f || p.n1.z != 0.f))
-            {
-                Aabb L = leaves[primLeaf[i]].box;
-                L.grow(b); // cone leaves are built from p0 only (GPUKernel.cpp:808-811)
-                const double N[3] = {p.n1.x, p.n1.y, p.n1.z};
-                const double R = fmax(fabs((double)S[0]), fabs((double)S[1])) * 1.001 + 0.05;
-                double u0 = -1e300, u1 = 1e300;
-                bool empty = false;
-                for (int a = 0; a < 3 && !empty; ++a)
-                {
-                    const double slack = R + 1e-5 * fmax(fabs((double)L.lo[a]), fabs((double)L.hi[a]));
-                    const double lo = L.lo[a] - slack, hi = L.hi[a] + slack;
-                    if (fabs(N[a]) < 1e-9) { empty = P0[a] < lo || P0[a] > hi; continue; }
-                    double ua = (lo - P0[a]) / N[a], ub = (hi - P0[a]) / N[a];
-                    if (ua > ub) std::swap(ua, ub);
-                    u0 = fmax(u0, ua); u1 = fmin(u1, ub);
-                }
-                if (!empty && u0 <= u1 && u0 > -1e299 && u1 < 1e299)
-                {
-                    // a thin diagonal region: cover it with short pieces, each in its own box (an origin near a joint lies
-                    // in two of them; the walk drops the duplicate)
-                    int pieces = (int)ceil((u1 - u0) / (4.0 * R));
-                    pieces = pieces < 1 ? 1 : (pieces > 64 ? 64 : pieces);
-                    for (int k = 0; k < pieces; ++k)
-                    {
-                        const double ua = u0 + (u1 - u0) * k / pieces, ub = u0 + (u1 - u0) * (k + 1) / pieces;
-                        LeafRec x; x.start = i; x.count = 1;
-                        for (int a = 0; a < 3; ++a)
-                        {
-                            const double e0 = P0[a] + ua * N[a], e1 = P0[a] + ub * N[a];
-                            const double slack = R + 1e-5 * fmax(fabs(e0), fabs(e1));
-                            x.box.lo[a] = (float)(fmin(e0, e1) - slack);
-                            x.box.hi[a] = (float)(fmax(e0, e1) + slack);
-                        }
-                        extBoxes.push_back(x);
-                    }
-                }
-            }
-        }
-        // the two trees are independent: the point-query tree is built on a second thread
-        std::vector<int> leafOfNode, leafOfNodeX, primOfNode;
-        std::vector<float4> unusedLeafRecs, unusedLeafRecsX;
-        int nbUX = 0;
-        std::thread extThread([&]() {
-            if (extBoxes.empty()) return;
-            SahBuilder sx(extBoxes, xbin, leafOfNodeX);
-            sx.build(0, (int)extBoxes.size(), 0);
-            primOfNode.resize(leafOfNodeX.size());
-            for (size_t k = 0; k < leafOfNodeX.size(); ++k) primOfNode[k] = leafOfNodeX[k] < 0 ? -1 : extBoxes[leafOfNodeX[k]].start;
-            nbUX = buildWide(xbin, xwide, unusedLeafRecsX, &primOfNode, UW_WIDTH);
-        });
-        ubin.reserve(4 * (size_t)nbPrims);
-        SahBuilder sb(primBoxes, ubin, leafOfNode);
-        sb.build(0, nbPrims, 0);
-        G.nbUWide = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode, UW_WIDTH);
-        extThread.join();
-        if (!extBoxes.empty())
-        {
-            G.nbUX = nbUX;
-            // appended to the first tree: inner refs move by its size, leaf refs get bit 30
-            for (size_t k = 0; k < xwide.size() / 8; ++k) // every 128-byte record
-            {
-                float4& rf = xwide[8 * k + 6];
-                float* f[4] = {&rf.x, &rf.y, &rf.z, &rf.w};
-                for (int c = 0; c < 4; ++c)
-                {
-                    int v; memcpy(&v, f[c], 4);
-                    if (v == (int)0x80000000) continue;
-                    v = v >= 0 ? v + G.nbUWide : ~((~v) | 0x40000000);
-                    memcpy(f[c], &v, 4);
-                }
-            }
-            uwide.insert(uwide.end(), xwide.begin(), xwide.end());
-        }
-    }
+    if (G.boxLayoutUsed == 2 && G.nbWide > 0 && g_useUnordered && nbPrims > 0) buildWalkTrees(leaves, prims, nbPrims, uwide, primLeaf, G.nbUWide, G.nbUX);
     if ((size_t)nbPrims > G.capPrimLeaf) { freeDev(G.dPrimLeaf); G.capPrimLeaf = (size_t)nbPrims + 1024; CK(cudaMalloc(&G.dPrimLeaf, G.capPrimLeaf * sizeof(int))); }
     if (nbPrims > 0) CK(cudaMemcpyAsync(G.dPrimLeaf, primLeaf.data(), (size_t)nbPrims * sizeof(int), cudaMemcpyHostToDevice, G.stream));
     if (uwide.size() > G.capUWide) { freeDev(G.dUWide); G.capUWide = uwide.size() + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
@@ -1932,6 +1942,23 @@ int b200_debug_build_unordered(const b200_BoundingBox* boxes, int nbBoxes, float
     const int n = (int)(ubin.size() / 2);
     if (outPacked && n <= capacityBoxes) memcpy(outPacked, ubin.data(), ubin.size() * sizeof(float4));
     return n;
+}
+
+int b200_debug_build_walk_trees(const b200_BoundingBox* boxes, int nbBoxes, const b200_Primitive* prims, int nbPrims, float* outNodes,
+                                int capacityFloat4, int* primLeafOut, int* nbMainOut, int* nbExtOut)
+{
+    std::vector<float4> packed, uwide;
+    std::vector<LeafRec> leaves;
+    std::vector<int> primLeaf;
+    int used = 0, nbMain = 0, nbExt = 0;
+    relayoutBoxes(boxes, nbBoxes, packed, &used, &leaves);
+    if (used != 2) return 0;
+    buildWalkTrees(leaves, prims, nbPrims, uwide, primLeaf, nbMain, nbExt);
+    if (outNodes && (int)uwide.size() <= capacityFloat4) memcpy(outNodes, uwide.data(), uwide.size() * sizeof(float4));
+    if (primLeafOut) memcpy(primLeafOut, primLeaf.data(), (size_t)(nbPrims > 0 ? nbPrims : 0) * sizeof(int));
+    if (nbMainOut) *nbMainOut = nbMain;
+    if (nbExtOut) *nbExtOut = nbExt;
+    return (int)uwide.size();
 }
 
 void b200_synchronize(void)

@@ -74,9 +74,28 @@ ABI_SYMBOLS = [
     "b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
     "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
     "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition",
-    "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
+    "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_build_walk_trees", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
     "b200_synchronize",
 ]
+
+
+def build_walk_trees(arrays):
+    """Host-only: (nodes float32[n, 8, 4], prim_leaf int32[m], nb_main, nb_ext) as h2d_scene builds them for the
+    order-independent walks."""
+    lib = load()
+    lib.b200_debug_build_walk_trees.restype = C.c_int
+    lib.b200_debug_build_walk_trees.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    boxes = np.ascontiguousarray(arrays["boxes"]); prims = np.ascontiguousarray(arrays["primitives"])
+    m = int(arrays["nbPrimitives"])
+    prim_leaf = np.zeros(max(m, 1), np.int32)
+    nb_main, nb_ext = C.c_int(0), C.c_int(0)
+    n4 = lib.b200_debug_build_walk_trees(_ptr(boxes), int(arrays["nbBoxes"]), _ptr(prims), m, None, 0, _ptr(prim_leaf),
+                                         C.byref(nb_main), C.byref(nb_ext))
+    nodes = np.zeros((max(n4, 1), 4), np.float32)
+    lib.b200_debug_build_walk_trees(_ptr(boxes), int(arrays["nbBoxes"]), _ptr(prims), m, _ptr(nodes), n4, _ptr(prim_leaf),
+                                    C.byref(nb_main), C.byref(nb_ext))
+    return nodes[:n4].reshape(-1, 8, 4), prim_leaf[:m], nb_main.value, nb_ext.value
 
 
 def _ptr(a):
