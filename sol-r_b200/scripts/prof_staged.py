@@ -9,7 +9,8 @@ mode, gl, nit, frames = (int(v) for v in sys.argv[1:5])
 sc = scenes.config2(); W, H = 1920, 1080
 si = wire.default_scene_info(W, H, graphics_level=gl, nb_ray_iterations=nit)
 h = host.SceneHost(si); sc.replay(h); a = h.arrays(); h.close()
-e = engine.Engine(si); e.set_option(6, mode)
+world = int(os.environ.get('SOLR_WORLD', '1'))
+e = engine.Engine(si, rank=0, world=world) if world > 1 else engine.Engine(si); e.set_option(6, mode)
 if os.environ.get('SOLR_OPT7'): e.set_option(7, int(os.environ['SOLR_OPT7']))
 e.upload(a, randoms=np.zeros(W * H, np.float32))
 for it in range(frames):
