@@ -323,7 +323,8 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary_latest.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                j = json.load(f)
+                traffic = j.get("dram_bytes_per_frame", j.get("dram_bytes_per_launch"))   # summed over the frame's launches
         except Exception:
             pass
         flops_frame = ALGORITHMIC_GFLOP_PER_FRAME * 1e9
