@@ -1238,7 +1238,10 @@ __device__ WALK_INLINE Hit closestHitWide(const float3 origin, const float3 targ
 
 struct WalkOut { Hit hit; float shadow; };
 
-__device__ __noinline__ WalkOut unorderedWalk(const int mode, const float3 rayOrigin, const float3 rayDir, const int iteration,
+#ifndef UW_INLINE
+#define UW_INLINE __noinline__
+#endif
+__device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigin, const float3 rayDir, const int iteration,
                                               const int currentMaterialId, const int lightId, const int objectId)
 {
     WalkOut out;
