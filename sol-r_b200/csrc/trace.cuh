@@ -1135,8 +1135,9 @@ SB_DEV bool wideStepSorted(const float4* __restrict__ n, const NodeRay& q, const
         const float tnx = __fmaf_rn(sx ? hx.C : lx.C, q.ix, q.nox), tfx = __fmaf_rn(sx ? lx.C : hx.C, q.ix, q.nox);  \
         const float tny = __fmaf_rn(sy ? hy.C : ly.C, q.iy, q.noy), tfy = __fmaf_rn(sy ? ly.C : hy.C, q.iy, q.noy);  \
         const float tnz = __fmaf_rn(sz ? hz.C : lz.C, q.iz, q.noz), tfz = __fmaf_rn(sz ? lz.C : hz.C, q.iz, q.noz);  \
-        const float tmin = fmaxf(fmaxf(tnx, tny), tnz), tmax = fminf(fminf(tfx, tfy), tfz);                          \
-        T = ((tmin <= tmax) & (tmin <= tLimit) & (tmax > 0.f)) ? tmin : 3.0e38f;                                     \
+        /* entry clamped to the origin, exit to the bound: one comparison says whether the box is crossed within [0, tLimit] */ \
+        const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.f), tmax = fminf(fminf(fminf(tfx, tfy), tfz), tLimit);           \
+        T = (tmin <= tmax) ? tmin : 3.0e38f;                                                                         \
     }
     UN_CHILD(x, t0) UN_CHILD(y, t1) UN_CHILD(z, t2) UN_CHILD(w, t3)
 #undef UN_CHILD
