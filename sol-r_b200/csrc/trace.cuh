@@ -1033,7 +1033,7 @@ __device__ WALK_INLINE float4 shadowWalkWide(const float3 lampCenter, const floa
 #define DBG_MAX(i, v)
 #define DBG_DECL(x)
 #endif
-#define GATHER_CAP 24
+#define GATHER_CAP 48 // candidates kept by a bounce-ray walk; a fuller list sends the ray to the ordered walk (24: 573 rays per frame of config 2, 0.2 ms)
 
 // slab test that also returns t_min (same arithmetic as slab())
 SB_DEV bool slabT(const float4 lo, const float4 hi, const Ray& r, const float t1, float& tminOut)
