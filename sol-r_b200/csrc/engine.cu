@@ -1434,6 +1434,50 @@ void b200_reshape_scene(b200_int2, b200_SceneInfo)
     G.pixelsCap = px;
 }
 
+// Renumbers the nodes of a wide tree breadth-first (node 0 stays the root), so that the top levels — visited by every
+// ray — are the first records of the array (the walks keep them in shared memory) and siblings are neighbours.
+static void renumberBreadthFirst(std::vector<float4>& wide, int nbNodes)
+{
+    const int recs = UW_WIDTH / 4;
+    const size_t f4 = 8 * (size_t)recs;
+    if (nbNodes <= 1) return;
+    std::vector<int> order, newIndex(nbNodes, -1);
+    order.reserve(nbNodes);
+    order.push_back(0); newIndex[0] = 0;
+    for (size_t head = 0; head < order.size(); ++head)
+    {
+        const int k = order[head];
+        for (int q = 0; q < recs; ++q)
+        {
+            const float4 rf = wide[f4 * k + 8 * q + 6];
+            const float f[4] = {rf.x, rf.y, rf.z, rf.w};
+            for (int c = 0; c < 4; ++c)
+            {
+                int v; memcpy(&v, &f[c], 4);
+                if (v >= 0 && v < nbNodes && newIndex[v] < 0) { newIndex[v] = (int)order.size(); order.push_back(v); }
+            }
+        }
+    }
+    if ((int)order.size() != nbNodes) return; // not a tree over all nodes: leave as is
+    std::vector<float4> out(wide.size());
+    for (int n = 0; n < nbNodes; ++n)
+    {
+        const int src = order[n];
+        for (size_t j = 0; j < f4; ++j) out[f4 * n + j] = wide[f4 * src + j];
+        for (int q = 0; q < recs; ++q)
+        {
+            float4& rf = out[f4 * n + 8 * q + 6];
+            float* f[4] = {&rf.x, &rf.y, &rf.z, &rf.w};
+            for (int c = 0; c < 4; ++c)
+            {
+                int v; memcpy(&v, f[c], 4);
+                if (v >= 0) { v = newIndex[v]; memcpy(f[c], &v, 4); }
+            }
+        }
+    }
+    wide.swap(out);
+}
+
 // The trees of the order-independent walks (h2d_scene step 2c; also behind the host-only b200_debug_build_walk_trees):
 // an unconstrained SAH BVH over PRIMITIVES with tight padded boxes — not over the reference's leaves: level-0 cell keys
 // wrap modulo 2^32 (GPUKernel.cpp:938-941), so in large scenes a reference leaf can hold primitives from distant cells and
@@ -1539,6 +1583,7 @@ static void buildWalkTrees(const std::vector<LeafRec>& leaves, const b200_Primit
     SahBuilder sb(primBoxes, ubin, leafOfNode);
     sb.build(0, nbPrims, 0);
     nbMain = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode, UW_WIDTH);
+    renumberBreadthFirst(uwide, nbMain);
     extThread.join();
     if (!extBoxes.empty())
     {
