@@ -37,7 +37,10 @@ SB_DEV void operator/=(float4& a, float b) { a.x /= b; a.y /= b; a.z /= b; a.w /
 // its frames), so the dot and cross products are spelled out with it.
 SB_DEV float dot(float3 a, float3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y))); }
 SB_DEV float length(float3 v) { return sqrtf(dot(v, v)); }
-SB_DEV float3 normalize(float3 v) { float invLen = rsqrtf(dot(v, v)); return v * invLen; }
+// dot(v, v) inside normalize: the reference's build rounds x*x on its own and fuses y, z (its SASS, e.g. the direction of every
+// ray in sphereIntersection) — the other way round from the dot products above
+SB_DEV float dotSelfForNormalize(float3 v) { return __fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, __fmul_rn(v.x, v.x))); }
+SB_DEV float3 normalize(float3 v) { float invLen = rsqrtf(dotSelfForNormalize(v)); return v * invLen; }
 SB_DEV float3 cross(float3 b, float3 c)
 {
     return f3(__fmaf_rn(b.y, c.z, -__fmul_rn(b.z, c.y)), __fmaf_rn(b.z, c.x, -__fmul_rn(b.x, c.z)), __fmaf_rn(b.x, c.y, -__fmul_rn(b.y, c.x)));

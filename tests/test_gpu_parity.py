@@ -127,12 +127,13 @@ def test_engine_vs_reference_cuda_engine(cfg):
         out[(gl, "ref_self")] = (frac_id_mismatch(o.ids, gids), frac_rgb_bad(o.bitmap, gbm))
     print(cfg, out)
     # The engine spells out the reference build's FMA contraction where rays are made and tested (vec.cuh "pinned
-    # rounding"), so even the chaotic full level follows the reference CUDA engine: measured 0 id mismatches and
-    # 0.045 % / 0.060 % of the pixels off by more than 2/255 (the reference's own IEEE build: >10 %).
+    # rounding"), so even the chaotic full level follows the reference CUDA engine: measured 0 id mismatches, bit-identical
+    # first-hit depth, and NO pixel off by more than 2/255 (3-17 pixels differ at all, by 1-2 levels; the reference's own IEEE
+    # build differs from its CUDA build on >10 % of the pixels at this level).
     for gl in (wire.GL_PHONG_BLINN, wire.GL_FULL):
         assert out[gl][0] <= 1e-5, "ids vs reference CUDA engine"
     assert out[wire.GL_PHONG_BLINN][1] <= 1e-4, "rgb vs reference CUDA engine (no secondary rays)"
-    assert out[wire.GL_FULL][1] <= 1e-3, "rgb within 2/255 on >= 99.9 % of the pixels, shadows + reflections"
+    assert out[wire.GL_FULL][1] <= 1e-4, "rgb within 2/255 on >= 99.99 % of the pixels, shadows + reflections"
     assert out[wire.GL_FULL][1] <= out[(wire.GL_FULL, "ref_self")][1]
 
 
