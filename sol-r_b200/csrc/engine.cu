@@ -192,8 +192,8 @@ SB_DEV void renderPixel(const Rotation& rot, const bool inFrame, const int xIn, 
         const float xf = leftEye ? (float)(x - (W / 2) + halfWidth / 2) : (float)(x - (W / 2) - halfWidth / 2);
         t.x = leftEye ? cP.target.x - stepx * xf + cSI.eyeSeparation : cP.target.x - stepx * xf - cSI.eyeSeparation;
         t.y = cP.target.y + stepy * (float)(y - (H / 2));
-        vectorRotation(o, rotationCenter, rot);
-        vectorRotation(t, rotationCenter, rot);
+        vectorRotation(o, rotationCenter, rot, true);
+        vectorRotation(t, rotationCenter, rot, true);
     }
     else if (camera == B200_CT_PANORAMIC)
     {

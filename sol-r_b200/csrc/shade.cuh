@@ -464,18 +464,20 @@ struct Rotation { float cx, cy, cz, sx, sy, sz; };
 // bit decides grazing hits differently (profiles/r01_history.md, "pinned rounding").
 SB_DEV float mulAdd2(const float a, const float b, const float c, const float d) { return __fmaf_rn(a, b, __fmul_rn(c, d)); }  // a*b + c*d
 SB_DEV float mulSub2(const float a, const float b, const float c, const float d) { return __fmaf_rn(a, b, -__fmul_rn(c, d)); } // a*b - c*d
-SB_DEV void vectorRotation(float3& v, const float3 c, const Rotation& R)
+// `stereo`: k_3DVisionRenderer's copy of the function fuses the other product in the first sum
+SB_DEV void vectorRotation(float3& v, const float3 c, const Rotation& R, const bool stereo = false)
 {
     float3 vec = f3(__fadd_rn(v.x, -c.x), __fadd_rn(v.y, -c.y), __fadd_rn(v.z, -c.z));
     float3 res = vec;
+    // in the reference's build the differences fuse their first product, the sums their second (k_standardRenderer SASS)
     res.y = mulSub2(vec.y, R.cx, vec.z, R.sx);
-    res.z = mulAdd2(vec.y, R.sx, vec.z, R.cx);
+    res.z = stereo ? mulAdd2(vec.y, R.sx, vec.z, R.cx) : mulAdd2(vec.z, R.cx, vec.y, R.sx);
     vec = res;
     res.z = mulSub2(vec.z, R.cy, vec.x, R.sy);
-    res.x = mulAdd2(vec.z, R.sy, vec.x, R.cy);
+    res.x = mulAdd2(vec.x, R.cy, vec.z, R.sy);
     vec = res;
     res.x = mulSub2(vec.x, R.cz, vec.y, R.sz);
-    res.y = mulAdd2(vec.x, R.sz, vec.y, R.cz);
+    res.y = mulAdd2(vec.y, R.cz, vec.x, R.sz);
     v.x = __fadd_rn(res.x, c.x); v.y = __fadd_rn(res.y, c.y); v.z = __fadd_rn(res.z, c.z);
 }
 

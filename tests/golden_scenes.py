@@ -112,6 +112,8 @@ CASES = {
     "spheres_ortho": dict(scene=spheres_scene, si=dict(nit=2, cameraType=wire.CT_ORTHOGRAPHIC), frames=[0]),
     "spheres_aa": dict(scene=spheres_scene, si=dict(nit=2, cameraType=wire.CT_ANTIALIASED), frames=[0]),
     "spheres_anaglyph": dict(scene=spheres_scene, si=dict(nit=2, cameraType=wire.CT_ANAGLYPH, maxPathTracingIterations=12), frames=[0, 10, 11], randoms=6),
+    "spheres_anaglyph_rotated": dict(scene=spheres_scene, si=dict(nit=2, cameraType=wire.CT_ANAGLYPH), frames=[0], angles=(0.2, -0.3, 0.1, 6400.0)),
+    "spheres_aa_rotated": dict(scene=spheres_scene, si=dict(nit=2, cameraType=wire.CT_ANTIALIASED), frames=[0], angles=(-0.15, 0.25, -0.1, 6400.0)),
     "spheres_fog_gradient": dict(scene=spheres_scene, si=dict(nit=2, atmosphericEffect=1, gradientBackground=1, viewDistance=21000.0,
                                                               backgroundColor=(0.3, 0.5, 0.9, 0.4)), frames=[0]),
     "spheres_boxes": dict(scene=spheres_scene, si=dict(nit=2, renderBoxes=1), frames=[0]),
