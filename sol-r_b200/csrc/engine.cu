@@ -771,6 +771,7 @@ struct Engine
     // staged rendering
     float* dPathWords = nullptr; float4* dPathColors = nullptr; float* dPathContrib = nullptr; int* dPathQueues = nullptr;
     unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
+    size_t pathFailedBytes = 0; // smallest path-state size that did not fit (not tried again)
     float* dHitWords = nullptr;
     int ctasPerSMStage[6] = {0, 0, 0, 0, 0, 0}; // k_stage_primary, k_stage_pass, k_stage_reflected, k_gen_primary, k_trace_closest, k_shade_pass
     float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
@@ -1804,23 +1805,39 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     int maxIteration = (si.graphicsLevel < B200_GL_REFLECTIONS) ? 1 : si.nbRayIterations + si.pathTracingIteration;
     maxIteration = maxIteration > B200_NB_MAX_ITERATIONS ? B200_NB_MAX_ITERATIONS : maxIteration;
     const bool giRays = (si.advancedIllumination == B200_AI_BASIC || si.advancedIllumination == B200_AI_FULL);
-    const bool staged = g_useStaged && (maxIteration > 1 || g_useStaged >= 2) && !giRays && si.renderBoxes == 0 &&
+    bool staged = g_useStaged && (maxIteration > 1 || g_useStaged >= 2) && !giRays && si.renderBoxes == 0 &&
                         (si.cameraType == B200_CT_PERSPECTIVE || si.cameraType == B200_CT_ORTHOGRAPHIC);
     if (staged)
     {
         const size_t stride = (((size_t)P.nbLocalTiles * 32) + 63) & ~(size_t)63;
-        if (stride > G.pathStride || maxIteration > G.pathIterations)
+        const size_t wantBytes = stride * (size_t)(maxIteration > G.pathIterations ? maxIteration : G.pathIterations);
+        if (G.pathFailedBytes && wantBytes >= G.pathFailedBytes) staged = false;
+        else if (stride > G.pathStride || maxIteration > G.pathIterations)
         {
             CK(cudaStreamSynchronize(G.stream));
             freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dHitWords);
             G.pathStride = stride > G.pathStride ? stride : G.pathStride;
             G.pathIterations = maxIteration > G.pathIterations ? maxIteration : G.pathIterations;
-            CK(cudaMalloc(&G.dPathWords, PATH_WORDS * G.pathStride * sizeof(float)));
-            CK(cudaMalloc(&G.dPathColors, (size_t)G.pathIterations * G.pathStride * sizeof(float4)));
-            CK(cudaMalloc(&G.dPathContrib, (size_t)G.pathIterations * G.pathStride * sizeof(float)));
-            CK(cudaMalloc(&G.dPathQueues, ((size_t)G.pathIterations + 1) * G.pathStride * sizeof(int)));
-            CK(cudaMalloc(&G.dHitWords, HIT_WORDS * G.pathStride * sizeof(float)));
+            // path state is ~0.3 KB per pixel and pass: if the device cannot hold it (very large frames next to a large scene),
+            // this frame size is rendered by the single kernel, which needs none
+            const bool ok = cudaMalloc(&G.dPathWords, PATH_WORDS * G.pathStride * sizeof(float)) == cudaSuccess &&
+                            cudaMalloc(&G.dPathColors, (size_t)G.pathIterations * G.pathStride * sizeof(float4)) == cudaSuccess &&
+                            cudaMalloc(&G.dPathContrib, (size_t)G.pathIterations * G.pathStride * sizeof(float)) == cudaSuccess &&
+                            cudaMalloc(&G.dPathQueues, ((size_t)G.pathIterations + 1) * G.pathStride * sizeof(int)) == cudaSuccess &&
+                            cudaMalloc(&G.dHitWords, HIT_WORDS * G.pathStride * sizeof(float)) == cudaSuccess;
+            if (!ok)
+            {
+                cudaGetLastError();
+                freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dHitWords);
+                G.pathStride = 0; G.pathIterations = 0;
+                G.pathFailedBytes = wantBytes;
+                staged = false;
+                fprintf(stderr, "solr_b200: no device memory for the staged renderer's path state at this frame size; using the single kernel\n");
+            }
         }
+    }
+    if (staged)
+    {
         if (!G.dQueueCounters) CK(cudaMalloc(&G.dQueueCounters, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int)));
         P.pathWords = G.dPathWords; P.pathColors = G.dPathColors; P.pathContributions = G.dPathContrib; P.pathQueues = G.dPathQueues;
         P.queueCounters = G.dQueueCounters; P.pathStride = G.pathStride; P.maxIteration = maxIteration; P.hitWords = G.dHitWords;
