@@ -325,3 +325,40 @@ def test_every_case_against_the_reference_cuda_engine(name):
     slack = 4e-4 if name == "mesh_noextended" else 1e-4
     assert (ids[..., 0] != gids[..., 0]).sum() <= max(2, slack * n)
     assert (np.abs(bm.astype(int) - gbm.astype(int)).max(-1) > 2).sum() <= max(2, slack * n)
+
+
+@pytest.mark.parametrize("cfg", ["config1", "molecule"])
+def test_drivers_produce_identical_frames(cfg):
+    """Option key 6: the single persistent kernel (0), the staged kernels (1, default) and the staged kernels with the
+    closest-hit walks in the trace-queue kernel (2) run the same device functions on the same rays: ids, the float
+    accumulation buffer and the RGB8 frame must be bit-identical, also across progressive frames."""
+    W, H = 640, 360
+    sc = scenes.config1(1000) if cfg == "config1" else scenes.molecule(cells=3)
+    si = wire.default_scene_info(W, H, graphics_level=wire.GL_FULL, nb_ray_iterations=3)
+    si.maxPathTracingIterations = 13
+    h = host.SceneHost(si)
+    sc.replay(h)
+    a = h.arrays()
+    h.close()
+    rnd = gs.randoms(41)
+    out = []
+    for mode in (0, 1, 2):
+        e = engine.Engine(si)
+        try:
+            e.set_option(6, mode)
+            e.upload(a, randoms=rnd)
+            for it in (0, 1, 10, 11):
+                si.pathTracingIteration = it
+                e.render(si, sc.eye, sc.target, sc.angles)
+            bm, ids = e.readback(si)
+            post = e.read_post_buffer(si)
+            rays, _ = e.counters(reset=True)
+            out.append((bm.copy(), ids.copy(), post.copy(), rays))
+        finally:
+            e.set_option(6, 1)
+            e.close()
+    for bm, ids, post, rays in out[1:]:
+        assert np.array_equal(ids, out[0][1])
+        assert np.array_equal(post.view(np.uint32), out[0][2].view(np.uint32))
+        assert np.array_equal(bm, out[0][0])
+        assert rays == out[0][3]
