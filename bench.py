@@ -93,6 +93,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def host_cores():
+    """Host threads for the CPU legs: every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which would silently run the reference arm on one core at N > 1, so the OpenMP runtime is told explicitly."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1", mode=ctypes.RTLD_GLOBAL).omp_set_num_threads(n)
+    except Exception:
+        pass
+    return n
+
+
 def scene_and_info(width, height):
     from solr_b200 import scenes, wire
     sc = scenes.config2()
@@ -111,7 +127,7 @@ def cpu_reference_run(steps, warmup, want_counts=True):
     a = h.arrays()
     h.close()
     rnd = np.zeros(wire.REF_MAX_BITMAP_SIZE, np.float32)
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     o = oracle.Oracle(a, SAMPLE_W, SAMPLE_H, randoms=rnd)
     t0 = time.perf_counter()
     o.render(si, sc.eye, sc.target, sc.angles, threads=cores)
