@@ -11,8 +11,10 @@ A *ray* is one box-list walk (closest-hit or shadow), SURVEY.md §8(d).
 
   value   whole-job Mrays/s with scene and frame state resident in HBM: K x b200_render, CUDA events on the
           render stream around each frame, L2 flushed (256 MiB memset) between frames, max over ranks.
-          N>1: ONE frame is split across the N GPUs as interleaved 8x4-pixel tiles (strong scaling) and the
-          per-rank partial bitmaps are summed onto rank 0 with NCCL inside the timed region.
+          N>1: ONE frame is split across the N GPUs as interleaved 8x4-pixel tiles (strong scaling); the exchange is fused
+          into the ray kernels — every rank stores its finished pixels straight into rank 0's device bitmap through NVLink
+          peer memory (partition.PeerFrame) — and a one-element NCCL all-reduce inside the timed region orders the frame.
+          After the timed runs rank 0 renders the whole frame alone and checks the merged frame against it, byte for byte.
   e2e     the same metric through the host-side drop-in (SceneHost.render_begin + render_end = the calls
           CudaKernel makes): per-frame parameter upload, kernel, device->host copy of RGB8 + id buffer into
           caller-owned host memory, wall clock.
@@ -241,10 +243,12 @@ def main():
     bitmap_t, ids_t = partition.device_tensors(eng, W, H)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+    peer = partition.PeerFrame(lib, rank, world) if world > 1 else None   # ranks > 0 now write into rank 0's frame
+
     def frame_device():
         lib.b200_render(occ, wire.Int4(8, 4, 1, 0), si0, objects, pp, eye, target, angles)
         if world > 1:
-            dist.reduce(bitmap_t, dst=0, op=dist.ReduceOp.SUM)   # the path's one exchange step (NVLink)
+            peer.fence()   # every rank's kernels, and with them their stores into rank 0's frame, are done
 
     # ---- device-resident timing --------------------------------------------------------------------------
     launches0 = eng.kernel_launches()
@@ -294,10 +298,13 @@ def main():
     def frame_e2e_all():
         si_live.pathTracingIteration = 0
         h.set_scene_info(si_live)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                peer.fence()   # rank 0 has read the previous frame back
         h.render_begin(0.0)
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.reduce(bitmap_t, dst=0, op=dist.ReduceOp.SUM)
+                peer.fence()   # the frame is complete in rank 0's device bitmap
         if rank == 0:
             h.render_end()
         else:
@@ -325,7 +332,20 @@ def main():
            "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()) * world,   # scene-info + camera + pointers block, per frame and rank
            "d2h_bytes_per_step": W * H * 3 + W * H * 16}   # RGB8 + PrimitiveXYIdBuffer, as d2h_bitmap copies (rank 0)
 
+    frame_check = None
     if world > 1:
+        # the merged frame rank 0 just read back against the whole frame rendered by rank 0 alone
+        dist.barrier()
+        peer.close()
+        if rank == 0:
+            merged = np.array(h.bitmap(), copy=True)
+            lib.b200_set_partition(0, 1)
+            frame_e2e()
+            whole = np.array(h.bitmap(), copy=True)
+            differing = int(np.count_nonzero(merged != whole))
+            frame_check = {"bytes_differing_from_the_one_gpu_frame": differing, "bytes": int(whole.size)}
+            if differing:
+                raise SystemExit("bench.py: the frame merged over %d GPUs differs from the one-GPU frame in %d bytes" % (world, differing))
         dist.barrier()
     if rank == 0:
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -333,9 +353,13 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_frame": rays_total / args.steps, "mpixels_per_s": px_total / (total_ms * 1e-3) / 1e6,
                            "l2": "flushed between timed frames (256 MiB memset outside the timed region)",
-                           "parallelism": "one frame, interleaved 8x4 tiles over %d GPU(s), NCCL sum-reduce of RGB8 to rank 0" % world},
+                           "parallelism": "one frame, interleaved 8x4 tiles over %d GPU(s)%s" % (
+                               world, ", finished pixels stored into rank 0's frame over NVLink peer memory by the ray kernels, "
+                               "one-element NCCL all-reduce as frame fence" if world > 1 else "")},
                 "clocks": clocks, "gpu_launches": int(launches), "kernel_ms_last_frame": kernel_ms}
         line["e2e"] = e2e
+        if frame_check is not None:
+            line["frame_check"] = frame_check
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary_latest.json")) as f:

@@ -80,6 +80,15 @@ void b200_set_option(int key, int value);
 /* Multi-GPU frame split: this process renders tiles t with t % worldSize == rank (interleaved 8x4-pixel
  * tiles). Non-owned pixels of the device bitmap/ids stay zero so frames merge by summation. */
 void b200_set_partition(int rank, int worldSize);
+/* The frame exchange fused into the ray kernels (replaces a reduce/gather of partial bitmaps after them; the reference's
+ * dormant multi-GPU path copies every device's band back through the host, CudaRayTracer.cu:1647-1672).  The root process
+ * exports a 64-byte inter-process handle of its device bitmap (after reshape_scene; a reshape invalidates it), every other
+ * process opens it, and from then on the kernel that ends a path stores its RGB8 straight into the root's frame through
+ * NVLink peer memory; the processes' own device bitmaps are no longer written.  The caller orders frames across processes
+ * (one stream-ordered barrier when the kernels are done, one before the next frame starts; sol-r_b200/partition.py).
+ * b200_peer_frame_open(NULL, 0) goes back to the local bitmap.  Both return 0 or the latched error code. */
+int b200_peer_frame_export(void* handle64, int handleBytes);
+int b200_peer_frame_open(const void* handle64, int handleBytes);
 /* Device pointers of the per-pixel buffers for in-place collectives (NCCL) — valid until reshape/finalize. */
 void b200_device_buffers(void** bitmap, void** primitivesXYIds, void** postProcessingBuffer);
 /* Copies the float accumulation buffer (W*H PostProcessingBuffer) to the host — the state k_default packs

@@ -786,6 +786,7 @@ struct Engine
     std::vector<b200_Material> hMats;
     // frame
     b200_PostProcessingBuffer* dPost = nullptr; int4* dIds = nullptr; unsigned char* dBitmap = nullptr;
+    unsigned char* dPeerBitmap = nullptr; // the root GPU's bitmap mapped into this process (b200_peer_frame_open), else null
     unsigned int* dTileCounter = nullptr; unsigned long long* dWork = nullptr;
     size_t pixelsCap = 0;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -1356,6 +1357,39 @@ void b200_set_partition(int rank, int world)
     if (world < 1 || rank < 0 || rank >= world) { latch(-2, "b200_set_partition", "rank/world out of range"); return; }
     G.rank = rank; G.world = world;
 }
+// The multi-GPU exchange step fused into the ray kernels: the root's device bitmap is mapped into every other process
+// (CUDA IPC; peer access over NVLink / NVSwitch) and the kernel that ends a path packs its RGB8 straight into the root's
+// frame, so the frame is complete on the root when the last rank's kernels are — no partial bitmaps, no reduce.
+static void closePeerFrame()
+{
+    if (G.dPeerBitmap) { cudaIpcCloseMemHandle(G.dPeerBitmap); cudaGetLastError(); G.dPeerBitmap = nullptr; }
+}
+int b200_peer_frame_export(void* handle, int handleBytes)
+{
+    if (!handle || handleBytes < (int)sizeof(cudaIpcMemHandle_t)) { latch(-12, "b200_peer_frame_export", "handle buffer too small (64 bytes)"); return -12; }
+    if (!G.dBitmap) { latch(-4, "b200_peer_frame_export", "reshape_scene not called"); return -4; }
+    if (!ensureDevice()) return G.err;
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, G.dBitmap);
+    if (e != cudaSuccess) { cudaGetLastError(); latch((int)e, "b200_peer_frame_export", cudaGetErrorString(e)); return (int)e; }
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+int b200_peer_frame_open(const void* handle, int handleBytes)
+{
+    if (!ensureDevice()) return G.err;
+    CK(cudaStreamSynchronize(G.stream));
+    closePeerFrame();
+    if (!handle) return 0;
+    if (handleBytes < (int)sizeof(cudaIpcMemHandle_t)) { latch(-12, "b200_peer_frame_open", "handle too small (64 bytes)"); return -12; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); latch((int)e, "b200_peer_frame_open", cudaGetErrorString(e)); return (int)e; }
+    G.dPeerBitmap = (unsigned char*)p;
+    return 0;
+}
 int b200_last_error(char* msg, int cap)
 {
     if (msg && cap > 0) { strncpy(msg, G.errMsg, cap - 1); msg[cap - 1] = 0; }
@@ -1399,6 +1433,7 @@ void b200_finalize_scene(b200_int2)
     if (!ensureDevice()) return;
     cudaDeviceSynchronize();
     unregisterHost();
+    closePeerFrame();
     freeDev(G.dWide); freeDev(G.dLeafRecs); G.capWide = G.capLeafRecs = 0; G.nbWide = 0;
     freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
@@ -1792,7 +1827,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.eye = make_float3(origin.x, origin.y, origin.z);
     P.target = make_float3(direction.x, direction.y, direction.z);
     P.angles = make_float4(angles.x, angles.y, angles.z, angles.w);
-    P.post = G.dPost; P.ids = G.dIds; P.bitmap = G.dBitmap;
+    P.post = G.dPost; P.ids = G.dIds; P.bitmap = G.dPeerBitmap ? G.dPeerBitmap : G.dBitmap;
     P.tileCounter = G.dTileCounter; P.workCounters = G.dWork;
     P.tilesX = (si.size.x + TILE_W - 1) / TILE_W;
     P.tilesY = (si.size.y + TILE_H - 1) / TILE_H;

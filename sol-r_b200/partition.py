@@ -1,6 +1,10 @@
 """Frame split across GPUs: interleaved ownership of 8x4-pixel tiles, tile t -> rank t % world,
-tiles numbered row-major.  Mirrors k_render's `tile = k * worldSize + rank` (csrc/engine.cu).  Frames merge
-by summation because every rank leaves the pixels it does not own at zero.
+tiles numbered row-major.  Mirrors k_render's `tile = k * worldSize + rank` (csrc/engine.cu).
+
+The exchange step has two forms.  PeerFrame (the GPU path): the root GPU's device bitmap is mapped into every other
+process and the ray kernels store finished pixels straight into it over NVLink, so the exchange is fused into the kernels and
+only a stream-ordered barrier remains.  merge_frames (gloo tests, and NCCL as the plain form): every rank leaves the pixels it
+does not own at zero and the partial frames are summed onto the root.
 
 The reference's dormant multi-GPU path splits contiguous row bands instead
 (/root/reference/solr/engines/cuda/CudaRayTracer.cu:1694-1706, :1647-1672); cost per pixel varies by >10x between sky and
@@ -49,3 +53,45 @@ def merge_frames(bitmap, ids=None, dst=0):
     dist.reduce(bitmap, dst=dst, op=dist.ReduceOp.SUM)
     if ids is not None:
         dist.reduce(ids, dst=dst, op=dist.ReduceOp.SUM)
+
+
+class PeerFrame:
+    """The fused exchange (include/solr_b200.h b200_peer_frame_*): rank `root` exports its device bitmap, the others open
+    it, and from then on their kernels write finished pixels into the root's frame through NVLink peer memory.
+
+    fence() is a one-element NCCL all-reduce on the current CUDA stream (under gloo — tests with two processes on one GPU —
+    it drains the engine's stream and meets the other ranks on the host).  A frame is: fence (the root has read the previous frame:
+    nobody overwrites it early), render on every rank, fence (every rank's kernels — and with them their peer stores — are
+    done), then the root's read-back."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, lib, rank, world, root=0):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        self.lib, self.rank, self.world, self.root, self.dist = lib, rank, world, root, dist
+        box = [None]
+        if rank == root:
+            buf = ctypes.create_string_buffer(self.HANDLE_BYTES)
+            if lib.b200_peer_frame_export(buf, self.HANDLE_BYTES) != 0:
+                raise RuntimeError("b200_peer_frame_export failed")
+            box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=root)
+        if rank != root:
+            self._handle = ctypes.create_string_buffer(box[0], self.HANDLE_BYTES)
+            if lib.b200_peer_frame_open(self._handle, self.HANDLE_BYTES) != 0:
+                raise RuntimeError("b200_peer_frame_open failed (no peer access to the root GPU?)")
+        self.nccl = dist.get_backend() == "nccl"
+        self.token = torch.zeros(1, dtype=torch.int32, device="cuda") if self.nccl else None
+
+    def fence(self):
+        if self.nccl:
+            self.dist.all_reduce(self.token)
+        else:
+            self.lib.b200_synchronize()
+            self.dist.barrier()
+
+    def close(self):
+        if self.rank != self.root:
+            self.lib.b200_peer_frame_open(None, 0)
