@@ -788,7 +788,6 @@ struct Engine
     b200_PostProcessingBuffer* dPost = nullptr; int4* dIds = nullptr; unsigned char* dBitmap = nullptr;
     unsigned char* dPeerBitmap = nullptr; // the root GPU's bitmap mapped into this process (b200_peer_frame_open), else null
     unsigned int* dTileCounter = nullptr; unsigned long long* dWork = nullptr;
-    float4* dCandScratch = nullptr; unsigned int candStride = 0; // candidate lists of the cooperative walks (trace.cuh)
     size_t pixelsCap = 0;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool timed = false;
@@ -1411,11 +1410,6 @@ void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
     CK(cudaEventCreate(&G.evStart));
     CK(cudaEventCreate(&G.evStop));
     CK(cudaMalloc(&G.dTileCounter, sizeof(unsigned int)));
-    // one column per thread of the largest grid any kernel runs (2048 threads per SM), COOP_CAP slots of 16 bytes; only the
-    // first few slots of a column are ever touched
-    G.candStride = (unsigned int)G.numSMs * 2048u;
-    freeDev(G.dCandScratch);
-    CK(cudaMalloc(&G.dCandScratch, (size_t)COOP_CAP * G.candStride * sizeof(float4)));
     CK(cudaMalloc(&G.dWork, 8 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(G.dWork, 0, 8 * sizeof(unsigned long long), G.stream));
     CK(cudaMalloc(&G.dLights, B200_NB_MAX_LIGHTINFORMATIONS * sizeof(b200_LightInformation)));
@@ -1444,7 +1438,7 @@ void b200_finalize_scene(b200_int2)
     freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
-    freeDev(G.dTileCounter); freeDev(G.dWork); freeDev(G.dCandScratch);
+    freeDev(G.dTileCounter); freeDev(G.dWork);
     freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters); freeDev(G.dHitWords);
     G.pathStride = 0; G.pathIterations = 0;
     if (G.evStart) { cudaEventDestroy(G.evStart); G.evStart = nullptr; }
@@ -1835,7 +1829,6 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.angles = make_float4(angles.x, angles.y, angles.z, angles.w);
     P.post = G.dPost; P.ids = G.dIds; P.bitmap = G.dPeerBitmap ? G.dPeerBitmap : G.dBitmap;
     P.tileCounter = G.dTileCounter; P.workCounters = G.dWork;
-    P.scene.candScratch = G.dCandScratch; P.scene.candStride = G.candStride;
     P.tilesX = (si.size.x + TILE_W - 1) / TILE_W;
     P.tilesY = (si.size.y + TILE_H - 1) / TILE_H;
     const int nbTiles = P.tilesX * P.tilesY;

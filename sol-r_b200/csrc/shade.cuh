@@ -280,7 +280,7 @@ SB_DEV float4 traceShadow(const float3 center, const float3 I, const int lightId
             bool ordered = true;
             if (cS.opaqueShadows && dot(d, d) >= 1.0002f)
             {
-                sh.w = UNORDERED_WALK(UW_SHADOW, I + normalize(d) * cSI.rayEpsilon, d, iteration, 0, lightId, objectId).shadow;
+                sh.w = unorderedWalk(UW_SHADOW, I + normalize(d) * cSI.rayEpsilon, d, iteration, 0, lightId, objectId).shadow;
                 ordered = sh.w < 0.f; // stack overflow in a degenerate tree
 #ifdef SOLR_DEBUG_SHADOWCMP
                 if (!ordered)

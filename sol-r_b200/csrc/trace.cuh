@@ -55,10 +55,6 @@ struct SceneDev
     // the only primitives that can register a hit behind it
     int nbUX; // its nodes follow the first tree's in uwnodes (root = nbUWide); leaf refs carry bit 30
     int opaqueShadows; // every shadow caster blocks fully (no transparent material, no textured plane): any-hit is exact
-    // cooperative walks (unorderedWalkCoop): candidate lists of the bounce rays, [slot][thread of the grid], addressable by every
-    // lane of the owner's warp
-    float4* candScratch;
-    unsigned int candStride; // threads the scratch was sized for (>= gridDim.x * blockDim.x of every kernel)
 };
 
 // The walks are kept out of line by default (one copy each, own register allocation); -DWALK_INLINE=__forceinline__ to compare.
@@ -1428,273 +1424,11 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     return out;
 }
 
-// ---- cooperative walk -----------------------------------------------------------------------------------------------------
-// unorderedWalk() runs a warp for as long as its longest walk: walks average 21 node visits but the maximum over 32 lanes is
-// ~100, so the bounce passes execute at 6-8 active lanes per instruction.  All three ray classes it serves are
-// order-independent by construction (minimum over candidates / a set of candidates / any blocker), so a walk can be SPLIT: a
-// lane whose stack has run empty takes the bottom entry (the oldest, i.e. largest pending subtree) of a busy lane's stack
-// together with that lane's ray, and walks it on behalf of that ray's owner.  Everything a walk accumulates lives where every
-// lane of the warp can reach it, indexed by the owner's thread:
-//   s_key[owner]  u64, atomicMin:  closest: (distance bits << 32) | primitive index  — minimum distance, ties to the lowest index,
-//                 exactly the rule of the sequential walk;  gather: distance bits in the high word (the window follows from it);
-//                 shadow: 0 once a blocker is found (every helper's bound collapses and its stack is dropped)
-//   s_n[owner]    gather: candidates appended (atomicAdd); the records go to cS.candScratch[slot][owner's grid thread]
-// The owner finishes its ray when the whole warp has run dry: hit point and flags are recomputed from the winning primitive
-// (the primitive tests are deterministic functions of (primitive, ray); a thief rebuilds the identical ray from the shuffled
-// origin and direction), the gather replay is the same as in unorderedWalk().  Culling uses whatever bound is current, which is
-// never tighter than the final one, so no candidate the sequential walk keeps can be lost, whoever finds it.
-#ifndef UW_COOP
-#define UW_COOP 0 // measured slower (profiles/r01_history.md): exact, but 7.0-10.5 ms per frame of config 2 against 4.43 ms
-#endif
-#ifndef COOP_ROUNDS
-#define COOP_ROUNDS 8 // node rounds between two looks for idle lanes
-#endif
-#ifndef COOP_BUSY_MAX
-#define COOP_BUSY_MAX 8 // work is only handed out in the tail of a warp's walks: at most this many lanes still busy
-#endif
-#ifndef COOP_CAP
-#define COOP_CAP 96 // candidate slots per bounce ray (helpers append before they know the owner's window, so more than GATHER_CAP)
-#endif
-#define COOP_OVERFLOW (1 << 20)
-
-__device__ __noinline__ WalkOut unorderedWalkCoop(int mode, const float3 rayOrigin, const float3 rayDir, const int iteration,
-                                                  const int currentMaterialId, const int lightId, const int objectId)
-{
-    __shared__ int2 s_stack[SM_STACK * WALK_THREADS];
-    __shared__ unsigned long long s_key[WALK_THREADS];
-    __shared__ int s_n[WALK_THREADS];
-    __shared__ unsigned char s_pair[WALK_THREADS];
-    WalkOut out;
-    out.hit.prim = -1; out.hit.p = f3(0.f, 0.f, 0.f); out.hit.flags = 0; out.shadow = 0.f;
-    const unsigned mask = __activemask();
-    const int lane = threadIdx.x & 31;
-    const int warpBase = threadIdx.x - lane;
-    const float shadowLimit = cSI.shadowIntensity;
-    const float myMin0 = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
-    const int myMode = mode;
-    const bool myLive = !(mode == UW_SHADOW && !(0.f < shadowLimit));
-    // the job this lane is working on (its own ray first)
-    Ray r;
-    makeRay(r, rayOrigin, rayDir);
-    NodeRay q;
-    nodeRay(q, r);
-    float min0 = myMin0;
-    float len2 = dot(r.d, r.d);
-    float invLen = rsqrtf(len2) * 1.0001f;
-    float lenOL = sqrtf(len2);
-    int owner = threadIdx.x;
-    int idA = (mode == UW_SHADOW) ? lightId : currentMaterialId, idB = objectId;
-    const float eps = cSI.geometryEpsilon;
-    const float4* __restrict__ leafRecs = cS.leafRecs;
-    const int* __restrict__ metas = cS.meta;
-    const bool extended = cSI.extendedGeometry != 0;
-    const float4* __restrict__ nodes = cS.uwnodes;
-    const int nbMain = cS.nbUWide;
-    int stackRef[UN_STACK - SM_STACK];
-    float stackT[UN_STACK - SM_STACK];
-    WalkStack st;
-    st.sm = s_stack + threadIdx.x; st.lref = stackRef; st.lt = stackT;
-    int base = 0, sp = 0;
-    s_key[threadIdx.x] = ((unsigned long long)__float_as_uint(myMin0)) << 32;
-    s_n[threadIdx.x] = 0;
-    if (myLive)
-    {
-        st.push(0, 0, 0.f); sp = 1;
-        if (cS.nbUX > 0) { st.push(1, nbMain, -3.0e38f); sp = 2; }
-    }
-    __syncwarp(mask);
-    for (;;)
-    {
-        // ---- idle lanes take work from busy ones --------------------------------------------------------------------------
-        if (mode == UW_SHADOW && sp > base && (unsigned)(s_key[owner] >> 32) == 0u) sp = base; // blocker found by somebody
-        if (sp <= base) { base = 0; sp = 0; }
-        const unsigned busyM = __ballot_sync(mask, sp > base);
-        if (busyM == 0u) break;
-        const unsigned idleM = mask & ~busyM;
-        if (idleM && __popc(busyM) <= COOP_BUSY_MAX)
-        {
-            const unsigned donorM = __ballot_sync(mask, sp - base >= 2 && base < SM_STACK);
-            if (donorM)
-            {
-                const int pairs = min(__popc(idleM), __popc(donorM));
-                const unsigned lt = (1u << lane) - 1u;
-                const bool amDonor = (donorM >> lane) & 1u;
-                const int myRank = amDonor ? __popc(donorM & lt) : __popc(idleM & lt);
-                const bool robbed = amDonor && myRank < pairs;
-                const bool thief = !amDonor && ((idleM >> lane) & 1u) && myRank < pairs;
-                if (robbed) s_pair[warpBase + myRank] = (unsigned char)lane;
-                __syncwarp(mask);
-                const int src = thief ? (int)s_pair[warpBase + myRank] : lane;
-                const float ox = __shfl_sync(mask, r.o.x, src), oy = __shfl_sync(mask, r.o.y, src), oz = __shfl_sync(mask, r.o.z, src);
-                const float dx = __shfl_sync(mask, r.d.x, src), dy = __shfl_sync(mask, r.d.y, src), dz = __shfl_sync(mask, r.d.z, src);
-                const int jOwner = __shfl_sync(mask, owner, src), jBase = __shfl_sync(mask, base, src), jMode = __shfl_sync(mask, mode, src);
-                const float jMin0 = __shfl_sync(mask, min0, src);
-                const int jA = __shfl_sync(mask, idA, src), jB = __shfl_sync(mask, idB, src);
-                if (thief)
-                {
-                    const int2 e = s_stack[jBase * WALK_THREADS + warpBase + src]; // the donor's bottom entry
-                    makeRay(r, f3(ox, oy, oz), f3(dx, dy, dz));
-                    nodeRay(q, r);
-                    len2 = dot(r.d, r.d); invLen = rsqrtf(len2) * 1.0001f; lenOL = sqrtf(len2);
-                    owner = jOwner; mode = jMode; min0 = jMin0; idA = jA; idB = jB;
-                    base = 0; sp = 1;
-                    st.push(0, e.x, __int_as_float(e.y));
-#ifdef COOP_STATS
-                    atomicAdd(cP.workCounters + 4, 1ull);
-#endif
-                }
-                if (robbed) ++base;
-                __syncwarp(mask);
-            }
-        }
-        // ---- node rounds until this lane holds a leaf (bounded, so that idle lanes are looked after regularly) ----------------
-        int cur = WIDE_NONE;
-        float cullT = 0.f, window = 0.f;
-        for (int k = 0; k < COOP_ROUNDS && cur == WIDE_NONE && sp > base; ++k)
-        {
-            const float best = __uint_as_float((unsigned)(s_key[owner] >> 32));
-            window = fminf(min0, GATHER_WINDOW * best);
-            cullT = (mode == UW_SHADOW) ? ((best == 0.f) ? -1.f : fminf(min0, UW_SHADOW_TLIMIT))
-                  : (mode == UW_CLOSEST) ? fminf(min0, best * invLen) : fminf(min0, window * invLen);
-            --sp;
-            int ref;
-            float tEntry;
-            st.pop(sp, ref, tEntry);
-            if (tEntry > cullT) continue;
-            if (ref < 0) { cur = ref; break; }
-            if (!unorderedStep(nodes, ref, q, (ref >= nbMain) ? 0.f : cullT, st, sp)) { atomicAdd(&s_n[owner], COOP_OVERFLOW); sp = base; }
-        }
-        if (cur == WIDE_NONE) continue;
-        // ---- a BVH leaf is one primitive ---------------------------------------------------------------------------------------
-        {
-            const bool behind = ((~cur) & 0x40000000) != 0; // from the point-query tree
-            const int idx = (~cur) & 0x3FFFFFFF;
-            const int meta = __ldg(metas + idx);
-            const int fast = PM_FAST(meta);
-            bool test;
-            if (mode == UW_SHADOW)
-            {
-                const int origIndex = __ldg(&cS.prims[idx].index);
-                const int type = extended ? PM_TYPE(meta) : B200_PT_TRIANGLE;
-                test = fast == 0 && origIndex != idA && origIndex != idB && type != B200_PT_CAMERA && type != B200_PT_ENVIRONMENT &&
-                       !(type == B200_PT_TRIANGLE && cSI.doubleSidedTriangles);
-            }
-            else
-                test = fast == 0 || (fast == 1 && idA != PM_MATERIAL(meta));
-            if (!test) continue;
-            float3 I;
-            int flags;
-            float planeShadow;
-            if (!primitiveTest(idx, meta, r, I, flags, planeShadow)) continue;
-            const float distance = length(I - r.o);
-            if (!(distance > eps)) continue;
-            if ((dot(I - r.o, r.d) < 0.f) != behind) continue;
-            const int leaf = __ldg(cS.primLeaf + idx);
-            const float4 lo = __ldg(leafRecs + 2 * leaf);
-            const float4 hi = __ldg(leafRecs + 2 * leaf + 1);
-            float leafT;
-            if (!slabT(lo, hi, r, (mode == UW_CLOSEST) ? 3.0e38f : min0, leafT)) continue;
-            if (mode == UW_SHADOW)
-            {
-                if (distance < lenOL) { s_key[owner] = 0ull; sp = base; }
-            }
-            else if (mode == UW_CLOSEST)
-            {
-                if (distance < min0)
-                    atomicMin(&s_key[owner], (((unsigned long long)__float_as_uint(distance)) << 32) | (unsigned)idx);
-            }
-            else
-            {
-                // the window may have shrunk since cullT was taken; re-read it so that the list stays short
-                const float bestNow = __uint_as_float((unsigned)(s_key[owner] >> 32));
-                const float windowNow = fminf(min0, GATHER_WINDOW * bestNow);
-                if (distance < min0 && distance <= windowNow)
-                {
-                    atomicMin(reinterpret_cast<unsigned int*>(&s_key[owner]) + 1, __float_as_uint(distance));
-                    const int slot = atomicAdd(&s_n[owner], 1);
-                    if (slot < COOP_CAP)
-                        cS.candScratch[(size_t)slot * cS.candStride + blockIdx.x * WALK_THREADS + owner] =
-                            make_float4(__int_as_float(idx), distance, leafT, __int_as_float(leaf));
-                }
-            }
-        }
-    }
-    __syncwarp(mask);
-    // ---- every lane finishes its own ray ------------------------------------------------------------------------------------------
-    if (!myLive) return out;
-    const unsigned long long key = s_key[threadIdx.x];
-    const int n = s_n[threadIdx.x];
-    if (n >= COOP_OVERFLOW || (myMode == UW_GATHER && n > COOP_CAP))
-    {
-        atomicAdd(cP.workCounters + 3, 1ull);
-        out.hit.prim = -2; out.shadow = -1.f; // caller runs the ordered walk
-        return out;
-    }
-    if (myMode == UW_SHADOW)
-    {
-        if ((unsigned)(key >> 32) == 0u) out.shadow = fmaxf(0.f, fminf(shadowLimit, shadowLimit));
-        return out;
-    }
-    int winner = -1;
-    if (myMode == UW_CLOSEST)
-    {
-        if ((unsigned)(key >> 32) < __float_as_uint(myMin0)) winner = (int)(unsigned)(key & 0xFFFFFFFFull);
-    }
-    else
-    {
-        // replay in array order, as unorderedWalk() does
-        const float4* __restrict__ cand = cS.candScratch + blockIdx.x * WALK_THREADS + threadIdx.x;
-        const size_t stride = cS.candStride;
-        const float windowF = fminf(myMin0, GATHER_WINDOW * __uint_as_float((unsigned)(key >> 32)));
-        float m = myMin0;
-        bool leafPass = false;
-        int prevLeaf = -1;
-        int last = -1;
-        for (int pass = 0; pass < n; ++pass)
-        {
-            int bi = 0x7fffffff;
-            float bD = 0.f, bT = 0.f;
-            int bLeaf = -1;
-            for (int j = 0; j < n; ++j)
-            {
-                const float4 c = cand[j * stride];
-                const int ci = __float_as_int(c.x);
-                if (ci > last && ci < bi && c.y <= windowF) { bi = ci; bD = c.y; bT = c.z; bLeaf = __float_as_int(c.w); }
-            }
-            if (bi == 0x7fffffff) break;
-            last = bi;
-            if (bLeaf != prevLeaf)
-            {
-                leafPass = bT < m;
-                prevLeaf = bLeaf;
-            }
-            if (leafPass && bD < m) { m = bD; winner = bi; }
-        }
-    }
-    if (winner >= 0)
-    {
-        Ray r0;
-        makeRay(r0, rayOrigin, rayDir);
-        const int meta = __ldg(metas + winner);
-        float3 I;
-        int flags;
-        float planeShadow;
-        primitiveTest(winner, meta, r0, I, flags, planeShadow);
-        out.hit.prim = winner; out.hit.p = I; out.hit.flags = flags;
-    }
-    return out;
-}
-#if UW_COOP
-#define UNORDERED_WALK unorderedWalkCoop
-#else
-#define UNORDERED_WALK unorderedWalk
-#endif
-
 SB_DEV Hit closestHitOrderIndependent(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)
 {
     const float3 d = target - origin;
     const int mode = (dot(d, d) >= 1.0002f) ? UW_CLOSEST : UW_GATHER;
-    const WalkOut o = UNORDERED_WALK(mode, origin, d, iteration, currentMaterialId, 0, 0);
+    const WalkOut o = unorderedWalk(mode, origin, d, iteration, currentMaterialId, 0, 0);
     if (o.hit.prim == -2) return closestHitWide(origin, target, iteration, currentMaterialId);
     return o.hit;
 }
