@@ -16,8 +16,9 @@ A *ray* is one box-list walk (closest-hit or shadow), SURVEY.md §8(d).
           peer memory (partition.PeerFrame) — and a one-element NCCL all-reduce inside the timed region orders the frame.
           After the timed runs rank 0 renders the whole frame alone and checks the merged frame against it, byte for byte.
   e2e     the same metric through the host-side drop-in (SceneHost.render_begin + render_end = the calls
-          CudaKernel makes): per-frame parameter upload, kernel, device->host copy of RGB8 + id buffer into
-          caller-owned host memory, wall clock.
+          CudaKernel makes): per-frame parameter upload, kernels, device->host copy of RGB8 into caller-owned
+          host memory, wall clock.  The id buffer (16 B per pixel) is read back on demand (getPrimitiveAt), as the
+          drop-in does by default; the figure with the reference's every-frame id read-back is reported beside it.
   roofline  FP32 CUDA-core roofline (north_star: compute-bound, no tensor cores): algorithmic flops counted by
           the oracle in REFERENCE traversal order (SURVEY §8(d) constants) / device time / (148 SM x 128 lanes x
           2 x sm_max_mhz).  HBM traffic is reported beside it.
@@ -310,27 +311,38 @@ def main():
         else:
             stream.synchronize()
 
-    for _ in range(3):
-        frame_e2e_all()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    eng.counters(reset=True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        frame_e2e_all()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    rays_e2e, _ = eng.counters(reset=True)
-    te = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    re_ = torch.tensor([float(rays_e2e)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(re_, op=dist.ReduceOp.SUM)
-    dt = float(te.item())
-    e2e = {"value": float(re_.item()) / dt / 1e6, "unit": "Mrays/s", "ms_per_frame": dt / args.steps * 1e3,
+    def measure_e2e():
+        for _ in range(3):
+            frame_e2e_all()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        eng.counters(reset=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            frame_e2e_all()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        rays_e2e, _ = eng.counters(reset=True)
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        re_ = torch.tensor([float(rays_e2e)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(re_, op=dist.ReduceOp.SUM)
+        return float(re_.item()) / float(te.item()) / 1e6, float(te.item()) / args.steps * 1e3
+
+    # the drop-in's default: render_end reads the pixels back, the id buffer stays on the device until getPrimitiveAt asks (its only
+    # host-side reader, GPUKernel.cpp:729-739); then the reference's own protocol — pixels and 16 bytes of ids per pixel, every frame
+    e2e_value, e2e_ms = measure_e2e()
+    h.set_lazy_ids(False)
+    eager_value, eager_ms = measure_e2e()
+    h.set_lazy_ids(True)
+    frame_e2e_all()
+    e2e = {"value": e2e_value, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
            "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()) * world,   # scene-info + camera + pointers block, per frame and rank
-           "d2h_bytes_per_step": W * H * 3 + W * H * 16}   # RGB8 + PrimitiveXYIdBuffer, as d2h_bitmap copies (rank 0)
+           "d2h_bytes_per_step": W * H * 3,   # RGB8 into caller-owned memory (rank 0)
+           "with_id_buffer_every_frame": {"value": eager_value, "ms_per_frame": eager_ms, "d2h_bytes_per_step": W * H * 3 + W * H * 16,
+                                          "note": "the reference's render_end protocol (CudaKernel.cpp:304-313)"}}
 
     frame_check = None
     if world > 1:

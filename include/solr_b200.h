@@ -91,6 +91,10 @@ int b200_peer_frame_export(void* handle64, int handleBytes);
 int b200_peer_frame_open(const void* handle64, int handleBytes);
 /* Device pointers of the per-pixel buffers for in-place collectives (NCCL) — valid until reshape/finalize. */
 void b200_device_buffers(void** bitmap, void** primitivesXYIds, void** postProcessingBuffer);
+/* One pixel's PrimitiveXYIdBuffer (16 bytes) from the device: what GPUKernel::getPrimitiveAt (GPUKernel.cpp:729-739) reads, the only
+ * host-side consumer of the id buffer d2h_bitmap copies every frame (33 MB at 1080p, CudaKernel.cpp:307).  A host class that
+ * passes primitivesXYIds = NULL to b200_d2h_bitmap and asks here on a pick moves 6 MB per frame instead of 39 MB. */
+void b200_d2h_primitive_id(b200_SceneInfo sceneInfo, int x, int y, b200_PrimitiveXYIdBuffer* id);
 /* Copies the float accumulation buffer (W*H PostProcessingBuffer) to the host — the state k_default packs
  * into RGB8; the reference keeps it device-only (CudaRayTracer.cu:38).  Used by parity tests. */
 void b200_d2h_post(b200_SceneInfo sceneInfo, b200_PostProcessingBuffer* postProcessingBuffer);

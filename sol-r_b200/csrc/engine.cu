@@ -1957,6 +1957,15 @@ void b200_d2h_bitmap(b200_int2, b200_SceneInfo si, b200_BitmapBuffer* bitmap, b2
     CK(cudaStreamSynchronize(G.stream));
 }
 
+void b200_d2h_primitive_id(b200_SceneInfo si, int x, int y, b200_PrimitiveXYIdBuffer* id)
+{
+    if (!G.dIds || !id) { latch(-4, "b200_d2h_primitive_id", "reshape_scene not called"); return; }
+    if (!ensureDevice()) return;
+    if (x < 0 || y < 0 || x >= si.size.x || y >= si.size.y || (size_t)si.size.x * si.size.y > G.pixelsCap) { latch(-6, "b200_d2h_primitive_id", "pixel outside the frame"); return; }
+    CK(cudaMemcpyAsync(id, G.dIds + ((size_t)y * si.size.x + x), sizeof(int4), cudaMemcpyDeviceToHost, G.stream));
+    CK(cudaStreamSynchronize(G.stream));
+}
+
 void b200_debug_counters(unsigned long long* out8)
 {
     if (G.dWork && ensureDevice())

@@ -652,15 +652,34 @@ void SceneHost::render_begin(const float) // CudaKernel.cpp:174-302
 
 void SceneHost::render_end() // CudaKernel.cpp:304-313 (the GL blit that follows there is the viewer's business)
 {
+    // The reference copies the id buffer back with every frame (33 MB at 1080p beside 6 MB of pixels) although only
+    // getPrimitiveAt reads it.  Here it stays on the device until somebody asks (setLazyIds(false) = the reference's protocol).
     b200_int2 occ = {1, 1};
-    b200_d2h_bitmap(occ, m_sceneInfo, m_bitmap.data(), m_primitivesXYIds.data());
+    b200_d2h_bitmap(occ, m_sceneInfo, m_bitmap.data(), m_lazyIds ? nullptr : m_primitivesXYIds.data());
+    m_idsOnDevice = m_lazyIds;
+}
+
+b200_PrimitiveXYIdBuffer* SceneHost::getPrimitiveIds()
+{
+    if (m_idsOnDevice && m_deviceInitialised)
+    {
+        b200_int2 occ = {1, 1};
+        b200_d2h_bitmap(occ, m_sceneInfo, nullptr, m_primitivesXYIds.data());
+        m_idsOnDevice = false;
+    }
+    return m_primitivesXYIds.data();
 }
 
 unsigned int SceneHost::getPrimitiveAt(int x, int y) // GPUKernel.cpp:729-739
 {
     unsigned int returnValue = (unsigned int)-1;
     const unsigned int index = y * m_sceneInfo.size.x + x;
-    if (index < static_cast<unsigned int>(m_sceneInfo.size.x * m_sceneInfo.size.y)) returnValue = m_primitivesXYIds[index].x;
+    if (index < static_cast<unsigned int>(m_sceneInfo.size.x * m_sceneInfo.size.y))
+    {
+        if (m_idsOnDevice && m_deviceInitialised && x >= 0 && x < m_sceneInfo.size.x)
+            b200_d2h_primitive_id(m_sceneInfo, x, y, &m_primitivesXYIds[index]);
+        returnValue = m_primitivesXYIds[index].x;
+    }
     return returnValue;
 }
 } // namespace solr_b200
@@ -753,6 +772,7 @@ void b200h_get_scene(void* h, b200h_Scene* out)
 void b200h_set_randoms(void* h, const float* r, long n, int timestamp) { static_cast<SceneHost*>(h)->setRandoms(r, (size_t)n, timestamp); }
 void b200h_set_capacity(void* h, long maxBoxes, long maxPrimitives) { static_cast<SceneHost*>(h)->setCapacity((size_t)maxBoxes, (size_t)maxPrimitives); }
 void b200h_set_limits(void* h, int w, int hh) { static_cast<SceneHost*>(h)->setLimits(w, hh); }
+void b200h_set_lazy_ids(void* h, int lazy) { static_cast<SceneHost*>(h)->setLazyIds(lazy != 0); }
 void b200h_set_partition(void* h, int rank, int world) { static_cast<SceneHost*>(h)->setPartition(rank, world); }
 void b200h_set_device(void* h, int device) { static_cast<SceneHost*>(h)->setDevice(device); }
 void b200h_init_buffers(void* h) { static_cast<SceneHost*>(h)->initBuffers(); }

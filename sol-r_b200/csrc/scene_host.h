@@ -81,7 +81,8 @@ public:
     void render_begin(float timer);
     void render_end();
     unsigned char* getBitmap() { return m_bitmap.data(); }
-    b200_PrimitiveXYIdBuffer* getPrimitiveIds() { return m_primitivesXYIds.data(); }
+    b200_PrimitiveXYIdBuffer* getPrimitiveIds(); // fetches the buffer from the device first when render_end left it there
+    void setLazyIds(bool lazy) { m_lazyIds = lazy; }
     unsigned int getPrimitiveAt(int x, int y);
 
     // ---- flattened arrays, as the engine seam receives them ----
@@ -134,6 +135,8 @@ private:
 
     std::vector<unsigned char> m_bitmap;
     std::vector<b200_PrimitiveXYIdBuffer> m_primitivesXYIds;
+    bool m_lazyIds = true;      // render_end copies the pixels only; ids are fetched when asked for
+    bool m_idsOnDevice = false; // the host copy is older than the last frame
     bool m_primitivesTransfered, m_materialsTransfered, m_texturesTransfered, m_randomsTransfered, m_refresh;
     bool m_deviceInitialised;
     int m_maxWidth, m_maxHeight, m_rank, m_world, m_device;

@@ -47,6 +47,8 @@ def load():
     lib.b200_set_option.restype = None
     lib.b200_set_partition.argtypes = [C.c_int, C.c_int]
     lib.b200_device_buffers.argtypes = [C.POINTER(C.c_void_p)] * 3
+    lib.b200_d2h_primitive_id.argtypes = [SI, C.c_int, C.c_int, C.c_void_p]
+    lib.b200_d2h_primitive_id.restype = None
     lib.b200_peer_frame_export.argtypes = [C.c_void_p, C.c_int]
     lib.b200_peer_frame_export.restype = C.c_int
     lib.b200_peer_frame_open.argtypes = [C.c_void_p, C.c_int]
@@ -79,7 +81,7 @@ ABI_SYMBOLS = [
     "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
     "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition",
     "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_build_walk_trees", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
-    "b200_synchronize", "b200_peer_frame_export", "b200_peer_frame_open",
+    "b200_synchronize", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
 ]
 
 

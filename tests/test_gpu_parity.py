@@ -212,6 +212,29 @@ def test_host_frame_protocol_equals_direct_seam_calls():
     assert np.array_equal(bm1, bm2) and np.array_equal(ids1, ids2)
 
 
+def test_id_buffer_is_read_back_on_demand():
+    """render_end leaves the id buffer on the device by default; a pick (getPrimitiveAt, GPUKernel.cpp:729-739) fetches one pixel's
+    16 bytes, primitive_ids() the whole buffer — both equal what the reference's every-frame read-back (set_lazy_ids(False)) gives."""
+    sc, si, eye, target, angles, rnd, _ = gs.case_setup("mixed_full")
+    W, H = si.size.x, si.size.y
+    picks = [(48, 36), (0, 0), (W - 1, H - 1), (W // 2, H // 2), (W // 3, 2 * H // 3)]
+    out = {}
+    for lazy in (True, False):
+        h = host.SceneHost(si)
+        sc.replay(h)
+        h.set_randoms(rnd, 0)
+        h.set_camera(eye, target, angles)
+        h.set_lazy_ids(lazy)
+        h.init_buffers()
+        h.render_begin(0.0); h.render_end()
+        picked = [h.get_primitive_at(x, y) for x, y in picks]      # before anything asked for the whole buffer
+        out[lazy] = (picked, h.primitive_ids().copy(), h.bitmap().copy())
+        h.close()
+    assert out[True][0] == out[False][0] == [int(out[False][1][y, x, 0]) & 0xFFFFFFFF for x, y in picks]
+    assert np.array_equal(out[True][1], out[False][1]) and np.array_equal(out[True][2], out[False][2])
+    assert (out[False][1][..., 0] >= 0).any()
+
+
 def test_errors_are_latched():
     si = wire.default_scene_info(4000, 3000)
     e = engine.Engine(wire.default_scene_info(64, 48))
