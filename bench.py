@@ -119,8 +119,31 @@ def scene_and_info(width, height):
     return sc, si
 
 
+class _NativeStdoutToStderr:
+    """The reference library logs its banner to the C stdout; bench.py's stdout carries one JSON line and nothing else."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_reference_run(steps, warmup, want_counts=True):
     """The reference arm / cpu_baseline: the path on host cores at SAMPLE_W x SAMPLE_H."""
+    with _NativeStdoutToStderr():
+        return _cpu_reference_run(steps, warmup)
+
+
+def _cpu_reference_run(steps, warmup):
     import oracle
     import refh
     from solr_b200 import host, wire
