@@ -96,6 +96,24 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries the one JSON line and nothing else: native libraries in the process log there too (the reference library's
+    banner, NCCL's version line), so file descriptor 1 is pointed at stderr and the line is written to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def host_cores():
     """Host threads for the CPU legs: every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its
     workers, which would silently run the reference arm on one core at N > 1, so the OpenMP runtime is told explicitly."""
@@ -119,28 +137,9 @@ def scene_and_info(width, height):
     return sc, si
 
 
-class _NativeStdoutToStderr:
-    """The reference library logs its banner to the C stdout; bench.py's stdout carries one JSON line and nothing else."""
-
-    def __enter__(self):
-        sys.stdout.flush()
-        self.saved = os.dup(1)
-        os.dup2(2, 1)
-
-    def __exit__(self, *exc):
-        try:
-            import ctypes
-            ctypes.CDLL(None).fflush(None)
-        except Exception:
-            pass
-        os.dup2(self.saved, 1)
-        os.close(self.saved)
-
-
 def cpu_reference_run(steps, warmup, want_counts=True):
     """The reference arm / cpu_baseline: the path on host cores at SAMPLE_W x SAMPLE_H."""
-    with _NativeStdoutToStderr():
-        return _cpu_reference_run(steps, warmup)
+    return _cpu_reference_run(steps, warmup)
 
 
 def _cpu_reference_run(steps, warmup):
@@ -196,7 +195,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -208,6 +207,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    claim_stdout()
 
     from _solr_b200_import import solr_b200  # noqa: F401
     import __graft_entry__ as graft
@@ -417,7 +417,7 @@ def main():
                             "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json), per GPU" % pk["source"],
                             "algorithmic_gflop_per_frame": flops_frame / 1e9, "algorithmic_flops_source": flops_source,
                             "hbm": {"peak_gbs": pk["hbm_gbs"], "mandatory_bytes_per_frame": W * H * (32 + 16 + 3) * 2}}
-        print(json.dumps(line))
+        emit(line)
     h.close()
     if world > 1:
         dist.destroy_process_group()
