@@ -130,9 +130,21 @@ def host_cores():
     return n
 
 
+# --workload: config2 is the configuration BASELINE.json's metric is quoted on (the default, and what the driver runs);
+# config4 (1 M spheres, 3840x2160, iterations 10..13 = 4 accumulated samples, one frame per step) is the size north_star's
+# 8-GPU efficiency target names.  The CPU legs and the roofline's flop count exist for config2 only.
+WORKLOADS = {
+    "config2": dict(name=WORKLOAD, size=(1920, 1080), nit=3, scene="config2", iterations=[0], limits=None, capacity=None),
+    "config4": dict(name="config4_1M_spheres_3840x2160_glFull_3_bounces_accumulated_samples_iterations_10_to_13",
+                    size=(3840, 2160), nit=3, scene="config4", iterations=[10, 11, 12, 13], limits=(3840, 2160),
+                    capacity=(16_000_000, 4_000_000)),
+}
+SELECTED = WORKLOADS["config2"]
+
+
 def scene_and_info(width, height):
     from solr_b200 import scenes, wire
-    sc = scenes.config2()
+    sc = getattr(scenes, SELECTED["scene"])()
     si = wire.default_scene_info(width, height, graphics_level=wire.GL_FULL, nb_ray_iterations=NB_RAY_ITERATIONS)
     return sc, si
 
@@ -205,7 +217,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global W, H, NB_RAY_ITERATIONS, WORKLOAD, SELECTED
+    SELECTED = WORKLOADS[args.workload]
+    (W, H), NB_RAY_ITERATIONS, WORKLOAD = SELECTED["size"], SELECTED["nit"], SELECTED["name"]
+    if args.workload != "config2":
+        args.no_cpu_baseline = True
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     claim_stdout()
 
@@ -233,10 +251,16 @@ def main():
 
     pk = peaks()
     sc, si = scene_and_info(W, H)
-    rnd = np.zeros(wire.REF_MAX_BITMAP_SIZE, np.float32)
+    rnd = np.zeros(max(wire.REF_MAX_BITMAP_SIZE, W * H), np.float32)
+    iterations = SELECTED["iterations"]
+    frame_no = [0]
+
+    def next_iteration():
+        frame_no[0] += 1
+        return iterations[frame_no[0] % len(iterations)]
 
     # ---- the drop-in host path (SceneHost -> C ABI) owns the engine in this process --------------------
-    h = host.SceneHost(si, rank=rank, world=world, device=local_rank)
+    h = host.SceneHost(si, limits=SELECTED["limits"], rank=rank, world=world, device=local_rank, capacity=SELECTED["capacity"])
     sc.replay(h)
     h.set_randoms(rnd, 0)
     h.set_camera(sc.eye, sc.target, sc.angles)
@@ -270,6 +294,7 @@ def main():
     peer = partition.PeerFrame(lib, rank, world) if world > 1 else None   # ranks > 0 now write into rank 0's frame
 
     def frame_device():
+        si0.pathTracingIteration = next_iteration()
         lib.b200_render(occ, wire.Int4(8, 4, 1, 0), si0, objects, pp, eye, target, angles)
         if world > 1:
             peer.fence()   # every rank's kernels, and with them their stores into rank 0's frame, are done
@@ -319,8 +344,8 @@ def main():
     # Every rank runs the host drop-in for its tiles (render_begin: per-frame parameter upload + launch); the partial RGB8
     # frames are summed onto rank 0 over NVLink (the path's one exchange step) and rank 0 reads the merged frame and its
     # ids back to host memory (render_end = d2h_bitmap).  Wall clock around K frames, max over ranks.
-    def frame_e2e_all():
-        si_live.pathTracingIteration = 0
+    def frame_e2e_all(iteration=None):
+        si_live.pathTracingIteration = next_iteration() if iteration is None else iteration
         h.set_scene_info(si_live)
         if world > 1:
             with torch.cuda.stream(stream):
@@ -360,7 +385,7 @@ def main():
     h.set_lazy_ids(False)
     eager_value, eager_ms = measure_e2e()
     h.set_lazy_ids(True)
-    frame_e2e_all()
+    frame_e2e_all(0)   # a single-sample frame on every rank: what frame_check compares
     e2e = {"value": e2e_value, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
            "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()) * world,   # scene-info + camera + pointers block, per frame and rank
            "d2h_bytes_per_step": W * H * 3,   # RGB8 into caller-owned memory (rank 0)
@@ -403,7 +428,7 @@ def main():
         except Exception:
             pass
         flops_frame = ALGORITHMIC_GFLOP_PER_FRAME * 1e9
-        flops_source = "oracle count in reference traversal order, full frame (recorded)"
+        flops_source = "oracle count in reference traversal order, full frame (recorded)" if args.workload == "config2" else "not counted for this workload"
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_run(1, 0)
             flops_frame = cb["flops_per_frame"] * (W * H) / float(SAMPLE_W * SAMPLE_H)
@@ -417,6 +442,8 @@ def main():
                             "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json), per GPU" % pk["source"],
                             "algorithmic_gflop_per_frame": flops_frame / 1e9, "algorithmic_flops_source": flops_source,
                             "hbm": {"peak_gbs": pk["hbm_gbs"], "mandatory_bytes_per_frame": W * H * (32 + 16 + 3) * 2}}
+        if args.workload != "config2":
+            line["roofline"].update(achieved=None, frac=None, traffic=None, algorithmic_gflop_per_frame=None)
         emit(line)
     h.close()
     if world > 1:

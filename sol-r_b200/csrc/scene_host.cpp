@@ -281,6 +281,13 @@ void SceneHost::realignTexturesAndMaterials()
 // ---------------------------------------------------------------------------------------------------
 // grid hierarchy (GPUKernel.cpp:741-1083)
 // ---------------------------------------------------------------------------------------------------
+// m_primitives[id] without the tree descent: the hierarchy build asks once per primitive and level-0 box, the flatten once more.
+HostPrimitive& SceneHost::primitiveById(unsigned int id)
+{
+    if (id < m_primitiveTable.size() && m_primitiveTable[id]) return *m_primitiveTable[id];
+    return m_primitives[id]; // a missing key is created empty, as in the reference
+}
+
 bool SceneHost::updateBoundingBox(HostBox& box) // :741-839
 {
     bool result = false;
@@ -289,7 +296,7 @@ bool SceneHost::updateBoundingBox(HostBox& box) // :741-839
     box.parameters[1] = v3(-1000000, -1000000, -1000000);
     for (const auto& p : box.primitives)
     {
-        HostPrimitive& primitive = m_primitives[p];
+        HostPrimitive& primitive = primitiveById((unsigned)p);
         result = (m_hMaterials[primitive.materialId].innerIllumination.x != 0.f);
         switch (primitive.type)
         {
@@ -335,9 +342,11 @@ void SceneHost::updateOutterBoundingBox(HostBox& outterBox, int depth) // :841-8
     const float vd = m_sceneInfo.viewDistance;
     outterBox.parameters[0] = v3(vd, vd, vd);
     outterBox.parameters[1] = v3(-vd, -vd, -vd);
-    for (const auto& p : outterBox.primitives)
+    const bool linked = outterBox.children.size() == outterBox.primitives.size();
+    for (size_t c = 0; c < outterBox.primitives.size(); ++c)
     {
-        HostBox& box = m_boundingBoxes[depth][p]; // operator[]: a missing key is created empty, as in the reference
+        // operator[]: a missing key is created empty, as in the reference
+        HostBox& box = linked ? *outterBox.children[c] : m_boundingBoxes[depth][(unsigned)outterBox.primitives[c]];
         if (outterBox.parameters[0].x > box.parameters[0].x) outterBox.parameters[0].x = box.parameters[0].x;
         if (outterBox.parameters[0].y > box.parameters[0].y) outterBox.parameters[0].y = box.parameters[0].y;
         if (outterBox.parameters[0].z > box.parameters[0].z) outterBox.parameters[0].z = box.parameters[0].z;
@@ -360,7 +369,7 @@ void SceneHost::resetBoxes(bool resetPrimitives) // :894-901
 
 void SceneHost::resetBox(HostBox& box, bool resetPrimitives) // :903-917
 {
-    if (resetPrimitives) { box.primitives.clear(); box.indexForNextBox = 1; }
+    if (resetPrimitives) { box.primitives.clear(); box.children.clear(); box.indexForNextBox = 1; }
     const float vd = m_sceneInfo.viewDistance;
     box.parameters[0] = v3(vd, vd, vd);
     box.parameters[1] = v3(-vd, -vd, -vd);
@@ -376,6 +385,12 @@ void SceneHost::processBoxes(const int boxSize) // :919-992 (simulate == false)
     boxSteps.y = (boxSteps.y == 0.f) ? 1 : boxSteps.y;
     boxSteps.z = (boxSteps.z == 0.f) ? 1 : boxSteps.z;
     const float vd = m_sceneInfo.viewDistance;
+    // The reference inserts into a std::map per primitive (find, insert, operator[]).  The same map results from taking the
+    // cell keys in iteration order, ordering them by key with a STABLE sort (a box lists its primitives in iteration order)
+    // and merging them into the map in one ascending sweep; lights go to the first box of the top level as they come.
+    struct Entry { unsigned int key; unsigned int p; bool light; };
+    std::vector<Entry> entries;
+    entries.reserve(m_primitives.size());
     unsigned int p = 0;
     for (const auto& prim : m_primitives)
     {
@@ -386,20 +401,27 @@ void SceneHost::processBoxes(const int boxSize) // :919-992 (simulate == false)
         unsigned int Y = static_cast<int>((center.y - m_minPos.y) / boxSteps.y);
         unsigned int Z = static_cast<int>((center.z - m_minPos.z) / boxSteps.z);
         unsigned int B = 1 + 1000 * (X * boxSize * boxSize + Y * boxSize + Z);
-        if (m_boundingBoxes[0].find(B) == m_boundingBoxes[0].end())
+        const bool light = m_hMaterials[primitive.materialId].innerIllumination.x != 0.f;
+        if (light) m_boundingBoxes[m_treeDepth][0].primitives.push_back(p); // lights: first box of the top level
+        entries.push_back({B, p, light});
+        ++p;
+    }
+    std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+    auto& level0 = m_boundingBoxes[0];
+    auto it = level0.begin();
+    for (const Entry& e : entries)
+    {
+        while (it != level0.end() && it->first < e.key) ++it;
+        if (it == level0.end() || it->first != e.key)
         {
             HostBox box;
             box.parameters[0] = v3(vd, vd, vd);
             box.parameters[1] = v3(-vd, -vd, -vd);
             box.center = v3(0.f, 0.f, 0.f);
             box.indexForNextBox = 1;
-            m_boundingBoxes[0].insert(std::make_pair(B, box));
+            it = level0.emplace_hint(it, e.key, std::move(box)); // the cell exists even if all it received was a light
         }
-        if (m_hMaterials[primitive.materialId].innerIllumination.x != 0.f)
-            m_boundingBoxes[m_treeDepth][0].primitives.push_back(p); // lights: first box of the top level
-        else
-            m_boundingBoxes[0][B].primitives.push_back(p);
-        ++p;
+        if (!e.light) it->second.primitives.push_back(e.p);
     }
     for (auto& box : m_boundingBoxes[0]) updateBoundingBox(box.second);
 }
@@ -414,7 +436,11 @@ void SceneHost::processOutterBoxes(const int boxSize, const int depth) // :994-1
     boxSteps.y = (boxSteps.y == 0.f) ? 1 : boxSteps.y;
     boxSteps.z = (boxSteps.z == 0.f) ? 1 : boxSteps.z;
     const float vd = m_sceneInfo.viewDistance;
-    for (const auto& box : m_boundingBoxes[depth - 1])
+    // as in processBoxes: keys in iteration order, stable sort, one ascending merge into the level's map
+    struct Entry { unsigned int key; unsigned int child; HostBox* box; };
+    std::vector<Entry> entries;
+    entries.reserve(m_boundingBoxes[depth - 1].size());
+    for (auto& box : m_boundingBoxes[depth - 1])
     {
         const b200_float3& center = box.second.center;
         int X = static_cast<int>((center.x - m_minPos.x) / boxSteps.x);
@@ -424,10 +450,20 @@ void SceneHost::processOutterBoxes(const int boxSize, const int depth) // :994-1
         const uint32_t bs = (uint32_t)boxSize;
         uint32_t Bu = (uint32_t)X * bs * bs + (uint32_t)Y * bs + (uint32_t)Z;
         Bu += 1; // key 0 holds the lights
-        HostBox& ob = m_boundingBoxes[depth][Bu];
+        entries.push_back({Bu, box.first, &box.second});
+    }
+    std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+    auto& level = m_boundingBoxes[depth];
+    auto it = level.begin();
+    for (const Entry& e : entries)
+    {
+        while (it != level.end() && it->first < e.key) ++it;
+        if (it == level.end() || it->first != e.key) it = level.emplace_hint(it, e.key, HostBox());
+        HostBox& ob = it->second;
         ob.parameters[0] = v3(vd, vd, vd);
         ob.parameters[1] = v3(-vd, -vd, -vd);
-        ob.primitives.push_back(box.first);
+        ob.primitives.push_back(e.child);
+        ob.children.push_back(e.box);
     }
     for (auto& box : m_boundingBoxes[depth]) updateOutterBoundingBox(box.second, depth - 1);
 }
@@ -435,6 +471,12 @@ void SceneHost::processOutterBoxes(const int boxSize, const int depth) // :994-1
 int SceneHost::compactBoxes(bool reconstructBoxes) // :1041-1083
 {
     m_primitivesTransfered = false;
+    m_primitiveTable.clear();
+    if (!m_primitives.empty() && m_primitives.rbegin()->first < 4u * m_primitives.size() + 1024u)
+    {
+        m_primitiveTable.assign((size_t)m_primitives.rbegin()->first + 1, nullptr);
+        for (auto& prim : m_primitives) m_primitiveTable[prim.first] = &prim.second;
+    }
     if (reconstructBoxes)
     {
         resetBox(m_boundingBoxes[m_treeDepth][0], true);
@@ -453,12 +495,13 @@ int SceneHost::compactBoxes(bool reconstructBoxes) // :1041-1083
         } while (nbBoxes > gridGranularity);
     }
     streamDataToGPU();
+    m_primitiveTable.clear();
     return m_nbActiveBoxes;
 }
 
 void SceneHost::emitPrimitive(long id) // :1116-1135, :1199-1212
 {
-    HostPrimitive& primitive = m_primitives[(unsigned)id];
+    HostPrimitive& primitive = primitiveById((unsigned)id);
     b200_Primitive out;
     memset(&out, 0, sizeof(out));
     out.index = (int)id;
@@ -472,11 +515,11 @@ void SceneHost::emitPrimitive(long id) // :1116-1135, :1199-1212
     ++m_nbActivePrimitives;
 }
 
-void SceneHost::recursiveDataStreamToGPU(const int depth, std::vector<long>& elements) // :1085-1149
+void SceneHost::recursiveDataStreamToGPU(const int depth, std::vector<long>& elements, const std::vector<HostBox*>* linked) // :1085-1149
 {
-    for (const auto& element : elements)
+    for (size_t c = 0; c < elements.size(); ++c)
     {
-        HostBox& box = m_boundingBoxes[depth][(unsigned)element];
+        HostBox& box = linked ? *(*linked)[c] : m_boundingBoxes[depth][(unsigned)elements[c]];
         if (box.primitives.size() != 0 && (size_t)m_nbActiveBoxes < m_maxBoxes)
         {
             const int boxIndex = m_nbActiveBoxes;
@@ -494,7 +537,7 @@ void SceneHost::recursiveDataStreamToGPU(const int depth, std::vector<long>& ele
                     if ((size_t)id < m_maxPrimitives && (size_t)m_nbActivePrimitives < m_maxPrimitives) emitPrimitive(id);
             }
             else
-                recursiveDataStreamToGPU(depth - 1, box.primitives);
+                recursiveDataStreamToGPU(depth - 1, box.primitives, box.children.size() == box.primitives.size() ? &box.children : nullptr);
             m_hBoundingBoxes[boxIndex].indexForNextBox.x = (depth == 0) ? 1 : m_nbActiveBoxes - boxIndex;
         }
     }
@@ -531,7 +574,7 @@ void SceneHost::streamDataToGPU() // :1151-1281
             for (long id : box.primitives)
             {
                 emitPrimitive(id);
-                const HostPrimitive& primitive = m_primitives[(unsigned)id];
+                const HostPrimitive& primitive = primitiveById((unsigned)id);
                 const b200_Material& material = m_hMaterials[primitive.materialId];
                 b200_LightInformation li;
                 memset(&li, 0, sizeof(li));
@@ -550,7 +593,8 @@ void SceneHost::streamDataToGPU() // :1151-1281
             m_hBoundingBoxes.push_back(out);
         first = false;
         ++m_nbActiveBoxes;
-        if (maxDepth > 0) recursiveDataStreamToGPU(maxDepth - 1, box.primitives);
+        if (maxDepth > 0)
+            recursiveDataStreamToGPU(maxDepth - 1, box.primitives, box.children.size() == box.primitives.size() ? &box.children : nullptr);
         m_hBoundingBoxes[boxIndex].indexForNextBox.x = m_nbActiveBoxes - boxIndex;
     }
     if ((size_t)m_nbActivePrimitives != m_primitives.size())

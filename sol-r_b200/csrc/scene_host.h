@@ -39,6 +39,9 @@ struct HostBox // GPUKernel.h:65-71 (CPUBoundingBox)
     b200_float3 center;
     std::vector<long> primitives; // level 0: primitive ids; level k: keys of level k-1 boxes
     long indexForNextBox;
+    // level k >= 1: the boxes those keys name, appended in step with `primitives` (std::map nodes do not move).  Where the two
+    // lists have the same length the builder follows the pointers instead of looking the keys up again.
+    std::vector<HostBox*> children;
 };
 
 class SceneHost
@@ -106,9 +109,11 @@ private:
     void resetBox(HostBox& box, bool resetPrimitives);
     void processBoxes(int boxSize);
     void processOutterBoxes(int boxSize, int depth);
-    void recursiveDataStreamToGPU(int depth, std::vector<long>& elements);
+    void recursiveDataStreamToGPU(int depth, std::vector<long>& elements, const std::vector<HostBox*>* linked);
     void streamDataToGPU();
     void emitPrimitive(long id);
+    HostPrimitive& primitiveById(unsigned int id);
+    std::vector<HostPrimitive*> m_primitiveTable; // id -> record, valid during one compactBoxes()
     void realignTexturesAndMaterials();
 
     b200_SceneInfo m_sceneInfo;

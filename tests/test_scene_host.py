@@ -54,6 +54,27 @@ def test_flattened_arrays_match_reference_live(maker):
     r.close(); h.close()
 
 
+@pytest.mark.skipif(not refh.available("cpu"), reason="reference not built (oracle/_ref)")
+@pytest.mark.parametrize("maker,repeats", [(lambda: scenes.config1(1000), 2), (lambda: scenes.config1(40), 3),
+                                           (lambda: scenes.molecule(cells=1), 1)])
+def test_repeated_compaction_matches_reference_live(maker, repeats):
+    """The reference keeps its per-level maps across compactBoxes(true) calls (boxes list their children again, light ids of
+    the first box are read as box keys one level down, GPUKernel.cpp:1041-1083, :1160-1260); the sorted-merge build here must
+    leave the same arrays behind, call after call.  (Sizes stay small: every repetition multiplies the reference's box count
+    and its fixed 2.5 M arrays are not bounds-checked on this path.)"""
+    sc = maker()
+    si = wire.default_scene_info(64, 48)
+    r = refh.RefScene(si, "cpu"); sc.replay(r)
+    h = host.SceneHost(si); sc.replay(h)
+    for _ in range(repeats):
+        nr, nh = r.compact_boxes(True), h.compact_boxes(True)
+        a, b = r.arrays(), h.arrays()
+        assert nr == nh
+        for k in ("boxes", "primitives", "lamps"):
+            assert np.array_equal(a[k], b[k]), k
+    r.close(); h.close()
+
+
 def test_skip_counts_are_consistent():
     sc = scenes.config1(500)
     h = host.SceneHost(wire.default_scene_info(64, 48)); n = sc.replay(h); a = h.arrays(); h.close()
