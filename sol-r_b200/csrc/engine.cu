@@ -450,6 +450,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
     cnt.rays = 0;
     const int q = passQueue(pass);
     const unsigned int count = cP.queueCounters[2 * q];
+    const bool fuseTail = (unsigned long long)count * 100ull <= (unsigned long long)gridDim.x * blockDim.x * (unsigned long long)cP.fuseTailPercent;
     while (true)
     {
         unsigned int base = 0;
@@ -476,7 +477,26 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
         GlobalColors C;
         C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
         pathPass(s, C, pass, has, index, f3(0.f, 0.f, 0.f), 0, cnt, separateWalk ? &hit : nullptr);
-        routePath(has, s, C, pass, slot, index);
+        if (!fuseTail)
+        {
+            routePath(has, s, C, pass, slot, index);
+            __syncwarp();
+            continue;
+        }
+        // Few paths left (at most one batch per resident warp: deep passes, small frames, a 1/8 share of a frame): another
+        // launch per pass would cost its tail and a round trip of the path through memory for nothing, since there are no
+        // other paths to fill the lanes with.  The warp keeps its paths in registers to the end of their ray trees, the way
+        // k_render does; the launches of the remaining passes find empty queues.
+        bool live = has;
+        for (int p = pass;; ++p)
+        {
+            const bool cont = live && s.carryon && s.rayLength < cSI.viewDistance && p + 1 < cP.maxIteration;
+            routePath(live && !cont, s, C, p, slot, index); // ends here: reflected-ray stage or pixel
+            live = cont;
+            if (!__any_sync(FULL_MASK, live)) break;
+            if (separateWalk && live) hit = closestHitOrderIndependent(s.curO, s.curT, p + 1, s.currentMaterialId);
+            pathPass(s, C, p + 1, live, index, f3(0.f, 0.f, 0.f), 0, cnt, separateWalk ? &hit : nullptr);
+        }
         __syncwarp();
     }
     flushCounters(cnt.rays, 0);
@@ -1297,6 +1317,7 @@ struct SahBuilder
 
 int g_useWide = 1;
 int g_useUnordered = 1;
+int g_fuseTailPercent = 300; // k_stage_pass carries its paths to the end in registers when the queue holds at most this share of the resident lanes (0: never)
 int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: also the closest-hit walks in their own kernel
 int g_traceCtasPerSM = 0; // experiment: resident CTAs per SM for the trace-queue kernel (0 = occupancy maximum)
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
@@ -1350,6 +1371,7 @@ void b200_set_option(int key, int value)
     else if (key == 5) g_useBackward = value != 0;
     else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value;
     else if (key == 7 && value >= 0) g_traceCtasPerSM = value;
+    else if (key == 8 && value >= 0) g_fuseTailPercent = value;
     else latch(-11, "b200_set_option", "unknown option");
 }
 void b200_set_partition(int rank, int world)
@@ -1833,6 +1855,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.tilesY = (si.size.y + TILE_H - 1) / TILE_H;
     const int nbTiles = P.tilesX * P.tilesY;
     P.rank = G.rank; P.worldSize = G.world;
+    P.fuseTailPercent = g_fuseTailPercent;
     P.packetMask = (G.boxLayoutUsed == 2) ? g_packetMask : 0; // packets need the ordered BVH (only leaf tests observable)
     P.nbLocalTiles = (nbTiles - G.rank + G.world - 1) / G.world;
 

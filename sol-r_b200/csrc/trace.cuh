@@ -76,6 +76,7 @@ struct RenderParams
     unsigned long long* workCounters; // [0] rays, [1] pixels
     int tilesX, tilesY, nbLocalTiles;
     int rank, worldSize;
+    int fuseTailPercent; // k_stage_pass: queues up to this share of the resident lanes are carried to the end in registers
     int packetMask; // which walks run warp-synchronously: bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow
     // staged rendering (engine.cu "staged kernels"): path state parked between passes, one array per word / per pass
     float* pathWords;          // [PATH_WORDS][pathStride]
