@@ -385,3 +385,40 @@ def test_drivers_produce_identical_frames(cfg):
         assert np.array_equal(post.view(np.uint32), out[0][2].view(np.uint32))
         assert np.array_equal(bm, out[0][0])
         assert rays == out[0][3]
+
+
+def test_small_queue_passes_in_registers_give_identical_frames():
+    """Option key 8: a bounce pass whose queue is small carries its paths to the end of their ray trees in registers instead
+    of parking them for another launch per pass.  Never (0), always (a huge percentage) and the default must agree bit for bit
+    with each other — ids, float accumulation buffer, RGB8, ray count — over deepening and accumulating frames (iterations 10
+    and up run ten passes)."""
+    W, H = 640, 360
+    sc = scenes.molecule(cells=3)
+    si = wire.default_scene_info(W, H, graphics_level=wire.GL_FULL, nb_ray_iterations=3)
+    si.maxPathTracingIterations = 13
+    h = host.SceneHost(si)
+    sc.replay(h)
+    a = h.arrays()
+    h.close()
+    rnd = gs.randoms(43)
+    out = []
+    for percent in (0, 300, 1 << 20):
+        e = engine.Engine(si)
+        try:
+            e.set_option(8, percent)
+            e.upload(a, randoms=rnd)
+            for it in (0, 1, 2, 10, 11, 12):
+                si.pathTracingIteration = it
+                e.render(si, sc.eye, sc.target, sc.angles)
+            bm, ids = e.readback(si)
+            post = e.read_post_buffer(si)
+            rays, _ = e.counters(reset=True)
+            out.append((bm.copy(), ids.copy(), post.copy(), rays))
+        finally:
+            e.set_option(8, 300)
+            e.close()
+    for bm, ids, post, rays in out[1:]:
+        assert np.array_equal(ids, out[0][1])
+        assert np.array_equal(post.view(np.uint32), out[0][2].view(np.uint32))
+        assert np.array_equal(bm, out[0][0])
+        assert rays == out[0][3]
