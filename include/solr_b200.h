@@ -76,8 +76,8 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
  *         (GeometryIntersections.cuh:316-325) (1, default); 0 drops them (not reference-exact; for measurement).
  * key 6 = staged rendering: one launch per bounce pass over a compacted queue of the paths still alive (1, default, used for
  *         the one-ray-tree-per-pixel cameras) or the single persistent kernel for every camera (0).
- * key 8 = a bounce pass whose queue holds at most this percentage of the GPU's resident lanes carries its paths to the end of
- *         their ray trees in registers instead of queueing them for one more launch per pass (default 300; 0 = never). */
+ * key 8 = bounce pass p whose queue holds at most p times this percentage of the GPU's resident lanes carries its paths to the
+ *         end of their ray trees in registers instead of queueing them for one more launch per pass (default 300; 0 = never). */
 void b200_set_option(int key, int value);
 /* Multi-GPU frame split: this process renders tiles t with t % worldSize == rank (interleaved 8x4-pixel
  * tiles). Non-owned pixels of the device bitmap/ids stay zero so frames merge by summation. */

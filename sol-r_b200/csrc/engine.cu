@@ -450,7 +450,9 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
     cnt.rays = 0;
     const int q = passQueue(pass);
     const unsigned int count = cP.queueCounters[2 * q];
-    const bool fuseTail = (unsigned long long)count * 100ull <= (unsigned long long)gridDim.x * blockDim.x * (unsigned long long)cP.fuseTailPercent;
+    // the deeper the pass, the fewer passes remain to carry finished lanes through: the bound grows with the pass number
+    const bool fuseTail = (unsigned long long)count * 100ull <=
+                          (unsigned long long)gridDim.x * blockDim.x * (unsigned long long)cP.fuseTailPercent * (unsigned long long)pass;
     while (true)
     {
         unsigned int base = 0;
@@ -1317,7 +1319,7 @@ struct SahBuilder
 
 int g_useWide = 1;
 int g_useUnordered = 1;
-int g_fuseTailPercent = 300; // k_stage_pass carries its paths to the end in registers when the queue holds at most this share of the resident lanes (0: never)
+int g_fuseTailPercent = 300; // k_stage_pass(p) carries its paths to the end in registers when the queue holds at most p times this share of the resident lanes (0: never)
 int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: also the closest-hit walks in their own kernel
 int g_traceCtasPerSM = 0; // experiment: resident CTAs per SM for the trace-queue kernel (0 = occupancy maximum)
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks

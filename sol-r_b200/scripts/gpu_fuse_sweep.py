@@ -16,7 +16,7 @@ for cfg in sys.argv[1:] or ["c2", "c4"]:
     for rank, world in ((0, 1), (0, 8)):
         e = engine.Engine(si, limits=(W, H), rank=rank, world=world)
         e.upload(a, randoms=np.zeros(W * H, np.float32))
-        for pct in (0, 100, 300, 1000):
+        for pct in (0, 150, 300, 600):
             e.set_option(8, pct)
             ms = []
             for rep in range(3):
