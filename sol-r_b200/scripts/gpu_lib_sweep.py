@@ -1,4 +1,4 @@
-"""Times build variants of the walk (csrc/libvar_*.so) on config 2 — one subprocess per variant, scene arrays built once (GPU box).
+"""Times build variants of the engine (csrc/libvar_*.so, built by hand with extra -D flags) on config 2, whole frame and a 1/8 share — one subprocess per variant, scene arrays built once (GPU box).
 Prints ms per frame (min of 4), checksums of bitmap and ids (exactness across variants) and the debug counters."""
 import sys, os, subprocess, glob, pickle
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from _solr_b200_import import solr_b200  # noqa
 from solr_b200 import wire, scenes, engine, host
-CACHE = "/tmp/coop_sweep_c2.pkl"
+CACHE = "/tmp/lib_sweep_c2.pkl"
 W, H = 1920, 1080
 if len(sys.argv) > 2 and sys.argv[1] == "child":
     import ctypes as C
