@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_render()
         if (lane == 0) k = atomicAdd(cP.tileCounter, 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= (unsigned int)cP.nbLocalTiles) break;
-        const int tile = k * cP.worldSize + cP.rank; // interleaved tile ownership across GPUs
+        const int tile = cP.tileOrder ? cP.tileOrder[k] : k * cP.worldSize + cP.rank; // interleaved tile ownership across GPUs
         const int tx = tile % cP.tilesX, ty = tile / cP.tilesX;
         const int x = tx * TILE_W + (lane & (TILE_W - 1));
         const int y = ty * TILE_H + (lane / TILE_W);
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PRIMARY) k_stage_primary
         if (lane == 0) k = atomicAdd(cP.tileCounter, 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= (unsigned int)cP.nbLocalTiles) break;
-        const int tile = k * cP.worldSize + cP.rank;
+        const int tile = cP.tileOrder ? cP.tileOrder[k] : k * cP.worldSize + cP.rank;
         const int tx = tile % cP.tilesX, ty = tile / cP.tilesX;
         const int xIn = tx * TILE_W + (lane & (TILE_W - 1));
         const int yIn = ty * TILE_H + (lane / TILE_W);
@@ -810,6 +810,7 @@ struct Engine
     b200_PostProcessingBuffer* dPost = nullptr; int4* dIds = nullptr; unsigned char* dBitmap = nullptr;
     unsigned char* dPeerBitmap = nullptr; // the root GPU's bitmap mapped into this process (b200_peer_frame_open), else null
     unsigned int* dTileCounter = nullptr; unsigned long long* dWork = nullptr;
+    int* dTileOrder = nullptr; size_t capTileOrder = 0; int tileOrderKey[4] = {0, 0, 0, 0}; // tilesX, tilesY, rank, world the table was made for
     size_t pixelsCap = 0;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool timed = false;
@@ -1319,6 +1320,7 @@ struct SahBuilder
 
 int g_useWide = 1;
 int g_useUnordered = 1;
+int g_tileOrder = 0; // order in which a GPU's own tiles are handed out: 0 row-major, 1 along a Z-order curve (neighbouring warps work on neighbouring tiles in both directions)
 int g_fuseTailPercent = 300; // k_stage_pass(p) carries its paths to the end in registers when the queue holds at most p times this share of the resident lanes (0: never)
 int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: also the closest-hit walks in their own kernel
 int g_traceCtasPerSM = 0; // experiment: resident CTAs per SM for the trace-queue kernel (0 = occupancy maximum)
@@ -1374,6 +1376,7 @@ void b200_set_option(int key, int value)
     else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value;
     else if (key == 7 && value >= 0) g_traceCtasPerSM = value;
     else if (key == 8 && value >= 0) g_fuseTailPercent = value;
+    else if (key == 9 && (value == 0 || value == 1)) g_tileOrder = value;
     else latch(-11, "b200_set_option", "unknown option");
 }
 void b200_set_partition(int rank, int world)
@@ -1462,7 +1465,7 @@ void b200_finalize_scene(b200_int2)
     freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
-    freeDev(G.dTileCounter); freeDev(G.dWork);
+    freeDev(G.dTileCounter); freeDev(G.dWork); freeDev(G.dTileOrder); G.capTileOrder = 0; G.tileOrderKey[0] = 0;
     freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters); freeDev(G.dHitWords);
     G.pathStride = 0; G.pathIterations = 0;
     if (G.evStart) { cudaEventDestroy(G.evStart); G.evStart = nullptr; }
@@ -1860,6 +1863,27 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.fuseTailPercent = g_fuseTailPercent;
     P.packetMask = (G.boxLayoutUsed == 2) ? g_packetMask : 0; // packets need the ordered BVH (only leaf tests observable)
     P.nbLocalTiles = (nbTiles - G.rank + G.world - 1) / G.world;
+    P.tileOrder = nullptr;
+    if (g_tileOrder == 1 && P.nbLocalTiles > 0)
+    {
+        // this GPU's tiles (t % world == rank, as ever) sorted along a Z-order curve over the tile grid
+        if (G.tileOrderKey[0] != P.tilesX || G.tileOrderKey[1] != P.tilesY || G.tileOrderKey[2] != G.rank || G.tileOrderKey[3] != G.world)
+        {
+            std::vector<std::pair<unsigned long long, int>> order;
+            order.reserve(P.nbLocalTiles);
+            auto spread = [](unsigned int v) { unsigned long long x = v; x = (x | (x << 16)) & 0x0000FFFF0000FFFFull; x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+                                               x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full; x = (x | (x << 2)) & 0x3333333333333333ull; x = (x | (x << 1)) & 0x5555555555555555ull; return x; };
+            for (int t = G.rank; t < nbTiles; t += G.world) order.push_back({spread(t % P.tilesX) | (spread(t / P.tilesX) << 1), t});
+            std::sort(order.begin(), order.end());
+            std::vector<int> table(order.size());
+            for (size_t i = 0; i < order.size(); ++i) table[i] = order[i].second;
+            if (table.size() > G.capTileOrder) { freeDev(G.dTileOrder); CK(cudaMalloc(&G.dTileOrder, table.size() * sizeof(int))); G.capTileOrder = table.size(); }
+            CK(cudaMemcpyAsync(G.dTileOrder, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+            CK(cudaStreamSynchronize(G.stream));
+            G.tileOrderKey[0] = P.tilesX; G.tileOrderKey[1] = P.tilesY; G.tileOrderKey[2] = G.rank; G.tileOrderKey[3] = G.world;
+        }
+        P.tileOrder = G.dTileOrder;
+    }
 
     // staged rendering where a pixel owns one ray tree and more than one pass can happen
     int maxIteration = (si.graphicsLevel < B200_GL_REFLECTIONS) ? 1 : si.nbRayIterations + si.pathTracingIteration;

@@ -73,6 +73,7 @@ struct RenderParams
     int4* ids;
     unsigned char* bitmap;
     unsigned int* tileCounter;        // atomic tile queue head
+    const int* tileOrder;             // the k-th tile this GPU hands out (null: k * worldSize + rank)
     unsigned long long* workCounters; // [0] rays, [1] pixels
     int tilesX, tilesY, nbLocalTiles;
     int rank, worldSize;

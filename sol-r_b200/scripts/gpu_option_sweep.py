@@ -1,12 +1,13 @@
-"""Option 8 (bounce passes carried to the end in registers when their queue is small) on configs 2 and 4, whole frame and a 1/8
-share: ms per frame and checksums (GPU box)."""
+"""One engine option (b200_set_option key, values) on configs 2 and 4, whole frame and a 1/8 share: ms per frame and checksums
+(GPU box).  usage: gpu_option_sweep.py KEY V1,V2,... [c2] [c4]   e.g. 8 0,150,300,600 (small-queue passes), 9 0,1 (tile order)"""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from _solr_b200_import import solr_b200  # noqa
 from solr_b200 import wire, scenes, engine, host
-for cfg in sys.argv[1:] or ["c2", "c4"]:
+KEY = int(sys.argv[1]); VALUES = [int(v) for v in sys.argv[2].split(",")]
+for cfg in sys.argv[3:] or ["c2", "c4"]:
     if cfg == "c2":
         sc, (W, H), iters, cap = scenes.config2(), (1920, 1080), [0], None
     else:
@@ -16,8 +17,8 @@ for cfg in sys.argv[1:] or ["c2", "c4"]:
     for rank, world in ((0, 1), (0, 8)):
         e = engine.Engine(si, limits=(W, H), rank=rank, world=world)
         e.upload(a, randoms=np.zeros(W * H, np.float32))
-        for pct in (0, 150, 300, 600):
-            e.set_option(8, pct)
+        for pct in VALUES:
+            e.set_option(KEY, pct)
             ms = []
             for rep in range(3):
                 for it in iters:
@@ -25,6 +26,6 @@ for cfg in sys.argv[1:] or ["c2", "c4"]:
                     e.render(si, sc.eye, sc.target, sc.angles); e.synchronize(); ms.append(e.last_render_ms())
             bm, ids = e.readback(si)
             n = len(iters)
-            print("%s part %d/%d fuse %4d%%  ms/frame %.3f  checksum %d %d" % (cfg, rank, world, pct, sum(ms[n:]) / len(ms[n:]),
+            print("%s part %d/%d option %d = %4d  ms/frame %.3f  checksum %d %d" % (cfg, rank, world, KEY, pct, sum(ms[n:]) / len(ms[n:]),
                   int(bm.astype(np.int64).sum()), int(ids[..., 0].astype(np.int64).sum())), flush=True)
         e.close()
