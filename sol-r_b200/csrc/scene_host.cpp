@@ -64,6 +64,7 @@ SceneHost::SceneHost(const b200_SceneInfo& sceneInfo)
 
 SceneHost::~SceneHost()
 {
+    dropFlat();
     if (m_deviceInitialised)
     {
         b200_int2 occ = {1, 1};
@@ -281,6 +282,37 @@ void SceneHost::realignTexturesAndMaterials()
 // ---------------------------------------------------------------------------------------------------
 // grid hierarchy (GPUKernel.cpp:741-1083)
 // ---------------------------------------------------------------------------------------------------
+// the box one primitive contributes to its cell (GPUKernel.cpp:752-826)
+static void primitiveExtent(const HostPrimitive& primitive, b200_float3& p0, b200_float3& p1)
+{
+    b200_float3 corner0, corner1;
+    switch (primitive.type)
+    {
+    case B200_PT_TRIANGLE: corner0 = min3(primitive.p0, primitive.p1, primitive.p2); corner1 = max3(primitive.p0, primitive.p1, primitive.p2); break;
+    case B200_PT_CYLINDER: corner0 = min2(primitive.p0, primitive.p1); corner1 = max2(primitive.p0, primitive.p1); break;
+    default: corner0 = primitive.p0; corner1 = primitive.p0; break;
+    }
+    p0.x = (corner0.x <= corner1.x) ? corner0.x : corner1.x;
+    p0.y = (corner0.y <= corner1.y) ? corner0.y : corner1.y;
+    p0.z = (corner0.z <= corner1.z) ? corner0.z : corner1.z;
+    p1.x = (corner0.x > corner1.x) ? corner0.x : corner1.x;
+    p1.y = (corner0.y > corner1.y) ? corner0.y : corner1.y;
+    p1.z = (corner0.z > corner1.z) ? corner0.z : corner1.z;
+    switch (primitive.type)
+    {
+    case B200_PT_CYLINDER:
+    case B200_PT_SPHERE:
+    case B200_PT_CONE:
+        p0.x -= primitive.size.x; p0.y -= primitive.size.x; p0.z -= primitive.size.x;
+        p1.x += primitive.size.x; p1.y += primitive.size.x; p1.z += primitive.size.x;
+        break;
+    default:
+        p0.x -= primitive.size.x; p0.y -= primitive.size.y; p0.z -= primitive.size.z;
+        p1.x += primitive.size.x; p1.y += primitive.size.y; p1.z += primitive.size.z;
+        break;
+    }
+}
+
 // m_primitives[id] without the tree descent: the hierarchy build asks once per primitive and level-0 box, the flatten once more.
 HostPrimitive& SceneHost::primitiveById(unsigned int id)
 {
@@ -291,39 +323,14 @@ HostPrimitive& SceneHost::primitiveById(unsigned int id)
 bool SceneHost::updateBoundingBox(HostBox& box) // :741-839
 {
     bool result = false;
-    b200_float3 corner0, corner1;
     box.parameters[0] = v3(1000000, 1000000, 1000000);
     box.parameters[1] = v3(-1000000, -1000000, -1000000);
     for (const auto& p : box.primitives)
     {
         HostPrimitive& primitive = primitiveById((unsigned)p);
         result = (m_hMaterials[primitive.materialId].innerIllumination.x != 0.f);
-        switch (primitive.type)
-        {
-        case B200_PT_TRIANGLE: corner0 = min3(primitive.p0, primitive.p1, primitive.p2); corner1 = max3(primitive.p0, primitive.p1, primitive.p2); break;
-        case B200_PT_CYLINDER: corner0 = min2(primitive.p0, primitive.p1); corner1 = max2(primitive.p0, primitive.p1); break;
-        default: corner0 = primitive.p0; corner1 = primitive.p0; break;
-        }
         b200_float3 p0, p1;
-        p0.x = (corner0.x <= corner1.x) ? corner0.x : corner1.x;
-        p0.y = (corner0.y <= corner1.y) ? corner0.y : corner1.y;
-        p0.z = (corner0.z <= corner1.z) ? corner0.z : corner1.z;
-        p1.x = (corner0.x > corner1.x) ? corner0.x : corner1.x;
-        p1.y = (corner0.y > corner1.y) ? corner0.y : corner1.y;
-        p1.z = (corner0.z > corner1.z) ? corner0.z : corner1.z;
-        switch (primitive.type)
-        {
-        case B200_PT_CYLINDER:
-        case B200_PT_SPHERE:
-        case B200_PT_CONE:
-            p0.x -= primitive.size.x; p0.y -= primitive.size.x; p0.z -= primitive.size.x;
-            p1.x += primitive.size.x; p1.y += primitive.size.x; p1.z += primitive.size.x;
-            break;
-        default:
-            p0.x -= primitive.size.x; p0.y -= primitive.size.y; p0.z -= primitive.size.z;
-            p1.x += primitive.size.x; p1.y += primitive.size.y; p1.z += primitive.size.z;
-            break;
-        }
+        primitiveExtent(primitive, p0, p1);
         if (p0.x < box.parameters[0].x) box.parameters[0].x = p0.x;
         if (p0.y < box.parameters[0].y) box.parameters[0].y = p0.y;
         if (p0.z < box.parameters[0].z) box.parameters[0].z = p0.z;
@@ -361,6 +368,7 @@ void SceneHost::updateOutterBoundingBox(HostBox& outterBox, int depth) // :841-8
 
 void SceneHost::resetBoxes(bool resetPrimitives) // :894-901
 {
+    materialiseBoxes();
     if (resetPrimitives)
         for (size_t i = 0; i < m_boundingBoxes[0].size(); ++i) resetBox(m_boundingBoxes[0][(unsigned)i], resetPrimitives);
     else
@@ -468,6 +476,357 @@ void SceneHost::processOutterBoxes(const int boxSize, const int depth) // :994-1
     for (auto& box : m_boundingBoxes[depth]) updateOutterBoundingBox(box.second, depth - 1);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// flat build: the first compaction of a fresh container without node-based containers
+// ---------------------------------------------------------------------------------------------------
+// GPUKernel::compactBoxes builds one std::map of boxes per level and flattens them by recursion with a map lookup per box
+// (GPUKernel.cpp:919-1149).  On a fresh container everything it computes is a function of sorted sequences: a level's boxes
+// are the distinct cell keys of the level below in ascending order, a box lists its children in ascending key order, its
+// bounds are the min / max over them.  So each level is one stable sort of (cell key, child) pairs and one pass over the runs,
+// the flattening a recursion over index ranges — the same arrays, byte for byte (tests/test_scene_host.py compares both paths
+// and the reference's own builder), in a form that is also the outline of a GPU build (sort by key, segmented reduce, scan).
+// What the reference leaves behind in its maps for later calls — including the empty box its first resetBox() creates at
+// level 2, and the empty boxes its look-ups of light ids as box keys create one level below the top — is materialised from
+// the flat arrays if and when a later call needs it.
+struct SceneHost::FlatHierarchy
+{
+    struct Level
+    {
+        struct Box { b200_float3 lo, hi; unsigned int first, count; }; // children of the box: items[first .. first + count)
+        std::vector<unsigned int> keys;         // ascending
+        std::vector<Box> boxes;                 // one 32-byte record per box: the flattening touches one cache line per box
+        std::vector<b200_float3> center;
+        std::vector<long> items;                // level 0: primitive ids; level d: keys of boxes of level d - 1
+        std::vector<unsigned int> itemIndex;    // level d >= 1: where that box is in level d - 1
+        void reserve(size_t nBoxes, size_t nItems, bool index)
+        {
+            keys.reserve(nBoxes); boxes.reserve(nBoxes); center.reserve(nBoxes); items.reserve(nItems);
+            if (index) itemIndex.reserve(nItems);
+        }
+        void add(unsigned int key, const b200_float3& lo, const b200_float3& hi, unsigned int first)
+        {
+            keys.push_back(key);
+            boxes.push_back({lo, hi, first, (unsigned int)items.size() - first});
+            center.push_back(b200_float3{(lo.x + hi.x) / 2.f, (lo.y + hi.y) / 2.f, (lo.z + hi.z) / 2.f});
+        }
+    };
+    std::vector<Level> levels;                  // 0 .. depth
+    std::vector<long> lights;                   // primitives of the first box of the top level
+    std::vector<unsigned int> lightKeyIndex;    // per light id: its index in level depth - 1 when read as a box key, or ~0u
+    b200_float3 lightsLo, lightsHi, lightsCenter;
+    unsigned int oldDepth = 0;                  // level of the empty box resetBox() created before the build
+    unsigned int depth = 0;
+};
+
+void SceneHost::dropFlat()
+{
+    delete m_flat;
+    m_flat = nullptr;
+}
+
+bool SceneHost::flatBuildApplies() const
+{
+    if (m_flat || !m_useFlatBuild) return false;
+    for (const auto& level : m_boundingBoxes)
+        if (!level.empty()) return false;
+    unsigned int depth = 0;
+    for (int nb = static_cast<int>(m_primitives.size()); nb > 2; nb /= 4) ++depth;
+    if (m_treeDepth < 1 || m_treeDepth >= depth) return false;        // the empty box of the old top level lies inside the new tree
+    if (m_primitiveTable.size() != m_primitives.size()) return false; // ids 0 .. n-1
+    bool light = false;
+    for (const auto& prim : m_primitives)
+        if (m_hMaterials[prim.second.materialId].innerIllumination.x != 0.f) { light = true; break; }
+    return light; // without a light the reference flattens its first ordinary box as if it held the lights
+}
+
+bool SceneHost::flatBuild()
+{
+    FlatHierarchy* F = new FlatHierarchy();
+    m_flat = F;
+    const float vd = m_sceneInfo.viewDistance;
+    const size_t n = m_primitives.size();
+    F->oldDepth = m_treeDepth;
+    const unsigned int F_oldDepth = m_treeDepth;
+    const int gridGranularity = 2, gridDivider = 4;
+    unsigned int depth = 0;
+    for (int nb = static_cast<int>(n); nb > gridGranularity; nb /= gridDivider) ++depth;
+    F->depth = depth;
+    F->levels.resize(depth + 1);
+
+    struct Entry { unsigned int key; unsigned int child; };
+    std::vector<Entry> entries;
+    // ---- level 0: primitives into cells (processBoxes) ----
+    {
+        const int boxSize = AABB_MAGIC_NUMBER;
+        b200_float3 boxSteps;
+        boxSteps.x = (m_maxPos.x - m_minPos.x) / boxSize;
+        boxSteps.y = (m_maxPos.y - m_minPos.y) / boxSize;
+        boxSteps.z = (m_maxPos.z - m_minPos.z) / boxSize;
+        boxSteps.x = (boxSteps.x == 0.f) ? 1 : boxSteps.x;
+        boxSteps.y = (boxSteps.y == 0.f) ? 1 : boxSteps.y;
+        boxSteps.z = (boxSteps.z == 0.f) ? 1 : boxSteps.z;
+        entries.reserve(n);
+        std::vector<unsigned char> isLight(n, 0);
+        for (unsigned int p = 0; p < n; ++p)
+        {
+            const HostPrimitive& primitive = *m_primitiveTable[p];
+            const b200_float3& center = primitive.p0;
+            unsigned int X = static_cast<int>((center.x - m_minPos.x) / boxSteps.x);
+            unsigned int Y = static_cast<int>((center.y - m_minPos.y) / boxSteps.y);
+            unsigned int Z = static_cast<int>((center.z - m_minPos.z) / boxSteps.z);
+            unsigned int B = 1 + 1000 * (X * boxSize * boxSize + Y * boxSize + Z);
+            if (m_hMaterials[primitive.materialId].innerIllumination.x != 0.f) { isLight[p] = 1; F->lights.push_back(p); }
+            entries.push_back({B, p});
+        }
+        std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+        FlatHierarchy::Level& L = F->levels[0];
+        L.reserve(entries.size(), entries.size(), false);
+        for (size_t i = 0; i < entries.size();)
+        {
+            size_t j = i;
+            const unsigned int first = (unsigned int)L.items.size();
+            b200_float3 lo = v3(1000000, 1000000, 1000000), hi = v3(-1000000, -1000000, -1000000);
+            for (; j < entries.size() && entries[j].key == entries[i].key; ++j)
+            {
+                if (isLight[entries[j].child]) continue; // the cell exists, the light itself goes to the top level
+                L.items.push_back(entries[j].child);
+                b200_float3 p0, p1;
+                primitiveExtent(*m_primitiveTable[entries[j].child], p0, p1);
+                if (p0.x < lo.x) lo.x = p0.x;
+                if (p0.y < lo.y) lo.y = p0.y;
+                if (p0.z < lo.z) lo.z = p0.z;
+                if (p1.x > hi.x) hi.x = p1.x;
+                if (p1.y > hi.y) hi.y = p1.y;
+                if (p1.z > hi.z) hi.z = p1.z;
+            }
+            L.add(entries[i].key, lo, hi, first);
+            i = j;
+        }
+    }
+    // ---- levels 1 .. depth: boxes of the level below into coarser cells (processOutterBoxes) ----
+    int boxSize = static_cast<int>(n);
+    for (unsigned int d = 1; d <= depth; ++d, boxSize /= gridDivider)
+    {
+        const FlatHierarchy::Level& below = F->levels[d - 1];
+        FlatHierarchy::Level& L = F->levels[d];
+        b200_float3 boxSteps;
+        boxSteps.x = (m_maxPos.x - m_minPos.x) / boxSize;
+        boxSteps.y = (m_maxPos.y - m_minPos.y) / boxSize;
+        boxSteps.z = (m_maxPos.z - m_minPos.z) / boxSize;
+        boxSteps.x = (boxSteps.x == 0.f) ? 1 : boxSteps.x;
+        boxSteps.y = (boxSteps.y == 0.f) ? 1 : boxSteps.y;
+        boxSteps.z = (boxSteps.z == 0.f) ? 1 : boxSteps.z;
+        entries.clear();
+        entries.reserve(below.keys.size());
+        for (unsigned int c = 0; c < below.keys.size(); ++c)
+        {
+            const b200_float3& center = below.center[c];
+            int X = static_cast<int>((center.x - m_minPos.x) / boxSteps.x);
+            int Y = static_cast<int>((center.y - m_minPos.y) / boxSteps.y);
+            int Z = static_cast<int>((center.z - m_minPos.z) / boxSteps.z);
+            const uint32_t bs = (uint32_t)boxSize;
+            uint32_t Bu = (uint32_t)X * bs * bs + (uint32_t)Y * bs + (uint32_t)Z;
+            Bu += 1; // key 0 holds the lights
+            entries.push_back({Bu, c});
+        }
+        std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+        if (!entries.empty() && entries[0].key == 0u)
+        {
+            // a cell key wrapped onto the key of the lights box: leave this scene to the literal path
+            delete F;
+            m_flat = nullptr;
+            m_treeDepth = F_oldDepth;
+            return false;
+        }
+        // the empty box resetBox() left at key 0 of the old top level is there before the level's own boxes
+        L.reserve(entries.size() + 1, entries.size(), true);
+        if (d == F->oldDepth) L.add(0u, v3(vd, vd, vd), v3(-vd, -vd, -vd), 0u);
+        for (size_t i = 0; i < entries.size();)
+        {
+            size_t j = i;
+            const unsigned int first = (unsigned int)L.items.size();
+            b200_float3 lo = v3(vd, vd, vd), hi = v3(-vd, -vd, -vd);
+            for (; j < entries.size() && entries[j].key == entries[i].key; ++j)
+            {
+                const unsigned int c = entries[j].child;
+                L.items.push_back((long)below.keys[c]);
+                L.itemIndex.push_back(c);
+                const FlatHierarchy::Level::Box& cb = below.boxes[c];
+                if (lo.x > cb.lo.x) lo.x = cb.lo.x;
+                if (lo.y > cb.lo.y) lo.y = cb.lo.y;
+                if (lo.z > cb.lo.z) lo.z = cb.lo.z;
+                if (hi.x < cb.hi.x) hi.x = cb.hi.x;
+                if (hi.y < cb.hi.y) hi.y = cb.hi.y;
+                if (hi.z < cb.hi.z) hi.z = cb.hi.z;
+            }
+            L.add(entries[i].key, lo, hi, first);
+            i = j;
+        }
+    }
+    // ---- the lights box (key 0 of the top level): its "children" are light ids read as box keys one level down ----
+    {
+        const FlatHierarchy::Level& below = F->levels[depth - 1];
+        b200_float3 lo = v3(vd, vd, vd), hi = v3(-vd, -vd, -vd);
+        for (long id : F->lights)
+        {
+            const auto it = std::lower_bound(below.keys.begin(), below.keys.end(), (unsigned int)id);
+            const bool found = it != below.keys.end() && *it == (unsigned int)id;
+            const unsigned int idx = found ? (unsigned int)(it - below.keys.begin()) : ~0u;
+            F->lightKeyIndex.push_back(idx);
+            const b200_float3 blo = found ? below.boxes[idx].lo : v3(0.f, 0.f, 0.f), bhi = found ? below.boxes[idx].hi : v3(0.f, 0.f, 0.f);
+            if (lo.x > blo.x) lo.x = blo.x;
+            if (lo.y > blo.y) lo.y = blo.y;
+            if (lo.z > blo.z) lo.z = blo.z;
+            if (hi.x < bhi.x) hi.x = bhi.x;
+            if (hi.y < bhi.y) hi.y = bhi.y;
+            if (hi.z < bhi.z) hi.z = bhi.z;
+        }
+        F->lightsLo = lo; F->lightsHi = hi;
+        F->lightsCenter = v3((lo.x + hi.x) / 2.f, (lo.y + hi.y) / 2.f, (lo.z + hi.z) / 2.f);
+    }
+    m_treeDepth = depth;
+    return true;
+}
+
+void SceneHost::flatRecurse(const int depth, const unsigned int j) // recursiveDataStreamToGPU for one box
+{
+    const FlatHierarchy::Level& L = m_flat->levels[depth];
+    const FlatHierarchy::Level::Box& B = L.boxes[j];
+    const unsigned int begin = B.first, end = B.first + B.count;
+    if (begin == end || (size_t)m_nbActiveBoxes >= m_maxBoxes) return;
+    const int boxIndex = m_nbActiveBoxes;
+    b200_BoundingBox out;
+    memset(&out, 0, sizeof(out));
+    out.parameters[0] = B.lo;
+    out.parameters[1] = B.hi;
+    out.nbPrimitives = (depth == 0) ? static_cast<int>(end - begin) : 0;
+    out.startIndex = (depth == 0) ? m_nbActivePrimitives : depth;
+    m_hBoundingBoxes.push_back(out);
+    ++m_nbActiveBoxes;
+    if (depth == 0)
+    {
+        for (unsigned int i = begin; i < end; ++i)
+        {
+            const long id = L.items[i];
+            if ((size_t)id < m_maxPrimitives && (size_t)m_nbActivePrimitives < m_maxPrimitives) emitPrimitive(id);
+        }
+    }
+    else
+        for (unsigned int i = begin; i < end; ++i) flatRecurse(depth - 1, L.itemIndex[i]);
+    m_hBoundingBoxes[boxIndex].indexForNextBox.x = (depth == 0) ? 1 : m_nbActiveBoxes - boxIndex;
+}
+
+void SceneHost::flatStream() // streamDataToGPU over the flat levels
+{
+    const FlatHierarchy& F = *m_flat;
+    m_primitivesTransfered = false;
+    m_nbActiveBoxes = 0; m_nbActivePrimitives = 0; m_nbActiveLamps = 0;
+    m_hBoundingBoxes.clear(); m_hPrimitives.clear(); m_hLamps.clear();
+    {
+        size_t boxes = 1;
+        for (const auto& L : F.levels) boxes += L.keys.size();
+        m_hBoundingBoxes.reserve(std::min(boxes, m_maxBoxes + 1));
+        m_hPrimitives.reserve(std::min(m_primitives.size(), m_maxPrimitives));
+    }
+    const float vd = m_sceneInfo.viewDistance;
+    const int maxDepth = (int)F.depth;
+    // box 0 of the top level holds the lights, with bounds +-viewDistance (:1177-1190)
+    {
+        const int boxIndex = m_nbActiveBoxes;
+        b200_BoundingBox out;
+        memset(&out, 0, sizeof(out));
+        m_lightInformationSize = 0;
+        m_lightInformation.clear();
+        out.parameters[0] = v3(-vd, -vd, -vd);
+        out.parameters[1] = v3(vd, vd, vd);
+        out.nbPrimitives = static_cast<int>(F.lights.size());
+        out.startIndex = 0;
+        m_hBoundingBoxes.push_back(out);
+        for (long id : F.lights)
+        {
+            emitPrimitive(id);
+            const HostPrimitive& primitive = primitiveById((unsigned)id);
+            const b200_Material& material = m_hMaterials[primitive.materialId];
+            b200_LightInformation li;
+            memset(&li, 0, sizeof(li));
+            li.primitiveId = (int)id;
+            li.materialId = primitive.materialId;
+            li.location = primitive.p0;
+            li.color.x = material.color.x; li.color.y = material.color.y; li.color.z = material.color.z;
+            li.color.w = material.innerIllumination.x;
+            if (m_lightInformationSize < B200_NB_MAX_LIGHTINFORMATIONS) m_lightInformation.push_back(li);
+            if (m_nbActiveLamps < NB_MAX_LAMPS) m_hLamps.push_back((int)id);
+            ++m_nbActiveLamps;
+            ++m_lightInformationSize;
+        }
+        ++m_nbActiveBoxes;
+        // the reference recurses into the lights box too, reading the light ids as keys of the level below
+        for (unsigned int idx : F.lightKeyIndex)
+            if (idx != ~0u) flatRecurse(maxDepth - 1, idx);
+        m_hBoundingBoxes[boxIndex].indexForNextBox.x = m_nbActiveBoxes - boxIndex;
+    }
+    const FlatHierarchy::Level& top = F.levels[maxDepth];
+    for (unsigned int j = 0; j < top.keys.size(); ++j)
+    {
+        const int boxIndex = m_nbActiveBoxes;
+        b200_BoundingBox out;
+        memset(&out, 0, sizeof(out));
+        out.parameters[0] = top.boxes[j].lo;
+        out.parameters[1] = top.boxes[j].hi;
+        out.nbPrimitives = 0;
+        out.startIndex = maxDepth;
+        m_hBoundingBoxes.push_back(out);
+        ++m_nbActiveBoxes;
+        for (unsigned int i = top.boxes[j].first; i < top.boxes[j].first + top.boxes[j].count; ++i) flatRecurse(maxDepth - 1, top.itemIndex[i]);
+        m_hBoundingBoxes[boxIndex].indexForNextBox.x = m_nbActiveBoxes - boxIndex;
+    }
+    if ((size_t)m_nbActivePrimitives != m_primitives.size())
+        fprintf(stderr, "[solr_b200] compactBoxes: lost primitives on the way... %d != %zu\n", m_nbActivePrimitives, m_primitives.size());
+}
+
+// The maps as the reference's own build would have left them, for whatever is called next.
+void SceneHost::materialiseBoxes()
+{
+    if (!m_flat) return;
+    FlatHierarchy* F = m_flat;
+    m_flat = nullptr;
+    std::vector<HostBox*> belowPtr, ptr;
+    for (unsigned int d = 0; d <= F->depth; ++d)
+    {
+        const FlatHierarchy::Level& L = F->levels[d];
+        auto& level = m_boundingBoxes[d];
+        ptr.assign(L.keys.size(), nullptr);
+        if (d == F->depth)
+        {
+            // the lights box: created by operator[] (all zero), bounds from the look-ups of its light ids
+            HostBox box;
+            memset(box.parameters, 0, sizeof(box.parameters));
+            box.parameters[0] = F->lightsLo; box.parameters[1] = F->lightsHi; box.center = F->lightsCenter;
+            box.indexForNextBox = 0;
+            box.primitives = F->lights;
+            level.emplace_hint(level.end(), 0u, std::move(box));
+        }
+        for (unsigned int j = 0; j < L.keys.size(); ++j)
+        {
+            HostBox box;
+            box.parameters[0] = L.boxes[j].lo; box.parameters[1] = L.boxes[j].hi; box.center = L.center[j];
+            box.indexForNextBox = (d == 0 || (d == F->oldDepth && L.keys[j] == 0u)) ? 1 : 0;
+            const unsigned int begin = L.boxes[j].first, end = begin + L.boxes[j].count;
+            box.primitives.assign(L.items.begin() + begin, L.items.begin() + end);
+            if (d > 0)
+                for (unsigned int i = begin; i < end; ++i) box.children.push_back(belowPtr[L.itemIndex[i]]);
+            auto it = level.emplace_hint(level.end(), L.keys[j], std::move(box));
+            ptr[j] = &it->second;
+        }
+        belowPtr.swap(ptr);
+    }
+    // light ids looked up as box keys one level below the top: a missing key was created empty by operator[]
+    for (size_t i = 0; i < F->lights.size(); ++i)
+        if (F->lightKeyIndex[i] == ~0u) m_boundingBoxes[F->depth - 1][(unsigned int)F->lights[i]];
+    delete F;
+}
+
 int SceneHost::compactBoxes(bool reconstructBoxes) // :1041-1083
 {
     m_primitivesTransfered = false;
@@ -477,6 +836,13 @@ int SceneHost::compactBoxes(bool reconstructBoxes) // :1041-1083
         m_primitiveTable.assign((size_t)m_primitives.rbegin()->first + 1, nullptr);
         for (auto& prim : m_primitives) m_primitiveTable[prim.first] = &prim.second;
     }
+    if (reconstructBoxes && flatBuildApplies() && flatBuild())
+    {
+        flatStream();
+        m_primitiveTable.clear();
+        return m_nbActiveBoxes;
+    }
+    materialiseBoxes();
     if (reconstructBoxes)
     {
         resetBox(m_boundingBoxes[m_treeDepth][0], true);
@@ -816,6 +1182,7 @@ void b200h_get_scene(void* h, b200h_Scene* out)
 void b200h_set_randoms(void* h, const float* r, long n, int timestamp) { static_cast<SceneHost*>(h)->setRandoms(r, (size_t)n, timestamp); }
 void b200h_set_capacity(void* h, long maxBoxes, long maxPrimitives) { static_cast<SceneHost*>(h)->setCapacity((size_t)maxBoxes, (size_t)maxPrimitives); }
 void b200h_set_limits(void* h, int w, int hh) { static_cast<SceneHost*>(h)->setLimits(w, hh); }
+void b200h_set_flat_build(void* h, int on) { static_cast<SceneHost*>(h)->setFlatBuild(on != 0); }
 void b200h_set_lazy_ids(void* h, int lazy) { static_cast<SceneHost*>(h)->setLazyIds(lazy != 0); }
 void b200h_set_partition(void* h, int rank, int world) { static_cast<SceneHost*>(h)->setPartition(rank, world); }
 void b200h_set_device(void* h, int device) { static_cast<SceneHost*>(h)->setDevice(device); }

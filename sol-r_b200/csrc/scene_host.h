@@ -86,6 +86,7 @@ public:
     unsigned char* getBitmap() { return m_bitmap.data(); }
     b200_PrimitiveXYIdBuffer* getPrimitiveIds(); // fetches the buffer from the device first when render_end left it there
     void setLazyIds(bool lazy) { m_lazyIds = lazy; }
+    void setFlatBuild(bool on) { m_useFlatBuild = on; } // false: always the literal per-level maps (tests compare the two)
     unsigned int getPrimitiveAt(int x, int y);
 
     // ---- flattened arrays, as the engine seam receives them ----
@@ -113,6 +114,17 @@ private:
     void streamDataToGPU();
     void emitPrimitive(long id);
     HostPrimitive& primitiveById(unsigned int id);
+    // first compaction of a fresh container: the same hierarchy and the same flattened arrays from sorted flat arrays per level
+    // (scene_host.cpp "flat build"); the per-level maps are only materialised if a later call needs them
+    bool flatBuildApplies() const;
+    bool flatBuild();
+    void flatStream();
+    void flatRecurse(int depth, unsigned int box);
+    void materialiseBoxes();
+    void dropFlat();
+    struct FlatHierarchy;
+    FlatHierarchy* m_flat = nullptr;
+    bool m_useFlatBuild = true;
     std::vector<HostPrimitive*> m_primitiveTable; // id -> record, valid during one compactBoxes()
     void realignTexturesAndMaterials();
 

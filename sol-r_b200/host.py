@@ -24,7 +24,7 @@ ABI_SYMBOLS = ["b200h_create", "b200h_destroy", "b200h_set_scene_info", "b200h_s
                "b200h_set_texcoords", "b200h_add_material", "b200h_add_materials", "b200h_set_material_raw",
                "b200h_set_texture", "b200h_compact_boxes", "b200h_get_scene", "b200h_set_randoms", "b200h_set_limits", "b200h_set_capacity",
                "b200h_set_partition", "b200h_set_device", "b200h_init_buffers", "b200h_render_begin", "b200h_render_end",
-               "b200h_get_bitmap", "b200h_get_primitive_ids", "b200h_get_primitive_at", "b200h_set_lazy_ids"]
+               "b200h_get_bitmap", "b200h_get_primitive_ids", "b200h_get_primitive_at", "b200h_set_lazy_ids", "b200h_set_flat_build"]
 
 
 def load():
@@ -57,6 +57,8 @@ def load():
     lib.b200h_set_limits.argtypes = [vp, C.c_int, C.c_int]
     lib.b200h_set_capacity.argtypes = [vp, C.c_long, C.c_long]
     lib.b200h_set_partition.argtypes = [vp, C.c_int, C.c_int]
+    lib.b200h_set_flat_build.argtypes = [vp, C.c_int]
+    lib.b200h_set_flat_build.restype = None
     lib.b200h_set_lazy_ids.argtypes = [vp, C.c_int]
     lib.b200h_set_lazy_ids.restype = None
     lib.b200h_set_device.argtypes = [vp, C.c_int]
@@ -160,6 +162,11 @@ class SceneHost:
 
     def render_end(self):
         self.lib.b200h_render_end(self.h)
+
+    def set_flat_build(self, on):
+        """False: compact_boxes always builds the reference's per-level maps literally (the flat sort-and-merge build of a fresh
+        container gives the same arrays; tests compare the two)."""
+        self.lib.b200h_set_flat_build(self.h, 1 if on else 0)
 
     def set_lazy_ids(self, lazy):
         """True (default): render_end copies the pixels only and the id buffer stays on the device until primitive_ids() /

@@ -75,6 +75,34 @@ def test_repeated_compaction_matches_reference_live(maker, repeats):
     r.close(); h.close()
 
 
+@pytest.mark.parametrize("maker", [lambda: scenes.config1(1000), lambda: scenes.config1(64), lambda: scenes.config1(63),
+                                   lambda: scenes.molecule(cells=2), lambda: scenes.triangle_mesh(20000),
+                                   lambda: scenes.random_spheres(50000, 20000.0, 20.0, 60.0, 7, "s50k")])
+def test_flat_build_equals_the_literal_build(maker):
+    """The first compaction of a fresh container takes the flat sort-and-merge build; the arrays, and whatever later calls
+    produce from the state it leaves behind (re-flattening without a rebuild, a second full compaction with the reference's
+    re-listing quirks), must equal the literal per-level-map build byte for byte."""
+    sc = maker()
+    si = wire.default_scene_info(64, 48)
+    out = []
+    for flat in (True, False):
+        h = host.SceneHost(si)
+        h.set_flat_build(flat)
+        seq = [sc.replay(h)]
+        seq.append(h.arrays())
+        seq.append(h.compact_boxes(False)); seq.append(h.arrays())
+        seq.append(h.compact_boxes(True)); seq.append(h.arrays())
+        out.append(seq)
+        h.close()
+    for a, b in zip(*out):
+        if isinstance(a, dict):
+            assert a["treeDepth"] == b["treeDepth"] and a["nbBoxes"] == b["nbBoxes"] and a["nbPrimitives"] == b["nbPrimitives"]
+            for k in ("boxes", "primitives", "materials", "lamps", "lightInformation", "bounds"):
+                assert np.array_equal(a[k], b[k]), k
+        else:
+            assert a == b
+
+
 def test_skip_counts_are_consistent():
     sc = scenes.config1(500)
     h = host.SceneHost(wire.default_scene_info(64, 48)); n = sc.replay(h); a = h.arrays(); h.close()
