@@ -767,6 +767,12 @@ void SceneHost::flatStream() // streamDataToGPU over the flat levels
         m_hBoundingBoxes[boxIndex].indexForNextBox.x = m_nbActiveBoxes - boxIndex;
     }
     const FlatHierarchy::Level& top = F.levels[maxDepth];
+    if (m_levelOrderFlatten && flatStreamByLevels())
+    {
+        if ((size_t)m_nbActivePrimitives != m_primitives.size())
+            fprintf(stderr, "[solr_b200] compactBoxes: lost primitives on the way... %d != %zu\n", m_nbActivePrimitives, m_primitives.size());
+        return;
+    }
     for (unsigned int j = 0; j < top.keys.size(); ++j)
     {
         const int boxIndex = m_nbActiveBoxes;
@@ -783,6 +789,93 @@ void SceneHost::flatStream() // streamDataToGPU over the flat levels
     }
     if ((size_t)m_nbActivePrimitives != m_primitives.size())
         fprintf(stderr, "[solr_b200] compactBoxes: lost primitives on the way... %d != %zu\n", m_nbActivePrimitives, m_primitives.size());
+}
+
+// The depth-first flatten above is a chain of dependent, scattered reads (a box, then its children, then theirs).  The same arrays
+// follow from three passes per level whose accesses are independent of each other: bottom-up the number of boxes and primitives
+// each subtree emits, top-down every box's slot (its parent's slot + 1 + the sizes of the siblings before it) and its first
+// primitive, then every record written straight to its slot.  Applies when nothing gets truncated by the capacities and no
+// light id doubles as a box key (the lights box is already out when this runs); otherwise the recursion does it.  Sizes, scan,
+// scatter: this is also the shape of a GPU flatten.
+bool SceneHost::flatStreamByLevels()
+{
+    const FlatHierarchy& F = *m_flat;
+    const int D = (int)F.depth;
+    for (unsigned int idx : F.lightKeyIndex)
+        if (idx != ~0u) return false;
+    if (m_primitives.size() > m_maxPrimitives) return false;
+    std::vector<std::vector<unsigned int>> size(D + 1), prims(D + 1), slot(D + 1), start(D + 1);
+    // ---- bottom-up: what every subtree emits ----
+    for (int d = 0; d <= D; ++d)
+    {
+        const FlatHierarchy::Level& L = F.levels[d];
+        const size_t nb = L.boxes.size();
+        size[d].resize(nb); prims[d].resize(nb);
+        for (size_t j = 0; j < nb; ++j)
+        {
+            const FlatHierarchy::Level::Box& B = L.boxes[j];
+            if (d == 0) { size[0][j] = B.count ? 1u : 0u; prims[0][j] = B.count; continue; }
+            unsigned int sz = 0, pr = 0;
+            if (B.count || d == D) // an inner box without children emits nothing; a top-level box always does
+            {
+                sz = 1;
+                for (unsigned int i = B.first; i < B.first + B.count; ++i) { sz += size[d - 1][L.itemIndex[i]]; pr += prims[d - 1][L.itemIndex[i]]; }
+            }
+            size[d][j] = sz; prims[d][j] = pr;
+        }
+    }
+    // ---- the top level in order, after the lights box ----
+    const FlatHierarchy::Level& top = F.levels[D];
+    slot[D].resize(top.boxes.size()); start[D].resize(top.boxes.size());
+    size_t boxes = (size_t)m_nbActiveBoxes, primitives = (size_t)m_nbActivePrimitives;
+    for (size_t j = 0; j < top.boxes.size(); ++j)
+    {
+        slot[D][j] = (unsigned int)boxes; start[D][j] = (unsigned int)primitives;
+        boxes += size[D][j]; primitives += prims[D][j];
+    }
+    if (boxes > m_maxBoxes || primitives > m_maxPrimitives || primitives != m_primitives.size()) return false;
+    b200_BoundingBox zeroBox;
+    memset(&zeroBox, 0, sizeof(zeroBox));
+    m_hBoundingBoxes.resize(boxes, zeroBox);
+    b200_Primitive zeroPrimitive;
+    memset(&zeroPrimitive, 0, sizeof(zeroPrimitive));
+    m_hPrimitives.resize(primitives, zeroPrimitive);
+    // ---- top-down: slots of the children, records of the level ----
+    for (int d = D; d >= 0; --d)
+    {
+        const FlatHierarchy::Level& L = F.levels[d];
+        if (d > 0) { slot[d - 1].assign(F.levels[d - 1].boxes.size(), 0u); start[d - 1].assign(F.levels[d - 1].boxes.size(), 0u); }
+        for (size_t j = 0; j < L.boxes.size(); ++j)
+        {
+            if (size[d][j] == 0) continue;
+            const FlatHierarchy::Level::Box& B = L.boxes[j];
+            b200_BoundingBox& out = m_hBoundingBoxes[slot[d][j]];
+            out.parameters[0] = B.lo;
+            out.parameters[1] = B.hi;
+            if (d == 0)
+            {
+                out.nbPrimitives = (int)B.count;
+                out.startIndex = (int)start[0][j];
+                out.indexForNextBox.x = 1;
+                for (unsigned int i = 0; i < B.count; ++i) writePrimitive(start[0][j] + i, L.items[B.first + i]);
+                continue;
+            }
+            out.nbPrimitives = 0;
+            out.startIndex = d;
+            out.indexForNextBox.x = (int)size[d][j];
+            unsigned int s = slot[d][j] + 1, p = start[d][j];
+            for (unsigned int i = B.first; i < B.first + B.count; ++i)
+            {
+                const unsigned int c = L.itemIndex[i];
+                slot[d - 1][c] = s; start[d - 1][c] = p;
+                s += size[d - 1][c]; p += prims[d - 1][c];
+            }
+        }
+        size[d].clear(); size[d].shrink_to_fit();
+    }
+    m_nbActiveBoxes = (int)boxes;
+    m_nbActivePrimitives = (int)primitives;
+    return true;
 }
 
 // The maps as the reference's own build would have left them, for whatever is called next.
@@ -863,6 +956,19 @@ int SceneHost::compactBoxes(bool reconstructBoxes) // :1041-1083
     streamDataToGPU();
     m_primitiveTable.clear();
     return m_nbActiveBoxes;
+}
+
+void SceneHost::writePrimitive(size_t slot, long id) // the record emitPrimitive appends, written in place
+{
+    const HostPrimitive& primitive = primitiveById((unsigned)id);
+    b200_Primitive& out = m_hPrimitives[slot]; // zero-filled by the caller
+    out.index = (int)id;
+    out.type = primitive.type;
+    out.p0 = primitive.p0; out.p1 = primitive.p1; out.p2 = primitive.p2;
+    out.n0 = primitive.n0; out.n1 = primitive.n1; out.n2 = primitive.n2;
+    out.size = primitive.size;
+    out.materialId = primitive.materialId;
+    out.vt0 = primitive.vt0; out.vt1 = primitive.vt1; out.vt2 = primitive.vt2;
 }
 
 void SceneHost::emitPrimitive(long id) // :1116-1135, :1199-1212
@@ -1182,7 +1288,7 @@ void b200h_get_scene(void* h, b200h_Scene* out)
 void b200h_set_randoms(void* h, const float* r, long n, int timestamp) { static_cast<SceneHost*>(h)->setRandoms(r, (size_t)n, timestamp); }
 void b200h_set_capacity(void* h, long maxBoxes, long maxPrimitives) { static_cast<SceneHost*>(h)->setCapacity((size_t)maxBoxes, (size_t)maxPrimitives); }
 void b200h_set_limits(void* h, int w, int hh) { static_cast<SceneHost*>(h)->setLimits(w, hh); }
-void b200h_set_flat_build(void* h, int on) { static_cast<SceneHost*>(h)->setFlatBuild(on != 0); }
+void b200h_set_flat_build(void* h, int mode) { static_cast<SceneHost*>(h)->setFlatBuild(mode); }
 void b200h_set_lazy_ids(void* h, int lazy) { static_cast<SceneHost*>(h)->setLazyIds(lazy != 0); }
 void b200h_set_partition(void* h, int rank, int world) { static_cast<SceneHost*>(h)->setPartition(rank, world); }
 void b200h_set_device(void* h, int device) { static_cast<SceneHost*>(h)->setDevice(device); }

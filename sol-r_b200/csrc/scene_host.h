@@ -86,7 +86,9 @@ public:
     unsigned char* getBitmap() { return m_bitmap.data(); }
     b200_PrimitiveXYIdBuffer* getPrimitiveIds(); // fetches the buffer from the device first when render_end left it there
     void setLazyIds(bool lazy) { m_lazyIds = lazy; }
-    void setFlatBuild(bool on) { m_useFlatBuild = on; } // false: always the literal per-level maps (tests compare the two)
+    // 0: always the literal per-level maps; 1: flat build with the depth-first flatten; 2 (default): flat build with the flatten by
+    // levels (tests compare the three)
+    void setFlatBuild(int mode) { m_useFlatBuild = mode != 0; m_levelOrderFlatten = mode == 2; }
     unsigned int getPrimitiveAt(int x, int y);
 
     // ---- flattened arrays, as the engine seam receives them ----
@@ -119,12 +121,15 @@ private:
     bool flatBuildApplies() const;
     bool flatBuild();
     void flatStream();
+    bool flatStreamByLevels();
+    void writePrimitive(size_t slot, long id);
     void flatRecurse(int depth, unsigned int box);
     void materialiseBoxes();
     void dropFlat();
     struct FlatHierarchy;
     FlatHierarchy* m_flat = nullptr;
     bool m_useFlatBuild = true;
+    bool m_levelOrderFlatten = true;
     std::vector<HostPrimitive*> m_primitiveTable; // id -> record, valid during one compactBoxes()
     void realignTexturesAndMaterials();
 

@@ -163,10 +163,10 @@ class SceneHost:
     def render_end(self):
         self.lib.b200h_render_end(self.h)
 
-    def set_flat_build(self, on):
-        """False: compact_boxes always builds the reference's per-level maps literally (the flat sort-and-merge build of a fresh
-        container gives the same arrays; tests compare the two)."""
-        self.lib.b200h_set_flat_build(self.h, 1 if on else 0)
+    def set_flat_build(self, mode):
+        """0 / False: compact_boxes always builds the reference's per-level maps literally; 1: flat sort-and-merge build of a fresh
+        container, flattened depth first; 2 / True (default): the same, flattened level by level.  Same arrays; tests compare them."""
+        self.lib.b200h_set_flat_build(self.h, 2 if mode is True else int(mode))
 
     def set_lazy_ids(self, lazy):
         """True (default): render_end copies the pixels only and the id buffer stays on the device until primitive_ids() /

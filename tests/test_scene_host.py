@@ -85,7 +85,7 @@ def test_flat_build_equals_the_literal_build(maker):
     sc = maker()
     si = wire.default_scene_info(64, 48)
     out = []
-    for flat in (True, False):
+    for flat in (0, 1, 2):
         h = host.SceneHost(si)
         h.set_flat_build(flat)
         seq = [sc.replay(h)]
@@ -94,13 +94,14 @@ def test_flat_build_equals_the_literal_build(maker):
         seq.append(h.compact_boxes(True)); seq.append(h.arrays())
         out.append(seq)
         h.close()
-    for a, b in zip(*out):
-        if isinstance(a, dict):
-            assert a["treeDepth"] == b["treeDepth"] and a["nbBoxes"] == b["nbBoxes"] and a["nbPrimitives"] == b["nbPrimitives"]
-            for k in ("boxes", "primitives", "materials", "lamps", "lightInformation", "bounds"):
-                assert np.array_equal(a[k], b[k]), k
-        else:
-            assert a == b
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            if isinstance(a, dict):
+                assert a["treeDepth"] == b["treeDepth"] and a["nbBoxes"] == b["nbBoxes"] and a["nbPrimitives"] == b["nbPrimitives"]
+                for k in ("boxes", "primitives", "materials", "lamps", "lightInformation", "bounds"):
+                    assert np.array_equal(a[k], b[k]), k
+            else:
+                assert a == b
 
 
 def test_skip_counts_are_consistent():
