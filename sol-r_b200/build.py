@@ -51,7 +51,7 @@ def build_host(force=False):
         return None
     if force or _stale(HOST_LIB, src):
         build_engine()
-        subprocess.check_call([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-sign-compare", "-o", HOST_LIB, src[0],
+        subprocess.check_call([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-sign-compare", "-o", HOST_LIB, src[0],
                                "-L" + CSRC, "-lsolr_b200", "-Wl,-rpath,$ORIGIN"])
     return HOST_LIB
 

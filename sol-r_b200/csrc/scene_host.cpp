@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <random>
+#include <thread>
 
 namespace solr_b200
 {
@@ -34,6 +35,50 @@ void normalizeVector(b200_float3& v) // GPUKernel.cpp:142-151
     float l = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
     if (l != 0.f) { v.x /= l; v.y /= l; v.z /= l; }
 }
+// Static partition of [0, n) over host threads: chunk t gets the same range whatever the timing, so results do not depend on it.
+unsigned int hostThreads()
+{
+    static const unsigned int n = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    return n;
+}
+template <class F> void parallelFor(size_t n, F&& body) // body(begin, end)
+{
+    const unsigned int T = (n < 65536) ? 1u : hostThreads();
+    if (T == 1) { body((size_t)0, n); return; }
+    std::vector<std::thread> pool;
+    for (unsigned int t = 0; t < T; ++t)
+    {
+        const size_t b = n * t / T, e = n * (t + 1) / T;
+        pool.emplace_back([&body, b, e]() { body(b, e); });
+    }
+    for (auto& th : pool) th.join();
+}
+// stable sort by key: chunks sorted on their own threads, then merged pairwise (std::inplace_merge keeps equal keys in order)
+template <class E> void parallelStableSortByKey(std::vector<E>& v)
+{
+    auto less = [](const E& a, const E& b) { return a.key < b.key; };
+    const size_t n = v.size();
+    unsigned int T = (n < 65536) ? 1u : hostThreads();
+    if (T == 1) { std::stable_sort(v.begin(), v.end(), less); return; }
+    std::vector<size_t> cut(T + 1);
+    for (unsigned int t = 0; t <= T; ++t) cut[t] = n * t / T;
+    {
+        std::vector<std::thread> pool;
+        for (unsigned int t = 0; t < T; ++t) pool.emplace_back([&, t]() { std::stable_sort(v.begin() + cut[t], v.begin() + cut[t + 1], less); });
+        for (auto& th : pool) th.join();
+    }
+    for (unsigned int width = 1; width < T; width *= 2)
+    {
+        std::vector<std::thread> pool;
+        for (unsigned int t = 0; t + width < T; t += 2 * width)
+        {
+            const size_t b = cut[t], m = cut[t + width], e = cut[std::min(T, t + 2 * width)];
+            pool.emplace_back([&, b, m, e]() { std::inplace_merge(v.begin() + b, v.begin() + m, v.begin() + e, less); });
+        }
+        for (auto& th : pool) th.join();
+    }
+}
+
 b200_float3 crossProduct(const b200_float3& b, const b200_float3& c) // GPUKernel.cpp:153-160
 {
     return v3(b.y * c.z - b.z * c.y, b.z * c.x - b.x * c.z, b.x * c.y - b.y * c.x);
@@ -566,20 +611,27 @@ bool SceneHost::flatBuild()
         boxSteps.x = (boxSteps.x == 0.f) ? 1 : boxSteps.x;
         boxSteps.y = (boxSteps.y == 0.f) ? 1 : boxSteps.y;
         boxSteps.z = (boxSteps.z == 0.f) ? 1 : boxSteps.z;
-        entries.reserve(n);
+        entries.resize(n);
         std::vector<unsigned char> isLight(n, 0);
+        std::vector<b200_float3> extentLo(n), extentHi(n);
+        parallelFor(n, [&](size_t begin, size_t end) {
+            for (size_t p = begin; p < end; ++p)
+            {
+                const HostPrimitive& primitive = *m_primitiveTable[p];
+                const b200_float3& center = primitive.p0;
+                // unsigned arithmetic: the key wraps modulo 2^32 for X >= 105 (:938-941)
+                unsigned int X = static_cast<int>((center.x - m_minPos.x) / boxSteps.x);
+                unsigned int Y = static_cast<int>((center.y - m_minPos.y) / boxSteps.y);
+                unsigned int Z = static_cast<int>((center.z - m_minPos.z) / boxSteps.z);
+                unsigned int B = 1 + 1000 * (X * boxSize * boxSize + Y * boxSize + Z);
+                isLight[p] = m_hMaterials[primitive.materialId].innerIllumination.x != 0.f;
+                entries[p] = {B, (unsigned int)p};
+                primitiveExtent(primitive, extentLo[p], extentHi[p]);
+            }
+        });
         for (unsigned int p = 0; p < n; ++p)
-        {
-            const HostPrimitive& primitive = *m_primitiveTable[p];
-            const b200_float3& center = primitive.p0;
-            unsigned int X = static_cast<int>((center.x - m_minPos.x) / boxSteps.x);
-            unsigned int Y = static_cast<int>((center.y - m_minPos.y) / boxSteps.y);
-            unsigned int Z = static_cast<int>((center.z - m_minPos.z) / boxSteps.z);
-            unsigned int B = 1 + 1000 * (X * boxSize * boxSize + Y * boxSize + Z);
-            if (m_hMaterials[primitive.materialId].innerIllumination.x != 0.f) { isLight[p] = 1; F->lights.push_back(p); }
-            entries.push_back({B, p});
-        }
-        std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+            if (isLight[p]) F->lights.push_back(p);
+        parallelStableSortByKey(entries);
         FlatHierarchy::Level& L = F->levels[0];
         L.reserve(entries.size(), entries.size(), false);
         for (size_t i = 0; i < entries.size();)
@@ -591,8 +643,8 @@ bool SceneHost::flatBuild()
             {
                 if (isLight[entries[j].child]) continue; // the cell exists, the light itself goes to the top level
                 L.items.push_back(entries[j].child);
-                b200_float3 p0, p1;
-                primitiveExtent(*m_primitiveTable[entries[j].child], p0, p1);
+                const b200_float3& p0 = extentLo[entries[j].child];
+                const b200_float3& p1 = extentHi[entries[j].child];
                 if (p0.x < lo.x) lo.x = p0.x;
                 if (p0.y < lo.y) lo.y = p0.y;
                 if (p0.z < lo.z) lo.z = p0.z;
@@ -617,20 +669,22 @@ bool SceneHost::flatBuild()
         boxSteps.x = (boxSteps.x == 0.f) ? 1 : boxSteps.x;
         boxSteps.y = (boxSteps.y == 0.f) ? 1 : boxSteps.y;
         boxSteps.z = (boxSteps.z == 0.f) ? 1 : boxSteps.z;
-        entries.clear();
-        entries.reserve(below.keys.size());
-        for (unsigned int c = 0; c < below.keys.size(); ++c)
-        {
-            const b200_float3& center = below.center[c];
-            int X = static_cast<int>((center.x - m_minPos.x) / boxSteps.x);
-            int Y = static_cast<int>((center.y - m_minPos.y) / boxSteps.y);
-            int Z = static_cast<int>((center.z - m_minPos.z) / boxSteps.z);
-            const uint32_t bs = (uint32_t)boxSize;
-            uint32_t Bu = (uint32_t)X * bs * bs + (uint32_t)Y * bs + (uint32_t)Z;
-            Bu += 1; // key 0 holds the lights
-            entries.push_back({Bu, c});
-        }
-        std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+        entries.resize(below.keys.size());
+        parallelFor(below.keys.size(), [&](size_t begin, size_t end) {
+            for (size_t c = begin; c < end; ++c)
+            {
+                const b200_float3& center = below.center[c];
+                int X = static_cast<int>((center.x - m_minPos.x) / boxSteps.x);
+                int Y = static_cast<int>((center.y - m_minPos.y) / boxSteps.y);
+                int Z = static_cast<int>((center.z - m_minPos.z) / boxSteps.z);
+                // int arithmetic in the reference (:1012-1014); it overflows for large grids, so wrap explicitly
+                const uint32_t bs = (uint32_t)boxSize;
+                uint32_t Bu = (uint32_t)X * bs * bs + (uint32_t)Y * bs + (uint32_t)Z;
+                Bu += 1; // key 0 holds the lights
+                entries[c] = {Bu, (unsigned int)c};
+            }
+        });
+        parallelStableSortByKey(entries);
         if (!entries.empty() && entries[0].key == 0u)
         {
             // a cell key wrapped onto the key of the lights box: leave this scene to the literal path
@@ -811,18 +865,20 @@ bool SceneHost::flatStreamByLevels()
         const FlatHierarchy::Level& L = F.levels[d];
         const size_t nb = L.boxes.size();
         size[d].resize(nb); prims[d].resize(nb);
-        for (size_t j = 0; j < nb; ++j)
-        {
-            const FlatHierarchy::Level::Box& B = L.boxes[j];
-            if (d == 0) { size[0][j] = B.count ? 1u : 0u; prims[0][j] = B.count; continue; }
-            unsigned int sz = 0, pr = 0;
-            if (B.count || d == D) // an inner box without children emits nothing; a top-level box always does
+        parallelFor(nb, [&](size_t begin, size_t end) {
+            for (size_t j = begin; j < end; ++j)
             {
-                sz = 1;
-                for (unsigned int i = B.first; i < B.first + B.count; ++i) { sz += size[d - 1][L.itemIndex[i]]; pr += prims[d - 1][L.itemIndex[i]]; }
+                const FlatHierarchy::Level::Box& B = L.boxes[j];
+                if (d == 0) { size[0][j] = B.count ? 1u : 0u; prims[0][j] = B.count; continue; }
+                unsigned int sz = 0, pr = 0;
+                if (B.count || d == D) // an inner box without children emits nothing; a top-level box always does
+                {
+                    sz = 1;
+                    for (unsigned int i = B.first; i < B.first + B.count; ++i) { sz += size[d - 1][L.itemIndex[i]]; pr += prims[d - 1][L.itemIndex[i]]; }
+                }
+                size[d][j] = sz; prims[d][j] = pr;
             }
-            size[d][j] = sz; prims[d][j] = pr;
-        }
+        });
     }
     // ---- the top level in order, after the lights box ----
     const FlatHierarchy::Level& top = F.levels[D];
@@ -845,32 +901,35 @@ bool SceneHost::flatStreamByLevels()
     {
         const FlatHierarchy::Level& L = F.levels[d];
         if (d > 0) { slot[d - 1].assign(F.levels[d - 1].boxes.size(), 0u); start[d - 1].assign(F.levels[d - 1].boxes.size(), 0u); }
-        for (size_t j = 0; j < L.boxes.size(); ++j)
-        {
-            if (size[d][j] == 0) continue;
-            const FlatHierarchy::Level::Box& B = L.boxes[j];
-            b200_BoundingBox& out = m_hBoundingBoxes[slot[d][j]];
-            out.parameters[0] = B.lo;
-            out.parameters[1] = B.hi;
-            if (d == 0)
+        // every box has one parent: the slots written below, and the records written at them, are all distinct
+        parallelFor(L.boxes.size(), [&](size_t begin, size_t end) {
+            for (size_t j = begin; j < end; ++j)
             {
-                out.nbPrimitives = (int)B.count;
-                out.startIndex = (int)start[0][j];
-                out.indexForNextBox.x = 1;
-                for (unsigned int i = 0; i < B.count; ++i) writePrimitive(start[0][j] + i, L.items[B.first + i]);
-                continue;
+                if (size[d][j] == 0) continue;
+                const FlatHierarchy::Level::Box& B = L.boxes[j];
+                b200_BoundingBox& out = m_hBoundingBoxes[slot[d][j]];
+                out.parameters[0] = B.lo;
+                out.parameters[1] = B.hi;
+                if (d == 0)
+                {
+                    out.nbPrimitives = (int)B.count;
+                    out.startIndex = (int)start[0][j];
+                    out.indexForNextBox.x = 1;
+                    for (unsigned int i = 0; i < B.count; ++i) writePrimitive(start[0][j] + i, L.items[B.first + i]);
+                    continue;
+                }
+                out.nbPrimitives = 0;
+                out.startIndex = d;
+                out.indexForNextBox.x = (int)size[d][j];
+                unsigned int s = slot[d][j] + 1, p = start[d][j];
+                for (unsigned int i = B.first; i < B.first + B.count; ++i)
+                {
+                    const unsigned int c = L.itemIndex[i];
+                    slot[d - 1][c] = s; start[d - 1][c] = p;
+                    s += size[d - 1][c]; p += prims[d - 1][c];
+                }
             }
-            out.nbPrimitives = 0;
-            out.startIndex = d;
-            out.indexForNextBox.x = (int)size[d][j];
-            unsigned int s = slot[d][j] + 1, p = start[d][j];
-            for (unsigned int i = B.first; i < B.first + B.count; ++i)
-            {
-                const unsigned int c = L.itemIndex[i];
-                slot[d - 1][c] = s; start[d - 1][c] = p;
-                s += size[d - 1][c]; p += prims[d - 1][c];
-            }
-        }
+        });
         size[d].clear(); size[d].shrink_to_fit();
     }
     m_nbActiveBoxes = (int)boxes;
