@@ -62,6 +62,13 @@ inline float fminf_(float a, float b) { return a < b ? a : b; }
 struct RayOT { V3 origin; V3 direction; }; // reference "Ray": origin + look-at target
 struct RayDir { V3 origin, direction, inv; int sx, sy, sz; };
 
+// Optional log of the closest-hit rays (analysis only, tests/analysis_ray_order.py): 9 floats per ray —
+// pixel, iteration, origin, look-at target, hit distance (or -1) — appended under an atomic counter.
+static float* g_rayLog = nullptr;
+static unsigned long long g_rayLogCapacity = 0;
+static unsigned long long g_rayLogCount = 0;
+static thread_local int g_currentPixel = 0;
+
 struct Ctx
 {
     const b200_SceneInfo& si;
@@ -703,6 +710,20 @@ bool intersectionWithPrimitives(const Ctx& c, const RayOT& ray, int iteration, i
         }
         else
             cptBoxes += box.indexForNextBox.x;
+    }
+    if (g_rayLog)
+    {
+        unsigned long long slot;
+#pragma omp atomic capture
+        slot = g_rayLogCount++;
+        if (slot < g_rayLogCapacity)
+        {
+            float* w = g_rayLog + 9 * slot;
+            w[0] = (float)g_currentPixel; w[1] = (float)iteration;
+            w[2] = ray.origin.x; w[3] = ray.origin.y; w[4] = ray.origin.z;
+            w[5] = ray.direction.x; w[6] = ray.direction.y; w[7] = ray.direction.z;
+            w[8] = intersections ? minDistance : -1.f;
+        }
     }
     return intersections;
 }
@@ -1367,6 +1388,57 @@ extern "C" {
 
 int oracle_abi_version() { return 1; }
 
+// analysis: start / stop logging closest-hit rays (see g_rayLog); returns the number of rays logged so far
+unsigned long long oracle_ray_log(float* buffer, unsigned long long capacityRays)
+{
+    const unsigned long long n = g_rayLogCount;
+    g_rayLog = buffer; g_rayLogCapacity = capacityRays; g_rayLogCount = 0;
+    return n;
+}
+
+// analysis: node visits of an ideal front-to-back walk of each ray through the engine's 4-wide tree (128-byte records: rows
+// lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] refs[4]; ref >= 0 inner node, < 0 leaf / empty) — the inner nodes whose
+// box the ray crosses before its hit (every crossed node for a miss).  A lower bound of what a culling walk visits, the same
+// for any order in which rays are grouped into warps.
+void oracle_walk_visits(const float* nodes, int nbNodes, const float* rays9, unsigned long long nRays, unsigned int* visits)
+{
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (long long k = 0; k < (long long)nRays; ++k)
+    {
+        const float* w = rays9 + 9 * k;
+        const float ox = w[2], oy = w[3], oz = w[4];
+        const float dx = w[5] - ox, dy = w[6] - oy, dz = w[7] - oz;
+        const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float tLimit = (w[8] > 0.f && len > 0.f) ? w[8] / len : 3.0e38f;
+        const float ix = dx != 0.f ? 1.f / dx : 1.f, iy = dy != 0.f ? 1.f / dy : 1.f, iz = dz != 0.f ? 1.f / dz : 1.f;
+        int stack[256];
+        int sp = 0;
+        unsigned int count = 0;
+        if (nbNodes > 0) stack[sp++] = 0;
+        while (sp > 0)
+        {
+            const int node = stack[--sp];
+            ++count;
+            const float* n = nodes + 32 * (size_t)node;
+            for (int c = 0; c < 4; ++c)
+            {
+                int ref;
+                memcpy(&ref, n + 24 + c, sizeof(int));
+                if (ref < 0) continue;
+                float t0x = (n[c] - ox) * ix, t1x = (n[12 + c] - ox) * ix;
+                float t0y = (n[4 + c] - oy) * iy, t1y = (n[16 + c] - oy) * iy;
+                float t0z = (n[8 + c] - oz) * iz, t1z = (n[20 + c] - oz) * iz;
+                if (t0x > t1x) { const float t = t0x; t0x = t1x; t1x = t; }
+                if (t0y > t1y) { const float t = t0y; t0y = t1y; t1y = t; }
+                if (t0z > t1z) { const float t = t0z; t0z = t1z; t1z = t; }
+                const float tmin = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), 0.f), tmax = fminf(fminf(fminf(t1x, t1y), t1z), tLimit);
+                if (tmin <= tmax && sp < 256 && ref < nbNodes) stack[sp++] = ref;
+            }
+        }
+        visits[k] = count;
+    }
+}
+
 void oracle_render(const oracle_Scene* s, const b200_SceneInfo* sceneInfo, const b200_PostProcessingInfo* postInfo,
                    const float* eye, const float* target, const float* angles, b200_PostProcessingBuffer* post,
                    b200_int4* ids, unsigned char* bitmap, int rowBegin, int rowEnd, int rowStride, int nThreads,
@@ -1390,6 +1462,7 @@ void oracle_render(const oracle_Scene* s, const b200_SceneInfo* sceneInfo, const
             const int y = rowBegin + k * rowStride;
             for (int x = 0; x < W; ++x)
             {
+                g_currentPixel = y * W + x;
                 renderPixel(c, x, y, eye, target, angles, post, ids);
                 // k_default, CudaRayTracer.cu:1057-1073
                 const int index = y * W + x;
