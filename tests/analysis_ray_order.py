@@ -102,6 +102,19 @@ def main():
                 rest = rest[rest > R] - R
                 phases += 1
             print("    cut after %2d rounds, continue compacted: warp-rounds %9d  (%.2f x) in %d phases" % (R, cost, cost / base, phases))
+        # (e) no state parked: a walk that exceeds its budget is abandoned and the ray walks again from the root in a later group of
+        # long rays (budgets R1 < R2 < unlimited)
+        def grouped(x, cap):
+            nfull = (len(x) + 31) // 32 * 32
+            pad = np.concatenate([x, np.zeros(nfull - len(x), x.dtype)]).reshape(-1, 32)
+            return int(np.minimum(pad.max(axis=1), cap).sum()) if len(x) else 0
+        for budgets in ((24,), (32,), (40,), (24, 48), (32, 64)):
+            rest, cost = vt, 0
+            for R in budgets:
+                cost += grouped(rest, R)
+                rest = rest[rest > R]
+            cost += grouped(rest, 1 << 30)
+            print("    abandon after %-8s rounds, walk again compacted: warp-rounds %9d  (%.2f x)" % ("/".join(map(str, budgets)), cost, cost / base))
 
 
 if __name__ == "__main__":
