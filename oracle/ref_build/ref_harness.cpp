@@ -190,6 +190,28 @@ int refh_compact_boxes(void* h)
     return static_cast<HarnessKernel*>(h)->compactBoxes(true);
 }
 
+// the animation step of the reference's scenes: move the primitives, refresh the box bounds, flatten again without a rebuild
+// (GPUKernel.cpp:1378-1513, :1574-1600; MoleculeScene.cpp:75-81)
+int refh_compact_boxes_mode(void* h, int reconstruct)
+{
+    return static_cast<HarnessKernel*>(h)->compactBoxes(reconstruct != 0);
+}
+void refh_rotate_primitives(void* h, const float* center3, const float* angles3)
+{
+    vec3f c = make_vec3f(center3[0], center3[1], center3[2]);
+    vec4f a = make_vec4f(angles3[0], angles3[1], angles3[2], 0.f);
+    static_cast<HarnessKernel*>(h)->rotatePrimitives(c, a);
+}
+void refh_translate_primitives(void* h, const float* t3)
+{
+    vec3f t = make_vec3f(t3[0], t3[1], t3[2]);
+    static_cast<HarnessKernel*>(h)->translatePrimitives(t);
+}
+void refh_scale_primitives(void* h, float scale)
+{
+    static_cast<HarnessKernel*>(h)->scalePrimitives(scale, 0, 0);
+}
+
 int refh_load_molecule(void* h, const char* filename, int geometryType, float atomSize, float stickSize,
                        int materialType, float scale)
 {

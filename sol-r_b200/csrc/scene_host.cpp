@@ -1259,6 +1259,119 @@ unsigned int SceneHost::getPrimitiveAt(int x, int y) // GPUKernel.cpp:729-739
 }
 } // namespace solr_b200
 
+
+// ---------------------------------------------------------------------------------------------------
+// animation step (GPUKernel.cpp:1378-1513, :1574-1721)
+// ---------------------------------------------------------------------------------------------------
+namespace solr_b200
+{
+namespace
+{
+void rotateVector(b200_float3& v, const b200_float3& rotationCenter, const b200_float3& cosAngles, const b200_float3& sinAngles) // :1602-1632
+{
+    b200_float3 vector = v3(v.x - rotationCenter.x, v.y - rotationCenter.y, v.z - rotationCenter.z);
+    b200_float3 result = vector;
+    /* X axis */
+    result.y = vector.y * cosAngles.x - vector.z * sinAngles.x;
+    result.z = vector.y * sinAngles.x + vector.z * cosAngles.x;
+    vector = result;
+    /* Y axis */
+    result.z = vector.z * cosAngles.y - vector.x * sinAngles.y;
+    result.x = vector.z * sinAngles.y + vector.x * cosAngles.y;
+    vector = result;
+    /* Z axis */
+    result.x = vector.x * cosAngles.z - vector.y * sinAngles.z;
+    result.y = vector.x * sinAngles.z + vector.y * cosAngles.z;
+    v = v3(result.x + rotationCenter.x, result.y + rotationCenter.y, result.z + rotationCenter.z);
+}
+void rotatePrimitive(HostPrimitive& primitive, const b200_float3& rotationCenter, const b200_float3& cosAngles,
+                     const b200_float3& sinAngles) // :1641-1674
+{
+    rotateVector(primitive.p0, rotationCenter, cosAngles, sinAngles);
+    if (primitive.type == B200_PT_CYLINDER || primitive.type == B200_PT_TRIANGLE)
+    {
+        rotateVector(primitive.p1, rotationCenter, cosAngles, sinAngles);
+        rotateVector(primitive.p2, rotationCenter, cosAngles, sinAngles);
+        const b200_float3 zeroCenter = v3(0.f, 0.f, 0.f);
+        rotateVector(primitive.n0, zeroCenter, cosAngles, sinAngles);
+        rotateVector(primitive.n1, zeroCenter, cosAngles, sinAngles);
+        rotateVector(primitive.n2, zeroCenter, cosAngles, sinAngles);
+        if (primitive.type == B200_PT_CYLINDER)
+        {
+            b200_float3 axis = v3(primitive.p1.x - primitive.p0.x, primitive.p1.y - primitive.p0.y, primitive.p1.z - primitive.p0.z);
+            const float len = sqrtf(axis.x * axis.x + axis.y * axis.y + axis.z * axis.z);
+            if (len != 0) { axis.x /= len; axis.y /= len; axis.z /= len; }
+            primitive.n1 = axis;
+        }
+    }
+}
+} // namespace
+
+// every level-0 box is reset and re-fitted to its primitives (an empty one keeps the reset bounds and its old centre: the
+// reference calls updateBoundingBox inside the loop over the box's primitives), then every box of every upper level to its children
+void SceneHost::refreshBoxesAfterMove()
+{
+    for (int b = 1; b < 64; ++b)
+        for (auto& box : m_boundingBoxes[b]) updateOutterBoundingBox(box.second, b - 1);
+}
+
+void SceneHost::rotatePrimitives(const b200_float3& rotationCenter, const b200_float3& angles) // :1378-1460
+{
+    materialiseBoxes();
+    m_primitivesTransfered = false;
+    const b200_float3 cosAngles = v3(cos(angles.x), cos(angles.y), cos(angles.z));
+    const b200_float3 sinAngles = v3(sin(angles.x), sin(angles.y), sin(angles.z));
+    for (auto& entry : m_boundingBoxes[0])
+    {
+        HostBox& box = entry.second;
+        resetBox(box, false);
+        for (long id : box.primitives)
+        {
+            HostPrimitive& primitive = m_primitives[(unsigned)id];
+            if (primitive.type != B200_PT_CAMERA) rotatePrimitive(primitive, rotationCenter, cosAngles, sinAngles);
+        }
+        if (!box.primitives.empty()) updateBoundingBox(box);
+    }
+    refreshBoxesAfterMove();
+}
+
+void SceneHost::translatePrimitives(const b200_float3& translation) // :1462-1513
+{
+    materialiseBoxes();
+    m_primitivesTransfered = false;
+    for (auto& entry : m_boundingBoxes[0])
+    {
+        HostBox& box = entry.second;
+        resetBox(box, false);
+        for (long id : box.primitives)
+        {
+            HostPrimitive& primitive = m_primitives[(unsigned)id];
+            if (primitive.type != B200_PT_CAMERA)
+            {
+                primitive.p0.x += translation.x; primitive.p0.y += translation.y; primitive.p0.z += translation.z;
+                primitive.p1.x += translation.x; primitive.p1.y += translation.y; primitive.p1.z += translation.z;
+                primitive.p2.x += translation.x; primitive.p2.y += translation.y; primitive.p2.z += translation.z;
+            }
+        }
+        if (!box.primitives.empty()) updateBoundingBox(box);
+    }
+    refreshBoxesAfterMove();
+}
+
+void SceneHost::scalePrimitives(const float scale) // :1574-1600 (the reference ignores its from / to arguments)
+{
+    m_primitivesTransfered = false;
+    for (auto& entry : m_primitives)
+    {
+        HostPrimitive& primitive = entry.second;
+        primitive.p0.x *= scale; primitive.p0.y *= scale; primitive.p0.z *= scale;
+        primitive.p1.x *= scale; primitive.p1.y *= scale; primitive.p1.z *= scale;
+        primitive.p2.x *= scale; primitive.p2.y *= scale; primitive.p2.z *= scale;
+        primitive.size.x *= scale; primitive.size.y *= scale; primitive.size.z *= scale;
+    }
+}
+} // namespace solr_b200
+
 // ---------------------------------------------------------------------------------------------------
 // flat C API (ctypes)
 // ---------------------------------------------------------------------------------------------------
@@ -1347,6 +1460,17 @@ void b200h_get_scene(void* h, b200h_Scene* out)
 void b200h_set_randoms(void* h, const float* r, long n, int timestamp) { static_cast<SceneHost*>(h)->setRandoms(r, (size_t)n, timestamp); }
 void b200h_set_capacity(void* h, long maxBoxes, long maxPrimitives) { static_cast<SceneHost*>(h)->setCapacity((size_t)maxBoxes, (size_t)maxPrimitives); }
 void b200h_set_limits(void* h, int w, int hh) { static_cast<SceneHost*>(h)->setLimits(w, hh); }
+void b200h_rotate_primitives(void* h, const float* c, const float* a)
+{
+    b200_float3 center = {c[0], c[1], c[2]}, angles = {a[0], a[1], a[2]};
+    static_cast<SceneHost*>(h)->rotatePrimitives(center, angles);
+}
+void b200h_translate_primitives(void* h, const float* t)
+{
+    b200_float3 translation = {t[0], t[1], t[2]};
+    static_cast<SceneHost*>(h)->translatePrimitives(translation);
+}
+void b200h_scale_primitives(void* h, float scale) { static_cast<SceneHost*>(h)->scalePrimitives(scale); }
 void b200h_set_flat_build(void* h, int mode) { static_cast<SceneHost*>(h)->setFlatBuild(mode); }
 void b200h_set_lazy_ids(void* h, int lazy) { static_cast<SceneHost*>(h)->setLazyIds(lazy != 0); }
 void b200h_set_partition(void* h, int rank, int world) { static_cast<SceneHost*>(h)->setPartition(rank, world); }

@@ -78,6 +78,11 @@ public:
     // box / primitive capacity of the flattened arrays; default = the reference's NB_MAX_BOXES / NB_MAX_PRIMITIVES (2.5 M,
     // Consts.h:32-33), at which compactBoxes silently drops boxes for ~1 M-primitive scenes (SURVEY finding 4)
     void setCapacity(size_t maxBoxes, size_t maxPrimitives) { m_maxBoxes = maxBoxes; m_maxPrimitives = maxPrimitives; }
+    // animation step (GPUKernel.cpp:1378-1513, :1574-1600): move the primitives, refresh the bounds of the existing boxes; the
+    // caller flattens again with compactBoxes(false)
+    void rotatePrimitives(const b200_float3& rotationCenter, const b200_float3& angles);
+    void translatePrimitives(const b200_float3& translation);
+    void scalePrimitives(float scale);
     void setPartition(int rank, int worldSize);
     void setDevice(int device);
     void initBuffers();
@@ -115,6 +120,7 @@ private:
     void recursiveDataStreamToGPU(int depth, std::vector<long>& elements, const std::vector<HostBox*>* linked);
     void streamDataToGPU();
     void emitPrimitive(long id);
+    void refreshBoxesAfterMove();
     HostPrimitive& primitiveById(unsigned int id);
     // first compaction of a fresh container: the same hierarchy and the same flattened arrays from sorted flat arrays per level
     // (scene_host.cpp "flat build"); the per-level maps are only materialised if a later call needs them

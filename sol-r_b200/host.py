@@ -24,7 +24,8 @@ ABI_SYMBOLS = ["b200h_create", "b200h_destroy", "b200h_set_scene_info", "b200h_s
                "b200h_set_texcoords", "b200h_add_material", "b200h_add_materials", "b200h_set_material_raw",
                "b200h_set_texture", "b200h_compact_boxes", "b200h_get_scene", "b200h_set_randoms", "b200h_set_limits", "b200h_set_capacity",
                "b200h_set_partition", "b200h_set_device", "b200h_init_buffers", "b200h_render_begin", "b200h_render_end",
-               "b200h_get_bitmap", "b200h_get_primitive_ids", "b200h_get_primitive_at", "b200h_set_lazy_ids", "b200h_set_flat_build"]
+               "b200h_get_bitmap", "b200h_get_primitive_ids", "b200h_get_primitive_at", "b200h_set_lazy_ids", "b200h_set_flat_build",
+               "b200h_rotate_primitives", "b200h_translate_primitives", "b200h_scale_primitives"]
 
 
 def load():
@@ -57,6 +58,12 @@ def load():
     lib.b200h_set_limits.argtypes = [vp, C.c_int, C.c_int]
     lib.b200h_set_capacity.argtypes = [vp, C.c_long, C.c_long]
     lib.b200h_set_partition.argtypes = [vp, C.c_int, C.c_int]
+    lib.b200h_rotate_primitives.argtypes = [vp, vp, vp]
+    lib.b200h_rotate_primitives.restype = None
+    lib.b200h_translate_primitives.argtypes = [vp, vp]
+    lib.b200h_translate_primitives.restype = None
+    lib.b200h_scale_primitives.argtypes = [vp, C.c_float]
+    lib.b200h_scale_primitives.restype = None
     lib.b200h_set_flat_build.argtypes = [vp, C.c_int]
     lib.b200h_set_flat_build.restype = None
     lib.b200h_set_lazy_ids.argtypes = [vp, C.c_int]
@@ -162,6 +169,18 @@ class SceneHost:
 
     def render_end(self):
         self.lib.b200h_render_end(self.h)
+
+    # animation step (GPUKernel::rotatePrimitives / translatePrimitives / scalePrimitives, then compact_boxes(False))
+    def rotate_primitives(self, center, angles):
+        c = (C.c_float * 3)(*center); a = (C.c_float * 3)(*angles)
+        self.lib.b200h_rotate_primitives(self.h, c, a)
+
+    def translate_primitives(self, t):
+        v = (C.c_float * 3)(*t)
+        self.lib.b200h_translate_primitives(self.h, v)
+
+    def scale_primitives(self, scale):
+        self.lib.b200h_scale_primitives(self.h, scale)
 
     def set_flat_build(self, mode):
         """0 / False: compact_boxes always builds the reference's per-level maps literally; 1: flat sort-and-merge build of a fresh

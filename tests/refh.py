@@ -95,7 +95,28 @@ class RefScene:
         self.lib.refh_set_texture(self.h, index, _ptr(t), t.shape[1], t.shape[0], t.shape[2])
 
     def compact_boxes(self, reconstruct=True):
-        return self.lib.refh_compact_boxes(self.h)
+        if reconstruct:
+            return self.lib.refh_compact_boxes(self.h)
+        self.lib.refh_compact_boxes_mode.argtypes = [C.c_void_p, C.c_int]
+        self.lib.refh_compact_boxes_mode.restype = C.c_int
+        return self.lib.refh_compact_boxes_mode(self.h, 0)
+
+    def rotate_primitives(self, center, angles):
+        c = (C.c_float * 3)(*center); a = (C.c_float * 3)(*angles)
+        self.lib.refh_rotate_primitives.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.refh_rotate_primitives.restype = None
+        self.lib.refh_rotate_primitives(self.h, c, a)
+
+    def translate_primitives(self, t):
+        v = (C.c_float * 3)(*t)
+        self.lib.refh_translate_primitives.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.refh_translate_primitives.restype = None
+        self.lib.refh_translate_primitives(self.h, v)
+
+    def scale_primitives(self, scale):
+        self.lib.refh_scale_primitives.argtypes = [C.c_void_p, C.c_float]
+        self.lib.refh_scale_primitives.restype = None
+        self.lib.refh_scale_primitives(self.h, scale)
 
     def arrays(self):
         """Copies of the flattened wire-format arrays the reference engine would receive."""

@@ -104,6 +104,37 @@ def test_flat_build_equals_the_literal_build(maker):
                 assert a == b
 
 
+@pytest.mark.skipif(not refh.available("cpu"), reason="reference not built (oracle/_ref)")
+@pytest.mark.parametrize("flat", [0, 2])
+@pytest.mark.parametrize("maker", [lambda: scenes.config1(1000), lambda: scenes.molecule(cells=2), lambda: scenes.triangle_mesh(5000)])
+def test_animation_step_matches_reference_live(maker, flat):
+    """The reference's animation step (MoleculeScene.cpp:75-81): rotatePrimitives / translatePrimitives move the primitives and
+    re-fit the existing boxes, compactBoxes(false) flattens again without a rebuild; scalePrimitives + a full compaction re-bins.
+    Same arrays as the reference's own container after every step (GPUKernel.cpp:1378-1513, :1574-1674)."""
+    sc = maker()
+    si = wire.default_scene_info(64, 48)
+    r = refh.RefScene(si, "cpu"); sc.replay(r)
+    h = host.SceneHost(si); h.set_flat_build(flat); sc.replay(h)
+
+    def same(step):
+        a, b = r.arrays(), h.arrays()
+        for k in ("boxes", "primitives", "lamps"):
+            assert np.array_equal(a[k], b[k]), (step, k)
+
+    same("build")
+    for step in range(2):
+        r.rotate_primitives((10.0, -20.0, 30.0), (0.02, 0.05 * (step + 1), -0.01)); h.rotate_primitives((10.0, -20.0, 30.0), (0.02, 0.05 * (step + 1), -0.01))
+        assert r.compact_boxes(False) == h.compact_boxes(False)
+        same("rotate %d" % step)
+    r.translate_primitives((100.0, -50.0, 25.0)); h.translate_primitives((100.0, -50.0, 25.0))
+    assert r.compact_boxes(False) == h.compact_boxes(False)
+    same("translate")
+    r.scale_primitives(0.5); h.scale_primitives(0.5)
+    assert r.compact_boxes(False) == h.compact_boxes(False)
+    same("scale")
+    r.close(); h.close()
+
+
 def test_skip_counts_are_consistent():
     sc = scenes.config1(500)
     h = host.SceneHost(wire.default_scene_info(64, 48)); n = sc.replay(h); a = h.arrays(); h.close()
