@@ -8,6 +8,9 @@ Groupings compared per pass: (a) tile order — what the staged kernels' compact
 tile they started from); (b) the same rays sorted by direction octant and the Z-order cell of their origin; (c) sorted by the
 visit count itself (the unreachable optimum, for scale).
 
+Bounce rays (passes >= 1) are walked by the engine in "gather" mode, which keeps every candidate within 1.5 x the closest distance
+(DESIGN.md 3): their walks are modelled with the bound at 1.5 x the hit distance.
+
 usage: python tests/analysis_ray_order.py [width height]     (default 960 540)
 """
 import ctypes as C
@@ -61,7 +64,9 @@ def main():
     o = oracle.Oracle(a, W, H, randoms=np.zeros(wire.REF_MAX_BITMAP_SIZE, np.float32))
     o.render(si, sc.eye, sc.target, sc.angles, threads=os.cpu_count())
     n = int(lib.oracle_ray_log(None, 0))
-    rays = log[:min(n, cap)]
+    rays = log[:min(n, cap)].copy()
+    bounce = (rays[:, 1] >= 1) & (rays[:, 8] > 0)
+    rays[bounce, 8] *= 1.5   # the gather window of the bounce-ray walks
     nodes, _, nb_main, _ = engine.build_walk_trees(a)
     visits = np.zeros(len(rays), np.uint32)
     flat = np.ascontiguousarray(nodes.reshape(-1))
