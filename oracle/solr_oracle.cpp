@@ -1400,7 +1400,16 @@ unsigned long long oracle_ray_log(float* buffer, unsigned long long capacityRays
 // lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] refs[4]; ref >= 0 inner node, < 0 leaf / empty) — the inner nodes whose
 // box the ray crosses before its hit (every crossed node for a miss).  A lower bound of what a culling walk visits, the same
 // for any order in which rays are grouped into warps.
+// stackAt (optional): entries on the walk's stack after `cutAfter` visits (0 if the walk is over by then), maxStack (optional): the
+// deepest the stack gets — how much state a walk parked after that many node rounds would have to carry.
+void oracle_walk_visits_ex(const float* nodes, int nbNodes, const float* rays9, unsigned long long nRays, unsigned int* visits,
+                           int cutAfter, unsigned int* stackAt, unsigned int* maxStack);
 void oracle_walk_visits(const float* nodes, int nbNodes, const float* rays9, unsigned long long nRays, unsigned int* visits)
+{
+    oracle_walk_visits_ex(nodes, nbNodes, rays9, nRays, visits, 0, nullptr, nullptr);
+}
+void oracle_walk_visits_ex(const float* nodes, int nbNodes, const float* rays9, unsigned long long nRays, unsigned int* visits,
+                           int cutAfter, unsigned int* stackAt, unsigned int* maxStack)
 {
 #pragma omp parallel for schedule(dynamic, 1024)
     for (long long k = 0; k < (long long)nRays; ++k)
@@ -1413,10 +1422,12 @@ void oracle_walk_visits(const float* nodes, int nbNodes, const float* rays9, uns
         const float ix = dx != 0.f ? 1.f / dx : 1.f, iy = dy != 0.f ? 1.f / dy : 1.f, iz = dz != 0.f ? 1.f / dz : 1.f;
         int stack[256];
         int sp = 0;
-        unsigned int count = 0;
+        unsigned int count = 0, deepest = 0, atCut = 0;
         if (nbNodes > 0) stack[sp++] = 0;
         while (sp > 0)
         {
+            if ((unsigned int)sp > deepest) deepest = (unsigned int)sp;
+            if ((int)count == cutAfter) atCut = (unsigned int)sp;
             const int node = stack[--sp];
             ++count;
             const float* n = nodes + 32 * (size_t)node;
@@ -1436,6 +1447,8 @@ void oracle_walk_visits(const float* nodes, int nbNodes, const float* rays9, uns
             }
         }
         visits[k] = count;
+        if (stackAt) stackAt[k] = atCut;
+        if (maxStack) maxStack[k] = deepest;
     }
 }
 

@@ -70,7 +70,11 @@ def main():
     nodes, _, nb_main, _ = engine.build_walk_trees(a)
     visits = np.zeros(len(rays), np.uint32)
     flat = np.ascontiguousarray(nodes.reshape(-1))
-    lib.oracle_walk_visits(flat.ctypes.data_as(C.c_void_p), nb_main, rays.ctypes.data_as(C.c_void_p), len(rays), visits.ctypes.data_as(C.c_void_p))
+    CUT = 24
+    stack_at, max_stack = np.zeros(len(rays), np.uint32), np.zeros(len(rays), np.uint32)
+    lib.oracle_walk_visits_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oracle_walk_visits_ex(flat.ctypes.data_as(C.c_void_p), nb_main, rays.ctypes.data_as(C.c_void_p), len(rays), visits.ctypes.data_as(C.c_void_p),
+                              CUT, stack_at.ctypes.data_as(C.c_void_p), max_stack.ctypes.data_as(C.c_void_p))
     print("config 2 at %dx%d: %d closest-hit rays, %d nodes in the tree" % (W, H, len(rays), nb_main))
     pixel = rays[:, 0].astype(np.int64)
     tile = (pixel // W // 4) * ((W + 7) // 8) + (pixel % W) // 8
@@ -96,6 +100,10 @@ def main():
             print("    %-26s utilisation %5.1f %%   warp-rounds %9d  (%.2f x)" % (name, 100.0 * u, cost, cost / base))
         print("    visits: hits mean %.1f, misses mean %.1f; share of rays with more than 32 / 48 / 64 visits: %.1f / %.1f / %.1f %%" % (
             v[hit].mean() if hit.any() else 0.0, v[~hit].mean() if (~hit).any() else 0.0, 100.0 * (v > 32).mean(), 100.0 * (v > 48).mean(), 100.0 * (v > 64).mean()))
+        sa, ms = stack_at[m][v > CUT], max_stack[m]
+        if len(sa):
+            print("    stack entries a walk cut after %d visits would park: mean %.1f, 95 %% <= %d, max %d (deepest stack of any walk: %d)" % (
+                CUT, sa.mean(), int(np.percentile(sa, 95)), sa.max(), ms.max()))
         # (d) walks cut off after R node rounds: the unfinished rays are parked with their stacks, compacted and continued 32 at a time
         vt = v[order_tile]
         for R in (16, 24, 32, 48):
