@@ -17,6 +17,9 @@
 #include "../../include/solr_b200.h"
 #include "shade.cuh"
 #include "tracequeue.cuh"
+#ifdef WITH_TRACE_SLICE
+#include "traceslice.cuh"
+#endif
 
 #define TILE_W 8
 #define TILE_H 4
@@ -1320,6 +1323,10 @@ struct SahBuilder
 
 int g_useWide = 1;
 int g_useUnordered = 1;
+#ifdef WITH_TRACE_SLICE
+int g_sliceRounds = 24; // node visits per slice
+int g_sliceCount = 6;   // slices per bounce pass, the last one unbounded
+#endif
 int g_tileOrder = 0; // order in which a GPU's own tiles are handed out: 0 row-major, 1 along a Z-order curve (neighbouring warps work on neighbouring tiles in both directions)
 int g_fuseTailPercent = 300; // k_stage_pass(p) carries its paths to the end in registers when the queue holds at most p times this share of the resident lanes (0: never)
 int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: also the closest-hit walks in their own kernel
@@ -1373,6 +1380,11 @@ void b200_set_option(int key, int value)
     else if (key == 3) g_useWide = value != 0;
     else if (key == 4) g_useUnordered = value != 0;
     else if (key == 5) g_useBackward = value != 0;
+#ifdef WITH_TRACE_SLICE
+    else if (key == 6 && value == 3) g_useStaged = 3; // sliced walks for the bounce passes (traceslice.cuh)
+    else if (key == 10 && value >= 1) g_sliceRounds = value;
+    else if (key == 11 && value >= 2 && value <= 32) g_sliceCount = value;
+#endif
     else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value;
     else if (key == 7 && value >= 0) g_traceCtasPerSM = value;
     else if (key == 8 && value >= 0) g_fuseTailPercent = value;
@@ -1942,6 +1954,46 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     else
     {
         CK(cudaMemsetAsync(G.dQueueCounters, 0, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int), G.stream));
+#ifdef WITH_TRACE_SLICE
+        static float* dSliceState = nullptr; static float4* dSliceCand = nullptr; static int* dSliceQueues = nullptr;
+        static unsigned int* dSliceCounters = nullptr; static size_t sliceStride = 0;
+        bool sliced = g_useStaged == 3 && P.scene.nbUWide > 0;
+        if (sliced && sliceStride < G.pathStride)
+        {
+            CK(cudaStreamSynchronize(G.stream));
+            freeDev(dSliceState); freeDev(dSliceCand); freeDev(dSliceQueues);
+            if (!dSliceCounters) CK(cudaMalloc(&dSliceCounters, 4 * sizeof(unsigned int)));
+            sliced = cudaMalloc(&dSliceState, (size_t)SLICE_WORDS * G.pathStride * sizeof(float)) == cudaSuccess &&
+                     cudaMalloc(&dSliceCand, (size_t)GATHER_CAP * G.pathStride * sizeof(float4)) == cudaSuccess &&
+                     cudaMalloc(&dSliceQueues, 2 * G.pathStride * sizeof(int)) == cudaSuccess;
+            if (!sliced) { cudaGetLastError(); freeDev(dSliceState); freeDev(dSliceCand); freeDev(dSliceQueues); sliceStride = 0; }
+            else sliceStride = G.pathStride;
+        }
+        if (sliced)
+        {
+            SliceParams SP;
+            SP.state = dSliceState; SP.cand = dSliceCand; SP.queues = dSliceQueues; SP.counters = dSliceCounters;
+            CK(cudaMemcpyToSymbolAsync(cSlice, &SP, sizeof(SP), 0, cudaMemcpyHostToDevice, G.stream));
+            int g0 = G.numSMs * G.ctasPerSMStage[0];
+            if (g0 > needed) g0 = needed > 0 ? needed : 1;
+            k_stage_primary<<<g0, CTA_THREADS, 0, G.stream>>>();
+            int perSM = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace_slice, CTA_THREADS, 0));
+            const int gs = G.numSMs * (perSM > 0 ? perSM : 1);
+            for (int pass = 1; pass < maxIteration; ++pass)
+            {
+                for (int sl = 0; sl < g_sliceCount; ++sl)
+                {
+                    CK(cudaMemsetAsync(dSliceCounters + 2 * (sl & 1), 0, 2 * sizeof(unsigned int), G.stream)); // the queue this slice fills
+                    k_trace_slice<<<gs, CTA_THREADS, 0, G.stream>>>(pass, sl, sl == g_sliceCount - 1 ? 0x7fffffff : g_sliceRounds);
+                }
+                k_shade_pass<<<G.numSMs * G.ctasPerSMStage[5], CTA_THREADS, 0, G.stream>>>(pass);
+            }
+            k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
+            G.launches += 2 + (maxIteration - 1) * (g_sliceCount + 1);
+        }
+        else
+#endif
         if (g_useStaged >= 2 && P.scene.nbUWide > 0)
         {
             // walks in their own kernel, per-lane refill from the ray queue
