@@ -40,7 +40,9 @@ def engine_sources():
 def build_engine(force=False, verbose=False, extra=()):
     src = engine_sources()
     if force or _stale(ENGINE_LIB, src):
-        cmd = [NVCC] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-o", ENGINE_LIB, src[0]]
+        # SOLR_B200_NVCC_FLAGS: extra flags for experimental builds, e.g. "-DWITH_TRACE_SLICE" (csrc/traceslice.cuh)
+        cmd = [NVCC] + NVCC_FLAGS + list(extra) + os.environ.get("SOLR_B200_NVCC_FLAGS", "").split() + \
+              (["-Xptxas", "-v"] if verbose else []) + ["-o", ENGINE_LIB, src[0]]
         subprocess.check_call(cmd)
     return ENGINE_LIB
 

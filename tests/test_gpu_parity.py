@@ -365,7 +365,8 @@ def test_drivers_produce_identical_frames(cfg):
     h.close()
     rnd = gs.randoms(41)
     out = []
-    for mode in (0, 1, 2):
+    # mode 3 (sliced walks, csrc/traceslice.cuh) only exists in builds made with SOLR_B200_NVCC_FLAGS=-DWITH_TRACE_SLICE
+    for mode in (0, 1, 2) + ((3,) if "WITH_TRACE_SLICE" in os.environ.get("SOLR_B200_NVCC_FLAGS", "") else ()):
         e = engine.Engine(si)
         try:
             e.set_option(6, mode)
