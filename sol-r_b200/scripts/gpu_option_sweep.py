@@ -1,5 +1,6 @@
 """One engine option (b200_set_option key, values) on configs 2 and 4, whole frame and a 1/8 share: ms per frame and checksums
-(GPU box).  usage: gpu_option_sweep.py KEY V1,V2,... [c2] [c4]   e.g. 8 0,150,300,600 (small-queue passes), 9 0,1 (tile order)"""
+(GPU box).  usage: gpu_option_sweep.py KEY V1,V2,... [c2] [c4]   e.g. 8 0,150,300,600 (small-queue passes), 9 0,1 (tile order);
+SOLR_OPT6=3 ... 10 16,24,32 (node visits per slice, build with SOLR_B200_NVCC_FLAGS=-DWITH_TRACE_SLICE)"""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -17,6 +18,8 @@ for cfg in sys.argv[3:] or ["c2", "c4"]:
     for rank, world in ((0, 1), (0, 8)):
         e = engine.Engine(si, limits=(W, H), rank=rank, world=world)
         e.upload(a, randoms=np.zeros(W * H, np.float32))
+        if os.environ.get("SOLR_OPT6") is not None:
+            e.set_option(6, int(os.environ["SOLR_OPT6"]))   # driver: 0 single kernel, 1 staged, 2 trace queue, 3 sliced walks (experimental builds)
         for pct in VALUES:
             e.set_option(KEY, pct)
             ms = []
