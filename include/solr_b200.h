@@ -131,6 +131,10 @@ int b200_debug_build_walk_trees(const b200_BoundingBox* boxes, int nbBoxes, cons
 void b200_debug_counters(unsigned long long* out8);
 /* Block until everything queued on the render stream is done. */
 void b200_synchronize(void);
+/* Measurement helper (bench.py): FP32 FMA microbenchmark on the current device — achieved TFLOP/s of dependent FFMA chains on
+ * every resident lane, and the SM clock sustained under that load (MHz): the measured roofline denominator BASELINE.md 2 asks
+ * for beside the nominal 148 SM x 128 lanes x 2 x f.  Returns 0 or the latched error code. */
+int b200_measure_fp32_peak(float* tflops, float* smMhz);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@
 // 8 CTAs x 128 threads = 32 warps/SM (64 registers): the walks are bound by dependent-load latency, and the extra
 // resident warps hide it better than the extra registers help (measured: 4 -> 11.9 ms, 6 -> 9.5 ms, 8 -> 8.4 ms, 12 -> 8.4 ms on config 2)
 #ifndef MIN_CTAS_PER_SM
-#define MIN_CTAS_PER_SM 8
+#define MIN_CTAS_PER_SM 6
 #endif
 
 // GeometryShaders.cuh:132-165 (makeColor) fused with k_default's averaging (CudaRayTracer.cu:1068-1072)
@@ -773,6 +773,27 @@ __global__ void __launch_bounds__(256) k_post_process()
     }
 }
 
+// FP32 FMA throughput probe (b200_measure_fp32_peak): 8 independent dependent-FFMA chains per thread, 16 steps each per iteration
+#define FP32_PEAK_FMAS_PER_ITER (8 * 16)
+__global__ void __launch_bounds__(256) k_fp32_peak(float* out, const int iters, long long* cycles)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f + 1e-9f * blockIdx.x, c = 1e-3f;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+        {
+            a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+            a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+        }
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 // ----------------------------------------------------------------------------------------------------
 // host state
 // ----------------------------------------------------------------------------------------------------
@@ -793,6 +814,7 @@ struct Engine
     float4* dUWide = nullptr; int nbUWide = 0; size_t capUWide = 0; int opaqueShadows = 0;
     int nbUX = 0; // point-query tree for backward cylinder hits, appended to dUWide
     int* dPrimLeaf = nullptr; size_t capPrimLeaf = 0;
+    float4* dPrimRecs = nullptr; size_t capPrimRecs = 0; // 96-byte records of the unit walk (trace.cuh), 6 float4 per primitive
     // staged rendering
     float* dPathWords = nullptr; float4* dPathColors = nullptr; float* dPathContrib = nullptr; int* dPathQueues = nullptr;
     unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
@@ -900,6 +922,10 @@ void uploadMeta()
     }
     G.opaqueShadows = opaque;
     CK(cudaMemcpyAsync(G.dMeta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+    // the unit walk reads the packed word from the primitive's record ((n1, packed word) is its fourth float4)
+    if (G.dPrimRecs && G.capPrimRecs >= PRIM_REC_F4 * meta.size())
+        CK(cudaMemcpy2DAsync(reinterpret_cast<char*>(G.dPrimRecs) + 3 * sizeof(float4) + 3 * sizeof(float), PRIM_REC_F4 * sizeof(float4), meta.data(),
+                             sizeof(int), sizeof(int), meta.size(), cudaMemcpyHostToDevice, G.stream));
     CK(cudaStreamSynchronize(G.stream)); // meta is a stack-lifetime staging vector
 }
 
@@ -1474,7 +1500,7 @@ void b200_finalize_scene(b200_int2)
     unregisterHost();
     closePeerFrame();
     freeDev(G.dWide); freeDev(G.dLeafRecs); G.capWide = G.capLeafRecs = 0; G.nbWide = 0;
-    freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0;
+    freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0; freeDev(G.dPrimRecs); G.capPrimRecs = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
     freeDev(G.dTileCounter); freeDev(G.dWork); freeDev(G.dTileOrder); G.capTileOrder = 0; G.tileOrderKey[0] = 0;
@@ -1729,6 +1755,27 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     }
     G.hPrims.assign(prims, prims + nbPrims);
 
+    // 3b. the unit walk's records: geometry + (packed word, patched in by uploadMeta) + the reference leaf's box and number + the
+    //     original id, so a leaf visit is one dependent access (trace.cuh)
+    if (G.nbUWide > 0)
+    {
+        std::vector<float4> recs((size_t)PRIM_REC_F4 * nbPrims + 2); // + 32 bytes: a 256-bit load never straddles the end
+        for (int i = 0; i < nbPrims; ++i)
+        {
+            const b200_Primitive& p = prims[i];
+            const int l = primLeaf[i];
+            const Aabb& lb = leaves[l].box;
+            float4* rec = &recs[(size_t)PRIM_REC_F4 * i];
+            rec[0] = geo[4 * (size_t)i + 0]; rec[1] = geo[4 * (size_t)i + 1]; rec[2] = geo[4 * (size_t)i + 2];
+            rec[3] = make_float4(p.n1.x, p.n1.y, p.n1.z, 0.f);
+            rec[4] = make_float4(lb.lo[0], lb.lo[1], lb.lo[2], intBits(l));
+            rec[5] = make_float4(lb.hi[0], lb.hi[1], lb.hi[2], intBits(p.index));
+        }
+        if (recs.size() > G.capPrimRecs) { freeDev(G.dPrimRecs); G.capPrimRecs = recs.size() + 1024; CK(cudaMalloc(&G.dPrimRecs, G.capPrimRecs * sizeof(float4))); }
+        CK(cudaMemcpyAsync(G.dPrimRecs, recs.data(), recs.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+        CK(cudaStreamSynchronize(G.stream)); // staging vector dies here
+    }
+
     // 4. device buffers (grow-only) and upload
     if ((size_t)nOut > G.capBoxes || (size_t)nbBoxes > G.capBoxes)
     {
@@ -1858,7 +1905,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.scene.mats = G.dMats; P.scene.lights = G.dLights; P.scene.lightInfoSize = objects.w; P.scene.nbLamps = objects.z;
     P.scene.tex = G.dTex; P.scene.randoms = G.dRandoms; P.scene.randomTableSize = G.maxW * G.maxH;
     P.scene.wnodes = G.dWide; P.scene.leafRecs = G.dLeafRecs; P.scene.nbWide = g_useWide ? G.nbWide : 0;
-    P.scene.primLeaf = G.dPrimLeaf;
+    P.scene.primLeaf = G.dPrimLeaf; P.scene.primRecs = G.dPrimRecs;
     P.scene.uwnodes = G.dUWide; P.scene.nbUWide = (g_useWide && g_useUnordered) ? G.nbUWide : 0; P.scene.opaqueShadows = G.opaqueShadows;
     P.scene.nbUX = g_useBackward ? G.nbUX : 0;
     P.scene.rawBoxes = G.dRawBoxes; P.scene.nbRawBoxes = objects.x < G.nbBoxesIn ? objects.x : G.nbBoxesIn;
@@ -2171,6 +2218,43 @@ int b200_debug_build_walk_trees(const b200_BoundingBox* boxes, int nbBoxes, cons
 void b200_synchronize(void)
 {
     if (G.stream && ensureDevice()) CK(cudaStreamSynchronize(G.stream));
+}
+
+// FP32 FMA microbenchmark (BASELINE.md 2 asks for a measured value next to the nominal 148 x 128 x 2 x f): every resident lane runs
+// dependent FFMA chains, eight independent ones per thread; flops / event time = achieved TFLOP/s, clock64 ticks / event time = the
+// SM clock sustained under that load.
+int b200_measure_fp32_peak(float* tflops, float* smMhz)
+{
+    if (!ensureDevice()) return G.err;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, G.device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float* dOut = nullptr; long long* dCycles = nullptr;
+    CK(cudaMalloc(&dOut, (size_t)blocks * threads * sizeof(float)));
+    CK(cudaMalloc(&dCycles, (size_t)blocks * sizeof(long long)));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    float bestMs = 1e30f;
+    for (int rep = 0; rep < 5; ++rep)
+    {
+        CK(cudaEventRecord(a, 0));
+        k_fp32_peak<<<blocks, threads>>>(dOut, iters, dCycles);
+        CK(cudaEventRecord(b, 0));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < bestMs) bestMs = ms;
+    }
+    std::vector<long long> cyc(blocks);
+    CK(cudaMemcpy(cyc.data(), dCycles, (size_t)blocks * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (long long c : cyc) mx = c > mx ? c : mx;
+    const double flops = (double)blocks * threads * (double)iters * FP32_PEAK_FMAS_PER_ITER * 2.0;
+    if (tflops) *tflops = (float)(flops / (bestMs * 1e-3) / 1e12);
+    if (smMhz) *smMhz = (float)((double)mx / (bestMs * 1e-3) / 1e6);
+    CK(cudaEventDestroy(a)); CK(cudaEventDestroy(b));
+    CK(cudaFree(dOut)); CK(cudaFree(dCycles));
+    return G.err;
 }
 }
 

@@ -54,6 +54,9 @@ struct SceneDev
     // second unordered tree over the grown boxes of cylinders/cones (engine.cu step 2c): the boxes containing a ray's origin are
     // the only primitives that can register a hit behind it
     int nbUX; // its nodes follow the first tree's in uwnodes (root = nbUWide); leaf refs carry bit 30
+    // one 96-byte record per primitive for the unit walk (engine.cu step 2d): everything a leaf visit needs behind ONE dependent
+    // load — (p0, size.x) (p1, size.y) (p2, size.z) (n1, packed word) (reference leaf box min, leaf number) (leaf box max, original id)
+    const float4* __restrict__ primRecs;
     int opaqueShadows; // every shadow caster blocks fully (no transparent material, no textured plane): any-hit is exact
 };
 
@@ -1103,7 +1106,7 @@ SB_DEV void nodeRay(NodeRay& q, const Ray& r)
 SB_DEV unsigned long long evictLastPolicy()
 {
     unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); // not volatile: one per walk, hoisted out of the node loop
     return p;
 }
 SB_DEV float4 ldNode(const float4* p, const unsigned long long policy)
@@ -1217,6 +1220,184 @@ SB_DEV bool unorderedStep(const float4* __restrict__ nodes, const int ref, const
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Lean node round (round 2).  ncu of the round-1 walk (profiles/r01_ncu_frame_v12_staged.json, SASS view) showed ~185 warp
+// instructions per node round, 75-80 % of all instructions of the ray kernels, of which only ~70 test boxes: the rest sorted
+// the four children (predicated register moves), pushed each hit child behind its own branch with a shared / local-memory split,
+// rebuilt the L2 policy descriptor and popped the child it had just pushed.  Here:
+//   * a child's result is ONE integer key: the bits of its clamped entry distance (non-negative floats order like integers) with
+//     the child number in the two lowest mantissa bits, KEY_MISS for a miss; min over the four keys = nearest hit child, and its
+//     two low bits say which — no sort, no (distance, ref) pairs to move;
+//   * the nearest hit child is walked next directly (never pushed), the other hit children are pushed in slot order by
+//     predicated stores (only "nearest first" matters, profiles/r01_history.md);
+//   * the whole stack lives in shared memory ([entry][thread], 8 bytes: ref + key; a popped entry whose key has fallen behind
+//     the bound is dropped without a node visit — ~10 % of the pops of primary rays); a walk that would exceed it takes the
+//     ordered walk (degenerate trees only: WALK_STACK 16 against a measured maximum depth of 15 with every hit child pushed);
+//   * the L2 evict-last policy descriptor is made once per walk.
+// The low key bits perturb the stored entry distance by <= 3 ulp; the bounds it is compared with carry 1e-4 relative slack.
+// ---------------------------------------------------------------------------------------------------
+#ifndef WALK_STACK
+#define WALK_STACK 16
+#endif
+#define WALK_DONE ((int)0x80000000) // no node, no leaf: the walk is over (never a leaf ref: primitive indices stay below 2^30 - 1)
+#define WALK_POP 0x7fffffff         // take the next entry from the stack (never a node index)
+#define KEY_MISS 0x7fffffff
+
+struct NodeKeys
+{
+    int k0, k1, k2, k3;
+    int4 refs;
+};
+
+// 32 bytes of a node record in one instruction (LDG.E.256, new with sm_100) through the read-only path, kept in L2 with the static
+// evict-last priority (only the 256-bit form takes it without a policy operand): 4 loads per 128-byte record instead of 7
+#ifndef NODE_LOAD_MODE
+#define NODE_LOAD_MODE 0
+#endif
+SB_DEV void ldNode256(const float4* p, float4& a, float4& b)
+{
+#if defined(NODE_LOAD_PLAIN) || NODE_LOAD_MODE == 3
+    a = __ldg(p); b = __ldg(p + 1);
+#else
+    unsigned long long t0, t1, t2, t3;
+    // (the .v8.f32 spelling of the same load crashes ptxas 12.9 inside these kernels; .v4.b64 is the same instruction)
+#if NODE_LOAD_MODE == 0
+    asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(t0), "=l"(t1), "=l"(t2), "=l"(t3) : "l"(p));
+#elif NODE_LOAD_MODE == 1
+    asm volatile("ld.global.nc.L1::evict_last.L2::evict_last.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(t0), "=l"(t1), "=l"(t2), "=l"(t3) : "l"(p));
+#elif NODE_LOAD_MODE == 2
+    asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(t0), "=l"(t1), "=l"(t2), "=l"(t3) : "l"(p));
+#else
+    asm volatile("ld.global.L1::evict_last.L2::evict_last.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(t0), "=l"(t1), "=l"(t2), "=l"(t3) : "l"(p));
+#endif
+    a.x = __uint_as_float((unsigned int)t0); a.y = __uint_as_float((unsigned int)(t0 >> 32));
+    a.z = __uint_as_float((unsigned int)t1); a.w = __uint_as_float((unsigned int)(t1 >> 32));
+    b.x = __uint_as_float((unsigned int)t2); b.y = __uint_as_float((unsigned int)(t2 >> 32));
+    b.z = __uint_as_float((unsigned int)t3); b.w = __uint_as_float((unsigned int)(t3 >> 32));
+#endif
+}
+
+SB_DEV void nodeKeys(const float4* __restrict__ n, const NodeRay& q, const float tLimit, NodeKeys& o)
+{
+#ifdef NODE_ADDR_SELECT
+    // near / far rows picked by address (rows are 16 bytes apart: lo.x lo.y lo.z hi.x hi.y hi.z): 6 address adds instead of 24 selects
+    const char* b = reinterpret_cast<const char*>(n);
+    const unsigned int ox = q.ix < 0.f ? 48u : 0u, oy = q.iy < 0.f ? 48u : 0u, oz = q.iz < 0.f ? 48u : 0u;
+    const float4 nx = __ldg(reinterpret_cast<const float4*>(b + ox)), fx = __ldg(reinterpret_cast<const float4*>(b + (48u - ox)));
+    const float4 ny = __ldg(reinterpret_cast<const float4*>(b + (16u + oy))), fy = __ldg(reinterpret_cast<const float4*>(b + (64u - oy)));
+    const float4 nz = __ldg(reinterpret_cast<const float4*>(b + (32u + oz))), fz = __ldg(reinterpret_cast<const float4*>(b + (80u - oz)));
+    const float4 rf = __ldg(n + 6);
+#define UN_NEAR(A, C) n##A.C
+#define UN_FAR(A, C) f##A.C
+#else
+    float4 lx, ly, lz, hx, hy, hz, rf, pad;
+    ldNode256(n, lx, ly); ldNode256(n + 2, lz, hx); ldNode256(n + 4, hy, hz); ldNode256(n + 6, rf, pad);
+    const bool sx = q.ix < 0.f, sy = q.iy < 0.f, sz = q.iz < 0.f;
+#define UN_NEAR(A, C) (s##A ? h##A.C : l##A.C)
+#define UN_FAR(A, C) (s##A ? l##A.C : h##A.C)
+#endif
+    o.refs = make_int4(__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w));
+    // a box is crossed within [0, tLimit] iff max(entry, 0) <= min(exit, tLimit): one comparison per child
+#define UN_KEY(C, K, J)                                                                                              \
+    {                                                                                                                \
+        const float tnx = __fmaf_rn(UN_NEAR(x, C), q.ix, q.nox), tfx = __fmaf_rn(UN_FAR(x, C), q.ix, q.nox);         \
+        const float tny = __fmaf_rn(UN_NEAR(y, C), q.iy, q.noy), tfy = __fmaf_rn(UN_FAR(y, C), q.iy, q.noy);         \
+        const float tnz = __fmaf_rn(UN_NEAR(z, C), q.iz, q.noz), tfz = __fmaf_rn(UN_FAR(z, C), q.iz, q.noz);         \
+        const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.f), tmax = fminf(fminf(fminf(tfx, tfy), tfz), tLimit); \
+        K = (tmin <= tmax) ? ((__float_as_int(tmin) & ~3) | J) : KEY_MISS;                                           \
+    }
+    UN_KEY(x, o.k0, 0) UN_KEY(y, o.k1, 1) UN_KEY(z, o.k2, 2) UN_KEY(w, o.k3, 3)
+#undef UN_KEY
+#undef UN_NEAR
+#undef UN_FAR
+}
+
+// The traversal stack: [entry][thread] in shared memory, addressed by 32-bit shared-window addresses so a push is a predicated
+// store and an add.  sp = address of the next free entry of this thread's column.
+#define WALK_STACK_STRIDE (WALK_THREADS * 8)
+SB_DEV void stackPut(const unsigned int at, const int ref, const int key)
+{
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at), "r"(ref), "r"(key) : "memory");
+}
+SB_DEV int2 stackGet(const unsigned int at)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(at) : "memory");
+    return v;
+}
+
+// One node round of a lane: `cur` is a node (>= 0, not WALK_POP) or WALK_POP; afterwards it is the next node, a leaf ref (< 0),
+// WALK_POP again (the popped entry had fallen behind the bound) or WALK_DONE.  The bottom entry of the stack is a sentinel
+// (WALK_DONE, key 0: never behind the bound), so a pop needs no emptiness test.  spLimit = shared address of entry
+// WALK_STACK - 3 of column 0: a round pushes at most three entries.  Returns false if the stack would overflow.
+SB_DEV bool walkRound(const float4* __restrict__ nodes, const int nbMain, const NodeRay& q, const float cullT, const unsigned int spLimit,
+                      unsigned int& sp, int& cur)
+{
+    // the pop first, so that a lane coming back from a leaf (or from a node without hits) visits its next node in this same round
+    if (cur == WALK_POP)
+    {
+        sp -= WALK_STACK_STRIDE;
+        const int2 e = stackGet(sp);
+        cur = (__int_as_float(e.y) > cullT) ? WALK_POP : e.x; // the bound shrank since this entry was pushed
+    }
+    if (cur >= 0 && cur != WALK_POP)
+    {
+        if (sp >= spLimit) return false; // before the loads: they all go out together
+        NodeKeys h;
+        nodeKeys(nodes + (size_t)8 * cur, q, (cur >= nbMain) ? 0.f : cullT, h);
+        const int kmin = min(min(h.k0, h.k1), min(h.k2, h.k3));
+        const int c = kmin & 3;
+        const int ra = (c & 1) ? h.refs.y : h.refs.x, rb = (c & 1) ? h.refs.w : h.refs.z;
+        cur = (kmin == KEY_MISS) ? WALK_POP : ((c & 2) ? rb : ra);
+        // keys are distinct (child number in the low bits), so "!= kmin" singles out the nearest; all KEY_MISS when nothing is hit
+        if ((h.k0 != kmin) & (h.k0 != KEY_MISS)) { stackPut(sp, h.refs.x, h.k0); sp += WALK_STACK_STRIDE; }
+        if ((h.k1 != kmin) & (h.k1 != KEY_MISS)) { stackPut(sp, h.refs.y, h.k1); sp += WALK_STACK_STRIDE; }
+        if ((h.k2 != kmin) & (h.k2 != KEY_MISS)) { stackPut(sp, h.refs.z, h.k2); sp += WALK_STACK_STRIDE; }
+        if ((h.k3 != kmin) & (h.k3 != KEY_MISS)) { stackPut(sp, h.refs.w, h.k3); sp += WALK_STACK_STRIDE; }
+    }
+    return true;
+}
+
+// Start of a walk: sentinel, then the root of the point-query tree if there is one; the root of the walk proper is `cur`.
+SB_DEV void walkStart(int2* const stack, const int nbMain, const bool pointQuery, unsigned int& spLimit, unsigned int& sp, int& cur)
+{
+    const unsigned int base = (unsigned int)__cvta_generic_to_shared(stack);
+    spLimit = base + (WALK_STACK - 3) * WALK_STACK_STRIDE;
+    sp = base + threadIdx.x * 8;
+    stackPut(sp, WALK_DONE, 0); sp += WALK_STACK_STRIDE;
+    if (pointQuery) { stackPut(sp, nbMain, 0); sp += WALK_STACK_STRIDE; }
+    cur = 0;
+}
+
+// A walk deeper than the shared stack (the round-2 form first sent those to the ordered walk: 6.3 ms instead of 4.5 ms per frame of
+// config 2 — a 4-wide tree leaves up to three entries behind per level and a few percent of the rays get past 11) moves the
+// eight oldest entries of its column to a thread-local buffer and slides the rest down; they come back when the sentinel is
+// popped.  Rare, so the node round itself only ever sees the shared stack.
+#ifndef WALK_SPILL
+#define WALK_SPILL 64 // entries a walk can hold in thread-local memory on top of the shared stack
+#endif
+SB_DEV bool walkSpill(int2* const stack, int2* const spillBuf, int& nSpill, unsigned int& sp)
+{
+    if (nSpill + 8 > WALK_SPILL) return false;
+    const unsigned int col = (unsigned int)__cvta_generic_to_shared(stack) + threadIdx.x * 8;
+    for (int k = 0; k < 8; ++k) spillBuf[nSpill + k] = stackGet(col + (1 + k) * WALK_STACK_STRIDE);
+    for (unsigned int at = col + 9 * WALK_STACK_STRIDE; at < sp; at += WALK_STACK_STRIDE)
+    {
+        const int2 e = stackGet(at);
+        stackPut(at - 8 * WALK_STACK_STRIDE, e.x, e.y);
+    }
+    sp -= 8 * WALK_STACK_STRIDE;
+    nSpill += 8;
+    return true;
+}
+SB_DEV void walkUnspill(int2* const stack, const int2* const spillBuf, int& nSpill, unsigned int& sp)
+{
+    const unsigned int col = (unsigned int)__cvta_generic_to_shared(stack) + threadIdx.x * 8;
+    nSpill -= 8;
+    for (int k = 0; k < 8; ++k) stackPut(col + (1 + k) * WALK_STACK_STRIDE, spillBuf[nSpill + k].x, spillBuf[nSpill + k].y);
+    sp = col + 9 * WALK_STACK_STRIDE; // the sentinel stays at entry 0
+}
+
 // One walk for the three order-independent ray classes (one copy of the node loop and of the primitive tests keeps the
 // instruction working set small — the megakernel is bound by instruction-cache misses otherwise, profiles/r01_history.md):
 //   UW_CLOSEST  |direction| >= 1: minimum distance, ties to the lowest array index; culls by the best distance found
@@ -1244,6 +1425,11 @@ struct WalkOut { Hit hit; float shadow; };
 #ifndef UW_INLINE
 #define UW_INLINE __noinline__
 #endif
+#ifndef UW_SHADOW_TLIMIT
+#define UW_SHADOW_TLIMIT 1.001f
+#endif
+#define PRIM_REC_F4 6 // float4 per primitive record of the unit walk
+#if defined(UW_LEGACY) || defined(UW_V1)
 __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigin, const float3 rayDir, const int iteration,
                                               const int currentMaterialId, const int lightId, const int objectId)
 {
@@ -1263,6 +1449,7 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     const float4* __restrict__ leafRecs = cS.leafRecs;
     const int* __restrict__ metas = cS.meta;
     const bool extended = cSI.extendedGeometry != 0;
+#ifdef UW_LEGACY
     __shared__ int2 s_stack[SM_STACK * WALK_THREADS];
     int stackRef[UN_STACK - SM_STACK];
     float stackT[UN_STACK - SM_STACK];
@@ -1270,6 +1457,13 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     st.sm = s_stack + threadIdx.x; st.lref = stackRef; st.lt = stackT;
     int sp = 1;
     st.push(0, 0, 0.f);
+#else
+    __shared__ int2 s_stack[WALK_STACK * WALK_THREADS];
+    unsigned int sp, spLimit;
+    int cur;
+    int2 spillBuf[WALK_SPILL];
+    int nSpill = 0;
+#endif
     int candIdx[GATHER_CAP], candLeaf[GATHER_CAP];
     float candD[GATHER_CAP], candLeafT[GATHER_CAP];
     int n = 0;
@@ -1287,11 +1481,16 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     // count there; only hits ahead of it count in the first.
     const float4* __restrict__ nodes = cS.uwnodes;
     const int nbMain = cS.nbUWide;
+#ifdef UW_LEGACY
     if (cS.nbUX > 0) { st.push(1, nbMain, -3.0e38f); sp = 2; }
+#else
+    walkStart(s_stack, nbMain, cS.nbUX > 0, spLimit, sp, cur);
+#endif
     bool done = false;
     DBG_DECL(int dbgVisits = 0;)
     while (!done)
     {
+#ifdef UW_LEGACY
         int cur = WIDE_NONE;
         while (sp > 0)
         {
@@ -1306,10 +1505,34 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
         }
         if (overflow) break;
         if (cur == WIDE_NONE) break;
+#else
+        // node rounds until this lane holds a leaf or has nothing left (nodes and WALK_POP are >= 0, leaves and WALK_DONE < 0)
+        while (cur >= 0)
+        {
+            DBG_ADD(5, 1); DBG_DECL(++dbgVisits;)
+            if (!walkRound(nodes, nbMain, q, cullT, spLimit, sp, cur))
+            {
+                // no room for this node's children: make some (the round is repeated), or give up on a degenerate tree
+                DBG_ADD(3, 1);
+                if (!walkSpill(s_stack, spillBuf, nSpill, sp)) { overflow = true; break; }
+            }
+        }
+        if (overflow) break;
+        if (cur == WALK_DONE)
+        {
+            if (nSpill == 0) break;
+            walkUnspill(s_stack, spillBuf, nSpill, sp);
+            cur = WALK_POP;
+            continue;
+        }
+#endif
         // a BVH leaf is one primitive
         {
             const bool behind = ((~cur) & 0x40000000) != 0; // from the point-query tree
             const int idx = (~cur) & 0x3FFFFFFF;
+#ifndef UW_LEGACY
+            cur = WALK_POP; // whatever happens to this leaf, the next round takes an entry from the stack
+#endif
             const int meta = __ldg(metas + idx);
             const int fast = PM_FAST(meta);
             bool test;
@@ -1382,7 +1605,7 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
             }
         }
     }
-    DBG_ADD(2, 1); DBG_ADD(3, overflow ? 1 : 0); DBG_ADD(4, n); DBG_MAX(6, dbgVisits); DBG_ADD(1, dbgVisits > 200 ? 1 : 0); DBG_ADD(0, dbgVisits > 1000 ? 1 : 0);
+    DBG_ADD(2, 1); DBG_ADD(3, overflow ? 1 : 0); DBG_ADD(4, n); DBG_MAX(6, dbgVisits);
     if (overflow)
     {
         out.hit.prim = -2; out.shadow = -1.f; // caller runs the ordered walk
@@ -1425,6 +1648,254 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     }
     return out;
 }
+
+#else
+// ---------------------------------------------------------------------------------------------------
+// The unit walk (round 2).  What the ncu source view of the round-1 walk showed: a node round takes a warp ~2 500 cycles whatever
+// the number of lanes in it (16 for primary rays, 6 for bounce rays) — it is one dependent memory access plus a long dependent
+// instruction chain, not issue slots — and a leaf visit was FOUR dependent accesses (packed word -> geometry -> leaf number ->
+// leaf box).  So the walk is rebuilt around "one dependent access per step, and every lane takes a step in every iteration":
+//   * a lane's current item is a node (128-byte record) or a primitive (96-byte record holding geometry, packed word, its
+//     reference leaf's box and number, its original id); every iteration each lane loads ITS item with the same 256-bit loads
+//     at the top of the loop, then the node lanes run the node round (keys, nearest child next, the other hit children pushed)
+//     and the leaf lanes the primitive test, the reference's leaf-box test and the acceptance rule — both from registers;
+//   * a lane that pops a leaf or a node works on it in the same iteration; nobody waits for the other lanes to reach a leaf.
+// Same candidates, same acceptance rules, same results as the round-1 walk (tests/test_gpu_parity.py compares it with the
+// ordered walks and with the reference CUDA engine).
+// ---------------------------------------------------------------------------------------------------
+SB_DEV void nodeKeysRegs(const float4 lx, const float4 ly, const float4 lz, const float4 hx, const float4 hy, const float4 hz, const float4 rf,
+                         const NodeRay& q, const float tLimit, NodeKeys& o)
+{
+    const bool sx = q.ix < 0.f, sy = q.iy < 0.f, sz = q.iz < 0.f;
+    o.refs = make_int4(__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w));
+#define UN_NEAR(A, C) (s##A ? h##A.C : l##A.C)
+#define UN_FAR(A, C) (s##A ? l##A.C : h##A.C)
+#define UN_KEY(C, K, J)                                                                                              \
+    {                                                                                                                \
+        const float tnx = __fmaf_rn(UN_NEAR(x, C), q.ix, q.nox), tfx = __fmaf_rn(UN_FAR(x, C), q.ix, q.nox);         \
+        const float tny = __fmaf_rn(UN_NEAR(y, C), q.iy, q.noy), tfy = __fmaf_rn(UN_FAR(y, C), q.iy, q.noy);         \
+        const float tnz = __fmaf_rn(UN_NEAR(z, C), q.iz, q.noz), tfz = __fmaf_rn(UN_FAR(z, C), q.iz, q.noz);         \
+        const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.f), tmax = fminf(fminf(fminf(tfx, tfy), tfz), tLimit); \
+        K = (tmin <= tmax) ? ((__float_as_int(tmin) & ~3) | J) : KEY_MISS;                                           \
+    }
+    UN_KEY(x, o.k0, 0) UN_KEY(y, o.k1, 1) UN_KEY(z, o.k2, 2) UN_KEY(w, o.k3, 3)
+#undef UN_KEY
+#undef UN_NEAR
+#undef UN_FAR
+}
+
+// dispatch on type with the geometry already in registers (primitiveTest() loads it)
+SB_DEV bool primitiveTestRegs(const float4 g0, const float4 g1, const float4 g2, const float4 g3, const int idx, const int meta, const Ray& r,
+                              float3& I, int& flags, float& planeShadow)
+{
+    const float eps = cSI.geometryEpsilon;
+    flags = 0;
+    if (!cSI.extendedGeometry) return triangleTest(g0, g1, g2, r, eps, I);
+    switch (PM_TYPE(meta))
+    {
+    case B200_PT_ENVIRONMENT:
+    case B200_PT_SPHERE: return sphereTest(g0, r, eps, I, flags);
+    case B200_PT_CYLINDER:
+    case B200_PT_CONE: return cylinderTest(g0, g1, g3, r, eps, I);
+    case B200_PT_ELLIPSOID: return ellipsoidTest(g0, f3(g0.w, g1.w, g2.w), r, eps, I);
+    case B200_PT_TRIANGLE: return triangleTest(g0, g1, g2, r, eps, I);
+    default: return planeTest(idx, r, I, flags, planeShadow);
+    }
+}
+
+
+__device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigin, const float3 rayDir, const int iteration,
+                                              const int currentMaterialId, const int lightId, const int objectId)
+{
+    WalkOut out;
+    out.hit.prim = -1; out.hit.p = f3(0.f, 0.f, 0.f); out.hit.flags = 0; out.shadow = 0.f;
+    const float minDistance0 = (iteration < 2) ? cSI.viewDistance : cSI.viewDistance / (iteration + 1);
+    const float shadowLimit = cSI.shadowIntensity;
+    if (mode == UW_SHADOW && !(0.f < shadowLimit)) return out;
+    Ray r;
+    makeRay(r, rayOrigin, rayDir);
+    NodeRay q;
+    nodeRay(q, r);
+    const float eps = cSI.geometryEpsilon;
+    const float len2 = dot(r.d, r.d);
+    const float invLen = rsqrtf(len2) * 1.0001f; // world distance -> t, with slack so culling stays conservative
+    const float lenOL = sqrtf(len2);             // shadow: distance to the lamp (length(O_L), :877)
+    const bool extended = cSI.extendedGeometry != 0;
+    __shared__ int2 s_stack[WALK_STACK * WALK_THREADS];
+    unsigned int sp, spLimit;
+    int cur;
+    int2 spillBuf[WALK_SPILL];
+    int nSpill = 0;
+    int candIdx[GATHER_CAP], candLeaf[GATHER_CAP];
+    float candD[GATHER_CAP], candLeafT[GATHER_CAP];
+    int n = 0;
+    bool overflow = false;
+    float best = minDistance0;   // closest accepted / gathered distance so far
+    float window = minDistance0; // UW_GATHER: candidates farther than this are inert
+    // entry-t bound for nodes: never beyond the reference's own t_min < closest-so-far test; a shadow blocker lies before the lamp (t ~ 1)
+    float cullT = (mode == UW_SHADOW) ? fminf(minDistance0, UW_SHADOW_TLIMIT) : fminf(minDistance0, minDistance0 * invLen);
+    if (mode == UW_GATHER) cullT = minDistance0;
+    const float4* __restrict__ nodes = cS.uwnodes;
+    const float4* __restrict__ recs = cS.primRecs;
+    const int nbMain = cS.nbUWide;
+    walkStart(s_stack, nbMain, cS.nbUX > 0, spLimit, sp, cur);
+    DBG_DECL(int dbgVisits = 0;)
+    while (true)
+    {
+        if (cur == WALK_POP)
+        {
+            sp -= WALK_STACK_STRIDE;
+            const int2 e = stackGet(sp);
+            cur = (__int_as_float(e.y) > cullT) ? WALK_POP : e.x; // the bound shrank since this entry was pushed
+            if (cur == WALK_POP) continue;
+        }
+        if (cur == WALK_DONE)
+        {
+            if (nSpill == 0) break;
+            walkUnspill(s_stack, spillBuf, nSpill, sp);
+            cur = WALK_POP;
+            continue;
+        }
+        // ---- this lane's item: one dependent access, the same instructions for nodes and primitives
+        const bool isNode = cur >= 0;
+        const int idx = (~cur) & 0x3FFFFFFF;
+        const float4* item = isNode ? nodes + (size_t)8 * cur : recs + (size_t)PRIM_REC_F4 * idx;
+        float4 a0, a1, a2, a3, a4, a5, a6 = f4(0.f, 0.f, 0.f, 0.f), a7;
+        ldNode256(item, a0, a1); ldNode256(item + 2, a2, a3); ldNode256(item + 4, a4, a5);
+        if (isNode) ldNode256(item + 6, a6, a7);
+        if (isNode)
+        {
+            DBG_ADD(5, 1); DBG_DECL(++dbgVisits;)
+            if (sp >= spLimit)
+            {
+                DBG_ADD(3, 1);
+                if (!walkSpill(s_stack, spillBuf, nSpill, sp)) { overflow = true; break; } // degenerate tree
+            }
+            NodeKeys h;
+            nodeKeysRegs(a0, a1, a2, a3, a4, a5, a6, q, (cur >= nbMain) ? 0.f : cullT, h);
+            const int kmin = min(min(h.k0, h.k1), min(h.k2, h.k3));
+            const int c = kmin & 3;
+            const int ra = (c & 1) ? h.refs.y : h.refs.x, rb = (c & 1) ? h.refs.w : h.refs.z;
+            cur = (kmin == KEY_MISS) ? WALK_POP : ((c & 2) ? rb : ra);
+            // keys are distinct (child number in the low bits), so "!= kmin" singles out the nearest; all KEY_MISS when nothing is hit
+            if ((h.k0 != kmin) & (h.k0 != KEY_MISS)) { stackPut(sp, h.refs.x, h.k0); sp += WALK_STACK_STRIDE; }
+            if ((h.k1 != kmin) & (h.k1 != KEY_MISS)) { stackPut(sp, h.refs.y, h.k1); sp += WALK_STACK_STRIDE; }
+            if ((h.k2 != kmin) & (h.k2 != KEY_MISS)) { stackPut(sp, h.refs.z, h.k2); sp += WALK_STACK_STRIDE; }
+            if ((h.k3 != kmin) & (h.k3 != KEY_MISS)) { stackPut(sp, h.refs.w, h.k3); sp += WALK_STACK_STRIDE; }
+            continue;
+        }
+        // ---- a BVH leaf is one primitive
+        const bool behind = ((~cur) & 0x40000000) != 0; // from the point-query tree
+        cur = WALK_POP;                                 // whatever happens to this leaf, the next thing is the stack
+        const int meta = __float_as_int(a3.w);
+        const int fast = PM_FAST(meta);
+        bool test;
+        if (mode == UW_SHADOW)
+        {
+            const int origIndex = __float_as_int(a5.w);
+            const int type = extended ? PM_TYPE(meta) : B200_PT_TRIANGLE;
+            // objectId is a compacted index compared with an original id — as the reference does (:829)
+            test = fast == 0 && origIndex != lightId && origIndex != objectId && type != B200_PT_CAMERA && type != B200_PT_ENVIRONMENT &&
+                   !(type == B200_PT_TRIANGLE && cSI.doubleSidedTriangles);
+        }
+        else
+            test = fast == 0 || (fast == 1 && currentMaterialId != PM_MATERIAL(meta));
+        if (!test) continue;
+        float3 I;
+        int flags;
+        float planeShadow;
+        DBG_ADD(7, 1);
+        if (!primitiveTestRegs(a0, a1, a2, a3, idx, meta, r, I, flags, planeShadow)) continue;
+        const float distance = length(I - r.o);
+        if (!(distance > eps)) continue;
+        if ((dot(I - r.o, r.d) < 0.f) != behind) continue; // hits behind the origin (cylinders/cones only) come from the point query
+        // the reference only tests a primitive whose leaf box passes its slab test (:690); checked for hits only
+        // (UW_CLOSEST: t_min(leaf) <= entry distance <= hit distance < closest-so-far whenever the hit would be accepted, so only the
+        //  geometric part of the leaf test can reject it)
+        float leafT;
+        if (!slabT(a4, a5, r, (mode == UW_CLOSEST) ? 3.0e38f : minDistance0, leafT)) continue;
+        if (mode == UW_SHADOW)
+        {
+            if (distance < lenOL) { out.shadow = fmaxf(0.f, fminf(shadowLimit, shadowLimit)); break; }
+        }
+        else if (mode == UW_CLOSEST)
+        {
+            if (distance < best || (distance == best && out.hit.prim >= 0 && idx < out.hit.prim))
+            {
+                best = distance;
+                out.hit.prim = idx; out.hit.p = I; out.hit.flags = flags;
+                cullT = fminf(minDistance0, best * invLen);
+            }
+        }
+        else if (distance < minDistance0 && distance <= window)
+        {
+            if (distance < best)
+            {
+                best = distance;
+                window = fminf(minDistance0, GATHER_WINDOW * best);
+                cullT = fminf(minDistance0, window * invLen);
+            }
+            if (n == GATHER_CAP)
+            {
+                int m2 = 0; // full: drop what fell out of the window meanwhile
+                for (int j = 0; j < n; ++j)
+                    if (candD[j] <= window)
+                    {
+                        candIdx[m2] = candIdx[j]; candD[m2] = candD[j]; candLeafT[m2] = candLeafT[j]; candLeaf[m2] = candLeaf[j];
+                        ++m2;
+                    }
+                n = m2;
+            }
+            if (n == GATHER_CAP) { overflow = true; break; }
+            // appended in visiting order; the replay below picks them in array order
+            candIdx[n] = idx; candD[n] = distance; candLeafT[n] = leafT; candLeaf[n] = __float_as_int(a4.w);
+            ++n;
+        }
+    }
+    DBG_ADD(2, 1); DBG_ADD(3, overflow ? 1 : 0); DBG_ADD(4, n); DBG_MAX(6, dbgVisits);
+    if (overflow)
+    {
+        out.hit.prim = -2; out.shadow = -1.f; // caller runs the ordered walk
+        return out;
+    }
+    if (mode != UW_GATHER) return out;
+    // replay in array order (selection by ascending index: the list is short; a cylinder listed twice by the point query is
+    // taken once).  Primitives of one leaf are contiguous and share the leaf's fate, decided when the leaf is reached (before
+    // any of its primitives): t_min(leaf) < closest-so-far.
+    float m = minDistance0;
+    bool leafPass = false;
+    int prevLeaf = -1;
+    int winner = -1;
+    int last = -1;
+    for (int pass = 0; pass < n; ++pass)
+    {
+        int bj = -1, bi = 0x7fffffff;
+        for (int j = 0; j < n; ++j)
+        {
+            const int ci = candIdx[j];
+            if (ci > last && ci < bi && candD[j] <= window) { bi = ci; bj = j; }
+        }
+        if (bj < 0) break;
+        last = bi;
+        if (candLeaf[bj] != prevLeaf)
+        {
+            leafPass = candLeafT[bj] < m;
+            prevLeaf = candLeaf[bj];
+        }
+        if (leafPass && candD[bj] < m) { m = candD[bj]; winner = bi; }
+    }
+    if (winner >= 0)
+    {
+        const int meta = __ldg(cS.meta + winner);
+        float3 I;
+        int flags;
+        float planeShadow;
+        primitiveTest(winner, meta, r, I, flags, planeShadow); // deterministic: same hit point as when it was gathered
+        out.hit.prim = winner; out.hit.p = I; out.hit.flags = flags;
+    }
+    return out;
+}
+#endif
 
 SB_DEV Hit closestHitOrderIndependent(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)
 {
