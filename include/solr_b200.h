@@ -79,8 +79,7 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
  * key 8 = bounce pass p whose queue holds at most p times this percentage of the GPU's resident lanes carries its paths to the
  *         end of their ray trees in registers instead of queueing them for one more launch per pass (default 300; 0 = never).
  * key 9 = order in which a GPU's own tiles are handed to its warps: 0 row-major (default), 1 along a Z-order curve.
- * Builds with -DWITH_TRACE_SLICE only (sol-r_b200/csrc/traceslice.cuh, experimental): key 6 = 3 walks the bounce passes in slices,
- * key 10 = node visits per slice (24), key 11 = slices per pass (6). */
+ */
 void b200_set_option(int key, int value);
 /* Multi-GPU frame split: this process renders tiles t with t % worldSize == rank (interleaved 8x4-pixel
  * tiles). Non-owned pixels of the device bitmap/ids stay zero so frames merge by summation. */

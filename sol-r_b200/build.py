@@ -33,14 +33,14 @@ def _stale(target, sources):
 
 def engine_sources():
     inc = os.path.join(os.path.dirname(HERE), "include")
-    return [os.path.join(CSRC, f) for f in ("engine.cu", "shade.cuh", "trace.cuh", "tracequeue.cuh", "traceslice.cuh", "vec.cuh")] + \
+    return [os.path.join(CSRC, f) for f in ("engine.cu", "shade.cuh", "trace.cuh", "tracegroup.cuh", "vec.cuh")] + \
            [os.path.join(inc, f) for f in ("solr_b200.h", "solr_b200_types.h")]
 
 
 def build_engine(force=False, verbose=False, extra=()):
     src = engine_sources()
     if force or _stale(ENGINE_LIB, src):
-        # SOLR_B200_NVCC_FLAGS: extra flags for experimental builds, e.g. "-DWITH_TRACE_SLICE" (csrc/traceslice.cuh)
+        # SOLR_B200_NVCC_FLAGS: extra flags for experimental builds, e.g. "-DUW_GROUP=0" (one ray per lane instead of the group walk)
         cmd = [NVCC] + NVCC_FLAGS + list(extra) + os.environ.get("SOLR_B200_NVCC_FLAGS", "").split() + \
               (["-Xptxas", "-v"] if verbose else []) + ["-o", ENGINE_LIB, src[0]]
         subprocess.check_call(cmd)

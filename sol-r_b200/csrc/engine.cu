@@ -16,10 +16,6 @@
 
 #include "../../include/solr_b200.h"
 #include "shade.cuh"
-#include "tracequeue.cuh"
-#ifdef WITH_TRACE_SLICE
-#include "traceslice.cuh"
-#endif
 
 #define TILE_W 8
 #define TILE_H 4
@@ -469,12 +465,21 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
         Hit hit;
         hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
         const bool separateWalk = cS.nbUWide > 0 && cSI.renderBoxes == 0;
+#if UW_GROUP
+        if (separateWalk)
+        {
+            const float* w = cP.pathWords + slot;
+            const size_t n = cP.pathStride;
+            hit = closestHitGroup(f3(w[0], w[n], w[2 * n]), f3(w[3 * n], w[4 * n], w[5 * n]), pass, __float_as_int(w[7 * n]), has);
+        }
+#else
         if (separateWalk && has)
         {
             const float* w = cP.pathWords + slot;
             const size_t n = cP.pathStride;
             hit = closestHitOrderIndependent(f3(w[0], w[n], w[2 * n]), f3(w[3 * n], w[4 * n], w[5 * n]), pass, __float_as_int(w[7 * n]));
         }
+#endif
         PathState s;
         int index = 0;
         loadPath(slot, s, index);
@@ -499,7 +504,11 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
             routePath(live && !cont, s, C, p, slot, index); // ends here: reflected-ray stage or pixel
             live = cont;
             if (!__any_sync(FULL_MASK, live)) break;
+#if UW_GROUP
+            if (separateWalk) hit = closestHitGroup(s.curO, s.curT, p + 1, s.currentMaterialId, live);
+#else
             if (separateWalk && live) hit = closestHitOrderIndependent(s.curO, s.curT, p + 1, s.currentMaterialId);
+#endif
             pathPass(s, C, p + 1, live, index, f3(0.f, 0.f, 0.f), 0, cnt, separateWalk ? &hit : nullptr);
         }
         __syncwarp();
@@ -535,86 +544,6 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
             const int4 id = make_int4(s.idx, s.iteration, s.idz, s.idw);
             resolvePixel(index, color, f4(0.f, 0.f, 0.f, 0.f), id, s.depthOfField, *reinterpret_cast<float4*>(&cP.post[index].colorInfo));
         }
-        __syncwarp();
-    }
-    flushCounters(cnt.rays, 0);
-}
-
-// Staged rendering with the closest-hit walks in their own kernel (tracequeue.cuh): per pass
-//   k_trace_closest(p)  walks the rays of queue p with per-lane refill, writes hitWords
-//   k_shade_pass(p)     the rest of the pass (normal, shading, shadow ray, next ray), queues / ends the path
-// Pass 0 reads its rays from k_gen_primary, which lists every pixel that needs work.
-__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_gen_primary()
-{
-    const int lane = threadIdx.x & 31;
-    unsigned int pixelsTraced = 0;
-    Rotation rot;
-    rot.cx = cosf(cP.angles.x); rot.cy = cosf(cP.angles.y); rot.cz = cosf(cP.angles.z);
-    rot.sx = sinf(cP.angles.x); rot.sy = sinf(cP.angles.y); rot.sz = sinf(cP.angles.z);
-    const int warpsTotal = gridDim.x * (CTA_THREADS / 32);
-    for (int k = blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5); k < cP.nbLocalTiles; k += warpsTotal)
-    {
-        const int tile = k * cP.worldSize + cP.rank;
-        const int tx = tile % cP.tilesX, ty = tile / cP.tilesX;
-        const int xIn = tx * TILE_W + (lane & (TILE_W - 1));
-        const int yIn = ty * TILE_H + (lane / TILE_W);
-        const bool inFrame = xIn < cSI.size.x && yIn < cSI.size.y;
-        const int x = inFrame ? xIn : 0, y = inFrame ? yIn : 0;
-        const int index = y * cSI.size.x + x;
-        const int4 id = cP.ids[index];
-        const bool valid = inFrame && pixelNeedsWork(id);
-        const size_t slot = (size_t)k * 32 + lane;
-        if (valid)
-        {
-            pixelsTraced++;
-            float3 o, t;
-            primaryRay(rot, x, y, index, cP.post[index].colorInfo.w, o, t);
-            float* w = cP.pathWords + slot;
-            const size_t n = cP.pathStride;
-            w[0] = o.x; w[n] = o.y; w[2 * n] = o.z; w[3 * n] = t.x; w[4 * n] = t.y; w[5 * n] = t.z;
-            w[7 * n] = __int_as_float(-2); // currentMaterialId before the first hit (pathInit)
-            w[(size_t)(PATH_WORDS - 1) * n] = __int_as_float(index);
-        }
-        pushPaths(passQueue(0), valid, slot);
-    }
-    flushCounters(0, pixelsTraced);
-}
-
-__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_shade_pass(const int pass)
-{
-    const int lane = threadIdx.x & 31;
-    Counters cnt;
-    cnt.rays = 0;
-    const int q = passQueue(pass);
-    const unsigned int count = cP.queueCounters[2 * q];
-    const size_t n = cP.pathStride;
-    const int warpsTotal = gridDim.x * (CTA_THREADS / 32);
-    for (unsigned int base = 32u * (blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5)); base < count; base += 32u * warpsTotal)
-    {
-        const bool has = base + lane < count;
-        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)q * n + base + lane] : 0;
-        PathState s;
-        int index = 0;
-        float3 rayO = f3(0.f, 0.f, 0.f);
-        if (pass == 0)
-        {
-            const float* w = cP.pathWords + slot;
-            rayO = f3(w[0], w[n], w[2 * n]);
-            pathInit(s, rayO, f3(w[3 * n], w[4 * n], w[5 * n]));
-            index = __float_as_int(w[(size_t)(PATH_WORDS - 1) * n]);
-        }
-        else
-            loadPath(slot, s, index);
-        if (!has) index = 0;
-        Hit hit;
-        const float* hw = cP.hitWords + slot;
-        hit.prim = has ? __float_as_int(hw[0]) : -1;
-        hit.p = f3(hw[n], hw[2 * n], hw[3 * n]);
-        hit.flags = __float_as_int(hw[4 * n]);
-        GlobalColors C;
-        C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = n;
-        pathPass(s, C, pass, has, index, rayO, 0, cnt, &hit);
-        routePath(has, s, C, pass, slot, index);
         __syncwarp();
     }
     flushCounters(cnt.rays, 0);
@@ -813,14 +742,15 @@ struct Engine
     float4* dWide = nullptr; float4* dLeafRecs = nullptr; int nbWide = 0; size_t capWide = 0, capLeafRecs = 0;
     float4* dUWide = nullptr; int nbUWide = 0; size_t capUWide = 0; int opaqueShadows = 0;
     int nbUX = 0; // point-query tree for backward cylinder hits, appended to dUWide
+    float4* dUGroup = nullptr; size_t capUGroup = 0; // the same trees child-major (group walk)
+    float4* dGatherScratch = nullptr; size_t capGatherScratch = 0;
     int* dPrimLeaf = nullptr; size_t capPrimLeaf = 0;
     float4* dPrimRecs = nullptr; size_t capPrimRecs = 0; // 96-byte records of the unit walk (trace.cuh), 6 float4 per primitive
     // staged rendering
     float* dPathWords = nullptr; float4* dPathColors = nullptr; float* dPathContrib = nullptr; int* dPathQueues = nullptr;
     unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
     size_t pathFailedBytes = 0; // smallest path-state size that did not fit (not tried again)
-    float* dHitWords = nullptr;
-    int ctasPerSMStage[6] = {0, 0, 0, 0, 0, 0}; // k_stage_primary, k_stage_pass, k_stage_reflected, k_gen_primary, k_trace_closest, k_shade_pass
+    int ctasPerSMStage[3] = {0, 0, 0}; // k_stage_primary, k_stage_pass, k_stage_reflected
     float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
     b200_BoundingBox* dRawBoxes = nullptr;
     b200_Material* dMats = nullptr; int nbMats = 0;
@@ -1349,14 +1279,9 @@ struct SahBuilder
 
 int g_useWide = 1;
 int g_useUnordered = 1;
-#ifdef WITH_TRACE_SLICE
-int g_sliceRounds = 24; // node visits per slice
-int g_sliceCount = 6;   // slices per bounce pass, the last one unbounded
-#endif
 int g_tileOrder = 0; // order in which a GPU's own tiles are handed out: 0 row-major, 1 along a Z-order curve (neighbouring warps work on neighbouring tiles in both directions)
 int g_fuseTailPercent = 300; // k_stage_pass(p) carries its paths to the end in registers when the queue holds at most p times this share of the resident lanes (0: never)
-int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: also the closest-hit walks in their own kernel
-int g_traceCtasPerSM = 0; // experiment: resident CTAs per SM for the trace-queue kernel (0 = occupancy maximum)
+int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
@@ -1406,13 +1331,7 @@ void b200_set_option(int key, int value)
     else if (key == 3) g_useWide = value != 0;
     else if (key == 4) g_useUnordered = value != 0;
     else if (key == 5) g_useBackward = value != 0;
-#ifdef WITH_TRACE_SLICE
-    else if (key == 6 && value == 3) g_useStaged = 3; // sliced walks for the bounce passes (traceslice.cuh)
-    else if (key == 10 && value >= 1) g_sliceRounds = value;
-    else if (key == 11 && value >= 2 && value <= 32) g_sliceCount = value;
-#endif
-    else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value;
-    else if (key == 7 && value >= 0) g_traceCtasPerSM = value;
+    else if (key == 6 && value >= 0 && value <= 1) g_useStaged = value;
     else if (key == 8 && value >= 0) g_fuseTailPercent = value;
     else if (key == 9 && (value == 0 || value == 1)) g_tileOrder = value;
     else latch(-11, "b200_set_option", "unknown option");
@@ -1485,9 +1404,6 @@ void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_primary, CTA_THREADS, 0)); G.ctasPerSMStage[0] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_pass, CTA_THREADS, 0)); G.ctasPerSMStage[1] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_reflected, CTA_THREADS, 0)); G.ctasPerSMStage[2] = perSM > 0 ? perSM : 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_gen_primary, CTA_THREADS, 0)); G.ctasPerSMStage[3] = perSM > 0 ? perSM : 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace_closest, CTA_THREADS, 0)); G.ctasPerSMStage[4] = perSM > 0 ? perSM : 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_shade_pass, CTA_THREADS, 0)); G.ctasPerSMStage[5] = perSM > 0 ? perSM : 1;
     G.initialised = true;
     G.launches = 0;
 }
@@ -1501,10 +1417,11 @@ void b200_finalize_scene(b200_int2)
     closePeerFrame();
     freeDev(G.dWide); freeDev(G.dLeafRecs); G.capWide = G.capLeafRecs = 0; G.nbWide = 0;
     freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0; freeDev(G.dPrimRecs); G.capPrimRecs = 0;
+    freeDev(G.dUGroup); G.capUGroup = 0; freeDev(G.dGatherScratch); G.capGatherScratch = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
     freeDev(G.dTileCounter); freeDev(G.dWork); freeDev(G.dTileOrder); G.capTileOrder = 0; G.tileOrderKey[0] = 0;
-    freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters); freeDev(G.dHitWords);
+    freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters);
     G.pathStride = 0; G.pathIterations = 0;
     if (G.evStart) { cudaEventDestroy(G.evStart); G.evStart = nullptr; }
     if (G.evStop) { cudaEventDestroy(G.evStop); G.evStop = nullptr; }
@@ -1741,6 +1658,26 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     if (nbPrims > 0) CK(cudaMemcpyAsync(G.dPrimLeaf, primLeaf.data(), (size_t)nbPrims * sizeof(int), cudaMemcpyHostToDevice, G.stream));
     if (uwide.size() > G.capUWide) { freeDev(G.dUWide); G.capUWide = uwide.size() + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
     if (!uwide.empty()) CK(cudaMemcpyAsync(G.dUWide, uwide.data(), uwide.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+    // child-major copy for the group walk: child c of node n at float4 (n * width + c) * 2 — (lo.xyz, hi.x) (hi.yz, ref, -)
+    std::vector<float4> ugroup;
+#if UW_GROUP
+    {
+        const int recs = UW_WIDTH / 4;
+        const size_t nbNodes = uwide.size() / (8 * (size_t)recs);
+        ugroup.resize(nbNodes * UW_WIDTH * 2 + 2);
+        for (size_t n = 0; n < nbNodes; ++n)
+            for (int c = 0; c < UW_WIDTH; ++c)
+            {
+                const float4* rec = &uwide[8 * (n * recs + c / 4)];
+                const int k = c % 4;
+                auto comp = [k](const float4& v) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; };
+                ugroup[(n * UW_WIDTH + c) * 2] = make_float4(comp(rec[0]), comp(rec[1]), comp(rec[2]), comp(rec[3]));
+                ugroup[(n * UW_WIDTH + c) * 2 + 1] = make_float4(comp(rec[4]), comp(rec[5]), comp(rec[6]), 0.f);
+            }
+        if (ugroup.size() > G.capUGroup) { freeDev(G.dUGroup); G.capUGroup = ugroup.size() + 1024; CK(cudaMalloc(&G.dUGroup, G.capUGroup * sizeof(float4))); }
+        if (nbNodes > 0) CK(cudaMemcpyAsync(G.dUGroup, ugroup.data(), ugroup.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+    }
+#endif
     CK(cudaStreamSynchronize(G.stream));
 
     // 3. primitives
@@ -1908,6 +1845,22 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.scene.primLeaf = G.dPrimLeaf; P.scene.primRecs = G.dPrimRecs;
     P.scene.uwnodes = G.dUWide; P.scene.nbUWide = (g_useWide && g_useUnordered) ? G.nbUWide : 0; P.scene.opaqueShadows = G.opaqueShadows;
     P.scene.nbUX = g_useBackward ? G.nbUX : 0;
+    P.scene.ugnodes = G.dUGroup;
+#if UW_GROUP
+    if (P.scene.nbUWide > 0)
+    {
+        // candidate lists of the group walk's bounce rays: one per ray slot of every warp a launch can hold
+        const size_t want = (size_t)G.numSMs * 16 * (CTA_THREADS / 32) * 32 * GW_GATHER_CAP;
+        if (want > G.capGatherScratch)
+        {
+            CK(cudaStreamSynchronize(G.stream));
+            freeDev(G.dGatherScratch);
+            CK(cudaMalloc(&G.dGatherScratch, want * sizeof(float4)));
+            G.capGatherScratch = want;
+        }
+        P.gatherScratch = G.dGatherScratch;
+    }
+#endif
     P.scene.rawBoxes = G.dRawBoxes; P.scene.nbRawBoxes = objects.x < G.nbBoxesIn ? objects.x : G.nbBoxesIn;
     P.si = si; P.pp = pp;
     P.eye = make_float3(origin.x, origin.y, origin.z);
@@ -1948,7 +1901,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     int maxIteration = (si.graphicsLevel < B200_GL_REFLECTIONS) ? 1 : si.nbRayIterations + si.pathTracingIteration;
     maxIteration = maxIteration > B200_NB_MAX_ITERATIONS ? B200_NB_MAX_ITERATIONS : maxIteration;
     const bool giRays = (si.advancedIllumination == B200_AI_BASIC || si.advancedIllumination == B200_AI_FULL);
-    bool staged = g_useStaged && (maxIteration > 1 || g_useStaged >= 2) && !giRays && si.renderBoxes == 0 &&
+    bool staged = g_useStaged && maxIteration > 1 && !giRays && si.renderBoxes == 0 &&
                         (si.cameraType == B200_CT_PERSPECTIVE || si.cameraType == B200_CT_ORTHOGRAPHIC);
     if (staged)
     {
@@ -1958,7 +1911,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         else if (stride > G.pathStride || maxIteration > G.pathIterations)
         {
             CK(cudaStreamSynchronize(G.stream));
-            freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dHitWords);
+            freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues);
             G.pathStride = stride > G.pathStride ? stride : G.pathStride;
             G.pathIterations = maxIteration > G.pathIterations ? maxIteration : G.pathIterations;
             // path state is ~0.3 KB per pixel and pass: if the device cannot hold it (very large frames next to a large scene),
@@ -1966,12 +1919,11 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
             const bool ok = cudaMalloc(&G.dPathWords, PATH_WORDS * G.pathStride * sizeof(float)) == cudaSuccess &&
                             cudaMalloc(&G.dPathColors, (size_t)G.pathIterations * G.pathStride * sizeof(float4)) == cudaSuccess &&
                             cudaMalloc(&G.dPathContrib, (size_t)G.pathIterations * G.pathStride * sizeof(float)) == cudaSuccess &&
-                            cudaMalloc(&G.dPathQueues, ((size_t)G.pathIterations + 1) * G.pathStride * sizeof(int)) == cudaSuccess &&
-                            cudaMalloc(&G.dHitWords, HIT_WORDS * G.pathStride * sizeof(float)) == cudaSuccess;
+                            cudaMalloc(&G.dPathQueues, ((size_t)G.pathIterations + 1) * G.pathStride * sizeof(int)) == cudaSuccess;
             if (!ok)
             {
                 cudaGetLastError();
-                freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dHitWords);
+                freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues);
                 G.pathStride = 0; G.pathIterations = 0;
                 G.pathFailedBytes = wantBytes;
                 staged = false;
@@ -1983,7 +1935,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     {
         if (!G.dQueueCounters) CK(cudaMalloc(&G.dQueueCounters, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int)));
         P.pathWords = G.dPathWords; P.pathColors = G.dPathColors; P.pathContributions = G.dPathContrib; P.pathQueues = G.dPathQueues;
-        P.queueCounters = G.dQueueCounters; P.pathStride = G.pathStride; P.maxIteration = maxIteration; P.hitWords = G.dHitWords;
+        P.queueCounters = G.dQueueCounters; P.pathStride = G.pathStride; P.maxIteration = maxIteration;
     }
 
     CK(cudaEventRecord(G.evStart, G.stream));
@@ -2001,61 +1953,6 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     else
     {
         CK(cudaMemsetAsync(G.dQueueCounters, 0, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int), G.stream));
-#ifdef WITH_TRACE_SLICE
-        static float* dSliceState = nullptr; static float4* dSliceCand = nullptr; static int* dSliceQueues = nullptr;
-        static unsigned int* dSliceCounters = nullptr; static size_t sliceStride = 0;
-        bool sliced = g_useStaged == 3 && P.scene.nbUWide > 0;
-        if (sliced && sliceStride < G.pathStride)
-        {
-            CK(cudaStreamSynchronize(G.stream));
-            freeDev(dSliceState); freeDev(dSliceCand); freeDev(dSliceQueues);
-            if (!dSliceCounters) CK(cudaMalloc(&dSliceCounters, 4 * sizeof(unsigned int)));
-            sliced = cudaMalloc(&dSliceState, (size_t)SLICE_WORDS * G.pathStride * sizeof(float)) == cudaSuccess &&
-                     cudaMalloc(&dSliceCand, (size_t)GATHER_CAP * G.pathStride * sizeof(float4)) == cudaSuccess &&
-                     cudaMalloc(&dSliceQueues, 2 * G.pathStride * sizeof(int)) == cudaSuccess;
-            if (!sliced) { cudaGetLastError(); freeDev(dSliceState); freeDev(dSliceCand); freeDev(dSliceQueues); sliceStride = 0; }
-            else sliceStride = G.pathStride;
-        }
-        if (sliced)
-        {
-            SliceParams SP;
-            SP.state = dSliceState; SP.cand = dSliceCand; SP.queues = dSliceQueues; SP.counters = dSliceCounters;
-            CK(cudaMemcpyToSymbolAsync(cSlice, &SP, sizeof(SP), 0, cudaMemcpyHostToDevice, G.stream));
-            int g0 = G.numSMs * G.ctasPerSMStage[0];
-            if (g0 > needed) g0 = needed > 0 ? needed : 1;
-            k_stage_primary<<<g0, CTA_THREADS, 0, G.stream>>>();
-            int perSM = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace_slice, CTA_THREADS, 0));
-            const int gs = G.numSMs * (perSM > 0 ? perSM : 1);
-            for (int pass = 1; pass < maxIteration; ++pass)
-            {
-                for (int sl = 0; sl < g_sliceCount; ++sl)
-                {
-                    CK(cudaMemsetAsync(dSliceCounters + 2 * (sl & 1), 0, 2 * sizeof(unsigned int), G.stream)); // the queue this slice fills
-                    k_trace_slice<<<gs, CTA_THREADS, 0, G.stream>>>(pass, sl, sl == g_sliceCount - 1 ? 0x7fffffff : g_sliceRounds);
-                }
-                k_shade_pass<<<G.numSMs * G.ctasPerSMStage[5], CTA_THREADS, 0, G.stream>>>(pass);
-            }
-            k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
-            G.launches += 2 + (maxIteration - 1) * (g_sliceCount + 1);
-        }
-        else
-#endif
-        if (g_useStaged >= 2 && P.scene.nbUWide > 0)
-        {
-            // walks in their own kernel, per-lane refill from the ray queue
-            int gg = G.numSMs * G.ctasPerSMStage[3];
-            if (gg > needed) gg = needed > 0 ? needed : 1;
-            k_gen_primary<<<gg, CTA_THREADS, 0, G.stream>>>();
-            for (int pass = 0; pass < maxIteration; ++pass)
-            {
-                k_trace_closest<<<G.numSMs * ((g_traceCtasPerSM > 0 && g_traceCtasPerSM < G.ctasPerSMStage[4]) ? g_traceCtasPerSM : G.ctasPerSMStage[4]), CTA_THREADS, 0, G.stream>>>(pass);
-                k_shade_pass<<<G.numSMs * G.ctasPerSMStage[5], CTA_THREADS, 0, G.stream>>>(pass);
-            }
-            k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
-            G.launches += 2 * maxIteration + 2;
-        }
-        else
         {
             int g0 = G.numSMs * G.ctasPerSMStage[0];
             if (g0 > needed) g0 = needed > 0 ? needed : 1;

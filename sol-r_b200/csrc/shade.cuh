@@ -271,6 +271,17 @@ SB_DEV float4 traceShadow(const float3 center, const float3 I, const int lightId
     {
         if (__any_sync(FULL_MASK, need)) sh = shadowWalkPacket(center, I, lightId, iteration, objectId, need);
     }
+#if UW_GROUP
+    else if (cS.nbUWide > 0)
+    {
+        // every lane calls the group walk; |direction| = distance to the lamp; any-hit is exact when every caster is opaque
+        const float3 d = center - I;
+        const bool grouped = need && cS.opaqueShadows && dot(d, d) >= 1.0002f;
+        const WalkOut w = groupWalk(grouped, UW_SHADOW, I + normalize(d) * cSI.rayEpsilon, d, iteration, 0, lightId, objectId);
+        if (grouped) sh.w = w.shadow;
+        if (need && (!grouped || w.shadow < 0.f)) sh = shadowWalkWide(center, I, lightId, iteration, objectId); // < 0: overflow in a degenerate tree
+    }
+#endif
     else if (need)
     {
         if (cS.nbUWide > 0)
@@ -492,6 +503,12 @@ SB_DEV Hit traceClosest(const float3 o, const float3 t, const int iteration, con
     {
         if (__any_sync(FULL_MASK, need)) hit = closestHitPacket(o, t, iteration, matId, need);
     }
+#if UW_GROUP
+    else if (cS.nbUWide > 0)
+    {
+        hit = closestHitGroup(o, t, iteration, matId, need); // every lane calls
+    }
+#endif
     else if (need)
     {
         if (cS.nbUWide > 0)

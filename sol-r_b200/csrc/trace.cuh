@@ -57,6 +57,8 @@ struct SceneDev
     // one 96-byte record per primitive for the unit walk (engine.cu step 2d): everything a leaf visit needs behind ONE dependent
     // load — (p0, size.x) (p1, size.y) (p2, size.z) (n1, packed word) (reference leaf box min, leaf number) (leaf box max, original id)
     const float4* __restrict__ primRecs;
+    // the unordered trees once more, child-major for the group walk (tracegroup.cuh): 32 bytes per child — (lo.xyz, hi.x) (hi.yz, ref, -)
+    const float4* __restrict__ ugnodes;
     int opaqueShadows; // every shadow caster blocks fully (no transparent material, no textured plane): any-hit is exact
 };
 
@@ -86,11 +88,11 @@ struct RenderParams
     float* pathWords;          // [PATH_WORDS][pathStride]
     float4* pathColors;        // [maxIteration][pathStride]
     float* pathContributions;  // [maxIteration][pathStride]
-    float* hitWords;           // [HIT_WORDS][pathStride] closest hit of the current pass (tracequeue.cuh)
     int* pathQueues;           // [maxIteration + 1][pathStride] path slots; queue q feeds pass q, queue maxIteration the reflected-ray stage
     unsigned int* queueCounters; // [2 * (B200_NB_MAX_ITERATIONS + 2)]: entries pushed, entries handed out
     size_t pathStride;
     int maxIteration;
+    float4* gatherScratch; // group walk: candidate lists of the bounce rays, [resident warps][32 ray slots][GW_GATHER_CAP]
 };
 
 // One frame's parameters live in constant memory (uploaded on the render stream before the launch):
@@ -1895,6 +1897,13 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     }
     return out;
 }
+#endif
+
+#ifndef UW_GROUP
+#define UW_GROUP 0 // 0: one ray per lane (unorderedWalk above, default); 1: walks shared out over groups of lanes (tracegroup.cuh; exact, measured slower: profiles/r02_history.md)
+#endif
+#if UW_GROUP
+#include "tracegroup.cuh"
 #endif
 
 SB_DEV Hit closestHitOrderIndependent(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)

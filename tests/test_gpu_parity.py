@@ -352,9 +352,8 @@ def test_every_case_against_the_reference_cuda_engine(name):
 
 @pytest.mark.parametrize("cfg", ["config1", "molecule"])
 def test_drivers_produce_identical_frames(cfg):
-    """Option key 6: the single persistent kernel (0), the staged kernels (1, default) and the staged kernels with the
-    closest-hit walks in the trace-queue kernel (2) run the same device functions on the same rays: ids, the float
-    accumulation buffer and the RGB8 frame must be bit-identical, also across progressive frames."""
+    """Option key 6: the single persistent kernel (0) and the staged kernels (1, default) run the same device functions on
+    the same rays: ids, the float accumulation buffer and the RGB8 frame must be bit-identical, also across progressive frames."""
     W, H = 640, 360
     sc = scenes.config1(1000) if cfg == "config1" else scenes.molecule(cells=3)
     si = wire.default_scene_info(W, H, graphics_level=wire.GL_FULL, nb_ray_iterations=3)
@@ -365,8 +364,7 @@ def test_drivers_produce_identical_frames(cfg):
     h.close()
     rnd = gs.randoms(41)
     out = []
-    # mode 3 (sliced walks, csrc/traceslice.cuh) only exists in builds made with SOLR_B200_NVCC_FLAGS=-DWITH_TRACE_SLICE
-    for mode in (0, 1, 2) + ((3,) if "WITH_TRACE_SLICE" in os.environ.get("SOLR_B200_NVCC_FLAGS", "") else ()):
+    for mode in (0, 1):
         e = engine.Engine(si)
         try:
             e.set_option(6, mode)
