@@ -3,11 +3,14 @@
 
 A *step* is one full frame of the workload through the hot path: per-pixel ray generation, box-list walk,
 primitive tests, shading with shadow rays, reflection/refraction bounce loop, accumulation, RGB8 pack.
-A *ray* is one box-list walk (closest-hit or shadow), SURVEY.md §8(d).
+A *ray* is one box-list walk (closest-hit or shadow), SURVEY.md §8(d), counted in-kernel.
 
-  workload (N=1 and N>1): BASELINE.json configs[1] — the molecule scene (105 k atom spheres + bond cylinders +
-  ground + light = 216 k primitives), 1920x1080, 1 spp, shadows, 3 bounces (glFull, nbRayIterations=3),
-  synthetic (the reference's 486-atom PDB file does not travel; sol-r_b200/scenes.py generates the lattice).
+  workload  the headline line is BASELINE.json configs[1] (sol-r_b200/workloads.py "config2"): the molecule scene (105 k atom
+          spheres + bond cylinders + ground + light = 216 k primitives), 1920x1080, 1 spp, shadows, 3 bounces — synthetic
+          (the reference's 486-atom PDB file does not travel; sol-r_b200/scenes.py generates the lattice).  The other
+          configurations ride along in the same JSON line under "workloads" (fewer frames each): config4 (1 M spheres,
+          3840x2160, accumulated samples — the size north_star's 8-GPU efficiency target names) at every N; config3
+          (1 M triangles, 5 bounces) and config5 (anaglyph 4K, 16-frame progressive) at N = 1.  --workload X makes X the headline.
 
   value   whole-job Mrays/s with scene and frame state resident in HBM: K x b200_render, CUDA events on the
           render stream around each frame, L2 flushed (256 MiB memset) between frames, max over ranks.
@@ -15,16 +18,20 @@ A *ray* is one box-list walk (closest-hit or shadow), SURVEY.md §8(d).
           into the ray kernels — every rank stores its finished pixels straight into rank 0's device bitmap through NVLink
           peer memory (partition.PeerFrame) — and a one-element NCCL all-reduce inside the timed region orders the frame.
           After the timed runs rank 0 renders the whole frame alone and checks the merged frame against it, byte for byte.
-  e2e     the same metric through the host-side drop-in (SceneHost.render_begin + render_end = the calls
-          CudaKernel makes): per-frame parameter upload, kernels, device->host copy of RGB8 into caller-owned
-          host memory, wall clock.  The id buffer (16 B per pixel) is read back on demand (getPrimitiveAt), as the
-          drop-in does by default; the figure with the reference's every-frame id read-back is reported beside it.
+  e2e     the same metric through the host-side drop-in (SceneHost.render_begin + render_end = the calls CudaKernel makes) with
+          the REFERENCE'S protocol: per-frame parameter upload, kernels, device->host copy of RGB8 AND of the 16-byte-per-pixel
+          id buffer into caller-owned host memory (CudaKernel.cpp:304-313), wall clock.  The figure with the id buffer fetched on
+          demand (getPrimitiveAt is its only reader) is reported beside it as e2e.lazy_ids.
   roofline  FP32 CUDA-core roofline (north_star: compute-bound, no tensor cores): algorithmic flops counted by
-          the oracle in REFERENCE traversal order (SURVEY §8(d) constants) / device time / (148 SM x 128 lanes x
-          2 x sm_max_mhz).  HBM traffic is reported beside it.
-  cpu_baseline / --impl reference: the reference's own code on the host cores (oracle/_ref/libsolr_ref_cpu.so =
-          its CUDA source compiled for the host, OpenMP over blocks) when that library travelled, else the
-          oracle port; sample = one whole 1920x1080 frame of the same scene/camera per step (about 1.1-1.5 s on 16 cores).
+          the oracle in REFERENCE traversal order (SURVEY §8(d) constants) / device time / peak, peak = 148 SM x 128 lanes x
+          2 x sm_max_mhz; the FFMA rate and clock a microbenchmark sustains on this GPU are reported beside it
+          (b200_measure_fp32_peak).  DRAM traffic per frame comes from the committed ncu capture, stamped with its commit.
+  parity  (N = 1, headline) after the timed region the frame is rendered once more and compared with the reference's own CUDA
+          engine on the same GPU (oracle/_ref/libsolr_ref_cuda.so, when it travelled): differing hit ids, pixels beyond 2/255.
+  cpu_baseline / --impl reference: the reference's own code on the host cores (oracle/_ref/libsolr_ref_cpu.so = its CUDA source
+          compiled for the host with OpenMP over blocks — NOT its OpenCL engine: no OpenCL CPU device exists on the box,
+          profiles/r02_opencl_probe.txt) when that library travelled, else the oracle port; sample = one whole frame of the same
+          scene / camera per step.  The reference arm loads no library of the product.
 """
 import argparse
 import json
@@ -42,13 +49,9 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 
 import numpy as np  # noqa: E402
 
-W, H, NB_RAY_ITERATIONS = 1920, 1080, 3
-SAMPLE_W, SAMPLE_H = 1920, 1080   # the CPU legs render the whole frame of the workload (about 1.5 s per frame on 16 cores)
-WORKLOAD = "config2_molecule_216k_primitives_1920x1080_glFull_3_bounces"
-# algorithmic work of one frame of this workload (SURVEY.md 8(d) flop weights x the oracle's counts in the reference's traversal
-# order, full 1920x1080 frame; the N=1 run re-counts it live on the CPU sample)
-ALGORITHMIC_GFLOP_PER_FRAME = 37.2259
 SM_COUNT, LANES_PER_SM = 148, 128
+# per-workload frames when a workload rides along as a sub-record: (warm-up frames, timed frames)
+SUB_FRAMES = {"config2": (3, 12), "config3": (3, 8), "config4": (4, 12), "config5": (16, 32)}
 
 
 def peaks():
@@ -61,6 +64,14 @@ def peaks():
         pass
     p["fp32_tflops"] = SM_COUNT * LANES_PER_SM * 2 * p["sm_max_mhz"] * 1e6 / 1e12
     return p
+
+
+def recorded_flops():
+    try:
+        with open(os.path.join(ROOT, "profiles", "algorithmic_flops.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -130,155 +141,132 @@ def host_cores():
     return n
 
 
-# --workload: config2 is the configuration BASELINE.json's metric is quoted on (the default, and what the driver runs);
-# config4 (1 M spheres, 3840x2160, iterations 10..13 = 4 accumulated samples, one frame per step) is the size north_star's
-# 8-GPU efficiency target names.  The CPU legs and the roofline's flop count exist for config2 only.
-WORKLOADS = {
-    "config2": dict(name=WORKLOAD, size=(1920, 1080), nit=3, scene="config2", iterations=[0], limits=None, capacity=None),
-    "config4": dict(name="config4_1M_spheres_3840x2160_glFull_3_bounces_accumulated_samples_iterations_10_to_13",
-                    size=(3840, 2160), nit=3, scene="config4", iterations=[10, 11, 12, 13], limits=(3840, 2160),
-                    capacity=(16_000_000, 4_000_000)),
-}
-SELECTED = WORKLOADS["config2"]
-
-
-def scene_and_info(width, height):
-    from solr_b200 import scenes, wire
-    sc = getattr(scenes, SELECTED["scene"])()
-    si = wire.default_scene_info(width, height, graphics_level=wire.GL_FULL, nb_ray_iterations=NB_RAY_ITERATIONS)
-    return sc, si
-
-
-def cpu_reference_run(steps, warmup, want_counts=True):
-    """The reference arm / cpu_baseline: the path on host cores at SAMPLE_W x SAMPLE_H."""
-    return _cpu_reference_run(steps, warmup)
-
-
-def _cpu_reference_run(steps, warmup):
+# ------------------------------------------------------------------------------------------------------------------
+# CPU legs: the reference's own code (or the oracle port) on the host cores.  No native library of the product is loaded here when
+# the reference library travelled: the reference's own container builds the scene.  Without it the product's host container
+# builds the same arrays for the port, and the record says so.
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(key, steps, warmup):
     import oracle
     import refh
-    from solr_b200 import host, wire
-    sc, si = scene_and_info(SAMPLE_W, SAMPLE_H)
-    h = host.SceneHost(si)
-    sc.replay(h)
-    a = h.arrays()
-    h.close()
+    from solr_b200 import wire, workloads   # pure-Python struct mirrors and scene recipes: no native library of the product
+    wl = workloads.WORKLOADS[key]
+    W, H = wl["size"]
+    if (W, H) != (1920, 1080):
+        raise SystemExit("bench.py: the CPU legs exist for the 1920x1080 workloads (the reference's frame limit)")
+    si = workloads.scene_info(key)
+    sc = wl["scene"]()
     rnd = np.zeros(wire.REF_MAX_BITMAP_SIZE, np.float32)
     cores = host_cores()
-    o = oracle.Oracle(a, SAMPLE_W, SAMPLE_H, randoms=rnd)
+    builder = "reference container (libsolr_ref_cpu.so)"
+    r = None
+    if refh.available("cpu"):
+        r = refh.RefScene(si, "cpu")
+        sc.replay(r)
+        a = r.arrays()
+    else:
+        from solr_b200 import host   # the reference library did not travel: the product's container builds the same arrays
+        builder = "product host container (reference library absent)"
+        h = host.SceneHost(si)
+        sc.replay(h)
+        a = h.arrays()
+        h.close()
+    o = oracle.Oracle(a, W, H, randoms=rnd)
     t0 = time.perf_counter()
     o.render(si, sc.eye, sc.target, sc.angles, threads=cores)
     t_port = time.perf_counter() - t0
     counters = o.counters.as_dict()
     rays = counters["rays"]
     kind, times = "port", []
-    if refh.available("cpu"):
+    if r is not None:
         kind = "reference"
-        r = refh.RefScene(si, "cpu")
-        sc.replay(r)
         for k in range(warmup + steps):
             t0 = time.perf_counter()
             r.render(si, sc.eye, sc.target, sc.angles, randoms=rnd, block=(16, 8), want_post=False)
             if k >= warmup:
                 times.append(time.perf_counter() - t0)
+        r.close()
     else:
         for k in range(warmup + steps):
-            o2 = oracle.Oracle(a, SAMPLE_W, SAMPLE_H, randoms=rnd)
+            o2 = oracle.Oracle(a, W, H, randoms=rnd)
             t0 = time.perf_counter()
             o2.render(si, sc.eye, sc.target, sc.angles, threads=cores)
             if k >= warmup:
                 times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     return {"kind": kind, "cores": cores, "rays_per_frame": rays, "sec_per_frame": sec, "mrays_s": rays / sec / 1e6,
-            "port_sec_per_frame": t_port, "flops_per_frame": o.flops(), "counters": counters,
-            "sample": "%dx%d frame of the same scene and camera (%s of the pixels), %d timed frames" % (
-                SAMPLE_W, SAMPLE_H, "all" if SAMPLE_W * SAMPLE_H == W * H else "1/%d" % round(W * H / (SAMPLE_W * SAMPLE_H)), len(times))}
+            "port_sec_per_frame": t_port, "flops_per_frame": o.flops(), "counters": counters, "scene_built_by": builder,
+            "sample": "whole %dx%d frame of the same scene and camera per step, %d timed frames; %s" % (
+                W, H, len(times), "the reference's CUDA source compiled for the host (OpenMP), not its OpenCL engine" if kind == "reference"
+                else "oracle port")}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup)
+    from solr_b200 import workloads
+    r = cpu_reference_run(args.workload, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "Mrays/s", "value": r["mrays_s"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["sec_per_frame"] * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bench_sample": r["sample"]},
+            "config": {"workload": workloads.WORKLOADS[args.workload]["name"], "bench_sample": r["sample"], "scene_built_by": r["scene_built_by"]},
             "cpu_baseline": {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
-    args = ap.parse_args()
-    global W, H, NB_RAY_ITERATIONS, WORKLOAD, SELECTED
-    SELECTED = WORKLOADS[args.workload]
-    (W, H), NB_RAY_ITERATIONS, WORKLOAD = SELECTED["size"], SELECTED["nit"], SELECTED["name"]
-    if args.workload != "config2":
-        args.no_cpu_baseline = True
-    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
-    claim_stdout()
+# ------------------------------------------------------------------------------------------------------------------
+# engine arm
+# ------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
 
-    from _solr_b200_import import solr_b200  # noqa: F401
-    import __graft_entry__ as graft
-    graft.build(quiet=True)
 
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
-
+def measure_workload(key, steps, warmup, ctx, sample_clocks=False, want_e2e=True):
+    """One workload through the drop-in host path and the C ABI on this process's GPU: device-resident timing, end-to-end timing,
+    and (N > 1) the merged-frame check.  Returns a dict (complete on rank 0)."""
     import torch
     import torch.distributed as dist
-    from solr_b200 import engine, host, partition, wire
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — this engine has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
-
-    pk = peaks()
-    sc, si = scene_and_info(W, H)
-    rnd = np.zeros(max(wire.REF_MAX_BITMAP_SIZE, W * H), np.float32)
-    iterations = SELECTED["iterations"]
-    frame_no = [0]
+    from solr_b200 import engine, host, partition, wire, workloads
+    wl = workloads.WORKLOADS[key]
+    W, H = wl["size"]
+    world, rank, local_rank, stream, lib = ctx.world, ctx.rank, ctx.local_rank, ctx.stream, ctx.lib
+    sc = wl["scene"]()
+    si = workloads.scene_info(key)
+    limits = wl["limits"]
+    table = max(wire.REF_MAX_BITMAP_SIZE, W * H)
+    rnd = np.zeros(table, np.float32)
+    iterations = wl["iterations"]
+    frame_no = [-1]
 
     def next_iteration():
         frame_no[0] += 1
         return iterations[frame_no[0] % len(iterations)]
 
     # ---- the drop-in host path (SceneHost -> C ABI) owns the engine in this process --------------------
-    h = host.SceneHost(si, limits=SELECTED["limits"], rank=rank, world=world, device=local_rank, capacity=SELECTED["capacity"])
+    t0 = time.perf_counter()
+    h = host.SceneHost(si, limits=limits, rank=rank, world=world, device=local_rank, capacity=wl["capacity"])
     sc.replay(h)
+    host_build_s = time.perf_counter() - t0
     h.set_randoms(rnd, 0)
     h.set_camera(sc.eye, sc.target, sc.angles)
-    stream = torch.cuda.Stream()
-    lib = engine.load()
     h.init_buffers()
     lib.b200_set_stream(stream.cuda_stream)
     si_live = h.scene_info
     si_live.maxPathTracingIterations = 1 << 30   # keep m_refresh true: every render_begin renders a frame
 
-    def frame_e2e():
-        si_live.pathTracingIteration = 0
+    def frame_e2e_once(iteration=0):
+        si_live.pathTracingIteration = iteration
         h.set_scene_info(si_live)
         h.render_begin(0.0)
         h.render_end()
 
-    frame_e2e()   # uploads the scene (dirty flags), first frame
+    t0 = time.perf_counter()
+    frame_e2e_once()   # uploads the scene (dirty flags), first frame
     torch.cuda.synchronize()
+    first_frame_s = time.perf_counter() - t0
     eng = engine.Engine.__new__(engine.Engine)   # thin view on the already-initialised library for counters etc.
     eng.lib = lib
     eng.counters(reset=True)
@@ -287,24 +275,23 @@ def main():
     occ = wire.Int2(1, 1)
     eye, target, angles = wire.Float3(*sc.eye), wire.Float3(*sc.target), wire.Float4(*sc.angles)
     pp = wire.PostProcessingInfo()
-    si0 = wire.default_scene_info(W, H, graphics_level=wire.GL_FULL, nb_ray_iterations=NB_RAY_ITERATIONS)
-    bitmap_t, ids_t = partition.device_tensors(eng, W, H)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
+    si0 = workloads.scene_info(key)
+    si0.maxPathTracingIterations = 1 << 30
     peer = partition.PeerFrame(lib, rank, world) if world > 1 else None   # ranks > 0 now write into rank 0's frame
 
     def frame_device():
-        si0.pathTracingIteration = next_iteration()
+        it = next_iteration()
+        si0.pathTracingIteration = it
         lib.b200_render(occ, wire.Int4(8, 4, 1, 0), si0, objects, pp, eye, target, angles)
         if world > 1:
             peer.fence()   # every rank's kernels, and with them their stores into rank 0's frame, are done
+        return it
 
     # ---- device-resident timing --------------------------------------------------------------------------
-    launches0 = eng.kernel_launches()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if sample_clocks else None
     with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            flush.zero_()
+        for _ in range(warmup):
+            ctx.flush.zero_()
             frame_device()
         stream.synchronize()
         if world > 1:
@@ -312,38 +299,45 @@ def main():
         torch.cuda.synchronize()
         eng.counters(reset=True)
         launches0 = eng.kernel_launches()
-        sampler.start()
+        if sampler:
+            sampler.start()
         evs = []
-        for _ in range(args.steps):
-            flush.zero_()                                  # L2 flush, outside the timed region
+        for _ in range(steps):
+            ctx.flush.zero_()                                  # L2 flush, outside the timed region
             if world > 1:
                 dist.barrier()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(stream)
-            frame_device()
+            it = frame_device()
             e.record(stream)
-            evs.append((s, e))
+            evs.append((s, e, it))
         stream.synchronize()
         torch.cuda.synchronize()
-    clocks = sampler.summary()
-    ms = [s.elapsed_time(e) for s, e in evs]
+    clocks = sampler.summary() if sampler else None
+    ms = [s.elapsed_time(e) for s, e, _ in evs]
+    per_it = {}
+    for (s, e, it), m in zip(evs, ms):
+        per_it.setdefault(it, []).append(m)
     launches = eng.kernel_launches() - launches0
     rays_local, px_local = eng.counters(reset=True)
-    t = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([sum(ms)] + [sum(per_it[i]) / len(per_it[i]) for i in sorted(per_it)], dtype=torch.float64, device="cuda")
     r = torch.tensor([float(rays_local), float(px_local)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
-    total_ms = float(t.item())
+    total_ms = float(t[0].item())
     rays_total, px_total = float(r[0].item()), float(r[1].item())
-    ms_per_step = total_ms / args.steps
-    value = rays_total / (total_ms * 1e-3) / 1e6
-    kernel_ms = float(lib.b200_last_render_ms())
+    rec = {"workload": wl["name"], "ms_per_step": total_ms / steps, "value": rays_total / (total_ms * 1e-3) / 1e6, "steps": steps, "warmup": warmup,
+           "rays_per_frame": rays_total / steps, "mpixels_per_s": px_total / (total_ms * 1e-3) / 1e6,
+           "ms_per_iteration": {str(i): round(float(v), 4) for i, v in zip(sorted(per_it), t[1:].tolist())},
+           "gpu_launches": int(launches), "kernel_ms_last_frame": float(lib.b200_last_render_ms()), "clocks": clocks,
+           "primitives": int(a["nbPrimitives"]), "boxes": int(a["nbBoxes"]), "host_scene_build_s": round(host_build_s, 2),
+           "first_frame_with_scene_upload_s": round(first_frame_s, 2), "size": [W, H]}
 
     # ---- end to end through the host drop-in -------------------------------------------------------------
-    # Every rank runs the host drop-in for its tiles (render_begin: per-frame parameter upload + launch); the partial RGB8
-    # frames are summed onto rank 0 over NVLink (the path's one exchange step) and rank 0 reads the merged frame and its
-    # ids back to host memory (render_end = d2h_bitmap).  Wall clock around K frames, max over ranks.
+    # Every rank runs the host drop-in for its tiles (render_begin: per-frame parameter upload + launch); finished pixels land in
+    # rank 0's frame over NVLink (the path's one exchange step) and rank 0 reads the merged frame back to host memory
+    # (render_end = d2h_bitmap).  Wall clock around K frames, max over ranks.
     def frame_e2e_all(iteration=None):
         si_live.pathTracingIteration = next_iteration() if iteration is None else iteration
         h.set_scene_info(si_live)
@@ -360,14 +354,15 @@ def main():
             stream.synchronize()
 
     def measure_e2e():
-        for _ in range(3):
+        frame_no[0] = -1
+        for _ in range(max(3, len(iterations))):
             frame_e2e_all()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         eng.counters(reset=True)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             frame_e2e_all()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -377,22 +372,23 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
             dist.all_reduce(re_, op=dist.ReduceOp.SUM)
-        return float(re_.item()) / float(te.item()) / 1e6, float(te.item()) / args.steps * 1e3
+        return float(re_.item()) / float(te.item()) / 1e6, float(te.item()) / steps * 1e3
 
-    # the drop-in's default: render_end reads the pixels back, the id buffer stays on the device until getPrimitiveAt asks (its only
-    # host-side reader, GPUKernel.cpp:729-739); then the reference's own protocol — pixels and 16 bytes of ids per pixel, every frame
-    e2e_value, e2e_ms = measure_e2e()
-    h.set_lazy_ids(False)
-    eager_value, eager_ms = measure_e2e()
-    h.set_lazy_ids(True)
+    if want_e2e:
+        # the reference's own protocol first — pixels and 16 bytes of ids per pixel, every frame (CudaKernel.cpp:304-313) —, then the
+        # drop-in's option: the id buffer stays on the device until getPrimitiveAt asks (its only host-side reader, GPUKernel.cpp:729-739)
+        h.set_lazy_ids(False)
+        eager_value, eager_ms = measure_e2e()
+        h.set_lazy_ids(True)
+        lazy_value, lazy_ms = measure_e2e()
+        rec["e2e"] = {"value": eager_value, "unit": "Mrays/s", "ms_per_frame": eager_ms,
+                      "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()) * world,   # scene-info + camera + pointers block, per frame and rank
+                      "d2h_bytes_per_step": W * H * 3 + W * H * 16,   # RGB8 + PrimitiveXYIdBuffer into caller-owned memory (rank 0)
+                      "protocol": "the reference's render_end: bitmap and id buffer read back every frame (CudaKernel.cpp:304-313)",
+                      "lazy_ids": {"value": lazy_value, "ms_per_frame": lazy_ms, "d2h_bytes_per_step": W * H * 3,
+                                   "note": "id buffer fetched on demand (getPrimitiveAt is its only host-side reader)"}}
     frame_e2e_all(0)   # a single-sample frame on every rank: what frame_check compares
-    e2e = {"value": e2e_value, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
-           "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()) * world,   # scene-info + camera + pointers block, per frame and rank
-           "d2h_bytes_per_step": W * H * 3,   # RGB8 into caller-owned memory (rank 0)
-           "with_id_buffer_every_frame": {"value": eager_value, "ms_per_frame": eager_ms, "d2h_bytes_per_step": W * H * 3 + W * H * 16,
-                                          "note": "the reference's render_end protocol (CudaKernel.cpp:304-313)"}}
 
-    frame_check = None
     if world > 1:
         # the merged frame rank 0 just read back against the whole frame rendered by rank 0 alone
         dist.barrier()
@@ -400,52 +396,192 @@ def main():
         if rank == 0:
             merged = np.array(h.bitmap(), copy=True)
             lib.b200_set_partition(0, 1)
-            frame_e2e()
+            frame_e2e_once(0)
             whole = np.array(h.bitmap(), copy=True)
             differing = int(np.count_nonzero(merged != whole))
-            frame_check = {"bytes_differing_from_the_one_gpu_frame": differing, "bytes": int(whole.size)}
+            rec["frame_check"] = {"bytes_differing_from_the_one_gpu_frame": differing, "bytes": int(whole.size)}
             if differing:
-                raise SystemExit("bench.py: the frame merged over %d GPUs differs from the one-GPU frame in %d bytes" % (world, differing))
+                raise SystemExit("bench.py: %s: the frame merged over %d GPUs differs from the one-GPU frame in %d bytes" % (key, world, differing))
         dist.barrier()
+    rec["_frame"] = (np.array(h.bitmap(), copy=True), np.array(h.primitive_ids(), copy=True)) if (rank == 0 and world == 1) else None
+    h.close()
+    return rec
+
+
+def parity_against_reference_cuda(key, frame):
+    """The engine's frame (iteration 0) against the reference's own CUDA engine on the same GPU.  Checker only: runs after every
+    timed region and in a child process — the reference's finalize_scene resets the device (CudaRayTracer.cu:1530), which would
+    take this process's CUDA context with it."""
+    import tempfile
+    import refh
+    from solr_b200 import workloads
+    if frame is None or not refh.available("cuda"):
+        return {"checked": False, "why": "reference CUDA build (oracle/_ref/libsolr_ref_cuda.so) not present"}
+    wl = workloads.WORKLOADS[key]
+    if wl["size"] != (1920, 1080) or wl["capacity"] is not None:
+        return {"checked": False, "why": "beyond the reference's frame / box limits: tests/test_gpu_parity_at_size.py compares this size with the oracle"}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "frame.npz")
+        np.savez(path, bm=frame[0], ids=frame[1])
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", key, "--parity-child", path],
+                                 capture_output=True, text=True, timeout=600)
+            return json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as ex:   # the checker failing must not lose the measurement
+            return {"checked": False, "why": "parity child failed: %r" % (ex,)}
+
+
+def parity_child(key, path):
+    import refh
+    from solr_b200 import wire, workloads
+    wl = workloads.WORKLOADS[key]
+    z = np.load(path)
+    bm, ids = z["bm"], z["ids"]
+    si = workloads.scene_info(key)
+    sc = wl["scene"]()
+    rg = refh.RefScene(si, "cuda")
+    sc.replay(rg)
+    si.pathTracingIteration = 0
+    gbm, gids, _ = rg.render(si, sc.eye, sc.target, sc.angles, randoms=np.zeros(wire.REF_MAX_BITMAP_SIZE, np.float32), block=(16, 8), want_post=False)
+    rg.close()
+    n = ids.shape[0] * ids.shape[1]
+    return {"checked": True, "against": "reference CUDA engine (sm_100 build), same GPU, same scene and camera", "pixels": n,
+            "ids_diff": int((ids[..., 0] != gids[..., 0]).sum()),
+            "rgb_bad": int((np.abs(bm.astype(int) - gbm.astype(int)).max(-1) > 2).sum()), "rgb_bar": "2/255 per channel"}
+
+
+def traffic_record():
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary_latest.json")) as f:
+            j = json.load(f)
+        return j.get("dram_bytes_per_frame", j.get("dram_bytes_per_launch")), {
+            "file": "profiles/ncu_summary_latest.json", "captured_at_commit": j.get("git_head"), "captured": j.get("captured"),
+            "note": "ncu --set full of one frame's ray kernels, dram__bytes_read.sum + dram__bytes_write.sum summed over the launches; "
+                    "a recorded capture, not taken in this run"}
+    except Exception:
+        return None, None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
+    ap.add_argument("--no-sub", action="store_true", help="headline workload only")
+    ap.add_argument("--parity-child", default=None, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    claim_stdout()
+
+    from _solr_b200_import import solr_b200  # noqa: F401
+    if args.parity_child:
+        emit(parity_child(args.workload, args.parity_child))
+        return
+    if args.impl == "reference":
+        import oracle
+        oracle.load()   # builds oracle/libsolr_oracle.so if it is missing; nothing of the product is built or loaded
+        run_reference_arm(args)
+        return
+
+    import __graft_entry__ as graft
+    graft.build(quiet=True)
+    import torch
+    import torch.distributed as dist
+    from solr_b200 import engine, workloads
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this engine has no CPU fallback")
+    ctx = Ctx()
+    ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    ctx.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(ctx.local_rank)
+    if ctx.world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local_rank))
+    assert ctx.world == args.gpus or ctx.world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    world, rank = ctx.world, ctx.rank
+    ctx.stream = torch.cuda.Stream()
+    ctx.lib = engine.load()
+    ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    pk = peaks()
+    flops_table = recorded_flops()
+
+    key = args.workload
+    head = measure_workload(key, args.steps, args.warmup, ctx, sample_clocks=True)
+    frame = head.pop("_frame")
+
+    subs = {}
+    if not args.no_sub:
+        sub_keys = [k for k in (["config4"] if world > 1 else ["config4", "config3", "config5"]) if k != key]
+        for k in sub_keys:
+            w, s = SUB_FRAMES[k]
+            rec = measure_workload(k, s, w, ctx, sample_clocks=False)
+            rec.pop("_frame")
+            subs[k] = rec
+
+    # FP32 FMA microbenchmark on this GPU (dependent FFMA chains on every resident lane) and the clock it sustains
+    fp32 = None
     if rank == 0:
-        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        import ctypes as C
+        tf, mhz = C.c_float(), C.c_float()
+        if ctx.lib.b200_measure_fp32_peak(C.byref(tf), C.byref(mhz)) == 0:
+            fp32 = {"ffma_tflops": round(tf.value, 2), "sm_mhz_under_that_load": round(mhz.value, 0)}
+
+    if rank == 0:
+        W, H = workloads.WORKLOADS[key]["size"]
+        line = {"metric": "Mrays/s", "value": head["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "rays_per_frame": rays_total / args.steps, "mpixels_per_s": px_total / (total_ms * 1e-3) / 1e6,
+                "config": {"workload": head["workload"], "rays_per_frame": head["rays_per_frame"], "mpixels_per_s": head["mpixels_per_s"],
+                           "primitives": head["primitives"], "boxes": head["boxes"],
                            "l2": "flushed between timed frames (256 MiB memset outside the timed region)",
                            "parallelism": "one frame, interleaved 8x4 tiles over %d GPU(s)%s" % (
                                world, ", finished pixels stored into rank 0's frame over NVLink peer memory by the ray kernels, "
                                "one-element NCCL all-reduce as frame fence" if world > 1 else "")},
-                "clocks": clocks, "gpu_launches": int(launches), "kernel_ms_last_frame": kernel_ms}
-        line["e2e"] = e2e
-        if frame_check is not None:
-            line["frame_check"] = frame_check
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_summary_latest.json")) as f:
-                j = json.load(f)
-                traffic = j.get("dram_bytes_per_frame", j.get("dram_bytes_per_launch"))   # summed over the frame's launches
-        except Exception:
-            pass
-        flops_frame = ALGORITHMIC_GFLOP_PER_FRAME * 1e9
-        flops_source = "oracle count in reference traversal order, full frame (recorded)" if args.workload == "config2" else "not counted for this workload"
-        if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference_run(1, 0)
-            flops_frame = cb["flops_per_frame"] * (W * H) / float(SAMPLE_W * SAMPLE_H)
-            flops_source = "oracle count in reference traversal order, live on the %dx%d CPU frame" % (SAMPLE_W, SAMPLE_H)
+                "clocks": head["clocks"], "gpu_launches": head["gpu_launches"], "kernel_ms_last_frame": head["kernel_ms_last_frame"],
+                "ms_per_iteration": head["ms_per_iteration"], "e2e": head["e2e"]}
+        if "frame_check" in head:
+            line["frame_check"] = head["frame_check"]
+
+        def roofline(k, rec, flops_frame, source):
+            achieved = flops_frame / (rec["ms_per_step"] * 1e-3) / 1e12 / world
+            w_, h_ = rec["size"]
+            return {"bound": "fp32", "achieved": achieved, "peak": pk["fp32_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["fp32_tflops"],
+                    "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json), per GPU" % pk["source"],
+                    "algorithmic_gflop_per_frame": flops_frame / 1e9, "algorithmic_flops_source": source,
+                    "hbm": {"peak_gbs": pk["hbm_gbs"], "mandatory_bytes_per_frame": w_ * h_ * (32 + 16 + 3) * 2}}
+
+        rec_flops = flops_table.get(key, {}).get("gflop_per_frame_mean_over_bench_iterations")
+        flops_frame = rec_flops * 1e9 if rec_flops else None
+        source = "oracle count in reference traversal order on sampled rows, recorded (profiles/algorithmic_flops.json)"
+        if world == 1 and not args.no_cpu_baseline and (W, H) == (1920, 1080):
+            cb = cpu_reference_run(key, 1, 0)
+            flops_frame = cb["flops_per_frame"]
+            source = "oracle count in reference traversal order, live on the whole %dx%d frame" % (W, H)
             line["cpu_baseline"] = {"value": cb["mrays_s"], "unit": "Mrays/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
-        # the frame is a handful of kernels of one code base (k_stage_primary, k_stage_pass per bounce, ...): the roofline is
-        # taken over the timed region they fill, per GPU
-        achieved = flops_frame / (ms_per_step * 1e-3) / 1e12 / world
-        line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
-                            "frac": achieved / pk["fp32_tflops"], "traffic": traffic,
-                            "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json), per GPU" % pk["source"],
-                            "algorithmic_gflop_per_frame": flops_frame / 1e9, "algorithmic_flops_source": flops_source,
-                            "hbm": {"peak_gbs": pk["hbm_gbs"], "mandatory_bytes_per_frame": W * H * (32 + 16 + 3) * 2}}
-        if args.workload != "config2":
-            line["roofline"].update(achieved=None, frac=None, traffic=None, algorithmic_gflop_per_frame=None)
+        if flops_frame:
+            # the frame is a handful of kernels of one code base (k_stage_primary, k_stage_pass per bounce, ...): the roofline is taken
+            # over the timed region they fill, per GPU
+            line["roofline"] = roofline(key, head, flops_frame, source)
+            traffic, stamp = traffic_record()
+            line["roofline"]["traffic"] = traffic if key == "config2" else None
+            line["roofline"]["traffic_source"] = stamp if key == "config2" else None
+            if fp32:
+                line["roofline"]["measured_fp32"] = fp32
+                line["roofline"]["frac_of_measured_ffma_rate"] = line["roofline"]["achieved"] / fp32["ffma_tflops"]
+        if world == 1:
+            line["parity"] = parity_against_reference_cuda(key, frame)
+        for k, rec in subs.items():
+            f = flops_table.get(k, {}).get("gflop_per_frame_mean_over_bench_iterations")
+            rec["unit"] = "Mrays/s"
+            if f:
+                rec["roofline"] = roofline(k, rec, f * 1e9, "oracle count in reference traversal order on sampled rows, recorded (profiles/algorithmic_flops.json)")
+        if subs:
+            line["workloads"] = subs
         emit(line)
-    h.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -247,9 +247,24 @@ SB_DEV void renderPixel(const Rotation& rot, const bool inFrame, const int xIn, 
 
 // Persistent CTAs: every warp pulls 8x4-pixel tiles from one atomic queue until the frame is drained, so
 // a warp stuck on deep bounce chains does not hold back the rest of its CTA or its SM.
+// What a ray kernel does before its first walk: the frame's first kernel asks the L2 for the scene arrays the walks read (a slice per
+// CTA), and every CTA stages the top of the tree in shared memory (trace.cuh "Bulk copies").
+SB_DEV void framePrologue(const bool firstKernelOfFrame)
+{
+#ifdef SCENE_L2_PREFETCH
+    if (firstKernelOfFrame && threadIdx.x == 0 && cS.nbUWide > 0)
+    {
+        scenePrefetchSlice(cS.uwnodes, (size_t)(cS.nbUWide + cS.nbUX) * 128);
+        scenePrefetchSlice(cS.primRecs, (size_t)cS.nbPrimitives * 96);
+    }
+#endif
+    topStage();
+}
+
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_render()
 {
     const int lane = threadIdx.x & 31;
+    framePrologue(true);
     Counters cnt;
     cnt.rays = 0;
     unsigned int pixelsTraced = 0;
@@ -404,6 +419,7 @@ SB_DEV void flushCounters(const unsigned int raysIn, const unsigned int pxIn)
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PRIMARY) k_stage_primary()
 {
     const int lane = threadIdx.x & 31;
+    framePrologue(true);
     Counters cnt;
     cnt.rays = 0;
     unsigned int pixelsTraced = 0;
@@ -445,6 +461,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PRIMARY) k_stage_primary
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const int pass)
 {
     const int lane = threadIdx.x & 31;
+    framePrologue(false);
     Counters cnt;
     cnt.rays = 0;
     const int q = passQueue(pass);
@@ -519,6 +536,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflected()
 {
     const int lane = threadIdx.x & 31;
+    framePrologue(false);
     Counters cnt;
     cnt.rays = 0;
     const int q = reflectedQueue();

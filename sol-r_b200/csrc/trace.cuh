@@ -1665,6 +1665,56 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
 // Same candidates, same acceptance rules, same results as the round-1 walk (tests/test_gpu_parity.py compares it with the
 // ordered walks and with the reference CUDA engine).
 // ---------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------
+// Bulk copies (TMA, cp.async.bulk) for the scene arrays the walks read.
+//   * SCENE_L2_PREFETCH: the first kernel of a frame asks the L2 for the node records and the primitive records, a slice per
+//     CTA (cp.async.bulk.prefetch.L2): the walks' first touches then meet L2 instead of DRAM latency.
+//   * TOP_SMEM = K: every persistent CTA copies the first K node records — the tree is numbered breadth-first, so these are
+//     its top levels, which every ray walks — into shared memory once (cp.async.bulk.shared::cluster.global with an mbarrier
+//     for completion) and the walk reads nodes < K from there.
+// ---------------------------------------------------------------------------------------------------
+SB_DEV void bulkPrefetchL2(const void* p, const unsigned int bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// one slice of [base, base + bytes) per CTA, in pieces of at most 64 KiB, multiples of 16 bytes; thread 0 of the CTA issues them
+SB_DEV void scenePrefetchSlice(const void* base, const size_t bytes)
+{
+    if (base == nullptr || bytes == 0) return;
+    const size_t per = (((bytes + gridDim.x - 1) / gridDim.x) + 127) & ~(size_t)127;
+    size_t at = (size_t)blockIdx.x * per;
+    const size_t end = (at + per < bytes) ? at + per : (bytes & ~(size_t)15);
+    for (; at < end; at += 65536)
+        bulkPrefetchL2(reinterpret_cast<const char*>(base) + at, (unsigned int)((end - at < 65536) ? end - at : 65536));
+}
+#ifdef TOP_SMEM
+__shared__ __align__(128) float4 s_topNodes[TOP_SMEM * 8];
+__shared__ __align__(8) unsigned long long s_topBar;
+// every thread of the CTA calls, once, before its first walk
+SB_DEV void topStage()
+{
+    const int n = cS.nbUWide < TOP_SMEM ? cS.nbUWide : TOP_SMEM;
+    if (n <= 0) return;
+    const unsigned int bar = (unsigned int)__cvta_generic_to_shared(&s_topBar);
+    if (threadIdx.x == 0)
+    {
+        const unsigned int dst = (unsigned int)__cvta_generic_to_shared(s_topNodes);
+        const unsigned int bytes = (unsigned int)n * 128u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the barrier's initialisation, seen by the copy engine
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(cS.uwnodes), "r"(bytes), "r"(bar) : "memory");
+    }
+    __syncthreads();
+    unsigned int done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+}
+#else
+SB_DEV void topStage() {}
+#endif
+
 SB_DEV void nodeKeysRegs(const float4 lx, const float4 ly, const float4 lz, const float4 hx, const float4 hy, const float4 hz, const float4 rf,
                          const NodeRay& q, const float tLimit, NodeKeys& o)
 {
@@ -1763,8 +1813,19 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
         const int idx = (~cur) & 0x3FFFFFFF;
         const float4* item = isNode ? nodes + (size_t)8 * cur : recs + (size_t)PRIM_REC_F4 * idx;
         float4 a0, a1, a2, a3, a4, a5, a6 = f4(0.f, 0.f, 0.f, 0.f), a7;
-        ldNode256(item, a0, a1); ldNode256(item + 2, a2, a3); ldNode256(item + 4, a4, a5);
-        if (isNode) ldNode256(item + 6, a6, a7);
+#ifdef TOP_SMEM
+        if (isNode && cur < TOP_SMEM && cur < nbMain)
+        {
+            // the top of the tree, staged in shared memory by topStage()
+            const float4* t = s_topNodes + 8 * cur;
+            a0 = t[0]; a1 = t[1]; a2 = t[2]; a3 = t[3]; a4 = t[4]; a5 = t[5]; a6 = t[6];
+        }
+        else
+#endif
+        {
+            ldNode256(item, a0, a1); ldNode256(item + 2, a2, a3); ldNode256(item + 4, a4, a5);
+            if (isNode) ldNode256(item + 6, a6, a7);
+        }
         if (isNode)
         {
             DBG_ADD(5, 1); DBG_DECL(++dbgVisits;)

@@ -65,7 +65,19 @@ for rep in reps:
             k = summarise(rows[0], rows[1], vals)
             k["report"] = os.path.basename(rep)
             kernels.append(k)
-summary = {"kernels": kernels,
+def _git_head():
+    try:
+        head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+        dirty = subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "--", "sol-r_b200/csrc"], capture_output=True, text=True).stdout.strip()
+        return head + (" + uncommitted changes under sol-r_b200/csrc" if dirty else "")
+    except Exception:
+        return None
+
+
+import datetime
+summary = {"git_head": os.environ.get("SOLR_CAPTURE_HEAD") or _git_head(),
+           "captured": datetime.datetime.utcfromtimestamp(os.path.getmtime(reps[0])).strftime("%Y-%m-%dT%H:%MZ") if reps else None,
+           "kernels": kernels,
            "duration_ms_sum": sum(k["duration_ms"] or 0 for k in kernels),
            "dram_bytes_per_frame": sum(k.get("dram_bytes_per_launch") or 0 for k in kernels)}
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
