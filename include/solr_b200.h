@@ -17,6 +17,7 @@
 
 #include "solr_b200_types.h"
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -134,6 +135,24 @@ void b200_synchronize(void);
  * every resident lane, and the SM clock sustained under that load (MHz): the measured roofline denominator BASELINE.md 2 asks
  * for beside the nominal 148 SM x 128 lanes x 2 x f.  Returns 0 or the latched error code. */
 int b200_measure_fp32_peak(float* tflops, float* smMhz);
+
+/* Pins a host buffer of the caller in place (cudaHostRegister) so that b200_d2h_bitmap into it is a direct DMA; the caller
+ * unregisters it before freeing it.  The engine never pins memory it does not own on its own initiative.  A host class registers
+ * the frame and id buffers it allocates once (GPUKernel.cpp:344-360).  0, or a negative code (-12: could not pin; copies into the
+ * buffer still work, staged). */
+int b200_register_host(void* buffer, size_t bytes);
+int b200_unregister_host(void* buffer);
+/* Sample-split accumulation over GPUs (the second split north_star names: "sample accumulation optionally split by GPU", frame
+ * "reduced with NCCL over NVLink").  Past NB_MAX_ITERATIONS the reference only adds a frame's sample to the accumulation buffer
+ * (CudaRayTracer.cu:550-562) and divides by the sample count when it packs (k_default, :1066-1070), so the samples of a
+ * progressive sequence can be rendered by different GPUs, each over the WHOLE frame (set_partition(0, 1) on every process), and
+ * summed: _clear zeroes the colour sums of this process (keeps depth and ids), _export writes them as one float4 per pixel to a
+ * device buffer of the caller (which the caller sum-reduces onto the root, sol-r_b200/partition.py SampleSplit), and
+ * _import_and_pack stores the reduced sums and packs the RGB8 frame as iteration `iteration` would (divide by
+ * iteration - NB_MAX_ITERATIONS + 1).  All three run on the render stream; each returns 0 or an error code. */
+int b200_accumulation_clear(void);
+int b200_accumulation_export(void* dstFloat4Device);
+int b200_accumulation_import_and_pack(const void* srcFloat4Device, int iteration);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,9 @@
 #include <Logging.h>
 #include <solr_b200.h>
 
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 namespace
 {
@@ -39,6 +41,7 @@ B200Kernel::B200Kernel()
     : GPUKernel(), m_deviceInitialized(false), m_fixedRandoms(false), m_fixedTimestamp(0), m_maxWidth(MAX_BITMAP_WIDTH),
       m_maxHeight(MAX_BITMAP_HEIGHT)
 {
+    m_pinned[0] = m_pinned[1] = nullptr;
     m_occupancyParameters.x = 1;
     m_occupancyParameters.y = 1;
     m_gpuDescription = "B200 engine (libsolr_b200)";
@@ -70,8 +73,28 @@ void B200Kernel::initBuffers()
 
 void B200Kernel::cleanup()
 {
+    unpin(); /* before GPUKernel frees the buffers */
     GPUKernel::cleanup();
     releaseDevice();
+}
+
+void B200Kernel::unpin()
+{
+    for (int i = 0; i < 2; ++i)
+        if (m_pinned[i])
+        {
+            b200_unregister_host(m_pinned[i]);
+            m_pinned[i] = nullptr;
+        }
+}
+
+unsigned int B200Kernel::getPrimitiveIdAt(int x, int y)
+{
+    if (m_bigIds.empty())
+        return getPrimitiveAt(x, y);
+    if (x < 0 || y < 0 || x >= m_sceneInfo.size.x || y >= m_sceneInfo.size.y)
+        return 0;
+    return m_bigIds[static_cast<size_t>(y) * m_sceneInfo.size.x + x].x;
 }
 
 void B200Kernel::initializeDevice()
@@ -79,16 +102,27 @@ void B200Kernel::initializeDevice()
     b200_set_limits(m_maxWidth, m_maxHeight);
     b200_initialize_scene(OCC, as<b200_SceneInfo>(m_sceneInfo), NB_MAX_PRIMITIVES, NB_MAX_LAMPS, NB_MAX_MATERIALS);
     b200_reshape_scene(OCC, as<b200_SceneInfo>(m_sceneInfo));
+    unpin();
     if (m_maxWidth * m_maxHeight > static_cast<int>(MAX_BITMAP_SIZE))
     {
         m_bigBitmap.assign(static_cast<size_t>(m_maxWidth) * m_maxHeight * gColorDepth, 0);
         m_bigIds.assign(static_cast<size_t>(m_maxWidth) * m_maxHeight, PrimitiveXYIdBuffer());
+        m_bigRandoms.assign(static_cast<size_t>(m_maxWidth) * m_maxHeight, 0.f);
     }
+    /* the frame and id buffers live as long as this object's buffers do: pinned in place for direct read-backs */
+    void *frame = m_bigBitmap.empty() ? static_cast<void *>(m_bitmap) : static_cast<void *>(m_bigBitmap.data());
+    void *ids = m_bigIds.empty() ? static_cast<void *>(m_hPrimitivesXYIds) : static_cast<void *>(m_bigIds.data());
+    const size_t px = static_cast<size_t>(m_maxWidth) * m_maxHeight;
+    if (frame && b200_register_host(frame, px * gColorDepth) == 0)
+        m_pinned[0] = frame;
+    if (ids && b200_register_host(ids, px * sizeof(PrimitiveXYIdBuffer)) == 0)
+        m_pinned[1] = ids;
     m_deviceInitialized = true;
 }
 
 void B200Kernel::releaseDevice()
 {
+    unpin();
     if (m_deviceInitialized)
         b200_finalize_scene(OCC);
     m_deviceInitialized = false;
@@ -98,8 +132,21 @@ void B200Kernel::render_begin(const float timer)
 {
     if (m_fixedRandoms)
         m_sceneInfo.timestamp = m_fixedTimestamp; /* skip GPUKernel::render_begin's rand()/time(0) draw */
-    else
+    else if (m_bigRandoms.empty())
         GPUKernel::render_begin(timer);
+    else
+    {
+        /* GPUKernel::render_begin (GPUKernel.cpp:2712-2727) fills size.x * size.y entries of a table that holds MAX_BITMAP_SIZE:
+         * beyond the reference's frame limit the same draw goes into the table of this class */
+        m_sceneInfo.timestamp = rand() % 10000;
+        if (!m_randomsTransfered || m_sceneInfo.pathTracingIteration % 50 == 1)
+        {
+            m_randomsTransfered = false;
+            srand(static_cast<int>(time(0)));
+            for (size_t i = 0; i < m_bigRandoms.size(); ++i)
+                m_bigRandoms[i] = 0.000005f * (rand() % 2000 - 1000);
+        }
+    }
     if (m_refresh)
     {
         const int nbBoxes = m_nbActiveBoxes[m_frame];
@@ -119,9 +166,9 @@ void B200Kernel::render_begin(const float timer)
             if (m_maxWidth * m_maxHeight > static_cast<int>(MAX_BITMAP_SIZE))
             {
                 /* the engine copies maxWidth*maxHeight floats; the reference's table only has 1920x1080 */
-                std::vector<float> table(static_cast<size_t>(m_maxWidth) * m_maxHeight, 0.f);
-                memcpy(table.data(), m_hRandoms, sizeof(float) * MAX_BITMAP_SIZE);
-                b200_h2d_randoms(OCC, table.data());
+                if (m_fixedRandoms)
+                    memcpy(m_bigRandoms.data(), m_hRandoms, sizeof(float) * MAX_BITMAP_SIZE);
+                b200_h2d_randoms(OCC, m_bigRandoms.data());
             }
             else
                 b200_h2d_randoms(OCC, m_hRandoms);

@@ -32,8 +32,14 @@ public:
     void render_end() override;
     std::string getGPUDescription() override { return m_gpuDescription; }
 
-    /* frame-size limits beyond the reference's 1920x1080 (Consts.h:39-41) and the multi-GPU frame split */
+    /* frame-size limits beyond the reference's 1920x1080 (Consts.h:39-41) and the multi-GPU frame split.  GPUKernel's own frame,
+     * id and random-number buffers are sized for MAX_BITMAP_SIZE and its getBitmap() / getPrimitiveAt() are not virtual, so a frame
+     * beyond that size lives in buffers of this class: read it with getFrame() / getPrimitiveIdAt(). */
     void setLimits(int maxWidth, int maxHeight);
+    /* the frame render_end read back, whatever its size: GPUKernel::getBitmap() within the reference's limit, else the large buffer */
+    BitmapBuffer *getFrame() { return m_bigBitmap.empty() ? m_bitmap : m_bigBitmap.data(); }
+    /* GPUKernel::getPrimitiveAt (GPUKernel.cpp:729-739) for any frame size */
+    unsigned int getPrimitiveIdAt(int x, int y);
     void setPartition(int rank, int worldSize);
     /* fixes what GPUKernel::render_begin draws from rand() (GPUKernel.cpp:2719-2727): deterministic frames */
     void setRandoms(const float *randoms, size_t count, int timestamp);
@@ -47,5 +53,8 @@ private:
     int m_maxWidth, m_maxHeight;
     std::vector<unsigned char> m_bigBitmap; /* used instead of m_bitmap when the limits exceed the reference's */
     std::vector<PrimitiveXYIdBuffer> m_bigIds;
+    std::vector<float> m_bigRandoms; /* the random table at the size of the limits */
+    void *m_pinned[2];               /* frame / id buffers registered with the engine, unregistered before they are freed */
+    void unpin();
 };
 }

@@ -89,6 +89,20 @@ void* refh_create(const SceneInfo* sceneInfo)
     return k;
 }
 
+#ifdef REFH_B200
+// the drop-in beyond the reference's frame limit: B200Kernel::setLimits before the buffers are made
+void* refh_create_limits(const SceneInfo* sceneInfo, int maxWidth, int maxHeight)
+{
+    void* mem = calloc(1, sizeof(HarnessKernel));
+    HarnessKernel* k = new (mem) HarnessKernel();
+    k->setLimits(maxWidth, maxHeight);
+    k->setSceneInfo(*sceneInfo);
+    k->initBuffers();
+    k->setFrame(0);
+    return k;
+}
+#endif
+
 void refh_destroy(void* h)
 {
     HarnessKernel* k = static_cast<HarnessKernel*>(h);
@@ -251,10 +265,11 @@ void refh_render(void* h, const SceneInfo* sceneInfo, const PostProcessingInfo* 
     k->render_begin(0.f);
     k->render_end();
     const size_t px = static_cast<size_t>(sceneInfo->size.x) * sceneInfo->size.y;
-    memcpy(bitmap, k->getBitmap(), px * gColorDepth);
+    // within the reference's frame limit these are GPUKernel::getBitmap() / getPrimitiveAt(); beyond it, B200Kernel's own buffers
+    memcpy(bitmap, k->getFrame(), px * gColorDepth);
     for (int y = 0; y < sceneInfo->size.y; ++y)
         for (int x = 0; x < sceneInfo->size.x; ++x)
-            ids[4 * (y * sceneInfo->size.x + x)] = static_cast<int>(k->getPrimitiveAt(x, y));
+            ids[4 * (y * sceneInfo->size.x + x)] = static_cast<int>(k->getPrimitiveIdAt(x, y));
     if (postBuffer) b200_d2h_post(*reinterpret_cast<const b200_SceneInfo*>(sceneInfo), reinterpret_cast<b200_PostProcessingBuffer*>(postBuffer));
 }
 #else

@@ -27,10 +27,10 @@
 #endif
 
 // GeometryShaders.cuh:132-165 (makeColor) fused with k_default's averaging (CudaRayTracer.cu:1068-1072)
-SB_DEV void packPixel(float4 color, unsigned char* bitmap, const int index)
+SB_DEV void packPixelAt(float4 color, unsigned char* bitmap, const int index, const int iteration)
 {
-    if (cSI.pathTracingIteration > B200_NB_MAX_ITERATIONS)
-        color /= (float)(cSI.pathTracingIteration - B200_NB_MAX_ITERATIONS + 1);
+    if (iteration > B200_NB_MAX_ITERATIONS)
+        color /= (float)(iteration - B200_NB_MAX_ITERATIONS + 1);
     color.x = (color.x > 1.f) ? 1.f : color.x; color.y = (color.y > 1.f) ? 1.f : color.y; color.z = (color.z > 1.f) ? 1.f : color.z;
     color.x = (color.x < 0.f) ? 0.f : color.x; color.y = (color.y < 0.f) ? 0.f : color.y; color.z = (color.z < 0.f) ? 0.f : color.z;
     if (cSI.frameBufferType == B200_FT_BGR)
@@ -49,6 +49,7 @@ SB_DEV void packPixel(float4 color, unsigned char* bitmap, const int index)
         bitmap[i + 2] = (unsigned char)(color.z * 255.f);
     }
 }
+SB_DEV void packPixel(const float4 color, unsigned char* bitmap, const int index) { packPixelAt(color, bitmap, index, cSI.pathTracingIteration); }
 
 // Primary ray of a pixel for the standard / orthographic / antialiased cameras (CudaRayTracer.cu:462-522): eye and look-at
 // target, the target shifted per pixel, both rotated; depth-of-field and rotated-grid jitter of the accumulation passes.
@@ -94,6 +95,25 @@ SB_DEV void primaryRay(const Rotation& rot, const int x, const int y, const int 
     }
 }
 
+// k_anaglyphRenderer's rays (CudaRayTracer.cu:866-901): eyes at origin.x -/+ eyeSeparation, both origin and target rotated
+SB_DEV void anaglyphRay(const Rotation& rot, const int x, const int y, const int eye, float3& o, float3& t)
+{
+    const int W = cSI.size.x, H = cSI.size.y;
+    const float ratio = (float)W / (float)H;
+    const float stepx = ratio * cP.angles.w / (float)W, stepy = cP.angles.w / (float)H;
+    const float3 rotationCenter = f3(0.f, 0.f, 0.f);
+    o = f3(eye == 0 ? cP.eye.x - cSI.eyeSeparation : cP.eye.x + cSI.eyeSeparation, cP.eye.y, cP.eye.z);
+    t.x = cP.target.x - stepx * (float)(x - (W / 2));
+    t.y = cP.target.y + stepy * (float)(y - (H / 2));
+    t.z = cP.target.z;
+    vectorRotation(o, rotationCenter, rot);
+    vectorRotation(t, rotationCenter, rot);
+}
+
+// left eye -> luma (CudaRayTracer.cu:905): x 0.299 + y 0.587 + z 0.114 with the contraction nvcc gives that expression (first product
+// fused into the sum, second rounded on its own, third fused), spelled out so that the two drivers that use it agree to the bit
+SB_DEV float anaglyphLuma(const float4 c) { return __fmaf_rn(c.z, 0.114f, __fmaf_rn(c.x, 0.299f, __fmul_rn(c.y, 0.587f))); }
+
 // What a pixel keeps of its ray tree(s) (:537-562, anaglyph :903-925), followed by k_default for that pixel.
 SB_DEV void resolvePixel(const int index, float4 color, const float4 left, const int4 id, const float dof, float4 stored)
 {
@@ -104,7 +124,7 @@ SB_DEV void resolvePixel(const int index, float4 color, const float4 left, const
     if (camera == B200_CT_ANAGLYPH)
     {
         // left eye -> luma in red, right eye -> green/blue (:903-925); sceneInfo is not written
-        const float r1 = left.x * 0.299f + left.y * 0.587f + left.z * 0.114f;
+        const float r1 = anaglyphLuma(left);
         const float g2 = color.y, b2 = color.z;
         if (iter <= B200_NB_MAX_ITERATIONS) { stored.x = r1 + 0.f; stored.y = 0.f + g2; stored.z = 0.f + b2; }
         else { stored.x += r1 + 0.f; stored.y += 0.f + g2; stored.z += 0.f + b2; }
@@ -146,6 +166,59 @@ SB_DEV void resolvePixel(const int index, float4 color, const float4 left, const
     *reinterpret_cast<float4*>(&cP.post[index].colorInfo) = stored;
     cP.ids[index] = id;
     packPixel(stored, cP.bitmap, index);
+}
+
+// One channel of packPixelAt (c = 0 red, 1 green, 2 blue): the three channels are divided, clamped and converted independently.
+SB_DEV void packChannel(float v, unsigned char* bitmap, const int index, const int c, const int iteration)
+{
+    if (iteration > B200_NB_MAX_ITERATIONS) v /= (float)(iteration - B200_NB_MAX_ITERATIONS + 1);
+    v = (v > 1.f) ? 1.f : v;
+    v = (v < 0.f) ? 0.f : v;
+    int i;
+    if (cSI.frameBufferType == B200_FT_BGR)
+    {
+        const int y = index / cSI.size.y, x = index % cSI.size.x;
+        i = ((y + 1) * cSI.size.y - x - 1) * B200_COLOR_DEPTH + (2 - c);
+    }
+    else
+        i = index * B200_COLOR_DEPTH + c;
+    bitmap[i] = (unsigned char)(v * 255.f);
+}
+
+// Staged anaglyph frames: the two eyes of a pixel are two paths that end in different stages, and what resolvePixel does with them
+// separates by component — the left eye's luma is the red channel, the right eye supplies green, blue, the first-hit depth and
+// the ids (it is traced second in k_anaglyphRenderer, CudaRayTracer.cu:866-925, so its values are the ones that stay) — so each
+// eye writes its own words of colorInfo and its own bytes of the frame.  Path tags carry the eye in bit 30 of the pixel index.
+#define PATH_EYE_BIT 30
+SB_DEV void resolveAnaglyphEye(const int index, const int eye, const float4 color, const int4 id, const float dof)
+{
+    const int iter = cSI.pathTracingIteration;
+    float* ci = &cP.post[index].colorInfo.x;
+    if (eye == 0)
+    {
+        const float r1 = anaglyphLuma(color);
+        const float v = (iter <= B200_NB_MAX_ITERATIONS) ? r1 + 0.f : ci[0] + (r1 + 0.f);
+        ci[0] = v;
+        packChannel(v, cP.bitmap, index, 0, iter);
+    }
+    else
+    {
+        const float g = (iter <= B200_NB_MAX_ITERATIONS) ? 0.f + color.y : ci[1] + (0.f + color.y);
+        const float b = (iter <= B200_NB_MAX_ITERATIONS) ? 0.f + color.z : ci[2] + (0.f + color.z);
+        ci[1] = g; ci[2] = b;
+        if (iter == 0) ci[3] = dof;
+        cP.ids[index] = id;
+        packChannel(g, cP.bitmap, index, 1, iter);
+        packChannel(b, cP.bitmap, index, 2, iter);
+    }
+}
+
+// a staged path has ended: its pixel (or its eye's share of the pixel) is resolved
+SB_DEV void endPath(const int tag, const float4 color, const int4 id, const float dof)
+{
+    const int index = tag & ((1 << PATH_EYE_BIT) - 1);
+    if (cSI.cameraType == B200_CT_ANAGLYPH) resolveAnaglyphEye(index, (tag >> PATH_EYE_BIT) & 1, color, id, dof);
+    else resolvePixel(index, color, f4(0.f, 0.f, 0.f, 0.f), id, dof, *reinterpret_cast<float4*>(&cP.post[index].colorInfo));
 }
 
 // pixels whose ray tree ended before this deepening pass need no work (:454-458)
@@ -222,13 +295,7 @@ SB_DEV void renderPixel(const Rotation& rot, const bool inFrame, const int xIn, 
     {
         if (anaglyph)
         {
-            // eyes at origin.x -/+ eyeSeparation, both origin and target rotated (:866-901)
-            o = f3(s == 0 ? cP.eye.x - cSI.eyeSeparation : cP.eye.x + cSI.eyeSeparation, cP.eye.y, cP.eye.z);
-            t.x = cP.target.x - stepx * (float)(x - (W / 2));
-            t.y = cP.target.y + stepy * (float)(y - (H / 2));
-            t.z = cP.target.z;
-            vectorRotation(o, rotationCenter, rot);
-            vectorRotation(t, rotationCenter, rot);
+            anaglyphRay(rot, x, y, s, o, t);
         }
         else if (antialiased && s < 4)
         {
@@ -379,18 +446,18 @@ SB_DEV void pushPaths(const int q, const bool want, const size_t slot)
 
 
 // after pass `pass` of a path (all 32 lanes call; `has` = this lane carries one): queue it for the next stage, or end it
-SB_DEV void routePath(const bool has, const PathState& s, const GlobalColors& C, const int pass, const size_t slot, const int index)
+SB_DEV void routePath(const bool has, const PathState& s, const GlobalColors& C, const int pass, const size_t slot, const int tag)
 {
     const bool cont = has && s.carryon && s.rayLength < cSI.viewDistance && pass + 1 < cP.maxIteration;
     const bool refl = has && !cont && cSI.graphicsLevel >= B200_GL_REFLECTIONS && s.reflectedRays != -1;
-    if (cont || refl) storePath(slot, s, index);
+    if (cont || refl) storePath(slot, s, tag);
     pushPaths(passQueue(pass + 1), cont, slot);
     pushPaths(reflectedQueue(), refl, slot);
     if (has && !cont && !refl)
     {
         const float4 color = pathFinish(s, C, true);
         const int4 id = make_int4(s.idx, s.iteration, s.idz, s.idw);
-        resolvePixel(index, color, f4(0.f, 0.f, 0.f, 0.f), id, s.depthOfField, *reinterpret_cast<float4*>(&cP.post[index].colorInfo));
+        endPath(tag, color, id, s.depthOfField);
     }
 }
 
@@ -443,16 +510,24 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PRIMARY) k_stage_primary
         const bool valid = inFrame && pixelNeedsWork(id);
         if (!__any_sync(FULL_MASK, valid)) continue;
         if (valid) pixelsTraced++;
-        float3 o, t;
-        primaryRay(rot, x, y, index, cP.post[index].colorInfo.w, o, t);
-        const size_t slot = (size_t)k * 32 + lane;
-        PathState s;
-        pathInit(s, o, t);
-        GlobalColors C;
-        C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
-        pathPass(s, C, 0, valid, index, o, cP.packetMask, cnt);
-        routePath(valid, s, C, 0, slot, index);
-        __syncwarp();
+        const bool anaglyph = cSI.cameraType == B200_CT_ANAGLYPH;
+        const float storedDepth = cP.post[index].colorInfo.w;
+#pragma unroll 1
+        for (int eye = 0; eye < (anaglyph ? 2 : 1); ++eye)
+        {
+            // the ids were read above, before either eye's path can end and rewrite them
+            float3 o, t;
+            if (anaglyph) anaglyphRay(rot, x, y, eye, o, t);
+            else primaryRay(rot, x, y, index, storedDepth, o, t);
+            const size_t slot = (size_t)k * 32 + lane + (size_t)eye * cP.eyeStride;
+            PathState s;
+            pathInit(s, o, t);
+            GlobalColors C;
+            C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
+            pathPass(s, C, 0, valid, index, o, cP.packetMask, cnt);
+            routePath(valid, s, C, 0, slot, index | (eye << PATH_EYE_BIT));
+            __syncwarp();
+        }
     }
     flushCounters(cnt.rays, pixelsTraced);
 }
@@ -498,15 +573,16 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
         }
 #endif
         PathState s;
-        int index = 0;
-        loadPath(slot, s, index);
-        if (!has) index = 0;
+        int tag = 0;
+        loadPath(slot, s, tag);
+        if (!has) tag = 0;
+        const int index = tag & ((1 << PATH_EYE_BIT) - 1);
         GlobalColors C;
         C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
         pathPass(s, C, pass, has, index, f3(0.f, 0.f, 0.f), 0, cnt, separateWalk ? &hit : nullptr);
         if (!fuseTail)
         {
-            routePath(has, s, C, pass, slot, index);
+            routePath(has, s, C, pass, slot, tag);
             __syncwarp();
             continue;
         }
@@ -518,7 +594,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
         for (int p = pass;; ++p)
         {
             const bool cont = live && s.carryon && s.rayLength < cSI.viewDistance && p + 1 < cP.maxIteration;
-            routePath(live && !cont, s, C, p, slot, index); // ends here: reflected-ray stage or pixel
+            routePath(live && !cont, s, C, p, slot, tag); // ends here: reflected-ray stage or pixel
             live = cont;
             if (!__any_sync(FULL_MASK, live)) break;
 #if UW_GROUP
@@ -550,9 +626,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
         const bool has = base + lane < count;
         const size_t slot = has ? (size_t)cP.pathQueues[(size_t)q * cP.pathStride + base + lane] : 0;
         PathState s;
-        int index = 0;
-        loadPath(slot, s, index);
-        if (!has) index = 0;
+        int tag = 0;
+        loadPath(slot, s, tag);
+        if (!has) tag = 0;
+        const int index = tag & ((1 << PATH_EYE_BIT) - 1);
         GlobalColors C;
         C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
         pathReflectedRay(s, C, has, index, 0, cnt);
@@ -560,7 +637,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
         {
             const float4 color = pathFinish(s, C, true);
             const int4 id = make_int4(s.idx, s.iteration, s.idz, s.idw);
-            resolvePixel(index, color, f4(0.f, 0.f, 0.f, 0.f), id, s.depthOfField, *reinterpret_cast<float4*>(&cP.post[index].colorInfo));
+            endPath(tag, color, id, s.depthOfField);
         }
         __syncwarp();
     }
@@ -720,6 +797,44 @@ __global__ void __launch_bounds__(256) k_post_process()
     }
 }
 
+// ----------------------------------------------------------------------------------------------------
+// Sample-split accumulation (north_star: "sample accumulation optionally split by GPU ... reduced with NCCL").  Past
+// NB_MAX_ITERATIONS a frame only ADDS its sample to colorInfo.xyz (CudaRayTracer.cu:550-562) and k_default divides the sum by
+// the number of samples when it packs the pixel (:1066-1070), so samples are exchangeable: every GPU renders whole frames for
+// its share of the iterations into its own accumulation buffer, the partial sums are reduced onto the root over NVLink, and the
+// root stores the total and packs.  These three kernels are the device side: one float4 per pixel crosses the wire.
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_accum_clear(b200_PostProcessingBuffer* post, const int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        float4 c = *reinterpret_cast<float4*>(&post[i].colorInfo);
+        c.x = 0.f; c.y = 0.f; c.z = 0.f; // .w is the first-hit depth of iteration 0: kept
+        *reinterpret_cast<float4*>(&post[i].colorInfo) = c;
+    }
+}
+__global__ void __launch_bounds__(256) k_accum_export(const b200_PostProcessingBuffer* post, float4* dst, const int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 c = *reinterpret_cast<const float4*>(&post[i].colorInfo);
+        dst[i] = make_float4(c.x, c.y, c.z, 0.f);
+    }
+}
+// the reduced sums come back: stored, divided by the sample count and packed (k_default fused)
+__global__ void __launch_bounds__(256) k_accum_import_pack(b200_PostProcessingBuffer* post, const float4* src, unsigned char* bitmap, const int n,
+                                                           const int iteration)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 t = src[i];
+        float4 c = *reinterpret_cast<float4*>(&post[i].colorInfo);
+        c.x = t.x; c.y = t.y; c.z = t.z;
+        *reinterpret_cast<float4*>(&post[i].colorInfo) = c;
+        packPixelAt(c, bitmap, i, iteration);
+    }
+}
+
 // FP32 FMA throughput probe (b200_measure_fp32_peak): 8 independent dependent-FFMA chains per thread, 16 steps each per iteration
 #define FP32_PEAK_FMAS_PER_ITER (8 * 16)
 __global__ void __launch_bounds__(256) k_fp32_peak(float* out, const int iters, long long* cycles)
@@ -753,6 +868,7 @@ struct Engine
     cudaStream_t ownStream = nullptr;
     cudaStream_t stream = nullptr; // the stream in use (own or caller's)
     int maxW = B200_REF_MAX_BITMAP_WIDTH, maxH = B200_REF_MAX_BITMAP_HEIGHT;
+    int frameW = 0, frameH = 0; // size of the last frame rendered
     int rank = 0, world = 1;
     int numSMs = 0, ctasPerSM = 0;
     // scene
@@ -789,8 +905,7 @@ struct Engine
     bool timed = false;
     unsigned long long launches = 0;
     // pinned registration cache for caller-owned readback buffers
-    void* regBitmap = nullptr; size_t regBitmapBytes = 0;
-    void* regIds = nullptr; size_t regIdsBytes = 0;
+    std::vector<std::pair<void*, size_t>> hostRegistered; // b200_register_host: pinned in place for their owners, never implicitly
     int err = 0;
     char errMsg[256] = {0};
 };
@@ -879,8 +994,10 @@ void uploadMeta()
 
 void unregisterHost()
 {
-    if (G.regBitmap) { cudaHostUnregister(G.regBitmap); G.regBitmap = nullptr; }
-    if (G.regIds) { cudaHostUnregister(G.regIds); G.regIds = nullptr; }
+    // owners unregister their buffers before freeing them; whatever is still listed is released here (an owner that freed first
+    // makes cudaHostUnregister fail, which must not surface later as a launch error)
+    for (auto& r : G.hostRegistered) if (cudaHostUnregister(r.first) != cudaSuccess) cudaGetLastError();
+    G.hostRegistered.clear();
     cudaGetLastError();
 }
 } // namespace
@@ -1853,6 +1970,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     if (objects.y > G.nbPrims || objects.w > B200_NB_MAX_LIGHTINFORMATIONS) { latch(-9, "b200_render", "object counts exceed uploaded scene"); return; }
     if (!G.dMats && G.nbPrims > 0) { latch(-10, "b200_render", "materials not uploaded"); return; }
 
+    G.frameW = si.size.x; G.frameH = si.size.y;
     RenderParams P;
     memset(&P, 0, sizeof(P));
     P.scene.boxes = G.dBoxes; P.scene.nbBoxes = G.nbBoxes;
@@ -1920,10 +2038,12 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     maxIteration = maxIteration > B200_NB_MAX_ITERATIONS ? B200_NB_MAX_ITERATIONS : maxIteration;
     const bool giRays = (si.advancedIllumination == B200_AI_BASIC || si.advancedIllumination == B200_AI_FULL);
     bool staged = g_useStaged && maxIteration > 1 && !giRays && si.renderBoxes == 0 &&
-                        (si.cameraType == B200_CT_PERSPECTIVE || si.cameraType == B200_CT_ORTHOGRAPHIC);
+                        (si.cameraType == B200_CT_PERSPECTIVE || si.cameraType == B200_CT_ORTHOGRAPHIC || si.cameraType == B200_CT_ANAGLYPH);
+    const int eyes = si.cameraType == B200_CT_ANAGLYPH ? 2 : 1; // paths per pixel
     if (staged)
     {
-        const size_t stride = (((size_t)P.nbLocalTiles * 32) + 63) & ~(size_t)63;
+        const size_t eyeStride = (((size_t)P.nbLocalTiles * 32) + 63) & ~(size_t)63;
+        const size_t stride = eyeStride * eyes;
         const size_t wantBytes = stride * (size_t)(maxIteration > G.pathIterations ? maxIteration : G.pathIterations);
         if (G.pathFailedBytes && wantBytes >= G.pathFailedBytes) staged = false;
         else if (stride > G.pathStride || maxIteration > G.pathIterations)
@@ -1954,6 +2074,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         if (!G.dQueueCounters) CK(cudaMalloc(&G.dQueueCounters, 2 * (B200_NB_MAX_ITERATIONS + 2) * sizeof(unsigned int)));
         P.pathWords = G.dPathWords; P.pathColors = G.dPathColors; P.pathContributions = G.dPathContrib; P.pathQueues = G.dPathQueues;
         P.queueCounters = G.dQueueCounters; P.pathStride = G.pathStride; P.maxIteration = maxIteration;
+        P.eyeStride = (((size_t)P.nbLocalTiles * 32) + 63) & ~(size_t)63;
     }
 
     CK(cudaEventRecord(G.evStart, G.stream));
@@ -2001,23 +2122,35 @@ void b200_d2h_bitmap(b200_int2, b200_SceneInfo si, b200_BitmapBuffer* bitmap, b2
     if (!ensureDevice()) return;
     const size_t px = (size_t)si.size.x * si.size.y;
     if (px > G.pixelsCap) { latch(-6, "b200_d2h_bitmap", "frame larger than the limits"); return; }
-    // The caller's buffers are pageable (GPUKernel.cpp:344-360); pin them in place once so every later
-    // frame is a straight DMA instead of a staged copy.
-    if (bitmap && (G.regBitmap != bitmap || G.regBitmapBytes < px * 3))
-    {
-        if (G.regBitmap) { cudaHostUnregister(G.regBitmap); G.regBitmap = nullptr; }
-        if (cudaHostRegister(bitmap, px * 3, cudaHostRegisterDefault) == cudaSuccess) { G.regBitmap = bitmap; G.regBitmapBytes = px * 3; }
-        else cudaGetLastError();
-    }
-    if (ids && (G.regIds != ids || G.regIdsBytes < px * 16))
-    {
-        if (G.regIds) { cudaHostUnregister(G.regIds); G.regIds = nullptr; }
-        if (cudaHostRegister(ids, px * 16, cudaHostRegisterDefault) == cudaSuccess) { G.regIds = ids; G.regIdsBytes = px * 16; }
-        else cudaGetLastError();
-    }
+    // The caller's buffers are pageable unless their owner pinned them in place (b200_register_host): the engine never pins
+    // memory it does not own on its own initiative — a cached registration outlives a freed buffer whose address is reused.
     if (bitmap) CK(cudaMemcpyAsync(bitmap, G.dBitmap, px * 3, cudaMemcpyDeviceToHost, G.stream));
     if (ids) CK(cudaMemcpyAsync(ids, G.dIds, px * 16, cudaMemcpyDeviceToHost, G.stream));
     CK(cudaStreamSynchronize(G.stream));
+}
+
+// Host buffers the caller owns for as long as they stay registered (the frame and id buffers of a host class: GPUKernel.cpp:344-360
+// allocates them once): pinned in place so that d2h_bitmap is a straight DMA instead of a staged copy.
+int b200_register_host(void* p, size_t bytes)
+{
+    if (!p || !bytes) return -4;
+    if (!ensureDevice()) return -1;
+    for (auto& r : G.hostRegistered) if (r.first == p) { if (r.second >= bytes) return 0; cudaHostUnregister(p); cudaGetLastError(); r = G.hostRegistered.back(); G.hostRegistered.pop_back(); break; }
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return -12; } // stays pageable: copies are staged
+    G.hostRegistered.push_back({p, bytes});
+    return 0;
+}
+int b200_unregister_host(void* p)
+{
+    for (size_t i = 0; i < G.hostRegistered.size(); ++i)
+        if (G.hostRegistered[i].first == p)
+        {
+            if (ensureDevice() && cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+            G.hostRegistered[i] = G.hostRegistered.back();
+            G.hostRegistered.pop_back();
+            return 0;
+        }
+    return -4;
 }
 
 void b200_d2h_primitive_id(b200_SceneInfo si, int x, int y, b200_PrimitiveXYIdBuffer* id)
@@ -2133,6 +2266,39 @@ int b200_debug_build_walk_trees(const b200_BoundingBox* boxes, int nbBoxes, cons
 void b200_synchronize(void)
 {
     if (G.stream && ensureDevice()) CK(cudaStreamSynchronize(G.stream));
+}
+
+static int accumulationPixels()
+{
+    if (!G.dPost || !G.frameW || !G.frameH) { latch(-4, "b200_accumulation_*", "no frame rendered yet"); return 0; }
+    return G.frameW * G.frameH;
+}
+int b200_accumulation_clear(void)
+{
+    if (!ensureDevice()) return -1;
+    const int n = accumulationPixels();
+    if (!n) return -4;
+    k_accum_clear<<<G.numSMs * 4, 256, 0, G.stream>>>(G.dPost, n);
+    G.launches++;
+    return (int)cudaGetLastError();
+}
+int b200_accumulation_export(void* dstFloat4)
+{
+    if (!ensureDevice()) return -1;
+    const int n = accumulationPixels();
+    if (!n || !dstFloat4) return -4;
+    k_accum_export<<<G.numSMs * 4, 256, 0, G.stream>>>(G.dPost, (float4*)dstFloat4, n);
+    G.launches++;
+    return (int)cudaGetLastError();
+}
+int b200_accumulation_import_and_pack(const void* srcFloat4, int iteration)
+{
+    if (!ensureDevice()) return -1;
+    const int n = accumulationPixels();
+    if (!n || !srcFloat4) return -4;
+    k_accum_import_pack<<<G.numSMs * 4, 256, 0, G.stream>>>(G.dPost, (const float4*)srcFloat4, G.dPeerBitmap ? G.dPeerBitmap : G.dBitmap, n, iteration);
+    G.launches++;
+    return (int)cudaGetLastError();
 }
 
 // FP32 FMA microbenchmark (BASELINE.md 2 asks for a measured value next to the nominal 148 x 128 x 2 x f): every resident lane runs

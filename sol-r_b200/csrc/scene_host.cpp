@@ -107,9 +107,16 @@ SceneHost::SceneHost(const b200_SceneInfo& sceneInfo)
     for (auto& t : m_textures) { t.offset = 0; t.size.x = t.size.y = t.size.z = 0; }
 }
 
+void SceneHost::unpinBuffers()
+{
+    if (m_pinnedBitmap) { b200_unregister_host(m_pinnedBitmap); m_pinnedBitmap = nullptr; }
+    if (m_pinnedIds) { b200_unregister_host(m_pinnedIds); m_pinnedIds = nullptr; }
+}
+
 SceneHost::~SceneHost()
 {
     dropFlat();
+    unpinBuffers();
     if (m_deviceInitialised)
     {
         b200_int2 occ = {1, 1};
@@ -1155,6 +1162,7 @@ void SceneHost::setRandoms(const float* randoms, size_t n, int timestamp)
 void SceneHost::initBuffers() // CudaKernel.cpp:116-145 + GPUKernel.cpp:299-360
 {
     const size_t px = (size_t)m_maxWidth * m_maxHeight;
+    unpinBuffers(); // a second initBuffers may move them
     m_bitmap.assign(px * B200_COLOR_DEPTH, 0);
     b200_PrimitiveXYIdBuffer zero = {0, 0, 0, 0};
     m_primitivesXYIds.assign(px, zero);
@@ -1173,6 +1181,9 @@ void SceneHost::initBuffers() // CudaKernel.cpp:116-145 + GPUKernel.cpp:299-360
     b200_initialize_scene(occ, m_sceneInfo, (int)m_maxPrimitives, NB_MAX_LAMPS, B200_NB_MAX_MATERIALS);
     b200_reshape_scene(occ, m_sceneInfo);
     m_deviceInitialised = true;
+    // this object owns the frame and id buffers for its lifetime: pinned in place, read-backs are direct DMAs
+    if (b200_register_host(m_bitmap.data(), m_bitmap.size()) == 0) m_pinnedBitmap = m_bitmap.data();
+    if (b200_register_host(m_primitivesXYIds.data(), m_primitivesXYIds.size() * sizeof(b200_PrimitiveXYIdBuffer)) == 0) m_pinnedIds = m_primitivesXYIds.data();
     m_primitivesTransfered = m_materialsTransfered = m_texturesTransfered = m_randomsTransfered = false;
 }
 

@@ -167,6 +167,9 @@ private:
     bool m_idsOnDevice = false; // the host copy is older than the last frame
     bool m_primitivesTransfered, m_materialsTransfered, m_texturesTransfered, m_randomsTransfered, m_refresh;
     bool m_deviceInitialised;
+    void* m_pinnedBitmap = nullptr; // buffers registered with the engine (b200_register_host), unpinned before they are freed
+    void* m_pinnedIds = nullptr;
+    void unpinBuffers();
     int m_maxWidth, m_maxHeight, m_rank, m_world, m_device;
 };
 } // namespace solr_b200

@@ -91,6 +91,7 @@ struct RenderParams
     int* pathQueues;           // [maxIteration + 1][pathStride] path slots; queue q feeds pass q, queue maxIteration the reflected-ray stage
     unsigned int* queueCounters; // [2 * (B200_NB_MAX_ITERATIONS + 2)]: entries pushed, entries handed out
     size_t pathStride;
+    size_t eyeStride;          // anaglyph: slots of the right eye's paths start here (two paths per pixel)
     int maxIteration;
     float4* gatherScratch; // group walk: candidate lists of the bounce rays, [resident warps][32 ray slots][GW_GATHER_CAP]
 };

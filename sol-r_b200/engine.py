@@ -69,6 +69,15 @@ def load():
     lib.b200_scene_stats.argtypes = [C.POINTER(C.c_int)] * 4
     lib.b200_measure_fp32_peak.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.b200_measure_fp32_peak.restype = C.c_int
+    lib.b200_accumulation_clear.restype = C.c_int
+    lib.b200_register_host.argtypes = [C.c_void_p, C.c_size_t]
+    lib.b200_register_host.restype = C.c_int
+    lib.b200_unregister_host.argtypes = [C.c_void_p]
+    lib.b200_unregister_host.restype = C.c_int
+    lib.b200_accumulation_export.argtypes = [C.c_void_p]
+    lib.b200_accumulation_export.restype = C.c_int
+    lib.b200_accumulation_import_and_pack.argtypes = [C.c_void_p, C.c_int]
+    lib.b200_accumulation_import_and_pack.restype = C.c_int
     for f in ("b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
               "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
               "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition", "b200_device_buffers",
@@ -84,7 +93,7 @@ ABI_SYMBOLS = [
     "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
     "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition",
     "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_build_walk_trees", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
-    "b200_synchronize", "b200_measure_fp32_peak", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
+    "b200_synchronize", "b200_measure_fp32_peak", "b200_register_host", "b200_unregister_host", "b200_accumulation_clear", "b200_accumulation_export", "b200_accumulation_import_and_pack", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
 ]
 
 

@@ -95,3 +95,47 @@ class PeerFrame:
     def close(self):
         if self.rank != self.root:
             self.lib.b200_peer_frame_open(None, 0)
+
+
+class SampleSplit:
+    """The second split north_star names: sample accumulation by GPU (include/solr_b200.h b200_accumulation_*).  Every process
+    renders the WHOLE frame (engine partition 0 of 1).  Iterations 0..first-1 — the deepening passes and the first sample, whose
+    per-pixel state (ids, first-hit depth) the later frames read — are rendered by everybody; the accumulation iterations
+    first..last are dealt out round-robin; finish() sum-reduces the partial colour sums onto the root (NCCL over NVLink; gloo
+    through host memory in the CPU-fenced tests) and the root stores them and packs the frame exactly as iteration `last` would.
+    Equal to the sequential frames up to the order of the float additions (and, for pixels that see an emissive surface, the
+    reference's running maximum over samples, CudaRayTracer.cu:553-557, which each process keeps over its own samples)."""
+
+    def __init__(self, lib, rank, world, width, height, root=0):
+        import torch
+        import torch.distributed as dist
+        self.lib, self.rank, self.world, self.root, self.dist, self.torch = lib, rank, world, root, dist, torch
+        self.buf = torch.zeros(height * width * 4, dtype=torch.float32, device="cuda")
+        self.nccl = dist.get_backend() == "nccl"
+
+    def iterations(self, first, last):
+        """This process's share of the accumulation iterations first..last."""
+        return [it for it in range(first, last + 1) if (it - first) % self.world == self.rank]
+
+    def begin(self):
+        """Call after the shared iterations (0..first-1): the root keeps the first sample, the others start their sums at zero."""
+        if self.rank != self.root:
+            self.lib.b200_accumulation_clear()
+
+    def finish(self, last):
+        lib, torch = self.lib, self.torch
+        if lib.b200_accumulation_export(self.buf.data_ptr()) != 0:
+            raise RuntimeError("b200_accumulation_export failed")
+        lib.b200_synchronize()   # the engine renders on its own stream
+        if self.nccl:
+            self.dist.reduce(self.buf, dst=self.root, op=self.dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+        else:
+            host = self.buf.cpu()
+            self.dist.reduce(host, dst=self.root, op=self.dist.ReduceOp.SUM)
+            self.buf.copy_(host)
+            torch.cuda.synchronize()
+        if self.rank == self.root:
+            if lib.b200_accumulation_import_and_pack(self.buf.data_ptr(), int(last)) != 0:
+                raise RuntimeError("b200_accumulation_import_and_pack failed")
+            lib.b200_synchronize()

@@ -115,6 +115,12 @@ def main():
                 rest = rest[rest > R] - R
                 phases += 1
             print("    cut after %2d rounds, continue compacted: warp-rounds %9d  (%.2f x) in %d phases" % (R, cost, cost / base, phases))
+        # (f) a pool of R rays per warp, lanes fetch the next ray when they finish theirs (no state parked, no second launch)
+        for R in (32, 64, 128, 256):
+            c1 = pool_rounds(vt, R)
+            c4 = pool_rounds(vt, R, refill_at=4)
+            print("    pool of %3d rays per warp, per-lane refill: warp-rounds %9d  (%.2f x); refill when 4 lanes idle: %9d  (%.2f x)" % (
+                R, c1, c1 / base, c4, c4 / base))
         # (e) no state parked: a walk that exceeds its budget is abandoned and the ray walks again from the root in a later group of
         # long rays (budgets R1 < R2 < unlimited)
         def grouped(x, cap):
@@ -128,6 +134,40 @@ def main():
                 rest = rest[rest > R]
             cost += grouped(rest, 1 << 30)
             print("    abandon after %-8s rounds, walk again compacted: warp-rounds %9d  (%.2f x)" % ("/".join(map(str, budgets)), cost, cost / base))
+
+
+def pool_rounds(v, R, lanes=32, refill_at=1):
+    """Warp-rounds when a warp takes R rays at a time and each of its lanes fetches the next ray of the pool as soon as it has
+    finished its own (greedy list scheduling in queue order); the warp runs until the pool's last ray is done.
+    refill_at: idle lanes wait until this many are idle (the refill branch then serves them together)."""
+    import heapq
+    total = 0
+    for b in range(0, len(v), R):
+        pool = list(v[b:b + R])
+        if refill_at <= 1:
+            heap = [0] * lanes
+            for x in pool:
+                t = heapq.heappop(heap)
+                heapq.heappush(heap, t + int(x))
+            total += max(heap)
+        else:
+            # event simulation with grouped refills
+            busy_until = [0] * lanes
+            nxt, now = 0, 0
+            while True:
+                idle = [i for i in range(lanes) if busy_until[i] <= now]
+                if nxt < len(pool) and (len(idle) >= refill_at or len(idle) == lanes):
+                    for i in idle:
+                        if nxt < len(pool):
+                            busy_until[i] = now + int(pool[nxt]); nxt += 1
+                later = [t for t in busy_until if t > now]
+                if not later:
+                    if nxt >= len(pool):
+                        break
+                    continue
+                now = min(later)
+            total += now
+    return total
 
 
 if __name__ == "__main__":

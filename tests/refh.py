@@ -62,9 +62,16 @@ def _ptr(a):
 class RefScene:
     """The reference's own scene container + engine, driven through its seam."""
 
-    def __init__(self, scene_info, kind="cpu"):
+    def __init__(self, scene_info, kind="cpu", limits=None):
+        """limits = (max width, max height): only the drop-in build ("b200") takes frames beyond the reference's 1920x1080."""
         self.lib = load(kind)
-        self.h = self.lib.refh_create(C.byref(scene_info))
+        if limits is not None:
+            assert kind == "b200", "the reference's own engines are limited to MAX_BITMAP_WIDTH x MAX_BITMAP_HEIGHT"
+            self.lib.refh_create_limits.restype = C.c_void_p
+            self.lib.refh_create_limits.argtypes = [C.POINTER(wire.SceneInfo), C.c_int, C.c_int]
+            self.h = self.lib.refh_create_limits(C.byref(scene_info), limits[0], limits[1])
+        else:
+            self.h = self.lib.refh_create(C.byref(scene_info))
 
     def close(self):
         if self.h:

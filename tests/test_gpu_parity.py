@@ -350,7 +350,7 @@ def test_every_case_against_the_reference_cuda_engine(name):
     assert (np.abs(bm.astype(int) - gbm.astype(int)).max(-1) > 2).sum() <= max(2, slack * n)
 
 
-@pytest.mark.parametrize("cfg", ["config1", "molecule"])
+@pytest.mark.parametrize("cfg", ["config1", "molecule", "molecule_anaglyph"])
 def test_drivers_produce_identical_frames(cfg):
     """Option key 6: the single persistent kernel (0) and the staged kernels (1, default) run the same device functions on
     the same rays: ids, the float accumulation buffer and the RGB8 frame must be bit-identical, also across progressive frames."""
@@ -358,6 +358,10 @@ def test_drivers_produce_identical_frames(cfg):
     sc = scenes.config1(1000) if cfg == "config1" else scenes.molecule(cells=3)
     si = wire.default_scene_info(W, H, graphics_level=wire.GL_FULL, nb_ray_iterations=3)
     si.maxPathTracingIterations = 13
+    if cfg == "molecule_anaglyph":
+        # two ray trees per pixel: staged, the eyes are separate paths that resolve their own channels (engine.cu resolveAnaglyphEye)
+        si.cameraType = wire.CT_ANAGLYPH
+        si.eyeSeparation = 380.0
     h = host.SceneHost(si)
     sc.replay(h)
     a = h.arrays()

@@ -56,3 +56,33 @@ def test_reference_host_drives_the_engine_unchanged(name):
     r.close()
     assert np.array_equal(bm1, bm2)
     assert np.array_equal(ids1[..., 0], ids2[..., 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not refh.available("b200"), reason="oracle/_ref/libsolr_ref_b200.so did not travel")
+def test_drop_in_beyond_the_reference_frame_limit():
+    """B200Kernel::setLimits(2560, 1440): GPUKernel's own frame / id / random buffers hold 1920x1080, so the frame lives in
+    B200Kernel's buffers and is read through getFrame() / getPrimitiveIdAt() — same pixels and ids as SceneHost at that size."""
+    W, H = 2560, 1440
+    sc, si, eye, target, angles, rnd, frames = gs.case_setup("molecule_full")
+    si.size.x, si.size.y = W, H
+    table = np.zeros(W * H, np.float32)
+    n = min(rnd.shape[0], 1920 * 1080)
+    table[:n] = rnd[:n]
+    h = host.SceneHost(si, limits=(W, H))
+    sc.replay(h)
+    h.set_randoms(table, si.timestamp)
+    h.set_camera(eye, target, angles)
+    h.init_buffers()
+    h.set_lazy_ids(False)
+    h.render_begin(0.0)
+    h.render_end()
+    bm1, ids1 = h.bitmap().copy(), h.primitive_ids().copy()
+    h.close()
+    r = refh.RefScene(si, "b200", limits=(W, H))
+    sc.replay(r)
+    bm2, ids2, _ = r.render(si, eye, target, angles, randoms=rnd, want_post=False)
+    r.close()
+    assert (ids1[..., 0] >= 0).sum() > 0.05 * W * H
+    assert np.array_equal(bm1, bm2)
+    assert np.array_equal(ids1[..., 0], ids2[..., 0])

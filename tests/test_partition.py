@@ -57,3 +57,16 @@ def test_world2_gloo_merge_reproduces_the_frame():
     port = _free_port()
     mp.spawn(_worker, args=(2, port, o.bitmap.copy(), o.ids.copy(), out), nprocs=2, join=True)
     assert out["bitmap_ok"] and out["ids_ok"]
+
+
+def test_sample_split_shares_partition_the_iterations():
+    """partition.SampleSplit deals the accumulation iterations out round-robin: every iteration to exactly one process."""
+    class _S(partition.SampleSplit):
+        def __init__(self, rank, world):
+            self.rank, self.world = rank, world
+    for world in (1, 2, 3, 8):
+        for first, last in ((11, 15), (11, 11), (11, 110)):
+            shares = [_S(r, world).iterations(first, last) for r in range(world)]
+            flat = sorted(it for s in shares for it in s)
+            assert flat == list(range(first, last + 1))
+            assert max(len(s) for s in shares) - min(len(s) for s in shares) <= 1
