@@ -93,7 +93,9 @@ struct RenderParams
     size_t pathStride;
     size_t eyeStride;          // anaglyph: slots of the right eye's paths start here (two paths per pixel)
     int maxIteration;
-    float4* gatherScratch; // group walk: candidate lists of the bounce rays, [resident warps][32 ray slots][GW_GATHER_CAP]
+    float4* gatherScratch; // group / wavefront walks: candidate lists of the bounce rays while they are walked
+    float* hitWords;       // wavefront stages (engine.cu k_wave_*): [HIT_WORDS][pathStride] closest hit of the current pass
+    float* shadowWords;    // [SHADOW_WORDS][pathStride] shadow ray of the current pass and its result
 };
 
 // One frame's parameters live in constant memory (uploaded on the render stream before the launch):
@@ -1757,6 +1759,9 @@ SB_DEV bool primitiveTestRegs(const float4 g0, const float4 g1, const float4 g2,
 }
 
 
+// the traversal stacks of a CTA's lanes ([entry][thread]); one array for the walks that use it (unorderedWalk, waveWalk)
+__shared__ int2 s_walkStack[WALK_STACK * WALK_THREADS];
+
 __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigin, const float3 rayDir, const int iteration,
                                               const int currentMaterialId, const int lightId, const int objectId)
 {
@@ -1774,7 +1779,7 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     const float invLen = rsqrtf(len2) * 1.0001f; // world distance -> t, with slack so culling stays conservative
     const float lenOL = sqrtf(len2);             // shadow: distance to the lamp (length(O_L), :877)
     const bool extended = cSI.extendedGeometry != 0;
-    __shared__ int2 s_stack[WALK_STACK * WALK_THREADS];
+    int2* const s_stack = s_walkStack;
     unsigned int sp, spLimit;
     int cur;
     int2 spillBuf[WALK_SPILL];
@@ -1966,6 +1971,10 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
 #endif
 #if UW_GROUP
 #include "tracegroup.cuh"
+#endif
+#if !defined(UW_LEGACY) && !defined(UW_V1)
+#include "tracewave.cuh"
+#define WITH_WAVE_WALK 1
 #endif
 
 SB_DEV Hit closestHitOrderIndependent(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)

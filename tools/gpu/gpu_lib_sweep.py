@@ -16,6 +16,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "child":
     parts = [(0, 1)] + ([(0, 8)] if len(sys.argv) > 3 else [])
     for rank, world in parts:
         e = engine.Engine(si, rank=rank, world=world)
+        if os.environ.get('SOLR_MODE'): e.set_option(6, int(os.environ['SOLR_MODE']))
         e.upload(a, randoms=np.zeros(1920 * 1080, np.float32))
         ms = []
         for it in range(5):
@@ -25,6 +26,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "child":
         e.lib.b200_debug_counters(cnt)
         print("%-24s part %d/%d  ms %.3f  checksum %d %d  counters %s" % (os.path.basename(sys.argv[2]), rank, world, min(ms[1:]),
               int(bm.astype(np.int64).sum()), int(ids[..., 0].astype(np.int64).sum()), list(cnt)[2:6]), flush=True)
+        if os.environ.get('SOLR_MODE'): e.set_option(6, 1)
         e.close()
 else:
     sc = scenes.config2()
