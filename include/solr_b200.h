@@ -82,6 +82,10 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
  * key 8 = bounce pass p whose queue holds at most p times this percentage of the GPU's resident lanes carries its paths to the
  *         end of their ray trees in registers instead of queueing them for one more launch per pass (default 300; 0 = never).
  * key 9 = order in which a GPU's own tiles are handed to its warps: 0 row-major (default), 1 along a Z-order curve.
+ * key 10 = where b200_h2d_scene builds the trees of the order-independent walks: 0 on host threads (binned SAH, default: the better
+ *         tree for a scene that is uploaded once), 1 on the GPU (linear BVH, sol-r_b200/csrc/treebuild.cuh: milliseconds instead of
+ *         tenths of a second per upload, for scenes that are re-uploaded every animation step — GPUKernel::rotatePrimitives +
+ *         compactBoxes(false), MoleculeScene.cpp:75-81).  Same frames either way.
  */
 void b200_set_option(int key, int value);
 /* Multi-GPU frame split: this process renders tiles t with t % worldSize == rank (interleaved 8x4-pixel
@@ -117,6 +121,9 @@ unsigned long long b200_kernel_launches(void);
 int b200_frame_parameter_bytes(void);
 /* Compacted scene statistics of the last h2d_scene: boxes kept after single-child chain collapse etc. */
 void b200_scene_stats(int* nbBoxesIn, int* nbBoxesDevice, int* nbPrimitives, int* reserved);
+/* The last b200_h2d_scene: host wall-clock milliseconds of the whole call, nodes of the main and of the point-query walk tree,
+ * and whether they were built on the GPU (option key 10).  Any pointer may be NULL. */
+void b200_scene_upload_stats(float* milliseconds, int* walkTreeNodes, int* pointQueryTreeNodes, int* builtOnGpu);
 /* Host-only (no CUDA call): the box re-layout h2d_scene applies — single-child chains collapsed, skip counts
  * recomputed, 8 floats per box: (min.xyz, w0) (max.xyz, w1), w as int bits.  Returns the number of boxes kept;
  * writes them if capacityBoxes suffices.  Lets tests check the collapse without a GPU. */

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <chrono>
 #include <algorithm>
 #include <thread>
 
@@ -1046,6 +1047,8 @@ struct Engine
     float4* dPrimRecs = nullptr; size_t capPrimRecs = 0; // 96-byte records of the unit walk (trace.cuh), 6 float4 per primitive
     // staged rendering
     float* dPathWords = nullptr; float4* dPathColors = nullptr; float* dPathContrib = nullptr; int* dPathQueues = nullptr;
+    float uploadMs = 0.f; int treesOnGpu = 0; // the last b200_h2d_scene
+    float4* dLeafBoxes = nullptr; size_t capLeafBoxes = 0; // boxes of the reference leaves, for the GPU tree build
     unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
     float* dWaveWords = nullptr; size_t waveStride = 0; // wavefront stages: hitWords + shadowWords, [HIT_WORDS + SHADOW_WORDS][waveStride]
     size_t pathFailedBytes = 0; // smallest path-state size that did not fit (not tried again)
@@ -1584,6 +1587,7 @@ int g_fuseTailPercent = 300; // k_stage_pass(p) carries its paths to the end in 
 int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: the same with pooled walks
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
+int g_gpuTrees = 0; // 1: the trees of the order-independent walks are built on the GPU (treebuild.cuh) instead of on host threads
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
 } // namespace
 
@@ -1614,6 +1618,11 @@ static int relayoutBoxes(const b200_BoundingBox* boxes, int nbBoxes, std::vector
 // ----------------------------------------------------------------------------------------------------
 // the seam
 // ----------------------------------------------------------------------------------------------------
+#ifndef UW_PAD
+#define UW_PAD 0.02f // padding of the walk trees' primitive boxes (buildWalkTrees, treebuild.cuh)
+#endif
+#include "treebuild.cuh"
+
 extern "C" {
 
 void b200_set_device(int device) { G.device = device; }
@@ -1631,6 +1640,7 @@ void b200_set_option(int key, int value)
     else if (key == 3) g_useWide = value != 0;
     else if (key == 4) g_useUnordered = value != 0;
     else if (key == 5) g_useBackward = value != 0;
+    else if (key == 10 && (value == 0 || value == 1)) g_gpuTrees = value;
     else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value; // 2: wavefront stages (k_wave_*)
     else if (key == 8 && value >= 0) g_fuseTailPercent = value;
     else if (key == 9 && (value == 0 || value == 1)) g_tileOrder = value;
@@ -1720,7 +1730,7 @@ void b200_finalize_scene(b200_int2)
     unregisterHost();
     closePeerFrame();
     freeDev(G.dWide); freeDev(G.dLeafRecs); G.capWide = G.capLeafRecs = 0; G.nbWide = 0;
-    freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0; freeDev(G.dPrimRecs); G.capPrimRecs = 0;
+    freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dLeafBoxes); G.capLeafBoxes = 0; treebuild::releaseScratch(); freeDev(G.dPrimLeaf); G.capPrimLeaf = 0; freeDev(G.dPrimRecs); G.capPrimRecs = 0;
     freeDev(G.dUGroup); G.capUGroup = 0; freeDev(G.dGatherScratch); G.capGatherScratch = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
@@ -1836,9 +1846,6 @@ static void buildWalkTrees(const std::vector<LeafRec>& leaves, const b200_Primit
             default: lo = P0[a] - fabsf(S[a]); hi = P0[a] + fabsf(S[a]); break; // ellipsoid, planes
             }
             // conservative: hit points are computed in float and the cylinder caps accept +-geometryEpsilon
-#ifndef UW_PAD
-#define UW_PAD 0.02f
-#endif
             const float pad = UW_PAD + 2e-5f * fmaxf(fabsf(lo), fabsf(hi));
             b.lo[a] = lo - pad; b.hi[a] = hi + pad;
         }
@@ -1941,11 +1948,22 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     if (!ensureDevice()) return;
     if (nbBoxes < 0 || nbPrims < 0) { latch(-5, "b200_h2d_scene", "negative count"); return; }
     G.nbBoxesIn = nbBoxes;
+    const auto uploadT0 = std::chrono::steady_clock::now();
+    const bool timing = getenv("SOLR_B200_TIMING") != nullptr;
+    auto lapT = uploadT0;
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(G.stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[solr_b200] h2d_scene %-28s %8.2f ms\n", what, std::chrono::duration<float, std::milli>(now - lapT).count());
+        lapT = now;
+    };
 
     std::vector<float4> packed;
     std::vector<LeafRec> leaves;
     const int nOut = relayoutBoxes(boxes, nbBoxes, packed, &G.boxLayoutUsed, &leaves);
 
+    lap("ordered tree (relayout)");
     // 2b. the 4-wide form of the ordered BVH for the per-lane walks
     std::vector<float4> wide, leafRecs;
     G.nbWide = (G.boxLayoutUsed == 2) ? buildWide(packed, wide, leafRecs) : 0;
@@ -1953,15 +1971,61 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     if (leafRecs.size() > G.capLeafRecs) { freeDev(G.dLeafRecs); G.capLeafRecs = leafRecs.size() + 1024; CK(cudaMalloc(&G.dLeafRecs, G.capLeafRecs * sizeof(float4))); }
     if (!wide.empty()) CK(cudaMemcpyAsync(G.dWide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
     if (!leafRecs.empty()) CK(cudaMemcpyAsync(G.dLeafRecs, leafRecs.data(), leafRecs.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+    lap("4-wide ordered tree + upload");
     // 2c. the trees of the order-independent walks
     std::vector<float4> uwide;
     std::vector<int> primLeaf(nbPrims > 0 ? nbPrims : 1, 0);
     G.nbUWide = 0; G.nbUX = 0;
-    if (G.boxLayoutUsed == 2 && G.nbWide > 0 && g_useUnordered && nbPrims > 0) buildWalkTrees(leaves, prims, nbPrims, uwide, primLeaf, G.nbUWide, G.nbUX);
+    const bool wantTrees = G.boxLayoutUsed == 2 && G.nbWide > 0 && g_useUnordered && nbPrims > 0;
+    const bool gpuTrees = wantTrees && g_gpuTrees && !UW_GROUP;
+    if (gpuTrees)
+    {
+        for (size_t l = 0; l < leaves.size(); ++l)
+            for (int k = 0; k < leaves[l].count; ++k)
+                if (leaves[l].start + k >= 0 && leaves[l].start + k < nbPrims) primLeaf[leaves[l].start + k] = (int)l;
+    }
+    else if (wantTrees) buildWalkTrees(leaves, prims, nbPrims, uwide, primLeaf, G.nbUWide, G.nbUX);
+    lap("walk trees on the host");
     if ((size_t)nbPrims > G.capPrimLeaf) { freeDev(G.dPrimLeaf); G.capPrimLeaf = (size_t)nbPrims + 1024; CK(cudaMalloc(&G.dPrimLeaf, G.capPrimLeaf * sizeof(int))); }
     if (nbPrims > 0) CK(cudaMemcpyAsync(G.dPrimLeaf, primLeaf.data(), (size_t)nbPrims * sizeof(int), cudaMemcpyHostToDevice, G.stream));
     if (uwide.size() > G.capUWide) { freeDev(G.dUWide); G.capUWide = uwide.size() + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
     if (!uwide.empty()) CK(cudaMemcpyAsync(G.dUWide, uwide.data(), uwide.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+    if (gpuTrees)
+    {
+        // the primitives and the reference leaves' boxes go up first; the trees are built from them on the device
+        if ((size_t)nbPrims > G.capPrims)
+        {
+            freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims);
+            G.capPrims = (size_t)nbPrims + 1024;
+            CK(cudaMalloc(&G.dGeo, 4 * G.capPrims * sizeof(float4)));
+            CK(cudaMalloc(&G.dMeta, G.capPrims * sizeof(int)));
+            CK(cudaMalloc(&G.dPrims, G.capPrims * sizeof(b200_Primitive)));
+        }
+        CK(cudaMemcpyAsync(G.dPrims, prims, (size_t)nbPrims * sizeof(b200_Primitive), cudaMemcpyHostToDevice, G.stream));
+        std::vector<float4> leafBoxes(2 * leaves.size());
+        for (size_t l = 0; l < leaves.size(); ++l)
+        {
+            leafBoxes[2 * l] = make_float4(leaves[l].box.lo[0], leaves[l].box.lo[1], leaves[l].box.lo[2], 0.f);
+            leafBoxes[2 * l + 1] = make_float4(leaves[l].box.hi[0], leaves[l].box.hi[1], leaves[l].box.hi[2], 0.f);
+        }
+        if (leafBoxes.size() > G.capLeafBoxes) { freeDev(G.dLeafBoxes); G.capLeafBoxes = leafBoxes.size() + 1024; CK(cudaMalloc(&G.dLeafBoxes, G.capLeafBoxes * sizeof(float4))); }
+        CK(cudaMemcpyAsync(G.dLeafBoxes, leafBoxes.data(), leafBoxes.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+        const int nbExtBoxes = g_useBackward ? treebuild::extCount(G.dPrims, nbPrims, G.dPrimLeaf, G.dLeafBoxes, G.stream) : 0;
+        int rc = nbExtBoxes < 0 ? nbExtBoxes : 0;
+        if (rc == 0)
+        {
+            const size_t wantF4 = 8 * ((size_t)nbPrims + (size_t)nbExtBoxes) + 8;
+            if (wantF4 > G.capUWide) { CK(cudaStreamSynchronize(G.stream)); freeDev(G.dUWide); G.capUWide = wantF4 + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
+            rc = treebuild::buildWalkTreesGpu(G.dPrims, nbPrims, G.dPrimLeaf, G.dLeafBoxes, nbExtBoxes, G.dUWide, G.nbUWide, G.nbUX, G.stream);
+        }
+        cudaError_t e = cudaGetLastError();
+        if (rc != 0 || e != cudaSuccess)
+        {
+            latch(rc != 0 ? rc : (int)e, "b200_h2d_scene", "building the walk trees on the GPU failed");
+            G.nbUWide = 0; G.nbUX = 0;
+        }
+    }
+    lap("walk trees on the GPU");
     // child-major copy for the group walk: child c of node n at float4 (n * width + c) * 2 — (lo.xyz, hi.x) (hi.yz, ref, -)
     std::vector<float4> ugroup;
 #if UW_GROUP
@@ -1984,6 +2048,7 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
 #endif
     CK(cudaStreamSynchronize(G.stream));
 
+    lap("uploads of the trees");
     // 3. primitives
     std::vector<float4> geo(4 * (size_t)nbPrims);
     for (int i = 0; i < nbPrims; ++i)
@@ -2017,6 +2082,7 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
         CK(cudaStreamSynchronize(G.stream)); // staging vector dies here
     }
 
+    lap("geometry + primitive records");
     // 4. device buffers (grow-only) and upload
     if ((size_t)nOut > G.capBoxes || (size_t)nbBoxes > G.capBoxes)
     {
@@ -2042,7 +2108,11 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     }
     CK(cudaStreamSynchronize(G.stream)); // staging vectors die at scope exit
     G.nbBoxes = nOut; G.nbPrims = nbPrims;
+    lap("boxes, geometry, primitives up");
     uploadMeta();
+    lap("packed words");
+    G.treesOnGpu = gpuTrees ? 1 : 0;
+    G.uploadMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - uploadT0).count();
 }
 
 void b200_h2d_materials(b200_int2, const b200_Material* materials, int n)
@@ -2426,6 +2496,14 @@ float b200_last_render_ms(void)
 
 unsigned long long b200_kernel_launches(void) { return G.launches; }
 int b200_frame_parameter_bytes(void) { return (int)sizeof(RenderParams); }
+
+void b200_scene_upload_stats(float* ms, int* nodes, int* nodesExt, int* gpu)
+{
+    if (ms) *ms = G.uploadMs;
+    if (nodes) *nodes = G.nbUWide;
+    if (nodesExt) *nodesExt = G.nbUX;
+    if (gpu) *gpu = G.treesOnGpu;
+}
 
 void b200_scene_stats(int* in, int* dev, int* prims, int* reserved)
 {

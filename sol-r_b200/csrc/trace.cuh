@@ -1788,6 +1788,11 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     float candD[GATHER_CAP], candLeafT[GATHER_CAP];
     int n = 0;
     bool overflow = false;
+    // UW_GATHER: the closest candidate so far (in out.hit), its reference leaf and that leaf's entry distance; whether another
+    // candidate lies at exactly its distance
+    int bestLeaf = -1;
+    float bestLeafT = 0.f;
+    bool bestTie = false;
     float best = minDistance0;   // closest accepted / gathered distance so far
     float window = minDistance0; // UW_GATHER: candidates farther than this are inert
     // entry-t bound for nodes: never beyond the reference's own t_min < closest-so-far test; a shadow blocker lies before the lamp (t ~ 1)
@@ -1903,7 +1908,10 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
                 best = distance;
                 window = fminf(minDistance0, GATHER_WINDOW * best);
                 cullT = fminf(minDistance0, window * invLen);
+                out.hit.prim = idx; out.hit.p = I; out.hit.flags = flags;
+                bestLeaf = __float_as_int(a4.w); bestLeafT = leafT; bestTie = false;
             }
+            else if (distance == best && idx != out.hit.prim) bestTie = true;
             if (n == GATHER_CAP)
             {
                 int m2 = 0; // full: drop what fell out of the window meanwhile
@@ -1928,6 +1936,21 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
         return out;
     }
     if (mode != UW_GATHER) return out;
+    if (n == 0) { out.hit.prim = -1; return out; }
+    // The reference's accept/reject sequence almost always ends with the closest candidate X (kept in out.hit with its hit point):
+    // every candidate accepted before X's leaf is reached lies farther than X, so the leaf passes its t_min < closest-so-far test
+    // unless one of them lies within [d_X, t_min(leaf of X)] — a candidate of another leaf, earlier in the array, at most t_min(leaf
+    // of X) away.  One pass over the list looks for such a candidate (any, accepted or not: conservative); only then — or when two
+    // candidates share the closest distance — the full replay below decides.  (Round 2: the replay, quadratic in the list length and
+    // run by one to three lanes of a warp, was a quarter of a bounce pass's time; profiles/r02_history.md.)
+    {
+        bool slow = bestTie;
+        for (int j = 0; j < n; ++j)
+            slow |= candIdx[j] < out.hit.prim && candLeaf[j] != bestLeaf && candD[j] <= bestLeafT && candD[j] <= window;
+        DBG_ADD(0 + 6, 0); DBG_ADD(3, slow ? 1 : 0);
+        if (!slow) return out;
+    }
+    out.hit.prim = -1; out.hit.p = f3(0.f, 0.f, 0.f); out.hit.flags = 0;
     // replay in array order (selection by ascending index: the list is short; a cylinder listed twice by the point query is
     // taken once).  Primitives of one leaf are contiguous and share the leaf's fate, decided when the leaf is reached (before
     // any of its primitives): t_min(leaf) < closest-so-far.

@@ -118,6 +118,7 @@ __device__ __forceinline__ void waveLeaves(const int kind, const float minDistan
         float3 I;
         int flags;
         float planeShadow;
+        DBG_ADD(7, 1);
         if (!primitiveTestRegs(a0, a1, a2, a3, idx, meta, r, I, flags, planeShadow)) continue;
         const float distance = length(I - r.o);
         if (!(distance > eps)) continue;
@@ -287,6 +288,7 @@ __device__ __forceinline__ void waveWalk(const int kind, const int iteration, co
                 {
                     if (!walkSpill(s_stack, spillBuf, nSpill, sp)) { fl |= PF_OVERFLOW; nSpill = 0; nq = 0; cur = WALK_DONE; continue; } // degenerate tree
                 }
+                DBG_ADD(5, 1);
                 const float4* item = nodes + (size_t)8 * cur;
                 float4 a0, a1, a2, a3, a4, a5, a6, a7;
                 ldNode256(item, a0, a1); ldNode256(item + 2, a2, a3); ldNode256(item + 4, a4, a5); ldNode256(item + 6, a6, a7);
@@ -306,6 +308,8 @@ __device__ __forceinline__ void waveWalk(const int kind, const int iteration, co
         // ------------------------------------------------------------------ LEAF phase
         if (__any_sync(FULL_MASK, nq > 0))
         {
+            if (lane == 0) { DBG_ADD(2, 1); }
+            DBG_ADD(4, nq);
             waveLeaves(kind, minDistance0, list, nq, cur, nSpill, fl, cullT);
             nq = 0;
         }

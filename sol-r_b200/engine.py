@@ -81,7 +81,7 @@ def load():
     for f in ("b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
               "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
               "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition", "b200_device_buffers",
-              "b200_get_counters", "b200_scene_stats", "b200_synchronize", "b200_clear_error"):
+              "b200_get_counters", "b200_scene_stats", "b200_scene_upload_stats", "b200_synchronize", "b200_clear_error"):
         getattr(lib, f).restype = None
     _lib = lib
     return lib
@@ -92,7 +92,7 @@ ABI_SYMBOLS = [
     "b200_initialize_scene", "b200_finalize_scene", "b200_reshape_scene", "b200_h2d_scene", "b200_h2d_materials",
     "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
     "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition",
-    "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_build_walk_trees", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats",
+    "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_build_walk_trees", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats", "b200_scene_upload_stats",
     "b200_synchronize", "b200_measure_fp32_peak", "b200_register_host", "b200_unregister_host", "b200_accumulation_clear", "b200_accumulation_export", "b200_accumulation_import_and_pack", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
 ]
 
@@ -230,7 +230,10 @@ class Engine:
     def scene_stats(self):
         v = [C.c_int() for _ in range(4)]
         self.lib.b200_scene_stats(*[C.byref(x) for x in v])
-        return {"boxes_in": v[0].value, "boxes_device": v[1].value, "primitives": v[2].value, "resident_ctas": v[3].value}
+        ms, n0, n1, gpu = C.c_float(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.b200_scene_upload_stats(C.byref(ms), C.byref(n0), C.byref(n1), C.byref(gpu))
+        return {"boxes_in": v[0].value, "boxes_device": v[1].value, "primitives": v[2].value, "resident_ctas": v[3].value,
+                "upload_ms": ms.value, "walk_tree_nodes": n0.value, "point_query_tree_nodes": n1.value, "trees_built_on_gpu": gpu.value}
 
     def device_buffers(self):
         b, i, p = C.c_void_p(), C.c_void_p(), C.c_void_p()

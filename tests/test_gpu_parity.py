@@ -391,6 +391,47 @@ def test_drivers_produce_identical_frames(cfg):
         assert rays == out[0][3]
 
 
+@pytest.mark.parametrize("cfg", ["config1", "molecule", "mesh"])
+def test_gpu_built_walk_trees_give_identical_frames(cfg):
+    """Option key 10: the trees of the order-independent walks built on the GPU (linear BVH, csrc/treebuild.cuh) instead of on host
+    threads (binned SAH).  The walks' results do not depend on the tree, so ids, float accumulation buffer, RGB8 and ray count must
+    be bit-identical — after the first upload and after the scene has been rotated and uploaded again (the animation step of
+    MoleculeScene.cpp:75-81), with the engine going back and forth between the two builders."""
+    W, H = 640, 360
+    sc = scenes.config1(1000) if cfg == "config1" else scenes.molecule(cells=3) if cfg == "molecule" else scenes.triangle_mesh(20000)
+    si = wire.default_scene_info(W, H, graphics_level=wire.GL_FULL, nb_ray_iterations=3)
+    rnd = gs.randoms(47)
+    h = host.SceneHost(si)
+    sc.replay(h)
+    steps = [dict(h.arrays())]
+    h.rotate_primitives((0.0, 0.0, 0.0), (0.1, 0.25, 0.05))
+    h.compact_boxes(False)
+    steps.append(dict(h.arrays()))
+    h.close()
+    out = {}
+    for gpu in (0, 1):
+        e = engine.Engine(si)
+        try:
+            e.set_option(10, gpu)
+            for k, a in enumerate(steps):
+                e.upload(a, randoms=rnd)
+                e.render(si, sc.eye, sc.target, sc.angles)
+                bm, ids = e.readback(si)
+                post = e.read_post_buffer(si)
+                rays, _ = e.counters(reset=True)
+                out[(gpu, k)] = (bm.copy(), ids.copy(), post.copy(), rays)
+                assert e.scene_stats()["walk_tree_nodes"] > 0
+        finally:
+            e.set_option(10, 0)
+            e.close()
+    for k in range(len(steps)):
+        assert np.array_equal(out[(1, k)][1], out[(0, k)][1])
+        assert np.array_equal(out[(1, k)][2].view(np.uint32), out[(0, k)][2].view(np.uint32))
+        assert np.array_equal(out[(1, k)][0], out[(0, k)][0])
+        assert out[(1, k)][3] == out[(0, k)][3]
+    assert not np.array_equal(out[(0, 0)][1], out[(0, 1)][1])  # the rotation changed the picture
+
+
 def test_small_queue_passes_in_registers_give_identical_frames():
     """Option key 8: a bounce pass whose queue is small carries its paths to the end of their ray trees in registers instead
     of parking them for another launch per pass.  Never (0), always (a huge percentage) and the default must agree bit for bit

@@ -25,7 +25,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "child":
         cnt = (C.c_ulonglong * 8)()
         e.lib.b200_debug_counters(cnt)
         print("%-24s part %d/%d  ms %.3f  checksum %d %d  counters %s" % (os.path.basename(sys.argv[2]), rank, world, min(ms[1:]),
-              int(bm.astype(np.int64).sum()), int(ids[..., 0].astype(np.int64).sum()), list(cnt)[2:6]), flush=True)
+              int(bm.astype(np.int64).sum()), int(ids[..., 0].astype(np.int64).sum()), list(cnt)[2:8]), flush=True)
         if os.environ.get('SOLR_MODE'): e.set_option(6, 1)
         e.close()
 else:
