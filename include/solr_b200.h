@@ -100,6 +100,18 @@ void b200_set_partition(int rank, int worldSize);
  * b200_peer_frame_open(NULL, 0) goes back to the local bitmap.  Both return 0 or the latched error code. */
 int b200_peer_frame_export(void* handle64, int handleBytes);
 int b200_peer_frame_open(const void* handle64, int handleBytes);
+/* Scene replication for the multi-GPU frame split (replaces the reference's per-device upload loop, CudaRayTracer.cu:1540-1613): the
+ * root process uploads the scene with b200_h2d_scene, b200_scene_layout describes what it built (B200_SCENE_LAYOUT_ENTRIES
+ * numbers), every other process passes those numbers to b200_scene_adopt_layout, which allocates its device arrays, and the
+ * arrays listed by b200_scene_device_arrays (same order on every process; a NULL pointer is an empty array) are then filled from
+ * the root's over NVLink — sol-r_b200/partition.py broadcast_scene does it with one NCCL broadcast per array.
+ * b200_scene_adopt_finish completes the adopted scene (host copy of the primitives, packed material words).  Materials, lights,
+ * textures and randoms go up per process as before.  All return a count or 0, or a negative / latched error code. */
+#define B200_SCENE_LAYOUT_ENTRIES 10
+int b200_scene_layout(long long* layout, int capacity);
+int b200_scene_adopt_layout(const long long* layout, int entries);
+int b200_scene_device_arrays(void** devicePointers, long long* bytes, int capacity);
+int b200_scene_adopt_finish(void);
 /* Device pointers of the per-pixel buffers for in-place collectives (NCCL) — valid until reshape/finalize. */
 void b200_device_buffers(void** bitmap, void** primitivesXYIds, void** postProcessingBuffer);
 /* One pixel's PrimitiveXYIdBuffer (16 bytes) from the device: what GPUKernel::getPrimitiveAt (GPUKernel.cpp:729-739) reads, the only

@@ -1048,6 +1048,7 @@ struct Engine
     // staged rendering
     float* dPathWords = nullptr; float4* dPathColors = nullptr; float* dPathContrib = nullptr; int* dPathQueues = nullptr;
     float uploadMs = 0.f; int treesOnGpu = 0; // the last b200_h2d_scene
+    size_t nWideF4 = 0, nLeafRecsF4 = 0;      // float4 in dWide / dLeafRecs (scene replication)
     float4* dLeafBoxes = nullptr; size_t capLeafBoxes = 0; // boxes of the reference leaves, for the GPU tree build
     unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
     float* dWaveWords = nullptr; size_t waveStride = 0; // wavefront stages: hitWords + shadowWords, [HIT_WORDS + SHADOW_WORDS][waveStride]
@@ -1496,7 +1497,10 @@ struct SahBuilder
             }
         }
         int mid = (i + j) / 2;
-        const int NB = 16;
+#ifndef SAH_BINS
+#define SAH_BINS 16
+#endif
+        const int NB = SAH_BINS;
         double bestCost = 1e300; int bestAxis = -1, bestBin = -1;
         if (depth < 60)
             for (int a = 0; a < 3; ++a)
@@ -1969,6 +1973,7 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     G.nbWide = (G.boxLayoutUsed == 2) ? buildWide(packed, wide, leafRecs) : 0;
     if (wide.size() > G.capWide) { freeDev(G.dWide); G.capWide = wide.size() + 1024; CK(cudaMalloc(&G.dWide, G.capWide * sizeof(float4))); }
     if (leafRecs.size() > G.capLeafRecs) { freeDev(G.dLeafRecs); G.capLeafRecs = leafRecs.size() + 1024; CK(cudaMalloc(&G.dLeafRecs, G.capLeafRecs * sizeof(float4))); }
+    G.nWideF4 = wide.size(); G.nLeafRecsF4 = leafRecs.size();
     if (!wide.empty()) CK(cudaMemcpyAsync(G.dWide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
     if (!leafRecs.empty()) CK(cudaMemcpyAsync(G.dLeafRecs, leafRecs.data(), leafRecs.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
     lap("4-wide ordered tree + upload");
@@ -2113,6 +2118,96 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     lap("packed words");
     G.treesOnGpu = gpuTrees ? 1 : 0;
     G.uploadMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - uploadT0).count();
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Scene replication for the multi-GPU frame split: one process uploads the scene (b200_h2d_scene: host tree builds and all), the
+// others adopt its layout and receive the device arrays from it over NVLink (sol-r_b200/partition.py broadcast_scene: one NCCL
+// broadcast per array) instead of each repeating the host work and its own PCIe copies — the reference's dormant multi-GPU path
+// uploads every array to every device from the host (CudaRayTracer.cu:1540-1613 inside the per-device loop).
+// Materials, lights, textures and randoms are small and go up per process as before.
+// ----------------------------------------------------------------------------------------------------
+#define SCENE_LAYOUT_ENTRIES 10
+static size_t sceneArrayList(void** ptrs, long long* bytes, int cap)
+{
+    void* p[10] = {G.dBoxes, G.dRawBoxes, G.dGeo, G.dMeta, G.dPrims, G.dWide, G.dLeafRecs, G.dPrimLeaf, G.dPrimRecs, G.dUWide};
+    const long long b[10] = {
+        (long long)(2 * (size_t)G.nbBoxes * sizeof(float4)), (long long)((size_t)G.nbBoxesIn * sizeof(b200_BoundingBox)),
+        (long long)(4 * (size_t)G.nbPrims * sizeof(float4)), (long long)((size_t)G.nbPrims * sizeof(int)),
+        (long long)((size_t)G.nbPrims * sizeof(b200_Primitive)), (long long)(G.nWideF4 * sizeof(float4)), (long long)(G.nLeafRecsF4 * sizeof(float4)),
+        (long long)((size_t)G.nbPrims * sizeof(int)), (long long)(G.nbUWide > 0 ? ((size_t)PRIM_REC_F4 * G.nbPrims + 2) * sizeof(float4) : 0),
+        (long long)(8 * ((size_t)G.nbUWide + (size_t)G.nbUX) * sizeof(float4))};
+    int n = 0;
+    for (int k = 0; k < 10 && n < cap; ++k, ++n) { if (ptrs) ptrs[n] = b[k] ? p[k] : nullptr; if (bytes) bytes[n] = b[k]; }
+    return (size_t)n;
+}
+
+int b200_scene_layout(long long* layout, int capacity)
+{
+    if (!layout || capacity < SCENE_LAYOUT_ENTRIES) return -4;
+    const long long v[SCENE_LAYOUT_ENTRIES] = {G.nbBoxesIn, G.nbBoxes, G.nbPrims, G.boxLayoutUsed, G.nbWide, (long long)G.nWideF4, (long long)G.nLeafRecsF4,
+                                               G.nbUWide, G.nbUX, G.treesOnGpu};
+    for (int k = 0; k < SCENE_LAYOUT_ENTRIES; ++k) layout[k] = v[k];
+    return SCENE_LAYOUT_ENTRIES;
+}
+
+int b200_scene_adopt_layout(const long long* layout, int n)
+{
+    if (!G.initialised) { latch(-4, "b200_scene_adopt_layout", "initialize_scene not called"); return -4; }
+    if (!layout || n < SCENE_LAYOUT_ENTRIES) return -4;
+    if (!ensureDevice()) return -1;
+    CK(cudaStreamSynchronize(G.stream));
+    const int nbBoxesIn = (int)layout[0], nOut = (int)layout[1], nbPrims = (int)layout[2];
+    if (nbBoxesIn < 0 || nOut < 0 || nbPrims < 0) { latch(-5, "b200_scene_adopt_layout", "negative count"); return -5; }
+    G.nbBoxesIn = nbBoxesIn; G.nbBoxes = nOut; G.nbPrims = nbPrims; G.boxLayoutUsed = (int)layout[3];
+    G.nbWide = (int)layout[4]; G.nWideF4 = (size_t)layout[5]; G.nLeafRecsF4 = (size_t)layout[6];
+    G.nbUWide = (int)layout[7]; G.nbUX = (int)layout[8]; G.treesOnGpu = (int)layout[9];
+    if ((size_t)nOut > G.capBoxes || (size_t)nbBoxesIn > G.capBoxes)
+    {
+        freeDev(G.dBoxes); freeDev(G.dRawBoxes);
+        G.capBoxes = (size_t)(nbBoxesIn > nOut ? nbBoxesIn : nOut) + 1024;
+        CK(cudaMalloc(&G.dBoxes, 2 * G.capBoxes * sizeof(float4)));
+        CK(cudaMalloc(&G.dRawBoxes, G.capBoxes * sizeof(b200_BoundingBox)));
+    }
+    if ((size_t)nbPrims > G.capPrims)
+    {
+        freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims);
+        G.capPrims = (size_t)nbPrims + 1024;
+        CK(cudaMalloc(&G.dGeo, 4 * G.capPrims * sizeof(float4)));
+        CK(cudaMalloc(&G.dMeta, G.capPrims * sizeof(int)));
+        CK(cudaMalloc(&G.dPrims, G.capPrims * sizeof(b200_Primitive)));
+    }
+    if (G.nWideF4 > G.capWide) { freeDev(G.dWide); G.capWide = G.nWideF4 + 1024; CK(cudaMalloc(&G.dWide, G.capWide * sizeof(float4))); }
+    if (G.nLeafRecsF4 > G.capLeafRecs) { freeDev(G.dLeafRecs); G.capLeafRecs = G.nLeafRecsF4 + 1024; CK(cudaMalloc(&G.dLeafRecs, G.capLeafRecs * sizeof(float4))); }
+    if ((size_t)nbPrims > G.capPrimLeaf) { freeDev(G.dPrimLeaf); G.capPrimLeaf = (size_t)nbPrims + 1024; CK(cudaMalloc(&G.dPrimLeaf, G.capPrimLeaf * sizeof(int))); }
+    const size_t recsF4 = G.nbUWide > 0 ? (size_t)PRIM_REC_F4 * nbPrims + 2 : 0;
+    if (recsF4 > G.capPrimRecs) { freeDev(G.dPrimRecs); G.capPrimRecs = recsF4 + 1024; CK(cudaMalloc(&G.dPrimRecs, G.capPrimRecs * sizeof(float4))); }
+    const size_t uwF4 = 8 * ((size_t)G.nbUWide + (size_t)G.nbUX);
+    if (uwF4 > G.capUWide) { freeDev(G.dUWide); G.capUWide = uwF4 + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
+    return G.err;
+}
+
+int b200_scene_device_arrays(void** ptrs, long long* bytes, int capacity)
+{
+    if (!ensureDevice()) return -1;
+    CK(cudaStreamSynchronize(G.stream)); // the arrays are about to be read or written by somebody else's stream
+    return (int)sceneArrayList(ptrs, bytes, capacity);
+}
+
+int b200_scene_adopt_finish(void)
+{
+    if (!ensureDevice()) return -1;
+    // the host copy of the primitives (the packed words are re-derived from it whenever the materials change)
+    G.hPrims.resize((size_t)G.nbPrims);
+    if (G.nbPrims > 0) CK(cudaMemcpy(G.hPrims.data(), G.dPrims, (size_t)G.nbPrims * sizeof(b200_Primitive), cudaMemcpyDeviceToHost));
+    if (!G.hMats.empty()) uploadMeta();
+    else
+    {
+        // no materials here yet: the packed words that arrived are the root's; whether every shadow caster is opaque follows from them
+        // only together with the materials, so stay on the safe side until b200_h2d_materials runs
+        G.opaqueShadows = 0;
+    }
+    return G.err;
 }
 
 void b200_h2d_materials(b200_int2, const b200_Material* materials, int n)

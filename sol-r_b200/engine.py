@@ -83,6 +83,11 @@ def load():
               "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition", "b200_device_buffers",
               "b200_get_counters", "b200_scene_stats", "b200_scene_upload_stats", "b200_synchronize", "b200_clear_error"):
         getattr(lib, f).restype = None
+    lib.b200_scene_layout.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    lib.b200_scene_adopt_layout.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    lib.b200_scene_device_arrays.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.c_int]
+    for f in ("b200_scene_layout", "b200_scene_adopt_layout", "b200_scene_device_arrays", "b200_scene_adopt_finish"):
+        getattr(lib, f).restype = C.c_int
     _lib = lib
     return lib
 
@@ -93,6 +98,7 @@ ABI_SYMBOLS = [
     "b200_h2d_randoms", "b200_h2d_textures", "b200_h2d_lightInformation", "b200_d2h_bitmap", "b200_render",
     "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition",
     "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_build_walk_trees", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats", "b200_scene_upload_stats",
+    "b200_scene_layout", "b200_scene_adopt_layout", "b200_scene_device_arrays", "b200_scene_adopt_finish",
     "b200_synchronize", "b200_measure_fp32_peak", "b200_register_host", "b200_unregister_host", "b200_accumulation_clear", "b200_accumulation_export", "b200_accumulation_import_and_pack", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
 ]
 
@@ -189,6 +195,49 @@ class Engine:
             infos, n = textures
             self.lib.b200_h2d_textures(self.OCC, n, C.cast(infos, C.c_void_p))
         self.objects = wire.Int4(a["nbBoxes"], a["nbPrimitives"], a.get("nbLamps", 0), a["lightInformationSize"])
+        self.check()
+
+    def upload_small(self, arrays, randoms=None, textures=None):
+        """Everything but the boxes and primitives (lights, materials, randoms, textures): what every process of a multi-GPU frame
+        split still uploads itself when the scene proper arrives from the root over NVLink (partition.broadcast_scene)."""
+        a = arrays
+        self._keep = {k: np.ascontiguousarray(v) for k, v in a.items() if isinstance(v, np.ndarray) and k not in ("boxes", "primitives")}
+        k = self._keep
+        self.lib.b200_h2d_lightInformation(self.OCC, _ptr(k["lightInformation"]) if a["lightInformationSize"] else None,
+                                           a["lightInformationSize"])
+        self.lib.b200_h2d_materials(self.OCC, _ptr(k["materials"]), a["nbMaterials"])
+        if randoms is not None:
+            r = np.ascontiguousarray(randoms, np.float32)
+            assert r.shape[0] >= self.limits[0] * self.limits[1]
+            self.lib.b200_h2d_randoms(self.OCC, _ptr(r))
+        if textures is not None:
+            infos, n = textures
+            self.lib.b200_h2d_textures(self.OCC, n, C.cast(infos, C.c_void_p))
+        self.check()
+
+    def scene_layout(self):
+        v = (C.c_longlong * 16)()
+        n = self.lib.b200_scene_layout(v, 16)
+        self.check()
+        return [int(x) for x in v[:n]]
+
+    def adopt_layout(self, layout, nb_lamps, light_information_size):
+        """Device arrays for a scene another process built (layout = its scene_layout())."""
+        v = (C.c_longlong * len(layout))(*layout)
+        self.lib.b200_scene_adopt_layout(v, len(layout))
+        self.objects = wire.Int4(int(layout[0]), int(layout[2]), nb_lamps, light_information_size)
+        self.check()
+
+    def scene_device_arrays(self):
+        """[(device pointer or None, bytes)] of the scene's device arrays, in the order every process lists them."""
+        ptrs = (C.c_void_p * 16)()
+        nbytes = (C.c_longlong * 16)()
+        n = self.lib.b200_scene_device_arrays(ptrs, nbytes, 16)
+        self.check()
+        return [(ptrs[i], int(nbytes[i])) for i in range(n)]
+
+    def adopt_finish(self):
+        self.lib.b200_scene_adopt_finish()
         self.check()
 
     def render(self, scene_info, eye, target, angles, post_info=None):

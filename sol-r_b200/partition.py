@@ -46,6 +46,47 @@ def device_tensors(engine, width, height):
     return bitmap, ids
 
 
+def broadcast_scene(engine, arrays, rank, world, src=0, randoms=None, textures=None):
+    """Scene replication for the frame split (include/solr_b200.h b200_scene_layout ...): the root uploads the scene — host tree
+    builds, PCIe copies — once; every other rank allocates device arrays of the same layout and receives them from the root's with
+    one broadcast per array (NCCL over NVLink; the reference's dormant multi-GPU path uploads everything per device from the host,
+    CudaRayTracer.cu:1540-1613).  `arrays` must be the same on every rank only as far as lights, materials and counts go: the boxes
+    and primitives of non-root ranks are never read.  Returns the bytes received per rank."""
+    import torch
+    import torch.distributed as dist
+    staged = dist.get_backend() != "nccl"  # gloo (tests: two ranks on one device) moves the arrays through host memory
+    dev = torch.device("cpu") if staged else torch.device("cuda", torch.cuda.current_device())
+    if rank == src:
+        engine.upload(arrays, randoms=randoms, textures=textures)
+        layout = torch.tensor(engine.scene_layout(), dtype=torch.int64, device=dev)
+    else:
+        engine.upload_small(arrays, randoms=randoms, textures=textures)
+        layout = torch.zeros(16, dtype=torch.int64, device=dev)
+    n = torch.tensor([layout.numel()], dtype=torch.int64, device=dev)
+    dist.broadcast(n, src)
+    layout = layout[: int(n.item())].contiguous()
+    dist.broadcast(layout, src)
+    if rank != src:
+        engine.adopt_layout([int(v) for v in layout.tolist()], int(arrays.get("nbLamps", 0)), int(arrays["lightInformationSize"]))
+    total = 0
+    for ptr, nbytes in engine.scene_device_arrays():
+        if nbytes == 0:
+            continue
+        t = torch.as_tensor(_DevicePtr(ptr, (nbytes,), "|u1"), device="cuda")
+        if staged:
+            c = t.cpu()
+            dist.broadcast(c, src)
+            if rank != src:
+                t.copy_(c)
+        else:
+            dist.broadcast(t, src)
+        total += nbytes
+    torch.cuda.synchronize()
+    if rank != src:
+        engine.adopt_finish()
+    return total
+
+
 def merge_frames(bitmap, ids=None, dst=0):
     """The one exchange step of the path: sum-reduce the per-rank partial frames onto rank `dst`.
     Works on NCCL (device tensors, NVLink) and gloo (CPU tensors, tests)."""
