@@ -408,6 +408,83 @@ def measure_workload(key, steps, warmup, ctx, sample_clocks=False, want_e2e=True
     return rec
 
 
+def measure_scene_paths(ctx):
+    """The scene side of the path, on config 2, outside every timed region above:
+      N = 1  one animation step of the drop-in host path — rotatePrimitives + compactBoxes(false) (MoleculeScene.cpp:75-81), then a
+             frame, which re-uploads the scene — with the walk trees built on host threads and on the GPU (option key 10);
+      N > 1  scene replication — every rank uploading the scene itself against the root uploading it and the other ranks receiving
+             the device arrays over NCCL (partition.broadcast_scene), max over ranks."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from solr_b200 import engine, host, partition, wire, workloads
+    key = "config2"
+    wl = workloads.WORKLOADS[key]
+    W, H = wl["size"]
+    world, rank, lib = ctx.world, ctx.rank, ctx.lib
+    sc = wl["scene"]()
+    si = workloads.scene_info(key)
+    rnd = np.zeros(max(wire.REF_MAX_BITMAP_SIZE, W * H), np.float32)
+
+    def upload_stats():
+        ms, n0, n1, gpu = C.c_float(), C.c_int(), C.c_int(), C.c_int()
+        lib.b200_scene_upload_stats(C.byref(ms), C.byref(n0), C.byref(n1), C.byref(gpu))
+        return ms.value, n0.value + n1.value, gpu.value
+
+    if world == 1:
+        out = {"workload": wl["name"], "step": "rotatePrimitives + compactBoxes(false) + one frame (scene re-uploaded), 3 steps each"}
+        for name, opt in (("host_built_trees", 0), ("gpu_built_trees", 1)):
+            lib.b200_set_option(10, opt)
+            h = host.SceneHost(si, limits=wl["limits"], rank=0, world=1, device=ctx.local_rank, capacity=wl["capacity"])
+            sc.replay(h)
+            h.set_randoms(rnd, 0)
+            h.set_camera(sc.eye, sc.target, sc.angles)
+            h.init_buffers()
+            h.render_begin(0.0); h.render_end()
+            torch.cuda.synchronize()
+            flat, frame, upl, render = [], [], [], []
+            for k in range(3):
+                t0 = time.perf_counter()
+                h.rotate_primitives((0.0, 0.0, 0.0), (0.0, 0.05, 0.0))
+                h.compact_boxes(False)
+                t1 = time.perf_counter()
+                h.render_begin(0.0); h.render_end()
+                torch.cuda.synchronize()
+                t2 = time.perf_counter()
+                flat.append((t1 - t0) * 1e3); frame.append((t2 - t1) * 1e3)
+                upl.append(upload_stats()[0]); render.append(float(lib.b200_last_render_ms()))
+            out[name] = {"host_box_compaction_ms": round(min(flat), 1), "frame_with_scene_upload_ms": round(min(frame), 1),
+                         "of_which_b200_h2d_scene_ms": round(min(upl), 1), "of_which_render_kernels_ms": round(min(render), 2),
+                         "walk_tree_nodes": upload_stats()[1]}
+            h.close()
+        lib.b200_set_option(10, 0)
+        return out
+
+    # N > 1
+    h = host.SceneHost(si, limits=wl["limits"])
+    sc.replay(h)
+    a = h.arrays()
+    h.close()
+    out = {"workload": wl["name"]}
+    for name in ("every_rank_uploads", "root_uploads_others_receive_over_nccl"):
+        e = engine.Engine(si, device=ctx.local_rank, limits=wl["limits"], rank=rank, world=world)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if name == "every_rank_uploads":
+            e.upload(a, randoms=rnd)
+            received = 0
+        else:
+            mine = a if rank == 0 else dict(a, boxes=np.zeros(0, np.uint8), primitives=np.zeros(0, np.uint8))
+            received = partition.broadcast_scene(e, mine, rank, world, src=0, randoms=rnd)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out[name] = {"ms_max_over_ranks": round(float(dt.item()) * 1e3, 1), "bytes_received_per_rank": int(received)}
+        e.close()
+    return out
+
+
 def parity_against_reference_cuda(key, frame):
     """The engine's frame (iteration 0) against the reference's own CUDA engine on the same GPU.  Checker only: runs after every
     timed region and in a child process — the reference's finalize_scene resets the device (CudaRayTracer.cu:1530), which would
@@ -522,6 +599,10 @@ def main():
             rec.pop("_frame")
             subs[k] = rec
 
+    scene_paths = None
+    if not args.no_sub:
+        scene_paths = measure_scene_paths(ctx)
+
     # FP32 FMA microbenchmark on this GPU (dependent FFMA chains on every resident lane) and the clock it sustains
     fp32 = None
     if rank == 0:
@@ -581,6 +662,8 @@ def main():
                 rec["roofline"] = roofline(k, rec, f * 1e9, "oracle count in reference traversal order on sampled rows, recorded (profiles/algorithmic_flops.json)")
         if subs:
             line["workloads"] = subs
+        if scene_paths:
+            line["scene_paths"] = scene_paths
         emit(line)
     if world > 1:
         dist.destroy_process_group()
