@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_render()
 // Used for the one-ray-tree-per-pixel cameras without box-debug / global-illumination rays; the rest take k_render.
 // ----------------------------------------------------------------------------------------------------
 #define PATH_WORDS 38
-#define QUEUE_COUNTERS (2 * (B200_NB_MAX_ITERATIONS + 2) + 4 * (B200_NB_MAX_ITERATIONS + 1)) // per queue: pushed, handed out; then one hand-out counter per wavefront launch
+#define QUEUE_COUNTERS (2 * (B200_NB_MAX_ITERATIONS + 2) + 4 * (B200_NB_MAX_ITERATIONS + 1) + 2 * (B200_NB_MAX_ITERATIONS + 2)) // per queue: pushed, handed out; one hand-out counter per wavefront launch; per pass: warps at work, entries available (fused driver)
+#define FUSED_CTR (2 * (B200_NB_MAX_ITERATIONS + 2) + 4 * (B200_NB_MAX_ITERATIONS + 1))
 SB_DEV void storePath(const size_t slot, const PathState& s, const int index)
 {
     float* w = cP.pathWords + slot;
@@ -419,8 +420,8 @@ SB_DEV void loadPath(const size_t slot, PathState& s, int& index)
     const float* w = cP.pathWords + slot;
     const size_t n = cP.pathStride;
     int k = 0;
-#define GET() w[(size_t)(k++) * n]
-#define GETI() __float_as_int(w[(size_t)(k++) * n])
+#define GET() __ldcg(w + (size_t)(k++) * n) // past L1: see GlobalColors
+#define GETI() __float_as_int(__ldcg(w + (size_t)(k++) * n))
     s.curO.x = GET(); s.curO.y = GET(); s.curO.z = GET(); s.curT.x = GET(); s.curT.y = GET(); s.curT.z = GET();
     s.initialRefraction = GET(); s.currentMaterialId = GETI();
     s.closestColor.x = GET(); s.closestColor.y = GET(); s.closestColor.z = GET(); s.closestColor.w = GET();
@@ -440,7 +441,9 @@ SB_DEV void loadPath(const size_t slot, PathState& s, int& index)
     s.colorBox = f4(0.f, 0.f, 0.f, 0.f);
 }
 
-// warp-aggregated push of the lanes with `want` onto queue q
+// warp-aggregated push of the lanes with `want` onto queue q.  The fused driver's consumers run in the same launch: there an entry is
+// slot + 1 written into a queue that was zeroed before the frame, AFTER a device-wide fence behind everything the lane stored for
+// the path (storePath), so whoever finds the entry non-zero finds the parked path too; the launch-per-pass drivers store the slot.
 SB_DEV void pushPaths(const int q, const bool want, const size_t slot)
 {
     const unsigned int m = __ballot_sync(FULL_MASK, want);
@@ -449,6 +452,14 @@ SB_DEV void pushPaths(const int q, const bool want, const size_t slot)
     unsigned int base = 0;
     if (lane == __ffs(m) - 1) base = atomicAdd(cP.queueCounters + 2 * q, (unsigned int)__popc(m));
     base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
+    if (cP.fusedQueues)
+    {
+        __threadfence();
+        if (want) __stcg(cP.pathQueues + (size_t)q * cP.pathStride + base + __popc(m & ((1u << lane) - 1u)), (int)slot + 1);
+        // the consumers' semaphore (a consumer that is handed an entry before it is written waits for it to turn non-zero)
+        if (lane == __ffs(m) - 1) atomicAdd(cP.queueCounters + FUSED_CTR + (B200_NB_MAX_ITERATIONS + 2) + q, (unsigned int)__popc(m));
+        return;
+    }
     if (want) cP.pathQueues[(size_t)q * cP.pathStride + base + __popc(m & ((1u << lane) - 1u))] = (int)slot;
 }
 
@@ -615,6 +626,183 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
         __syncwarp();
     }
     flushCounters(cnt.rays, 0);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Fused stages (b200_set_option(6, 3)): the staged kernels as ONE persistent launch per frame.  A launch per pass ends with a tail
+// — the pass is as long as its slowest warp while the next pass's paths sit in their queue — and a frame of p passes pays p tails:
+// a tenth of a 1080p frame on one GPU, a third of a 1/8 share of it (8 GPUs), and ten tails per 4K frame of config 4.  Here a warp
+// that runs out of work of one pass takes work of another:
+//   1. 32 entries of the DEEPEST pass queue that has that many (depth first keeps the parked paths short-lived);
+//   2. else a tile of primary rays (pass 0);
+//   3. else the remainder (< 32 entries) of a queue that can get no more entries — every earlier pass is done;
+//   4. else it sleeps a little and looks again, until the last pass is done.
+// "Pass p is done" = its queue is closed (pass p - 1 is done; the tile queue is closed from the start), every entry is claimed, and
+// no warp is at work on it (counter raised BEFORE a claim, lowered after the warp's pushes are reserved).  Compaction stays what it
+// was: batches are full except one per pass.  Entries and parked paths cross SMs inside the launch: a producer fences and then writes
+// slot + 1 into its reserved places of a zeroed queue, a consumer waits for its entry to turn non-zero and reads the path past L1
+// (loadPath, GlobalColors).
+// Same device functions, same rays, same results as the launch-per-pass drivers; one-ray-tree-per-pixel cameras with the
+// order-independent walks only (the others keep the launches).
+// ----------------------------------------------------------------------------------------------------
+SB_DEV unsigned int ctrLoad(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
+
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_fused()
+{
+    const int lane = threadIdx.x & 31;
+    framePrologue(true);
+    Counters cnt;
+    cnt.rays = 0;
+    unsigned int pixelsTraced = 0;
+    Rotation rot;
+    rot.cx = cosf(cP.angles.x); rot.cy = cosf(cP.angles.y); rot.cz = cosf(cP.angles.z);
+    rot.sx = sinf(cP.angles.x); rot.sy = sinf(cP.angles.y); rot.sz = sinf(cP.angles.z);
+    const int maxIt = cP.maxIteration;
+    unsigned int* const Q = cP.queueCounters;
+    unsigned int* const atWork = Q + FUSED_CTR;
+    unsigned int* const avail = Q + FUSED_CTR + (B200_NB_MAX_ITERATIONS + 2);
+    bool tilesLeft = true;
+    while (true)
+    {
+        // ---- what to do next (lane 0 decides)
+        int pass = -2;            // -2: nothing right now, -3: the frame is done, 0: a tile, >= 1: a batch of that pass
+        unsigned int base = 0, n = 0;
+        if (lane == 0)
+        {
+            // 1. a full batch, deepest pass first.  avail[p] is a semaphore (entries reserved by producers minus entries taken):
+            //    take 32 and give them back if there were not that many — no retry loops on a contended counter
+            for (int p = maxIt - 1; p >= 1 && pass == -2; --p)
+            {
+                if ((int)ctrLoad(avail + p) < 32) continue;
+                atomicAdd(atWork + p, 1u);
+                if ((int)atomicSub(avail + p, 32u) >= 32) { pass = p; n = 32u; base = atomicAdd(Q + 2 * p + 1, 32u); }
+                else { atomicAdd(avail + p, 32u); atomicSub(atWork + p, 1u); }
+            }
+            // 2. a tile
+            if (pass == -2 && tilesLeft)
+            {
+                atomicAdd(atWork, 1u);
+                const unsigned int k = atomicAdd(cP.tileCounter, 1u);
+                if (k < (unsigned int)cP.nbLocalTiles) { pass = 0; base = k; }
+                else { atomicSub(atWork, 1u); tilesLeft = false; }
+            }
+            // 2b. nothing full and no tile: rather than idle until a queue closes, a partial batch of the shallowest queue that has
+            //     FUSED_MIN_PARTIAL entries (the idle warp costs nothing, and what it produces lets the deeper queues fill earlier)
+#ifndef FUSED_MIN_PARTIAL
+#define FUSED_MIN_PARTIAL 1
+#endif
+            for (int p = 1; p < maxIt && pass == -2 && FUSED_MIN_PARTIAL < 32; ++p)
+            {
+                if ((int)ctrLoad(avail + p) < FUSED_MIN_PARTIAL) continue;
+                atomicAdd(atWork + p, 1u);
+                const int had = (int)atomicSub(avail + p, 32u);
+                if (had >= FUSED_MIN_PARTIAL)
+                {
+                    const unsigned int take = had < 32 ? (unsigned int)had : 32u;
+                    if (take < 32u) atomicAdd(avail + p, 32u - take);
+                    pass = p; n = take; base = atomicAdd(Q + 2 * p + 1, take);
+                }
+                else { atomicAdd(avail + p, 32u); atomicSub(atWork + p, 1u); }
+            }
+            // 3. / 4. remainders of closed queues, or the end
+            if (pass == -2)
+            {
+                bool closed = ctrLoad(cP.tileCounter) >= (unsigned int)cP.nbLocalTiles && ctrLoad(atWork) == 0u; // pass 0 done
+                for (int p = 1; p < maxIt && closed; ++p)
+                {
+                    __threadfence();
+                    // queue p is closed: what is reserved is all there will be
+                    if ((int)ctrLoad(avail + p) > 0)
+                    {
+                        atomicAdd(atWork + p, 1u);
+                        const int had = (int)atomicSub(avail + p, 32u);
+                        if (had > 0)
+                        {
+                            const unsigned int take = had < 32 ? (unsigned int)had : 32u;
+                            if (take < 32u) atomicAdd(avail + p, 32u - take);
+                            pass = p; n = take; base = atomicAdd(Q + 2 * p + 1, take);
+                        }
+                        else { atomicAdd(avail + p, 32u); atomicSub(atWork + p, 1u); }
+                        closed = false; // taken, or somebody else was faster: look again next time
+                        break;
+                    }
+                    closed = ctrLoad(Q + 2 * p + 1) == ctrLoad(Q + 2 * p) && ctrLoad(atWork + p) == 0u; // pass p done?
+                }
+                if (pass == -2 && closed) pass = -3;
+            }
+        }
+        pass = __shfl_sync(FULL_MASK, pass, 0);
+        if (pass == -3) break;
+        if (pass == -2) { __nanosleep(1000); continue; }
+        base = __shfl_sync(FULL_MASK, base, 0);
+        n = __shfl_sync(FULL_MASK, n, 0);
+        tilesLeft = __shfl_sync(FULL_MASK, tilesLeft ? 1 : 0, 0) != 0;
+
+        // ---- one batch: 32 pixels of a tile (pass 0) or up to 32 parked paths (pass >= 1)
+        bool has;
+        size_t slot;
+        int tag = 0;
+        float3 rayO = f3(0.f, 0.f, 0.f), o = f3(0.f, 0.f, 0.f), t = f3(0.f, 0.f, 0.f);
+        int material = -2;
+        if (pass == 0)
+        {
+            const unsigned int k = base;
+            const int tile = cP.tileOrder ? cP.tileOrder[k] : k * cP.worldSize + cP.rank;
+            const int tx = tile % cP.tilesX, ty = tile / cP.tilesX;
+            const int xIn = tx * TILE_W + (lane & (TILE_W - 1));
+            const int yIn = ty * TILE_H + (lane / TILE_W);
+            const bool inFrame = xIn < cSI.size.x && yIn < cSI.size.y;
+            const int x = inFrame ? xIn : 0, y = inFrame ? yIn : 0;
+            const int index = y * cSI.size.x + x;
+            has = inFrame && pixelNeedsWork(cP.ids[index]);
+            if (has) pixelsTraced++;
+            primaryRay(rot, x, y, index, cP.post[index].colorInfo.w, o, t);
+            rayO = o;
+            slot = (size_t)k * 32 + lane;
+            tag = index;
+        }
+        else
+        {
+            has = (unsigned int)lane < n;
+            slot = 0;
+            if (has)
+            {
+                // the entry is reserved; its producer writes it right after its fence
+                const volatile int* entry = cP.pathQueues + (size_t)passQueue(pass) * cP.pathStride + base + lane;
+                int e;
+                while ((e = *entry) == 0) __nanosleep(20);
+                __threadfence();
+                slot = (size_t)(e - 1);
+                const float* w = cP.pathWords + slot;
+                const size_t s = cP.pathStride;
+                o = f3(__ldcg(w), __ldcg(w + s), __ldcg(w + 2 * s)); t = f3(__ldcg(w + 3 * s), __ldcg(w + 4 * s), __ldcg(w + 5 * s));
+                material = __float_as_int(__ldcg(w + 7 * s));
+            }
+        }
+        if (__any_sync(FULL_MASK, has))
+        {
+            // the walk first, with only the ray live (k_stage_pass has the why)
+            Hit hit;
+            hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
+            if (has) hit = closestHitOrderIndependent(o, t, pass, material);
+            PathState s;
+            if (pass == 0) pathInit(s, o, t);
+            else
+            {
+                loadPath(slot, s, tag);
+                if (!has) tag = 0;
+            }
+            const int index = tag & ((1 << PATH_EYE_BIT) - 1);
+            GlobalColors C;
+            C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
+            pathPass(s, C, pass, has, index, rayO, 0, cnt, &hit);
+            routePath(has, s, C, pass, slot, tag);
+        }
+        __syncwarp();
+        // this warp's pushes are reserved (pushPaths): it is no longer at work on the pass
+        if (lane == 0) { __threadfence(); atomicSub(atWork + pass, 1u); }
+    }
+    flushCounters(cnt.rays, pixelsTraced);
 }
 
 #ifdef WITH_WAVE_WALK
@@ -789,7 +977,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) break;
         const bool has = base + lane < count;
-        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)q * cP.pathStride + base + lane] : 0;
+        const size_t slot = has ? (size_t)(cP.pathQueues[(size_t)q * cP.pathStride + base + lane] - cP.fusedQueues) : 0;
         PathState s;
         int tag = 0;
         loadPath(slot, s, tag);
@@ -1053,7 +1241,7 @@ struct Engine
     unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
     float* dWaveWords = nullptr; size_t waveStride = 0; // wavefront stages: hitWords + shadowWords, [HIT_WORDS + SHADOW_WORDS][waveStride]
     size_t pathFailedBytes = 0; // smallest path-state size that did not fit (not tried again)
-    int ctasPerSMStage[5] = {0, 0, 0, 0, 0}; // k_stage_primary, k_stage_pass, k_stage_reflected, k_wave_walk, k_wave_shade
+    int ctasPerSMStage[6] = {0, 0, 0, 0, 0, 0}; // k_stage_primary, k_stage_pass, k_stage_reflected, k_wave_walk, k_wave_shade, k_stage_fused
     float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
     b200_BoundingBox* dRawBoxes = nullptr;
     b200_Material* dMats = nullptr; int nbMats = 0;
@@ -1645,7 +1833,7 @@ void b200_set_option(int key, int value)
     else if (key == 4) g_useUnordered = value != 0;
     else if (key == 5) g_useBackward = value != 0;
     else if (key == 10 && (value == 0 || value == 1)) g_gpuTrees = value;
-    else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value; // 2: wavefront stages (k_wave_*)
+    else if (key == 6 && value >= 0 && value <= 3) g_useStaged = value; // 2: wavefront stages (k_wave_*)
     else if (key == 8 && value >= 0) g_fuseTailPercent = value;
     else if (key == 9 && (value == 0 || value == 1)) g_tileOrder = value;
     else latch(-11, "b200_set_option", "unknown option");
@@ -1718,6 +1906,7 @@ void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_primary, CTA_THREADS, 0)); G.ctasPerSMStage[0] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_pass, CTA_THREADS, 0)); G.ctasPerSMStage[1] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_reflected, CTA_THREADS, 0)); G.ctasPerSMStage[2] = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_fused, CTA_THREADS, 0)); G.ctasPerSMStage[5] = perSM > 0 ? perSM : 1;
 #ifdef WITH_WAVE_WALK
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_wave_walk, CTA_THREADS, 0)); G.ctasPerSMStage[3] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_wave_shade, CTA_THREADS, 0)); G.ctasPerSMStage[4] = perSM > 0 ? perSM : 1;
@@ -2435,8 +2624,12 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     }
 #endif
 
+    const bool fused = staged && !wave && g_useStaged == 3 && P.scene.nbUWide > 0 && eyes == 1 && P.packetMask == 0 && !UW_GROUP;
+    P.fusedQueues = fused ? 1 : 0;
     CK(cudaEventRecord(G.evStart, G.stream));
     CK(cudaMemsetAsync(G.dTileCounter, 0, sizeof(unsigned int), G.stream));
+    // the fused driver's consumers recognise a written entry by its being non-zero
+    if (fused) CK(cudaMemsetAsync(G.dPathQueues, 0, ((size_t)maxIteration + 1) * G.pathStride * sizeof(int), G.stream));
     const int warpsPerCta = CTA_THREADS / 32;
     int grid = G.numSMs * G.ctasPerSM;
     const int needed = (P.nbLocalTiles + warpsPerCta - 1) / warpsPerCta;
@@ -2469,6 +2662,14 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         }
         else
 #endif
+        if (fused)
+        {
+            // persistent: every CTA must be resident, or a sleeping warp could wait for one that never starts
+            k_stage_fused<<<G.numSMs * G.ctasPerSMStage[5], CTA_THREADS, 0, G.stream>>>();
+            k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
+            G.launches += 2;
+        }
+        else
         {
             int g0 = G.numSMs * G.ctasPerSMStage[0];
             if (g0 > needed) g0 = needed > 0 ? needed : 1;

@@ -610,8 +610,9 @@ struct GlobalColors
     float4* c;
     float* k;
     size_t slot, stride;
-    SB_DEV float4 color(const int i) const { return c[(size_t)i * stride + slot]; }
-    SB_DEV float contribution(const int i) const { return k[(size_t)i * stride + slot]; }
+    // read past L1 (ld.global.cg): in the fused driver the pass that wrote them may have run on another SM during this same launch
+    SB_DEV float4 color(const int i) const { return __ldcg(c + (size_t)i * stride + slot); }
+    SB_DEV float contribution(const int i) const { return __ldcg(k + (size_t)i * stride + slot); }
     SB_DEV void setColor(const int i, const float4 v) { c[(size_t)i * stride + slot] = v; }
     SB_DEV void setContribution(const int i, const float v) { k[(size_t)i * stride + slot] = v; }
 };

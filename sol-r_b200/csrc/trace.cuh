@@ -93,6 +93,7 @@ struct RenderParams
     size_t pathStride;
     size_t eyeStride;          // anaglyph: slots of the right eye's paths start here (two paths per pixel)
     int maxIteration;
+    int fusedQueues;           // 1: queue entries are slot + 1 in zeroed queues, published behind a fence (engine.cu k_stage_fused)
     float4* gatherScratch; // group / wavefront walks: candidate lists of the bounce rays while they are walked
     float* hitWords;       // wavefront stages (engine.cu k_wave_*): [HIT_WORDS][pathStride] closest hit of the current pass
     float* shadowWords;    // [SHADOW_WORDS][pathStride] shadow ray of the current pass and its result

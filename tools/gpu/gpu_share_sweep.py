@@ -13,10 +13,10 @@ for key in sys.argv[1:] or ["config4"]:
     sc = wl["scene"]()
     h = host.SceneHost(si, limits=wl["limits"], capacity=wl["capacity"]); sc.replay(h); a = h.arrays(); h.close()
     for world in (1, 8):
-        for o8, o9 in ((300, 0), (0, 0), (100, 0), (600, 0), (1200, 0), (5000, 0), (300, 1)):
+        for o8, o9 in ((300, 0),) if os.environ.get('SOLR_MODE') else ((300, 0), (0, 0), (100, 0), (600, 0), (1200, 0), (5000, 0), (300, 1)):
             if world == 1 and (o8, o9) != (300, 0): continue
             e = engine.Engine(si, limits=wl["limits"], rank=0, world=world)
-            e.set_option(8, o8); e.set_option(9, o9)
+            e.set_option(8, o8); e.set_option(9, o9); e.set_option(6, int(os.environ.get('SOLR_MODE', '1')))
             e.upload(a, randoms=np.zeros(max(W * H, 1920 * 1080), np.float32))
             per = {}
             for rep in range(3):
@@ -26,4 +26,4 @@ for key in sys.argv[1:] or ["config4"]:
                     per.setdefault(it, []).append(e.last_render_ms())
             ms = {it: min(v[1:]) for it, v in per.items()}
             print("%s share 1/%d option8 %5d option9 %d  mean %.3f ms  %s" % (key, world, o8, o9, sum(ms.values()) / len(ms), {k: round(v, 3) for k, v in ms.items()}), flush=True)
-            e.set_option(8, 300); e.set_option(9, 0); e.close()
+            e.set_option(8, 300); e.set_option(9, 0); e.set_option(6, 1); e.close()
