@@ -77,8 +77,8 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
  *         (GeometryIntersections.cuh:316-325) (1, default); 0 drops them (not reference-exact; for measurement).
  * key 6 = staged rendering: one launch per bounce pass over a compacted queue of the paths still alive (1, default, used for
  *         the one-ray-tree-per-pixel cameras and the anaglyph camera), the single persistent kernel for every camera (0), or
- *         wavefront stages (2: every step of a pass its own launch, the walks in a kernel of their own whose lanes take rays
- *         from the pass's queue one at a time; sol-r_b200/csrc/tracewave.cuh; exact, measured slower).
+ *         fused stages (2: every pass of the frame in ONE persistent launch, a warp that runs out of work of one pass taking
+ *         work of another; exact, measured 5 % slower on one GPU — engine.cu k_stage_fused, profiles/r02_history.md).
  * key 8 = bounce pass p whose queue holds at most p times this percentage of the GPU's resident lanes carries its paths to the
  *         end of their ray trees in registers instead of queueing them for one more launch per pass (default 300; 0 = never).
  * key 9 = order in which a GPU's own tiles are handed to its warps: 0 row-major (default), 1 along a Z-order curve.

@@ -390,8 +390,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_render()
 // Used for the one-ray-tree-per-pixel cameras without box-debug / global-illumination rays; the rest take k_render.
 // ----------------------------------------------------------------------------------------------------
 #define PATH_WORDS 38
-#define QUEUE_COUNTERS (2 * (B200_NB_MAX_ITERATIONS + 2) + 4 * (B200_NB_MAX_ITERATIONS + 1) + 2 * (B200_NB_MAX_ITERATIONS + 2)) // per queue: pushed, handed out; one hand-out counter per wavefront launch; per pass: warps at work, entries available (fused driver)
-#define FUSED_CTR (2 * (B200_NB_MAX_ITERATIONS + 2) + 4 * (B200_NB_MAX_ITERATIONS + 1))
+#define QUEUE_COUNTERS (4 * (B200_NB_MAX_ITERATIONS + 2)) // per queue: pushed, handed out; per pass: warps at work, entries available (fused driver)
+#define FUSED_CTR (2 * (B200_NB_MAX_ITERATIONS + 2))
 SB_DEV void storePath(const size_t slot, const PathState& s, const int index)
 {
     float* w = cP.pathWords + slot;
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Fused stages (b200_set_option(6, 3)): the staged kernels as ONE persistent launch per frame.  A launch per pass ends with a tail
+// Fused stages (b200_set_option(6, 2)): the staged kernels as ONE persistent launch per frame.  A launch per pass ends with a tail
 // — the pass is as long as its slowest warp while the next pass's paths sit in their queue — and a frame of p passes pays p tails:
 // a tenth of a 1080p frame on one GPU, a third of a 1/8 share of it (8 GPUs), and ten tails per 4K frame of config 4.  Here a warp
 // that runs out of work of one pass takes work of another:
@@ -805,161 +805,6 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_fused()
     flushCounters(cnt.rays, pixelsTraced);
 }
 
-#ifdef WITH_WAVE_WALK
-// ----------------------------------------------------------------------------------------------------
-// Wavefront stages (b200_set_option(6, 2)): every step of a pass is its own launch over the pass's queue, and the walks are
-// kernels that contain nothing but the walk (tracewave.cuh):
-//   k_wave_gen                     primary rays of the pixels that need work -> pathWords, queue 0
-//   per pass p:  k_wave_walk(closest)   the rays of queue p; lanes take rays from the queue one at a time, so a warp never waits
-//                                       for the longest of 32 walks; results -> hitWords
-//                k_wave_shade(probe)    per path: the pass shaded once to learn its shadow ray (ShadowHook PROBE, result thrown
-//                                       away) -> shadowWords, shadow queue
-//                k_wave_walk(shadow)    the shadow rays, the same way
-//                k_wave_shade(final)    the pass for good with hit and shadow handed in -> routePath (next queue / pixel)
-//   k_stage_reflected              as in the staged driver
-// Why separate launches and not one kernel per pass: a kernel whose warps sit in the walk, in the shader and in the hand-over at
-// the same time misses its instruction caches on every other fetch (tracewave.cuh has the numbers); here every launch runs one
-// piece of code on every warp.  Shading twice costs arithmetic at full warps.  Rays, hits and shadow requests cross launches
-// through L2 (about 100 bytes per path and pass).  Same device functions, same rays, same results as the other drivers.
-// ----------------------------------------------------------------------------------------------------
-#define WAVE_CTR (2 * (B200_NB_MAX_ITERATIONS + 2)) // queueCounters: hand-out counters of the wavefront launches start here
-#define WAVE_CTRS (4 * (B200_NB_MAX_ITERATIONS + 1))
-SB_DEV int shadowQueue() { return cP.maxIteration + 1; }
-
-// pixel of a pass-0 path slot (slot = local tile number * 32 + lane)
-SB_DEV bool slotPixel(const size_t slot, int& x, int& y, int& index)
-{
-    const unsigned int kt = (unsigned int)(slot >> 5);
-    const int lane = (int)(slot & 31);
-    const int tile = cP.tileOrder ? cP.tileOrder[kt] : kt * cP.worldSize + cP.rank;
-    const int tx = tile % cP.tilesX, ty = tile / cP.tilesX;
-    x = tx * TILE_W + (lane & (TILE_W - 1));
-    y = ty * TILE_H + (lane / TILE_W);
-    const bool inFrame = x < cSI.size.x && y < cSI.size.y;
-    if (!inFrame) { x = 0; y = 0; }
-    index = y * cSI.size.x + x;
-    return inFrame;
-}
-
-__global__ void __launch_bounds__(CTA_THREADS, 8) k_wave_gen()
-{
-    const int lane = threadIdx.x & 31;
-    unsigned int pixelsTraced = 0;
-    Rotation rot;
-    rot.cx = cosf(cP.angles.x); rot.cy = cosf(cP.angles.y); rot.cz = cosf(cP.angles.z);
-    rot.sx = sinf(cP.angles.x); rot.sy = sinf(cP.angles.y); rot.sz = sinf(cP.angles.z);
-    const int warpsTotal = gridDim.x * (CTA_THREADS / 32);
-    for (int kt = blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5); kt < cP.nbLocalTiles; kt += warpsTotal)
-    {
-        const size_t slot = (size_t)kt * 32 + lane;
-        int x, y, index;
-        const bool inFrame = slotPixel(slot, x, y, index);
-        const bool valid = inFrame && pixelNeedsWork(cP.ids[index]);
-        if (valid)
-        {
-            pixelsTraced++;
-            float3 o, t;
-            primaryRay(rot, x, y, index, cP.post[index].colorInfo.w, o, t);
-            float* w = cP.pathWords + slot;
-            const size_t n = cP.pathStride;
-            w[0] = o.x; w[n] = o.y; w[2 * n] = o.z; w[3 * n] = t.x; w[4 * n] = t.y; w[5 * n] = t.z;
-            w[7 * n] = __int_as_float(-2); // pathInit's currentMaterialId
-        }
-        pushPaths(passQueue(0), valid, slot);
-    }
-    flushCounters(0, pixelsTraced);
-}
-
-#ifndef MIN_CTAS_WALK
-#define MIN_CTAS_WALK 6
-#endif
-__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_WALK) k_wave_walk(const int kind, const int pass, const int ctr)
-{
-    waveWalk(kind, pass, kind == WAVE_SHADOW ? shadowQueue() : passQueue(pass), cP.queueCounters + WAVE_CTR + ctr);
-}
-
-// phase SHADOW_HOOK_PROBE: shadow request of the pass;  SHADOW_HOOK_GIVEN: the pass for good
-__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_wave_shade(const int pass, const int phase, const int ctr)
-{
-    const int lane = threadIdx.x & 31;
-    Counters cnt;
-    cnt.rays = 0;
-    const int q = passQueue(pass);
-    const unsigned int count = cP.queueCounters[2 * q];
-    const size_t stride = cP.pathStride;
-    // the shadow queue of this pass has been walked: empty it for the next pass (nobody reads it during this launch)
-    if (phase == SHADOW_HOOK_GIVEN && blockIdx.x == 0 && threadIdx.x == 0) cP.queueCounters[2 * shadowQueue()] = 0u;
-    Rotation rot;
-    rot.cx = cosf(cP.angles.x); rot.cy = cosf(cP.angles.y); rot.cz = cosf(cP.angles.z);
-    rot.sx = sinf(cP.angles.x); rot.sy = sinf(cP.angles.y); rot.sz = sinf(cP.angles.z);
-    while (true)
-    {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(cP.queueCounters + WAVE_CTR + ctr, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        const bool has = base + lane < count;
-        const size_t slot = has ? (size_t)cP.pathQueues[(size_t)q * stride + base + lane] : 0;
-        PathState s;
-        int tag = 0;
-        float3 rayO = f3(0.f, 0.f, 0.f);
-        if (pass == 0)
-        {
-            // a pass-0 path is its pixel: nothing was parked
-            int x, y, index;
-            slotPixel(slot, x, y, index);
-            float3 o, t;
-            primaryRay(rot, x, y, index, cP.post[index].colorInfo.w, o, t);
-            pathInit(s, o, t);
-            rayO = o;
-            tag = index;
-        }
-        else
-        {
-            loadPath(slot, s, tag);
-            if (!has) tag = 0;
-        }
-        const int index = tag & ((1 << PATH_EYE_BIT) - 1);
-        GlobalColors C;
-        C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = stride;
-        Hit hit;
-        hit.prim = -1; hit.p = f3(0.f, 0.f, 0.f); hit.flags = 0;
-        if (has)
-        {
-            float* hw = cP.hitWords + slot;
-            hit.prim = __float_as_int(hw[0]); hit.p = f3(hw[stride], hw[2 * stride], hw[3 * stride]); hit.flags = __float_as_int(hw[4 * stride]);
-            if (hit.prim == WAVE_OVERFLOW)
-            {
-                // the walk gave up (candidate list or stack full): the ordered walk, once; the final run finds its result
-                hit = closestHitWide(s.curO, s.curT, pass, s.currentMaterialId);
-                hw[0] = __int_as_float(hit.prim); hw[stride] = hit.p.x; hw[2 * stride] = hit.p.y; hw[3 * stride] = hit.p.z;
-                hw[4 * stride] = __int_as_float(hit.flags);
-            }
-        }
-        ShadowHook hook;
-        hook.mode = phase; hook.seen = false; hook.need = false; hook.value = 0.f;
-        hook.o = hook.d = f3(0.f, 0.f, 0.f); hook.lightId = 0; hook.objectId = 0;
-        if (phase == SHADOW_HOOK_GIVEN && has) hook.value = cP.shadowWords[8 * stride + slot];
-        pathPass(s, C, pass, has, index, rayO, 0, cnt, &hit, &hook);
-        if (phase == SHADOW_HOOK_PROBE)
-        {
-            const bool want = has && hook.seen && hook.need;
-            if (want)
-            {
-                float* w = cP.shadowWords + slot;
-                w[0] = hook.o.x; w[stride] = hook.o.y; w[2 * stride] = hook.o.z;
-                w[3 * stride] = hook.d.x; w[4 * stride] = hook.d.y; w[5 * stride] = hook.d.z;
-                w[6 * stride] = __int_as_float(hook.lightId); w[7 * stride] = __int_as_float(hook.objectId);
-            }
-            pushPaths(shadowQueue(), want, slot);
-        }
-        else
-            routePath(has, s, C, pass, slot, tag);
-        __syncwarp();
-    }
-    if (phase == SHADOW_HOOK_GIVEN) flushCounters(cnt.rays, 0);
-}
-#endif
 
 
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflected()
@@ -1239,9 +1084,8 @@ struct Engine
     size_t nWideF4 = 0, nLeafRecsF4 = 0;      // float4 in dWide / dLeafRecs (scene replication)
     float4* dLeafBoxes = nullptr; size_t capLeafBoxes = 0; // boxes of the reference leaves, for the GPU tree build
     unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
-    float* dWaveWords = nullptr; size_t waveStride = 0; // wavefront stages: hitWords + shadowWords, [HIT_WORDS + SHADOW_WORDS][waveStride]
     size_t pathFailedBytes = 0; // smallest path-state size that did not fit (not tried again)
-    int ctasPerSMStage[6] = {0, 0, 0, 0, 0, 0}; // k_stage_primary, k_stage_pass, k_stage_reflected, k_wave_walk, k_wave_shade, k_stage_fused
+    int ctasPerSMStage[6] = {0, 0, 0, 0, 0, 0}; // k_stage_primary, k_stage_pass, k_stage_reflected, -, -, k_stage_fused
     float4* dGeo = nullptr; int* dMeta = nullptr; b200_Primitive* dPrims = nullptr; int nbPrims = 0;
     b200_BoundingBox* dRawBoxes = nullptr;
     b200_Material* dMats = nullptr; int nbMats = 0;
@@ -1776,7 +1620,7 @@ int g_useWide = 1;
 int g_useUnordered = 1;
 int g_tileOrder = 0; // order in which a GPU's own tiles are handed out: 0 row-major, 1 along a Z-order curve (neighbouring warps work on neighbouring tiles in both directions)
 int g_fuseTailPercent = 300; // k_stage_pass(p) carries its paths to the end in registers when the queue holds at most p times this share of the resident lanes (0: never)
-int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: the same with pooled walks
+int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: every pass in one persistent launch
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
 int g_gpuTrees = 0; // 1: the trees of the order-independent walks are built on the GPU (treebuild.cuh) instead of on host threads
@@ -1833,7 +1677,7 @@ void b200_set_option(int key, int value)
     else if (key == 4) g_useUnordered = value != 0;
     else if (key == 5) g_useBackward = value != 0;
     else if (key == 10 && (value == 0 || value == 1)) g_gpuTrees = value;
-    else if (key == 6 && value >= 0 && value <= 3) g_useStaged = value; // 2: wavefront stages (k_wave_*)
+    else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value; // 2: fused stages (k_stage_fused)
     else if (key == 8 && value >= 0) g_fuseTailPercent = value;
     else if (key == 9 && (value == 0 || value == 1)) g_tileOrder = value;
     else latch(-11, "b200_set_option", "unknown option");
@@ -1907,10 +1751,6 @@ void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_pass, CTA_THREADS, 0)); G.ctasPerSMStage[1] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_reflected, CTA_THREADS, 0)); G.ctasPerSMStage[2] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_fused, CTA_THREADS, 0)); G.ctasPerSMStage[5] = perSM > 0 ? perSM : 1;
-#ifdef WITH_WAVE_WALK
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_wave_walk, CTA_THREADS, 0)); G.ctasPerSMStage[3] = perSM > 0 ? perSM : 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_wave_shade, CTA_THREADS, 0)); G.ctasPerSMStage[4] = perSM > 0 ? perSM : 1;
-#endif
     G.initialised = true;
     G.launches = 0;
 }
@@ -1928,7 +1768,7 @@ void b200_finalize_scene(b200_int2)
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
     freeDev(G.dTileCounter); freeDev(G.dWork); freeDev(G.dTileOrder); G.capTileOrder = 0; G.tileOrderKey[0] = 0;
-    freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters); freeDev(G.dWaveWords); G.waveStride = 0;
+    freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters);
     G.pathStride = 0; G.pathIterations = 0;
     if (G.evStart) { cudaEventDestroy(G.evStart); G.evStart = nullptr; }
     if (G.evStop) { cudaEventDestroy(G.evStop); G.evStop = nullptr; }
@@ -2505,15 +2345,11 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.scene.uwnodes = G.dUWide; P.scene.nbUWide = (g_useWide && g_useUnordered) ? G.nbUWide : 0; P.scene.opaqueShadows = G.opaqueShadows;
     P.scene.nbUX = g_useBackward ? G.nbUX : 0;
     P.scene.ugnodes = G.dUGroup;
-#if UW_GROUP || defined(WITH_WAVE_WALK)
-    if (P.scene.nbUWide > 0 && (UW_GROUP || g_useStaged == 2))
-    {
-        // candidate lists of the bounce rays of the group / wavefront walks: one per lane (group walk: per ray slot of every warp) a launch can hold
 #if UW_GROUP
+    if (P.scene.nbUWide > 0)
+    {
+        // candidate lists of the bounce rays of the group walk: one per ray slot of every warp a launch can hold
         const size_t want = (size_t)G.numSMs * 16 * (CTA_THREADS / 32) * 32 * GW_GATHER_CAP;
-#else
-        const size_t want = (size_t)G.numSMs * (size_t)G.ctasPerSMStage[3] * CTA_THREADS * WAVE_GATHER_CAP;
-#endif
         if (want > G.capGatherScratch)
         {
             CK(cudaStreamSynchronize(G.stream));
@@ -2603,28 +2439,8 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         P.queueCounters = G.dQueueCounters; P.pathStride = G.pathStride; P.maxIteration = maxIteration;
         P.eyeStride = (((size_t)P.nbLocalTiles * 32) + 63) & ~(size_t)63;
     }
-    bool wave = false;
-#ifdef WITH_WAVE_WALK
-    wave = staged && g_useStaged == 2 && P.scene.nbUWide > 0 && eyes == 1;
-    if (wave)
-    {
-        if (G.waveStride < G.pathStride)
-        {
-            CK(cudaStreamSynchronize(G.stream));
-            freeDev(G.dWaveWords);
-            G.waveStride = 0;
-            if (cudaMalloc(&G.dWaveWords, (size_t)(HIT_WORDS + SHADOW_WORDS) * G.pathStride * sizeof(float)) == cudaSuccess) G.waveStride = G.pathStride;
-            else { cudaGetLastError(); wave = false; }
-        }
-        if (wave)
-        {
-            P.hitWords = G.dWaveWords;
-            P.shadowWords = G.dWaveWords + (size_t)HIT_WORDS * G.pathStride;
-        }
-    }
-#endif
 
-    const bool fused = staged && !wave && g_useStaged == 3 && P.scene.nbUWide > 0 && eyes == 1 && P.packetMask == 0 && !UW_GROUP;
+    const bool fused = staged && g_useStaged == 2 && P.scene.nbUWide > 0 && eyes == 1 && P.packetMask == 0 && !UW_GROUP;
     P.fusedQueues = fused ? 1 : 0;
     CK(cudaEventRecord(G.evStart, G.stream));
     CK(cudaMemsetAsync(G.dTileCounter, 0, sizeof(unsigned int), G.stream));
@@ -2643,25 +2459,6 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     else
     {
         CK(cudaMemsetAsync(G.dQueueCounters, 0, QUEUE_COUNTERS * sizeof(unsigned int), G.stream));
-#ifdef WITH_WAVE_WALK
-        if (wave)
-        {
-            int gg = G.numSMs * 8;
-            if (gg > needed) gg = needed > 0 ? needed : 1;
-            k_wave_gen<<<gg, CTA_THREADS, 0, G.stream>>>();
-            const int gw = G.numSMs * G.ctasPerSMStage[3], gs = G.numSMs * G.ctasPerSMStage[4];
-            for (int pass = 0; pass < maxIteration; ++pass)
-            {
-                k_wave_walk<<<gw, CTA_THREADS, 0, G.stream>>>(WAVE_CLOSEST, pass, 4 * pass);
-                k_wave_shade<<<gs, CTA_THREADS, 0, G.stream>>>(pass, SHADOW_HOOK_PROBE, 4 * pass + 1);
-                k_wave_walk<<<gw, CTA_THREADS, 0, G.stream>>>(WAVE_SHADOW, pass, 4 * pass + 2);
-                k_wave_shade<<<gs, CTA_THREADS, 0, G.stream>>>(pass, SHADOW_HOOK_GIVEN, 4 * pass + 3);
-            }
-            k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
-            G.launches += 4 * maxIteration + 2;
-        }
-        else
-#endif
         if (fused)
         {
             // persistent: every CTA must be resident, or a sleeping warp could wait for one that never starts

@@ -261,51 +261,12 @@ __device__ int g_dbgN;
 #endif
 SB_DEV float rnd(const int i) { return __ldg(cS.randoms + i); }
 
-// The wavefront driver (engine.cu k_wave_*) walks the shadow rays of a pass in a kernel of their own, so a pass is shaded twice: once to find out
-// which shadow ray the path asks for (PROBE: the walk is skipped, the request recorded, the rest of the pass abandoned) and once
-// with the walk's result handed in (GIVEN).  Only rays the order-independent any-hit walk handles exactly are pooled (every caster
-// opaque, |direction| >= 1); the others — and a pooled walk that overflowed (value < 0) — take the ordered walk in the second run.
-#define SHADOW_HOOK_PROBE 1
-#define SHADOW_HOOK_GIVEN 2
-struct ShadowHook
-{
-    int mode;       // 0: none
-    bool seen;      // PROBE: a request was recorded (the lamp loop asks for the same ray lightInformationSize times)
-    bool need;      // PROBE: the request is a ray for the pool
-    float3 o, d;    // PROBE: origin, direction (to the lamp)
-    int lightId, objectId;
-    float value;    // GIVEN: the pooled walk's result (shadow intensity, < 0: overflow)
-};
-SB_DEV bool shadowPoolable(const float3 center, const float3 I)
-{
-    const float3 d = center - I;
-    return cS.nbUWide > 0 && cS.opaqueShadows && dot(d, d) >= 1.0002f;
-}
-
 // Shadow ray of one shaded hit: packet walk when the policy says so for this ray class, else per lane.
 SB_DEV float4 traceShadow(const float3 center, const float3 I, const int lightId, const int iteration, const int objectId,
-                          const bool need, const bool packet, Counters& cnt, ShadowHook* hook = nullptr)
+                          const bool need, const bool packet, Counters& cnt)
 {
     float4 sh = f4(0.f, 0.f, 0.f, 0.f);
-    if (hook && hook->mode == SHADOW_HOOK_PROBE)
-    {
-        if (!hook->seen)
-        {
-            hook->seen = true;
-            hook->need = need && shadowPoolable(center, I);
-            const float3 d = center - I;
-            hook->o = I + normalize(d) * cSI.rayEpsilon; hook->d = d;
-            hook->lightId = lightId; hook->objectId = objectId;
-        }
-        return sh;
-    }
     if (need) cnt.rays++;
-    if (hook && hook->mode == SHADOW_HOOK_GIVEN && need && shadowPoolable(center, I))
-    {
-        sh.w = hook->value;
-        if (sh.w < 0.f) sh = shadowWalkWide(center, I, lightId, iteration, objectId); // stack overflow in a degenerate tree
-        return sh;
-    }
     if (packet)
     {
         if (__any_sync(FULL_MASK, need)) sh = shadowWalkPacket(center, I, lightId, iteration, objectId, need);
@@ -381,7 +342,7 @@ SB_DEV float4 traceShadow(const float3 center, const float3 I, const int lightId
 // that the 32 shadow rays of a tile can be walked as one packet.
 SB_DEV float4 primitiveShader(const bool act, const int index, const float3 origin, float3& normal, const int objectIdIn, const float3 I,
                               const float3 areas, float4& closestColor, const int iteration, float& shadowIntensity, float4& totalBlinn,
-                              float4& attributes, const bool packetShadow, Counters& cnt, ShadowHook* hook = nullptr)
+                              float4& attributes, const bool packetShadow, Counters& cnt)
 {
     const int objectId = objectIdIn;
     int primIndex = -1;
@@ -444,7 +405,7 @@ SB_DEV float4 primitiveShader(const bool act, const int index, const float3 orig
                     needShadow = lambert > 0.f && cSI.graphicsLevel > 3 && iteration < 4 && mInner.x == 0.f;
                 }
             }
-            const float4 sh = traceShadow(center, I, lightPrimId, iteration, objectId, needShadow, packetShadow, cnt, hook);
+            const float4 sh = traceShadow(center, I, lightPrimId, iteration, objectId, needShadow, packetShadow, cnt);
             if (inRange)
             {
                 float4 shadowColor = f4(0.f, 0.f, 0.f, 0.f);
@@ -652,7 +613,7 @@ SB_DEV void pathInit(PathState& s, const float3 rayO, const float3 rayT)
 // was done elsewhere.
 template <class Colors>
 SB_DEV void pathPass(PathState& s, Colors& C, const int pass, const bool act, const int index, const float3 rayO, const int packetMask,
-                     Counters& cnt, const Hit* given = nullptr, ShadowHook* hook = nullptr)
+                     Counters& cnt, const Hit* given = nullptr)
 {
     const bool debugBoxes = cSI.renderBoxes != 0;
     float3 areas = f3(0.f, 0.f, 0.f);
@@ -669,7 +630,7 @@ SB_DEV void pathPass(PathState& s, Colors& C, const int pass, const bool act, co
     {
         if (given)
         {
-            // the walk ran in its own kernel (tracequeue.cuh)
+            // the walk ran before the path was loaded (engine.cu k_stage_pass, k_stage_fused)
             if (act) { cnt.rays++; rayNd = normalize(s.curT - s.curO); hit = *given; }
         }
         else
@@ -714,8 +675,7 @@ SB_DEV void pathPass(PathState& s, Colors& C, const int pass, const bool act, co
         s.rBlinn.w = attributes.y;
     }
     const float4 shaded = primitiveShader(found, index, s.curO, normal, hit.prim, hit.p, areas, s.closestColor, pass, s.shadowIntensity,
-                                          s.rBlinn, attributes, (packetMask & (pass == 0 ? 4 : 8)) != 0, cnt, hook);
-    if (hook && hook->mode == SHADOW_HOOK_PROBE) return; // the request is recorded; this run of the pass is thrown away
+                                          s.rBlinn, attributes, (packetMask & (pass == 0 ? 4 : 8)) != 0, cnt);
     if (found)
     {
         const float3 closestIntersection = hit.p;

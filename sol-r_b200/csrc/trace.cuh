@@ -94,9 +94,7 @@ struct RenderParams
     size_t eyeStride;          // anaglyph: slots of the right eye's paths start here (two paths per pixel)
     int maxIteration;
     int fusedQueues;           // 1: queue entries are slot + 1 in zeroed queues, published behind a fence (engine.cu k_stage_fused)
-    float4* gatherScratch; // group / wavefront walks: candidate lists of the bounce rays while they are walked
-    float* hitWords;       // wavefront stages (engine.cu k_wave_*): [HIT_WORDS][pathStride] closest hit of the current pass
-    float* shadowWords;    // [SHADOW_WORDS][pathStride] shadow ray of the current pass and its result
+    float4* gatherScratch; // group walk: candidate lists of the bounce rays while they are walked
 };
 
 // One frame's parameters live in constant memory (uploaded on the render stream before the launch):
@@ -1760,7 +1758,7 @@ SB_DEV bool primitiveTestRegs(const float4 g0, const float4 g1, const float4 g2,
 }
 
 
-// the traversal stacks of a CTA's lanes ([entry][thread]); one array for the walks that use it (unorderedWalk, waveWalk)
+// the traversal stacks of a CTA's lanes ([entry][thread]); the unit walk's
 __shared__ int2 s_walkStack[WALK_STACK * WALK_THREADS];
 
 __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigin, const float3 rayDir, const int iteration,
@@ -1995,10 +1993,6 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
 #endif
 #if UW_GROUP
 #include "tracegroup.cuh"
-#endif
-#if !defined(UW_LEGACY) && !defined(UW_V1)
-#include "tracewave.cuh"
-#define WITH_WAVE_WALK 1
 #endif
 
 SB_DEV Hit closestHitOrderIndependent(const float3 origin, const float3 target, const int iteration, const int currentMaterialId)

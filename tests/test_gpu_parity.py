@@ -352,8 +352,8 @@ def test_every_case_against_the_reference_cuda_engine(name):
 
 @pytest.mark.parametrize("cfg", ["config1", "molecule", "molecule_anaglyph"])
 def test_drivers_produce_identical_frames(cfg):
-    """Option key 6: the single persistent kernel (0), the staged kernels (1), the wavefront stages with the phased walk kernel (2)
-    and the fused stages (3: every pass in one persistent launch) run the same device functions on the same rays: ids, the float accumulation buffer and the RGB8 frame must be
+    """Option key 6: the single persistent kernel (0), the staged kernels (1, default) and the fused stages (2: every pass in one
+    persistent launch) run the same device functions on the same rays: ids, the float accumulation buffer and the RGB8 frame must be
     bit-identical, also across progressive frames."""
     W, H = 640, 360
     sc = scenes.config1(1000) if cfg == "config1" else scenes.molecule(cells=3)
@@ -369,7 +369,7 @@ def test_drivers_produce_identical_frames(cfg):
     h.close()
     rnd = gs.randoms(41)
     out = []
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2):
         e = engine.Engine(si)
         try:
             e.set_option(6, mode)
