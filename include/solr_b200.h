@@ -100,6 +100,19 @@ void b200_set_partition(int rank, int worldSize);
  * b200_peer_frame_open(NULL, 0) goes back to the local bitmap.  Both return 0 or the latched error code. */
 int b200_peer_frame_export(void* handle64, int handleBytes);
 int b200_peer_frame_open(const void* handle64, int handleBytes);
+/* The reference's animation step on the device-resident scene: GPUKernel::rotatePrimitives / translatePrimitives / scalePrimitives
+ * (GPUKernel.cpp:1378-1513, :1574-1600) followed by compactBoxes(false) and the re-upload (MoleculeScene.cpp:75-81 does this per frame).
+ * The step keeps the hierarchy's shape, so the flattened arrays keep their order and only coordinates change: the primitives are
+ * moved, the reference's boxes re-fitted and everything the engine derives from them rebuilt WITHOUT leaving the device
+ * (sol-r_b200/csrc/animate.cuh), with the reference's arithmetic — b200_d2h_scene afterwards returns arrays byte-identical to the
+ * host container's after the same step.  Needs a scene uploaded by b200_h2d_scene with the default layout; returns 0 or the latched
+ * error (-13: this scene cannot be animated on the device).  angles: radians about x, y, z, as the reference takes them.
+ * b200_d2h_scene copies the (animated) reference arrays back, e.g. to re-synchronise a host container; either pointer may be NULL. */
+int b200_rotate_primitives(b200_float3 rotationCenter, b200_float3 angles);
+int b200_translate_primitives(b200_float3 translation);
+int b200_scale_primitives(float scale);
+int b200_d2h_scene(b200_BoundingBox* boundingBoxes, b200_Primitive* primitives);
+float b200_last_animation_ms(void);
 /* Scene replication for the multi-GPU frame split (replaces the reference's per-device upload loop, CudaRayTracer.cu:1540-1613): the
  * root process uploads the scene with b200_h2d_scene, b200_scene_layout describes what it built (B200_SCENE_LAYOUT_ENTRIES
  * numbers), every other process passes those numbers to b200_scene_adopt_layout, which allocates its device arrays, and the

@@ -33,7 +33,7 @@ def _stale(target, sources):
 
 def engine_sources():
     inc = os.path.join(os.path.dirname(HERE), "include")
-    return [os.path.join(CSRC, f) for f in ("engine.cu", "shade.cuh", "trace.cuh", "tracegroup.cuh", "treebuild.cuh", "vec.cuh")] + \
+    return [os.path.join(CSRC, f) for f in ("engine.cu", "shade.cuh", "trace.cuh", "tracegroup.cuh", "treebuild.cuh", "animate.cuh", "vec.cuh")] + \
            [os.path.join(inc, f) for f in ("solr_b200.h", "solr_b200_types.h")]
 
 

@@ -1081,6 +1081,12 @@ struct Engine
     // staged rendering
     float* dPathWords = nullptr; float4* dPathColors = nullptr; float* dPathContrib = nullptr; int* dPathQueues = nullptr;
     float uploadMs = 0.f; int treesOnGpu = 0; // the last b200_h2d_scene
+    // device-side animation (animate.cuh): per reference leaf its raw box and its node in the ordered tree, the ordered tree's parent
+    // links, the binary node behind every child slot of its 4-wide form, scratch flags; levels of the reference hierarchy
+    int* dLeafRaw = nullptr; int* dLeafNode = nullptr; int* dPackedParent = nullptr; int4* dWideKid = nullptr; int* dFitFlags = nullptr;
+    size_t capLeafMaps = 0, capPackedParent = 0, capWideKid = 0;
+    int nbLeaves = 0, nbPacked = 0, maxBoxLevel = 0, nbLightPrims = 0; bool animatable = false; float animateMs = 0.f;
+    float viewDistance = 0.f; // SceneInfo.viewDistance as last seen (the reference resets inner boxes to +-viewDistance before re-fitting them)
     size_t nWideF4 = 0, nLeafRecsF4 = 0;      // float4 in dWide / dLeafRecs (scene replication)
     float4* dLeafBoxes = nullptr; size_t capLeafBoxes = 0; // boxes of the reference leaves, for the GPU tree build
     unsigned int* dQueueCounters = nullptr; size_t pathStride = 0; int pathIterations = 0;
@@ -1384,6 +1390,7 @@ struct WideBuilder
     const std::vector<float4>& bin;  // 2 float4 per binary node
     std::vector<float4>& wide;       // 8 float4 per record
     std::vector<int> leafOrdinal;    // binary node index -> leaf ordinal
+    std::vector<int>* kidNodes = nullptr; // optional: binary node of every child slot of every record (-1: empty), 4 per record
     int width;
     WideBuilder(const std::vector<float4>& b, std::vector<float4>& w, int wd) : bin(b), wide(w), width(wd) {}
     int w0(int i) const { int v; memcpy(&v, &bin[2 * (size_t)i].w, 4); return v; }
@@ -1419,6 +1426,11 @@ struct WideBuilder
                 }
             }
             float4* rec = &wide[8 * ((size_t)at * recs + q)];
+            if (kidNodes)
+            {
+                if (kidNodes->size() < 4 * ((size_t)at * recs + q + 1)) kidNodes->resize(4 * ((size_t)at * recs + q + 1), -1);
+                for (int k = 0; k < 4; ++k) (*kidNodes)[4 * ((size_t)at * recs + q) + k] = (4 * q + k < n) ? kids[4 * q + k] : -1;
+            }
             for (int r = 0; r < 6; ++r) rec[r] = make_float4(rows[r][0], rows[r][1], rows[r][2], rows[r][3]);
             rec[6] = make_float4(intBits(rf[0]), intBits(rf[1]), intBits(rf[2]), intBits(rf[3]));
             rec[7] = make_float4(intBits(n), 0.f, 0.f, 0.f);
@@ -1454,12 +1466,15 @@ struct WideBuilder
 
 // wide nodes + leaf records from the binary list; returns the number of wide nodes
 int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::vector<float4>& leafRecs,
-              const std::vector<int>* leafOfNode = nullptr, int width = 4)
+              const std::vector<int>* leafOfNode = nullptr, int width = 4, std::vector<int>* kidNodes = nullptr, std::vector<int>* leafNodes = nullptr)
 {
     wide.clear();
     const int nb = (int)(bin.size() / 2);
     if (nb == 0) return 0;
     WideBuilder b(bin, wide, width);
+    b.kidNodes = kidNodes;
+    if (kidNodes) kidNodes->clear();
+    if (leafNodes) leafNodes->clear();
     b.leafOrdinal.assign(nb, -1);
     if (leafOfNode)
     {
@@ -1473,6 +1488,7 @@ int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::ve
             if (b.isLeaf(i))
             {
                 b.leafOrdinal[i] = (int)(leafRecs.size() / 2);
+                if (leafNodes) leafNodes->push_back(i);
                 leafRecs.push_back(bin[2 * (size_t)i]);
                 leafRecs.push_back(bin[2 * (size_t)i + 1]);
             }
@@ -1658,6 +1674,7 @@ static int relayoutBoxes(const b200_BoundingBox* boxes, int nbBoxes, std::vector
 #define UW_PAD 0.02f // padding of the walk trees' primitive boxes (buildWalkTrees, treebuild.cuh)
 #endif
 #include "treebuild.cuh"
+#include "animate.cuh"
 
 extern "C" {
 
@@ -1727,8 +1744,9 @@ int b200_last_error(char* msg, int cap)
 }
 void b200_clear_error(void) { G.err = 0; G.errMsg[0] = 0; }
 
-void b200_initialize_scene(b200_int2 occ, b200_SceneInfo, int, int, int)
+void b200_initialize_scene(b200_int2 occ, b200_SceneInfo si, int, int, int)
 {
+    G.viewDistance = si.viewDistance;
     if (occ.x != 1) latch(-3, "b200_initialize_scene", "one process drives one GPU: occupancyParameters.x must be 1 (use b200_set_partition)");
     if (!ensureDevice()) return;
     if (G.initialised) return;
@@ -1763,7 +1781,8 @@ void b200_finalize_scene(b200_int2)
     unregisterHost();
     closePeerFrame();
     freeDev(G.dWide); freeDev(G.dLeafRecs); G.capWide = G.capLeafRecs = 0; G.nbWide = 0;
-    freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dLeafBoxes); G.capLeafBoxes = 0; treebuild::releaseScratch(); freeDev(G.dPrimLeaf); G.capPrimLeaf = 0; freeDev(G.dPrimRecs); G.capPrimRecs = 0;
+    freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dLeafBoxes); G.capLeafBoxes = 0; treebuild::releaseScratch();
+    freeDev(G.dLeafRaw); freeDev(G.dLeafNode); freeDev(G.dPackedParent); freeDev(G.dFitFlags); freeDev(G.dWideKid); G.capLeafMaps = G.capPackedParent = G.capWideKid = 0; G.animatable = false; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0; freeDev(G.dPrimRecs); G.capPrimRecs = 0;
     freeDev(G.dUGroup); G.capUGroup = 0; freeDev(G.dGatherScratch); G.capGatherScratch = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
@@ -1781,8 +1800,9 @@ void b200_finalize_scene(b200_int2)
     // no cudaDeviceReset(): the process may share the device with NCCL / PyTorch
 }
 
-void b200_reshape_scene(b200_int2, b200_SceneInfo)
+void b200_reshape_scene(b200_int2, b200_SceneInfo si)
 {
+    G.viewDistance = si.viewDistance;
     if (!ensureDevice()) return;
     const size_t px = (size_t)G.maxW * (size_t)G.maxH;
     freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
@@ -1999,7 +2019,8 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     lap("ordered tree (relayout)");
     // 2b. the 4-wide form of the ordered BVH for the per-lane walks
     std::vector<float4> wide, leafRecs;
-    G.nbWide = (G.boxLayoutUsed == 2) ? buildWide(packed, wide, leafRecs) : 0;
+    std::vector<int> wideKidNodes, leafNodes;
+    G.nbWide = (G.boxLayoutUsed == 2) ? buildWide(packed, wide, leafRecs, nullptr, 4, &wideKidNodes, &leafNodes) : 0;
     if (wide.size() > G.capWide) { freeDev(G.dWide); G.capWide = wide.size() + 1024; CK(cudaMalloc(&G.dWide, G.capWide * sizeof(float4))); }
     if (leafRecs.size() > G.capLeafRecs) { freeDev(G.dLeafRecs); G.capLeafRecs = leafRecs.size() + 1024; CK(cudaMalloc(&G.dLeafRecs, G.capLeafRecs * sizeof(float4))); }
     G.nWideF4 = wide.size(); G.nLeafRecsF4 = leafRecs.size();
@@ -2145,6 +2166,60 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     lap("boxes, geometry, primitives up");
     uploadMeta();
     lap("packed words");
+    // what the device-side animation step needs besides the arrays themselves (animate.cuh)
+    G.animatable = false;
+    if (G.boxLayoutUsed == 2 && G.nbWide > 0 && leafNodes.size() == leaves.size() && !leaves.empty())
+    {
+        std::vector<int> leafRaw;
+        leafRaw.reserve(leaves.size());
+        int maxLevel = 0;
+        for (int i = 0; i < nbBoxes; ++i)
+        {
+            if (boxes[i].nbPrimitives > 0) leafRaw.push_back(i);
+            else if (boxes[i].startIndex > maxLevel) maxLevel = boxes[i].startIndex;
+        }
+        const size_t nbPacked = packed.size() / 2;
+        std::vector<int> parent(nbPacked, -1);
+        {
+            // depth-first list with subtree sizes: a node's children are the next node and the one after the first child's subtree
+            std::vector<std::pair<int, int>> stack; // (node, end)
+            for (size_t i = 0; i < nbPacked; ++i)
+            {
+                while (!stack.empty() && stack.back().second <= (int)i) stack.pop_back();
+                parent[i] = stack.empty() ? -1 : stack.back().first;
+                int w0, w1;
+                memcpy(&w0, &packed[2 * i].w, 4); memcpy(&w1, &packed[2 * i + 1].w, 4);
+                if (w1 <= 0) stack.push_back({(int)i, (int)i + (w0 > 1 ? w0 : 1)});
+            }
+        }
+        bool ok = leafRaw.size() == leaves.size() && wideKidNodes.size() == 4 * (size_t)G.nbWide;
+        for (size_t k = 0; ok && k < leaves.size(); ++k) ok = boxes[leafRaw[k]].startIndex == leaves[k].start && boxes[leafRaw[k]].nbPrimitives == leaves[k].count;
+        if (ok)
+        {
+            if (leaves.size() > G.capLeafMaps)
+            {
+                freeDev(G.dLeafRaw); freeDev(G.dLeafNode);
+                G.capLeafMaps = leaves.size() + 1024;
+                CK(cudaMalloc(&G.dLeafRaw, G.capLeafMaps * sizeof(int))); CK(cudaMalloc(&G.dLeafNode, G.capLeafMaps * sizeof(int)));
+            }
+            if (nbPacked > G.capPackedParent)
+            {
+                freeDev(G.dPackedParent); freeDev(G.dFitFlags);
+                G.capPackedParent = nbPacked + 1024;
+                CK(cudaMalloc(&G.dPackedParent, G.capPackedParent * sizeof(int))); CK(cudaMalloc(&G.dFitFlags, G.capPackedParent * sizeof(int)));
+            }
+            if ((size_t)G.nbWide > G.capWideKid) { freeDev(G.dWideKid); G.capWideKid = (size_t)G.nbWide + 1024; CK(cudaMalloc(&G.dWideKid, G.capWideKid * sizeof(int4))); }
+            CK(cudaMemcpyAsync(G.dLeafRaw, leafRaw.data(), leafRaw.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+            CK(cudaMemcpyAsync(G.dLeafNode, leafNodes.data(), leafNodes.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+            CK(cudaMemcpyAsync(G.dPackedParent, parent.data(), nbPacked * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+            CK(cudaMemcpyAsync(G.dWideKid, wideKidNodes.data(), wideKidNodes.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+            CK(cudaStreamSynchronize(G.stream));
+            G.nbLeaves = (int)leaves.size(); G.nbPacked = (int)nbPacked; G.maxBoxLevel = maxLevel;
+            G.nbLightPrims = (nbBoxes > 0 && boxes[0].nbPrimitives > 0 && boxes[0].startIndex == 0) ? boxes[0].nbPrimitives : 0;
+            G.animatable = G.err == 0;
+        }
+    }
+    lap("animation maps");
     G.treesOnGpu = gpuTrees ? 1 : 0;
     G.uploadMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - uploadT0).count();
 }
@@ -2239,6 +2314,94 @@ int b200_scene_adopt_finish(void)
     return G.err;
 }
 
+// ----------------------------------------------------------------------------------------------------
+// The animation step on the device-resident scene (animate.cuh has the what and why).
+// ----------------------------------------------------------------------------------------------------
+static int animateScene(const animate::Move& move)
+{
+    if (!G.initialised || !ensureDevice()) return -1;
+    if (!G.animatable || G.nbPrims <= 0) { latch(-13, "device-side animation", "needs a scene uploaded with the ordered-tree layout (b200_h2d_scene, options 1 and 4 at their defaults)"); return -13; }
+    const auto t0 = std::chrono::steady_clock::now();
+    const int T = 256;
+    const int nbMovable = G.nbPrims - (move.mode == animate::MOVE_SCALE ? 0 : G.nbLightPrims);
+    const int firstMovable = move.mode == animate::MOVE_SCALE ? 0 : G.nbLightPrims;
+    if (nbMovable > 0) animate::k_an_move<<<(nbMovable + T - 1) / T, T, 0, G.stream>>>(G.dPrims, firstMovable, G.nbPrims, move);
+    if (move.mode == animate::MOVE_SCALE && G.nbLights > 0) animate::k_an_scale_lights<<<(G.nbLights + T - 1) / T, T, 0, G.stream>>>(G.dLights, G.nbLights, move.s);
+    if (move.mode != animate::MOVE_SCALE && G.nbBoxesIn > 1)
+    {
+        // the reference's scalePrimitives leaves the boxes alone (GPUKernel.cpp:1574-1600); rotate and translate re-fit them
+        const int B = (G.nbBoxesIn - 1 + T - 1) / T;
+        animate::k_an_leaf_boxes<<<B, T, 0, G.stream>>>(G.dRawBoxes, G.nbBoxesIn, G.dPrims, G.nbPrims);
+        for (int level = 1; level <= G.maxBoxLevel; ++level)
+            animate::k_an_inner_boxes<<<B, T, 0, G.stream>>>(G.dRawBoxes, G.nbBoxesIn, level, G.viewDistance);
+    }
+    // derived: ordered tree, its wide form and leaf records, geometry and primitive records, walk trees
+    if ((size_t)2 * G.nbLeaves > G.capLeafBoxes) { CK(cudaStreamSynchronize(G.stream)); freeDev(G.dLeafBoxes); G.capLeafBoxes = (size_t)2 * G.nbLeaves + 1024; CK(cudaMalloc(&G.dLeafBoxes, G.capLeafBoxes * sizeof(float4))); }
+    const int BL = (G.nbLeaves + T - 1) / T;
+    animate::k_an_ordered_leaves<<<BL, T, 0, G.stream>>>(G.dRawBoxes, G.dLeafRaw, G.dLeafNode, G.nbLeaves, G.dBoxes, G.dLeafBoxes);
+    CK(cudaMemsetAsync(G.dFitFlags, 0, (size_t)G.nbPacked * sizeof(int), G.stream));
+    animate::k_an_ordered_fit<<<BL, T, 0, G.stream>>>(G.dBoxes, G.dPackedParent, G.dLeafNode, G.nbLeaves, G.dFitFlags);
+    animate::k_an_ordered_wide<<<(G.nbWide + T - 1) / T, T, 0, G.stream>>>(G.dBoxes, G.dWideKid, G.nbWide, G.dWide);
+    animate::k_an_leaf_recs<<<BL, T, 0, G.stream>>>(G.dBoxes, G.dLeafNode, G.nbLeaves, G.dLeafRecs);
+    animate::k_an_records<<<(G.nbPrims + T - 1) / T, T, 0, G.stream>>>(G.dPrims, G.nbPrims, G.dPrimLeaf, G.dLeafBoxes, G.dGeo, G.nbUWide > 0 ? G.dPrimRecs : nullptr);
+    int rc = 0;
+    if (G.nbUWide > 0)
+    {
+        const int nbExtBoxes = g_useBackward ? treebuild::extCount(G.dPrims, G.nbPrims, G.dPrimLeaf, G.dLeafBoxes, G.stream) : 0;
+        rc = nbExtBoxes < 0 ? nbExtBoxes : 0;
+        if (rc == 0)
+        {
+            const size_t wantF4 = 8 * ((size_t)G.nbPrims + (size_t)nbExtBoxes) + 8;
+            if (wantF4 > G.capUWide) { CK(cudaStreamSynchronize(G.stream)); freeDev(G.dUWide); G.capUWide = wantF4 + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
+            rc = treebuild::buildWalkTreesGpu(G.dPrims, G.nbPrims, G.dPrimLeaf, G.dLeafBoxes, nbExtBoxes, G.dUWide, G.nbUWide, G.nbUX, G.stream);
+            G.treesOnGpu = 1;
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (rc != 0 || e != cudaSuccess) { latch(rc != 0 ? rc : (int)e, "device-side animation", "a kernel or the tree build failed"); G.animatable = false; return G.err; }
+    // the host copy of the primitives backs the packed material words only (type and material id: untouched by a move)
+    CK(cudaStreamSynchronize(G.stream));
+    G.animateMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return G.err;
+}
+
+int b200_rotate_primitives(b200_float3 center, b200_float3 angles)
+{
+    animate::Move m;
+    memset(&m, 0, sizeof(m));
+    m.mode = animate::MOVE_ROTATE;
+    m.center = make_float3(center.x, center.y, center.z);
+    // GPUKernel.cpp:1383-1391: the cosines and sines are taken in double and kept as floats
+    m.cosA = make_float3((float)cos((double)angles.x), (float)cos((double)angles.y), (float)cos((double)angles.z));
+    m.sinA = make_float3((float)sin((double)angles.x), (float)sin((double)angles.y), (float)sin((double)angles.z));
+    return animateScene(m);
+}
+int b200_translate_primitives(b200_float3 t)
+{
+    animate::Move m;
+    memset(&m, 0, sizeof(m));
+    m.mode = animate::MOVE_TRANSLATE;
+    m.t = make_float3(t.x, t.y, t.z);
+    return animateScene(m);
+}
+int b200_scale_primitives(float scale)
+{
+    animate::Move m;
+    memset(&m, 0, sizeof(m));
+    m.mode = animate::MOVE_SCALE;
+    m.s = scale;
+    return animateScene(m);
+}
+int b200_d2h_scene(b200_BoundingBox* boxes, b200_Primitive* prims)
+{
+    if (!G.initialised || !ensureDevice()) return -1;
+    if (boxes && G.nbBoxesIn > 0) CK(cudaMemcpyAsync(boxes, G.dRawBoxes, (size_t)G.nbBoxesIn * sizeof(b200_BoundingBox), cudaMemcpyDeviceToHost, G.stream));
+    if (prims && G.nbPrims > 0) CK(cudaMemcpyAsync(prims, G.dPrims, (size_t)G.nbPrims * sizeof(b200_Primitive), cudaMemcpyDeviceToHost, G.stream));
+    CK(cudaStreamSynchronize(G.stream));
+    return G.err;
+}
+float b200_last_animation_ms(void) { return G.animateMs; }
+
 void b200_h2d_materials(b200_int2, const b200_Material* materials, int n)
 {
     if (!G.initialised) { latch(-4, "b200_h2d_materials", "initialize_scene not called"); return; }
@@ -2307,6 +2470,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
                  b200_float3 direction, b200_float4 angles)
 {
     if (!G.initialised || !G.dPost) { latch(-4, "b200_render", "initialize_scene/reshape_scene not called"); return; }
+    G.viewDistance = si.viewDistance;
     if (!ensureDevice()) return;
     if (si.size.x <= 0 || si.size.y <= 0 || (size_t)si.size.x * si.size.y > G.pixelsCap)
     {

@@ -83,6 +83,13 @@ def load():
               "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition", "b200_device_buffers",
               "b200_get_counters", "b200_scene_stats", "b200_scene_upload_stats", "b200_synchronize", "b200_clear_error"):
         getattr(lib, f).restype = None
+    lib.b200_rotate_primitives.argtypes = [wire.Float3, wire.Float3]
+    lib.b200_translate_primitives.argtypes = [wire.Float3]
+    lib.b200_scale_primitives.argtypes = [C.c_float]
+    lib.b200_d2h_scene.argtypes = [C.c_void_p, C.c_void_p]
+    for f in ("b200_rotate_primitives", "b200_translate_primitives", "b200_scale_primitives", "b200_d2h_scene"):
+        getattr(lib, f).restype = C.c_int
+    lib.b200_last_animation_ms.restype = C.c_float
     lib.b200_scene_layout.argtypes = [C.POINTER(C.c_longlong), C.c_int]
     lib.b200_scene_adopt_layout.argtypes = [C.POINTER(C.c_longlong), C.c_int]
     lib.b200_scene_device_arrays.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.c_int]
@@ -99,6 +106,7 @@ ABI_SYMBOLS = [
     "b200_last_error", "b200_clear_error", "b200_set_device", "b200_set_option", "b200_set_stream", "b200_set_limits", "b200_set_partition",
     "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_build_walk_trees", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats", "b200_scene_upload_stats",
     "b200_scene_layout", "b200_scene_adopt_layout", "b200_scene_device_arrays", "b200_scene_adopt_finish",
+    "b200_rotate_primitives", "b200_translate_primitives", "b200_scale_primitives", "b200_d2h_scene", "b200_last_animation_ms",
     "b200_synchronize", "b200_measure_fp32_peak", "b200_register_host", "b200_unregister_host", "b200_accumulation_clear", "b200_accumulation_export", "b200_accumulation_import_and_pack", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
 ]
 
@@ -214,6 +222,30 @@ class Engine:
             infos, n = textures
             self.lib.b200_h2d_textures(self.OCC, n, C.cast(infos, C.c_void_p))
         self.check()
+
+    # ---- the animation step on the device-resident scene (csrc/animate.cuh) ----
+    def rotate_primitives(self, center, angles):
+        self.lib.b200_rotate_primitives(wire.Float3(*[float(v) for v in center]), wire.Float3(*[float(v) for v in angles]))
+        self.check()
+
+    def translate_primitives(self, t):
+        self.lib.b200_translate_primitives(wire.Float3(*[float(v) for v in t]))
+        self.check()
+
+    def scale_primitives(self, scale):
+        self.lib.b200_scale_primitives(float(scale))
+        self.check()
+
+    def download_scene(self):
+        """The reference arrays as they are on the device (after animation steps): (boxes, primitives) as uint8 arrays."""
+        boxes = np.zeros(self.objects.x * 48, np.uint8)
+        prims = np.zeros(self.objects.y * 128, np.uint8)
+        self.lib.b200_d2h_scene(_ptr(boxes), _ptr(prims))
+        self.check()
+        return boxes, prims
+
+    def last_animation_ms(self):
+        return float(self.lib.b200_last_animation_ms())
 
     def scene_layout(self):
         v = (C.c_longlong * 16)()

@@ -432,6 +432,65 @@ def test_gpu_built_walk_trees_give_identical_frames(cfg):
     assert not np.array_equal(out[(0, 0)][1], out[(0, 1)][1])  # the rotation changed the picture
 
 
+@pytest.mark.parametrize("cfg", ["config1", "molecule", "mesh"])
+def test_device_animation_equals_the_host_step(cfg):
+    """b200_rotate_primitives / b200_translate_primitives / b200_scale_primitives (csrc/animate.cuh) against the host container's
+    animation step — rotatePrimitives / translatePrimitives / scalePrimitives + compactBoxes(false), itself byte-identical to the
+    reference's (tests/test_scene_host.py) — followed by a fresh upload: after every step the reference arrays on the device must be
+    BYTE-identical to the host container's, and the frame rendered from the device-animated scene bit-identical (ids, float
+    accumulation buffer, RGB8, ray count) to the frame rendered from the uploaded one."""
+    W, H = 640, 360
+    sc = scenes.config1(1000) if cfg == "config1" else scenes.molecule(cells=3) if cfg == "molecule" else scenes.triangle_mesh(20000)
+    si = wire.default_scene_info(W, H, graphics_level=wire.GL_FULL, nb_ray_iterations=3)
+    rnd = gs.randoms(53)
+    moves = [("rotate", ((0.0, 0.0, 0.0), (0.1, 0.25, 0.05))), ("translate", ((40.0, -25.0, 10.0),)),
+             ("rotate", ((100.0, 50.0, -30.0), (-0.3, 0.02, 0.4))), ("scale", (1.03,))]
+    h = host.SceneHost(si)
+    sc.replay(h)
+    states = [dict(h.arrays())]
+    for kind, args in moves:
+        getattr(h, kind + "_primitives")(*args)
+        h.compact_boxes(False)
+        states.append(dict(h.arrays()))
+    h.close()
+
+    def frame(e):
+        e.render(si, sc.eye, sc.target, sc.angles)
+        bm, ids = e.readback(si)
+        post = e.read_post_buffer(si)
+        rays, _ = e.counters(reset=True)
+        return bm.copy(), ids.copy(), post.copy(), rays
+
+    uploaded = []
+    e = engine.Engine(si)
+    try:
+        for a in states:
+            e.upload(a, randoms=rnd)
+            uploaded.append(frame(e))
+    finally:
+        e.close()
+    e = engine.Engine(si)
+    try:
+        e.upload(states[0], randoms=rnd)
+        animated = [frame(e)]
+        for k, (kind, args) in enumerate(moves):
+            getattr(e, kind + "_primitives")(*args)
+            boxes, prims = e.download_scene()
+            want = states[k + 1]
+            assert states[k + 1]["nbBoxes"] == states[0]["nbBoxes"] and states[k + 1]["nbPrimitives"] == states[0]["nbPrimitives"]
+            assert np.array_equal(prims, np.asarray(want["primitives"]).view(np.uint8).ravel()), "primitives after step %d (%s)" % (k, kind)
+            assert np.array_equal(boxes, np.asarray(want["boxes"]).view(np.uint8).ravel()), "boxes after step %d (%s)" % (k, kind)
+            animated.append(frame(e))
+    finally:
+        e.close()
+    for k, (u, d) in enumerate(zip(uploaded, animated)):
+        assert np.array_equal(d[1], u[1]), "ids, state %d" % k
+        assert np.array_equal(d[2].view(np.uint32), u[2].view(np.uint32)), "accumulation buffer, state %d" % k
+        assert np.array_equal(d[0], u[0]), "bitmap, state %d" % k
+        assert d[3] == u[3]
+    assert not np.array_equal(uploaded[0][1], uploaded[1][1])  # the steps changed the picture
+
+
 def test_small_queue_passes_in_registers_give_identical_frames():
     """Option key 8: a bounce pass whose queue is small carries its paths to the end of their ray trees in registers instead
     of parking them for another launch per pass.  Never (0), always (a huge percentage) and the default must agree bit for bit
