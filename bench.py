@@ -458,6 +458,29 @@ def measure_scene_paths(ctx):
                          "walk_tree_nodes": upload_stats()[1]}
             h.close()
         lib.b200_set_option(10, 0)
+        # the same step applied where the scene lives (b200_rotate_primitives, csrc/animate.cuh): no host compaction, no upload
+        h = host.SceneHost(si, limits=wl["limits"], rank=0, world=1, device=ctx.local_rank, capacity=wl["capacity"])
+        sc.replay(h)
+        h.set_randoms(rnd, 0)
+        h.set_camera(sc.eye, sc.target, sc.angles)
+        h.init_buffers()
+        h.render_begin(0.0); h.render_end()
+        torch.cuda.synchronize()
+        h.set_device_animation(True)
+        step, frame, render = [], [], []
+        for k in range(5):
+            t0 = time.perf_counter()
+            h.rotate_primitives((0.0, 0.0, 0.0), (0.0, 0.05, 0.0))
+            h.compact_boxes(False)
+            t1 = time.perf_counter()
+            h.render_begin(0.0); h.render_end()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            step.append((t1 - t0) * 1e3); frame.append((t2 - t1) * 1e3); render.append(float(lib.b200_last_render_ms()))
+        out["on_the_device"] = {"step_ms": round(min(step), 2), "of_which_device_work_ms": round(float(lib.b200_last_animation_ms()), 2),
+                                "frame_ms": round(min(frame), 2), "of_which_render_kernels_ms": round(min(render), 2),
+                                "walk_tree_nodes": upload_stats()[1]}
+        h.close()
         return out
 
     # N > 1

@@ -988,6 +988,8 @@ void SceneHost::materialiseBoxes()
 
 int SceneHost::compactBoxes(bool reconstructBoxes) // :1041-1083
 {
+    if (m_hostStale && !reconstructBoxes) return m_nbActiveBoxes; // the step was applied on the device, where the arrays already are
+    syncFromDevice();
     m_primitivesTransfered = false;
     m_primitiveTable.clear();
     if (!m_primitives.empty() && m_primitives.rbegin()->first < 4u * m_primitives.size() + 1024u)
@@ -1326,8 +1328,38 @@ void SceneHost::refreshBoxesAfterMove()
         for (auto& box : m_boundingBoxes[b]) updateOutterBoundingBox(box.second, b - 1);
 }
 
+// The reference arrays come back from the device (where the last animation steps were applied), the primitives go back into the
+// container by their ids, and the boxes are re-fitted the way a host-side step would have left them.
+void SceneHost::syncFromDevice()
+{
+    if (!m_hostStale) return;
+    m_hostStale = false;
+    if (b200_d2h_scene(m_hBoundingBoxes.data(), m_hPrimitives.data()) != 0) return;
+    materialiseBoxes();
+    for (const b200_Primitive& p : m_hPrimitives)
+    {
+        auto it = m_primitives.find((unsigned)p.index);
+        if (it == m_primitives.end()) continue;
+        HostPrimitive& hp = it->second;
+        hp.p0 = p.p0; hp.p1 = p.p1; hp.p2 = p.p2; hp.n0 = p.n0; hp.n1 = p.n1; hp.n2 = p.n2; hp.size = p.size;
+    }
+    for (auto& entry : m_boundingBoxes[0])
+    {
+        HostBox& box = entry.second;
+        resetBox(box, false);
+        if (!box.primitives.empty()) updateBoundingBox(box);
+    }
+    refreshBoxesAfterMove();
+}
+
 void SceneHost::rotatePrimitives(const b200_float3& rotationCenter, const b200_float3& angles) // :1378-1460
 {
+    if (m_deviceAnimation && m_deviceInitialised && m_primitivesTransfered && b200_rotate_primitives(rotationCenter, angles) == 0)
+    {
+        m_hostStale = true;
+        return;
+    }
+    syncFromDevice();
     materialiseBoxes();
     m_primitivesTransfered = false;
     const b200_float3 cosAngles = v3(cos(angles.x), cos(angles.y), cos(angles.z));
@@ -1348,6 +1380,12 @@ void SceneHost::rotatePrimitives(const b200_float3& rotationCenter, const b200_f
 
 void SceneHost::translatePrimitives(const b200_float3& translation) // :1462-1513
 {
+    if (m_deviceAnimation && m_deviceInitialised && m_primitivesTransfered && b200_translate_primitives(translation) == 0)
+    {
+        m_hostStale = true;
+        return;
+    }
+    syncFromDevice();
     materialiseBoxes();
     m_primitivesTransfered = false;
     for (auto& entry : m_boundingBoxes[0])
@@ -1371,6 +1409,7 @@ void SceneHost::translatePrimitives(const b200_float3& translation) // :1462-151
 
 void SceneHost::scalePrimitives(const float scale) // :1574-1600 (the reference ignores its from / to arguments)
 {
+    syncFromDevice();
     m_primitivesTransfered = false;
     for (auto& entry : m_primitives)
     {
@@ -1460,6 +1499,7 @@ int b200h_compact_boxes(void* h, int reconstruct) { return static_cast<SceneHost
 void b200h_get_scene(void* h, b200h_Scene* out)
 {
     SceneHost* s = static_cast<SceneHost*>(h);
+    s->syncFromDevice();
     out->boxes = s->boxes(); out->nbBoxes = s->nbActiveBoxes();
     out->primitives = s->primitives(); out->nbPrimitives = s->nbActivePrimitives();
     out->materials = s->materials(); out->nbMaterials = s->nbMaterials();
@@ -1482,6 +1522,8 @@ void b200h_translate_primitives(void* h, const float* t)
     static_cast<SceneHost*>(h)->translatePrimitives(translation);
 }
 void b200h_scale_primitives(void* h, float scale) { static_cast<SceneHost*>(h)->scalePrimitives(scale); }
+void b200h_set_device_animation(void* h, int on) { static_cast<SceneHost*>(h)->setDeviceAnimation(on != 0); }
+void b200h_sync_from_device(void* h) { static_cast<SceneHost*>(h)->syncFromDevice(); }
 void b200h_set_flat_build(void* h, int mode) { static_cast<SceneHost*>(h)->setFlatBuild(mode); }
 void b200h_set_lazy_ids(void* h, int lazy) { static_cast<SceneHost*>(h)->setLazyIds(lazy != 0); }
 void b200h_set_partition(void* h, int rank, int world) { static_cast<SceneHost*>(h)->setPartition(rank, world); }

@@ -91,6 +91,12 @@ public:
     unsigned char* getBitmap() { return m_bitmap.data(); }
     b200_PrimitiveXYIdBuffer* getPrimitiveIds(); // fetches the buffer from the device first when render_end left it there
     void setLazyIds(bool lazy) { m_lazyIds = lazy; }
+    // Animation on the device (b200_rotate_primitives / b200_translate_primitives): once the scene is on the device, rotatePrimitives
+    // and translatePrimitives move it THERE and this container's own copy goes stale until somebody needs it (syncFromDevice: any
+    // setter, compactBoxes(true), the array accessors after a step) — the per-frame loop of MoleculeScene.cpp:75-81 never does.
+    void setDeviceAnimation(bool on) { if (!on) syncFromDevice(); m_deviceAnimation = on; }
+    void syncFromDevice();
+    bool hostIsStale() const { return m_hostStale; }
     // 0: always the literal per-level maps; 1: flat build with the depth-first flatten; 2 (default): flat build with the flatten by
     // levels (tests compare the three)
     void setFlatBuild(int mode) { m_useFlatBuild = mode != 0; m_levelOrderFlatten = mode == 2; }
@@ -164,6 +170,7 @@ private:
     std::vector<unsigned char> m_bitmap;
     std::vector<b200_PrimitiveXYIdBuffer> m_primitivesXYIds;
     bool m_lazyIds = true;      // render_end copies the pixels only; ids are fetched when asked for
+    bool m_deviceAnimation = false, m_hostStale = false;
     bool m_idsOnDevice = false; // the host copy is older than the last frame
     bool m_primitivesTransfered, m_materialsTransfered, m_texturesTransfered, m_randomsTransfered, m_refresh;
     bool m_deviceInitialised;

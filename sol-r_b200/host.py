@@ -65,6 +65,8 @@ def load():
     lib.b200h_scale_primitives.argtypes = [vp, C.c_float]
     lib.b200h_scale_primitives.restype = None
     lib.b200h_set_flat_build.argtypes = [vp, C.c_int]
+    lib.b200h_set_device_animation.argtypes = [vp, C.c_int]
+    lib.b200h_sync_from_device.argtypes = [vp]
     lib.b200h_set_flat_build.restype = None
     lib.b200h_set_lazy_ids.argtypes = [vp, C.c_int]
     lib.b200h_set_lazy_ids.restype = None
@@ -181,6 +183,14 @@ class SceneHost:
 
     def scale_primitives(self, scale):
         self.lib.b200h_scale_primitives(self.h, scale)
+
+    def set_device_animation(self, on=True):
+        """rotate_primitives / translate_primitives move the scene on the device once it is there (csrc/animate.cuh); this container's
+        own copy is brought up to date when somebody asks for it (arrays(), any later host-side step)."""
+        self.lib.b200h_set_device_animation(self.h, 1 if on else 0)
+
+    def sync_from_device(self):
+        self.lib.b200h_sync_from_device(self.h)
 
     def set_flat_build(self, mode):
         """0 / False: compact_boxes always builds the reference's per-level maps literally; 1: flat sort-and-merge build of a fresh

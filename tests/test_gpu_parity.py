@@ -212,6 +212,46 @@ def test_host_frame_protocol_equals_direct_seam_calls():
     assert np.array_equal(bm1, bm2) and np.array_equal(ids1, ids2)
 
 
+def test_host_container_animates_on_the_device():
+    """SceneHost.set_device_animation: rotate_primitives / translate_primitives + compact_boxes(False) + a frame, the per-frame loop of
+    MoleculeScene.cpp:75-81, with the step applied on the device (no host work, no upload) against the same loop on the host: the same
+    frames; and the container's own arrays, brought back from the device when asked for, byte-identical to the host-side ones — also
+    after a further host-side step on top."""
+    sc, si, eye, target, angles, rnd, _ = gs.case_setup("molecule_full")
+    si.maxPathTracingIterations = 1 << 30
+    moves = [("rotate", ((0.0, 0.0, 0.0), (0.05, 0.2, 0.0))), ("translate", ((15.0, 0.0, -20.0),)), ("rotate", ((0.0, 0.0, 0.0), (0.0, 0.2, 0.1)))]
+    out = {}
+    for on_device in (False, True):
+        h = host.SceneHost(si)
+        sc.replay(h)
+        h.set_randoms(rnd, 0)
+        h.set_camera(eye, target, angles)
+        h.init_buffers()
+        h.render_begin(0.0); h.render_end()
+        h.set_device_animation(on_device)
+        frames = []
+        for kind, args in moves:
+            getattr(h, kind + "_primitives")(*args)
+            h.compact_boxes(False)
+            h.render_begin(0.0); h.render_end()
+            frames.append((h.bitmap().copy(), h.primitive_ids().copy()))
+        a = dict(h.arrays())   # device animation: synchronises the container
+        h.scale_primitives(1.01)
+        h.rotate_primitives((0.0, 0.0, 0.0), (0.1, 0.0, 0.0))   # on the device again when on_device (the scale forced an upload)
+        h.compact_boxes(False)
+        h.render_begin(0.0); h.render_end()
+        frames.append((h.bitmap().copy(), h.primitive_ids().copy()))
+        b = dict(h.arrays())
+        h.close()
+        out[on_device] = (frames, a, b)
+    for (bm0, id0), (bm1, id1) in zip(out[False][0], out[True][0]):
+        assert np.array_equal(id0, id1) and np.array_equal(bm0, bm1)
+    for k in (1, 2):
+        for name in ("boxes", "primitives", "lightInformation"):
+            assert np.array_equal(np.asarray(out[False][k][name]), np.asarray(out[True][k][name])), name
+    assert not np.array_equal(out[False][0][0][1], out[False][0][1][1])
+
+
 def test_id_buffer_is_read_back_on_demand():
     """render_end leaves the id buffer on the device by default; a pick (getPrimitiveAt, GPUKernel.cpp:729-739) fetches one pixel's
     16 bytes, primitive_ids() the whole buffer — both equal what the reference's every-frame read-back (set_lazy_ids(False)) gives."""
