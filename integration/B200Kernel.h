@@ -41,6 +41,15 @@ public:
     /* GPUKernel::getPrimitiveAt (GPUKernel.cpp:729-739) for any frame size */
     unsigned int getPrimitiveIdAt(int x, int y);
     void setPartition(int rank, int worldSize);
+    /* The animation step on the device (include/solr_b200.h b200_rotate_primitives / b200_translate_primitives): what
+     * GPUKernel::rotatePrimitives / translatePrimitives + compactBoxes(false) + the re-upload do per frame in MoleculeScene.cpp:75-81,
+     * applied to the arrays where they live — same arithmetic, same arrays, no host work.  GPUKernel's own methods are not virtual
+     * (GPUKernel.h:119-128,304), so a scene calls these instead while it animates, and syncFromDevice() before it reads or edits the
+     * container again (getPrimitive, setPrimitive, compactBoxes(true) ...).  Both fall back to the host-side step — and return
+     * false — when the scene is not on the device yet. */
+    bool rotatePrimitivesOnDevice(const vec3f &rotationCenter, const vec4f &angles);
+    bool translatePrimitivesOnDevice(const vec3f &translation);
+    void syncFromDevice();
     /* fixes what GPUKernel::render_begin draws from rand() (GPUKernel.cpp:2719-2727): deterministic frames */
     void setRandoms(const float *randoms, size_t count, int timestamp);
 
@@ -49,6 +58,7 @@ private:
     void releaseDevice();
     bool m_deviceInitialized;
     bool m_fixedRandoms;
+    bool m_hostStale; /* the last animation steps were applied on the device only */
     int m_fixedTimestamp;
     int m_maxWidth, m_maxHeight;
     std::vector<unsigned char> m_bigBitmap; /* used instead of m_bitmap when the limits exceed the reference's */

@@ -226,6 +226,22 @@ void refh_scale_primitives(void* h, float scale)
     static_cast<HarnessKernel*>(h)->scalePrimitives(scale, 0, 0);
 }
 
+#ifdef REFH_B200
+// the same steps applied on the device through integration/B200Kernel (returns 1 when the device did it, 0 when the host fallback ran)
+int refh_rotate_primitives_on_device(void* h, const float* center3, const float* angles3)
+{
+    vec3f c = make_vec3f(center3[0], center3[1], center3[2]);
+    vec4f a = make_vec4f(angles3[0], angles3[1], angles3[2], 0.f);
+    return static_cast<HarnessKernel*>(h)->rotatePrimitivesOnDevice(c, a) ? 1 : 0;
+}
+int refh_translate_primitives_on_device(void* h, const float* t3)
+{
+    vec3f t = make_vec3f(t3[0], t3[1], t3[2]);
+    return static_cast<HarnessKernel*>(h)->translatePrimitivesOnDevice(t) ? 1 : 0;
+}
+void refh_sync_from_device(void* h) { static_cast<HarnessKernel*>(h)->syncFromDevice(); }
+#endif
+
 int refh_load_molecule(void* h, const char* filename, int geometryType, float atomSize, float stickSize,
                        int materialType, float scale)
 {

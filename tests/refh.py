@@ -114,6 +114,23 @@ class RefScene:
         self.lib.refh_rotate_primitives.restype = None
         self.lib.refh_rotate_primitives(self.h, c, a)
 
+    # integration/B200Kernel only: the step applied on the device (True) or by the host fallback (False)
+    def rotate_primitives_on_device(self, center, angles):
+        c = np.asarray(center, np.float32); a = np.asarray(angles, np.float32)
+        self.lib.refh_rotate_primitives_on_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.refh_rotate_primitives_on_device.restype = C.c_int
+        return bool(self.lib.refh_rotate_primitives_on_device(self.h, _ptr(c), _ptr(a)))
+
+    def translate_primitives_on_device(self, t):
+        v = np.asarray(t, np.float32)
+        self.lib.refh_translate_primitives_on_device.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.refh_translate_primitives_on_device.restype = C.c_int
+        return bool(self.lib.refh_translate_primitives_on_device(self.h, _ptr(v)))
+
+    def sync_from_device(self):
+        self.lib.refh_sync_from_device.argtypes = [C.c_void_p]
+        self.lib.refh_sync_from_device(self.h)
+
     def translate_primitives(self, t):
         v = (C.c_float * 3)(*t)
         self.lib.refh_translate_primitives.argtypes = [C.c_void_p, C.c_void_p]

@@ -86,3 +86,38 @@ def test_drop_in_beyond_the_reference_frame_limit():
     assert (ids1[..., 0] >= 0).sum() > 0.05 * W * H
     assert np.array_equal(bm1, bm2)
     assert np.array_equal(ids1[..., 0], ids2[..., 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not refh.available("b200"), reason="oracle/_ref/libsolr_ref_b200.so did not travel")
+def test_reference_host_animates_on_the_device():
+    """The reference's own GPUKernel with B200Kernel as engine class: the per-frame loop of MoleculeScene.cpp:75-81 — rotatePrimitives
+    + compactBoxes(false) + frame — run by the reference's host code (arrays re-flattened and re-uploaded every step) against
+    B200Kernel::rotatePrimitivesOnDevice / translatePrimitivesOnDevice (the arrays moved where they live): same frames; and after
+    syncFromDevice the reference container's own flattened arrays are byte-identical to the host-side loop's."""
+    moves = [("rotate", ((0.0, 0.0, 0.0), (0.05, 0.2, 0.0))), ("translate", ((15.0, 0.0, -20.0),)), ("rotate", ((0.0, 0.0, 0.0), (0.0, 0.2, 0.1)))]
+    out = {}
+    for on_device in (False, True):
+        sc, si, eye, target, angles, rnd, frames = gs.case_setup("molecule_full")
+        r = refh.RefScene(si, "b200")
+        sc.replay(r)
+        r.render(si, eye, target, angles, randoms=rnd, want_post=False)   # the scene goes up
+        shots = []
+        for kind, args in moves:
+            if on_device:
+                assert getattr(r, kind + "_primitives_on_device")(*args), "the step fell back to the host"
+            else:
+                getattr(r, kind + "_primitives")(*args)
+                r.compact_boxes(False)
+            bm, ids, _ = r.render(si, eye, target, angles, randoms=rnd, want_post=False)
+            shots.append((np.array(bm, copy=True), np.array(ids, copy=True)))
+        if on_device:
+            r.sync_from_device()
+        a = r.arrays()
+        r.close()
+        out[on_device] = (shots, a)
+    for (bm0, id0), (bm1, id1) in zip(out[False][0], out[True][0]):
+        assert np.array_equal(bm0, bm1) and np.array_equal(id0, id1)
+    for name in ("boxes", "primitives"):
+        assert np.array_equal(out[False][1][name], out[True][1][name]), name
+    assert not np.array_equal(out[False][0][0][0], out[False][0][1][0])
