@@ -1942,39 +1942,44 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     // of X) away.  One pass over the list looks for such a candidate (any, accepted or not: conservative); only then — or when two
     // candidates share the closest distance — the full replay below decides.  (Round 2: the replay, quadratic in the list length and
     // run by one to three lanes of a warp, was a quarter of a bounce pass's time; profiles/r02_history.md.)
+    float m = minDistance0;
+    int winner = -1;
     {
         bool slow = bestTie;
         for (int j = 0; j < n; ++j)
             slow |= candIdx[j] < out.hit.prim && candLeaf[j] != bestLeaf && candD[j] <= bestLeafT && candD[j] <= window;
-        DBG_ADD(0 + 6, 0); DBG_ADD(3, slow ? 1 : 0);
-        if (!slow) return out;
+        DBG_ADD(3, slow ? 1 : 0);
+        if (!slow) winner = out.hit.prim;
+        else
+        {
+            // replay in array order (selection by ascending index: the list is short; a primitive listed twice — by the point query,
+            // or as two pieces of a long cylinder — is taken once).  Primitives of one leaf are contiguous and share the leaf's fate,
+            // decided when the leaf is reached (before any of its primitives): t_min(leaf) < closest-so-far.
+            bool leafPass = false;
+            int prevLeaf = -1;
+            int last = -1;
+            for (int pass = 0; pass < n; ++pass)
+            {
+                int bj = -1, bi = 0x7fffffff;
+                for (int j = 0; j < n; ++j)
+                {
+                    const int ci = candIdx[j];
+                    if (ci > last && ci < bi && candD[j] <= window) { bi = ci; bj = j; }
+                }
+                if (bj < 0) break;
+                last = bi;
+                if (candLeaf[bj] != prevLeaf)
+                {
+                    leafPass = candLeafT[bj] < m;
+                    prevLeaf = candLeaf[bj];
+                }
+                if (leafPass && candD[bj] < m) { m = candD[bj]; winner = bi; }
+            }
+        }
     }
+    // the winner's hit point comes from ONE copy of the primitive test whichever way it was found and whatever the tree looked
+    // like (two differently scheduled copies may round a grazing hit apart)
     out.hit.prim = -1; out.hit.p = f3(0.f, 0.f, 0.f); out.hit.flags = 0;
-    // replay in array order (selection by ascending index: the list is short; a cylinder listed twice by the point query is
-    // taken once).  Primitives of one leaf are contiguous and share the leaf's fate, decided when the leaf is reached (before
-    // any of its primitives): t_min(leaf) < closest-so-far.
-    float m = minDistance0;
-    bool leafPass = false;
-    int prevLeaf = -1;
-    int winner = -1;
-    int last = -1;
-    for (int pass = 0; pass < n; ++pass)
-    {
-        int bj = -1, bi = 0x7fffffff;
-        for (int j = 0; j < n; ++j)
-        {
-            const int ci = candIdx[j];
-            if (ci > last && ci < bi && candD[j] <= window) { bi = ci; bj = j; }
-        }
-        if (bj < 0) break;
-        last = bi;
-        if (candLeaf[bj] != prevLeaf)
-        {
-            leafPass = candLeafT[bj] < m;
-            prevLeaf = candLeaf[bj];
-        }
-        if (leafPass && candD[bj] < m) { m = candD[bj]; winner = bi; }
-    }
     if (winner >= 0)
     {
         const int meta = __ldg(cS.meta + winner);
