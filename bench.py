@@ -277,7 +277,7 @@ def measure_workload(key, steps, warmup, ctx, sample_clocks=False, want_e2e=True
     pp = wire.PostProcessingInfo()
     si0 = workloads.scene_info(key)
     si0.maxPathTracingIterations = 1 << 30
-    peer = partition.PeerFrame(lib, rank, world) if world > 1 else None   # ranks > 0 now write into rank 0's frame
+    peer = partition.PeerFrame(lib, rank, world, stream=stream) if world > 1 else None   # ranks > 0 now write into rank 0's frame
 
     def frame_device():
         it = next_iteration()

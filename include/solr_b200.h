@@ -72,7 +72,8 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
  * key 2 = which walks run warp-synchronously as packets (bit0 primary rays, bit1 secondary rays, bit2 shadow rays
  * of primary hits, bit3 other shadow rays); packets are only used with the ordered BVH.
  * key 3 = per-lane walks over the 4-wide form of the ordered BVH (1, default) or over the binary list (0).
- * key 4 = order-independent walks over the unordered SAH BVH where they are exact (1, default) or ordered walks only (0).
+ * key 4 = order-independent walks over the unordered SAH BVH where they are exact (1, default; a bounce ray whose candidates form a
+ *         chain up to the edge of its gather window, or overflow its list, takes the ordered walk) or ordered walks only (0).
  * key 5 = order-independent walks also look up hits BEHIND the ray origin, which the reference's cylinder/cone test registers
  *         (GeometryIntersections.cuh:316-325) (1, default); 0 drops them (not reference-exact; for measurement).
  * key 6 = staged rendering: one launch per bounce pass over a compacted queue of the paths still alive (1, default, used for

@@ -1436,8 +1436,10 @@ struct WideBuilder
             rec[7] = make_float4(intBits(n), 0.f, 0.f, 0.f);
         }
     }
-    int build(int i) // i: inner binary node
+    int maxDepth = 0; // deepest wide node (root = 1): a walk's stack holds at most 3 entries per level
+    int build(int i, int depth = 1) // i: inner binary node
     {
+        if (depth > maxDepth) maxDepth = depth;
         int kids[8], n = 2;
         kids[0] = i + 1;
         kids[1] = i + 1 + size(i + 1);
@@ -1458,7 +1460,7 @@ struct WideBuilder
         const int at = (int)(wide.size() / (8 * (size_t)recs));
         wide.resize(wide.size() + 8 * (size_t)recs);
         int refs[8];
-        for (int k = 0; k < n; ++k) refs[k] = isLeaf(kids[k]) ? ~leafOrdinal[kids[k]] : build(kids[k]);
+        for (int k = 0; k < n; ++k) refs[k] = isLeaf(kids[k]) ? ~leafOrdinal[kids[k]] : build(kids[k], depth + 1);
         writeNode(at, kids, refs, n);
         return at;
     }
@@ -1466,8 +1468,10 @@ struct WideBuilder
 
 // wide nodes + leaf records from the binary list; returns the number of wide nodes
 int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::vector<float4>& leafRecs,
-              const std::vector<int>* leafOfNode = nullptr, int width = 4, std::vector<int>* kidNodes = nullptr, std::vector<int>* leafNodes = nullptr)
+              const std::vector<int>* leafOfNode = nullptr, int width = 4, std::vector<int>* kidNodes = nullptr, std::vector<int>* leafNodes = nullptr,
+              int* maxDepthOut = nullptr)
 {
+    if (maxDepthOut) *maxDepthOut = 1;
     wide.clear();
     const int nb = (int)(bin.size() / 2);
     if (nb == 0) return 0;
@@ -1503,6 +1507,7 @@ int buildWide(const std::vector<float4>& bin, std::vector<float4>& wide, std::ve
         return 1;
     }
     b.build(0);
+    if (maxDepthOut) *maxDepthOut = b.maxDepth;
     return (int)(wide.size() / (8 * (size_t)recs));
 }
 
@@ -2020,7 +2025,14 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     // 2b. the 4-wide form of the ordered BVH for the per-lane walks
     std::vector<float4> wide, leafRecs;
     std::vector<int> wideKidNodes, leafNodes;
-    G.nbWide = (G.boxLayoutUsed == 2) ? buildWide(packed, wide, leafRecs, nullptr, 4, &wideKidNodes, &leafNodes) : 0;
+    int wideDepth = 0;
+    G.nbWide = (G.boxLayoutUsed == 2) ? buildWide(packed, wide, leafRecs, nullptr, 4, &wideKidNodes, &leafNodes, &wideDepth) : 0;
+    if (3 * wideDepth + 3 > WIDE_STACK)
+    {
+        // closestHitWide / shadowWalkWide keep up to three entries per level in a fixed stack (trace.cuh WIDE_STACK): a tree this deep
+        // (SAH splits of a badly skewed scene) is walked as the stackless list instead
+        G.nbWide = 0; wide.clear(); leafRecs.clear(); wideKidNodes.clear(); leafNodes.clear();
+    }
     if (wide.size() > G.capWide) { freeDev(G.dWide); G.capWide = wide.size() + 1024; CK(cudaMalloc(&G.dWide, G.capWide * sizeof(float4))); }
     if (leafRecs.size() > G.capLeafRecs) { freeDev(G.dLeafRecs); G.capLeafRecs = leafRecs.size() + 1024; CK(cudaMalloc(&G.dLeafRecs, G.capLeafRecs * sizeof(float4))); }
     G.nWideF4 = wide.size(); G.nLeafRecsF4 = leafRecs.size();

@@ -1415,7 +1415,9 @@ SB_DEV void walkUnspill(int2* const stack, const int2* const spillBuf, int& nSpi
 // are chained by ratios <= 1/L.  Sorting the candidates by distance, everything beyond the first gap wider than 1/L is
 // inert: it can neither win nor hide anything that can.  The walk keeps every candidate within GATHER_WINDOW x the closest
 // distance (1.5 = eight links of such a chain, each of which would additionally need a matching array order and leaf
-// entry); the ordered walk (option key 4 = 0) is the literal form and tests compare the two.
+// entry) and, when it is over, checks that no chain of kept candidates climbs from the closest one into the window's outermost
+// shell (L * window, window] — if one does, something outside the window could hang on to it and the ray takes the ordered walk
+// instead (option key 4 = 0 is that literal form for every ray; tests compare the two).
 #define GATHER_WINDOW 1.5f
 #define UW_CLOSEST 0
 #define UW_GATHER 1
@@ -1948,6 +1950,35 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
         bool slow = bestTie;
         for (int j = 0; j < n; ++j)
             slow |= candIdx[j] < out.hit.prim && candLeaf[j] != bestLeaf && candD[j] <= bestLeafT && candD[j] <= window;
+        // Candidates beyond the window are left out.  They can only matter through a chain of candidates each within 1/L of the
+        // next (see above): if such a chain climbs from the closest candidate into the outermost shell of the window, (L * window,
+        // window], a candidate outside could hang on to it, and then the ordered walk decides rather than a heuristic.  At
+        // L = 0.95 — every bounce ray the shader makes — that takes seven links, i.e. eight candidates: the gate keeps the check
+        // out of the common case (it cost 2 % of the frame run on every ray).
+        if (n >= 8 || lenOL < 0.949f)
+        {
+            float dmax = 0.f;
+            for (int j = 0; j < n; ++j)
+                if (candD[j] <= window) dmax = fmaxf(dmax, candD[j]);
+            if (dmax > lenOL * window)
+            {
+                float reach = best;
+                for (bool grew = true; grew;)
+                {
+                    grew = false;
+                    float next = reach;
+                    const float limit = reach / lenOL * 1.000001f;
+                    for (int j = 0; j < n; ++j)
+                        if (candD[j] > reach && candD[j] <= limit && candD[j] <= window) next = fmaxf(next, candD[j]);
+                    if (next > reach) { reach = next; grew = true; }
+                }
+                if (reach > lenOL * window)
+                {
+                    out.hit.prim = -2; out.shadow = -1.f; // caller runs the ordered walk
+                    return out;
+                }
+            }
+        }
         DBG_ADD(3, slow ? 1 : 0);
         if (!slow) winner = out.hit.prim;
         else

@@ -100,18 +100,23 @@ class PeerFrame:
     """The fused exchange (include/solr_b200.h b200_peer_frame_*): rank `root` exports its device bitmap, the others open
     it, and from then on their kernels write finished pixels into the root's frame through NVLink peer memory.
 
-    fence() is a one-element NCCL all-reduce on the current CUDA stream (under gloo — tests with two processes on one GPU —
-    it drains the engine's stream and meets the other ranks on the host).  A frame is: fence (the root has read the previous frame:
+    fence() is a one-element NCCL all-reduce ON THE STREAM THE ENGINE RENDERS ON: pass that torch stream as `stream` and the engine
+    is switched to it (b200_set_stream), so the collective is ordered behind the kernels and their peer stores without a host
+    round trip; without a stream the engine keeps its own and fence() drains it on the host before the collective (correct,
+    slower).  Under gloo — tests with two processes on one GPU — it drains the engine's stream and meets the other ranks on the host.  A frame is: fence (the root has read the previous frame:
     nobody overwrites it early), render on every rank, fence (every rank's kernels — and with them their peer stores — are
     done), then the root's read-back."""
 
     HANDLE_BYTES = 64
 
-    def __init__(self, lib, rank, world, root=0):
+    def __init__(self, lib, rank, world, root=0, stream=None):
         import ctypes
         import torch
         import torch.distributed as dist
         self.lib, self.rank, self.world, self.root, self.dist = lib, rank, world, root, dist
+        self.torch, self.stream = torch, stream
+        if stream is not None:
+            lib.b200_set_stream(ctypes.c_void_p(stream.cuda_stream))
         box = [None]
         if rank == root:
             buf = ctypes.create_string_buffer(self.HANDLE_BYTES)
@@ -127,8 +132,13 @@ class PeerFrame:
         self.token = torch.zeros(1, dtype=torch.int32, device="cuda") if self.nccl else None
 
     def fence(self):
-        if self.nccl:
+        if self.nccl and self.stream is not None:
+            with self.torch.cuda.stream(self.stream):
+                self.dist.all_reduce(self.token)
+        elif self.nccl:
+            self.lib.b200_synchronize()   # the engine renders on a stream of its own: its kernels first, then the collective
             self.dist.all_reduce(self.token)
+            self.torch.cuda.current_stream().synchronize()
         else:
             self.lib.b200_synchronize()
             self.dist.barrier()
