@@ -48,12 +48,12 @@ def build_engine(force=False, verbose=False, extra=()):
 
 
 def build_host(force=False):
-    src = [os.path.join(CSRC, "scene_host.cpp"), os.path.join(CSRC, "scene_host.h")]
+    src = [os.path.join(CSRC, "scene_host.cpp"), os.path.join(CSRC, "scene_host.h"), os.path.join(CSRC, "loaders.cpp")]
     if not os.path.exists(src[0]):
         return None
     if force or _stale(HOST_LIB, src):
         build_engine()
-        subprocess.check_call([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-sign-compare", "-o", HOST_LIB, src[0],
+        subprocess.check_call([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-sign-compare", "-ffp-contract=off", "-o", HOST_LIB, src[0], src[2],
                                "-L" + CSRC, "-lsolr_b200", "-Wl,-rpath,$ORIGIN"])
     return HOST_LIB
 

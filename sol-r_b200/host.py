@@ -88,6 +88,25 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def find_bonds(xyz, processed, is_backbone, stick_distance=1.7, backbone_geometry=False):
+    """The bond search of PDBReader.cpp:616-660 without its n^2 loop (csrc/loaders.cpp): for atoms in std::map order, (first, partners)
+    with partners[first[i]:first[i + 1]] = the atoms atom i gets a stick to, ascending."""
+    lib = load()
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    n = xyz.shape[0]
+    processed = np.ascontiguousarray(processed, np.int32)
+    is_backbone = np.ascontiguousarray(is_backbone, np.uint8)
+    first = np.zeros(n + 1, np.int32)
+    lib.b200h_find_bonds.restype = C.c_long
+    lib.b200h_find_bonds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_long]
+    need = lib.b200h_find_bonds(_ptr(xyz), _ptr(processed), _ptr(is_backbone), n, 1 if backbone_geometry else 0, stick_distance, _ptr(first), None, 0)
+    need = abs(int(need))
+    partners = np.zeros(max(need, 1), np.int32)
+    got = lib.b200h_find_bonds(_ptr(xyz), _ptr(processed), _ptr(is_backbone), n, 1 if backbone_geometry else 0, stick_distance, _ptr(first), _ptr(partners), need)
+    assert got == need
+    return first, partners[:need]
+
+
 class SceneHost:
     """Same call sequence a Sol-R application makes on solr::GPUKernel (SURVEY.md §3.1-3.3)."""
 
