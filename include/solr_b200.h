@@ -121,7 +121,7 @@ float b200_last_animation_ms(void);
  * the root's over NVLink — sol-r_b200/partition.py broadcast_scene does it with one NCCL broadcast per array.
  * b200_scene_adopt_finish completes the adopted scene (host copy of the primitives, packed material words).  Materials, lights,
  * textures and randoms go up per process as before.  All return a count or 0, or a negative / latched error code. */
-#define B200_SCENE_LAYOUT_ENTRIES 10
+#define B200_SCENE_LAYOUT_ENTRIES 15
 int b200_scene_layout(long long* layout, int capacity);
 int b200_scene_adopt_layout(const long long* layout, int entries);
 int b200_scene_device_arrays(void** devicePointers, long long* bytes, int capacity);

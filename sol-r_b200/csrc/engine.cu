@@ -2243,18 +2243,22 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
 // uploads every array to every device from the host (CudaRayTracer.cu:1540-1613 inside the per-device loop).
 // Materials, lights, textures and randoms are small and go up per process as before.
 // ----------------------------------------------------------------------------------------------------
-#define SCENE_LAYOUT_ENTRIES 10
+#define SCENE_LAYOUT_ENTRIES 15
 static size_t sceneArrayList(void** ptrs, long long* bytes, int cap)
 {
-    void* p[10] = {G.dBoxes, G.dRawBoxes, G.dGeo, G.dMeta, G.dPrims, G.dWide, G.dLeafRecs, G.dPrimLeaf, G.dPrimRecs, G.dUWide};
-    const long long b[10] = {
+    const size_t an = G.animatable ? 1 : 0; // the maps of the device-side animation travel with an animatable scene
+    void* p[14] = {G.dBoxes, G.dRawBoxes, G.dGeo, G.dMeta, G.dPrims, G.dWide, G.dLeafRecs, G.dPrimLeaf, G.dPrimRecs, G.dUWide,
+                   G.dLeafRaw, G.dLeafNode, G.dPackedParent, G.dWideKid};
+    const long long b[14] = {
         (long long)(2 * (size_t)G.nbBoxes * sizeof(float4)), (long long)((size_t)G.nbBoxesIn * sizeof(b200_BoundingBox)),
         (long long)(4 * (size_t)G.nbPrims * sizeof(float4)), (long long)((size_t)G.nbPrims * sizeof(int)),
         (long long)((size_t)G.nbPrims * sizeof(b200_Primitive)), (long long)(G.nWideF4 * sizeof(float4)), (long long)(G.nLeafRecsF4 * sizeof(float4)),
         (long long)((size_t)G.nbPrims * sizeof(int)), (long long)(G.nbUWide > 0 ? ((size_t)PRIM_REC_F4 * G.nbPrims + 2) * sizeof(float4) : 0),
-        (long long)(8 * ((size_t)G.nbUWide + (size_t)G.nbUX) * sizeof(float4))};
+        (long long)(8 * ((size_t)G.nbUWide + (size_t)G.nbUX) * sizeof(float4)),
+        (long long)(an * (size_t)G.nbLeaves * sizeof(int)), (long long)(an * (size_t)G.nbLeaves * sizeof(int)),
+        (long long)(an * (size_t)G.nbPacked * sizeof(int)), (long long)(an * (size_t)G.nbWide * sizeof(int4))};
     int n = 0;
-    for (int k = 0; k < 10 && n < cap; ++k, ++n) { if (ptrs) ptrs[n] = b[k] ? p[k] : nullptr; if (bytes) bytes[n] = b[k]; }
+    for (int k = 0; k < 14 && n < cap; ++k, ++n) { if (ptrs) ptrs[n] = b[k] ? p[k] : nullptr; if (bytes) bytes[n] = b[k]; }
     return (size_t)n;
 }
 
@@ -2262,7 +2266,7 @@ int b200_scene_layout(long long* layout, int capacity)
 {
     if (!layout || capacity < SCENE_LAYOUT_ENTRIES) return -4;
     const long long v[SCENE_LAYOUT_ENTRIES] = {G.nbBoxesIn, G.nbBoxes, G.nbPrims, G.boxLayoutUsed, G.nbWide, (long long)G.nWideF4, (long long)G.nLeafRecsF4,
-                                               G.nbUWide, G.nbUX, G.treesOnGpu};
+                                               G.nbUWide, G.nbUX, G.treesOnGpu, G.animatable ? 1 : 0, G.nbLeaves, G.nbPacked, G.maxBoxLevel, G.nbLightPrims};
     for (int k = 0; k < SCENE_LAYOUT_ENTRIES; ++k) layout[k] = v[k];
     return SCENE_LAYOUT_ENTRIES;
 }
@@ -2300,6 +2304,23 @@ int b200_scene_adopt_layout(const long long* layout, int n)
     if (recsF4 > G.capPrimRecs) { freeDev(G.dPrimRecs); G.capPrimRecs = recsF4 + 1024; CK(cudaMalloc(&G.dPrimRecs, G.capPrimRecs * sizeof(float4))); }
     const size_t uwF4 = 8 * ((size_t)G.nbUWide + (size_t)G.nbUX);
     if (uwF4 > G.capUWide) { freeDev(G.dUWide); G.capUWide = uwF4 + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
+    G.animatable = layout[10] != 0; G.nbLeaves = (int)layout[11]; G.nbPacked = (int)layout[12]; G.maxBoxLevel = (int)layout[13]; G.nbLightPrims = (int)layout[14];
+    if (G.animatable)
+    {
+        if ((size_t)G.nbLeaves > G.capLeafMaps)
+        {
+            freeDev(G.dLeafRaw); freeDev(G.dLeafNode);
+            G.capLeafMaps = (size_t)G.nbLeaves + 1024;
+            CK(cudaMalloc(&G.dLeafRaw, G.capLeafMaps * sizeof(int))); CK(cudaMalloc(&G.dLeafNode, G.capLeafMaps * sizeof(int)));
+        }
+        if ((size_t)G.nbPacked > G.capPackedParent)
+        {
+            freeDev(G.dPackedParent); freeDev(G.dFitFlags);
+            G.capPackedParent = (size_t)G.nbPacked + 1024;
+            CK(cudaMalloc(&G.dPackedParent, G.capPackedParent * sizeof(int))); CK(cudaMalloc(&G.dFitFlags, G.capPackedParent * sizeof(int)));
+        }
+        if ((size_t)G.nbWide > G.capWideKid) { freeDev(G.dWideKid); G.capWideKid = (size_t)G.nbWide + 1024; CK(cudaMalloc(&G.dWideKid, G.capWideKid * sizeof(int4))); }
+    }
     return G.err;
 }
 

@@ -248,8 +248,8 @@ class Engine:
         return float(self.lib.b200_last_animation_ms())
 
     def scene_layout(self):
-        v = (C.c_longlong * 16)()
-        n = self.lib.b200_scene_layout(v, 16)
+        v = (C.c_longlong * 32)()
+        n = self.lib.b200_scene_layout(v, 32)
         self.check()
         return [int(x) for x in v[:n]]
 

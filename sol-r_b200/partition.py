@@ -61,7 +61,7 @@ def broadcast_scene(engine, arrays, rank, world, src=0, randoms=None, textures=N
         layout = torch.tensor(engine.scene_layout(), dtype=torch.int64, device=dev)
     else:
         engine.upload_small(arrays, randoms=randoms, textures=textures)
-        layout = torch.zeros(16, dtype=torch.int64, device=dev)
+        layout = torch.zeros(32, dtype=torch.int64, device=dev)
     n = torch.tensor([layout.numel()], dtype=torch.int64, device=dev)
     dist.broadcast(n, src)
     layout = layout[: int(n.item())].contiguous()

@@ -1,7 +1,7 @@
 """GPU test of the scene replication (include/solr_b200.h b200_scene_layout / b200_scene_adopt_layout / b200_scene_device_arrays /
 b200_scene_adopt_finish, sol-r_b200/partition.py broadcast_scene): rank 0 uploads the scene, rank 1 — which is handed EMPTY box and
-primitive arrays — adopts the layout and receives the device arrays with one broadcast per array; both then render their tiles of
-the frame split, and the merged frame must equal the frame one process renders alone, bit for bit, with host-built and with
+primitive arrays — adopts the layout and receives the device arrays with one broadcast per array; both then rotate the scene ON THE DEVICE and render
+their tiles of the frame split, and the merged frame must equal the frame one process renders alone, bit for bit, with host-built and with
 GPU-built walk trees.  gloo carries the broadcasts here because NCCL refuses two ranks on one device; bench.py runs the same path
 with NCCL over NVLink."""
 import os
@@ -35,6 +35,8 @@ def _worker(rank, world, port, case, gpu_trees, out):
     e = engine.Engine(si, rank=rank, world=world)
     e.set_option(10, gpu_trees)
     received = partition.broadcast_scene(e, a, rank, world, src=0, randoms=rnd)
+    # the adopted scene animates on the device like the uploaded one (the maps of csrc/animate.cuh travelled with it)
+    e.rotate_primitives((0.0, 0.0, 0.0), (0.1, 0.2, 0.0))
     e.render(si, eye, target, angles)
     bm, ids = e.readback(si)
     t = torch.from_numpy(bm.astype(np.int32))  # pixels this rank does not own are zero: the partial frames merge by summation
@@ -45,6 +47,7 @@ def _worker(rank, world, port, case, gpu_trees, out):
     if rank == 0:
         e = engine.Engine(si)
         e.upload(full, randoms=rnd)
+        e.rotate_primitives((0.0, 0.0, 0.0), (0.1, 0.2, 0.0))
         e.render(si, eye, target, angles)
         whole = e.readback(si)[0].copy()
         e.close()
