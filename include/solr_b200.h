@@ -87,6 +87,8 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
  *         tree for a scene that is uploaded once), 1 on the GPU (linear BVH, sol-r_b200/csrc/treebuild.cuh: milliseconds instead of
  *         tenths of a second per upload, for scenes that are re-uploaded every animation step — GPUKernel::rotatePrimitives +
  *         compactBoxes(false), MoleculeScene.cpp:75-81).  Same frames either way.
+ * key 11 = what b200_rotate_primitives / b200_translate_primitives / b200_scale_primitives do with the main walk tree: 1 re-fit it in
+ *         place (default: the tree keeps the shape its builder gave it), 0 rebuild it on the GPU.  Same frames either way.
  */
 void b200_set_option(int key, int value);
 /* Multi-GPU frame split: this process renders tiles t with t % worldSize == rank (interleaved 8x4-pixel
@@ -121,7 +123,7 @@ float b200_last_animation_ms(void);
  * the root's over NVLink — sol-r_b200/partition.py broadcast_scene does it with one NCCL broadcast per array.
  * b200_scene_adopt_finish completes the adopted scene (host copy of the primitives, packed material words).  Materials, lights,
  * textures and randoms go up per process as before.  All return a count or 0, or a negative / latched error code. */
-#define B200_SCENE_LAYOUT_ENTRIES 15
+#define B200_SCENE_LAYOUT_ENTRIES 16
 int b200_scene_layout(long long* layout, int capacity);
 int b200_scene_adopt_layout(const long long* layout, int entries);
 int b200_scene_device_arrays(void** devicePointers, long long* bytes, int capacity);

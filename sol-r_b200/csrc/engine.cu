@@ -1086,6 +1086,7 @@ struct Engine
     int* dLeafRaw = nullptr; int* dLeafNode = nullptr; int* dPackedParent = nullptr; int4* dWideKid = nullptr; int* dFitFlags = nullptr;
     size_t capLeafMaps = 0, capPackedParent = 0, capWideKid = 0;
     int nbLeaves = 0, nbPacked = 0, maxBoxLevel = 0, nbLightPrims = 0; bool animatable = false; float animateMs = 0.f;
+    int walkTreeLevels = 0;   // levels of the main walk tree (passes a re-fit in place needs)
     float viewDistance = 0.f; // SceneInfo.viewDistance as last seen (the reference resets inner boxes to +-viewDistance before re-fitting them)
     size_t nWideF4 = 0, nLeafRecsF4 = 0;      // float4 in dWide / dLeafRecs (scene replication)
     float4* dLeafBoxes = nullptr; size_t capLeafBoxes = 0; // boxes of the reference leaves, for the GPU tree build
@@ -1644,6 +1645,7 @@ int g_fuseTailPercent = 300; // k_stage_pass(p) carries its paths to the end in 
 int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: every pass in one persistent launch
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
+int g_animateRefit = 1; // device-side animation: 1 re-fits the main walk tree in place (default), 0 rebuilds it (linear BVH)
 int g_gpuTrees = 0; // 1: the trees of the order-independent walks are built on the GPU (treebuild.cuh) instead of on host threads
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
 } // namespace
@@ -1699,6 +1701,7 @@ void b200_set_option(int key, int value)
     else if (key == 4) g_useUnordered = value != 0;
     else if (key == 5) g_useBackward = value != 0;
     else if (key == 10 && (value == 0 || value == 1)) g_gpuTrees = value;
+    else if (key == 11 && (value == 0 || value == 1)) g_animateRefit = value;
     else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value; // 2: fused stages (k_stage_fused)
     else if (key == 8 && value >= 0) g_fuseTailPercent = value;
     else if (key == 9 && (value == 0 || value == 1)) g_tileOrder = value;
@@ -1874,8 +1877,9 @@ static void renumberBreadthFirst(std::vector<float4>& wide, int nbNodes)
 // span a large part of the scene — followed by the point-query tree of grown cylinder/cone boxes.  primLeaf keeps the
 // reference leaf each primitive belongs to, because a hit only counts if that leaf's box passes the reference's slab test.
 static void buildWalkTrees(const std::vector<LeafRec>& leaves, const b200_Primitive* prims, int nbPrims, std::vector<float4>& uwide,
-                           std::vector<int>& primLeaf, int& nbMain, int& nbExt)
+                           std::vector<int>& primLeaf, int& nbMain, int& nbExt, int* mainDepth = nullptr)
 {
+    if (mainDepth) *mainDepth = 0;
     std::vector<float4> ubin, xbin, xwide;
     uwide.clear();
     primLeaf.assign(nbPrims > 0 ? nbPrims : 1, 0);
@@ -1969,7 +1973,7 @@ static void buildWalkTrees(const std::vector<LeafRec>& leaves, const b200_Primit
     ubin.reserve(4 * (size_t)nbPrims);
     SahBuilder sb(primBoxes, ubin, leafOfNode);
     sb.build(0, nbPrims, 0);
-    nbMain = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode, UW_WIDTH);
+    nbMain = buildWide(ubin, uwide, unusedLeafRecs, &leafOfNode, UW_WIDTH, nullptr, nullptr, mainDepth);
     renumberBreadthFirst(uwide, nbMain);
     extThread.join();
     if (!extBoxes.empty())
@@ -2051,7 +2055,7 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
             for (int k = 0; k < leaves[l].count; ++k)
                 if (leaves[l].start + k >= 0 && leaves[l].start + k < nbPrims) primLeaf[leaves[l].start + k] = (int)l;
     }
-    else if (wantTrees) buildWalkTrees(leaves, prims, nbPrims, uwide, primLeaf, G.nbUWide, G.nbUX);
+    else if (wantTrees) buildWalkTrees(leaves, prims, nbPrims, uwide, primLeaf, G.nbUWide, G.nbUX, &G.walkTreeLevels);
     lap("walk trees on the host");
     if ((size_t)nbPrims > G.capPrimLeaf) { freeDev(G.dPrimLeaf); G.capPrimLeaf = (size_t)nbPrims + 1024; CK(cudaMalloc(&G.dPrimLeaf, G.capPrimLeaf * sizeof(int))); }
     if (nbPrims > 0) CK(cudaMemcpyAsync(G.dPrimLeaf, primLeaf.data(), (size_t)nbPrims * sizeof(int), cudaMemcpyHostToDevice, G.stream));
@@ -2083,7 +2087,7 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
         {
             const size_t wantF4 = 8 * ((size_t)nbPrims + (size_t)nbExtBoxes) + 8;
             if (wantF4 > G.capUWide) { CK(cudaStreamSynchronize(G.stream)); freeDev(G.dUWide); G.capUWide = wantF4 + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
-            rc = treebuild::buildWalkTreesGpu(G.dPrims, nbPrims, G.dPrimLeaf, G.dLeafBoxes, nbExtBoxes, G.dUWide, G.nbUWide, G.nbUX, G.stream);
+            rc = treebuild::buildWalkTreesGpu(G.dPrims, nbPrims, G.dPrimLeaf, G.dLeafBoxes, nbExtBoxes, G.dUWide, G.nbUWide, G.nbUX, G.stream, &G.walkTreeLevels);
         }
         cudaError_t e = cudaGetLastError();
         if (rc != 0 || e != cudaSuccess)
@@ -2243,7 +2247,7 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
 // uploads every array to every device from the host (CudaRayTracer.cu:1540-1613 inside the per-device loop).
 // Materials, lights, textures and randoms are small and go up per process as before.
 // ----------------------------------------------------------------------------------------------------
-#define SCENE_LAYOUT_ENTRIES 15
+#define SCENE_LAYOUT_ENTRIES 16
 static size_t sceneArrayList(void** ptrs, long long* bytes, int cap)
 {
     const size_t an = G.animatable ? 1 : 0; // the maps of the device-side animation travel with an animatable scene
@@ -2266,7 +2270,7 @@ int b200_scene_layout(long long* layout, int capacity)
 {
     if (!layout || capacity < SCENE_LAYOUT_ENTRIES) return -4;
     const long long v[SCENE_LAYOUT_ENTRIES] = {G.nbBoxesIn, G.nbBoxes, G.nbPrims, G.boxLayoutUsed, G.nbWide, (long long)G.nWideF4, (long long)G.nLeafRecsF4,
-                                               G.nbUWide, G.nbUX, G.treesOnGpu, G.animatable ? 1 : 0, G.nbLeaves, G.nbPacked, G.maxBoxLevel, G.nbLightPrims};
+                                               G.nbUWide, G.nbUX, G.treesOnGpu, G.animatable ? 1 : 0, G.nbLeaves, G.nbPacked, G.maxBoxLevel, G.nbLightPrims, G.walkTreeLevels};
     for (int k = 0; k < SCENE_LAYOUT_ENTRIES; ++k) layout[k] = v[k];
     return SCENE_LAYOUT_ENTRIES;
 }
@@ -2304,7 +2308,7 @@ int b200_scene_adopt_layout(const long long* layout, int n)
     if (recsF4 > G.capPrimRecs) { freeDev(G.dPrimRecs); G.capPrimRecs = recsF4 + 1024; CK(cudaMalloc(&G.dPrimRecs, G.capPrimRecs * sizeof(float4))); }
     const size_t uwF4 = 8 * ((size_t)G.nbUWide + (size_t)G.nbUX);
     if (uwF4 > G.capUWide) { freeDev(G.dUWide); G.capUWide = uwF4 + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
-    G.animatable = layout[10] != 0; G.nbLeaves = (int)layout[11]; G.nbPacked = (int)layout[12]; G.maxBoxLevel = (int)layout[13]; G.nbLightPrims = (int)layout[14];
+    G.animatable = layout[10] != 0; G.nbLeaves = (int)layout[11]; G.nbPacked = (int)layout[12]; G.maxBoxLevel = (int)layout[13]; G.nbLightPrims = (int)layout[14]; G.walkTreeLevels = (int)layout[15];
     if (G.animatable)
     {
         if ((size_t)G.nbLeaves > G.capLeafMaps)
@@ -2384,10 +2388,25 @@ static int animateScene(const animate::Move& move)
         rc = nbExtBoxes < 0 ? nbExtBoxes : 0;
         if (rc == 0)
         {
-            const size_t wantF4 = 8 * ((size_t)G.nbPrims + (size_t)nbExtBoxes) + 8;
-            if (wantF4 > G.capUWide) { CK(cudaStreamSynchronize(G.stream)); freeDev(G.dUWide); G.capUWide = wantF4 + 1024; CK(cudaMalloc(&G.dUWide, G.capUWide * sizeof(float4))); }
-            rc = treebuild::buildWalkTreesGpu(G.dPrims, G.nbPrims, G.dPrimLeaf, G.dLeafBoxes, nbExtBoxes, G.dUWide, G.nbUWide, G.nbUX, G.stream);
-            G.treesOnGpu = 1;
+            const bool refit = g_animateRefit && G.walkTreeLevels > 0;
+            const size_t wantF4 = 8 * ((refit ? (size_t)G.nbUWide : (size_t)G.nbPrims) + (size_t)nbExtBoxes) + 8;
+            if (wantF4 > G.capUWide)
+            {
+                // more room behind the main tree, which moves along when it is kept
+                float4* grown = nullptr;
+                CK(cudaMalloc(&grown, (wantF4 + 1024) * sizeof(float4)));
+                if (refit && grown && G.dUWide) CK(cudaMemcpyAsync(grown, G.dUWide, 8 * (size_t)G.nbUWide * sizeof(float4), cudaMemcpyDeviceToDevice, G.stream));
+                CK(cudaStreamSynchronize(G.stream));
+                freeDev(G.dUWide);
+                G.dUWide = grown; G.capUWide = wantF4 + 1024;
+            }
+            // The main tree keeps its shape — a rigid move leaves a good clustering good, and the host's SAH tree is the better one —
+            // and is re-fitted in place; the point-query tree's boxes change their number with the orientation and are rebuilt.
+            if (refit) rc = treebuild::refitMain(G.dUWide, G.nbUWide, G.walkTreeLevels, G.dPrims, G.stream);
+            if (rc == 0)
+                rc = treebuild::buildWalkTreesGpu(G.dPrims, G.nbPrims, G.dPrimLeaf, G.dLeafBoxes, nbExtBoxes, G.dUWide, G.nbUWide, G.nbUX, G.stream,
+                                                  refit ? nullptr : &G.walkTreeLevels, refit);
+            if (!refit) G.treesOnGpu = 1;
         }
     }
     cudaError_t e = cudaGetLastError();

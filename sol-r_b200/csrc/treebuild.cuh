@@ -326,6 +326,49 @@ static __global__ void k_tb_single(const float4* __restrict__ itemBoxes, float4*
     rec[7] = make_float4(__int_as_float(1), 0.f, 0.f, 0.f);
 }
 
+// One relaxation pass of a re-fit of the main tree in place: every child slot of every node takes the (padded) box of its primitive
+// or the union of its child node's slots (empty slots hold +-3e38 and drop out of the min / max).  `levels` passes settle the tree:
+// after pass p every node at most p levels above the leaves is final, and a final node is only ever re-written with the same values.
+static __global__ void k_tb_refit(float4* __restrict__ wide, const int nbNodes, const b200_Primitive* __restrict__ prims)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbNodes) return;
+    float4* rec = wide + 8 * (size_t)i;
+    const float4 rf = rec[6];
+    const int refs[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
+    float rows[6][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+    {
+        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        if (refs[c] != (int)0x80000000)
+        {
+            if (refs[c] < 0) primBox(prims[(~refs[c]) & 0x3FFFFFFF], lo, hi);
+            else
+            {
+                const volatile float4* ch = wide + 8 * (size_t)refs[c];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                {
+                    const float4 l = make_float4(ch[a].x, ch[a].y, ch[a].z, ch[a].w), h = make_float4(ch[3 + a].x, ch[3 + a].y, ch[3 + a].z, ch[3 + a].w);
+                    lo[a] = fminf(fminf(l.x, l.y), fminf(l.z, l.w));
+                    hi[a] = fmaxf(fmaxf(h.x, h.y), fmaxf(h.z, h.w));
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { rows[a][c] = lo[a]; rows[3 + a][c] = hi[a]; }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) rec[r] = make_float4(rows[r][0], rows[r][1], rows[r][2], rows[r][3]);
+}
+static int refitMain(float4* wide, const int nbMain, const int levels, const b200_Primitive* dPrims, cudaStream_t stream)
+{
+    if (nbMain <= 0) return 0;
+    for (int p = 0; p < levels; ++p) k_tb_refit<<<(nbMain + 127) / 128, 128, 0, stream>>>(wide, nbMain, dPrims);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 struct Arena
 {
     char* base; size_t at, cap;
@@ -351,8 +394,10 @@ static size_t arenaBytes(const size_t n)
 
 // LBVH over `n` items whose boxes (with their leaf refs in lo.w) are in itemBoxes and whose centre bounds are in `bounds`; wide
 // records are written from node `nodeBase` of `wide` on, inner refs are offset by it.  Returns the number of wide nodes, < 0 on error.
-static int buildOne(const float4* itemBoxes, const int n, const unsigned int* bounds, float4* wide, const int nodeBase, Arena& A, cudaStream_t stream)
+static int buildOne(const float4* itemBoxes, const int n, const unsigned int* bounds, float4* wide, const int nodeBase, Arena& A, cudaStream_t stream,
+                    int* levelsOut = nullptr)
 {
+    if (levelsOut) *levelsOut = n > 0 ? 1 : 0;
     if (n <= 0) return 0;
     if (n == 1)
     {
@@ -401,6 +446,7 @@ static int buildOne(const float4* itemBoxes, const int n, const unsigned int* bo
         ++level;
     }
     A.at = at0; // the scratch of this tree is free again (everything above ran to completion)
+    if (levelsOut) *levelsOut = level;
     return levelBase;
 }
 
@@ -443,10 +489,13 @@ static int extCount(const b200_Primitive* dPrims, const int nbPrims, const int* 
 
 // Both trees into `wide` (room for nbPrims + nbExtBoxes 128-byte records; nbExtBoxes from extCount() just before).  primLeaf /
 // leafBoxes: the reference leaf of each primitive and the reference leaves' boxes (2 float4 each).  Returns 0, or < 0 on error.
+// keepMain: the main tree in `wide` (nbMain nodes) stays as it is — re-fitted by its owner — and only the point-query tree behind it
+// is rebuilt (an animation step: the grown boxes change their number with the orientation, the main tree's shape need not).
 static int buildWalkTreesGpu(const b200_Primitive* dPrims, const int nbPrims, const int* dPrimLeaf, const float4* dLeafBoxes, const int nbExtBoxes,
-                             float4* wide, int& nbMain, int& nbExt, cudaStream_t stream)
+                             float4* wide, int& nbMain, int& nbExt, cudaStream_t stream, int* mainLevels = nullptr, const bool keepMain = false)
 {
-    nbMain = 0; nbExt = 0;
+    if (!keepMain) nbMain = 0;
+    nbExt = 0;
     if (nbPrims <= 0) return 0;
     const size_t n = (size_t)nbPrims;
     if (!ensureScratch(g_scratch, 2 * n * 16 + 256 + arenaBytes(n) + 4096, stream)) return -4;
@@ -457,10 +506,13 @@ static int buildWalkTreesGpu(const b200_Primitive* dPrims, const int nbPrims, co
     const unsigned int boundsInit[12] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     if (cudaMemcpyAsync(bounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -2;
     const int T = 256, B = (nbPrims + T - 1) / T;
-    k_tb_prim_boxes<<<B, T, 0, stream>>>(dPrims, nbPrims, itemBoxes, bounds);
-    const int m = buildOne(itemBoxes, nbPrims, bounds, wide, 0, A, stream);
-    if (m < 0) return m;
-    nbMain = m;
+    if (!keepMain)
+    {
+        k_tb_prim_boxes<<<B, T, 0, stream>>>(dPrims, nbPrims, itemBoxes, bounds);
+        const int m = buildOne(itemBoxes, nbPrims, bounds, wide, 0, A, stream, mainLevels);
+        if (m < 0) return m;
+        nbMain = m;
+    }
     if (nbExtBoxes > 0)
     {
         // the point-query tree, appended: its nodes are numbered from nbMain on

@@ -472,8 +472,9 @@ def test_gpu_built_walk_trees_give_identical_frames(cfg):
     assert not np.array_equal(out[(0, 0)][1], out[(0, 1)][1])  # the rotation changed the picture
 
 
+@pytest.mark.parametrize("refit", [1, 0])
 @pytest.mark.parametrize("cfg", ["config1", "molecule", "mesh"])
-def test_device_animation_equals_the_host_step(cfg):
+def test_device_animation_equals_the_host_step(cfg, refit):
     """b200_rotate_primitives / b200_translate_primitives / b200_scale_primitives (csrc/animate.cuh) against the host container's
     animation step — rotatePrimitives / translatePrimitives / scalePrimitives + compactBoxes(false), itself byte-identical to the
     reference's (tests/test_scene_host.py) — followed by a fresh upload: after every step the reference arrays on the device must be
@@ -511,6 +512,7 @@ def test_device_animation_equals_the_host_step(cfg):
         e.close()
     e = engine.Engine(si)
     try:
+        e.set_option(11, refit)   # the main walk tree re-fitted in place (default) or rebuilt on the GPU
         e.upload(states[0], randoms=rnd)
         animated = [frame(e)]
         for k, (kind, args) in enumerate(moves):
@@ -522,6 +524,7 @@ def test_device_animation_equals_the_host_step(cfg):
             assert np.array_equal(boxes, np.asarray(want["boxes"]).view(np.uint8).ravel()), "boxes after step %d (%s)" % (k, kind)
             animated.append(frame(e))
     finally:
+        e.set_option(11, 1)
         e.close()
     for k, (u, d) in enumerate(zip(uploaded, animated)):
         assert np.array_equal(d[1], u[1]), "ids, state %d" % k
