@@ -25,7 +25,8 @@ ABI_SYMBOLS = ["b200h_create", "b200h_destroy", "b200h_set_scene_info", "b200h_s
                "b200h_set_texture", "b200h_compact_boxes", "b200h_get_scene", "b200h_set_randoms", "b200h_set_limits", "b200h_set_capacity",
                "b200h_set_partition", "b200h_set_device", "b200h_init_buffers", "b200h_render_begin", "b200h_render_end",
                "b200h_get_bitmap", "b200h_get_primitive_ids", "b200h_get_primitive_at", "b200h_set_lazy_ids", "b200h_set_flat_build",
-               "b200h_rotate_primitives", "b200h_translate_primitives", "b200h_scale_primitives"]
+               "b200h_rotate_primitives", "b200h_translate_primitives", "b200h_scale_primitives",
+               "b200h_set_device_animation", "b200h_sync_from_device", "b200h_find_bonds"]
 
 
 def load():
