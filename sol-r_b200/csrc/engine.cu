@@ -2120,40 +2120,8 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     CK(cudaStreamSynchronize(G.stream));
 
     lap("uploads of the trees");
-    // 3. primitives
-    std::vector<float4> geo(4 * (size_t)nbPrims);
-    for (int i = 0; i < nbPrims; ++i)
-    {
-        const b200_Primitive& p = prims[i];
-        geo[4 * (size_t)i + 0] = make_float4(p.p0.x, p.p0.y, p.p0.z, p.size.x);
-        geo[4 * (size_t)i + 1] = make_float4(p.p1.x, p.p1.y, p.p1.z, p.size.y);
-        geo[4 * (size_t)i + 2] = make_float4(p.p2.x, p.p2.y, p.p2.z, p.size.z);
-        geo[4 * (size_t)i + 3] = make_float4(p.n1.x, p.n1.y, p.n1.z, 0.f);
-    }
     G.hPrims.assign(prims, prims + nbPrims);
 
-    // 3b. the unit walk's records: geometry + (packed word, patched in by uploadMeta) + the reference leaf's box and number + the
-    //     original id, so a leaf visit is one dependent access (trace.cuh)
-    if (G.nbUWide > 0)
-    {
-        std::vector<float4> recs((size_t)PRIM_REC_F4 * nbPrims + 2); // + 32 bytes: a 256-bit load never straddles the end
-        for (int i = 0; i < nbPrims; ++i)
-        {
-            const b200_Primitive& p = prims[i];
-            const int l = primLeaf[i];
-            const Aabb& lb = leaves[l].box;
-            float4* rec = &recs[(size_t)PRIM_REC_F4 * i];
-            rec[0] = geo[4 * (size_t)i + 0]; rec[1] = geo[4 * (size_t)i + 1]; rec[2] = geo[4 * (size_t)i + 2];
-            rec[3] = make_float4(p.n1.x, p.n1.y, p.n1.z, 0.f);
-            rec[4] = make_float4(lb.lo[0], lb.lo[1], lb.lo[2], intBits(l));
-            rec[5] = make_float4(lb.hi[0], lb.hi[1], lb.hi[2], intBits(p.index));
-        }
-        if (recs.size() > G.capPrimRecs) { freeDev(G.dPrimRecs); G.capPrimRecs = recs.size() + 1024; CK(cudaMalloc(&G.dPrimRecs, G.capPrimRecs * sizeof(float4))); }
-        CK(cudaMemcpyAsync(G.dPrimRecs, recs.data(), recs.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
-        CK(cudaStreamSynchronize(G.stream)); // staging vector dies here
-    }
-
-    lap("geometry + primitive records");
     // 4. device buffers (grow-only) and upload
     if ((size_t)nOut > G.capBoxes || (size_t)nbBoxes > G.capBoxes)
     {
@@ -2174,12 +2142,32 @@ void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const
     if (nbBoxes) CK(cudaMemcpyAsync(G.dRawBoxes, boxes, (size_t)nbBoxes * sizeof(b200_BoundingBox), cudaMemcpyHostToDevice, G.stream));
     if (nbPrims)
     {
-        CK(cudaMemcpyAsync(G.dGeo, geo.data(), geo.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
         CK(cudaMemcpyAsync(G.dPrims, prims, (size_t)nbPrims * sizeof(b200_Primitive), cudaMemcpyHostToDevice, G.stream));
+        // 3. hot geometry, and the unit walk's records — geometry + (packed word, patched in by uploadMeta) + the reference leaf's box
+        //    and number + the original id, so that a leaf visit is one dependent access (trace.cuh) — derived on the device from what
+        //    is there already (the kernel the animation step uses: animate.cuh)
+        if (G.nbUWide > 0)
+        {
+            if (!gpuTrees)
+            {
+                std::vector<float4> leafBoxes(2 * leaves.size());
+                for (size_t l = 0; l < leaves.size(); ++l)
+                {
+                    leafBoxes[2 * l] = make_float4(leaves[l].box.lo[0], leaves[l].box.lo[1], leaves[l].box.lo[2], 0.f);
+                    leafBoxes[2 * l + 1] = make_float4(leaves[l].box.hi[0], leaves[l].box.hi[1], leaves[l].box.hi[2], 0.f);
+                }
+                if (leafBoxes.size() > G.capLeafBoxes) { freeDev(G.dLeafBoxes); G.capLeafBoxes = leafBoxes.size() + 1024; CK(cudaMalloc(&G.dLeafBoxes, G.capLeafBoxes * sizeof(float4))); }
+                CK(cudaMemcpyAsync(G.dLeafBoxes, leafBoxes.data(), leafBoxes.size() * sizeof(float4), cudaMemcpyHostToDevice, G.stream));
+                CK(cudaStreamSynchronize(G.stream)); // staging vector dies here
+            }
+            const size_t recsF4 = (size_t)PRIM_REC_F4 * nbPrims + 2; // + 32 bytes: a 256-bit load never straddles the end
+            if (recsF4 > G.capPrimRecs) { freeDev(G.dPrimRecs); G.capPrimRecs = recsF4 + 1024; CK(cudaMalloc(&G.dPrimRecs, G.capPrimRecs * sizeof(float4))); }
+        }
+        animate::k_an_records<<<(nbPrims + 255) / 256, 256, 0, G.stream>>>(G.dPrims, nbPrims, G.dPrimLeaf, G.dLeafBoxes, G.dGeo, G.nbUWide > 0 ? G.dPrimRecs : nullptr);
     }
     CK(cudaStreamSynchronize(G.stream)); // staging vectors die at scope exit
     G.nbBoxes = nOut; G.nbPrims = nbPrims;
-    lap("boxes, geometry, primitives up");
+    lap("boxes, primitives up; geometry + records");
     uploadMeta();
     lap("packed words");
     // what the device-side animation step needs besides the arrays themselves (animate.cuh)
