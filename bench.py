@@ -378,10 +378,18 @@ def measure_workload(key, steps, warmup, ctx, sample_clocks=False, want_e2e=True
         # the reference's own protocol first — pixels and 16 bytes of ids per pixel, every frame (CudaKernel.cpp:304-313) —, then the
         # drop-in's option: the id buffer stays on the device until getPrimitiveAt asks (its only host-side reader, GPUKernel.cpp:729-739)
         h.set_lazy_ids(False)
+        streamed0 = int(lib.b200_frames_streamed())
         eager_value, eager_ms = measure_e2e()
+        streamed = int(lib.b200_frames_streamed()) - streamed0
+        lib.b200_set_option(12, 0)   # the same protocol with the frame and the ids copied after the kernels (no streamed output)
+        copied_value, copied_ms = measure_e2e()
+        lib.b200_set_option(12, 1)
         h.set_lazy_ids(True)
         lazy_value, lazy_ms = measure_e2e()
         rec["e2e"] = {"value": eager_value, "unit": "Mrays/s", "ms_per_frame": eager_ms,
+                      "output": ("streamed: the ray kernels write the caller's pinned frame and id buffers tile by tile as tiles finish (%d of %d timed + warm-up frames)"
+                                 % (streamed, steps + max(3, len(iterations)))) if streamed else "copied after the kernels",
+                      "copied_output": {"value": copied_value, "ms_per_frame": copied_ms, "note": "option 12 = 0: cudaMemcpyAsync of both buffers in render_end"},
                       "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()) * world,   # scene-info + camera + pointers block, per frame and rank
                       "d2h_bytes_per_step": W * H * 3 + W * H * 16,   # RGB8 + PrimitiveXYIdBuffer into caller-owned memory (rank 0)
                       "protocol": "the reference's render_end: bitmap and id buffer read back every frame (CudaKernel.cpp:304-313)",

@@ -89,6 +89,7 @@ void b200_set_limits(int maxBitmapWidth, int maxBitmapHeight);
  *         compactBoxes(false), MoleculeScene.cpp:75-81).  Same frames either way.
  * key 11 = what b200_rotate_primitives / b200_translate_primitives / b200_scale_primitives do with the main walk tree: 1 re-fit it in
  *         place (default: the tree keeps the shape its builder gave it), 0 rebuild it on the GPU.  Same frames either way.
+ * key 12 = streamed output into registered host buffers (1, default; see b200_frames_streamed below), 0 = always copy.
  */
 void b200_set_option(int key, int value);
 /* Multi-GPU frame split: this process renders tiles t with t % worldSize == rank (interleaved 8x4-pixel
@@ -179,6 +180,14 @@ int b200_measure_fp32_peak(float* tflops, float* smMhz);
  * buffer still work, staged). */
 int b200_register_host(void* buffer, size_t bytes);
 int b200_unregister_host(void* buffer);
+/* Streamed output (option key 12, default 1).  The reference's render_end reads the frame and the id buffer back after every frame
+ * (CudaKernel.cpp:304-313: 19 bytes per pixel behind the kernels).  When b200_d2h_bitmap has just filled REGISTERED buffers, the
+ * next frame's ray kernels write those buffers themselves — each 8 x 4 tile as its last path ends, over PCIe while the rest of the
+ * frame is still being traced — and the b200_d2h_bitmap that follows with the same pointers only waits for the stream.  Same bytes as
+ * the copy.  Frames it does not apply to (post-processing effect, single-kernel cameras, fused stages, BGR frames, sizes that are not
+ * whole tiles, other buffers) are copied as before; a frame rendered without an intervening b200_d2h_bitmap is not streamed
+ * either (nobody is reading every frame).  b200_frames_streamed counts the frames whose outputs were written this way. */
+unsigned long long b200_frames_streamed(void);
 /* Sample-split accumulation over GPUs (the second split north_star names: "sample accumulation optionally split by GPU", frame
  * "reduced with NCCL over NVLink").  Past NB_MAX_ITERATIONS the reference only adds a frame's sample to the accumulation buffer
  * (CudaRayTracer.cu:550-562) and divides by the sample count when it packs (k_default, :1066-1070), so the samples of a

@@ -214,12 +214,69 @@ SB_DEV void resolveAnaglyphEye(const int index, const int eye, const float4 colo
     }
 }
 
-// a staged path has ended: its pixel (or its eye's share of the pixel) is resolved
-SB_DEV void endPath(const int tag, const float4 color, const int4 id, const float dof)
+// ----------------------------------------------------------------------------------------------------
+// Streamed output.  The reference's host protocol reads the frame AND the id buffer back after every frame
+// (CudaKernel.cpp:304-313): 19 bytes per pixel, 39 MB per 1080p frame, 0.8 ms of PCIe time behind a 4.5 ms frame — and behind a
+// 1.2 ms frame when eight GPUs share it.  When the caller's buffers are pinned (b200_register_host) and it reads every frame, the
+// staged kernels write them directly instead: every tile (8 x 4 pixels) counts the paths it still has to end, the lane that ends
+// the last one says so, and the warp copies the tile's finished ids (four full 128-byte lines) and RGB bytes (four runs of 24) from
+// the device buffers into the mapped host buffers — posted writes over PCIe while the other tiles are still being traced.  A pixel
+// the frame does not touch (pixelNeedsWork) keeps the value both sides already hold.  b200_d2h_bitmap then only waits for the stream.
+// ----------------------------------------------------------------------------------------------------
+// paths the warp's tile will end in this frame (stage 0, all lanes; before any of them can end)
+SB_DEV void streamExpect(const int tile, const bool valid, const int eyes)
+{
+    if (cP.tileRemaining == nullptr) return;
+    const unsigned int m = __ballot_sync(FULL_MASK, valid);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(cP.tileRemaining + tile, __popc(m) * eyes);
+    __syncwarp();
+}
+// after a path's pixel has been written: the tile it completes, or -1
+SB_DEV int streamPathEnded(const int index)
+{
+    if (cP.tileRemaining == nullptr) return -1;
+    const int x = index % cSI.size.x, y = index / cSI.size.x;
+    const int tile = (y / TILE_H) * cP.tilesX + x / TILE_W;
+    __threadfence(); // the pixel's words, before the count that announces them
+    return (atomicSub(cP.tileRemaining + tile, 1) == 1) ? tile : -1;
+}
+// all lanes: the tiles that lanes of this warp completed go to the host buffers
+SB_DEV void streamTiles(const int doneTile)
+{
+    if (cP.tileRemaining == nullptr) return;
+    unsigned int m = __ballot_sync(FULL_MASK, doneTile >= 0);
+    if (m == 0) return;
+    __threadfence(); // the other lanes' (other warps', other SMs') pixels of these tiles, after the counts that announced them
+    const int lane = threadIdx.x & 31;
+    const int W = cSI.size.x;
+    while (m)
+    {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int tile = __shfl_sync(FULL_MASK, doneTile, src);
+        const int x0 = (tile % cP.tilesX) * TILE_W, y0 = (tile / cP.tilesX) * TILE_H;
+        if (cP.hostIds)
+        {
+            const size_t i = (size_t)(y0 + lane / TILE_W) * W + x0 + (lane & (TILE_W - 1));
+            cP.hostIds[i] = __ldcg(cP.ids + i);
+        }
+        if (cP.hostBitmap && lane < TILE_H * (TILE_W * B200_COLOR_DEPTH / 4))
+        {
+            // a row of the tile is TILE_W x 3 = 24 bytes at a multiple of 8 (the frame's width is a multiple of TILE_W): six words
+            const int row = lane / (TILE_W * B200_COLOR_DEPTH / 4), w = lane % (TILE_W * B200_COLOR_DEPTH / 4);
+            const size_t b = ((size_t)(y0 + row) * W + x0) * B200_COLOR_DEPTH + 4 * (size_t)w;
+            *reinterpret_cast<unsigned int*>(cP.hostBitmap + b) = __ldcg(reinterpret_cast<const unsigned int*>(cP.bitmap + b));
+        }
+    }
+}
+
+// a staged path has ended: its pixel (or its eye's share of the pixel) is resolved; returns the tile this completed (streamed output), or -1
+SB_DEV int endPath(const int tag, const float4 color, const int4 id, const float dof)
 {
     const int index = tag & ((1 << PATH_EYE_BIT) - 1);
     if (cSI.cameraType == B200_CT_ANAGLYPH) resolveAnaglyphEye(index, (tag >> PATH_EYE_BIT) & 1, color, id, dof);
     else resolvePixel(index, color, f4(0.f, 0.f, 0.f, 0.f), id, dof, *reinterpret_cast<float4*>(&cP.post[index].colorInfo));
+    return streamPathEnded(index);
 }
 
 // pixels whose ray tree ended before this deepening pass need no work (:454-458)
@@ -472,12 +529,14 @@ SB_DEV void routePath(const bool has, const PathState& s, const GlobalColors& C,
     if (cont || refl) storePath(slot, s, tag);
     pushPaths(passQueue(pass + 1), cont, slot);
     pushPaths(reflectedQueue(), refl, slot);
+    int doneTile = -1;
     if (has && !cont && !refl)
     {
         const float4 color = pathFinish(s, C, true);
         const int4 id = make_int4(s.idx, s.iteration, s.idz, s.idw);
-        endPath(tag, color, id, s.depthOfField);
+        doneTile = endPath(tag, color, id, s.depthOfField);
     }
+    streamTiles(doneTile);
 }
 
 SB_DEV void flushCounters(const unsigned int raysIn, const unsigned int pxIn)
@@ -530,6 +589,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PRIMARY) k_stage_primary
         if (!__any_sync(FULL_MASK, valid)) continue;
         if (valid) pixelsTraced++;
         const bool anaglyph = cSI.cameraType == B200_CT_ANAGLYPH;
+        streamExpect(tile, valid, anaglyph ? 2 : 1);
         const float storedDepth = cP.post[index].colorInfo.w;
 #pragma unroll 1
         for (int eye = 0; eye < (anaglyph ? 2 : 1); ++eye)
@@ -831,13 +891,15 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
         GlobalColors C;
         C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
         pathReflectedRay(s, C, has, index, 0, cnt);
+        int doneTile = -1;
         if (has)
         {
             const float4 color = pathFinish(s, C, true);
             const int4 id = make_int4(s.idx, s.iteration, s.idz, s.idw);
-            endPath(tag, color, id, s.depthOfField);
+            doneTile = endPath(tag, color, id, s.depthOfField);
         }
         __syncwarp();
+        streamTiles(doneTile);
     }
     flushCounters(cnt.rays, 0);
 }
@@ -1114,6 +1176,16 @@ struct Engine
     unsigned long long launches = 0;
     // pinned registration cache for caller-owned readback buffers
     std::vector<std::pair<void*, size_t>> hostRegistered; // b200_register_host: pinned in place for their owners, never implicitly
+    // streamed output: the registered host buffers the last b200_d2h_bitmap filled (host == device until the next frame), the same as
+    // the device sees them, whether the frame in flight writes them itself, and the tiles' path counts
+    void* mirrorBitmap = nullptr; void* mirrorIds = nullptr;
+    unsigned char* mirrorDevBitmap = nullptr; int4* mirrorDevIds = nullptr;
+    size_t mirrorPixels = 0;
+    bool mirrorArmed = false;                     // a b200_d2h_bitmap since the last frame: the reader reads every frame
+    bool validBitmap = false, validIds = false;   // the host buffer holds what the device buffer holds (once the stream is idle)
+    bool streamedBitmap = false, streamedIds = false; // the frame in flight writes them
+    int* dTileRemaining = nullptr; size_t capTileRemaining = 0;
+    unsigned long long framesStreamed = 0;
     int err = 0;
     char errMsg[256] = {0};
 };
@@ -1200,8 +1272,16 @@ void uploadMeta()
     CK(cudaStreamSynchronize(G.stream)); // meta is a stack-lifetime staging vector
 }
 
+void dropMirror()
+{
+    G.mirrorBitmap = G.mirrorIds = nullptr; G.mirrorDevBitmap = nullptr; G.mirrorDevIds = nullptr;
+    G.mirrorArmed = G.validBitmap = G.validIds = G.streamedBitmap = G.streamedIds = false;
+}
+
 void unregisterHost()
 {
+    if (G.streamedBitmap || G.streamedIds) cudaStreamSynchronize(G.stream); // a frame in flight may be writing them
+    dropMirror();
     // owners unregister their buffers before freeing them; whatever is still listed is released here (an owner that freed first
     // makes cudaHostUnregister fail, which must not surface later as a launch error)
     for (auto& r : G.hostRegistered) if (cudaHostUnregister(r.first) != cudaSuccess) cudaGetLastError();
@@ -1645,6 +1725,7 @@ int g_fuseTailPercent = 300; // k_stage_pass(p) carries its paths to the end in 
 int g_useStaged = 1;   // 0: always the single kernel; 1: one launch per pass over compacted path queues where the camera allows it; 2: every pass in one persistent launch
 int g_useBackward = 1; // point query for hits behind the origin (cylinders/cones); 0 drops that reference behaviour from the order-independent walks
 int g_packetMask = 0x0; // per-lane wide walks with deferred leaves beat packets once the code working set is small (profiles/r01_history.md) // bit0 primary, bit1 secondary, bit2 shadow of primary hits, bit3 other shadow walks as packets
+int g_streamOutput = 1; // frames whose reader reads every frame into pinned buffers are written there by the ray kernels (engine.cu "streamed output")
 int g_animateRefit = 1; // device-side animation: 1 re-fits the main walk tree in place (default), 0 rebuilds it (linear BVH)
 int g_gpuTrees = 0; // 1: the trees of the order-independent walks are built on the GPU (treebuild.cuh) instead of on host threads
 int g_boxLayout = 0; // 0 auto (ordered BVH when provably equivalent), 1 literal, 2 ordered BVH (unchecked)
@@ -1702,6 +1783,7 @@ void b200_set_option(int key, int value)
     else if (key == 5) g_useBackward = value != 0;
     else if (key == 10 && (value == 0 || value == 1)) g_gpuTrees = value;
     else if (key == 11 && (value == 0 || value == 1)) g_animateRefit = value;
+    else if (key == 12 && (value == 0 || value == 1)) g_streamOutput = value;
     else if (key == 6 && value >= 0 && value <= 2) g_useStaged = value; // 2: fused stages (k_stage_fused)
     else if (key == 8 && value >= 0) g_fuseTailPercent = value;
     else if (key == 9 && (value == 0 || value == 1)) g_tileOrder = value;
@@ -1794,6 +1876,7 @@ void b200_finalize_scene(b200_int2)
     freeDev(G.dUGroup); G.capUGroup = 0; freeDev(G.dGatherScratch); G.capGatherScratch = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
     freeDev(G.dLights); freeDev(G.dTex); freeDev(G.dRandoms); freeDev(G.dPost); freeDev(G.dIds); freeDev(G.dBitmap);
+    freeDev(G.dTileRemaining); G.capTileRemaining = 0;
     freeDev(G.dTileCounter); freeDev(G.dWork); freeDev(G.dTileOrder); G.capTileOrder = 0; G.tileOrderKey[0] = 0;
     freeDev(G.dPathWords); freeDev(G.dPathColors); freeDev(G.dPathContrib); freeDev(G.dPathQueues); freeDev(G.dQueueCounters);
     G.pathStride = 0; G.pathIterations = 0;
@@ -2646,6 +2729,30 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
 
     const bool fused = staged && g_useStaged == 2 && P.scene.nbUWide > 0 && eyes == 1 && P.packetMask == 0 && !UW_GROUP;
     P.fusedQueues = fused ? 1 : 0;
+    // Streamed output: the reader took the previous frame into pinned buffers (b200_d2h_bitmap armed them: host == device right now)
+    // and this frame is the staged kernels' alone (no effect pass, no other GPU's pixels) in whole tiles of RGB
+    const bool stream = g_streamOutput && G.mirrorArmed && (G.validBitmap || G.validIds) && staged && !fused && pp.type == B200_PPE_NONE && G.world == 1 && !G.dPeerBitmap &&
+                        si.size.x % TILE_W == 0 && si.size.y % TILE_H == 0 && si.frameBufferType == B200_FT_RGB &&
+                        (size_t)si.size.x * si.size.y == G.mirrorPixels;
+    const bool wasStreaming = G.streamedBitmap || G.streamedIds;
+    G.mirrorArmed = false;
+    G.streamedBitmap = stream && G.validBitmap; G.streamedIds = stream && G.validIds;
+    G.validBitmap = G.streamedBitmap; G.validIds = G.streamedIds; // the device is ahead of a host buffer this frame does not write
+    if (stream)
+    {
+        if ((size_t)nbTiles > G.capTileRemaining)
+        {
+            CK(cudaStreamSynchronize(G.stream));
+            freeDev(G.dTileRemaining);
+            CK(cudaMalloc(&G.dTileRemaining, (size_t)nbTiles * sizeof(int)));
+            G.capTileRemaining = nbTiles;
+        }
+        // every count returns to zero with its tile's last path; cleared when streaming (re)starts, in case a frame was cut short
+        if (!wasStreaming) CK(cudaMemsetAsync(G.dTileRemaining, 0, G.capTileRemaining * sizeof(int), G.stream));
+        P.tileRemaining = G.dTileRemaining;
+        P.hostBitmap = G.streamedBitmap ? G.mirrorDevBitmap : nullptr; P.hostIds = G.streamedIds ? G.mirrorDevIds : nullptr;
+        G.framesStreamed++;
+    }
     CK(cudaEventRecord(G.evStart, G.stream));
     CK(cudaMemsetAsync(G.dTileCounter, 0, sizeof(unsigned int), G.stream));
     // the fused driver's consumers recognise a written entry by its being non-zero
@@ -2703,19 +2810,55 @@ void b200_d2h_bitmap(b200_int2, b200_SceneInfo si, b200_BitmapBuffer* bitmap, b2
     if (px > G.pixelsCap) { latch(-6, "b200_d2h_bitmap", "frame larger than the limits"); return; }
     // The caller's buffers are pageable unless their owner pinned them in place (b200_register_host): the engine never pins
     // memory it does not own on its own initiative — a cached registration outlives a freed buffer whose address is reused.
-    if (bitmap) CK(cudaMemcpyAsync(bitmap, G.dBitmap, px * 3, cudaMemcpyDeviceToHost, G.stream));
-    if (ids) CK(cudaMemcpyAsync(ids, G.dIds, px * 16, cudaMemcpyDeviceToHost, G.stream));
+    // Streamed output: what the frame's own kernels wrote into these very buffers needs no copy, only the end of the stream
+    const bool haveBitmap = bitmap && G.validBitmap && bitmap == G.mirrorBitmap && px == G.mirrorPixels;
+    const bool haveIds = ids && G.validIds && ids == G.mirrorIds && px == G.mirrorPixels;
+    if (bitmap && !haveBitmap) CK(cudaMemcpyAsync(bitmap, G.dBitmap, px * 3, cudaMemcpyDeviceToHost, G.stream));
+    if (ids && !haveIds) CK(cudaMemcpyAsync(ids, G.dIds, px * 16, cudaMemcpyDeviceToHost, G.stream));
     CK(cudaStreamSynchronize(G.stream));
+    // ... and the buffers now hold what the device holds: the pinned ones may be written by the next frame itself
+    if (px != G.mirrorPixels) dropMirror();
+    G.mirrorPixels = px;
+    auto mapped = [](void* p, size_t bytes) -> void* {
+        for (auto& r : G.hostRegistered)
+            if (r.first == p && r.second >= bytes)
+            {
+                void* d = nullptr;
+                if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+                return d;
+            }
+        return nullptr;
+    };
+    if (bitmap && !haveBitmap)
+    {
+        G.mirrorDevBitmap = (unsigned char*)mapped(bitmap, px * 3);
+        G.mirrorBitmap = G.mirrorDevBitmap ? bitmap : nullptr;
+        G.validBitmap = G.mirrorBitmap != nullptr;
+    }
+    if (ids && !haveIds)
+    {
+        G.mirrorDevIds = (int4*)mapped(ids, px * 16);
+        G.mirrorIds = G.mirrorDevIds ? ids : nullptr;
+        G.validIds = G.mirrorIds != nullptr;
+    }
+    G.mirrorArmed = true; // somebody reads the frames as they come
 }
 
 // Host buffers the caller owns for as long as they stay registered (the frame and id buffers of a host class: GPUKernel.cpp:344-360
-// allocates them once): pinned in place so that d2h_bitmap is a straight DMA instead of a staged copy.
+// allocates them once): pinned in place so that d2h_bitmap is a straight DMA instead of a staged copy, and mapped so that the ray
+// kernels can write them ("streamed output" above).
 int b200_register_host(void* p, size_t bytes)
 {
     if (!p || !bytes) return -4;
     if (!ensureDevice()) return -1;
-    for (auto& r : G.hostRegistered) if (r.first == p) { if (r.second >= bytes) return 0; cudaHostUnregister(p); cudaGetLastError(); r = G.hostRegistered.back(); G.hostRegistered.pop_back(); break; }
-    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return -12; } // stays pageable: copies are staged
+    for (auto& r : G.hostRegistered)
+        if (r.first == p)
+        {
+            if (r.second >= bytes) return 0;
+            b200_unregister_host(p);
+            break;
+        }
+    if (cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return -12; } // stays pageable: copies are staged
     G.hostRegistered.push_back({p, bytes});
     return 0;
 }
@@ -2724,6 +2867,12 @@ int b200_unregister_host(void* p)
     for (size_t i = 0; i < G.hostRegistered.size(); ++i)
         if (G.hostRegistered[i].first == p)
         {
+            if (p == G.mirrorBitmap || p == G.mirrorIds)
+            {
+                if ((G.streamedBitmap || G.streamedIds) && ensureDevice()) cudaStreamSynchronize(G.stream); // a frame in flight may be writing it
+                if (p == G.mirrorBitmap) { G.mirrorBitmap = nullptr; G.mirrorDevBitmap = nullptr; G.validBitmap = G.streamedBitmap = false; }
+                if (p == G.mirrorIds) { G.mirrorIds = nullptr; G.mirrorDevIds = nullptr; G.validIds = G.streamedIds = false; }
+            }
             if (ensureDevice() && cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
             G.hostRegistered[i] = G.hostRegistered.back();
             G.hostRegistered.pop_back();
@@ -2731,6 +2880,8 @@ int b200_unregister_host(void* p)
         }
     return -4;
 }
+
+unsigned long long b200_frames_streamed(void) { return G.framesStreamed; }
 
 void b200_d2h_primitive_id(b200_SceneInfo si, int x, int y, b200_PrimitiveXYIdBuffer* id)
 {
@@ -2883,6 +3034,7 @@ int b200_accumulation_import_and_pack(const void* srcFloat4, int iteration)
     if (!ensureDevice()) return -1;
     const int n = accumulationPixels();
     if (!n || !srcFloat4) return -4;
+    G.validBitmap = false; // the frame is rewritten on the device
     k_accum_import_pack<<<G.numSMs * 4, 256, 0, G.stream>>>(G.dPost, (const float4*)srcFloat4, G.dPeerBitmap ? G.dPeerBitmap : G.dBitmap, n, iteration);
     G.launches++;
     return (int)cudaGetLastError();

@@ -95,6 +95,11 @@ struct RenderParams
     int maxIteration;
     int fusedQueues;           // 1: queue entries are slot + 1 in zeroed queues, published behind a fence (engine.cu k_stage_fused)
     float4* gatherScratch; // group walk: candidate lists of the bounce rays while they are walked
+    // streamed frame output (engine.cu "streamed output"): the caller's pinned host buffers as the device sees them, and the number
+    // of paths every tile still has to end in this frame; all null when the frame is copied after the render instead
+    int4* hostIds;
+    unsigned char* hostBitmap;
+    int* tileRemaining;
 };
 
 // One frame's parameters live in constant memory (uploaded on the render stream before the launch):

@@ -74,6 +74,7 @@ def load():
     lib.b200_register_host.restype = C.c_int
     lib.b200_unregister_host.argtypes = [C.c_void_p]
     lib.b200_unregister_host.restype = C.c_int
+    lib.b200_frames_streamed.restype = C.c_ulonglong
     lib.b200_accumulation_export.argtypes = [C.c_void_p]
     lib.b200_accumulation_export.restype = C.c_int
     lib.b200_accumulation_import_and_pack.argtypes = [C.c_void_p, C.c_int]
@@ -107,7 +108,7 @@ ABI_SYMBOLS = [
     "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_build_walk_trees", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats", "b200_scene_upload_stats",
     "b200_scene_layout", "b200_scene_adopt_layout", "b200_scene_device_arrays", "b200_scene_adopt_finish",
     "b200_rotate_primitives", "b200_translate_primitives", "b200_scale_primitives", "b200_d2h_scene", "b200_last_animation_ms",
-    "b200_synchronize", "b200_measure_fp32_peak", "b200_register_host", "b200_unregister_host", "b200_accumulation_clear", "b200_accumulation_export", "b200_accumulation_import_and_pack", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
+    "b200_synchronize", "b200_measure_fp32_peak", "b200_register_host", "b200_unregister_host", "b200_frames_streamed", "b200_accumulation_clear", "b200_accumulation_export", "b200_accumulation_import_and_pack", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
 ]
 
 
@@ -323,6 +324,17 @@ class Engine:
 
     def set_option(self, key, value):
         self.lib.b200_set_option(key, value)
+
+    def register_host(self, array):
+        """b200_register_host: pins a host array of the caller in place (the caller keeps it alive and unregisters it before freeing it)."""
+        return self.lib.b200_register_host(_ptr(array), array.nbytes)
+
+    def unregister_host(self, array):
+        return self.lib.b200_unregister_host(_ptr(array))
+
+    def frames_streamed(self):
+        """Frames whose bitmap / ids the ray kernels wrote into registered host buffers themselves (solr_b200.h, option key 12)."""
+        return int(self.lib.b200_frames_streamed())
 
     def set_stream(self, stream):
         self.lib.b200_set_stream(C.c_void_p(stream) if stream else None)
