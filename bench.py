@@ -338,16 +338,18 @@ def measure_workload(key, steps, warmup, ctx, sample_clocks=False, want_e2e=True
     # Every rank runs the host drop-in for its tiles (render_begin: per-frame parameter upload + launch); finished pixels land in
     # rank 0's frame over NVLink (the path's one exchange step) and rank 0 reads the merged frame back to host memory
     # (render_end = d2h_bitmap).  Wall clock around K frames, max over ranks.
+    meet = [peer]   # what orders the ranks around a frame: the peer frame's fence, then the shared host frame's
+
     def frame_e2e_all(iteration=None):
         si_live.pathTracingIteration = next_iteration() if iteration is None else iteration
         h.set_scene_info(si_live)
         if world > 1:
             with torch.cuda.stream(stream):
-                peer.fence()   # rank 0 has read the previous frame back
+                meet[0].fence()   # rank 0 has read the previous frame
         h.render_begin(0.0)
         if world > 1:
             with torch.cuda.stream(stream):
-                peer.fence()   # the frame is complete in rank 0's device bitmap
+                meet[0].fence()   # the frame is complete: in rank 0's device bitmap, or in the shared host frame
         if rank == 0:
             h.render_end()
         else:
@@ -378,18 +380,34 @@ def measure_workload(key, steps, warmup, ctx, sample_clocks=False, want_e2e=True
         # the reference's own protocol first — pixels and 16 bytes of ids per pixel, every frame (CudaKernel.cpp:304-313) —, then the
         # drop-in's option: the id buffer stays on the device until getPrimitiveAt asks (its only host-side reader, GPUKernel.cpp:729-739)
         h.set_lazy_ids(False)
+        if world > 1:
+            # first the frame merged in the root GPU's memory over NVLink and read back by the root (its own ids only) ...
+            lib.b200_set_option(12, 0)
+            copied_value, copied_ms = measure_e2e()
+            h.set_lazy_ids(True)
+            lazy_value, lazy_ms = measure_e2e()
+            h.set_lazy_ids(False)
+            lib.b200_set_option(12, 1)
+            # ... then ONE frame in shared host memory that every GPU's kernels fill with their own tiles, ids included, over their
+            # own PCIe links (partition.SharedHostFrame): no exchange between GPUs, no read-back on the root
+            meet[0] = partition.SharedHostFrame(h, lib, rank, world, stream=stream)
         streamed0 = int(lib.b200_frames_streamed())
         eager_value, eager_ms = measure_e2e()
         streamed = int(lib.b200_frames_streamed()) - streamed0
-        lib.b200_set_option(12, 0)   # the same protocol with the frame and the ids copied after the kernels (no streamed output)
-        copied_value, copied_ms = measure_e2e()
-        lib.b200_set_option(12, 1)
-        h.set_lazy_ids(True)
-        lazy_value, lazy_ms = measure_e2e()
+        if world == 1:
+            lib.b200_set_option(12, 0)   # the same protocol with the frame and the ids copied after the kernels (no streamed output)
+            copied_value, copied_ms = measure_e2e()
+            lib.b200_set_option(12, 1)
+            h.set_lazy_ids(True)
+            lazy_value, lazy_ms = measure_e2e()
         rec["e2e"] = {"value": eager_value, "unit": "Mrays/s", "ms_per_frame": eager_ms,
-                      "output": ("streamed: the ray kernels write the caller's pinned frame and id buffers tile by tile as tiles finish (%d of %d timed + warm-up frames)"
+                      "output": (("streamed: every GPU's ray kernels write the tiles they own, pixels and ids, into one frame in shared pinned host memory (%d of %d timed + warm-up frames on rank 0)"
+                                  if world > 1 else
+                                  "streamed: the ray kernels write the caller's pinned frame and id buffers tile by tile as tiles finish (%d of %d timed + warm-up frames)")
                                  % (streamed, steps + max(3, len(iterations)))) if streamed else "copied after the kernels",
-                      "copied_output": {"value": copied_value, "ms_per_frame": copied_ms, "note": "option 12 = 0: cudaMemcpyAsync of both buffers in render_end"},
+                      "copied_output": {"value": copied_value, "ms_per_frame": copied_ms,
+                                        "note": "option 12 = 0: cudaMemcpyAsync of both buffers in render_end" +
+                                                (" on rank 0, from the frame the other GPUs' kernels filled over NVLink (the id buffer: rank 0's own tiles only)" if world > 1 else "")},
                       "h2d_bytes_per_step": int(lib.b200_frame_parameter_bytes()) * world,   # scene-info + camera + pointers block, per frame and rank
                       "d2h_bytes_per_step": W * H * 3 + W * H * 16,   # RGB8 + PrimitiveXYIdBuffer into caller-owned memory (rank 0)
                       "protocol": "the reference's render_end: bitmap and id buffer read back every frame (CudaKernel.cpp:304-313)",
@@ -402,12 +420,15 @@ def measure_workload(key, steps, warmup, ctx, sample_clocks=False, want_e2e=True
         dist.barrier()
         peer.close()
         if rank == 0:
-            merged = np.array(h.bitmap(), copy=True)
+            merged, merged_ids = np.array(h.bitmap(), copy=True), np.array(h.primitive_ids(), copy=True)
             lib.b200_set_partition(0, 1)
             frame_e2e_once(0)
-            whole = np.array(h.bitmap(), copy=True)
+            whole, whole_ids = np.array(h.bitmap(), copy=True), np.array(h.primitive_ids(), copy=True)
             differing = int(np.count_nonzero(merged != whole))
             rec["frame_check"] = {"bytes_differing_from_the_one_gpu_frame": differing, "bytes": int(whole.size)}
+            if want_e2e:   # the shared host frame carries every rank's ids too
+                rec["frame_check"]["id_words_differing_from_the_one_gpu_frame"] = int(np.count_nonzero(merged_ids != whole_ids))
+                differing += rec["frame_check"]["id_words_differing_from_the_one_gpu_frame"]
             if differing:
                 raise SystemExit("bench.py: %s: the frame merged over %d GPUs differs from the one-GPU frame in %d bytes" % (key, world, differing))
         dist.barrier()

@@ -188,6 +188,15 @@ int b200_unregister_host(void* buffer);
  * whole tiles, other buffers) are copied as before; a frame rendered without an intervening b200_d2h_bitmap is not streamed
  * either (nobody is reading every frame).  b200_frames_streamed counts the frames whose outputs were written this way. */
 unsigned long long b200_frames_streamed(void);
+/* Names the host buffers of the frame outright: from now on EVERY frame this process renders goes there — tile by tile from the ray
+ * kernels where they count tiles, else in one launch after the frame's other kernels — for the tiles this GPU owns
+ * (b200_set_partition), whatever else is read or not.  This is how several processes fill ONE host frame: the buffers lie in memory
+ * they share (POSIX shared memory mapped and registered by each: SceneHost::shareFrame, partition.SharedHostFrame), every GPU
+ * writes its own tiles over its own PCIe link, and once every rank's stream is idle the frame AND the id buffer are whole in host
+ * memory — no GPU-to-GPU exchange, no read-back on the root.  It takes precedence over b200_peer_frame_open (the root GPU's
+ * frame as the destination).  Both buffers must be registered (b200_register_host) and hold si.size.x * si.size.y pixels; either
+ * may be NULL; both NULL ends it.  b200_d2h_bitmap with these pointers only waits for the stream.  0 or a negative code. */
+int b200_stream_target(b200_SceneInfo si, b200_BitmapBuffer* bitmap, b200_PrimitiveXYIdBuffer* ids);
 /* Sample-split accumulation over GPUs (the second split north_star names: "sample accumulation optionally split by GPU", frame
  * "reduced with NCCL over NVLink").  Past NB_MAX_ITERATIONS the reference only adds a frame's sample to the accumulation buffer
  * (CudaRayTracer.cu:550-562) and divides by the sample count when it packs (k_default, :1066-1070), so the samples of a

@@ -904,6 +904,30 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
     flushCounters(cnt.rays, 0);
 }
 
+// Streamed output, whole-frame form: every pixel of the tiles this GPU owns goes from the device buffers to the host buffers in one
+// launch after the frame's other kernels.  For the frames whose kernels do not count tiles (single-kernel cameras, an effect pass,
+// sizes that are not whole tiles), and to bring a newly named target up to date (b200_stream_target).
+__global__ void __launch_bounds__(256) k_stream_own_tiles(const int4* ids, const unsigned char* bitmap, int4* hostIds, unsigned char* hostBitmap,
+                                                          const int W, const int H, const int tilesX, const int nbLocalTiles, const int rank, const int world, const int bgr)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < nbLocalTiles; k += warps)
+    {
+        const int tile = k * world + rank;
+        const int x = (tile % tilesX) * TILE_W + (lane & (TILE_W - 1)), y = (tile / tilesX) * TILE_H + lane / TILE_W;
+        if (x >= W || y >= H) continue;
+        const int index = y * W + x;
+        if (hostIds) hostIds[index] = ids[index];
+        if (hostBitmap)
+        {
+            // where packPixelAt puts the pixel
+            const int i = bgr ? (((index / H) + 1) * H - (index % W) - 1) * B200_COLOR_DEPTH : index * B200_COLOR_DEPTH;
+            hostBitmap[i] = bitmap[i]; hostBitmap[i + 1] = bitmap[i + 1]; hostBitmap[i + 2] = bitmap[i + 2];
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // Post-processing effects: cudaRender's second pass (CudaRayTracer.cu:1853-1886) — k_depthOfField :1081-1119,
 // k_ambiantOcclusion :1127-1180, k_radiosity :1188-1228, k_filter :1236-1330, k_cartoon :1338-1357.  Each output pixel
@@ -1181,6 +1205,7 @@ struct Engine
     void* mirrorBitmap = nullptr; void* mirrorIds = nullptr;
     unsigned char* mirrorDevBitmap = nullptr; int4* mirrorDevIds = nullptr;
     size_t mirrorPixels = 0;
+    bool mirrorExplicit = false;                  // the buffers were named by b200_stream_target: every frame goes there, on every rank
     bool mirrorArmed = false;                     // a b200_d2h_bitmap since the last frame: the reader reads every frame
     bool validBitmap = false, validIds = false;   // the host buffer holds what the device buffer holds (once the stream is idle)
     bool streamedBitmap = false, streamedIds = false; // the frame in flight writes them
@@ -1275,7 +1300,7 @@ void uploadMeta()
 void dropMirror()
 {
     G.mirrorBitmap = G.mirrorIds = nullptr; G.mirrorDevBitmap = nullptr; G.mirrorDevIds = nullptr;
-    G.mirrorArmed = G.validBitmap = G.validIds = G.streamedBitmap = G.streamedIds = false;
+    G.mirrorArmed = G.mirrorExplicit = G.validBitmap = G.validIds = G.streamedBitmap = G.streamedIds = false;
 }
 
 void unregisterHost()
@@ -2589,6 +2614,19 @@ void b200_h2d_lightInformation(b200_int2, const b200_LightInformation* li, int n
     G.nbLights = n;
 }
 
+// every pixel of this GPU's tiles, device buffers -> the host buffers named by b200_stream_target (k_stream_own_tiles)
+static void streamOwnTiles(int W, int H, bool bgr)
+{
+    const int tilesX = (W + TILE_W - 1) / TILE_W, tilesY = (H + TILE_H - 1) / TILE_H;
+    const int nbLocal = (tilesX * tilesY - G.rank + G.world - 1) / G.world;
+    if (nbLocal <= 0 || (!G.mirrorDevBitmap && !G.mirrorDevIds)) return;
+    int grid = (nbLocal + 7) / 8;
+    if (grid > G.numSMs * 8) grid = G.numSMs * 8;
+    k_stream_own_tiles<<<grid, 256, 0, G.stream>>>(G.dIds, G.dBitmap, G.validIds ? G.mirrorDevIds : nullptr, G.validBitmap ? G.mirrorDevBitmap : nullptr,
+                                                   W, H, tilesX, nbLocal, G.rank, G.world, bgr ? 1 : 0);
+    G.launches++;
+}
+
 void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b200_PostProcessingInfo pp, b200_float3 origin,
                  b200_float3 direction, b200_float4 angles)
 {
@@ -2652,7 +2690,8 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.eye = make_float3(origin.x, origin.y, origin.z);
     P.target = make_float3(direction.x, direction.y, direction.z);
     P.angles = make_float4(angles.x, angles.y, angles.z, angles.w);
-    P.post = G.dPost; P.ids = G.dIds; P.bitmap = G.dPeerBitmap ? G.dPeerBitmap : G.dBitmap;
+    // the frame's destination: the host buffers named by b200_stream_target (through this GPU's own frame), else the root GPU's frame, else this GPU's
+    P.post = G.dPost; P.ids = G.dIds; P.bitmap = (G.dPeerBitmap && !G.mirrorExplicit) ? G.dPeerBitmap : G.dBitmap;
     P.tileCounter = G.dTileCounter; P.workCounters = G.dWork;
     P.tilesX = (si.size.x + TILE_W - 1) / TILE_W;
     P.tilesY = (si.size.y + TILE_H - 1) / TILE_H;
@@ -2731,12 +2770,17 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.fusedQueues = fused ? 1 : 0;
     // Streamed output: the reader took the previous frame into pinned buffers (b200_d2h_bitmap armed them: host == device right now)
     // and this frame is the staged kernels' alone (no effect pass, no other GPU's pixels) in whole tiles of RGB
-    const bool stream = g_streamOutput && G.mirrorArmed && (G.validBitmap || G.validIds) && staged && !fused && pp.type == B200_PPE_NONE && G.world == 1 && !G.dPeerBitmap &&
-                        si.size.x % TILE_W == 0 && si.size.y % TILE_H == 0 && si.frameBufferType == B200_FT_RGB &&
-                        (size_t)si.size.x * si.size.y == G.mirrorPixels;
+    // (or the buffers were named outright, b200_stream_target: then every frame goes there, whole after the kernels if need be)
+    const bool sizeOk = (size_t)si.size.x * si.size.y == G.mirrorPixels;
+    const bool stale = G.mirrorExplicit && ((G.mirrorBitmap && !G.validBitmap) || (G.mirrorIds && !G.validIds)); // a frame of another size came between
+    const bool tiled = staged && !fused && pp.type == B200_PPE_NONE && si.size.x % TILE_W == 0 && si.size.y % TILE_H == 0 &&
+                       si.frameBufferType == B200_FT_RGB && sizeOk && !stale;
+    const bool whole = G.mirrorExplicit && !tiled && sizeOk; // k_stream_own_tiles after the frame's other kernels
+    const bool stream = tiled && (G.mirrorExplicit || (g_streamOutput && G.mirrorArmed && (G.validBitmap || G.validIds) && G.world == 1 && !G.dPeerBitmap));
+    if (whole) { G.validBitmap = G.mirrorBitmap != nullptr; G.validIds = G.mirrorIds != nullptr; }
     const bool wasStreaming = G.streamedBitmap || G.streamedIds;
     G.mirrorArmed = false;
-    G.streamedBitmap = stream && G.validBitmap; G.streamedIds = stream && G.validIds;
+    G.streamedBitmap = (stream || whole) && G.validBitmap; G.streamedIds = (stream || whole) && G.validIds;
     G.validBitmap = G.streamedBitmap; G.validIds = G.streamedIds; // the device is ahead of a host buffer this frame does not write
     if (stream)
     {
@@ -2796,6 +2840,7 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         k_post_process<<<gp, 256, 0, G.stream>>>();
         G.launches++;
     }
+    if (whole) streamOwnTiles(si.size.x, si.size.y, si.frameBufferType == B200_FT_BGR);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) latch((int)e, "render kernel launch", cudaGetErrorString(e));
     CK(cudaEventRecord(G.evStop, G.stream));
@@ -2817,6 +2862,7 @@ void b200_d2h_bitmap(b200_int2, b200_SceneInfo si, b200_BitmapBuffer* bitmap, b2
     if (ids && !haveIds) CK(cudaMemcpyAsync(ids, G.dIds, px * 16, cudaMemcpyDeviceToHost, G.stream));
     CK(cudaStreamSynchronize(G.stream));
     // ... and the buffers now hold what the device holds: the pinned ones may be written by the next frame itself
+    if (G.mirrorExplicit) return; // the named target stays what it is, whatever else is read
     if (px != G.mirrorPixels) dropMirror();
     G.mirrorPixels = px;
     auto mapped = [](void* p, size_t bytes) -> void* {
@@ -2882,6 +2928,36 @@ int b200_unregister_host(void* p)
 }
 
 unsigned long long b200_frames_streamed(void) { return G.framesStreamed; }
+
+int b200_stream_target(b200_SceneInfo si, b200_BitmapBuffer* bitmap, b200_PrimitiveXYIdBuffer* ids)
+{
+    if (!ensureDevice()) return -1;
+    if (G.streamedBitmap || G.streamedIds) CK(cudaStreamSynchronize(G.stream));
+    dropMirror();
+    if (!bitmap && !ids) return 0;
+    if (!G.dBitmap) { latch(-4, "b200_stream_target", "reshape_scene not called"); return -4; }
+    const size_t px = (size_t)si.size.x * si.size.y;
+    if (px == 0 || px > G.pixelsCap) { latch(-6, "b200_stream_target", "frame larger than the limits"); return -6; }
+    auto mapped = [](void* p, size_t bytes) -> void* {
+        for (auto& r : G.hostRegistered)
+            if (r.first == p && r.second >= bytes)
+            {
+                void* d = nullptr;
+                if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+                return d;
+            }
+        return nullptr;
+    };
+    if (bitmap && !(G.mirrorDevBitmap = (unsigned char*)mapped(bitmap, px * 3))) { latch(-12, "b200_stream_target", "frame buffer not registered (b200_register_host)"); return -12; }
+    if (ids && !(G.mirrorDevIds = (int4*)mapped(ids, px * 16))) { G.mirrorDevBitmap = nullptr; latch(-12, "b200_stream_target", "id buffer not registered (b200_register_host)"); return -12; }
+    G.mirrorBitmap = bitmap; G.mirrorIds = ids; G.mirrorPixels = px;
+    G.validBitmap = bitmap != nullptr; G.validIds = ids != nullptr;
+    G.mirrorExplicit = true;
+    // what this GPU's tiles hold right now
+    streamOwnTiles(si.size.x, si.size.y, si.frameBufferType == B200_FT_BGR);
+    CK(cudaStreamSynchronize(G.stream));
+    return 0;
+}
 
 void b200_d2h_primitive_id(b200_SceneInfo si, int x, int y, b200_PrimitiveXYIdBuffer* id)
 {

@@ -9,6 +9,10 @@
 #include <cstring>
 #include <random>
 #include <thread>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace solr_b200
 {
@@ -113,9 +117,48 @@ void SceneHost::unpinBuffers()
     if (m_pinnedIds) { b200_unregister_host(m_pinnedIds); m_pinnedIds = nullptr; }
 }
 
+void SceneHost::dropSharedFrame()
+{
+    if (!m_shared) return;
+    b200_SceneInfo none = m_sceneInfo;
+    b200_stream_target(none, nullptr, nullptr); // waits for a frame in flight, then forgets the buffers
+    unpinBuffers();
+    munmap(m_shared, m_sharedBytes);
+    if (m_sharedOwner) shm_unlink(m_sharedName.c_str());
+    m_shared = nullptr; m_sharedBytes = 0; m_sharedOwner = false;
+    m_bitmapPtr = m_bitmap.data(); m_idsPtr = m_primitivesXYIds.data();
+}
+
+int SceneHost::shareFrame(const char* name, bool create)
+{
+    if (!m_deviceInitialised || !name) return -4;
+    dropSharedFrame();
+    const size_t px = (size_t)m_maxWidth * m_maxHeight;
+    const size_t bitmapBytes = (px * B200_COLOR_DEPTH + 4095) & ~(size_t)4095; // the id buffer starts on a page
+    const size_t bytes = bitmapBytes + px * sizeof(b200_PrimitiveXYIdBuffer);
+    const int fd = shm_open(name, create ? (O_CREAT | O_RDWR | O_TRUNC) : O_RDWR, 0600);
+    if (fd < 0) return -13;
+    if (create && ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name); return -13; }
+    void* base = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (base == MAP_FAILED) { if (create) shm_unlink(name); return -13; }
+    unpinBuffers();
+    m_shared = base; m_sharedBytes = bytes; m_sharedName = name; m_sharedOwner = create;
+    m_bitmapPtr = static_cast<unsigned char*>(base);
+    m_idsPtr = reinterpret_cast<b200_PrimitiveXYIdBuffer*>(static_cast<unsigned char*>(base) + bitmapBytes);
+    if (b200_register_host(m_bitmapPtr, px * B200_COLOR_DEPTH) == 0) m_pinnedBitmap = m_bitmapPtr;
+    if (b200_register_host(m_idsPtr, px * sizeof(b200_PrimitiveXYIdBuffer)) == 0) m_pinnedIds = m_idsPtr;
+    if (!m_pinnedBitmap || !m_pinnedIds) { dropSharedFrame(); return -12; }
+    b200_SceneInfo si = m_sceneInfo;
+    const int rc = b200_stream_target(si, m_bitmapPtr, m_idsPtr);
+    if (rc != 0) { dropSharedFrame(); return rc; }
+    return 0;
+}
+
 SceneHost::~SceneHost()
 {
     dropFlat();
+    dropSharedFrame();
     unpinBuffers();
     if (m_deviceInitialised)
     {
@@ -1164,10 +1207,12 @@ void SceneHost::setRandoms(const float* randoms, size_t n, int timestamp)
 void SceneHost::initBuffers() // CudaKernel.cpp:116-145 + GPUKernel.cpp:299-360
 {
     const size_t px = (size_t)m_maxWidth * m_maxHeight;
+    dropSharedFrame();
     unpinBuffers(); // a second initBuffers may move them
     m_bitmap.assign(px * B200_COLOR_DEPTH, 0);
     b200_PrimitiveXYIdBuffer zero = {0, 0, 0, 0};
     m_primitivesXYIds.assign(px, zero);
+    m_bitmapPtr = m_bitmap.data(); m_idsPtr = m_primitivesXYIds.data();
     if (m_hRandoms.size() != px)
     {
         // GPUKernel::render_begin fills the table with 0.000005f * (rand() % 2000 - 1000), rand() seeded from
@@ -1243,8 +1288,10 @@ void SceneHost::render_end() // CudaKernel.cpp:304-313 (the GL blit that follows
     // The reference copies the id buffer back with every frame (33 MB at 1080p beside 6 MB of pixels) although only
     // getPrimitiveAt reads it.  Here it stays on the device until somebody asks (setLazyIds(false) = the reference's protocol).
     b200_int2 occ = {1, 1};
-    b200_d2h_bitmap(occ, m_sceneInfo, m_bitmap.data(), m_lazyIds ? nullptr : m_primitivesXYIds.data());
-    m_idsOnDevice = m_lazyIds;
+    // (a shared frame receives both from every GPU's kernels: nothing to copy, nothing left on the device)
+    const bool lazy = m_lazyIds && !m_shared;
+    b200_d2h_bitmap(occ, m_sceneInfo, m_bitmapPtr, lazy ? nullptr : m_idsPtr);
+    m_idsOnDevice = lazy;
 }
 
 b200_PrimitiveXYIdBuffer* SceneHost::getPrimitiveIds()
@@ -1252,10 +1299,10 @@ b200_PrimitiveXYIdBuffer* SceneHost::getPrimitiveIds()
     if (m_idsOnDevice && m_deviceInitialised)
     {
         b200_int2 occ = {1, 1};
-        b200_d2h_bitmap(occ, m_sceneInfo, nullptr, m_primitivesXYIds.data());
+        b200_d2h_bitmap(occ, m_sceneInfo, nullptr, m_idsPtr);
         m_idsOnDevice = false;
     }
-    return m_primitivesXYIds.data();
+    return m_idsPtr;
 }
 
 unsigned int SceneHost::getPrimitiveAt(int x, int y) // GPUKernel.cpp:729-739
@@ -1265,8 +1312,8 @@ unsigned int SceneHost::getPrimitiveAt(int x, int y) // GPUKernel.cpp:729-739
     if (index < static_cast<unsigned int>(m_sceneInfo.size.x * m_sceneInfo.size.y))
     {
         if (m_idsOnDevice && m_deviceInitialised && x >= 0 && x < m_sceneInfo.size.x)
-            b200_d2h_primitive_id(m_sceneInfo, x, y, &m_primitivesXYIds[index]);
-        returnValue = m_primitivesXYIds[index].x;
+            b200_d2h_primitive_id(m_sceneInfo, x, y, &m_idsPtr[index]);
+        returnValue = m_idsPtr[index].x;
     }
     return returnValue;
 }
@@ -1529,6 +1576,7 @@ void b200h_set_lazy_ids(void* h, int lazy) { static_cast<SceneHost*>(h)->setLazy
 void b200h_set_partition(void* h, int rank, int world) { static_cast<SceneHost*>(h)->setPartition(rank, world); }
 void b200h_set_device(void* h, int device) { static_cast<SceneHost*>(h)->setDevice(device); }
 void b200h_init_buffers(void* h) { static_cast<SceneHost*>(h)->initBuffers(); }
+int b200h_share_frame(void* h, const char* name, int create) { return static_cast<SceneHost*>(h)->shareFrame(name, create != 0); }
 void b200h_render_begin(void* h, float timer) { static_cast<SceneHost*>(h)->render_begin(timer); }
 void b200h_render_end(void* h) { static_cast<SceneHost*>(h)->render_end(); }
 unsigned char* b200h_get_bitmap(void* h) { return static_cast<SceneHost*>(h)->getBitmap(); }

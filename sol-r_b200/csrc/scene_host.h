@@ -88,7 +88,13 @@ public:
     void initBuffers();
     void render_begin(float timer);
     void render_end();
-    unsigned char* getBitmap() { return m_bitmap.data(); }
+    unsigned char* getBitmap() { return m_bitmapPtr; }
+    // One host frame for several processes (one per GPU, each rendering its own tiles: setPartition): the frame and id buffers move
+    // into POSIX shared memory `name` (created by the process that passes create = true, opened by the others afterwards), pinned
+    // by each process and named to its engine as the destination of every frame (b200_stream_target): every GPU writes its own tiles
+    // there over its own PCIe link, and once every rank's stream is idle getBitmap() / getPrimitiveIds() of any of them is the whole
+    // frame.  Call after initBuffers(), with the same frame limits everywhere.  0, or a negative code.
+    int shareFrame(const char* name, bool create);
     b200_PrimitiveXYIdBuffer* getPrimitiveIds(); // fetches the buffer from the device first when render_end left it there
     void setLazyIds(bool lazy) { m_lazyIds = lazy; }
     // Animation on the device (b200_rotate_primitives / b200_translate_primitives): once the scene is on the device, rotatePrimitives
@@ -169,6 +175,10 @@ private:
 
     std::vector<unsigned char> m_bitmap;
     std::vector<b200_PrimitiveXYIdBuffer> m_primitivesXYIds;
+    unsigned char* m_bitmapPtr = nullptr;           // the vectors' storage, or the shared frame's (shareFrame)
+    b200_PrimitiveXYIdBuffer* m_idsPtr = nullptr;
+    void* m_shared = nullptr; size_t m_sharedBytes = 0; std::string m_sharedName; bool m_sharedOwner = false;
+    void dropSharedFrame();
     bool m_lazyIds = true;      // render_end copies the pixels only; ids are fetched when asked for
     bool m_deviceAnimation = false, m_hostStale = false;
     bool m_idsOnDevice = false; // the host copy is older than the last frame

@@ -75,6 +75,8 @@ def load():
     lib.b200_unregister_host.argtypes = [C.c_void_p]
     lib.b200_unregister_host.restype = C.c_int
     lib.b200_frames_streamed.restype = C.c_ulonglong
+    lib.b200_stream_target.argtypes = [SI, C.c_void_p, C.c_void_p]
+    lib.b200_stream_target.restype = C.c_int
     lib.b200_accumulation_export.argtypes = [C.c_void_p]
     lib.b200_accumulation_export.restype = C.c_int
     lib.b200_accumulation_import_and_pack.argtypes = [C.c_void_p, C.c_int]
@@ -108,7 +110,7 @@ ABI_SYMBOLS = [
     "b200_device_buffers", "b200_d2h_post", "b200_debug_relayout_boxes", "b200_frame_parameter_bytes", "b200_debug_build_unordered", "b200_debug_build_walk_trees", "b200_debug_counters", "b200_get_counters", "b200_last_render_ms", "b200_kernel_launches", "b200_scene_stats", "b200_scene_upload_stats",
     "b200_scene_layout", "b200_scene_adopt_layout", "b200_scene_device_arrays", "b200_scene_adopt_finish",
     "b200_rotate_primitives", "b200_translate_primitives", "b200_scale_primitives", "b200_d2h_scene", "b200_last_animation_ms",
-    "b200_synchronize", "b200_measure_fp32_peak", "b200_register_host", "b200_unregister_host", "b200_frames_streamed", "b200_accumulation_clear", "b200_accumulation_export", "b200_accumulation_import_and_pack", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
+    "b200_synchronize", "b200_measure_fp32_peak", "b200_register_host", "b200_unregister_host", "b200_frames_streamed", "b200_stream_target", "b200_accumulation_clear", "b200_accumulation_export", "b200_accumulation_import_and_pack", "b200_peer_frame_export", "b200_peer_frame_open", "b200_d2h_primitive_id",
 ]
 
 

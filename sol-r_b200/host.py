@@ -26,7 +26,7 @@ ABI_SYMBOLS = ["b200h_create", "b200h_destroy", "b200h_set_scene_info", "b200h_s
                "b200h_set_partition", "b200h_set_device", "b200h_init_buffers", "b200h_render_begin", "b200h_render_end",
                "b200h_get_bitmap", "b200h_get_primitive_ids", "b200h_get_primitive_at", "b200h_set_lazy_ids", "b200h_set_flat_build",
                "b200h_rotate_primitives", "b200h_translate_primitives", "b200h_scale_primitives",
-               "b200h_set_device_animation", "b200h_sync_from_device", "b200h_find_bonds"]
+               "b200h_set_device_animation", "b200h_sync_from_device", "b200h_find_bonds", "b200h_share_frame"]
 
 
 def load():
@@ -73,6 +73,8 @@ def load():
     lib.b200h_set_lazy_ids.restype = None
     lib.b200h_set_device.argtypes = [vp, C.c_int]
     lib.b200h_init_buffers.argtypes = [vp]
+    lib.b200h_share_frame.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.b200h_share_frame.restype = C.c_int
     lib.b200h_render_begin.argtypes = [vp, C.c_float]
     lib.b200h_render_end.argtypes = [vp]
     lib.b200h_get_bitmap.argtypes = [vp]
@@ -185,6 +187,13 @@ class SceneHost:
 
     def init_buffers(self):
         self.lib.b200h_init_buffers(self.h)
+
+    def share_frame(self, name, create):
+        """SceneHost::shareFrame: the frame and id buffers move into POSIX shared memory `name`; every process's GPU writes its own
+        tiles there (partition.SharedHostFrame does the naming and the ordering between processes)."""
+        rc = self.lib.b200h_share_frame(self.h, name.encode(), 1 if create else 0)
+        if rc != 0:
+            raise RuntimeError("b200h_share_frame(%s) failed: %d" % (name, rc))
 
     def render_begin(self, timer=0.0):
         self.lib.b200h_render_begin(self.h, timer)

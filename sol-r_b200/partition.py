@@ -148,6 +148,53 @@ class PeerFrame:
             self.lib.b200_peer_frame_open(None, 0)
 
 
+class SharedHostFrame:
+    """One host frame for every process of a node (SceneHost::shareFrame, include/solr_b200.h b200_stream_target): when the frame's
+    destination is HOST memory — the reference's render_end reads the frame and the id buffer back after every frame,
+    CudaKernel.cpp:304-313 — no GPU needs another GPU's pixels.  Rank `root` creates a shared-memory segment, every rank maps and
+    pins it, and from then on every GPU's ray kernels write the tiles they own straight into it over their own PCIe link, ids
+    included.  A frame is: render_begin on every rank, fence() (every rank's kernels, and with them their writes, are done), then
+    any rank reads `host_scene.bitmap()` / `primitive_ids()`: the whole frame.  fence() is PeerFrame's: a one-element all-reduce on
+    the render stream under NCCL, a host barrier behind a drained stream under gloo."""
+
+    def __init__(self, host_scene, lib, rank, world, root=0, stream=None, name=None):
+        import os
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        self.h, self.lib, self.rank, self.world, self.root, self.dist, self.torch, self.stream = host_scene, lib, rank, world, root, dist, torch, stream
+        if stream is not None:
+            lib.b200_set_stream(ctypes.c_void_p(stream.cuda_stream))
+        box = [name or "/solr_b200_frame_%d" % os.getpid()]
+        if world > 1:
+            dist.broadcast_object_list(box, src=root)
+        self.name = box[0]
+        if rank == root:
+            host_scene.share_frame(self.name, True)
+        if world > 1:
+            dist.barrier()
+        if rank != root:
+            host_scene.share_frame(self.name, False)
+        if world > 1:
+            dist.barrier()
+        self.nccl = world > 1 and dist.get_backend() == "nccl"
+        self.token = torch.zeros(1, dtype=torch.int32, device="cuda") if self.nccl else None
+
+    def fence(self):
+        if self.world == 1:
+            self.lib.b200_synchronize()
+        elif self.nccl and self.stream is not None:
+            with self.torch.cuda.stream(self.stream):
+                self.dist.all_reduce(self.token)
+        elif self.nccl:
+            self.lib.b200_synchronize()
+            self.dist.all_reduce(self.token)
+            self.torch.cuda.current_stream().synchronize()
+        else:
+            self.lib.b200_synchronize()
+            self.dist.barrier()
+
+
 class SampleSplit:
     """The second split north_star names: sample accumulation by GPU (include/solr_b200.h b200_accumulation_*).  Every process
     renders the WHOLE frame (engine partition 0 of 1).  Iterations 0..first-1 — the deepening passes and the first sample, whose
