@@ -185,8 +185,8 @@ int b200_unregister_host(void* buffer);
  * next frame's ray kernels write those buffers themselves — each 8 x 4 tile as its last path ends, over PCIe while the rest of the
  * frame is still being traced — and the b200_d2h_bitmap that follows with the same pointers only waits for the stream.  Same bytes as
  * the copy.  Frames it does not apply to (post-processing effect, single-kernel cameras, fused stages, BGR frames, sizes that are not
- * whole tiles, other buffers) are copied as before; a frame rendered without an intervening b200_d2h_bitmap is not streamed
- * either (nobody is reading every frame).  b200_frames_streamed counts the frames whose outputs were written this way. */
+ * whole tiles, other buffers, a reader that takes the pixels without the ids) are copied as before; a frame rendered without an
+ * intervening b200_d2h_bitmap is not streamed either (nobody is reading every frame).  b200_frames_streamed counts the frames whose outputs were written this way. */
 unsigned long long b200_frames_streamed(void);
 /* Names the host buffers of the frame outright: from now on EVERY frame this process renders goes there — tile by tile from the ray
  * kernels where they count tiles, else in one launch after the frame's other kernels — for the tiles this GPU owns

@@ -231,28 +231,33 @@ SB_DEV void streamExpect(const int tile, const bool valid, const int eyes)
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(cP.tileRemaining + tile, __popc(m) * eyes);
     __syncwarp();
 }
-// after a path's pixel has been written: the tile it completes, or -1
-SB_DEV int streamPathEnded(const int index)
-{
-    if (cP.tileRemaining == nullptr) return -1;
-    const int x = index % cSI.size.x, y = index / cSI.size.x;
-    const int tile = (y / TILE_H) * cP.tilesX + x / TILE_W;
-    __threadfence(); // the pixel's words, before the count that announces them
-    return (atomicSub(cP.tileRemaining + tile, 1) == 1) ? tile : -1;
-}
-// all lanes: the tiles that lanes of this warp completed go to the host buffers
-SB_DEV void streamTiles(const int doneTile)
+// All lanes, where the warp is convergent again after a batch of paths (nothing of the paths is live any more): `ended` = this lane's
+// path ended in the batch and its pixel `index` is written.  One fence for the batch, one count per tile touched (the lanes of a tile
+// elect a leader), and the tiles this completes go to the host buffers: ids as four full 128-byte lines, RGB as four runs of 24 bytes.
+SB_DEV void streamBatch(const bool ended, const int index)
 {
     if (cP.tileRemaining == nullptr) return;
-    unsigned int m = __ballot_sync(FULL_MASK, doneTile >= 0);
+    const unsigned int m = __ballot_sync(FULL_MASK, ended);
     if (m == 0) return;
-    __threadfence(); // the other lanes' (other warps', other SMs') pixels of these tiles, after the counts that announced them
+    __threadfence(); // the pixels' words, before the counts that announce them
     const int lane = threadIdx.x & 31;
     const int W = cSI.size.x;
-    while (m)
+    int doneTile = -1;
+    if (ended)
     {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
+        const int x = index % W, y = index / W;
+        const int tile = (y / TILE_H) * cP.tilesX + x / TILE_W;
+        const unsigned int peers = __match_any_sync(m, tile);
+        const int n = __popc(peers);
+        if (lane == __ffs(peers) - 1 && atomicSub(cP.tileRemaining + tile, n) == n) doneTile = tile;
+    }
+    unsigned int d = __ballot_sync(FULL_MASK, doneTile >= 0);
+    if (d == 0) return;
+    __threadfence(); // the other warps' (other SMs') pixels of these tiles, after the counts that announced them
+    while (d)
+    {
+        const int src = __ffs(d) - 1;
+        d &= d - 1;
         const int tile = __shfl_sync(FULL_MASK, doneTile, src);
         const int x0 = (tile % cP.tilesX) * TILE_W, y0 = (tile / cP.tilesX) * TILE_H;
         if (cP.hostIds)
@@ -270,13 +275,12 @@ SB_DEV void streamTiles(const int doneTile)
     }
 }
 
-// a staged path has ended: its pixel (or its eye's share of the pixel) is resolved; returns the tile this completed (streamed output), or -1
-SB_DEV int endPath(const int tag, const float4 color, const int4 id, const float dof)
+// a staged path has ended: its pixel (or its eye's share of the pixel) is resolved
+SB_DEV void endPath(const int tag, const float4 color, const int4 id, const float dof)
 {
     const int index = tag & ((1 << PATH_EYE_BIT) - 1);
     if (cSI.cameraType == B200_CT_ANAGLYPH) resolveAnaglyphEye(index, (tag >> PATH_EYE_BIT) & 1, color, id, dof);
     else resolvePixel(index, color, f4(0.f, 0.f, 0.f, 0.f), id, dof, *reinterpret_cast<float4*>(&cP.post[index].colorInfo));
-    return streamPathEnded(index);
 }
 
 // pixels whose ray tree ended before this deepening pass need no work (:454-458)
@@ -522,21 +526,22 @@ SB_DEV void pushPaths(const int q, const bool want, const size_t slot)
 
 
 // after pass `pass` of a path (all 32 lanes call; `has` = this lane carries one): queue it for the next stage, or end it
-SB_DEV void routePath(const bool has, const PathState& s, const GlobalColors& C, const int pass, const size_t slot, const int tag)
+// returns whether the lane's path ended here (its pixel is written)
+SB_DEV bool routePath(const bool has, const PathState& s, const GlobalColors& C, const int pass, const size_t slot, const int tag)
 {
     const bool cont = has && s.carryon && s.rayLength < cSI.viewDistance && pass + 1 < cP.maxIteration;
     const bool refl = has && !cont && cSI.graphicsLevel >= B200_GL_REFLECTIONS && s.reflectedRays != -1;
     if (cont || refl) storePath(slot, s, tag);
     pushPaths(passQueue(pass + 1), cont, slot);
     pushPaths(reflectedQueue(), refl, slot);
-    int doneTile = -1;
-    if (has && !cont && !refl)
+    const bool ends = has && !cont && !refl;
+    if (ends)
     {
         const float4 color = pathFinish(s, C, true);
         const int4 id = make_int4(s.idx, s.iteration, s.idz, s.idw);
-        doneTile = endPath(tag, color, id, s.depthOfField);
+        endPath(tag, color, id, s.depthOfField);
     }
-    streamTiles(doneTile);
+    return ends;
 }
 
 SB_DEV void flushCounters(const unsigned int raysIn, const unsigned int pxIn)
@@ -561,6 +566,7 @@ SB_DEV void flushCounters(const unsigned int raysIn, const unsigned int pxIn)
 #ifndef MIN_CTAS_PASS
 #define MIN_CTAS_PASS MIN_CTAS_PER_SM
 #endif
+template <bool STREAM>
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PRIMARY) k_stage_primary()
 {
     const int lane = threadIdx.x & 31;
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PRIMARY) k_stage_primary
         if (!__any_sync(FULL_MASK, valid)) continue;
         if (valid) pixelsTraced++;
         const bool anaglyph = cSI.cameraType == B200_CT_ANAGLYPH;
-        streamExpect(tile, valid, anaglyph ? 2 : 1);
+        if (STREAM) streamExpect(tile, valid, anaglyph ? 2 : 1);
         const float storedDepth = cP.post[index].colorInfo.w;
 #pragma unroll 1
         for (int eye = 0; eye < (anaglyph ? 2 : 1); ++eye)
@@ -604,14 +610,19 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PRIMARY) k_stage_primary
             GlobalColors C;
             C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
             pathPass(s, C, 0, valid, index, o, cP.packetMask, cnt);
-            routePath(valid, s, C, 0, slot, index | (eye << PATH_EYE_BIT));
+            const bool ended = routePath(valid, s, C, 0, slot, index | (eye << PATH_EYE_BIT));
             __syncwarp();
+            // STREAM: the kernel instance that counts tiles and writes the host buffers (streamed output), at the one place of a
+            // batch where nothing of its paths is live; the other instance carries none of it (hooks inside routePath cost the
+            // frame 3 % even when idle: 4.62 -> 4.76 ms on config 2)
+            if (STREAM) streamBatch(ended, index);
         }
     }
     flushCounters(cnt.rays, pixelsTraced);
 }
 
 // pass >= 1: 32 queue entries per warp at a time
+template <bool STREAM>
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const int pass)
 {
     const int lane = threadIdx.x & 31;
@@ -661,19 +672,20 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
         pathPass(s, C, pass, has, index, f3(0.f, 0.f, 0.f), 0, cnt, separateWalk ? &hit : nullptr);
         if (!fuseTail)
         {
-            routePath(has, s, C, pass, slot, tag);
+            const bool ended = routePath(has, s, C, pass, slot, tag);
             __syncwarp();
+            if (STREAM) streamBatch(ended, index);
             continue;
         }
         // Few paths left (at most one batch per resident warp: deep passes, small frames, a 1/8 share of a frame): another
         // launch per pass would cost its tail and a round trip of the path through memory for nothing, since there are no
         // other paths to fill the lanes with.  The warp keeps its paths in registers to the end of their ray trees, the way
         // k_render does; the launches of the remaining passes find empty queues.
-        bool live = has;
+        bool live = has, ended = false;
         for (int p = pass;; ++p)
         {
             const bool cont = live && s.carryon && s.rayLength < cSI.viewDistance && p + 1 < cP.maxIteration;
-            routePath(live && !cont, s, C, p, slot, tag); // ends here: reflected-ray stage or pixel
+            ended |= routePath(live && !cont, s, C, p, slot, tag); // ends here: reflected-ray stage or pixel
             live = cont;
             if (!__any_sync(FULL_MASK, live)) break;
 #if UW_GROUP
@@ -684,6 +696,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_pass(const
             pathPass(s, C, p + 1, live, index, f3(0.f, 0.f, 0.f), 0, cnt, separateWalk ? &hit : nullptr);
         }
         __syncwarp();
+        if (STREAM) streamBatch(ended, index);
     }
     flushCounters(cnt.rays, 0);
 }
@@ -867,6 +880,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_fused()
 
 
 
+template <bool STREAM>
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflected()
 {
     const int lane = threadIdx.x & 31;
@@ -891,15 +905,14 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
         GlobalColors C;
         C.c = cP.pathColors; C.k = cP.pathContributions; C.slot = slot; C.stride = cP.pathStride;
         pathReflectedRay(s, C, has, index, 0, cnt);
-        int doneTile = -1;
         if (has)
         {
             const float4 color = pathFinish(s, C, true);
             const int4 id = make_int4(s.idx, s.iteration, s.idz, s.idw);
-            doneTile = endPath(tag, color, id, s.depthOfField);
+            endPath(tag, color, id, s.depthOfField);
         }
         __syncwarp();
-        streamTiles(doneTile);
+        if (STREAM) streamBatch(has, index);
     }
     flushCounters(cnt.rays, 0);
 }
@@ -1880,9 +1893,9 @@ void b200_initialize_scene(b200_int2 occ, b200_SceneInfo si, int, int, int)
     int perSM = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render, CTA_THREADS, 0));
     G.ctasPerSM = perSM > 0 ? perSM : 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_primary, CTA_THREADS, 0)); G.ctasPerSMStage[0] = perSM > 0 ? perSM : 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_pass, CTA_THREADS, 0)); G.ctasPerSMStage[1] = perSM > 0 ? perSM : 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_reflected, CTA_THREADS, 0)); G.ctasPerSMStage[2] = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_primary<false>, CTA_THREADS, 0)); G.ctasPerSMStage[0] = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_pass<false>, CTA_THREADS, 0)); G.ctasPerSMStage[1] = perSM > 0 ? perSM : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_reflected<false>, CTA_THREADS, 0)); G.ctasPerSMStage[2] = perSM > 0 ? perSM : 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_stage_fused, CTA_THREADS, 0)); G.ctasPerSMStage[5] = perSM > 0 ? perSM : 1;
     G.initialised = true;
     G.launches = 0;
@@ -2776,7 +2789,8 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     const bool tiled = staged && !fused && pp.type == B200_PPE_NONE && si.size.x % TILE_W == 0 && si.size.y % TILE_H == 0 &&
                        si.frameBufferType == B200_FT_RGB && sizeOk && !stale;
     const bool whole = G.mirrorExplicit && !tiled && sizeOk; // k_stream_own_tiles after the frame's other kernels
-    const bool stream = tiled && (G.mirrorExplicit || (g_streamOutput && G.mirrorArmed && (G.validBitmap || G.validIds) && G.world == 1 && !G.dPeerBitmap));
+    // (a reader of the pixels alone is better served by the copy: 6 MB at 1080p cost 0.13 ms, the counting kernels 0.26 ms)
+    const bool stream = tiled && (G.mirrorExplicit || (g_streamOutput && G.mirrorArmed && G.validIds && G.world == 1 && !G.dPeerBitmap));
     if (whole) { G.validBitmap = G.mirrorBitmap != nullptr; G.validIds = G.mirrorIds != nullptr; }
     const bool wasStreaming = G.streamedBitmap || G.streamedIds;
     G.mirrorArmed = false;
@@ -2795,6 +2809,10 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         if (!wasStreaming) CK(cudaMemsetAsync(G.dTileRemaining, 0, G.capTileRemaining * sizeof(int), G.stream));
         P.tileRemaining = G.dTileRemaining;
         P.hostBitmap = G.streamedBitmap ? G.mirrorDevBitmap : nullptr; P.hostIds = G.streamedIds ? G.mirrorDevIds : nullptr;
+        // measurement only (tools/gpu/gpu_stream_e2e.py): 1 = count tiles but write nothing to the host, 2 = the counting instance of the kernels with nothing to count
+        static const int dbg = getenv("SOLR_B200_STREAM_DEBUG") ? atoi(getenv("SOLR_B200_STREAM_DEBUG")) : 0;
+        if (dbg >= 1) P.hostBitmap = nullptr, P.hostIds = nullptr;
+        if (dbg >= 2) P.tileRemaining = nullptr;
         G.framesStreamed++;
     }
     CK(cudaEventRecord(G.evStart, G.stream));
@@ -2818,17 +2836,23 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
         {
             // persistent: every CTA must be resident, or a sleeping warp could wait for one that never starts
             k_stage_fused<<<G.numSMs * G.ctasPerSMStage[5], CTA_THREADS, 0, G.stream>>>();
-            k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
+            k_stage_reflected<false><<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
             G.launches += 2;
         }
         else
         {
             int g0 = G.numSMs * G.ctasPerSMStage[0];
             if (g0 > needed) g0 = needed > 0 ? needed : 1;
-            k_stage_primary<<<g0, CTA_THREADS, 0, G.stream>>>();
+            if (stream) k_stage_primary<true><<<g0, CTA_THREADS, 0, G.stream>>>();
+            else k_stage_primary<false><<<g0, CTA_THREADS, 0, G.stream>>>();
             // queue lengths are only known on the device: persistent grids sized for the device, each warp takes 32 entries at a time
-            for (int pass = 1; pass < maxIteration; ++pass) k_stage_pass<<<G.numSMs * G.ctasPerSMStage[1], CTA_THREADS, 0, G.stream>>>(pass);
-            k_stage_reflected<<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
+            for (int pass = 1; pass < maxIteration; ++pass)
+            {
+                if (stream) k_stage_pass<true><<<G.numSMs * G.ctasPerSMStage[1], CTA_THREADS, 0, G.stream>>>(pass);
+                else k_stage_pass<false><<<G.numSMs * G.ctasPerSMStage[1], CTA_THREADS, 0, G.stream>>>(pass);
+            }
+            if (stream) k_stage_reflected<true><<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
+            else k_stage_reflected<false><<<G.numSMs * G.ctasPerSMStage[2], CTA_THREADS, 0, G.stream>>>();
             G.launches += maxIteration + 1;
         }
     }

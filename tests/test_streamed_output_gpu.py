@@ -74,11 +74,12 @@ def test_streamed_frames_equal_copied_frames(name):
     _same(copied, streamed)
 
 
-def test_streamed_bitmap_with_ids_on_demand():
-    """The drop-in's lazy-id protocol: only the bitmap is read every frame (streamed), the ids once at the end (copied)."""
+def test_pixels_alone_are_copied():
+    """The drop-in's lazy-id protocol: only the bitmap is read every frame, the ids once at the end.  Six megabytes of pixels are
+    cheaper to copy than to count tiles for (measured: profiles/r02_history.md), so nothing is streamed — same bytes either way."""
     copied, _ = _sequence("spheres_progressive", False, lazy_ids=True)
     streamed, n = _sequence("spheres_progressive", True, lazy_ids=True)
-    assert n == len(copied) - 2
+    assert n == 0
     _same(copied, streamed)
 
 
