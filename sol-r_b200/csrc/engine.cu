@@ -162,10 +162,19 @@ SB_DEV void resolvePixel(const int index, float4 color, const float4 left, const
             sinfo.z = (id.z > 0) ? fmaxf(sinfo.z, color.z) : color.z;
             stored.x += sinfo.x; stored.y += sinfo.y; stored.z += sinfo.z;
         }
+#if STREAM_HINTS >= 2
+        stOnce(reinterpret_cast<float4*>(&cP.post[index].sceneInfo), sinfo);
+#else
         *reinterpret_cast<float4*>(&cP.post[index].sceneInfo) = sinfo;
+#endif
     }
+#if STREAM_HINTS >= 2
+    stOnce(reinterpret_cast<float4*>(&cP.post[index].colorInfo), stored);
+    stOnce(reinterpret_cast<float4*>(cP.ids + index), make_float4(__int_as_float(id.x), __int_as_float(id.y), __int_as_float(id.z), __int_as_float(id.w)));
+#else
     *reinterpret_cast<float4*>(&cP.post[index].colorInfo) = stored;
     cP.ids[index] = id;
+#endif
     packPixel(stored, cP.bitmap, index);
 }
 
@@ -458,8 +467,8 @@ SB_DEV void storePath(const size_t slot, const PathState& s, const int index)
     float* w = cP.pathWords + slot;
     const size_t n = cP.pathStride;
     int k = 0;
-#define PUT(v) w[(size_t)(k++) * n] = (v)
-#define PUTI(v) w[(size_t)(k++) * n] = __int_as_float(v)
+#define PUT(v) stOnce(w + (size_t)(k++) * n, (v)) // vec.cuh: written once, read once
+#define PUTI(v) stOnce(w + (size_t)(k++) * n, __int_as_float(v))
     PUT(s.curO.x); PUT(s.curO.y); PUT(s.curO.z); PUT(s.curT.x); PUT(s.curT.y); PUT(s.curT.z);
     PUT(s.initialRefraction); PUTI(s.currentMaterialId);
     PUT(s.closestColor.x); PUT(s.closestColor.y); PUT(s.closestColor.z); PUT(s.closestColor.w);
@@ -481,8 +490,8 @@ SB_DEV void loadPath(const size_t slot, PathState& s, int& index)
     const float* w = cP.pathWords + slot;
     const size_t n = cP.pathStride;
     int k = 0;
-#define GET() __ldcg(w + (size_t)(k++) * n) // past L1: see GlobalColors
-#define GETI() __float_as_int(__ldcg(w + (size_t)(k++) * n))
+#define GET() ldOnce(w + (size_t)(k++) * n) // past L1: see GlobalColors
+#define GETI() __float_as_int(ldOnce(w + (size_t)(k++) * n))
     s.curO.x = GET(); s.curO.y = GET(); s.curO.z = GET(); s.curT.x = GET(); s.curT.y = GET(); s.curT.z = GET();
     s.initialRefraction = GET(); s.currentMaterialId = GETI();
     s.closestColor.x = GET(); s.closestColor.y = GET(); s.closestColor.z = GET(); s.closestColor.w = GET();

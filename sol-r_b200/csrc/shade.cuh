@@ -572,10 +572,10 @@ struct GlobalColors
     float* k;
     size_t slot, stride;
     // read past L1 (ld.global.cg): in the fused driver the pass that wrote them may have run on another SM during this same launch
-    SB_DEV float4 color(const int i) const { return __ldcg(c + (size_t)i * stride + slot); }
-    SB_DEV float contribution(const int i) const { return __ldcg(k + (size_t)i * stride + slot); }
-    SB_DEV void setColor(const int i, const float4 v) { c[(size_t)i * stride + slot] = v; }
-    SB_DEV void setContribution(const int i, const float v) { k[(size_t)i * stride + slot] = v; }
+    SB_DEV float4 color(const int i) const { return ldOnce(c + (size_t)i * stride + slot); }
+    SB_DEV float contribution(const int i) const { return ldOnce(k + (size_t)i * stride + slot); }
+    SB_DEV void setColor(const int i, const float4 v) { stOnce(c + (size_t)i * stride + slot, v); }
+    SB_DEV void setContribution(const int i, const float v) { stOnce(k + (size_t)i * stride + slot, v); }
 };
 
 SB_DEV int pathMaxIteration()
