@@ -926,6 +926,30 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM) k_stage_reflecte
     flushCounters(cnt.rays, 0);
 }
 
+// The unit walk's form of the walk trees (trace.cuh nodeKeysRegs): every child box of every node record as centre and half extent,
+// the half extent rounded up so that the box contains the lo/hi box it came from; refs and the child count are copied.  One thread
+// per record, after every build, re-fit or adoption of the lo/hi array (which stays what the builders and the re-fit work on).
+__global__ void __launch_bounds__(256) k_nodes_centre_half(const float4* __restrict__ lohi, float4* __restrict__ ch, const int nbRecords)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbRecords) return;
+    const float4* n = lohi + 8 * (size_t)i;
+    float4* o = ch + 8 * (size_t)i;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        const float4 lo = n[a], hi = n[3 + a];
+        float4 c, h;
+#define CH(C)                                                                                      \
+    if (lo.C <= hi.C) { c.C = 0.5f * (lo.C + hi.C); h.C = fmaxf(__fsub_ru(hi.C, c.C), __fsub_ru(c.C, lo.C)); } \
+    else { c.C = 0.f; h.C = -INFINITY; } // empty slot (lo = 3e38, hi = -3e38): never entered
+        CH(x) CH(y) CH(z) CH(w)
+#undef CH
+        o[a] = c; o[3 + a] = h;
+    }
+    o[6] = n[6]; o[7] = n[7];
+}
+
 // Streamed output, whole-frame form: every pixel of the tiles this GPU owns goes from the device buffers to the host buffers in one
 // launch after the frame's other kernels.  For the frames whose kernels do not count tiles (single-kernel cameras, an effect pass,
 // sizes that are not whole tiles), and to bring a newly named target up to date (b200_stream_target).
@@ -1181,6 +1205,7 @@ struct Engine
     float4* dBoxes = nullptr; int nbBoxes = 0; int nbBoxesIn = 0; int boxLayoutUsed = 0;
     float4* dWide = nullptr; float4* dLeafRecs = nullptr; int nbWide = 0; size_t capWide = 0, capLeafRecs = 0;
     float4* dUWide = nullptr; int nbUWide = 0; size_t capUWide = 0; int opaqueShadows = 0;
+    float4* dUWideCH = nullptr; size_t capUWideCH = 0; bool uwDirty = true; // the unit walk's centre / half-extent form of dUWide, refreshed before a frame when dUWide changed
     int nbUX = 0; // point-query tree for backward cylinder hits, appended to dUWide
     float4* dUGroup = nullptr; size_t capUGroup = 0; // the same trees child-major (group walk)
     float4* dGatherScratch = nullptr; size_t capGatherScratch = 0;
@@ -1918,7 +1943,7 @@ void b200_finalize_scene(b200_int2)
     unregisterHost();
     closePeerFrame();
     freeDev(G.dWide); freeDev(G.dLeafRecs); G.capWide = G.capLeafRecs = 0; G.nbWide = 0;
-    freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dLeafBoxes); G.capLeafBoxes = 0; treebuild::releaseScratch();
+    freeDev(G.dUWide); G.capUWide = 0; G.nbUWide = 0; G.nbUX = 0; freeDev(G.dUWideCH); G.capUWideCH = 0; G.uwDirty = true; freeDev(G.dLeafBoxes); G.capLeafBoxes = 0; treebuild::releaseScratch();
     freeDev(G.dLeafRaw); freeDev(G.dLeafNode); freeDev(G.dPackedParent); freeDev(G.dFitFlags); freeDev(G.dWideKid); G.capLeafMaps = G.capPackedParent = G.capWideKid = 0; G.animatable = false; freeDev(G.dPrimLeaf); G.capPrimLeaf = 0; freeDev(G.dPrimRecs); G.capPrimRecs = 0;
     freeDev(G.dUGroup); G.capUGroup = 0; freeDev(G.dGatherScratch); G.capGatherScratch = 0;
     freeDev(G.dBoxes); freeDev(G.dGeo); freeDev(G.dMeta); freeDev(G.dPrims); freeDev(G.dRawBoxes); freeDev(G.dMats);
@@ -2136,6 +2161,7 @@ static void buildWalkTrees(const std::vector<LeafRec>& leaves, const b200_Primit
 // own, so the pair of tests equals the child's test alone), and skip counts recomputed.
 void b200_h2d_scene(b200_int2, const b200_BoundingBox* boxes, int nbBoxes, const b200_Primitive* prims, int nbPrims, const int*, int)
 {
+    G.uwDirty = true; // the walk trees change: their centre / half-extent form is refreshed before the next frame
     if (!G.initialised) { latch(-4, "b200_h2d_scene", "initialize_scene not called"); return; }
     if (!ensureDevice()) return;
     if (nbBoxes < 0 || nbPrims < 0) { latch(-5, "b200_h2d_scene", "negative count"); return; }
@@ -2455,6 +2481,7 @@ int b200_scene_device_arrays(void** ptrs, long long* bytes, int capacity)
 
 int b200_scene_adopt_finish(void)
 {
+    G.uwDirty = true; // the walk trees change: their centre / half-extent form is refreshed before the next frame
     if (!ensureDevice()) return -1;
     // the host copy of the primitives (the packed words are re-derived from it whenever the materials change)
     G.hPrims.resize((size_t)G.nbPrims);
@@ -2474,6 +2501,7 @@ int b200_scene_adopt_finish(void)
 // ----------------------------------------------------------------------------------------------------
 static int animateScene(const animate::Move& move)
 {
+    G.uwDirty = true; // the walk trees change: their centre / half-extent form is refreshed before the next frame
     if (!G.initialised || !ensureDevice()) return -1;
     if (!G.animatable || G.nbPrims <= 0) { latch(-13, "device-side animation", "needs a scene uploaded with the ordered-tree layout (b200_h2d_scene, options 1 and 4 at their defaults)"); return -13; }
     const auto t0 = std::chrono::steady_clock::now();
@@ -2690,6 +2718,21 @@ void b200_render(b200_int2, b200_int4, b200_SceneInfo si, b200_int4 objects, b20
     P.scene.wnodes = G.dWide; P.scene.leafRecs = G.dLeafRecs; P.scene.nbWide = g_useWide ? G.nbWide : 0;
     P.scene.primLeaf = G.dPrimLeaf; P.scene.primRecs = G.dPrimRecs;
     P.scene.uwnodes = G.dUWide; P.scene.nbUWide = (g_useWide && g_useUnordered) ? G.nbUWide : 0; P.scene.opaqueShadows = G.opaqueShadows;
+    if (P.scene.nbUWide > 0 && (G.uwDirty || !G.dUWideCH))
+    {
+        const size_t recs = (size_t)(G.nbUWide + G.nbUX) * (UW_WIDTH / 4);
+        if (8 * recs + 2 > G.capUWideCH)
+        {
+            CK(cudaStreamSynchronize(G.stream));
+            freeDev(G.dUWideCH);
+            G.capUWideCH = 8 * recs + 1024;
+            CK(cudaMalloc(&G.dUWideCH, G.capUWideCH * sizeof(float4)));
+        }
+        k_nodes_centre_half<<<(unsigned int)((recs + 255) / 256), 256, 0, G.stream>>>(G.dUWide, G.dUWideCH, (int)recs);
+        G.launches++;
+        G.uwDirty = false;
+    }
+    P.scene.uwch = G.dUWideCH;
     P.scene.nbUX = g_useBackward ? G.nbUX : 0;
     P.scene.ugnodes = G.dUGroup;
 #if UW_GROUP

@@ -48,6 +48,7 @@ struct SceneDev
     int nbWide;
     // unordered 4-wide BVH (binned SAH, no ordering constraint) over the same leaf records, for the walks whose result
     // does not depend on the visiting order
+    const float4* __restrict__ uwch;    // uwnodes with every child box as centre + half extent (the unit walk's form, engine.cu k_nodes_centre_half)
     const float4* __restrict__ uwnodes; // leaves are single primitives (ref = ~primitive index), boxes are tight per-primitive boxes
     const int* __restrict__ primLeaf;   // [nbPrimitives] reference leaf (index into leafRecs) each primitive belongs to
     int nbUWide;
@@ -1724,6 +1725,34 @@ SB_DEV void topStage()
 SB_DEV void topStage() {}
 #endif
 
+#if !defined(TOP_SMEM) && !defined(UW_LOHI)
+#define UW_CENTRE_HALF 1
+#endif
+#ifdef UW_CENTRE_HALF
+// Child boxes as centre c and half extent h (>= the exact one: rounded up): entry and exit along an axis are
+// (c - o) inv -/+ h |inv| whatever the sign of the direction — three FMAs per axis and child on the FMA pipe instead of two FMAs
+// and two sign selects on the ALU pipe, which is the pipe the node round fills (24 selects of ~70 ALU instructions per round).
+// An empty child slot has h = -inf: entry +inf, exit -inf.  Conservative like the lo/hi form (two more roundings of ~1e-7 x the
+// distance, against boxes padded by 0.02 + 2e-5 |coordinate|); a NaN (0 x inf on an axis the ray does not move along) leaves
+// that axis unconstrained, as before.
+SB_DEV void nodeKeysRegs(const float4 cx, const float4 cy, const float4 cz, const float4 hx, const float4 hy, const float4 hz, const float4 rf,
+                         const NodeRay& q, const float tLimit, NodeKeys& o)
+{
+    o.refs = make_int4(__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w));
+    const float ax = fabsf(q.ix), ay = fabsf(q.iy), az = fabsf(q.iz);
+#define UN_KEY(C, K, J)                                                                                              \
+    {                                                                                                                \
+        const float tcx = __fmaf_rn(cx.C, q.ix, q.nox), tcy = __fmaf_rn(cy.C, q.iy, q.noy), tcz = __fmaf_rn(cz.C, q.iz, q.noz); \
+        const float tnx = __fmaf_rn(-hx.C, ax, tcx), tfx = __fmaf_rn(hx.C, ax, tcx);                                 \
+        const float tny = __fmaf_rn(-hy.C, ay, tcy), tfy = __fmaf_rn(hy.C, ay, tcy);                                 \
+        const float tnz = __fmaf_rn(-hz.C, az, tcz), tfz = __fmaf_rn(hz.C, az, tcz);                                 \
+        const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.f), tmax = fminf(fminf(fminf(tfx, tfy), tfz), tLimit); \
+        K = (tmin <= tmax) ? ((__float_as_int(tmin) & ~3) | J) : KEY_MISS;                                           \
+    }
+    UN_KEY(x, o.k0, 0) UN_KEY(y, o.k1, 1) UN_KEY(z, o.k2, 2) UN_KEY(w, o.k3, 3)
+#undef UN_KEY
+}
+#else
 SB_DEV void nodeKeysRegs(const float4 lx, const float4 ly, const float4 lz, const float4 hx, const float4 hy, const float4 hz, const float4 rf,
                          const NodeRay& q, const float tLimit, NodeKeys& o)
 {
@@ -1744,6 +1773,8 @@ SB_DEV void nodeKeysRegs(const float4 lx, const float4 ly, const float4 lz, cons
 #undef UN_NEAR
 #undef UN_FAR
 }
+
+#endif
 
 // dispatch on type with the geometry already in registers (primitiveTest() loads it)
 SB_DEV bool primitiveTestRegs(const float4 g0, const float4 g1, const float4 g2, const float4 g3, const int idx, const int meta, const Ray& r,
@@ -1804,7 +1835,11 @@ __device__ UW_INLINE WalkOut unorderedWalk(const int mode, const float3 rayOrigi
     // entry-t bound for nodes: never beyond the reference's own t_min < closest-so-far test; a shadow blocker lies before the lamp (t ~ 1)
     float cullT = (mode == UW_SHADOW) ? fminf(minDistance0, UW_SHADOW_TLIMIT) : fminf(minDistance0, minDistance0 * invLen);
     if (mode == UW_GATHER) cullT = minDistance0;
+#ifdef UW_CENTRE_HALF
+    const float4* __restrict__ nodes = cS.uwch;
+#else
     const float4* __restrict__ nodes = cS.uwnodes;
+#endif
     const float4* __restrict__ recs = cS.primRecs;
     const int nbMain = cS.nbUWide;
     walkStart(s_stack, nbMain, cS.nbUX > 0, spLimit, sp, cur);
