@@ -10,11 +10,18 @@
 // are LOOKED AT, never which are taken.  The loader keeps its loop over the atoms and replaces the inner loop by a walk over
 // pairs[first[i] .. first[i + 1]) (INTEGRATION.md has the three lines).
 //
-// OBJReader keeps its vertices in std::map<int, vec3f> keyed 1..n (OBJReader.cpp:415-418): a vector indexed by the key is the same
-// container for that use and needs no code of its own.
+// OBJReader::loadModelFromFile reads the file twice (solr/io/OBJReader.cpp:440-563 the "v" / "vn" / "vt" lines, :602 onwards the
+// faces).  Its first pass keeps the vertices, normals and texture coordinates in three std::map<int, ...> keyed 1..n
+// (OBJReader.cpp:415-418) and builds every number character by character in a std::string: for the 1 M-triangle mesh of config 3
+// (500 k vertices + normals) that is 1.5 M map nodes and 30 M string appends before a single face is read.  b200h_obj_vertex_pass is
+// that first pass over the whole text at once into flat arrays indexed by key - 1 — the same tokenisation (a separator is a blank
+// that follows a non-blank; later blanks join the next token, which atof then skips), the same atof, the same sign flips
+// (z of vertices and normals negated), the same folding of negative texture coordinates, the same bounding box — so the second
+// pass reads `vertices[3 * (key - 1)]` where it read `vertices[key]`.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -111,5 +118,74 @@ long b200h_find_bonds(const float* xyz, const int* processed, const unsigned cha
         }
     }
     return total;
+}
+// First pass of OBJReader::loadModelFromFile over the text of a .obj file (OBJReader.cpp:440-563).  vertices / normals: 3 floats
+// per entry, texCoords: 2; any of them may be NULL (counting call).  counts[3] = entries found (vertices, normals, texture
+// coordinates); aabb[6] = min xyz, max xyz of the vertices, starting from the reference's +/-100000.  Entries beyond a capacity are
+// counted but not stored.  Returns 0.
+int b200h_obj_vertex_pass(const char* text, size_t len, float* vertices, int vertexCapacity, float* normals, int normalCapacity,
+                          float* texCoords, int texCoordCapacity, int* counts, float* aabb)
+{
+    int nv = 0, nn = 0, nt = 0;
+    float box[6] = {100000.f, 100000.f, 100000.f, -100000.f, -100000.f, -100000.f};
+    std::vector<char> line;  // the line without its carriage returns (:443)
+    char token[512];
+    size_t at = 0;
+    while (at < len)
+    {
+        size_t end = at;
+        while (end < len && text[end] != '\n') ++end;
+        line.clear();
+        for (size_t k = at; k < end; ++k)
+            if (text[k] != '\r') line.push_back(text[k]);
+        at = end + 1;
+        const size_t n = line.size();
+        if (n <= 1 || line[0] != 'v') continue;
+        float v[3] = {0.f, 0.f, 0.f};
+        // :457-512 — a blank after a non-blank closes an item; item 0 is the keyword itself; items 1..3 are x, y, z
+        size_t i = 1, tl = 0;
+        int item = 0;
+        char previous = line[0];
+        auto assign = [&](int it) {
+            if (it >= 1 && it <= 3) { token[tl] = 0; v[it - 1] = static_cast<float>(atof(token)); }
+        };
+        while (i < n && item < 4)
+        {
+            if (line[i] == ' ' && previous != ' ')
+            {
+                assign(item);
+                ++item;
+                tl = 0;
+            }
+            else if (tl + 1 < sizeof(token)) token[tl++] = line[i];
+            previous = line[i];
+            ++i;
+        }
+        if (tl != 0) assign(item);
+        if (line[1] == 'n')
+        {
+            if (normals && nn < normalCapacity) { normals[3 * (size_t)nn] = v[0]; normals[3 * (size_t)nn + 1] = v[1]; normals[3 * (size_t)nn + 2] = -v[2]; }
+            ++nn;
+        }
+        else if (line[1] == 't')
+        {
+            float x = v[0], y = v[1];
+            if (x < 0.f) { const int a = static_cast<int>(std::fabs(x)); x = std::fabs(x) - a; }
+            if (y < 0.f) { const int a = static_cast<int>(std::fabs(y)); y = std::fabs(y) - a; }
+            if (texCoords && nt < texCoordCapacity) { texCoords[2 * (size_t)nt] = x; texCoords[2 * (size_t)nt + 1] = y; }
+            ++nt;
+        }
+        else if (line[1] == ' ')
+        {
+            const float z = -v[2];
+            if (vertices && nv < vertexCapacity) { vertices[3 * (size_t)nv] = v[0]; vertices[3 * (size_t)nv + 1] = v[1]; vertices[3 * (size_t)nv + 2] = z; }
+            ++nv;
+            box[0] = (v[0] < box[0]) ? v[0] : box[0]; box[1] = (v[1] < box[1]) ? v[1] : box[1]; box[2] = (z < box[2]) ? z : box[2];
+            box[3] = (v[0] > box[3]) ? v[0] : box[3]; box[4] = (v[1] > box[4]) ? v[1] : box[4]; box[5] = (z > box[5]) ? z : box[5];
+        }
+    }
+    if (counts) { counts[0] = nv; counts[1] = nn; counts[2] = nt; }
+    if (aabb) memcpy(aabb, box, sizeof(box));
+    return 0;
 }
 } // extern "C"

@@ -26,7 +26,7 @@ ABI_SYMBOLS = ["b200h_create", "b200h_destroy", "b200h_set_scene_info", "b200h_s
                "b200h_set_partition", "b200h_set_device", "b200h_init_buffers", "b200h_render_begin", "b200h_render_end",
                "b200h_get_bitmap", "b200h_get_primitive_ids", "b200h_get_primitive_at", "b200h_set_lazy_ids", "b200h_set_flat_build",
                "b200h_rotate_primitives", "b200h_translate_primitives", "b200h_scale_primitives",
-               "b200h_set_device_animation", "b200h_sync_from_device", "b200h_find_bonds", "b200h_share_frame"]
+               "b200h_set_device_animation", "b200h_sync_from_device", "b200h_find_bonds", "b200h_share_frame", "b200h_obj_vertex_pass"]
 
 
 def load():
@@ -89,6 +89,22 @@ def load():
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def obj_vertex_pass(text):
+    """b200h_obj_vertex_pass (csrc/loaders.cpp): the first pass of OBJReader::loadModelFromFile (OBJReader.cpp:440-563) over the text
+    of a .obj file.  Returns (vertices float32[n, 3], normals float32[m, 3], tex_coords float32[k, 2], aabb float32[6]); entry i of
+    an array is the reference's map entry i + 1."""
+    lib = load()
+    lib.b200h_obj_vertex_pass.restype = C.c_int
+    lib.b200h_obj_vertex_pass.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    data = text if isinstance(text, bytes) else text.encode("latin-1")
+    counts = np.zeros(3, np.int32)
+    aabb = np.zeros(6, np.float32)
+    lib.b200h_obj_vertex_pass(data, len(data), None, 0, None, 0, None, 0, _ptr(counts), _ptr(aabb))
+    v = np.zeros((int(counts[0]), 3), np.float32); n = np.zeros((int(counts[1]), 3), np.float32); t = np.zeros((int(counts[2]), 2), np.float32)
+    lib.b200h_obj_vertex_pass(data, len(data), _ptr(v), v.shape[0], _ptr(n), n.shape[0], _ptr(t), t.shape[0], _ptr(counts), _ptr(aabb))
+    return v, n, t, aabb
 
 
 def find_bonds(xyz, processed, is_backbone, stick_distance=1.7, backbone_geometry=False):
