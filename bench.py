@@ -437,6 +437,62 @@ def measure_workload(key, steps, warmup, ctx, sample_clocks=False, want_e2e=True
     return rec
 
 
+
+def measure_sample_split(key, ctx, groups=3):
+    """north_star's second split (configs 4 / 5: "sample accumulation optionally split by GPU", reduced with NCCL over NVLink): every
+    rank renders the WHOLE frame for its share of the accumulation iterations (partition.SampleSplit), the partial colour sums are
+    sum-reduced onto the root and packed.  Past NB_MAX_ITERATIONS a frame only adds a sample (CudaRayTracer.cu:550-562), so the
+    samples of a progressive sequence are exchangeable.  Timed: `groups` rounds of one accumulation iteration per rank + the reduce
+    and the pack, wall clock between device synchronisations, max over ranks.  Complete on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from solr_b200 import engine, host, partition, wire, workloads
+    wl = workloads.WORKLOADS[key]
+    W, H = wl["size"]
+    world, rank, local_rank, stream, lib = ctx.world, ctx.rank, ctx.local_rank, ctx.stream, ctx.lib
+    sc = wl["scene"]()
+    si = workloads.scene_info(key)
+    si.maxPathTracingIterations = 1 << 30
+    h = host.SceneHost(si, limits=wl["limits"], capacity=wl["capacity"])
+    sc.replay(h)
+    a = h.arrays()
+    h.close()
+    e = engine.Engine(si, device=local_rank, limits=wl["limits"])      # whole frame on every rank
+    e.upload(a, randoms=np.zeros(max(wire.REF_MAX_BITMAP_SIZE, W * H), np.float32))
+    first = 11   # NB_MAX_ITERATIONS + 1: the first iteration that only adds a sample
+    for it in range(0, first):                                         # the deepening passes and the first sample: everybody
+        si.pathTracingIteration = it
+        e.render(si, sc.eye, sc.target, sc.angles)
+    e.synchronize()
+    split = partition.SampleSplit(lib, rank, world, W, H)
+    split.begin()
+    e.counters(reset=True)
+    last = first + groups * world - 1
+    mine = split.iterations(first, last)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for it in mine:
+        si.pathTracingIteration = it
+        e.render(si, sc.eye, sc.target, sc.angles)
+    e.synchronize()
+    t1 = time.perf_counter()
+    split.finish(last)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    rays, _ = e.counters(reset=True)
+    t = torch.tensor([t2 - t0, t1 - t0], dtype=torch.float64, device="cuda")
+    r = torch.tensor([float(rays)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    e.close()
+    dt, render_s = float(t[0].item()), float(t[1].item())
+    samples = groups * world
+    return {"split": "samples: every GPU renders the whole frame for iterations = rank mod N, colour sums reduced onto rank 0 over NCCL and packed",
+            "samples": samples, "ms_per_sample": dt / samples * 1e3, "value": float(r.item()) / dt / 1e6, "unit": "Mrays/s",
+            "ms_render_per_rank": render_s * 1e3, "ms_reduce_and_pack": (dt - render_s) * 1e3,
+            "reduce_bytes_per_rank": W * H * 16, "iterations": [first, last]}
+
+
 def measure_scene_paths(ctx):
     """The scene side of the path, on config 2, outside every timed region above:
       N = 1  one animation step of the drop-in host path — rotatePrimitives + compactBoxes(false) (MoleculeScene.cpp:75-81), then a
@@ -650,6 +706,12 @@ def main():
             rec = measure_workload(k, s, w, ctx, sample_clocks=False)
             rec.pop("_frame")
             subs[k] = rec
+        if world > 1 and "config4" in subs:
+            # the other way to share config 4 out: whole frames of different samples per GPU instead of tiles of one frame
+            ss = measure_sample_split("config4", ctx)
+            per_frame = subs["config4"]["ms_per_iteration"]
+            ss["tile_split_ms_per_sample_same_iterations"] = per_frame.get("11")
+            subs["config4"]["sample_split"] = ss
 
     scene_paths = None
     if not args.no_sub:
