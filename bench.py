@@ -700,18 +700,18 @@ def main():
 
     subs = {}
     if not args.no_sub:
-        sub_keys = [k for k in (["config4"] if world > 1 else ["config4", "config3", "config5"]) if k != key]
+        sub_keys = [k for k in (["config4", "config5"] if world > 1 else ["config4", "config3", "config5"]) if k != key]
         for k in sub_keys:
             w, s = SUB_FRAMES[k]
             rec = measure_workload(k, s, w, ctx, sample_clocks=False)
             rec.pop("_frame")
             subs[k] = rec
-        if world > 1 and "config4" in subs:
-            # the other way to share config 4 out: whole frames of different samples per GPU instead of tiles of one frame
-            ss = measure_sample_split("config4", ctx)
-            per_frame = subs["config4"]["ms_per_iteration"]
-            ss["tile_split_ms_per_sample_same_iterations"] = per_frame.get("11")
-            subs["config4"]["sample_split"] = ss
+        for k in ("config4", "config5"):
+            if world > 1 and k in subs:
+                # the other way to share configs 4 / 5 out: whole frames of different samples per GPU instead of tiles of one frame
+                ss = measure_sample_split(k, ctx)
+                ss["tile_split_ms_per_sample_same_iterations"] = subs[k]["ms_per_iteration"].get("11")
+                subs[k]["sample_split"] = ss
 
     scene_paths = None
     if not args.no_sub:
