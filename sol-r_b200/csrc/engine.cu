@@ -241,14 +241,12 @@ SB_DEV void streamExpect(const int tile, const bool valid, const int eyes)
     __syncwarp();
 }
 // All lanes, where the warp is convergent again after a batch of paths (nothing of the paths is live any more): `ended` = this lane's
-// path ended in the batch and its pixel `index` is written.  One fence for the batch, one count per tile touched (the lanes of a tile
-// elect a leader), and the tiles this completes go to the host buffers: ids as four full 128-byte lines, RGB as four runs of 24 bytes.
+// path ended in the batch and its pixel `index` is written.  Every such lane counts its tile down, and the tiles this completes go
+// to the host buffers: ids as four full 128-byte lines, RGB as four runs of 24 bytes.
 SB_DEV void streamBatch(const bool ended, const int index)
 {
     if (cP.tileRemaining == nullptr) return;
-    const unsigned int m = __ballot_sync(FULL_MASK, ended);
-    if (m == 0) return;
-    __threadfence(); // the pixels' words, before the counts that announce them
+    if (!__any_sync(FULL_MASK, ended)) return;
     const int lane = threadIdx.x & 31;
     const int W = cSI.size.x;
     int doneTile = -1;
@@ -256,13 +254,18 @@ SB_DEV void streamBatch(const bool ended, const int index)
     {
         const int x = index % W, y = index / W;
         const int tile = (y / TILE_H) * cP.tilesX + x / TILE_W;
-        const unsigned int peers = __match_any_sync(m, tile);
-        const int n = __popc(peers);
-        if (lane == __ffs(peers) - 1 && atomicSub(cP.tileRemaining + tile, n) == n) doneTile = tile;
+        // The count is decremented with RELEASE semantics by the lane that wrote the pixel (its words are performed before the count
+        // moves), not behind a __threadfence(): that is MEMBAR + CCTL.IVALL — it throws the SM's whole L1 away, 87 k times per frame
+        // in pass 0 alone, and the walks of every warp on the SM pay for it (ncu, profiles/r02_ncu_streamed_frame.json: +0.17 ms in
+        // k_stage_primary, long-scoreboard 2.8 -> 3.6 per issue).  atom.release is MEMBAR + ATOMG.
+        int old;
+        asm volatile("atom.release.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(cP.tileRemaining + tile), "r"(-1) : "memory");
+        if (old == 1) doneTile = tile;
     }
     unsigned int d = __ballot_sync(FULL_MASK, doneTile >= 0);
     if (d == 0) return;
-    __threadfence(); // the other warps' (other SMs') pixels of these tiles, after the counts that announced them
+    // the finished tiles are read past L1 (ld.cg): the other warps' (other SMs') pixels were performed before their counts, and the count
+    // that reached zero was seen after them — the reader's side of a fenced reduction needs no L1 invalidation of its own
     while (d)
     {
         const int src = __ffs(d) - 1;
