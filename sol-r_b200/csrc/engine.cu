@@ -527,8 +527,10 @@ SB_DEV void pushPaths(const int q, const bool want, const size_t slot)
     base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
     if (cP.fusedQueues)
     {
-        __threadfence();
-        if (want) __stcg(cP.pathQueues + (size_t)q * cP.pathStride + base + __popc(m & ((1u << lane) - 1u)), (int)slot + 1);
+        // published with RELEASE semantics by the lane that parked the path (MEMBAR + store), not behind a __threadfence(), whose
+        // CCTL.IVALL throws the SM's L1 away with every push (see streamBatch)
+        if (want)
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(cP.pathQueues + (size_t)q * cP.pathStride + base + __popc(m & ((1u << lane) - 1u))), "r"((int)slot + 1) : "memory");
         // the consumers' semaphore (a consumer that is handed an entry before it is written waits for it to turn non-zero)
         if (lane == __ffs(m) - 1) atomicAdd(cP.queueCounters + FUSED_CTR + (B200_NB_MAX_ITERATIONS + 2) + q, (unsigned int)__popc(m));
         return;
@@ -856,7 +858,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_fused()
                 const volatile int* entry = cP.pathQueues + (size_t)passQueue(pass) * cP.pathStride + base + lane;
                 int e;
                 while ((e = *entry) == 0) __nanosleep(20);
-                __threadfence();
+                // the parked path is read through addresses that depend on e, past L1 (ld.cg / no-allocate): no fence, no invalidation
                 slot = (size_t)(e - 1);
                 const float* w = cP.pathWords + slot;
                 const size_t s = cP.pathStride;
@@ -885,7 +887,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PASS) k_stage_fused()
         }
         __syncwarp();
         // this warp's pushes are reserved (pushPaths): it is no longer at work on the pass
-        if (lane == 0) { __threadfence(); atomicSub(atWork + pass, 1u); }
+        if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(atWork + pass), "r"(0xffffffffu) : "memory"); // behind the __syncwarp above
     }
     flushCounters(cnt.rays, pixelsTraced);
 }
